@@ -1,0 +1,91 @@
+"""ctypes binding of libhallucidet_b200.so (the C ABI declared in include/hallucidet_b200.h).
+
+There is no CPU fallback: importing works on a CPU-only host (symbol checks), but every compute
+call raises ``RuntimeError`` unless the CUDA library is present and a B200 is the current device.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhallucidet_b200.so")
+
+c_int, c_float, c_double, c_void_p, c_int64 = ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_void_p, ctypes.c_int64
+
+
+class HdAct(ctypes.Structure):
+    _fields_ = [("ptr", c_void_p), ("n", ctypes.c_int32), ("h", ctypes.c_int32), ("w", ctypes.c_int32), ("c", ctypes.c_int32)]
+
+
+class HdConvArgs(ctypes.Structure):
+    _fields_ = [
+        ("x0", HdAct), ("x1", HdAct), ("y0", HdAct), ("y1", HdAct),
+        ("w", c_void_p),
+        ("kh", ctypes.c_int32), ("kw", ctypes.c_int32), ("stride", ctypes.c_int32),
+        ("bias", c_void_p), ("add", c_void_p), ("mask", c_void_p),
+        ("relu", ctypes.c_int32), ("sigmoid", ctypes.c_int32),
+        ("stats", c_void_p), ("stats_replicas", ctypes.c_int32),
+        ("out_f32_nchw", c_void_p), ("out_f32_channels", ctypes.c_int32),
+        ("store_bf16", ctypes.c_int32), ("phase_mask", ctypes.c_int32),
+        ("dw", c_void_p), ("split_k", ctypes.c_int32),
+    ]
+
+
+P = ctypes.POINTER
+# name -> argtypes (restype is int unless listed in _RESTYPES)
+PROTOTYPES = {
+    "hd_version": [],
+    "hd_last_error": [],
+    "hd_device_ok": [],
+    "hd_conv_fwd": [P(HdConvArgs), c_void_p],
+    "hd_conv_dgrad": [P(HdConvArgs), c_void_p],
+    "hd_conv_wgrad": [P(HdConvArgs), c_void_p],
+    "hd_pack_conv_weight": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p],
+    "hd_unpack_wgrad": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
+    "hd_stem_im2col": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "hd_stem_col2im": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "hd_bn_finalize": [c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
+                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    "hd_bn_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p],
+    "hd_bn_bwd_reduce": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p],
+    "hd_bn_bwd_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p,
+                        c_void_p, c_void_p, c_int64, c_int, c_void_p],
+    "hd_maxpool_fwd": [P(HdAct), P(HdAct), c_void_p],
+    "hd_maxpool_bwd": [P(HdAct), P(HdAct), c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "hd_upsample2x_fwd": [P(HdAct), P(HdAct), c_void_p],
+    "hd_upsample2x_bwd": [P(HdAct), P(HdAct), c_void_p],
+    "hd_add_nearest_fwd": [P(HdAct), P(HdAct), c_void_p],
+    "hd_add_nearest_bwd": [P(HdAct), P(HdAct), c_int, c_void_p],
+    "hd_nchw_f32_to_nhwc_bf16": [c_void_p, P(HdAct), c_int, c_void_p],
+    "hd_nhwc_bf16_to_nchw_f32": [P(HdAct), c_void_p, c_int, c_void_p],
+    "hd_sigmoid_bwd_pack": [c_void_p, c_void_p, P(HdAct), c_int, c_void_p, c_void_p],
+    "hd_resize_nearest_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "hd_resize_nearest_bwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
+    "hd_regulariser": [c_int, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_int, c_int, c_void_p, c_void_p,
+                       c_float, c_int, c_void_p],
+}
+_RESTYPES = {"hd_last_error": ctypes.c_char_p}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (raises if it has not been built; never falls back to another implementation)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m hallucidet_b200.build` "
+                "(hallucidet_b200 has no CPU / PyTorch fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in PROTOTYPES.items():
+            fn = getattr(lib, name)           # AttributeError = ABI mismatch, fail loudly
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, c_int)
+        _lib = lib
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().hd_last_error()
+        raise RuntimeError(f"{what} failed with hd_status {status}: {msg.decode() if msg else ''}")

@@ -1,0 +1,501 @@
+// conv_gemm.cu -- convolution forward / input-gradient as an implicit GEMM on the sm_100a tensor cores.
+//
+//   out[pixel, co] = sum_{tap, ci}  A_tap[pixel, ci] * W[co][tap*Cin + ci]
+//
+// * M (128 rows) = a TW x TH patch of output pixels of one image; the A tile of a filter tap is the same
+//   patch of the NHWC input shifted by (dh, dw): one 5-D TMA box load, out-of-bounds rows/cols zero-filled
+//   by the TMA unit (that IS the zero padding).  Stride-2 convolutions address the input through a
+//   (2C, W/2, 2, H/2, N) "phase" view of the same memory, so every tap is still a dense box.
+// * B = pre-packed bf16 weights, K-major, one 2-D TMA box per k-block.
+// * tcgen05.mma (cta_group::1, M=128, N=BN<=128, K=16) accumulates fp32 in TMEM; one elected thread issues.
+// * warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-5 = epilogue
+//   (tcgen05.ld -> bias / add / ReLU / mask -> bf16 -> swizzled smem -> TMA store; optional BN statistics,
+//   optional fp32 NCHW (+sigmoid) store for module-edge tensors).
+// * input-gradient of a stride-2 convolution = 4 output phases (grid.z), each a dense stride-1 problem.
+//
+// Reference operators replaced: see include/hallucidet_b200.h (hd_conv_fwd / hd_conv_dgrad).
+#include "hd_common.cuh"
+
+#include <cstring>
+
+namespace hd {
+
+constexpr int kMaxTaps = 9;
+constexpr int kThreads = 192;
+
+struct ConvGemmParams {
+    CUtensorMap tmA[2];
+    CUtensorMap tmB;
+    CUtensorMap tmOut[2];
+    int TW, TH, tiles_w, tiles_h;
+    int Hg, Wg;                 // output grid iterated by tiles (per phase)
+    int BN, BK;
+    int kpt, kb_split;          // k-blocks per tap (all sources), k-blocks served by source 0
+    int tap_begin[5];
+    int tap_dh[kMaxTaps], tap_dw[kMaxTaps], tap_p[kMaxTaps], tap_q[kMaxTaps], tap_bk[kMaxTaps];
+    int a_qstride[2];
+    int out_p[4], out_q[4];
+    int out_C0, out_qstride[2];
+    int Cout_total;
+    int ostride, Hout, Wout;    // full-resolution output geometry (add / mask / fp32 output addressing)
+    const float* bias;
+    const __nv_bfloat16* add;
+    const __nv_bfloat16* mask;
+    int relu, sigmoid;
+    float* stats;
+    int stats_replicas;
+    float* out_f32;
+    int out_f32_c;
+    int store_bf16;
+    int stages, a_bytes, stage_bytes;
+    int tmem_cols;
+};
+
+__global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_constant__ ConvGemmParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int stages = P.stages;
+    const uint32_t bar_base = smem_base + static_cast<uint32_t>(max(stages * P.stage_bytes, 128 * P.BN * 2));
+    // barriers: full[s] at +8s, empty[s] at +8(stages+s), tmem_full at +16*stages, tmem ptr at +16*stages+8
+    const uint32_t full0 = bar_base, empty0 = bar_base + 8u * stages, tfull = bar_base + 16u * stages;
+    const uint32_t tmem_slot = tfull + 8u;
+
+    const int z = blockIdx.z;
+    const int tile = blockIdx.x;
+    const int tw_i = tile % P.tiles_w;
+    const int th_i = (tile / P.tiles_w) % P.tiles_h;
+    const int img = tile / (P.tiles_w * P.tiles_h);
+    const int w0 = tw_i * P.TW, h0 = th_i * P.TH;
+    const int n0 = blockIdx.y * P.BN;
+    const int tap_lo = P.tap_begin[z];
+    const int num_k = (P.tap_begin[z + 1] - tap_lo) * P.kpt;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(full0 + 8u * s, 1);
+            mbar_init(empty0 + 8u * s, 1);
+        }
+        mbar_init(tfull, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&P.tmA[0]);
+        tma_prefetch_desc(&P.tmB);
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, P.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (elect_one()) {
+            const uint32_t tx_bytes = static_cast<uint32_t>((P.TW * P.TH + P.BN) * P.BK * 2);
+            int stage = 0;
+            uint32_t phase = 0;
+            int tap = tap_lo, kb = 0;
+            for (int ks = 0; ks < num_k; ++ks) {
+                mbar_wait(empty0 + 8u * stage, phase ^ 1u);
+                const uint32_t sa = smem_base + stage * P.stage_bytes;
+                const uint32_t sb = sa + P.a_bytes;
+                const uint32_t fb = full0 + 8u * stage;
+                mbar_expect_tx(fb, tx_bytes);
+                const int src = kb < P.kb_split ? 0 : 1;
+                const int c = (src ? kb - P.kb_split : kb) * P.BK + P.tap_q[tap] * P.a_qstride[src];
+                tma_load_5d(sa, &P.tmA[src], fb, c, w0 + P.tap_dw[tap], P.tap_p[tap], h0 + P.tap_dh[tap], img);
+                tma_load_2d(sb, &P.tmB, fb, P.tap_bk[tap] + kb * P.BK, n0);
+                if (++kb == P.kpt) { kb = 0; ++tap; }
+                if (++stage == stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(128, P.BN, 0, 0);
+            const uint32_t swz_bytes = P.BK * 2;
+            const uint32_t lt = swizzle_layout_type(swz_bytes);
+            const uint32_t sbo = 8u * swz_bytes;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int ks = 0; ks < num_k; ++ks) {
+                mbar_wait(full0 + 8u * stage, phase);
+                tc_fence_after();
+                const uint32_t sa = smem_base + stage * P.stage_bytes;
+                const uint32_t sb = sa + P.a_bytes;
+                for (int k = 0; k < P.BK / 16; ++k) {
+                    const uint64_t da = make_smem_desc(sa + k * 32, 16, sbo, lt);
+                    const uint64_t db = make_smem_desc(sb + k * 32, 16, sbo, lt);
+                    umma_bf16(tmem_base, da, db, idesc, (ks | k) != 0);
+                }
+                umma_commit(empty0 + 8u * stage);
+                if (++stage == stages) { stage = 0; phase ^= 1u; }
+            }
+            umma_commit(tfull);
+        }
+    } else {
+        // ================= epilogue (4 warps = 4 TMEM lane quadrants) =================
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const int et = (warp - 2) * 32 + lane;            // 0..127 epilogue thread id
+        const int hl = row / P.TW, wl = row - hl * P.TW;
+        const int hg = h0 + hl, wg = w0 + wl;
+        const bool valid = (row < P.TW * P.TH) && hg < P.Hg && wg < P.Wg;
+        const int ho = hg * P.ostride + P.out_p[z], wo = wg * P.ostride + P.out_q[z];
+        const long pix = (static_cast<long>(img) * P.Hout + ho) * P.Wout + wo;
+        const int sub_c = P.BN < 64 ? P.BN : 64;            // channels per staging sub-tile
+        const uint32_t row_b = sub_c * 2;
+        const uint32_t smask = row_b / 16 - 1;
+
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        for (int c16 = 0; c16 < P.BN / 16; ++c16) {
+            uint32_t acc[16];
+            tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c16 * 16, acc);
+            tmem_ld_wait();
+            const int ch0 = n0 + c16 * 16;
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+            if (P.bias != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (ch0 + j < P.Cout_total) v[j] += __ldg(P.bias + ch0 + j);
+            }
+            if (P.add != nullptr && valid && ch0 < P.Cout_total) {
+                const uint4* ap = reinterpret_cast<const uint4*>(P.add + pix * P.Cout_total + ch0);
+                const uint4 a0 = ap[0], a1 = ap[1];
+                const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    v[2 * j] += bf16_lo(aw[j]);
+                    v[2 * j + 1] += bf16_hi(aw[j]);
+                }
+            }
+            if (P.relu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (P.mask != nullptr && valid && ch0 < P.Cout_total) {
+                const uint4* mp = reinterpret_cast<const uint4*>(P.mask + pix * P.Cout_total + ch0);
+                const uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+                const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (!(bf16_lo(mw[j]) > 0.f)) v[2 * j] = 0.f;
+                    if (!(bf16_hi(mw[j]) > 0.f)) v[2 * j + 1] = 0.f;
+                }
+            }
+            if (!valid) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            }
+            if (P.out_f32 != nullptr && valid) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int ch = ch0 + j;
+                    if (ch < P.out_f32_c) {
+                        float o = v[j];
+                        if (P.sigmoid) o = 1.f / (1.f + __expf(-o));
+                        P.out_f32[((static_cast<long>(img) * P.out_f32_c + ch) * P.Hout + ho) * P.Wout + wo] = o;
+                    }
+                }
+            }
+            if (P.store_bf16) {
+                const int cl = c16 * 16;                   // channel offset inside the N tile
+                const uint32_t sub = cl / sub_c;
+                const uint32_t off = sub * 128u * row_b + row * row_b + (cl - sub * sub_c) * 2;
+                uint4 q0, q1;
+                q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
+                q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
+                q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
+                q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
+                const uint32_t d0 = smem_base + swz(off, smask), d1 = smem_base + swz(off + 16, smask);
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d0), "r"(q0.x), "r"(q0.y), "r"(q0.z), "r"(q0.w) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d1), "r"(q1.x), "r"(q1.y), "r"(q1.z), "r"(q1.w) : "memory");
+            }
+        }
+        tc_fence_before();
+        if (P.store_bf16) {
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (et == 0) {
+                const int nsub = (P.BN + sub_c - 1) / sub_c;
+                for (int s = 0; s < nsub; ++s) {
+                    const int ch = n0 + s * sub_c;
+                    if (ch >= P.Cout_total) break;
+                    const int o = ch < P.out_C0 ? 0 : 1;
+                    const int cc = (o ? ch - P.out_C0 : ch) + P.out_q[z] * P.out_qstride[o];
+                    tma_store_5d(&P.tmOut[o], smem_base + s * 128u * row_b, cc, w0, P.out_p[z], h0, img);
+                }
+                tma_store_commit();
+            }
+            if (P.stats != nullptr) {
+                // per-channel sum / sum-of-squares of the staged (bf16-rounded, invalid rows zeroed) tile
+                const int pairs = P.BN / 2;
+                const int cp = et % pairs, rg = et / pairs, nrg = 128 / pairs;
+                const int cl = cp * 2;
+                const uint32_t sub = cl / sub_c;
+                float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                for (int r = rg; r < 128; r += nrg) {
+                    const uint32_t off = sub * 128u * row_b + r * row_b + (cl - sub * sub_c) * 2;
+                    uint32_t w;
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(smem_base + swz(off, smask)));
+                    const float a = bf16_lo(w), b = bf16_hi(w);
+                    s0 += a; q0 += a * a; s1 += b; q1 += b * b;
+                }
+                const int ch = n0 + cl;
+                if (ch < P.Cout_total) {
+                    float* st = P.stats + static_cast<long>(blockIdx.x % P.stats_replicas) * 2 * P.Cout_total;
+                    atomicAdd(st + ch, s0);
+                    atomicAdd(st + ch + 1, s1);
+                    atomicAdd(st + P.Cout_total + ch, q0);
+                    atomicAdd(st + P.Cout_total + ch + 1, q1);
+                }
+            }
+            if (et == 0) tma_store_wait_all();
+        }
+    }
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static void pick_tile(int Hg, int Wg, int* TW, int* TH) {
+    // choose a TW x TH (<=128 pixels) box maximising useful pixels per tile; ties -> wider rows
+    double best = -1.0;
+    int bw = 128, bh = 1;
+    for (int tw = 1; tw <= 128; ++tw) {
+        const int th = 128 / tw;
+        if (th < 1) continue;
+        const long tiles = static_cast<long>((Wg + tw - 1) / tw) * ((Hg + th - 1) / th);
+        const double eff = static_cast<double>(Hg) * Wg / (tiles * 128.0);
+        if (eff > best + 1e-9 || (eff > best - 1e-9 && tw > bw)) { best = eff; bw = tw; bh = th; }
+    }
+    *TW = bw;
+    *TH = bh;
+}
+
+static int act_map(CUtensorMap* m, const hd_act& t, bool phase_view, int box_c, int TW, int TH, int swizzle) {
+    uint64_t dims[5], str[4];
+    uint32_t box[5] = {static_cast<uint32_t>(box_c), static_cast<uint32_t>(TW), 1u, static_cast<uint32_t>(TH), 1u};
+    const uint64_t C = t.c, W = t.w, H = t.h;
+    if (!phase_view) {
+        dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = t.n;
+        str[0] = C * 2; str[1] = W * C * 2; str[2] = W * C * 2; str[3] = H * W * C * 2;
+    } else {
+        dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = t.n;
+        str[0] = 2 * C * 2; str[1] = W * C * 2; str[2] = 2 * W * C * 2; str[3] = H * W * C * 2;
+    }
+    return make_tensor_map(m, t.ptr, 5, dims, str, box, swizzle);
+}
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStream_t stream) {
+    P.a_bytes = round_up(128 * P.BK * 2, 1024);
+    P.stage_bytes = P.a_bytes + round_up(P.BN * P.BK * 2, 1024);
+    int stages = (100 * 1024) / P.stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) stages = 2;
+    P.stages = stages;
+    int cols = 32;
+    while (cols < P.BN) cols *= 2;
+    P.tmem_cols = cols;
+    const int staging = 128 * P.BN * 2;
+    const int body = stages * P.stage_bytes > staging ? stages * P.stage_bytes : staging;
+    const size_t smem = 1024 + body + 16 * stages + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        HD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set = true;
+    }
+    dim3 grid(P.tiles_w * P.tiles_h * n_img, (P.Cout_total + P.BN - 1) / P.BN, nphases);
+    conv_gemm_kernel<<<grid, kThreads, smem, stream>>>(P);
+    HD_CUDA_OK(cudaPeekAtLastError());
+    return HD_OK;
+}
+
+static int pick_bk(int c0, int c1) {
+    for (int bk = 64; bk >= 16; bk >>= 1)
+        if (c0 % bk == 0 && c1 % bk == 0) return bk;
+    return 0;
+}
+
+static int pick_bn(int c) { return c >= 128 ? 128 : (c >= 64 ? 64 : (c >= 32 ? 32 : 16)); }
+
+static int check_act(const hd_act& t) {
+    return t.ptr != nullptr && t.n > 0 && t.h > 0 && t.w > 0 && t.c > 0 && t.c % 16 == 0 &&
+           (reinterpret_cast<uintptr_t>(t.ptr) & 15) == 0;
+}
+
+static int fill_epilogue(ConvGemmParams& P, const hd_conv_args* a) {
+    P.bias = a->bias;
+    P.add = static_cast<const __nv_bfloat16*>(a->add);
+    P.mask = static_cast<const __nv_bfloat16*>(a->mask);
+    P.relu = a->relu;
+    P.sigmoid = a->sigmoid;
+    P.stats = a->stats;
+    P.stats_replicas = a->stats_replicas > 0 ? a->stats_replicas : 1;
+    P.out_f32 = a->out_f32_nchw;
+    P.out_f32_c = a->out_f32_channels;
+    P.store_bf16 = a->store_bf16;
+    HD_CHECK_ARG(a->store_bf16 || a->out_f32_nchw != nullptr);
+    HD_CHECK_ARG(!(a->y1.ptr != nullptr && (a->add != nullptr || a->mask != nullptr || a->stats != nullptr)));
+    return HD_OK;
+}
+
+}  // namespace hd
+
+using namespace hd;
+
+extern "C" int hd_conv_fwd(const hd_conv_args* a, hd_stream stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    HD_CHECK_ARG(a != nullptr && a->w != nullptr);
+    HD_CHECK_ARG(check_act(a->x0) && check_act(a->y0) && a->y1.ptr == nullptr);
+    const bool two = a->x1.ptr != nullptr;
+    if (two) HD_CHECK_ARG(check_act(a->x1) && a->x1.n == a->x0.n && a->x1.h == a->x0.h && a->x1.w == a->x0.w);
+    const int k = a->kh, s = a->stride;
+    HD_CHECK_ARG(a->kh == a->kw && (k == 1 || k == 3) && (s == 1 || s == 2));
+    const int pad = k / 2;
+    const int H = a->x0.h, W = a->x0.w, N = a->x0.n;
+    if (s == 2) HD_CHECK_ARG(H % 2 == 0 && W % 2 == 0);
+    const int Ho = H / s, Wo = W / s;
+    HD_CHECK_ARG(a->y0.n == N && a->y0.h == Ho && a->y0.w == Wo);
+    const int cin = a->x0.c + (two ? a->x1.c : 0), cout = a->y0.c;
+
+    ConvGemmParams P;
+    memset(&P, 0, sizeof(P));
+    P.BK = pick_bk(a->x0.c, two ? a->x1.c : a->x0.c);
+    HD_CHECK_ARG(P.BK != 0);
+    P.BN = pick_bn(cout);
+    P.kpt = cin / P.BK;
+    P.kb_split = a->x0.c / P.BK;
+    P.Hg = Ho; P.Wg = Wo; P.ostride = 1; P.Hout = Ho; P.Wout = Wo;
+    pick_tile(P.Hg, P.Wg, &P.TW, &P.TH);
+    P.tiles_w = (P.Wg + P.TW - 1) / P.TW;
+    P.tiles_h = (P.Hg + P.TH - 1) / P.TH;
+    int t = 0;
+    for (int r = 0; r < k; ++r)
+        for (int c = 0; c < k; ++c, ++t) {
+            const int eh = r - pad, ew = c - pad;
+            if (s == 1) {
+                P.tap_dh[t] = eh; P.tap_dw[t] = ew; P.tap_p[t] = 0; P.tap_q[t] = 0;
+            } else {
+                const int p = eh & 1, q = ew & 1;
+                P.tap_p[t] = p; P.tap_q[t] = q;
+                P.tap_dh[t] = (eh - p) / 2; P.tap_dw[t] = (ew - q) / 2;
+            }
+            P.tap_bk[t] = t * cin;
+        }
+    P.tap_begin[0] = 0; P.tap_begin[1] = t;
+    P.a_qstride[0] = a->x0.c; P.a_qstride[1] = two ? a->x1.c : 0;
+    P.out_C0 = cout; P.Cout_total = cout;
+    if (int e = fill_epilogue(P, a)) return e;
+
+    const int swz = P.BK * 2;
+    if (act_map(&P.tmA[0], a->x0, s == 2, P.BK, P.TW, P.TH, swz)) return HD_ERR_CUDA;
+    if (two) { if (act_map(&P.tmA[1], a->x1, s == 2, P.BK, P.TW, P.TH, swz)) return HD_ERR_CUDA; }
+    else P.tmA[1] = P.tmA[0];
+    {
+        uint64_t dims[2] = {static_cast<uint64_t>(k * k * cin), static_cast<uint64_t>(round_up(cout, 16))};
+        uint64_t str[1] = {dims[0] * 2};
+        uint32_t box[2] = {static_cast<uint32_t>(P.BK), static_cast<uint32_t>(P.BN)};
+        if (make_tensor_map(&P.tmB, a->w, 2, dims, str, box, swz)) return HD_ERR_CUDA;
+    }
+    const int sub_c = P.BN < 64 ? P.BN : 64;
+    if (act_map(&P.tmOut[0], a->y0, false, sub_c, P.TW, P.TH, sub_c * 2)) return HD_ERR_CUDA;
+    P.tmOut[1] = P.tmOut[0];
+    return launch_conv_gemm(P, N, 1, stream);
+}
+
+extern "C" int hd_conv_dgrad(const hd_conv_args* a, hd_stream stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    HD_CHECK_ARG(a != nullptr && a->w != nullptr);
+    HD_CHECK_ARG(check_act(a->x0) && check_act(a->y0) && a->x1.ptr == nullptr);
+    const bool two = a->y1.ptr != nullptr;
+    if (two) HD_CHECK_ARG(check_act(a->y1) && a->y1.n == a->y0.n && a->y1.h == a->y0.h && a->y1.w == a->y0.w);
+    const int k = a->kh, s = a->stride;
+    HD_CHECK_ARG(a->kh == a->kw && (k == 1 || k == 3) && (s == 1 || s == 2));
+    const int pad = k / 2;
+    const int H = a->y0.h, W = a->y0.w, N = a->y0.n;       // input-gradient geometry
+    if (s == 2) HD_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && !two);
+    HD_CHECK_ARG(a->x0.n == N && a->x0.h == H / s && a->x0.w == W / s);
+    const int cout = a->x0.c;                              // GEMM K per tap
+    const int cin = a->y0.c + (two ? a->y1.c : 0);         // GEMM N
+
+    ConvGemmParams P;
+    memset(&P, 0, sizeof(P));
+    P.BK = pick_bk(cout, cout);
+    HD_CHECK_ARG(P.BK != 0);
+    if (two) {
+        P.BN = 0;
+        for (int bn = 128; bn >= 16; bn >>= 1)
+            if (a->y0.c % bn == 0) { P.BN = bn; break; }
+        HD_CHECK_ARG(P.BN != 0);
+    } else {
+        P.BN = pick_bn(cin);
+    }
+    P.kpt = cout / P.BK;
+    P.kb_split = P.kpt;
+    P.Hg = H / s; P.Wg = W / s; P.ostride = s; P.Hout = H; P.Wout = W;
+    pick_tile(P.Hg, P.Wg, &P.TW, &P.TH);
+    P.tiles_w = (P.Wg + P.TW - 1) / P.TW;
+    P.tiles_h = (P.Hg + P.TH - 1) / P.TH;
+    int nph = 0, t = 0;
+    if (s == 1) {
+        for (int r = 0; r < k; ++r)
+            for (int c = 0; c < k; ++c, ++t) {
+                P.tap_dh[t] = pad - r; P.tap_dw[t] = pad - c; P.tap_bk[t] = (r * k + c) * cout;
+            }
+        P.tap_begin[0] = 0; P.tap_begin[1] = t;
+        nph = 1;
+    } else {
+        for (int p = 0; p < 2; ++p)
+            for (int q = 0; q < 2; ++q) {
+                if (a->phase_mask && !((a->phase_mask >> (2 * p + q)) & 1)) continue;
+                const int t0 = t;
+                for (int r = 0; r < k; ++r) {
+                    if (((p + pad - r) & 1) != 0) continue;
+                    for (int c = 0; c < k; ++c) {
+                        if (((q + pad - c) & 1) != 0) continue;
+                        HD_CHECK_ARG(t < kMaxTaps);
+                        P.tap_dh[t] = (p + pad - r) / 2; P.tap_dw[t] = (q + pad - c) / 2;
+                        P.tap_bk[t] = (r * k + c) * cout;
+                        ++t;
+                    }
+                }
+                if (t == t0) continue;                     // no tap reaches this phase (1x1 stride 2)
+                P.tap_begin[nph] = t0; P.tap_begin[nph + 1] = t;
+                P.out_p[nph] = p; P.out_q[nph] = q;
+                ++nph;
+            }
+        HD_CHECK_ARG(nph > 0);
+    }
+    P.a_qstride[0] = 0; P.a_qstride[1] = 0;
+    P.out_C0 = a->y0.c; P.Cout_total = cin;
+    P.out_qstride[0] = a->y0.c; P.out_qstride[1] = two ? a->y1.c : 0;
+    if (int e = fill_epilogue(P, a)) return e;
+
+    const int swz = P.BK * 2;
+    if (act_map(&P.tmA[0], a->x0, false, P.BK, P.TW, P.TH, swz)) return HD_ERR_CUDA;
+    P.tmA[1] = P.tmA[0];
+    {
+        uint64_t dims[2] = {static_cast<uint64_t>(k * k * cout), static_cast<uint64_t>(round_up(cin, 16))};
+        uint64_t str[1] = {dims[0] * 2};
+        uint32_t box[2] = {static_cast<uint32_t>(P.BK), static_cast<uint32_t>(P.BN)};
+        if (make_tensor_map(&P.tmB, a->w, 2, dims, str, box, swz)) return HD_ERR_CUDA;
+    }
+    const int sub_c = P.BN < 64 ? P.BN : 64;
+    if (act_map(&P.tmOut[0], a->y0, s == 2, sub_c, P.TW, P.TH, sub_c * 2)) return HD_ERR_CUDA;
+    if (two) { if (act_map(&P.tmOut[1], a->y1, false, sub_c, P.TW, P.TH, sub_c * 2)) return HD_ERR_CUDA; }
+    else P.tmOut[1] = P.tmOut[0];
+    return launch_conv_gemm(P, N, nph, stream);
+}

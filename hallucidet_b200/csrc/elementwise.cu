@@ -1,0 +1,916 @@
+// elementwise.cu -- the memory-bound kernels of the HalluciDet hot path (HBM roofline): weight packing,
+// stem im2col/col2im, train-mode BatchNorm finalize/apply/backward, max-pool, nearest up-sampling, FPN
+// top-down add, layout converters, detector input transform, sigmoid-head backward and the pixel regulariser.
+// All activation kernels move 16 bytes (8 bf16 channels) per thread per access, consecutive threads on
+// consecutive channel groups / pixels (coalesced NHWC), grid sized from the element count.
+#include "hd_common.cuh"
+
+namespace hd {
+
+constexpr int kEwThreads = 256;
+
+static inline int ew_blocks(long work) {
+    long b = (work + kEwThreads - 1) / kEwThreads;
+    if (b < 1) b = 1;
+    const long cap = 148L * 64;                      // grid-stride above ~64 blocks per SM
+    return static_cast<int>(b > cap ? cap : b);
+}
+
+struct bf8 {                                          // 8 bf16 channels = one 16-byte access
+    uint4 u;
+    __device__ __forceinline__ void load(const void* p) { u = *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ void store(void* p) const { *reinterpret_cast<uint4*>(p) = u; }
+    __device__ __forceinline__ void unpack(float* f) const {
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { f[2 * i] = bf16_lo(w[i]); f[2 * i + 1] = bf16_hi(w[i]); }
+    }
+    __device__ __forceinline__ void pack(const float* f) {
+        u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+        u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+    }
+};
+
+// -------------------------------------------------------------------------------------------------
+// weight packing
+// -------------------------------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale, int cout, int cin,
+                                   int kh, int kw, __nv_bfloat16* w_fwd, int cout_pad, int k_pad,
+                                   __nv_bfloat16* w_dgrad, int cin_pad, __nv_bfloat16* w_t) {
+    const int taps = kh * kw;
+    const long n_fwd = static_cast<long>(cout_pad) * k_pad;
+    const long n_dg = static_cast<long>(cin_pad) * taps * cout;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n_fwd + n_dg;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        if (i < n_fwd) {
+            const int co = static_cast<int>(i / k_pad), k = static_cast<int>(i % k_pad);
+            float v = 0.f;
+            if (co < cout && k < taps * cin) {
+                const int tap = k / cin, ci = k % cin;
+                v = w[(static_cast<long>(co) * cin + ci) * taps + tap];
+                if (scale) v *= scale[co];
+            }
+            const __nv_bfloat16 b = __float2bfloat16_rn(v);
+            if (w_fwd) w_fwd[i] = b;
+            if (w_t) w_t[static_cast<long>(k) * cout_pad + co] = b;
+        } else if (w_dgrad) {
+            const long j = i - n_fwd;
+            const int ci = static_cast<int>(j / (taps * cout));
+            const int rem = static_cast<int>(j % (taps * cout));
+            const int tap = rem / cout, co = rem % cout;
+            float v = 0.f;
+            if (ci < cin) {
+                v = w[(static_cast<long>(co) * cin + ci) * taps + tap];
+                if (scale) v *= scale[co];
+            }
+            w_dgrad[j] = __float2bfloat16_rn(v);
+        }
+    }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dw, float* __restrict__ g, int cout, int cin, int taps,
+                                    int tap_stride, int row_stride, float scale) {
+    const long n = static_cast<long>(cout) * cin * taps;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int tap = static_cast<int>(i % taps);
+        const int ci = static_cast<int>((i / taps) % cin);
+        const int co = static_cast<int>(i / (static_cast<long>(taps) * cin));
+        g[i] = dw[static_cast<long>(co) * row_stride + static_cast<long>(tap) * tap_stride + ci] * scale;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// stem 7x7/2 patches
+// -------------------------------------------------------------------------------------------------
+__global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ patches, int n, int h, int w,
+                                   int k_pad) {
+    const int ho = h / 2, wo = w / 2, groups = k_pad / 8;
+    const long total = static_cast<long>(n) * ho * wo * groups;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % groups);
+        const long pix = i / groups;
+        const int ow = static_cast<int>(pix % wo), oh = static_cast<int>((pix / wo) % ho), b = static_cast<int>(pix / (static_cast<long>(wo) * ho));
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = g * 8 + j;
+            float v = 0.f;
+            if (k < 147) {
+                const int c = k % 3, tap = k / 3, r = tap / 7, s = tap % 7;
+                const int ih = 2 * oh + r - 3, iw = 2 * ow + s - 3;
+                if (ih >= 0 && ih < h && iw >= 0 && iw < w) v = __ldg(x + ((static_cast<long>(b) * 3 + c) * h + ih) * w + iw);
+            }
+            f[j] = v;
+        }
+        bf8 o;
+        o.pack(f);
+        o.store(patches + pix * k_pad + g * 8);
+    }
+}
+
+__global__ void stem_col2im_kernel(const __nv_bfloat16* __restrict__ dp, float* __restrict__ dx, int n, int h, int w, int k_pad) {
+    const int ho = h / 2, wo = w / 2;
+    const long total = static_cast<long>(n) * h * w;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int iw = static_cast<int>(i % w), ih = static_cast<int>((i / w) % h), b = static_cast<int>(i / (static_cast<long>(w) * h));
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int r = (ih + 3) & 1; r < 7; r += 2) {
+            const int oh = (ih + 3 - r) / 2;
+            if (ih + 3 - r < 0 || oh >= ho) continue;
+            for (int s = (iw + 3) & 1; s < 7; s += 2) {
+                const int ow = (iw + 3 - s) / 2;
+                if (iw + 3 - s < 0 || ow >= wo) continue;
+                const __nv_bfloat16* p = dp + ((static_cast<long>(b) * ho + oh) * wo + ow) * k_pad + (r * 7 + s) * 3;
+                a0 += __bfloat162float(p[0]); a1 += __bfloat162float(p[1]); a2 += __bfloat162float(p[2]);
+            }
+        }
+        const long plane = static_cast<long>(h) * w;
+        float* o = dx + static_cast<long>(b) * 3 * plane + static_cast<long>(ih) * w + iw;
+        o[0] = a0; o[plane] = a1; o[2 * plane] = a2;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// train-mode BatchNorm
+// -------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, int reps, int C, double count, const float* gamma,
+                                   const float* beta, float eps, float momentum, float* rm, float* rv, float* mean_out,
+                                   float* invstd_out, float* scale_out, float* shift_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int r = 0; r < reps; ++r) {
+        s += stats[(static_cast<long>(r) * 2) * C + c];
+        q += stats[(static_cast<long>(r) * 2 + 1) * C + c];
+    }
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float sc = gamma[c] * invstd;
+    if (mean_out) mean_out[c] = static_cast<float>(mean);
+    if (invstd_out) invstd_out[c] = invstd;
+    scale_out[c] = sc;
+    shift_out[c] = beta[c] - static_cast<float>(mean) * sc;
+    if (rm) rm[c] = (1.f - momentum) * rm[c] + momentum * static_cast<float>(mean);
+    if (rv) {
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        rv[c] = (1.f - momentum) * rv[c] + momentum * static_cast<float>(unbiased);
+    }
+}
+
+__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ scale,
+                                const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
+                                const float* __restrict__ rscale, const float* __restrict__ rshift, int relu,
+                                __nv_bfloat16* __restrict__ y, long n_pix, int C) {
+    const int G = C / 8;
+    const long total = n_pix * G;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int c0 = static_cast<int>(i % G) * 8;
+        bf8 v;
+        v.load(z + i * 8);
+        float f[8];
+        v.unpack(f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], __ldg(scale + c0 + j), __ldg(shift + c0 + j));
+        if (res) {
+            bf8 rv;
+            rv.load(res + i * 8);
+            float r[8];
+            rv.unpack(r);
+            if (rscale) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r[j] = fmaf(r[j], __ldg(rscale + c0 + j), __ldg(rshift + c0 + j));
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += r[j];
+        }
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        v.pack(f);
+        v.store(y + i * 8);
+    }
+}
+
+// sums[0][c] = sum g, sums[1][c] = sum g*xhat with g = dy*(y>0)
+__global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ yrelu,
+                                     const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, float* __restrict__ sums, long n_pix, int C,
+                                     long pix_per_block) {
+    extern __shared__ float sacc[];                    // [2][C]
+    const int G = C / 8;
+    const int L = blockDim.x / G;                      // pixel lanes
+    const int g = threadIdx.x % G, l = threadIdx.x / G;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+    float a[8], b[8], mu[8], is[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a[j] = 0.f; b[j] = 0.f; mu[j] = mean[g * 8 + j]; is[j] = invstd[g * 8 + j]; }
+    const long p0 = blockIdx.x * pix_per_block;
+    long p1 = p0 + pix_per_block;
+    if (p1 > n_pix) p1 = n_pix;
+    if (l < L) {
+        for (long p = p0 + l; p < p1; p += L) {
+            const long off = p * C + g * 8;
+            bf8 d, zz;
+            d.load(dy + off);
+            zz.load(z + off);
+            float df[8], zf[8];
+            d.unpack(df);
+            zz.unpack(zf);
+            if (yrelu) {
+                bf8 yy;
+                yy.load(yrelu + off);
+                float yf[8];
+                yy.unpack(yf);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (!(yf[j] > 0.f)) df[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a[j] += df[j]; b[j] += df[j] * (zf[j] - mu[j]) * is[j]; }
+        }
+        if (G < 32 && (G & (G - 1)) == 0) {              // lanes sharing a channel group inside the warp
+            for (int o = 16; o >= G; o >>= 1) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
+                    b[j] += __shfl_xor_sync(0xffffffffu, b[j], o);
+                }
+            }
+            if ((threadIdx.x & 31) < G) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { atomicAdd(&sacc[g * 8 + j], a[j]); atomicAdd(&sacc[C + g * 8 + j], b[j]); }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { atomicAdd(&sacc[g * 8 + j], a[j]); atomicAdd(&sacc[C + g * 8 + j], b[j]); }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], sacc[i]);
+}
+
+__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ yrelu,
+                                    const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
+                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                    const float* __restrict__ sums, float inv_count, __nv_bfloat16* __restrict__ dz,
+                                    __nv_bfloat16* __restrict__ gout, float* dgamma, float* dbeta, long n_pix, int C) {
+    const int G = C / 8;
+    const long total = n_pix * G;
+    if (blockIdx.x == 0) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            if (dbeta) dbeta[c] = sums[c];
+            if (dgamma) dgamma[c] = sums[C + c];
+        }
+    }
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int c0 = static_cast<int>(i % G) * 8;
+        bf8 d, zz;
+        d.load(dy + i * 8);
+        zz.load(z + i * 8);
+        float df[8], zf[8], o[8];
+        d.unpack(df);
+        zz.unpack(zf);
+        if (yrelu) {
+            bf8 yy;
+            yy.load(yrelu + i * 8);
+            float yf[8];
+            yy.unpack(yf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (!(yf[j] > 0.f)) df[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = c0 + j;
+            const float is = __ldg(invstd + c);
+            const float xh = (zf[j] - __ldg(mean + c)) * is;
+            o[j] = __ldg(gamma + c) * is * (df[j] - __ldg(sums + c) * inv_count - xh * __ldg(sums + C + c) * inv_count);
+        }
+        bf8 ov;
+        ov.pack(o);
+        ov.store(dz + i * 8);
+        if (gout) {
+            bf8 gv;
+            gv.pack(df);
+            gv.store(gout + i * 8);
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// max-pool 3x3 stride 2 pad 1 (NHWC)
+// -------------------------------------------------------------------------------------------------
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int h, int w,
+                                   int C) {
+    const int ho = h / 2, wo = w / 2, G = C / 8;
+    const long total = static_cast<long>(n) * ho * wo * G;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % G);
+        const long pix = i / G;
+        const int ow = static_cast<int>(pix % wo), oh = static_cast<int>((pix / wo) % ho), b = static_cast<int>(pix / (static_cast<long>(wo) * ho));
+        float m[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+        for (int r = 0; r < 3; ++r) {
+            const int ih = 2 * oh + r - 1;
+            if (ih < 0 || ih >= h) continue;
+            for (int s = 0; s < 3; ++s) {
+                const int iw = 2 * ow + s - 1;
+                if (iw < 0 || iw >= w) continue;
+                bf8 v;
+                v.load(x + ((static_cast<long>(b) * h + ih) * w + iw) * C + g * 8);
+                float f[8];
+                v.unpack(f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+            }
+        }
+        bf8 o;
+        o.pack(m);
+        o.store(y + pix * C + g * 8);
+    }
+}
+
+// dx[ih,iw] = (add) + sum over windows whose FIRST maximum (scan order) is (ih,iw) of dy; optional x>0 mask
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
+                                   const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ add,
+                                   __nv_bfloat16* __restrict__ dx, int n, int h, int w, int C, int relu_mask) {
+    const int ho = h / 2, wo = w / 2, G = C / 8;
+    const long total = static_cast<long>(n) * h * w * G;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % G);
+        const long pix = i / G;
+        const int iw = static_cast<int>(pix % w), ih = static_cast<int>((pix / w) % h), b = static_cast<int>(pix / (static_cast<long>(w) * h));
+        bf8 xv;
+        xv.load(x + pix * C + g * 8);
+        float xf[8], acc[8];
+        xv.unpack(xf);
+        if (add) {
+            bf8 av;
+            av.load(add + pix * C + g * 8);
+            av.unpack(acc);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        }
+        for (int oh = ih / 2; oh <= (ih + 1) / 2; ++oh) {      // windows with 2*oh-1 <= ih <= 2*oh+1
+            if (oh < 0 || oh >= ho) continue;
+            for (int ow = iw / 2; ow <= (iw + 1) / 2; ++ow) {
+                if (ow < 0 || ow >= wo) continue;
+                const long opix = (static_cast<long>(b) * ho + oh) * wo + ow;
+                bf8 yv, dv;
+                yv.load(y + opix * C + g * 8);
+                float yf[8];
+                yv.unpack(yf);
+                unsigned hit = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) hit |= (xf[j] == yf[j]) ? (1u << j) : 0u;
+                if (!hit) continue;
+                // drop channels where an earlier window element already equals the max (ATen keeps the first)
+                const int rr = ih - (2 * oh - 1), ss = iw - (2 * ow - 1);
+                for (int r = 0; r <= rr && hit; ++r) {
+                    const int jh = 2 * oh + r - 1;
+                    if (jh < 0) continue;
+                    const int s_end = (r == rr) ? ss : 3;
+                    for (int s = 0; s < s_end; ++s) {
+                        const int jw = 2 * ow + s - 1;
+                        if (jw < 0 || jw >= w) continue;
+                        bf8 ev;
+                        ev.load(x + ((static_cast<long>(b) * h + jh) * w + jw) * C + g * 8);
+                        float ef[8];
+                        ev.unpack(ef);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) if (ef[j] == yf[j]) hit &= ~(1u << j);
+                    }
+                }
+                if (!hit) continue;
+                dv.load(dy + opix * C + g * 8);
+                float df[8];
+                dv.unpack(df);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (hit & (1u << j)) acc[j] += df[j];
+            }
+        }
+        if (relu_mask) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (!(xf[j] > 0.f)) acc[j] = 0.f;
+        }
+        bf8 o;
+        o.pack(acc);
+        o.store(dx + pix * C + g * 8);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// nearest up-sampling x2 and FPN top-down add
+// -------------------------------------------------------------------------------------------------
+__global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int h, int w,
+                                      int C) {            // h,w = OUTPUT size
+    const int G = C / 8;
+    const long total = static_cast<long>(n) * h * w * G;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % G);
+        const long pix = i / G;
+        const int ow = static_cast<int>(pix % w), oh = static_cast<int>((pix / w) % h), b = static_cast<int>(pix / (static_cast<long>(w) * h));
+        bf8 v;
+        v.load(x + ((static_cast<long>(b) * (h / 2) + oh / 2) * (w / 2) + ow / 2) * C + g * 8);
+        v.store(y + pix * C + g * 8);
+    }
+}
+
+__global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int n, int h, int w,
+                                      int C) {            // h,w = INPUT (small) size
+    const int G = C / 8;
+    const long total = static_cast<long>(n) * h * w * G;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % G);
+        const long pix = i / G;
+        const int iw = static_cast<int>(pix % w), ih = static_cast<int>((pix / w) % h), b = static_cast<int>(pix / (static_cast<long>(w) * h));
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int r = 0; r < 2; ++r)
+            for (int s = 0; s < 2; ++s) {
+                bf8 v;
+                v.load(dy + ((static_cast<long>(b) * (2 * h) + 2 * ih + r) * (2 * w) + 2 * iw + s) * C + g * 8);
+                float f[8];
+                v.unpack(f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += f[j];
+            }
+        bf8 o;
+        o.pack(acc);
+        o.store(dx + pix * C + g * 8);
+    }
+}
+
+__device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
+    const int s = static_cast<int>(floorf(static_cast<float>(dst) * scale));
+    return s < in_size - 1 ? s : in_size - 1;
+}
+
+__global__ void add_nearest_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int hi, int wi,
+                                       int ho, int wo, int C, float sh, float sw) {
+    const int G = C / 8;
+    const long total = static_cast<long>(n) * ho * wo * G;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % G);
+        const long pix = i / G;
+        const int ow = static_cast<int>(pix % wo), oh = static_cast<int>((pix / wo) % ho), b = static_cast<int>(pix / (static_cast<long>(wo) * ho));
+        const int ih = nearest_src(oh, sh, hi), iw = nearest_src(ow, sw, wi);
+        bf8 a, c;
+        a.load(x + ((static_cast<long>(b) * hi + ih) * wi + iw) * C + g * 8);
+        c.load(y + pix * C + g * 8);
+        float fa[8], fc[8];
+        a.unpack(fa);
+        c.unpack(fc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) fc[j] += fa[j];
+        c.pack(fc);
+        c.store(y + pix * C + g * 8);
+    }
+}
+
+__global__ void add_nearest_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int n, int hi,
+                                       int wi, int ho, int wo, int C, float sh, float sw, int accumulate) {
+    const int G = C / 8;
+    const long total = static_cast<long>(n) * hi * wi * G;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % G);
+        const long pix = i / G;
+        const int iw = static_cast<int>(pix % wi), ih = static_cast<int>((pix / wi) % hi), b = static_cast<int>(pix / (static_cast<long>(wi) * hi));
+        float acc[8];
+        if (accumulate) {
+            bf8 v;
+            v.load(dx + pix * C + g * 8);
+            v.unpack(acc);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        }
+        int h_lo = static_cast<int>(ih / sh) - 2, w_lo = static_cast<int>(iw / sw) - 2;
+        if (h_lo < 0) h_lo = 0;
+        if (w_lo < 0) w_lo = 0;
+        for (int oh = h_lo; oh < ho; ++oh) {
+            const int sh_i = nearest_src(oh, sh, hi);
+            if (sh_i < ih) continue;
+            if (sh_i > ih) break;
+            for (int ow = w_lo; ow < wo; ++ow) {
+                const int sw_i = nearest_src(ow, sw, wi);
+                if (sw_i < iw) continue;
+                if (sw_i > iw) break;
+                bf8 v;
+                v.load(dy + ((static_cast<long>(b) * ho + oh) * wo + ow) * C + g * 8);
+                float f[8];
+                v.unpack(f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += f[j];
+            }
+        }
+        bf8 o;
+        o.pack(acc);
+        o.store(dx + pix * C + g * 8);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// layout converters
+// -------------------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int h, int w, int Cs,
+                                    int Cd) {
+    // thread = (pixel, 8-channel group); consecutive threads -> consecutive pixels (coalesced fp32 reads)
+    const int G = Cd / 8;
+    const long plane = static_cast<long>(h) * w;
+    const long total = static_cast<long>(n) * plane * G;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const long p = i % plane;
+        const int g = static_cast<int>((i / plane) % G);
+        const int b = static_cast<int>(i / (plane * G));
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = g * 8 + j;
+            f[j] = c < Cs ? __ldg(x + (static_cast<long>(b) * Cs + c) * plane + p) : 0.f;
+        }
+        bf8 o;
+        o.pack(f);
+        o.store(y + (static_cast<long>(b) * plane + p) * Cd + g * 8);
+    }
+}
+
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int n, int h, int w, int Cs,
+                                    int Cd) {
+    const int G = (Cd + 7) / 8;
+    const long plane = static_cast<long>(h) * w;
+    const long total = static_cast<long>(n) * plane * G;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const long p = i % plane;
+        const int g = static_cast<int>((i / plane) % G);
+        const int b = static_cast<int>(i / (plane * G));
+        bf8 v;
+        v.load(x + (static_cast<long>(b) * plane + p) * Cs + g * 8);
+        float f[8];
+        v.unpack(f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = g * 8 + j;
+            if (c < Cd) y[(static_cast<long>(b) * Cd + c) * plane + p] = f[j];
+        }
+    }
+}
+
+__global__ void sigmoid_bwd_pack_kernel(const float* __restrict__ dhal, const float* __restrict__ hal,
+                                        __nv_bfloat16* __restrict__ dl, int n, int h, int w, int ch, int Cd, float* dbias) {
+    __shared__ float sb[4];
+    if (threadIdx.x < 4) sb[threadIdx.x] = 0.f;
+    __syncthreads();
+    const long plane = static_cast<long>(h) * w;
+    const long total = static_cast<long>(n) * plane;
+    float loc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const long p = i % plane;
+        const int b = static_cast<int>(i / plane);
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = 0.f;
+        for (int c = 0; c < ch && c < 4; ++c) {
+            const long idx = (static_cast<long>(b) * ch + c) * plane + p;
+            const float s = hal[idx];
+            const float g = dhal[idx] * s * (1.f - s);
+            f[c] = g;
+            loc[c] += g;
+        }
+        for (int g8 = 0; g8 < 2; ++g8) {
+            bf8 o;
+            o.pack(f + g8 * 8);
+            o.store(dl + i * Cd + g8 * 8);
+        }
+    }
+    if (dbias) {
+        for (int c = 0; c < ch && c < 4; ++c) {
+            float v = loc[c];
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&sb[c], v);
+        }
+        __syncthreads();
+        if (threadIdx.x < ch && threadIdx.x < 4) atomicAdd(dbias + threadIdx.x, sb[threadIdx.x]);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// detector input transform (fp32 NCHW)
+// -------------------------------------------------------------------------------------------------
+__global__ void resize_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int c, int hi, int wi, int ho,
+                                  int wo, float sh, float sw, const float* mean, const float* stdv) {
+    const long total = static_cast<long>(n) * c * ho * wo;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int ow = static_cast<int>(i % wo), oh = static_cast<int>((i / wo) % ho);
+        const long bc = i / (static_cast<long>(wo) * ho);
+        const int ch = static_cast<int>(bc % c);
+        const int ih = nearest_src(oh, sh, hi), iw = nearest_src(ow, sw, wi);
+        float v = __ldg(x + (bc * hi + ih) * wi + iw);
+        if (mean) v = (v - mean[ch]) / stdv[ch];
+        y[i] = v;
+    }
+}
+
+__global__ void resize_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int n, int c, int hi, int wi, int ho,
+                                  int wo, float sh, float sw, const float* stdv, int accumulate) {
+    const long total = static_cast<long>(n) * c * hi * wi;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int iw = static_cast<int>(i % wi), ih = static_cast<int>((i / wi) % hi);
+        const long bc = i / (static_cast<long>(wi) * hi);
+        const int ch = static_cast<int>(bc % c);
+        int h_lo = static_cast<int>(ih / sh) - 2, w_lo = static_cast<int>(iw / sw) - 2;
+        if (h_lo < 0) h_lo = 0;
+        if (w_lo < 0) w_lo = 0;
+        float acc = 0.f;
+        for (int oh = h_lo; oh < ho; ++oh) {
+            const int s = nearest_src(oh, sh, hi);
+            if (s < ih) continue;
+            if (s > ih) break;
+            for (int ow = w_lo; ow < wo; ++ow) {
+                const int t = nearest_src(ow, sw, wi);
+                if (t < iw) continue;
+                if (t > iw) break;
+                acc += __ldg(dy + (bc * ho + oh) * wo + ow);
+            }
+        }
+        if (stdv) acc /= stdv[ch];
+        dx[i] = accumulate ? dx[i] + acc : acc;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// pixel regulariser (fused loss + gradient): warp-shuffle reduction, one atomic per block
+// -------------------------------------------------------------------------------------------------
+__global__ void regulariser_kernel(int kind, const float* __restrict__ hal, const float* __restrict__ rgb,
+                                   const float* __restrict__ ir, float w_rgb, float w_ir, int n, long plane, float* loss,
+                                   float* dhal, float grad_scale, int accumulate) {
+    const long total = static_cast<long>(n) * 3 * plane;
+    const float inv_n = 1.f / static_cast<float>(total);
+    float l_rgb = 0.f, l_ir = 0.f;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const long p = i % plane;
+        const int b = static_cast<int>(i / (3 * plane));
+        const float hv = hal[i];
+        float g = 0.f;
+        if (rgb) {
+            const float d = hv - __ldg(rgb + i);
+            if (kind == 0) { l_rgb += d * d; g += w_rgb * 2.f * d * inv_n; }
+            else { l_rgb += fabsf(d); g += w_rgb * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * inv_n; }
+        }
+        if (ir) {
+            const float d = hv - __ldg(ir + static_cast<long>(b) * plane + p);
+            if (kind == 0) { l_ir += d * d; g += w_ir * 2.f * d * inv_n; }
+            else { l_ir += fabsf(d); g += w_ir * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * inv_n; }
+        }
+        if (dhal) dhal[i] = accumulate ? dhal[i] + g * grad_scale : g * grad_scale;
+    }
+    __shared__ float s[2];
+    if (threadIdx.x < 2) s[threadIdx.x] = 0.f;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) {
+        l_rgb += __shfl_xor_sync(0xffffffffu, l_rgb, o);
+        l_ir += __shfl_xor_sync(0xffffffffu, l_ir, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s[0], l_rgb); atomicAdd(&s[1], l_ir); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(loss, s[0] * inv_n * w_rgb);
+        atomicAdd(loss + 1, s[1] * inv_n * w_ir);
+    }
+}
+
+}  // namespace hd
+
+using namespace hd;
+
+#define HD_LAUNCH_OK() HD_CUDA_OK(cudaPeekAtLastError())
+
+extern "C" int hd_pack_conv_weight(const float* w, const float* scale, int cout, int cin, int kh, int kw, void* w_fwd,
+                                   int cout_pad, int k_pad, void* w_dgrad, int cin_pad, void* w_t, hd_stream st) {
+    HD_CHECK_ARG(w != nullptr && cout > 0 && cin > 0 && kh > 0 && kw > 0);
+    HD_CHECK_ARG(cout_pad >= cout && k_pad >= kh * kw * cin && cin_pad >= cin);
+    const long work = static_cast<long>(cout_pad) * k_pad + (w_dgrad ? static_cast<long>(cin_pad) * kh * kw * cout : 0);
+    pack_weight_kernel<<<ew_blocks(work), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
+        w, scale, cout, cin, kh, kw, static_cast<__nv_bfloat16*>(w_fwd), cout_pad, k_pad,
+        static_cast<__nv_bfloat16*>(w_dgrad), cin_pad, static_cast<__nv_bfloat16*>(w_t));
+    HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_unpack_wgrad(const float* dw, float* g, int cout, int cin, int kh, int kw, int tap_stride, int row_stride,
+                               float scale, hd_stream st) {
+    HD_CHECK_ARG(dw && g && cout > 0 && cin > 0);
+    unpack_wgrad_kernel<<<ew_blocks(static_cast<long>(cout) * cin * kh * kw), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
+        dw, g, cout, cin, kh * kw, tap_stride, row_stride, scale);
+    HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_stem_im2col(const float* x, void* patches, int n, int h, int w, int k_pad, hd_stream st) {
+    HD_CHECK_ARG(x && patches && h % 2 == 0 && w % 2 == 0 && k_pad >= 152 && k_pad % 8 == 0);
+    stem_im2col_kernel<<<ew_blocks(static_cast<long>(n) * (h / 2) * (w / 2) * (k_pad / 8)), kEwThreads, 0,
+                         static_cast<cudaStream_t>(st)>>>(x, static_cast<__nv_bfloat16*>(patches), n, h, w, k_pad);
+    HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_stem_col2im(const void* dp, float* dx, int n, int h, int w, int k_pad, hd_stream st) {
+    HD_CHECK_ARG(dp && dx && h % 2 == 0 && w % 2 == 0);
+    stem_col2im_kernel<<<ew_blocks(static_cast<long>(n) * h * w), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
+        static_cast<const __nv_bfloat16*>(dp), dx, n, h, w, k_pad);
+    HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_bn_finalize(const float* stats, int reps, int C, double count, const float* gamma, const float* beta,
+                              float eps, float momentum, float* rm, float* rv, float* mean_out, float* invstd_out,
+                              float* scale_out, float* shift_out, hd_stream st) {
+    HD_CHECK_ARG(stats && gamma && beta && scale_out && shift_out && C > 0 && reps > 0 && count > 0);
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(st)>>>(stats, reps, C, count, gamma, beta, eps,
+                                                                                 momentum, rm, rv, mean_out, invstd_out,
+                                                                                 scale_out, shift_out);
+    HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_bn_apply(const void* z, const float* scale, const float* shift, const void* res, const float* rscale,
+                           const float* rshift, int relu, void* y, int64_t n_pix, int C, hd_stream st) {
+    HD_CHECK_ARG(z && scale && shift && y && C % 8 == 0 && n_pix > 0);
+    bn_apply_kernel<<<ew_blocks(n_pix * (C / 8)), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
+        static_cast<const __nv_bfloat16*>(z), scale, shift, static_cast<const __nv_bfloat16*>(res), rscale, rshift, relu,
+        static_cast<__nv_bfloat16*>(y), n_pix, C);
+    HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_bn_bwd_reduce(const void* dy, const void* yrelu, const void* z, const float* mean, const float* invstd,
+                                float* sums, int64_t n_pix, int C, hd_stream st) {
+    HD_CHECK_ARG(dy && z && mean && invstd && sums && C % 8 == 0 && C / 8 <= 256 && n_pix > 0);
+    const int G = C / 8;
+    int L = 256 / G;
+    if (L < 1) L = 1;
+    const int threads = G * L;
+    long blocks = 148L * 4;
+    long ppb = (n_pix + blocks - 1) / blocks;
+    if (ppb < L) ppb = L;
+    blocks = (n_pix + ppb - 1) / ppb;
+    bn_bwd_reduce_kernel<<<static_cast<int>(blocks), threads, 2 * C * sizeof(float), static_cast<cudaStream_t>(st)>>>(
+        static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(yrelu),
+        static_cast<const __nv_bfloat16*>(z), mean, invstd, sums, n_pix, C, ppb);
+    HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_bn_bwd_apply(const void* dy, const void* yrelu, const void* z, const float* mean, const float* invstd,
+                               const float* gamma, const float* sums, double count, void* dz, void* gout, float* dgamma,
+                               float* dbeta, int64_t n_pix, int C, hd_stream st) {
+    HD_CHECK_ARG(dy && z && mean && invstd && gamma && sums && dz && C % 8 == 0 && n_pix > 0 && count > 0);
+    bn_bwd_apply_kernel<<<ew_blocks(n_pix * (C / 8)), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
+        static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(yrelu),
+        static_cast<const __nv_bfloat16*>(z), mean, invstd, gamma, sums, static_cast<float>(1.0 / count),
+        static_cast<__nv_bfloat16*>(dz), static_cast<__nv_bfloat16*>(gout), dgamma, dbeta, n_pix, C);
+    HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_maxpool_fwd(const hd_act* x, const hd_act* y, hd_stream st) {
+    HD_CHECK_ARG(x && y && x->ptr && y->ptr && x->c % 8 == 0 && x->c == y->c && x->h % 2 == 0 && x->w % 2 == 0);
+    HD_CHECK_ARG(y->h == x->h / 2 && y->w == x->w / 2 && y->n == x->n);
+    maxpool_fwd_kernel<<<ew_blocks(static_cast<long>(y->n) * y->h * y->w * (y->c / 8)), kEwThreads, 0,
+                         static_cast<cudaStream_t>(st)>>>(static_cast<const __nv_bfloat16*>(x->ptr),
+                                                          static_cast<__nv_bfloat16*>(y->ptr), x->n, x->h, x->w, x->c);
+    HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_maxpool_bwd(const hd_act* x, const hd_act* y, const void* dy, const void* add, void* dx, int relu_mask,
+                              hd_stream st) {
+    HD_CHECK_ARG(x && y && x->ptr && y->ptr && dy && dx && x->c % 8 == 0 && x->c == y->c);
+    HD_CHECK_ARG(y->h == x->h / 2 && y->w == x->w / 2 && y->n == x->n);
+    maxpool_bwd_kernel<<<ew_blocks(static_cast<long>(x->n) * x->h * x->w * (x->c / 8)), kEwThreads, 0,
+                         static_cast<cudaStream_t>(st)>>>(
+        static_cast<const __nv_bfloat16*>(x->ptr), static_cast<const __nv_bfloat16*>(y->ptr),
+        static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(add), static_cast<__nv_bfloat16*>(dx),
+        x->n, x->h, x->w, x->c, relu_mask);
+    HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_upsample2x_fwd(const hd_act* x, const hd_act* y, hd_stream st) {
+    HD_CHECK_ARG(x && y && x->ptr && y->ptr && x->c == y->c && x->c % 8 == 0 && y->h == 2 * x->h && y->w == 2 * x->w && x->n == y->n);
+    upsample2x_fwd_kernel<<<ew_blocks(static_cast<long>(y->n) * y->h * y->w * (y->c / 8)), kEwThreads, 0,
+                            static_cast<cudaStream_t>(st)>>>(static_cast<const __nv_bfloat16*>(x->ptr),
+                                                             static_cast<__nv_bfloat16*>(y->ptr), y->n, y->h, y->w, y->c);
+    HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_upsample2x_bwd(const hd_act* dy, const hd_act* dx, hd_stream st) {
+    HD_CHECK_ARG(dy && dx && dy->ptr && dx->ptr && dx->c == dy->c && dx->c % 8 == 0 && dy->h == 2 * dx->h && dy->w == 2 * dx->w && dx->n == dy->n);
+    upsample2x_bwd_kernel<<<ew_blocks(static_cast<long>(dx->n) * dx->h * dx->w * (dx->c / 8)), kEwThreads, 0,
+                            static_cast<cudaStream_t>(st)>>>(static_cast<const __nv_bfloat16*>(dy->ptr),
+                                                             static_cast<__nv_bfloat16*>(dx->ptr), dx->n, dx->h, dx->w, dx->c);
+    HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_add_nearest_fwd(const hd_act* x, const hd_act* y, hd_stream st) {
+    HD_CHECK_ARG(x && y && x->ptr && y->ptr && x->c == y->c && x->c % 8 == 0 && x->n == y->n);
+    const float sh = static_cast<float>(x->h) / static_cast<float>(y->h), sw = static_cast<float>(x->w) / static_cast<float>(y->w);
+    add_nearest_fwd_kernel<<<ew_blocks(static_cast<long>(y->n) * y->h * y->w * (y->c / 8)), kEwThreads, 0,
+                             static_cast<cudaStream_t>(st)>>>(static_cast<const __nv_bfloat16*>(x->ptr),
+                                                              static_cast<__nv_bfloat16*>(y->ptr), y->n, x->h, x->w, y->h,
+                                                              y->w, y->c, sh, sw);
+    HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_add_nearest_bwd(const hd_act* dy, const hd_act* dx, int accumulate, hd_stream st) {
+    HD_CHECK_ARG(dy && dx && dy->ptr && dx->ptr && dx->c == dy->c && dx->c % 8 == 0 && dx->n == dy->n);
+    const float sh = static_cast<float>(dx->h) / static_cast<float>(dy->h), sw = static_cast<float>(dx->w) / static_cast<float>(dy->w);
+    add_nearest_bwd_kernel<<<ew_blocks(static_cast<long>(dx->n) * dx->h * dx->w * (dx->c / 8)), kEwThreads, 0,
+                             static_cast<cudaStream_t>(st)>>>(static_cast<const __nv_bfloat16*>(dy->ptr),
+                                                              static_cast<__nv_bfloat16*>(dx->ptr), dx->n, dx->h, dx->w,
+                                                              dy->h, dy->w, dx->c, sh, sw, accumulate);
+    HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_nchw_f32_to_nhwc_bf16(const float* x, const hd_act* y, int channels, hd_stream st) {
+    HD_CHECK_ARG(x && y && y->ptr && y->c % 8 == 0 && channels <= y->c && channels > 0);
+    nchw_to_nhwc_kernel<<<ew_blocks(static_cast<long>(y->n) * y->h * y->w * (y->c / 8)), kEwThreads, 0,
+                          static_cast<cudaStream_t>(st)>>>(x, static_cast<__nv_bfloat16*>(y->ptr), y->n, y->h, y->w, channels, y->c);
+    HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_nhwc_bf16_to_nchw_f32(const hd_act* x, float* y, int channels, hd_stream st) {
+    HD_CHECK_ARG(x && y && x->ptr && x->c % 8 == 0 && channels <= x->c && channels > 0);
+    nhwc_to_nchw_kernel<<<ew_blocks(static_cast<long>(x->n) * x->h * x->w * ((channels + 7) / 8)), kEwThreads, 0,
+                          static_cast<cudaStream_t>(st)>>>(static_cast<const __nv_bfloat16*>(x->ptr), y, x->n, x->h, x->w, x->c, channels);
+    HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_sigmoid_bwd_pack(const float* dhal, const float* hal, const hd_act* dl, int channels, float* dbias, hd_stream st) {
+    HD_CHECK_ARG(dhal && hal && dl && dl->ptr && dl->c == 16 && channels >= 1 && channels <= 4);
+    sigmoid_bwd_pack_kernel<<<ew_blocks(static_cast<long>(dl->n) * dl->h * dl->w), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
+        dhal, hal, static_cast<__nv_bfloat16*>(dl->ptr), dl->n, dl->h, dl->w, channels, dl->c, dbias);
+    HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_resize_nearest_fwd(const float* x, float* y, int n, int c, int hi, int wi, int ho, int wo, const float* mean,
+                                     const float* stdv, hd_stream st) {
+    HD_CHECK_ARG(x && y && n > 0 && c > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0 && ((mean == nullptr) == (stdv == nullptr)));
+    const float sh = static_cast<float>(hi) / static_cast<float>(ho), sw = static_cast<float>(wi) / static_cast<float>(wo);
+    resize_fwd_kernel<<<ew_blocks(static_cast<long>(n) * c * ho * wo), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
+        x, y, n, c, hi, wi, ho, wo, sh, sw, mean, stdv);
+    HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_resize_nearest_bwd(const float* dy, float* dx, int n, int c, int hi, int wi, int ho, int wo, const float* stdv,
+                                     int accumulate, hd_stream st) {
+    HD_CHECK_ARG(dy && dx && n > 0 && c > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0);
+    const float sh = static_cast<float>(hi) / static_cast<float>(ho), sw = static_cast<float>(wi) / static_cast<float>(wo);
+    resize_bwd_kernel<<<ew_blocks(static_cast<long>(n) * c * hi * wi), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
+        dy, dx, n, c, hi, wi, ho, wo, sh, sw, stdv, accumulate);
+    HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_regulariser(int kind, const float* hal, const float* rgb, const float* ir, float w_rgb, float w_ir, int n,
+                              int h, int w, float* loss, float* dhal, float grad_scale, int accumulate, hd_stream st) {
+    HD_CHECK_ARG((kind == 0 || kind == 1) && hal && loss && n > 0 && h > 0 && w > 0);
+    const long plane = static_cast<long>(h) * w;
+    long blocks = (static_cast<long>(n) * 3 * plane + kEwThreads * 8 - 1) / (kEwThreads * 8);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    regulariser_kernel<<<static_cast<int>(blocks), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
+        kind, hal, rgb, ir, w_rgb, w_ir, n, plane, loss, dhal, grad_scale, accumulate);
+    HD_LAUNCH_OK();
+    return HD_OK;
+}

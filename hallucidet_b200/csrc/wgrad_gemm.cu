@@ -1,0 +1,289 @@
+// wgrad_gemm.cu -- convolution weight-gradient on the sm_100a tensor cores.
+//
+//   dW[co][tap][ci] = sum_{n,ho,wo}  dY[n,ho,wo,co] * X_tap[n,ho,wo,ci]
+//
+// GEMM with M = output channels, N = input channels, K = pixels.  Both operands are "MN-major" in shared
+// memory exactly as TMA delivers an NHWC box ([pixel][channel], channel contiguous), so no transpose is
+// needed: the UMMA descriptors carry the major-ness.  One CTA = (filter tap, co tile, ci tile, pixel
+// range); the pixel range is the split-K dimension, partial sums are combined with vector fp32 reductions
+// (red.global.add.v4.f32) into the caller-zeroed dW buffer.  X_tap is the input box shifted by the tap
+// offset (TMA zero-fills the halo); stride-2 convolutions read X through the phase view used by the forward.
+//
+// warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2-5 = epilogue.
+// Replaces cuDNN's convolution backward-weights as reached from nn.Conv2d in the U-Net (a6 in SURVEY.md 8a).
+#include "hd_common.cuh"
+
+#include <cstring>
+
+namespace hd {
+
+constexpr int kWMaxTaps = 9;
+constexpr int kWThreads = 192;
+
+struct WgradParams {
+    CUtensorMap tmDY;
+    CUtensorMap tmX[2];
+    int TW, TH, tiles_w, tiles_h, total_tiles;
+    int KP;                       // pixels per stage (multiple of 16)
+    int M, ca, m_chunks;          // UMMA M (64/128), channel chunk of the dY boxes, chunks actually loaded
+    int BNt, cb;                  // ci tile, channel chunk of the X boxes
+    int Cout, Cin, C0;            // C0 = channels of source 0
+    int ci_tiles, splits;
+    int tap_dh[kWMaxTaps], tap_dw[kWMaxTaps], tap_p[kWMaxTaps], tap_q[kWMaxTaps];
+    int x_qstride[2];
+    int taps;
+    float* dw;
+    int stages, a_bytes, stage_bytes, tmem_cols;
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kWThreads) wgrad_gemm_kernel(const __grid_constant__ WgradParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int stages = P.stages;
+    const uint32_t bar_base = smem_base + static_cast<uint32_t>(stages * P.stage_bytes);
+    const uint32_t full0 = bar_base, empty0 = bar_base + 8u * stages, tfull = bar_base + 16u * stages;
+    const uint32_t tmem_slot = tfull + 8u;
+
+    const int tap = blockIdx.z;
+    const int co_tile = blockIdx.y / P.ci_tiles, ci_tile = blockIdx.y % P.ci_tiles;
+    const int co0 = co_tile * P.M, ci0 = ci_tile * P.BNt;
+    const long t_lo = static_cast<long>(P.total_tiles) * blockIdx.x / P.splits;
+    const long t_hi = static_cast<long>(P.total_tiles) * (blockIdx.x + 1) / P.splits;
+    const int num_k = static_cast<int>(t_hi - t_lo);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(full0 + 8u * s, 1);
+            mbar_init(empty0 + 8u * s, 1);
+        }
+        mbar_init(tfull, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&P.tmDY);
+        tma_prefetch_desc(&P.tmX[0]);
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, P.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int n_chunks = P.BNt / P.cb;
+    if (warp == 0) {
+        if (elect_one()) {
+            int nb = 0;                                        // X chunks inside the tensor
+            for (int j = 0; j < n_chunks; ++j) nb += (ci0 + j * P.cb < P.Cin) ? 1 : 0;
+            const uint32_t tx_bytes = static_cast<uint32_t>(P.KP * 2 * (P.m_chunks * P.ca + nb * P.cb));
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long t = t_lo; t < t_hi; ++t) {
+                const int tw_i = static_cast<int>(t % P.tiles_w);
+                const int th_i = static_cast<int>((t / P.tiles_w) % P.tiles_h);
+                const int img = static_cast<int>(t / (P.tiles_w * P.tiles_h));
+                const int w0 = tw_i * P.TW, h0 = th_i * P.TH;
+                mbar_wait(empty0 + 8u * stage, phase ^ 1u);
+                const uint32_t sa = smem_base + stage * P.stage_bytes;
+                const uint32_t sb = sa + P.a_bytes;
+                const uint32_t fb = full0 + 8u * stage;
+                mbar_expect_tx(fb, tx_bytes);
+                for (int i = 0; i < P.m_chunks; ++i)
+                    tma_load_5d(sa + i * P.KP * P.ca * 2, &P.tmDY, fb, co0 + i * P.ca, w0, 0, h0, img);
+                for (int j = 0; j < n_chunks; ++j) {
+                    const int cc = ci0 + j * P.cb;
+                    if (cc >= P.Cin) break;
+                    const int src = cc < P.C0 ? 0 : 1;
+                    const int c = (src ? cc - P.C0 : cc) + P.tap_q[tap] * P.x_qstride[src];
+                    tma_load_5d(sb + j * P.KP * P.cb * 2, &P.tmX[src], fb, c, w0 + P.tap_dw[tap], P.tap_p[tap],
+                                h0 + P.tap_dh[tap], img);
+                }
+                if (++stage == stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(P.M, P.BNt, 1, 1);
+            const uint32_t lta = swizzle_layout_type(P.ca * 2), ltb = swizzle_layout_type(P.cb * 2);
+            const uint32_t lbo_a = P.KP * P.ca * 2, sbo_a = 8 * P.ca * 2, kstep_a = 16 * P.ca * 2;
+            const uint32_t lbo_b = P.KP * P.cb * 2, sbo_b = 8 * P.cb * 2, kstep_b = 16 * P.cb * 2;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int ks = 0; ks < num_k; ++ks) {
+                mbar_wait(full0 + 8u * stage, phase);
+                tc_fence_after();
+                const uint32_t sa = smem_base + stage * P.stage_bytes;
+                const uint32_t sb = sa + P.a_bytes;
+                for (int k = 0; k < P.KP / 16; ++k) {
+                    const uint64_t da = make_smem_desc(sa + k * kstep_a, lbo_a, sbo_a, lta);
+                    const uint64_t db = make_smem_desc(sb + k * kstep_b, lbo_b, sbo_b, ltb);
+                    umma_bf16(tmem_base, da, db, idesc, (ks | k) != 0);
+                }
+                umma_commit(empty0 + 8u * stage);
+                if (++stage == stages) { stage = 0; phase ^= 1u; }
+            }
+            umma_commit(tfull);
+        }
+    } else if (num_k > 0) {
+        const int quad = warp & 3;
+        // M=128: row = TMEM lane; M=64: rows 16q..16q+15 live in lanes 0..15 of quadrant q
+        const int row = P.M == 128 ? quad * 32 + lane : quad * 16 + lane;
+        const bool row_ok = (P.M == 128 || lane < 16) && (co0 + row < P.Cout);
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        float* out_row = P.dw + (static_cast<long>(co0 + row) * P.taps + tap) * P.Cin;
+        for (int c16 = 0; c16 < P.BNt / 16; ++c16) {
+            uint32_t acc[16];
+            tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c16 * 16, acc);
+            tmem_ld_wait();
+            const int ci = ci0 + c16 * 16;
+            if (row_ok && ci < P.Cin) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    red_add_v4(out_row + ci + j, __uint_as_float(acc[j]), __uint_as_float(acc[j + 1]),
+                               __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3]));
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
+}
+
+static int wround_up(int a, int b) { return (a + b - 1) / b * b; }
+
+static int chunk_of(int c0, int c1) {
+    for (int c = 64; c >= 16; c >>= 1)
+        if (c0 % c == 0 && c1 % c == 0) return c;
+    return 0;
+}
+
+static int wact_map(CUtensorMap* m, const hd_act& t, bool phase_view, int box_c, int TW, int TH) {
+    uint64_t dims[5], str[4];
+    uint32_t box[5] = {static_cast<uint32_t>(box_c), static_cast<uint32_t>(TW), 1u, static_cast<uint32_t>(TH), 1u};
+    const uint64_t C = t.c, W = t.w, H = t.h;
+    if (!phase_view) {
+        dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = t.n;
+        str[0] = C * 2; str[1] = W * C * 2; str[2] = W * C * 2; str[3] = H * W * C * 2;
+    } else {
+        dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = t.n;
+        str[0] = 2 * C * 2; str[1] = W * C * 2; str[2] = 2 * W * C * 2; str[3] = H * W * C * 2;
+    }
+    return make_tensor_map(m, t.ptr, 5, dims, str, box, box_c * 2);
+}
+
+}  // namespace hd
+
+using namespace hd;
+
+extern "C" int hd_conv_wgrad(const hd_conv_args* a, hd_stream stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    HD_CHECK_ARG(a != nullptr && a->dw != nullptr);
+    const hd_act& x0 = a->x0;
+    const hd_act& dy = a->y0;
+    HD_CHECK_ARG(x0.ptr && dy.ptr && x0.c % 16 == 0 && dy.c % 16 == 0);
+    const bool two = a->x1.ptr != nullptr;
+    if (two) HD_CHECK_ARG(a->x1.c % 16 == 0 && a->x1.n == x0.n && a->x1.h == x0.h && a->x1.w == x0.w);
+    const int k = a->kh, s = a->stride;
+    HD_CHECK_ARG(a->kh == a->kw && (k == 1 || k == 3) && (s == 1 || s == 2));
+    const int pad = k / 2;
+    if (s == 2) HD_CHECK_ARG(x0.h % 2 == 0 && x0.w % 2 == 0);
+    const int Ho = x0.h / s, Wo = x0.w / s, N = x0.n;
+    HD_CHECK_ARG(dy.n == N && dy.h == Ho && dy.w == Wo);
+
+    WgradParams P;
+    memset(&P, 0, sizeof(P));
+    P.Cout = dy.c;
+    P.C0 = x0.c;
+    P.Cin = x0.c + (two ? a->x1.c : 0);
+    P.taps = k * k;
+    P.M = P.Cout >= 128 ? 128 : 64;
+    P.ca = chunk_of(P.Cout, P.Cout);
+    P.cb = chunk_of(x0.c, two ? a->x1.c : x0.c);
+    HD_CHECK_ARG(P.ca && P.cb);
+    {
+        const int want = P.M / P.ca, have = (P.Cout + P.ca - 1) / P.ca;
+        P.m_chunks = want < have ? want : have;
+    }
+    P.BNt = P.Cin >= 128 ? 128 : wround_up(P.Cin, P.cb);
+    P.ci_tiles = (P.Cin + P.BNt - 1) / P.BNt;
+    const int co_tiles = (P.Cout + P.M - 1) / P.M;
+
+    // pixel box: TW*TH a multiple of 16, <= 128, maximise useful pixels
+    {
+        double best = -1.0;
+        int bw = 128, bh = 1;
+        for (int tw = 1; tw <= 128; ++tw)
+            for (int th = 1; tw * th <= 128; ++th) {
+                if ((tw * th) % 16 != 0 || tw * th < 64) continue;
+                const long tiles = static_cast<long>((Wo + tw - 1) / tw) * ((Ho + th - 1) / th);
+                const double eff = static_cast<double>(Ho) * Wo / (static_cast<double>(tiles) * tw * th);
+                const double score = eff + 1e-4 * tw * th / 128.0 + 1e-6 * tw;
+                if (score > best) { best = score; bw = tw; bh = th; }
+            }
+        P.TW = bw; P.TH = bh;
+    }
+    P.KP = P.TW * P.TH;
+    P.tiles_w = (Wo + P.TW - 1) / P.TW;
+    P.tiles_h = (Ho + P.TH - 1) / P.TH;
+    P.total_tiles = P.tiles_w * P.tiles_h * N;
+
+    int t = 0;
+    for (int r = 0; r < k; ++r)
+        for (int c = 0; c < k; ++c, ++t) {
+            const int eh = r - pad, ew = c - pad;
+            if (s == 1) {
+                P.tap_dh[t] = eh; P.tap_dw[t] = ew;
+            } else {
+                const int p = eh & 1, q = ew & 1;
+                P.tap_p[t] = p; P.tap_q[t] = q;
+                P.tap_dh[t] = (eh - p) / 2; P.tap_dw[t] = (ew - q) / 2;
+            }
+        }
+    P.x_qstride[0] = x0.c; P.x_qstride[1] = two ? a->x1.c : 0;
+    P.dw = a->dw;
+
+    P.a_bytes = wround_up(P.KP * P.M * 2, 1024);
+    P.stage_bytes = P.a_bytes + wround_up(P.KP * P.BNt * 2, 1024);
+    int stages = (190 * 1024) / P.stage_bytes;
+    if (stages > 6) stages = 6;
+    if (stages < 2) stages = 2;
+    P.stages = stages;
+    int cols = 32;
+    while (cols < P.BNt) cols *= 2;
+    P.tmem_cols = cols;
+
+    const int units = P.taps * co_tiles * P.ci_tiles;
+    int splits = a->split_k;
+    if (splits <= 0) {
+        splits = (2 * 148 + units - 1) / units;
+        const int max_by_work = P.total_tiles / 4 > 0 ? P.total_tiles / 4 : 1;
+        if (splits > max_by_work) splits = max_by_work;
+    }
+    if (splits > P.total_tiles) splits = P.total_tiles;
+    if (splits < 1) splits = 1;
+    P.splits = splits;
+
+    if (wact_map(&P.tmDY, dy, false, P.ca, P.TW, P.TH)) return HD_ERR_CUDA;
+    if (wact_map(&P.tmX[0], x0, s == 2, P.cb, P.TW, P.TH)) return HD_ERR_CUDA;
+    if (two) { if (wact_map(&P.tmX[1], a->x1, s == 2, P.cb, P.TW, P.TH)) return HD_ERR_CUDA; }
+    else P.tmX[1] = P.tmX[0];
+
+    const size_t smem = 1024 + static_cast<size_t>(stages) * P.stage_bytes + 16 * stages + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        HD_CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+        attr_set = true;
+    }
+    dim3 grid(splits, co_tiles * P.ci_tiles, P.taps);
+    wgrad_gemm_kernel<<<grid, kWThreads, smem, stream>>>(P);
+    HD_CUDA_OK(cudaPeekAtLastError());
+    return HD_OK;
+}

@@ -1,0 +1,153 @@
+/* hallucidet_b200.h -- C ABI of libhallucidet_b200.so (sm_100a only).
+ *
+ * Drop-in boundary for the HalluciDet hot path: the reference is pure Python and
+ * reaches its arithmetic through ATen/cuDNN operators; each entry point below replaces the operator the
+ * reference's modules call at the cited site (paths relative to the reference repo; "TV:" = torchvision).
+ * There is no CPU fallback: every compute entry point returns HD_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers owned by the caller (PyTorch's allocator); the library never
+ *     allocates, frees or retains them past the call; all work is enqueued on `stream`, no host sync;
+ *   - activations: NHWC bf16, channel count a multiple of 16, base 16-byte aligned (hd_act);
+ *   - module-edge tensors: NCHW fp32 (what the reference's modules exchange);
+ *   - return value: 0 (HD_OK) or a negative hd_status; hd_last_error() gives a thread-local message.
+ */
+#ifndef HALLUCIDET_B200_H
+#define HALLUCIDET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* hd_stream; /* cudaStream_t */
+
+typedef enum hd_status {
+    HD_OK = 0,
+    HD_ERR_BAD_ARG = -1,   /* shape / alignment / unsupported configuration */
+    HD_ERR_CUDA = -2,      /* CUDA runtime or driver error (incl. no device, wrong arch) */
+    HD_ERR_UNSUPPORTED = -3
+} hd_status;
+
+/* NHWC bf16 activation tensor [n][h][w][c], c contiguous. */
+typedef struct hd_act {
+    void* ptr;
+    int32_t n, h, w, c;
+} hd_act;
+
+/* ---- library ------------------------------------------------------------------------------------ */
+int hd_version(void);                 /* ABI version (1) */
+const char* hd_last_error(void);      /* message of the last failing call on this thread */
+int hd_device_ok(void);               /* HD_OK iff the current device is sm_100 */
+
+/* ---- convolution as implicit GEMM on tcgen05 -------------------------------------------------------
+ * Replaces nn.Conv2d forward / input-gradient / weight-gradient (cuDNN) at
+ *   src/segmentation_models/base/modules.py:29-36 (Conv2dReLU conv), base/heads.py:24 (head conv),
+ *   TV: models/resnet.py:59-105,108-163 (BasicBlock / Bottleneck convs), TV: ops/feature_pyramid_network.py:91-96.
+ * Supported (kh,kw,stride): (1,1,1) (3,3,1) (1,1,2) (3,3,2); padding = k/2; dilation 1; groups 1.
+ * The input may be the channel-concatenation of two tensors (x0 | x1) -- the U-Net skip concat
+ * (decoders/unet/decoder.py:41) without materialising it; the dgrad output may be split the same way (y0 | y1).
+ */
+typedef struct hd_conv_args {
+    hd_act x0, x1;            /* fwd: input (x1.ptr NULL if unused).  dgrad: x0 = dY.  wgrad: input X */
+    hd_act y0, y1;            /* fwd: output.  dgrad: dX (optionally split).  wgrad: y0 = dY (y1 unused) */
+    const void* w;            /* fwd: bf16 [cout_pad][kh*kw*cin]; dgrad: bf16 [cin_pad][kh*kw*cout]; wgrad: unused */
+    int32_t kh, kw, stride;
+    /* epilogue (fwd / dgrad), applied in this order: +bias, +add, relu, mask, stats, stores */
+    const float* bias;        /* [channels of y] or NULL */
+    const void* add;          /* bf16 NHWC tensor shaped like y0 (single-output only), may alias y0.ptr (in-place) */
+    const void* mask;         /* bf16 NHWC tensor shaped like y0: result zeroed where mask <= 0 (ReLU backward) */
+    int32_t relu;
+    int32_t sigmoid;          /* applied to the fp32 NCHW output only */
+    float* stats;             /* fp32 [stats_replicas][2][channels]: per-channel sum / sum-of-squares of the (bf16-rounded) output, accumulated with atomics; NULL = off */
+    int32_t stats_replicas;
+    float* out_f32_nchw;      /* optional fp32 NCHW copy of the output (first out_f32_channels channels) */
+    int32_t out_f32_channels;
+    int32_t store_bf16;       /* 1: write y0/y1 (bf16 NHWC); 0: only out_f32_nchw */
+    int32_t phase_mask;       /* dgrad stride 2 only: bit (2*p+q) set = compute output phase (row parity p, col parity q); 0 = all */
+    /* wgrad only */
+    float* dw;                /* fp32 [cout][kh*kw][cin] accumulated with atomics (caller zeroes) */
+    int32_t split_k;          /* 0 = auto */
+} hd_conv_args;
+
+int hd_conv_fwd(const hd_conv_args* a, hd_stream stream);
+int hd_conv_dgrad(const hd_conv_args* a, hd_stream stream);
+int hd_conv_wgrad(const hd_conv_args* a, hd_stream stream);
+
+/* Weight packing (once per optimizer step for the U-Net, once at load for the frozen detector).
+ * w_oihw fp32 [cout][cin][kh][kw] (the reference's parameter layout); scale: optional per-cout multiplier
+ * (frozen / eval BatchNorm fold, TV: ops/misc.py:54-63).  Any output pointer may be NULL.
+ *   w_fwd   bf16 [cout_pad][k_pad]          k = (r*kw+s)*cin + ci          (zero padded)
+ *   w_dgrad bf16 [cin_pad ][kh*kw*cout]     k = (r*kw+s)*cout + co
+ *   w_t     bf16 [k_pad  ][cout_pad]        transpose of w_fwd (stem col2im GEMM)
+ */
+int hd_pack_conv_weight(const float* w_oihw, const float* scale, int cout, int cin, int kh, int kw,
+                        void* w_fwd, int cout_pad, int k_pad, void* w_dgrad, int cin_pad, void* w_t, hd_stream stream);
+/* dw_packed[co*row_stride + tap*tap_stride + ci] -> grad fp32 OIHW [cout][cin][kh][kw], multiplied by `scale`.
+ * hd_conv_wgrad output: tap_stride = cin, row_stride = kh*kw*cin; stem GEMM output [cout][k_pad]: tap_stride = cin, row_stride = k_pad. */
+int hd_unpack_wgrad(const float* dw_packed, float* grad_oihw, int cout, int cin, int kh, int kw, int tap_stride,
+                    int row_stride, float scale, hd_stream stream);
+
+/* ---- stem 7x7 stride-2 pad-3 conv via explicit patches (cin = 3 is not TMA-addressable) --------------
+ * Replaces encoder.conv1 (encoders/resnet.py:50) and body.conv1 (TV: models/resnet.py:197) im2col/col2im.
+ * x fp32 NCHW [n][3][h][w] -> patches bf16 [n*ho*wo][k_pad], k = (r*7+s)*3 + c, ho = h/2, wo = w/2. */
+int hd_stem_im2col(const float* x_nchw, void* patches, int n, int h, int w, int k_pad, hd_stream stream);
+/* dpatches bf16 [n*ho*wo][k_pad] -> dx fp32 NCHW [n][3][h][w] (overwrites). */
+int hd_stem_col2im(const void* dpatches, float* dx_nchw, int n, int h, int w, int k_pad, hd_stream stream);
+
+/* ---- train-mode BatchNorm2d (U-Net; base/modules.py:42, TV: models/resnet.py:80-83) --------------------
+ * stats -> per-channel scale/shift (+ running-stat update, momentum/unbiased var as nn.BatchNorm2d). */
+int hd_bn_finalize(const float* stats, int stats_replicas, int channels, double count, const float* gamma,
+                   const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                   float* mean_out, float* invstd_out, float* scale_out, float* shift_out, hd_stream stream);
+/* y = relu?( z*scale+shift + (res ? (res_scale ? res*res_scale+res_shift : res) : 0) ), all bf16 NHWC, n_pix pixels. */
+int hd_bn_apply(const void* z, const float* scale, const float* shift, const void* res, const float* res_scale,
+                const float* res_shift, int relu, void* y, int64_t n_pix, int channels, hd_stream stream);
+/* Backward, pass 1: with g = dy * (y>0 if relu_y given) : sums[0][c] = sum g, sums[1][c] = sum g*xhat (atomics; caller zeroes). */
+int hd_bn_bwd_reduce(const void* dy, const void* y_relu, const void* z, const float* mean, const float* invstd,
+                     float* sums, int64_t n_pix, int channels, hd_stream stream);
+/* Backward, pass 2: dz = gamma*invstd*(g - sums0/count - xhat*sums1/count); optional g_out = g (masked dy);
+ * dgamma = sums1, dbeta = sums0 are written (fp32, scaled by grad_scale) when non-NULL. */
+int hd_bn_bwd_apply(const void* dy, const void* y_relu, const void* z, const float* mean, const float* invstd,
+                    const float* gamma, const float* sums, double count, void* dz, void* g_out, float* dgamma,
+                    float* dbeta, int64_t n_pix, int channels, hd_stream stream);
+
+/* ---- memory-bound glue ------------------------------------------------------------------------------ */
+/* MaxPool2d(3,2,1) after the stem ReLU (encoders/resnet.py:51, TV: models/resnet.py:199). */
+int hd_maxpool_fwd(const hd_act* x, const hd_act* y, hd_stream stream);
+/* dx = (add ? add : 0) + scatter of dy to the arg-max taps (first max in window order, as ATen); optional ReLU mask. */
+int hd_maxpool_bwd(const hd_act* x, const hd_act* y, const void* dy, const void* add, void* dx, int relu_mask, hd_stream stream);
+/* Nearest upsample x2 (decoders/unet/decoder.py:7-8): y[h][w] = x[h/2][w/2]; backward = 2x2 sum. */
+int hd_upsample2x_fwd(const hd_act* x, const hd_act* y, hd_stream stream);
+int hd_upsample2x_bwd(const hd_act* dy, const hd_act* dx, hd_stream stream);
+/* FPN top-down (TV: ops/feature_pyramid_network.py:193-196): y += nearest_resize(x to y's size); backward dx = gather-sum(dy). */
+int hd_add_nearest_fwd(const hd_act* x, const hd_act* y, hd_stream stream);
+int hd_add_nearest_bwd(const hd_act* dy, const hd_act* dx, int accumulate, hd_stream stream);
+/* Layout / dtype converters at the module edges. */
+int hd_nchw_f32_to_nhwc_bf16(const float* x, const hd_act* y, int channels, hd_stream stream);
+int hd_nhwc_bf16_to_nchw_f32(const hd_act* x, float* y, int channels, hd_stream stream);
+/* Segmentation head backward prologue: dlogits = dhal * hal * (1-hal) (fp32 NCHW [n][3][h][w]) -> bf16 NHWC, c = 16 (zero padded);
+ * dbias[c] += sum (atomics, caller zeroes). */
+int hd_sigmoid_bwd_pack(const float* dhal, const float* hal, const hd_act* dlogits, int channels, float* dbias, hd_stream stream);
+
+/* ---- detector input transform (src/models/custom_generalized_transform.py:136-186, 52-100, 256-274) ------
+ * y[b][c][i][j] = (x[b][c][src(i)][src(j)] - mean[c]) / std[c], src(d) = min(floor(d * fp32(in/out)), in-1). */
+int hd_resize_nearest_fwd(const float* x, float* y, int n, int c, int h_in, int w_in, int h_out, int w_out,
+                          const float* mean, const float* std, hd_stream stream);
+/* dx = sum of dy over the output pixels that sampled each input pixel, divided by std[c]; overwrites dx (or accumulates). */
+int hd_resize_nearest_bwd(const float* dy, float* dx, int n, int c, int h_in, int w_in, int h_out, int w_out,
+                          const float* std, int accumulate, hd_stream stream);
+
+/* ---- hallucination regulariser (src/losses/losses.py:28-48; train_hallucidet.py:173-176) -----------------
+ * kind 0 = MSE, 1 = L1.  loss[0] += w_rgb*pixel(rgb,hal), loss[1] += w_ir*pixel(ir3,hal) (mean over n*3*h*w; caller zeroes),
+ * dhal (fp32 NCHW, may be NULL) receives (accumulate ? += : =) the gradient of (loss[0]+loss[1]) * grad_scale.
+ * ir is [n][1][h][w] (broadcast to 3 channels, src/utils/utils.py:52-53); rgb/hal are [n][3][h][w]. */
+int hd_regulariser(int kind, const float* hal, const float* rgb, const float* ir, float w_rgb, float w_ir,
+                   int n, int h, int w, float* loss, float* dhal, float grad_scale, int accumulate, hd_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HALLUCIDET_B200_H */
