@@ -156,8 +156,13 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
         tc_fence_after();
         for (int c16 = 0; c16 < P.BN / 16; ++c16) {
             uint32_t acc[16];
-            tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c16 * 16, acc);
-            tmem_ld_wait();
+            if (num_k > 0) {
+                tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c16 * 16, acc);
+                tmem_ld_wait();
+            } else {                                       // phase without filter taps: epilogue-only (add / mask)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] = 0u;
+            }
             const int ch0 = n0 + c16 * 16;
             float v[16];
 #pragma unroll
@@ -472,7 +477,8 @@ extern "C" int hd_conv_dgrad(const hd_conv_args* a, hd_stream stream_) {
                         ++t;
                     }
                 }
-                if (t == t0) continue;                     // no tap reaches this phase (1x1 stride 2)
+                if (t == t0 && a->mask == nullptr) continue;   // no tap reaches this phase (1x1 stride 2): nothing to do
+                                                               // unless a mask must still be applied to the accumulated tensor
                 P.tap_begin[nph] = t0; P.tap_begin[nph + 1] = t;
                 P.out_p[nph] = p; P.out_q[nph] = q;
                 ++nph;

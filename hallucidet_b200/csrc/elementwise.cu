@@ -530,7 +530,7 @@ __global__ void add_nearest_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __n
 // layout converters
 // -------------------------------------------------------------------------------------------------
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int h, int w, int Cs,
-                                    int Cd) {
+                                    int Cd, int accumulate) {
     // thread = (pixel, 8-channel group); consecutive threads -> consecutive pixels (coalesced fp32 reads)
     const int G = Cd / 8;
     const long plane = static_cast<long>(h) * w;
@@ -547,6 +547,13 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* 
             f[j] = c < Cs ? __ldg(x + (static_cast<long>(b) * Cs + c) * plane + p) : 0.f;
         }
         bf8 o;
+        if (accumulate) {
+            o.load(y + (static_cast<long>(b) * plane + p) * Cd + g * 8);
+            float old[8];
+            o.unpack(old);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += old[j];
+        }
         o.pack(f);
         o.store(y + (static_cast<long>(b) * plane + p) * Cd + g * 8);
     }
@@ -858,10 +865,10 @@ extern "C" int hd_add_nearest_bwd(const hd_act* dy, const hd_act* dx, int accumu
     return HD_OK;
 }
 
-extern "C" int hd_nchw_f32_to_nhwc_bf16(const float* x, const hd_act* y, int channels, hd_stream st) {
+extern "C" int hd_nchw_f32_to_nhwc_bf16(const float* x, const hd_act* y, int channels, int accumulate, hd_stream st) {
     HD_CHECK_ARG(x && y && y->ptr && y->c % 8 == 0 && channels <= y->c && channels > 0);
     nchw_to_nhwc_kernel<<<ew_blocks(static_cast<long>(y->n) * y->h * y->w * (y->c / 8)), kEwThreads, 0,
-                          static_cast<cudaStream_t>(st)>>>(x, static_cast<__nv_bfloat16*>(y->ptr), y->n, y->h, y->w, channels, y->c);
+                          static_cast<cudaStream_t>(st)>>>(x, static_cast<__nv_bfloat16*>(y->ptr), y->n, y->h, y->w, channels, y->c, accumulate);
     HD_LAUNCH_OK();
     return HD_OK;
 }

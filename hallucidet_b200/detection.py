@@ -1,0 +1,209 @@
+"""Host-side mirror of the reference's detector glue, so the hot path has its caller on a box where the
+reference repository is absent (bench / smoke / tests).  Same names, arguments and behaviour as
+
+  src/models/detector.py:25-66,104-141          Detector (2-class re-heading, fixed-size transform, calculate_loss)
+  src/utils/eval_forward_fasterrcnn.py:13-147   eval_forward_fasterrcnn / rpn_eval / roi_heads_eval
+  src/utils/eval_forward_retinanet.py:22-244    eval_forward_retinanet and its losses
+
+The RPN / RoI heads / RetinaNet head, anchor generator, matcher, samplers, box coder and the losses are
+torchvision's own objects ("stay as the reference implements them"); only ``model.transform`` and
+``model.backbone`` are the B200 modules.
+"""
+import math
+from collections import OrderedDict
+
+import torch
+import torch.nn.functional as F
+import torchvision
+from torchvision.models.detection.roi_heads import fastrcnn_loss
+from torchvision.models.detection.rpn import concat_box_prediction_layers
+
+from .backbone import FrozenBackbone
+from .transform import GeneralizedRCNNTransform
+
+
+def _xavier_init(module):
+    for layer in module.modules():
+        if isinstance(layer, torch.nn.Conv2d):
+            torch.nn.init.xavier_uniform_(layer.weight)
+            if layer.bias is not None:
+                torch.nn.init.constant_(layer.bias, 0.0)
+
+
+class Detector:
+    """src/models/detector.py:23-79 with random-init weights unless a state dict is loaded afterwards."""
+
+    def __init__(self, name="fasterrcnn_resnet50_fpn", pretrained=False, n_classes=2, size=300, eval_path=None, b200=True):
+        self.detector = Detector.select_detector(detector_name=name, pretrained=pretrained)
+        self.detector.transform = GeneralizedRCNNTransform(min_size=size, max_size=size, image_mean=[0.0], image_std=[1.0],
+                                                           size_divisible=1, fixed_size=(size, size))
+        if "fasterrcnn" in name:
+            in_features = self.detector.roi_heads.box_predictor.cls_score.in_features
+            self.detector.roi_heads.box_predictor = torchvision.models.detection.faster_rcnn.FastRCNNPredictor(in_features, n_classes)
+            _xavier_init(self.detector.roi_heads)
+        elif "retinanet" in name:
+            out_channels = self.detector.head.classification_head.conv[0].out_channels
+            num_anchors = self.detector.head.classification_head.num_anchors
+            self.detector.head.classification_head.num_classes = n_classes
+            cls_logits = torch.nn.Conv2d(out_channels, num_anchors * n_classes, kernel_size=3, stride=1, padding=1)
+            torch.nn.init.normal_(cls_logits.weight, std=0.01)
+            torch.nn.init.constant_(cls_logits.bias, -math.log((1 - 0.01) / 0.01))
+            self.detector.head.classification_head.cls_logits = cls_logits
+        if eval_path is not None:
+            self.detector.load_state_dict(torch.load(eval_path))
+
+    @staticmethod
+    def select_detector(detector_name="fasterrcnn_resnet50_fpn", pretrained=False):
+        if pretrained:
+            raise NotImplementedError("no network: load a detector state dict instead of pretrained=True")
+        if "retinanet" in detector_name:
+            return torchvision.models.detection.retinanet_resnet50_fpn(weights=None, weights_backbone=None)
+        if "fasterrcnn" in detector_name:
+            return torchvision.models.detection.fasterrcnn_resnet50_fpn(weights=None, weights_backbone=None)
+        raise NotImplementedError(f"{detector_name}: the B200 hot path covers fasterrcnn and retinanet")
+
+    @staticmethod
+    def calculate_loss(detector, outs, targets, train_det=False, model_name="fasterrcnn"):
+        if "fasterrcnn" in model_name:
+            return eval_forward_fasterrcnn(detector, outs, targets, train_det=train_det, model_name=model_name)
+        if "retinanet" in model_name:
+            return eval_forward_retinanet(detector, outs, targets, train_det=train_det, model_name=model_name)
+        raise NotImplementedError(model_name)
+
+
+def install_b200_backbone(detector):
+    """Freeze the detector and replace ``detector.backbone`` by the B200 dgrad-only module (call AFTER weights are loaded)."""
+    detector.eval()
+    for p in detector.parameters():
+        p.requires_grad_(False)
+    if not isinstance(detector.backbone, FrozenBackbone):
+        detector.backbone = FrozenBackbone.from_torchvision(detector.backbone)
+    return detector
+
+
+def _check_targets(targets):
+    for target in targets:
+        boxes = target["boxes"]
+        torch._assert(isinstance(boxes, torch.Tensor), f"Expected target boxes to be of type Tensor, got {type(boxes)}.")
+        torch._assert(len(boxes.shape) == 2 and boxes.shape[-1] == 4,
+                      f"Expected target boxes to be a tensor of shape [N, 4], got {boxes.shape}.")
+
+
+def rpn_eval(model, images, features, targets):
+    features = list(features.values())
+    objectness, pred_bbox_deltas = model.rpn.head(features)
+    anchors = model.rpn.anchor_generator(images, features)
+    num_images = len(anchors)
+    num_anchors_per_level = [o[0].shape[0] * o[0].shape[1] * o[0].shape[2] for o in objectness]
+    objectness, pred_bbox_deltas = concat_box_prediction_layers(objectness, pred_bbox_deltas)
+    proposals = model.rpn.box_coder.decode(pred_bbox_deltas.detach(), anchors)
+    proposals = proposals.view(num_images, -1, 4)
+    boxes, scores = model.rpn.filter_proposals(proposals, objectness, images.image_sizes, num_anchors_per_level)
+    if targets is None:
+        raise ValueError("targets should not be None")
+    labels, matched_gt_boxes = model.rpn.assign_targets_to_anchors(anchors, targets)
+    regression_targets = model.rpn.box_coder.encode(matched_gt_boxes, anchors)
+    loss_objectness, loss_rpn_box_reg = model.rpn.compute_loss(objectness, pred_bbox_deltas, labels, regression_targets)
+    return boxes, {"loss_objectness": loss_objectness, "loss_rpn_box_reg": loss_rpn_box_reg}
+
+
+def roi_heads_eval(model, features, proposals, image_shapes, targets=None, train_det=False):
+    for t in targets:
+        if t["boxes"].dtype not in (torch.float, torch.double, torch.half):
+            raise TypeError(f"target boxes must of float type, instead got {t['boxes'].dtype}")
+        if t["labels"].dtype != torch.int64:
+            raise TypeError(f"target labels must of int64 type, instead got {t['labels'].dtype}")
+    proposals, matched_idxs, labels, regression_targets = model.roi_heads.select_training_samples(proposals, targets)
+    box_features = model.roi_heads.box_roi_pool(features, proposals, image_shapes)
+    box_features = model.roi_heads.box_head(box_features)
+    class_logits, box_regression = model.roi_heads.box_predictor(box_features)
+    loss_classifier, loss_box_reg = fastrcnn_loss(class_logits, box_regression, labels, regression_targets)
+    losses = {"loss_classifier": loss_classifier, "loss_box_reg": loss_box_reg}
+    boxes, scores, labels = model.roi_heads.postprocess_detections(class_logits, box_regression, proposals, image_shapes)
+    result = [{"boxes": boxes[i], "labels": labels[i], "scores": scores[i]} for i in range(len(boxes))]
+    return result, losses
+
+
+def eval_forward_fasterrcnn(model, images, targets, train_det=False, model_name="fasterrcnn"):
+    if not train_det:
+        model.eval()
+    _check_targets(targets)
+    original_image_sizes = [tuple(img.shape[-2:]) for img in images]
+    images, targets = model.transform(images, targets)
+    for target_idx, target in enumerate(targets):
+        boxes = target["boxes"]
+        degenerate_boxes = boxes[:, 2:] <= boxes[:, :2]
+        if degenerate_boxes.any():
+            bb_idx = torch.where(degenerate_boxes.any(dim=1))[0][0]
+            torch._assert(False, "All bounding boxes should have positive height and width."
+                                 f" Found invalid box {boxes[bb_idx].tolist()} for target at index {target_idx}.")
+    features = model.backbone(images.tensors)
+    if isinstance(features, torch.Tensor):
+        features = OrderedDict([("0", features)])
+    proposals, proposal_losses = rpn_eval(model, images, features, targets)
+    detections, detector_losses = roi_heads_eval(model, features, proposals, images.image_sizes, targets)
+    detections = model.transform.postprocess(detections, images.image_sizes, original_image_sizes)
+    losses = {}
+    losses.update(detector_losses)
+    losses.update(proposal_losses)
+    return losses, detections
+
+
+def sigmoid_focal_loss(inputs, targets, alpha=0.25, gamma=2, reduction="none"):
+    p = torch.sigmoid(inputs)
+    ce_loss = F.binary_cross_entropy_with_logits(inputs, targets, reduction="none")
+    p_t = p * targets + (1 - p) * (1 - targets)
+    loss = ce_loss * ((1 - p_t) ** gamma)
+    if alpha >= 0:
+        loss = (alpha * targets + (1 - alpha) * (1 - targets)) * loss
+    if reduction == "mean":
+        return loss.mean()
+    if reduction == "sum":
+        return loss.sum()
+    return loss
+
+
+def compute_retinanet_loss(targets, head_outputs, anchors, model):
+    matched_idxs = []
+    for anchors_per_image, targets_per_image in zip(anchors, targets):
+        if targets_per_image["boxes"].numel() == 0:
+            matched_idxs.append(torch.full((anchors_per_image.size(0),), -1, dtype=torch.int64, device=anchors_per_image.device))
+            continue
+        matched_idxs.append(model.proposal_matcher(torchvision.ops.box_iou(targets_per_image["boxes"], anchors_per_image)))
+    cls_losses, reg_losses = [], []
+    for t, logits, reg, anc, midx in zip(targets, head_outputs["cls_logits"], head_outputs["bbox_regression"], anchors, matched_idxs):
+        fg = midx >= 0
+        num_fg = fg.sum()
+        gt = torch.zeros_like(logits)
+        gt[fg, t["labels"][midx[fg]]] = 1.0
+        valid = midx != model.head.classification_head.BETWEEN_THRESHOLDS
+        cls_losses.append(sigmoid_focal_loss(logits[valid], gt[valid], reduction="sum") / max(1, num_fg))
+        fg_idx = torch.where(fg)[0]
+        target_regression = model.box_coder.encode_single(t["boxes"][midx[fg_idx]], anc[fg_idx, :])
+        reg_losses.append(F.smooth_l1_loss(reg[fg_idx, :], target_regression, reduction="sum", beta=1.0) / max(1, fg_idx.numel()))
+    return {"classification": sum(cls_losses[1:], cls_losses[0]) / len(targets),
+            "bbox_regression": sum(reg_losses[1:], reg_losses[0]) / max(1, len(targets))}
+
+
+def eval_forward_retinanet(model, images, targets, train_det=False, model_name="retinanet"):
+    if not train_det:
+        model.eval()
+    _check_targets(targets)
+    original_image_sizes = [tuple(img.shape[-2:]) for img in images]
+    images, targets = model.transform(images, targets)
+    features = model.backbone(images.tensors)
+    if isinstance(features, torch.Tensor):
+        features = OrderedDict([("0", features)])
+    features = list(features.values())
+    head_outputs = model.head(features)
+    anchors = model.anchor_generator(images, features)
+    losses = compute_retinanet_loss(targets, head_outputs, anchors, model)
+    num_anchors_per_level = [x.size(2) * x.size(3) for x in features]
+    hw = sum(num_anchors_per_level)
+    a = head_outputs["cls_logits"].size(1) // hw
+    num_anchors_per_level = [n * a for n in num_anchors_per_level]
+    split_head_outputs = {k: list(v.split(num_anchors_per_level, dim=1)) for k, v in head_outputs.items()}
+    split_anchors = [list(x.split(num_anchors_per_level)) for x in anchors]
+    detections = model.postprocess_detections(split_head_outputs, split_anchors, images.image_sizes)
+    detections = model.transform.postprocess(detections, images.image_sizes, original_image_sizes)
+    return losses, detections

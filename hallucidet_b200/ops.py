@@ -163,10 +163,11 @@ def add_nearest_bwd(dy, dx, accumulate=False):
     check(_lib.load().hd_add_nearest_bwd(ctypes.byref(ay), ctypes.byref(ax), int(accumulate), _stream()), "hd_add_nearest_bwd")
 
 
-def nchw_f32_to_nhwc_bf16(x, y):
+def nchw_f32_to_nhwc_bf16(x, y, accumulate=False):
     assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[0] == y.shape[0] and x.shape[2:] == y.shape[1:3]
     ay = act(y)
-    check(_lib.load().hd_nchw_f32_to_nhwc_bf16(_ptr(x), ctypes.byref(ay), x.shape[1], _stream()), "hd_nchw_f32_to_nhwc_bf16")
+    check(_lib.load().hd_nchw_f32_to_nhwc_bf16(_ptr(x), ctypes.byref(ay), x.shape[1], int(accumulate), _stream()),
+          "hd_nchw_f32_to_nhwc_bf16")
 
 
 def nhwc_bf16_to_nchw_f32(x, y):

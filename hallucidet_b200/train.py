@@ -1,0 +1,129 @@
+"""The HalluciDet train step on the B200 modules (host-side mirror of ``EncoderDecoderLit``).
+
+Follows the reference's train_hallucidet.py: ``forward_step`` (:161-240: U-Net on the 3x-repeated IR image,
+pixel regulariser, frozen-detector loss weighted 0.1 x4, total), ``training_step`` + Lightning's
+``loss.backward()`` (:243-283), ``clip_grad_value_(0.5)`` (:498-499), Adam lr 1e-4 (:56, src/config/config.py:215-219).
+The two extra no-grad detector passes (:183,:186) and the plotting normalisation (:218) are optional
+(``reference_extra_passes``): they do not influence the loss or the gradients.
+
+Data parallelism (new in this build): one process per GPU, identical replicas, per-replica
+BatchNorm statistics, one NCCL all-reduce(sum)/world of the hallucinator's flat fp32 gradient block per step.
+"""
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import ops
+from .detection import Detector, install_b200_backbone
+from .unet import Unet
+
+LOSS_WEIGHTS = {                       # src/config/config.py:58-69
+    "pixel_rgb": 0.0, "pixel_ir": 0.0, "perceptual_rgb": 0.0, "perceptual_ir": 0.0,
+    "det_regression": 0.1, "det_classification": 0.1, "det_objectness": 0.1, "det_rpn_box_reg": 0.1,
+    "det_bbox_ctrness": 0.1,
+}
+
+
+class _PixelRegulariser(torch.autograd.Function):
+    """w_rgb * pixel(rgb, hal) + w_ir * pixel(ir3, hal) with the gradient produced in the same pass."""
+
+    @staticmethod
+    def forward(ctx, hal, rgb, ir, kind, w_rgb, w_ir):
+        loss = torch.zeros(2, device=hal.device)
+        dhal = torch.empty_like(hal)
+        ops.regulariser(kind, hal.contiguous(), rgb.contiguous(), ir.contiguous(), float(w_rgb), float(w_ir), loss, dhal)
+        ctx.save_for_backward(dhal)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dhal,) = ctx.saved_tensors
+        # both terms normally receive the same upstream gradient (they are summed into the total loss)
+        return dhal * g[0], None, None, None, None, None
+
+
+def expand_one_channel_to_output_channels(imgs, output_channels=3):
+    """src/utils/utils.py:52-53."""
+    return imgs.repeat(1, output_channels, 1, 1)
+
+
+class HalluciDetTrainer(nn.Module):
+    def __init__(self, detector_name="fasterrcnn", size=640, pixel=None, weights=None, lr=1e-4, clip_value=0.5,
+                 seed=123, device="cuda", reference_extra_passes=False, use_cuda_graph=False, detector_state=None):
+        super().__init__()
+        torch.manual_seed(seed)
+        self.detector_name = detector_name
+        self.size = size
+        self.pixel = pixel
+        self.weights = dict(LOSS_WEIGHTS, **(weights or {}))
+        self.clip_value = clip_value
+        self.reference_extra_passes = reference_extra_passes
+        # src/models/encoder_decoder.py:22-30
+        self.encoder_decoder = Unet("resnet34", encoder_depth=5, encoder_weights=None, decoder_attention_type=None,
+                                    in_channels=3, classes=3)
+        self.encoder_decoder.segmentation_head[-1] = nn.Sigmoid()
+        self.detector = Detector(name=detector_name, pretrained=False, n_classes=2, size=size).detector
+        if detector_state is not None:
+            self.detector.load_state_dict(detector_state)
+        self.to(device)
+        install_b200_backbone(self.detector)
+        self.encoder_decoder.use_cuda_graph = use_cuda_graph
+        self.detector.backbone.use_cuda_graph = use_cuda_graph
+        self.optimizer = torch.optim.Adam(self.encoder_decoder.parameters(), lr=lr)   # train_hallucidet.py:429-435
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def forward_step(self, imgs_rgb, targets_rgb, imgs_ir, targets_ir, det_seed=None):
+        """train_hallucidet.py:161-240 -> dict(total, parts, hal)."""
+        w = self.weights
+        ir3 = expand_one_channel_to_output_channels(imgs_ir, 3)
+        hal = self.encoder_decoder(ir3)
+        if self.pixel is not None:
+            reg = _PixelRegulariser.apply(hal, imgs_rgb, imgs_ir, self.pixel, w["pixel_rgb"], w["pixel_ir"])
+            loss_pixel_rgb, loss_pixel_ir = reg[0], reg[1]
+        else:
+            loss_pixel_rgb, loss_pixel_ir = 0.0, 0.0
+        if det_seed is not None:
+            torch.manual_seed(det_seed)
+        losses_det, detections = Detector.calculate_loss(self.detector, hal, targets_ir, train_det=False, model_name=self.detector_name)
+        if self.reference_extra_passes:
+            with torch.no_grad():
+                Detector.calculate_loss(self.detector, imgs_rgb, targets_rgb, train_det=False, model_name=self.detector_name)
+                Detector.calculate_loss(self.detector, ir3, targets_ir, train_det=False, model_name=self.detector_name)
+        frcnn = "fasterrcnn" in self.detector_name
+        if frcnn:
+            losses_det["classification"] = losses_det["loss_classifier"]
+            losses_det["bbox_regression"] = losses_det["loss_box_reg"]
+        losses_det["bbox_regression"] = losses_det["bbox_regression"] * w["det_regression"]
+        losses_det["classification"] = losses_det["classification"] * w["det_classification"]
+        losses_det["loss_objectness"] = losses_det["loss_objectness"] * w["det_objectness"] if frcnn else 0.0
+        losses_det["loss_rpn_box_reg"] = losses_det["loss_rpn_box_reg"] * w["det_rpn_box_reg"] if frcnn else 0.0
+        loss_det_total = losses_det["bbox_regression"] + losses_det["classification"] + losses_det["loss_objectness"] + \
+            losses_det["loss_rpn_box_reg"]
+        total = loss_det_total + loss_pixel_rgb + loss_pixel_ir
+        return {"total": total, "det_total": loss_det_total, "pixel_rgb": loss_pixel_rgb, "pixel_ir": loss_pixel_ir,
+                "losses_det": losses_det, "hal": hal, "detections": detections}
+
+    def allreduce_gradients(self):
+        """Mean of the per-replica gradients: one all-reduce over the U-Net's flat gradient block."""
+        if self.world == 1:
+            return
+        params = [p for p in self.encoder_decoder.parameters() if p.grad is not None]
+        eng = next(iter(self.encoder_decoder._engines.values()), None)
+        flat = eng.flat_grad if eng is not None and params and params[0].grad.data_ptr() == eng.flat_grad.data_ptr() else None
+        if flat is not None:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            flat.mul_(1.0 / self.world)
+        else:
+            for p in params:
+                dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
+                p.grad.mul_(1.0 / self.world)
+
+    def training_step(self, imgs_rgb, targets_rgb, imgs_ir, targets_ir, det_seed=None):
+        self.encoder_decoder.train()
+        self.optimizer.zero_grad(set_to_none=True)
+        out = self.forward_step(imgs_rgb, targets_rgb, imgs_ir, targets_ir, det_seed=det_seed)
+        out["total"].backward()
+        self.allreduce_gradients()
+        torch.nn.utils.clip_grad_value_(self.encoder_decoder.parameters(), self.clip_value)     # train_hallucidet.py:498-499
+        self.optimizer.step()
+        return out

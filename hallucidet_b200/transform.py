@@ -1,0 +1,113 @@
+"""B200-native drop-in for the detector input transform.
+
+Mirrors ``CustomGeneralizedRCNNTransform`` (src/models/custom_generalized_transform.py:103-299 of the reference):
+same constructor, ``forward(images, targets) -> (ImageList, targets)``, ``postprocess``; the per-image
+normalise -> nearest resize to ``fixed_size`` -> zero-padded batch (:136-175, :177-186, :52-100, :256-274) is one
+batched CUDA kernel with a gather backward (hd_resize_nearest_fwd/bwd), instead of a Python loop of ATen calls.
+"""
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+from torchvision.models.detection.image_list import ImageList
+
+from . import ops
+
+
+def resize_boxes(boxes, original_size, new_size):
+    """custom_generalized_transform.py:325-338."""
+    ratios = [torch.tensor(s, dtype=torch.float32, device=boxes.device) / torch.tensor(s_orig, dtype=torch.float32, device=boxes.device)
+              for s, s_orig in zip(new_size, original_size)]
+    ratio_height, ratio_width = ratios
+    xmin, ymin, xmax, ymax = boxes.unbind(1)
+    return torch.stack((xmin * ratio_width, ymin * ratio_height, xmax * ratio_width, ymax * ratio_height), dim=1)
+
+
+class _ResizeFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, out_h, out_w, mean, std):
+        y = torch.empty(x.shape[0], x.shape[1], out_h, out_w, device=x.device)
+        ops.resize_nearest_fwd(x, y, mean, std)
+        ctx.in_shape = x.shape
+        ctx.std = std
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dx = torch.empty(ctx.in_shape, device=dy.device)
+        ops.resize_nearest_bwd(dy.contiguous().float(), dx, ctx.std)
+        return dx, None, None, None, None
+
+
+class GeneralizedRCNNTransform(nn.Module):
+    def __init__(self, min_size, max_size, image_mean, image_std, size_divisible=32, fixed_size=None, **kwargs):
+        super().__init__()
+        if not isinstance(min_size, (list, tuple)):
+            min_size = (min_size,)
+        self.min_size, self.max_size = min_size, max_size
+        self.image_mean, self.image_std = image_mean, image_std
+        self.size_divisible = size_divisible
+        self.fixed_size = fixed_size
+        self._skip_resize = kwargs.pop("_skip_resize", False)
+        if fixed_size is None:
+            raise NotImplementedError("the B200 transform implements the fixed-size mode HalluciDet configures "
+                                      "(src/models/detector.py:43-48)")
+
+    def _affine(self, c, device):
+        mean = torch.as_tensor(self.image_mean, dtype=torch.float32, device=device)
+        std = torch.as_tensor(self.image_std, dtype=torch.float32, device=device)
+        if bool((mean == 0).all()) and bool((std == 1).all()):
+            return None, None
+        return mean.expand(c).contiguous(), std.expand(c).contiguous()
+
+    def forward(self, images, targets: Optional[List[Dict[str, torch.Tensor]]] = None):
+        if torch.is_tensor(images):
+            if images.dim() != 4:
+                raise ValueError(f"images is expected to be a batch [B, C, H, W] or a list of [C, H, W], got {images.shape}")
+            same_shape = True
+        else:
+            images = [img for img in images]
+            for img in images:
+                if img.dim() != 3:
+                    raise ValueError(f"images is expected to be a list of 3d tensors of shape [C, H, W], got {img.shape}")
+            same_shape = all(img.shape == images[0].shape for img in images)
+        first = images[0]
+        if not first.is_floating_point():
+            raise TypeError(f"Expected input images to be of floating type (in range [0, 1]), but found type {first.dtype} instead")
+        if not first.is_cuda:
+            raise RuntimeError("hallucidet_b200 transform runs only on CUDA tensors; there is no CPU path")
+        if targets is not None:
+            targets = [{k: v for k, v in t.items()} for t in targets]
+        out_h, out_w = self.fixed_size[1], self.fixed_size[0]
+        c = first.shape[0] if not torch.is_tensor(images) else images.shape[1]
+        mean, std = self._affine(c, first.device)
+        if same_shape:
+            batch = images if torch.is_tensor(images) else torch.stack(images)
+            orig_sizes = [tuple(batch.shape[-2:])] * batch.shape[0]
+            resized = _ResizeFunction.apply(batch.contiguous().float(), out_h, out_w, mean, std)
+        else:
+            orig_sizes = [tuple(img.shape[-2:]) for img in images]
+            resized = torch.cat([_ResizeFunction.apply(img[None].contiguous().float(), out_h, out_w, mean, std) for img in images])
+        image_sizes = [(out_h, out_w)] * resized.shape[0]
+        stride = float(self.size_divisible)
+        mh = int(math.ceil(out_h / stride) * stride)
+        mw = int(math.ceil(out_w / stride) * stride)
+        if (mh, mw) != (out_h, out_w):
+            resized = torch.nn.functional.pad(resized, (0, mw - out_w, 0, mh - out_h))
+        if targets is not None:
+            for t, osz in zip(targets, orig_sizes):
+                t["boxes"] = resize_boxes(t["boxes"], osz, (out_h, out_w))
+        return ImageList(resized, image_sizes), targets
+
+    def postprocess(self, result, image_shapes: List[Tuple[int, int]], original_image_sizes: List[Tuple[int, int]]):
+        """custom_generalized_transform.py:276-299."""
+        if self.training:
+            return result
+        for i, (pred, im_s, o_im_s) in enumerate(zip(result, image_shapes, original_image_sizes)):
+            result[i]["boxes"] = resize_boxes(pred["boxes"], im_s, o_im_s)
+        return result
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__}(Normalize(mean={self.image_mean}, std={self.image_std}), "
+                f"Resize(fixed_size={self.fixed_size}, mode='nearest'))")

@@ -1,0 +1,487 @@
+"""B200-native drop-in for the reference's hallucination U-Net.
+
+Mirrors ``smp.Unet('resnet34', ...)`` as used at src/models/encoder_decoder.py:22-30 (reference repo):
+same constructor arguments, same sub-module / ``state_dict`` names and shapes (278 entries), same
+``forward(Tensor[B,3,H,W] fp32) -> Tensor[B,3,H,W] fp32`` with autograd, ``.train()/.eval()`` switching the
+BatchNorm mode, ``segmentation_head[-1]`` assignable (the reference replaces it with ``nn.Sigmoid``).
+
+The ``nn.Conv2d`` / ``nn.BatchNorm2d`` children only HOLD parameters (fp32 masters for Adam / checkpoints);
+they are never called.  All arithmetic runs in the hand-written sm_100a kernels of libhallucidet_b200.so
+through ``hallucidet_b200.ops`` (NHWC bf16 activations, fp32 accumulation, fp32 BN statistics).  There is no
+PyTorch/CPU fallback: a CPU tensor or a missing library raises.
+
+Reference semantics followed: src/segmentation_models/base/model.py:24-38, encoders/resnet.py:47-65,
+decoders/unet/decoder.py:7-8,38-46,111-124, base/modules.py:10-47, base/heads.py:21-27,
+base/initialization.py:4-27; TV models/resnet.py:59-105 (BasicBlock).
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+
+BN_EPS = 1e-5
+
+
+# ------------------------------------------------------------------------------------------------------
+# parameter-holding module tree (names == reference state_dict)
+# ------------------------------------------------------------------------------------------------------
+class _Conv2dReLU(nn.Sequential):
+    """Holder mirroring base/modules.py:10-47: [conv(bias=False), bn, relu]."""
+
+    def __init__(self, cin, cout):
+        super().__init__(nn.Conv2d(cin, cout, 3, padding=1, bias=False), nn.BatchNorm2d(cout), nn.ReLU(inplace=True))
+
+
+class _DecoderBlock(nn.Module):
+    def __init__(self, cin, cskip, cout):
+        super().__init__()
+        self.conv1 = _Conv2dReLU(cin + cskip, cout)
+        self.attention1 = nn.Identity()
+        self.conv2 = _Conv2dReLU(cout, cout)
+        self.attention2 = nn.Identity()
+
+
+class _UnetDecoder(nn.Module):
+    def __init__(self, encoder_channels, decoder_channels):
+        super().__init__()
+        enc = list(encoder_channels[1:])[::-1]
+        ins = [enc[0]] + list(decoder_channels[:-1])
+        skips = enc[1:] + [0]
+        self.center = nn.Identity()
+        self.blocks = nn.ModuleList(_DecoderBlock(i, s, o) for i, s, o in zip(ins, skips, decoder_channels))
+        self.channels = list(zip(ins, skips, decoder_channels))
+
+
+def _make_encoder(name):
+    from torchvision.models.resnet import ResNet, BasicBlock
+    layers = {"resnet18": [2, 2, 2, 2], "resnet34": [3, 4, 6, 3]}
+    if name not in layers:
+        raise KeyError(f"Wrong encoder name `{name}`, supported encoders: {list(layers)} (B200 hot path: BasicBlock ResNets)")
+    enc = ResNet(block=BasicBlock, layers=layers[name])
+    del enc.fc
+    del enc.avgpool
+    enc.out_channels = (3, 64, 64, 128, 256, 512)
+    enc.output_stride = 32
+    enc.layer_spec = layers[name]
+    return enc
+
+
+class Unet(nn.Module):
+    def __init__(self, encoder_name="resnet34", encoder_depth=5, encoder_weights=None, decoder_use_batchnorm=True,
+                 decoder_channels=(256, 128, 64, 32, 16), decoder_attention_type=None, in_channels=3, classes=1,
+                 activation=None, aux_params=None):
+        super().__init__()
+        if encoder_depth != 5 or decoder_use_batchnorm is not True or decoder_attention_type is not None \
+                or in_channels != 3 or aux_params is not None or tuple(decoder_channels) != (256, 128, 64, 32, 16):
+            raise NotImplementedError("hallucidet_b200.Unet implements the configuration HalluciDet uses "
+                                      "(depth 5, BN decoder (256,128,64,32,16), no attention, 3 input channels)")
+        if encoder_weights is not None:
+            raise NotImplementedError("pretrained encoder download is not available; load a state_dict instead")
+        if classes > 16:
+            raise NotImplementedError("segmentation head supports up to 16 classes")
+        self.encoder = _make_encoder(encoder_name)
+        self.decoder = _UnetDecoder(self.encoder.out_channels, decoder_channels)
+        act = {None: nn.Identity(), "identity": nn.Identity(), "sigmoid": nn.Sigmoid()}
+        if activation not in act:
+            raise NotImplementedError(f"activation {activation!r}")
+        self.segmentation_head = nn.Sequential(nn.Conv2d(decoder_channels[-1], classes, 3, padding=1), nn.Identity(), act[activation])
+        self.classification_head = None
+        self.name = "u-{}".format(encoder_name)
+        self.classes = classes
+        self.initialize()
+        self._engines = {}
+        self.use_cuda_graph = False
+
+    def initialize(self):
+        """base/initialization.py:4-27 (decoder kaiming_uniform fan_in/relu, BN 1/0; head xavier_uniform, bias 0)."""
+        for m in self.decoder.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_uniform_(m.weight, mode="fan_in", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+        head = self.segmentation_head[0]
+        nn.init.xavier_uniform_(head.weight)
+        nn.init.constant_(head.bias, 0)
+
+    def check_input_shape(self, x):
+        """base/model.py:12-22."""
+        h, w = x.shape[-2:]
+        if h % 32 != 0 or w % 32 != 0:
+            new_h = (h // 32 + 1) * 32 if h % 32 != 0 else h
+            new_w = (w // 32 + 1) * 32 if w % 32 != 0 else w
+            raise RuntimeError(f"Wrong input shape height={h}, width={w}. Expected image height and width "
+                               f"divisible by 32. Consider pad your images to shape ({new_h}, {new_w}).")
+
+    def _engine(self, x):
+        key = (tuple(x.shape), x.device.index, self.training, self.segmentation_head[0].weight.data_ptr())
+        eng = self._engines.get(key)
+        if eng is None:
+            if len(self._engines) >= 4:
+                self._engines.clear()
+            eng = _UnetEngine(self, x.shape[0], x.shape[2], x.shape[3], x.device, self.training)
+            self._engines[key] = eng
+        return eng
+
+    def forward(self, x):
+        self.check_input_shape(x)
+        if not x.is_cuda:
+            raise RuntimeError("hallucidet_b200.Unet runs only on a CUDA (B200) device; there is no CPU path")
+        head_act = self.segmentation_head[-1]
+        if isinstance(head_act, nn.Sigmoid):
+            sigmoid = True
+        elif isinstance(head_act, nn.Identity):
+            sigmoid = False
+        else:
+            raise NotImplementedError(f"segmentation head activation {type(head_act).__name__} is not implemented in the B200 path")
+        x = x.contiguous().float()
+        eng = self._engine(x)
+        params = [p for _, p in eng.named_params]
+        return _UnetFunction.apply(x, eng, sigmoid, *params)
+
+    @torch.no_grad()
+    def predict(self, x):
+        if self.training:
+            self.eval()
+        return self.forward(x)
+
+
+class _UnetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eng, sigmoid, *params):
+        ctx.eng = eng
+        ctx.sigmoid = sigmoid
+        out = eng.forward(x, sigmoid)
+        ctx.generation = eng.generation
+        return out
+
+    @staticmethod
+    def backward(ctx, dhal):
+        eng = ctx.eng
+        if not ctx.sigmoid:
+            raise NotImplementedError("backward needs the sigmoid head (the HalluciDet configuration)")
+        if not eng.training:
+            raise NotImplementedError("backward through the eval-mode (folded BatchNorm) U-Net is not implemented")
+        if ctx.generation != eng.generation:
+            raise RuntimeError("hallucidet_b200.Unet: the activations saved for this backward were overwritten by a later "
+                               "forward of the same module (one forward per backward is supported)")
+        grads = eng.backward(dhal.contiguous().float())
+        return (None, None, None) + tuple(grads)
+
+
+# ------------------------------------------------------------------------------------------------------
+# execution engine: static buffers + kernel program for one (B, H, W, mode)
+# ------------------------------------------------------------------------------------------------------
+class _Layer:
+    """One convolution (+ optional BatchNorm) of the U-Net with its packed operands and saved tensors."""
+
+    def __init__(self, eng, name, conv, bn, cin, cout, k, stride, in_hw, cout_pad=None, packed=None):
+        self.name, self.conv, self.bn = name, conv, bn
+        self.cin, self.cout, self.k, self.stride = cin, cout, k, stride
+        self.h_in, self.w_in = in_hw
+        self.h, self.w = in_hw[0] // stride, in_hw[1] // stride
+        self.cp = cout_pad or cout                       # channel count of the activation tensors
+        dev = eng.device
+        self.packed = packed if packed is not None else ops.PackedConv(self.cp, cin, k, dev, need_dgrad=True)
+        self.z = eng.new_act(self.h, self.w, self.cp)
+        if bn is not None:
+            self.stats = torch.zeros(ops.STATS_REPLICAS, 2, cout, device=dev)
+            self.mean, self.invstd, self.scale, self.shift = (torch.empty(cout, device=dev) for _ in range(4))
+            self.sums = torch.zeros(2, cout, device=dev)
+            self.bias = torch.empty(cout, device=dev)    # eval-mode folded shift
+        self.dz = None
+
+
+class _UnetEngine:
+    def __init__(self, module, B, H, W, device, training):
+        self.m, self.B, self.H, self.W, self.device, self.training = module, B, H, W, device, training
+        self.acts = []
+        enc, dec = module.encoder, module.decoder
+        self.named_params = [(n, p) for n, p in module.named_parameters()]
+        # flat fp32 gradient buffer (views returned to autograd, one allreduce-able block)
+        sizes = [p.numel() for _, p in self.named_params]
+        self.flat_grad = torch.zeros(sum(sizes), device=device)
+        self.grad_views, off = {}, 0
+        for (n, p), s in zip(self.named_params, sizes):
+            self.grad_views[n] = self.flat_grad[off:off + s].view_as(p)
+            off += s
+
+        h2, w2 = H // 2, W // 2
+        # ---- stem (7x7/2 via patches GEMM)
+        self.stem = _Layer(self, "encoder.conv1", enc.conv1, enc.bn1, 3, 64, 7, 2, (H, W),
+                           packed=ops.PackedConv(64, 3, 7, device, need_dgrad=False, k_pad=ops.STEM_KPAD))
+        self.patches = torch.empty(1, 1, B * h2 * w2, ops.STEM_KPAD, dtype=torch.bfloat16, device=device)
+        self.a_stem = self.new_act(h2, w2, 64)
+        self.p0 = self.new_act(h2 // 2, w2 // 2, 64)
+        # ---- encoder layers
+        self.blocks = []
+        hw, cin = (h2 // 2, w2 // 2), 64
+        for li, (planes, nblk) in enumerate(zip((64, 128, 256, 512), enc.layer_spec), start=1):
+            layer = getattr(enc, f"layer{li}")
+            for b in range(nblk):
+                blk = layer[b]
+                stride = 2 if (li > 1 and b == 0) else 1
+                pfx = f"encoder.layer{li}.{b}"
+                c1 = _Layer(self, pfx + ".conv1", blk.conv1, blk.bn1, cin, planes, 3, stride, hw)
+                ohw = (hw[0] // stride, hw[1] // stride)
+                c2 = _Layer(self, pfx + ".conv2", blk.conv2, blk.bn2, planes, planes, 3, 1, ohw)
+                cd = None
+                if blk.downsample is not None:
+                    cd = _Layer(self, pfx + ".downsample.0", blk.downsample[0], blk.downsample[1], cin, planes, 1, stride, hw)
+                    cd.bn_name = pfx + ".downsample.1"
+                c1.bn_name, c2.bn_name = pfx + ".bn1", pfx + ".bn2"
+                a1 = self.new_act(ohw[0], ohw[1], planes)
+                out = self.new_act(ohw[0], ohw[1], planes)
+                self.blocks.append(dict(c1=c1, c2=c2, cd=cd, a1=a1, out=out, end_of_layer=(b == nblk - 1), li=li))
+                hw, cin = ohw, planes
+        # ---- decoder
+        self.dblocks = []
+        x_hw, x_c = hw, cin
+        skips_c = [256, 128, 64, 64, 0]
+        for i, (ci, cs, co) in enumerate(dec.channels):
+            blk = dec.blocks[i]
+            ohw = (x_hw[0] * 2, x_hw[1] * 2)
+            up = self.new_act(ohw[0], ohw[1], ci)
+            c1 = _Layer(self, f"decoder.blocks.{i}.conv1.0", blk.conv1[0], blk.conv1[1], ci + cs, co, 3, 1, ohw)
+            c2 = _Layer(self, f"decoder.blocks.{i}.conv2.0", blk.conv2[0], blk.conv2[1], co, co, 3, 1, ohw)
+            c1.bn_name, c2.bn_name = f"decoder.blocks.{i}.conv1.1", f"decoder.blocks.{i}.conv2.1"
+            a1 = self.new_act(ohw[0], ohw[1], co)
+            a2 = self.new_act(ohw[0], ohw[1], co)
+            self.dblocks.append(dict(c1=c1, c2=c2, up=up, a1=a1, a2=a2, cskip=cs, cin=ci))
+            x_hw, x_c = ohw, co
+        # ---- head (cout padded to 16 channels)
+        self.head = _Layer(self, "segmentation_head.0", module.segmentation_head[0], None, 16, module.classes, 3, 1, (H, W), cout_pad=16)
+        self.head_w_pad = torch.zeros(16, 16, 3, 3, device=device)
+        self.head_bias_pad = torch.zeros(16, device=device)
+        self.hal = torch.empty(B, module.classes, H, W, device=device)
+        self.dlogits = self.new_act(H, W, 16)
+        self.stem.bn_name = "encoder.bn1"
+        self.all_layers = [self.stem] + [l for b in self.blocks for l in (b["c1"], b["c2"], b["cd"]) if l is not None] + \
+                          [l for d in self.dblocks for l in (d["c1"], d["c2"])] + [self.head]
+        # packed weight-gradient accumulators (one flat buffer, zeroed once per backward)
+        tot = 0
+        for l in self.all_layers:
+            l.dw_off = tot
+            l.dw_rows = l.cp
+            l.dw_cols = l.k * l.k * l.cin if l is not self.stem else ops.STEM_KPAD
+            tot += l.dw_rows * l.dw_cols
+        self.dw_flat = torch.zeros(tot, device=device)
+        for l in self.all_layers:
+            l.dw = self.dw_flat[l.dw_off:l.dw_off + l.dw_rows * l.dw_cols]
+        self.grad_bufs = {}
+        self.graphs = {}
+        self.sigmoid = None
+        self.generation = 0
+        self.x_in = torch.empty(B, 3, H, W, device=device)
+        self.dhal_in = torch.empty(B, module.classes, H, W, device=device)
+        self.nbt = [m.num_batches_tracked for m in module.modules() if isinstance(m, nn.BatchNorm2d)]
+
+    # ---- helpers -------------------------------------------------------------------------------------
+    def new_act(self, h, w, c):
+        t = torch.empty(self.B, h, w, c, dtype=torch.bfloat16, device=self.device)
+        self.acts.append(t)
+        return t
+
+    def gbuf(self, key, like):
+        t = self.grad_bufs.get(key)
+        if t is None:
+            t = torch.empty_like(like)
+            self.grad_bufs[key] = t
+        return t
+
+    def _pack_weights(self):
+        for l in self.all_layers:
+            if l is self.head:
+                self.head_w_pad[:l.cout].copy_(l.conv.weight.detach())
+                self.head_bias_pad[:l.cout].copy_(l.conv.bias.detach())
+                l.packed.pack(self.head_w_pad)
+            elif self.training or l.bn is None:
+                l.packed.pack(l.conv.weight.detach().contiguous())
+            else:                                         # eval: fold running statistics (TV ops/misc.py-style affine)
+                bn = l.bn
+                scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
+                l.bias.copy_(bn.bias.detach() - bn.running_mean * scale)
+                l.packed.pack(l.conv.weight.detach().contiguous(), scale.contiguous())
+
+    def _conv_bn(self, l, x0, a_out, x1=None, relu=True, res=None, res_layer=None, apply=True):
+        """train: z = conv(x) (+stats) -> finalize -> a_out = relu(bn(z) + res).   eval: fused epilogue."""
+        if self.training:
+            l.stats.zero_()
+            ops.conv_fwd(ops.conv_args(x0, l.z, l.packed.w_fwd, k=l.k, stride=l.stride, x1=x1, stats=l.stats))
+            bn = l.bn
+            ops.bn_finalize(l.stats, self.B * l.h * l.w, bn.weight.detach(), bn.bias.detach(), bn.eps,
+                            bn.momentum if bn.momentum is not None else 0.1, bn.running_mean, bn.running_var,
+                            l.mean, l.invstd, l.scale, l.shift)
+            if apply:
+                if res_layer is not None:
+                    ops.bn_apply(l.z, l.scale, l.shift, a_out, relu=relu, res=res_layer.z, res_scale=res_layer.scale, res_shift=res_layer.shift)
+                else:
+                    ops.bn_apply(l.z, l.scale, l.shift, a_out, relu=relu, res=res)
+        else:
+            add = res_layer.z if res_layer is not None else res
+            ops.conv_fwd(ops.conv_args(x0, a_out if apply else l.z, l.packed.w_fwd, k=l.k, stride=l.stride, x1=x1, bias=l.bias,
+                                       add=add, relu=relu and apply))
+
+    # ---- forward ---------------------------------------------------------------------------------------
+    def _run(self, kind, fn):
+        """Run a kernel program eagerly, or (module.use_cuda_graph) warm up once, capture once, then replay."""
+        if not self.m.use_cuda_graph:
+            fn()
+            return
+        state = self.graphs.get(kind)
+        if state is None:
+            fn()
+            self.graphs[kind] = "warm"
+        elif state == "warm":
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            self.graphs[kind] = g
+            g.replay()
+        else:
+            state.replay()
+
+    def forward(self, x, sigmoid):
+        if self.sigmoid is not None and self.sigmoid != sigmoid:
+            self.graphs.clear()
+        self.sigmoid = sigmoid
+        self.x_in.copy_(x)
+        self._run("fwd", self._forward_impl)
+        self.generation += 1
+        return self.hal.clone()
+
+    def backward(self, dhal):
+        self.dhal_in.copy_(dhal)
+        self._run("bwd", self._backward_impl)
+        params = [p for _, p in self.named_params]
+        alias_ok = all(p.grad is None for p in params)
+        src = self.flat_grad if alias_ok else self.flat_grad.clone()
+        out, off = [], 0
+        for p in params:
+            n = p.numel()
+            out.append(src[off:off + n].view_as(p) if p.requires_grad else None)
+            off += n
+        return out
+
+    def _forward_impl(self):
+        sigmoid = self.sigmoid
+        x = self.x_in
+        self._pack_weights()
+        st = self.stem
+        ops.stem_im2col(x, self.patches)
+        zs = st.z.view(1, 1, -1, 64)
+        a_stem_flat = self.a_stem.view(1, 1, -1, 64)
+        if self.training:
+            st.stats.zero_()
+            ops.conv_fwd(ops.conv_args(self.patches, zs, st.packed.w_fwd, k=1, stats=st.stats))
+            bn = st.bn
+            ops.bn_finalize(st.stats, zs.shape[2], bn.weight.detach(), bn.bias.detach(), bn.eps, bn.momentum or 0.1,
+                            bn.running_mean, bn.running_var, st.mean, st.invstd, st.scale, st.shift)
+            ops.bn_apply(zs, st.scale, st.shift, a_stem_flat, relu=True)
+        else:
+            ops.conv_fwd(ops.conv_args(self.patches, a_stem_flat, st.packed.w_fwd, k=1, bias=st.bias, relu=True))
+        ops.maxpool_fwd(self.a_stem, self.p0)
+        x_in = self.p0
+        feats = {1: self.a_stem}
+        for blk in self.blocks:
+            c1, c2, cd = blk["c1"], blk["c2"], blk["cd"]
+            self._conv_bn(c1, x_in, blk["a1"])
+            if cd is not None:
+                self._conv_bn(cd, x_in, None, apply=False, relu=False)
+                self._conv_bn(c2, blk["a1"], blk["out"], res_layer=cd)
+            else:
+                self._conv_bn(c2, blk["a1"], blk["out"], res=x_in)
+            blk["x_in"] = x_in
+            x_in = blk["out"]
+            if blk["end_of_layer"]:
+                feats[blk["li"] + 1] = x_in
+        skips = [feats[4], feats[3], feats[2], feats[1], None]
+        xd = feats[5]
+        for i, d in enumerate(self.dblocks):
+            ops.upsample2x_fwd(xd, d["up"])
+            d["skip"] = skips[i]
+            self._conv_bn(d["c1"], d["up"], d["a1"], x1=skips[i])
+            self._conv_bn(d["c2"], d["a1"], d["a2"])
+            xd = d["a2"]
+        hd = self.head
+        ops.conv_fwd(ops.conv_args(xd, hd.z, hd.packed.w_fwd, k=3, bias=self.head_bias_pad, sigmoid=sigmoid, out_f32=self.hal,
+                                   out_f32_channels=hd.cout, store_bf16=False))
+        self.head_in = xd
+        if self.training:
+            torch._foreach_add_(self.nbt, 1)
+
+    # ---- backward --------------------------------------------------------------------------------------
+    def _bn_bwd(self, l, g, y_relu, z=None, g_out=None):
+        """BatchNorm backward for layer l given dL/d(post-BN, pre-ReLU-mask) = g masked by y_relu>0 -> l.dz."""
+        z = l.z if z is None else z
+        l.sums.zero_()
+        ops.bn_bwd_reduce(g, y_relu, z, l.mean, l.invstd, l.sums)
+        dz = self.gbuf(("dz", l.name), z)
+        ops.bn_bwd_apply(g, y_relu, z, l.mean, l.invstd, l.bn.weight.detach(), l.sums, dz, g_out,
+                         self.grad_views[l.bn_name + ".weight"], self.grad_views[l.bn_name + ".bias"])
+        return dz
+
+    def _wgrad(self, l, x0, dz, x1=None):
+        ops.conv_wgrad(ops.conv_args(x0, dz, k=l.k, stride=l.stride, x1=x1, dw=l.dw))
+        ops.unpack_wgrad(l.dw, self.grad_views[l.name + ".weight"], l.cout, l.cin, l.k, l.cin, l.k * l.k * l.cin)
+
+    def _backward_impl(self):
+        dhal = self.dhal_in
+        self.dw_flat.zero_()
+        hd = self.head
+        gv = self.grad_views
+        gv["segmentation_head.0.bias"].zero_()
+        ops.sigmoid_bwd_pack(dhal, self.hal, self.dlogits, gv["segmentation_head.0.bias"])
+        self._wgrad(hd, self.head_in, self.dlogits)
+        g = self.gbuf(("g", "head_in"), self.head_in)
+        ops.conv_dgrad(ops.conv_args(self.dlogits, g, hd.packed.w_dgrad, k=3))
+        # ---- decoder
+        skip_grads = {}
+        for i in reversed(range(len(self.dblocks))):
+            d = self.dblocks[i]
+            c1, c2 = d["c1"], d["c2"]
+            dz2 = self._bn_bwd(c2, g, d["a2"])
+            self._wgrad(c2, d["a1"], dz2)
+            g_a1 = self.gbuf(("g", c2.name), d["a1"])
+            ops.conv_dgrad(ops.conv_args(dz2, g_a1, c2.packed.w_dgrad, k=3))
+            dz1 = self._bn_bwd(c1, g_a1, d["a1"])
+            self._wgrad(c1, d["up"], dz1, x1=d["skip"])
+            g_up = self.gbuf(("gup", i), d["up"])
+            g_skip = self.gbuf(("gskip", i), d["skip"]) if d["skip"] is not None else None
+            ops.conv_dgrad(ops.conv_args(dz1, g_up, c1.packed.w_dgrad, k=3, y1=g_skip))
+            skip_grads[i] = g_skip
+            x_small_like = self.dblocks[i - 1]["a2"] if i > 0 else self.blocks[-1]["out"]
+            g = self.gbuf(("gdown", i), x_small_like)
+            ops.upsample2x_bwd(g_up, g)
+        # skips: decoder block 0 <- f4 (layer3 out), 1 <- f3 (layer2 out), 2 <- f2 (layer1 out), 3 <- f1 (stem)
+        skip_for_layer = {3: skip_grads[0], 2: skip_grads[1], 1: skip_grads[2]}
+        # ---- encoder
+        for blk in reversed(self.blocks):
+            c1, c2, cd = blk["c1"], blk["c2"], blk["cd"]
+            g_masked = self.gbuf(("gm", c2.name), blk["out"]) if cd is None else None
+            dz2 = self._bn_bwd(c2, g, blk["out"], g_out=g_masked)
+            dzd = self._bn_bwd(cd, g, blk["out"]) if cd is not None else None
+            self._wgrad(c2, blk["a1"], dz2)
+            g_a1 = self.gbuf(("g", c2.name), blk["a1"])
+            ops.conv_dgrad(ops.conv_args(dz2, g_a1, c2.packed.w_dgrad, k=3))
+            dz1 = self._bn_bwd(c1, g_a1, blk["a1"])
+            x_in = blk["x_in"]
+            self._wgrad(c1, x_in, dz1)
+            g_x = self.gbuf(("gx", c1.name), x_in)
+            if cd is None:
+                ops.conv_dgrad(ops.conv_args(dz1, g_x, c1.packed.w_dgrad, k=3, stride=c1.stride, add=g_masked))
+            else:
+                # input of a down-sampling block is the previous layer's output, which also feeds a decoder skip
+                ops.conv_dgrad(ops.conv_args(dz1, g_x, c1.packed.w_dgrad, k=3, stride=c1.stride, add=skip_for_layer[blk["li"] - 1]))
+                self._wgrad(cd, x_in, dzd)
+                ops.conv_dgrad(ops.conv_args(dzd, g_x, cd.packed.w_dgrad, k=1, stride=cd.stride, add=g_x))
+            g = g_x
+        # ---- stem: max-pool backward (+ decoder skip of f1), BN backward, weight gradient through the patch GEMM
+        st = self.stem
+        g_stem = self.gbuf(("g", "stem"), self.a_stem)
+        ops.maxpool_bwd(self.a_stem, self.p0, g, g_stem, add=skip_grads[3])
+        zs = st.z.view(1, 1, -1, 64)
+        dzs = self._bn_bwd(st, g_stem.view(1, 1, -1, 64), self.a_stem.view(1, 1, -1, 64), z=zs)
+        ops.conv_wgrad(ops.conv_args(self.patches, dzs, k=1, dw=st.dw))
+        ops.unpack_wgrad(st.dw, gv["encoder.conv1.weight"], 64, 3, 7, 3, ops.STEM_KPAD)

@@ -126,7 +126,7 @@ int hd_upsample2x_bwd(const hd_act* dy, const hd_act* dx, hd_stream stream);
 int hd_add_nearest_fwd(const hd_act* x, const hd_act* y, hd_stream stream);
 int hd_add_nearest_bwd(const hd_act* dy, const hd_act* dx, int accumulate, hd_stream stream);
 /* Layout / dtype converters at the module edges. */
-int hd_nchw_f32_to_nhwc_bf16(const float* x, const hd_act* y, int channels, hd_stream stream);
+int hd_nchw_f32_to_nhwc_bf16(const float* x, const hd_act* y, int channels, int accumulate, hd_stream stream);
 int hd_nhwc_bf16_to_nchw_f32(const hd_act* x, float* y, int channels, hd_stream stream);
 /* Segmentation head backward prologue: dlogits = dhal * hal * (1-hal) (fp32 NCHW [n][3][h][w]) -> bf16 NHWC, c = 16 (zero padded);
  * dbias[c] += sum (atomics, caller zeroes). */

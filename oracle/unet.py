@@ -77,6 +77,26 @@ def init_unet_state(seed=123, classes=3):
     return state
 
 
+class _RoundBF16(torch.autograd.Function):
+    """bf16 storage emulation: round the value forward and the gradient backward (straight-through)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+def round_bf16(x):
+    return _RoundBF16.apply(x)
+
+
+def _id(x):
+    return x
+
+
 def is_param(key):
     return not (key.endswith("running_mean") or key.endswith("running_var") or key.endswith("num_batches_tracked"))
 
@@ -92,31 +112,31 @@ def _bn(state, prefix, x, training, update_stats):
     return y
 
 
-def _basic_block(state, p, x, stride, has_down, training, update_stats):
-    """TV models/resnet.py:89-105."""
-    out = F.conv2d(x, state[p + ".conv1.weight"], stride=stride, padding=1)
-    out = F.relu(_bn(state, p + ".bn1", out, training, update_stats))
-    out = F.conv2d(out, state[p + ".conv2.weight"], padding=1)
+def _basic_block(state, p, x, stride, has_down, training, update_stats, q=_id):
+    """TV models/resnet.py:89-105.  q = storage-rounding hook (identity for the fp32 oracle)."""
+    out = q(F.conv2d(x, q(state[p + ".conv1.weight"]), stride=stride, padding=1))
+    out = q(F.relu(_bn(state, p + ".bn1", out, training, update_stats)))
+    out = q(F.conv2d(out, q(state[p + ".conv2.weight"]), padding=1))
     out = _bn(state, p + ".bn2", out, training, update_stats)
     if has_down:
-        idn = F.conv2d(x, state[p + ".downsample.0.weight"], stride=stride)
+        idn = q(F.conv2d(x, q(state[p + ".downsample.0.weight"]), stride=stride))
         idn = _bn(state, p + ".downsample.1", idn, training, update_stats)
     else:
         idn = x
-    return F.relu(out + idn)
+    return q(F.relu(out + idn))
 
 
-def encoder_forward(state, x, training=True, update_stats=False):
+def encoder_forward(state, x, training=True, update_stats=False, q=_id):
     """encoders/resnet.py:47-65 -> list of 6 features."""
     feats = [x]
-    h = F.conv2d(x, state["encoder.conv1.weight"], stride=2, padding=3)
-    h = F.relu(_bn(state, "encoder.bn1", h, training, update_stats))
+    h = q(F.conv2d(q(x), q(state["encoder.conv1.weight"]), stride=2, padding=3))
+    h = q(F.relu(_bn(state, "encoder.bn1", h, training, update_stats)))
     feats.append(h)
     h = F.max_pool2d(h, kernel_size=3, stride=2, padding=1)
     for li, nblocks in enumerate(ENCODER_LAYERS, start=1):
         for b in range(nblocks):
             stride = 2 if (li > 1 and b == 0) else 1
-            h = _basic_block(state, f"encoder.layer{li}.{b}", h, stride, li > 1 and b == 0, training, update_stats)
+            h = _basic_block(state, f"encoder.layer{li}.{b}", h, stride, li > 1 and b == 0, training, update_stats, q)
         feats.append(h)
     return feats
 
@@ -126,7 +146,7 @@ def upsample2x(x):
     return x[:, :, :, None, :, None].expand(-1, -1, -1, 2, -1, 2).reshape(x.size(0), x.size(1), x.size(2) * 2, x.size(3) * 2)
 
 
-def decoder_forward(state, feats, training=True, update_stats=False):
+def decoder_forward(state, feats, training=True, update_stats=False, q=_id):
     """decoders/unet/decoder.py:111-124, 38-46."""
     feats = feats[1:][::-1]
     x, skips = feats[0], feats[1:]
@@ -136,12 +156,12 @@ def decoder_forward(state, feats, training=True, update_stats=False):
             x = torch.cat([x, skips[i]], dim=1)
         for j in (1, 2):
             p = f"decoder.blocks.{i}.conv{j}"
-            x = F.conv2d(x, state[p + ".0.weight"], padding=1)
-            x = F.relu(_bn(state, p + ".1", x, training, update_stats))
+            x = q(F.conv2d(x, q(state[p + ".0.weight"]), padding=1))
+            x = q(F.relu(_bn(state, p + ".1", x, training, update_stats)))
     return x
 
 
-def unet_forward(state, x, training=True, update_stats=False, return_intermediates=False):
+def unet_forward(state, x, training=True, update_stats=False, return_intermediates=False, q=_id):
     """base/model.py:24-38 with the Sigmoid head of src/models/encoder_decoder.py:29-30.
 
     x: [B,3,H,W] fp32, H%32==W%32==0 (base/model.py:12-22).  Returns hal [B,3,H,W] in (0,1).
@@ -149,9 +169,9 @@ def unet_forward(state, x, training=True, update_stats=False, return_intermediat
     h, w = x.shape[-2:]
     if h % 32 != 0 or w % 32 != 0:
         raise RuntimeError(f"Wrong input shape height={h}, width={w}. Expected image height and width divisible by 32.")
-    feats = encoder_forward(state, x, training, update_stats)
-    d = decoder_forward(state, feats, training, update_stats)
-    logits = F.conv2d(d, state["segmentation_head.0.weight"], state["segmentation_head.0.bias"], padding=1)
+    feats = encoder_forward(state, x, training, update_stats, q)
+    d = decoder_forward(state, feats, training, update_stats, q)
+    logits = F.conv2d(d, q(state["segmentation_head.0.weight"]), state["segmentation_head.0.bias"], padding=1)
     hal = torch.sigmoid(logits)
     if return_intermediates:
         return hal, {"features": feats, "decoder_out": d, "logits": logits}
