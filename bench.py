@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench.py -- HalluciDet train-step throughput on B200 (BASELINE.json metric: train images/s, 640x512 IR, bf16).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W    # the reference's algorithm on the host CPU (oracle port)
+
+One step = one full training step of BASELINE config 2: U-Net forward, frozen Faster R-CNN R50-FPN detection loss
+(backbone = B200 kernels, RPN/RoI heads = torchvision as the reference runs them), backward (backbone dgrad + U-Net
+dgrad/wgrad/BN), clip-by-value and Adam -- batch 8 per GPU, 512x640 IR, detector size 640.
+Prints ONE JSON line (rank 0).  `value` = device-resident inputs; `e2e` = pinned-host inputs copied every step and
+the loss read back every step, through the public trainer API.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GFLOP_PER_IMAGE = 459.702        # SURVEY.md 8(d) / BASELINE.md section 2: U-Net fwd+dgrad+wgrad + backbone fwd+dgrad
+METRIC = "train images/s (640x512 IR, bf16)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        load = [v for v in sm if v > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args):
+    """The reference's algorithm on the host CPU: the fp32 oracle port (oracle/step.py), all host threads.
+    Bounded sample of the same workload: one image (B=1, 512x640 -> S=640) per step."""
+    import torch
+    from oracle import unet as ou, detector as odet, step as ostep
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    state = ou.init_unet_state(123)
+    det = odet.build_detector("fasterrcnn", seed=123)
+    ir, rgb, targets = ostep.synthetic_batch(1, 512, 640, seed=123)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        ostep.train_step(state, det, ir, rgb, targets, size=640, detector_name="fasterrcnn", det_seed=7)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    v = 1.0 / t
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "HalluciDet train step (U-Net fwd/bwd + frozen Faster R-CNN R50-FPN loss dgrad), 512x640 IR, S=640",
+                   "sample": "B=1 per step (bounded sample of the B=8 workload)", "detector": "fasterrcnn"},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} train steps of B=1 512x640 (fp32 oracle port of the reference, torch CPU, {cores} threads)"},
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def cpu_baseline_sample(budget_s=25.0):
+    import torch
+    from oracle import unet as ou, detector as odet, step as ostep
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    state = ou.init_unet_state(123)
+    det = odet.build_detector("fasterrcnn", seed=123)
+    ir, rgb, targets = ostep.synthetic_batch(1, 512, 640, seed=123)
+    ostep.train_step(state, det, ir, rgb, targets, size=640, det_seed=7)          # warm-up
+    times, t_start = [], time.perf_counter()
+    while len(times) < 3 or (time.perf_counter() - t_start < budget_s and len(times) < 8):
+        t0 = time.perf_counter()
+        ostep.train_step(state, det, ir, rgb, targets, size=640, det_seed=7)
+        times.append(time.perf_counter() - t0)
+    t = statistics.median(times)
+    return {"value": 1.0 / t, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"{len(times)} train steps of B=1 512x640 S=640 (fp32 oracle port, torch CPU, {cores} threads), median"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--detector", default="fasterrcnn")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pixel", default=None, help="enable the pixel regulariser (mse / l1); default off as in the reference config")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from hallucidet_b200 import ops
+    from hallucidet_b200.train import HalluciDetTrainer
+    from oracle import step as ostep            # synthetic input generator only (no oracle compute on this arm)
+
+    torch.backends.cudnn.benchmark = True       # train_hallucidet.py:28-29
+    B, H, W, S = args.batch, 512, 640, 640
+    weights = {"pixel_rgb": 1.0, "pixel_ir": 1.0} if args.pixel else None
+    tr = HalluciDetTrainer(detector_name=args.detector, size=S, pixel=args.pixel, weights=weights, seed=123, device=dev,
+                           use_cuda_graph=not args.no_graph)
+    ir_h, rgb_h, targets = ostep.synthetic_batch(B, H, W, seed=123 + rank)
+    ir_h, rgb_h = ir_h.pin_memory(), rgb_h.pin_memory()
+    targets = [{k: v.to(dev) for k, v in t.items()} for t in targets]
+    ir_d, rgb_d = ir_h.to(dev), rgb_h.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    def step_resident():
+        tr.training_step(rgb_d, targets, ir_d, targets)
+
+    host_loss = []
+
+    def step_e2e():
+        ir = ir_h.to(dev, non_blocking=True)
+        rgb = rgb_h.to(dev, non_blocking=True)
+        out = tr.training_step(rgb, targets, ir, targets)
+        host_loss.append(float(out["total"].detach()))          # device -> host read of the step's result
+
+    ops.LAUNCHES = 0
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+    # our kernel launches per step (graph replays re-issue the same captured launches)
+    was_graph = tr.encoder_decoder.use_cuda_graph
+    tr.encoder_decoder.use_cuda_graph = tr.detector.backbone.use_cuda_graph = False
+    ops.LAUNCHES = 0
+    step_resident()
+    torch.cuda.synchronize()
+    launches_per_step = ops.LAUNCHES
+    # per-launch device time of the conv GEMM kernels (CUDA events on the launching stream), for the roofline
+    ops.PROFILE = []
+    step_resident()
+    torch.cuda.synchronize()
+    prof = [(name, flops, a.elapsed_time(b)) for name, flops, a, b in ops.PROFILE]
+    ops.PROFILE = None
+    tr.encoder_decoder.use_cuda_graph = tr.detector.backbone.use_cuda_graph = was_graph
+    for _ in range(2):
+        step_resident()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step_resident, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps)
+
+    if rank == 0:
+        ms_step = ms / args.steps
+        value = world * B * args.steps / (ms / 1e3)
+        e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+        burst, sustained, hbm, which = load_peaks()
+        conv = [p for p in prof if p[0] in ("conv_fwd", "conv_dgrad", "conv_wgrad")]
+        conv_flops = sum(p[1] for p in conv)
+        conv_ms = sum(p[2] for p in conv)
+        achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        gemm_only = [p for p in prof if p[0] in ("conv_fwd", "conv_dgrad")]
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"HalluciDet train step: U-Net(ResNet-34) fwd/bwd + frozen {args.detector} R50-FPN detection-loss dgrad, "
+                                   f"batch {B}/GPU, 512x640 IR, S={S}, Adam + clip 0.5",
+                       "detector": args.detector, "batch_per_gpu": B, "input": "512x640", "detector_size": S,
+                       "parallelism": f"dp{world}", "cuda_graph": bool(was_graph), "pixel_regulariser": args.pixel,
+                       "l2": "working set (activations + weights, several GB per step) far exceeds the 126 MB L2; no explicit flush"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": ir_h.numel() * 4 + rgb_h.numel() * 4, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel + wgrad_gemm_kernel (tcgen05 implicit GEMM)",
+                         "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "peak_source": which,
+                         "traffic": None, "conv_launches_per_step": len(conv), "conv_ms_per_step": conv_ms,
+                         "conv_gflop_per_step": conv_flops / 1e9,
+                         "fwd_dgrad_tflops": (sum(p[1] for p in gemm_only) / (sum(p[2] for p in gemm_only) * 1e-3) / 1e12) if gemm_only else None,
+                         "all_kernels_ms_per_step": sum(p[2] for p in prof),
+                         "step_tflops_algorithmic": GFLOP_PER_IMAGE * value / world / 1e3,
+                         "step_frac_of_sustained_peak": GFLOP_PER_IMAGE * value / world / 1e3 / sustained},
+            "loss": host_loss[-1] if host_loss else None,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_sample()
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

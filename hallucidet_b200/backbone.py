@@ -220,7 +220,7 @@ class _BackboneEngine:
     def _forward_impl(self):
         st = self.stem
         ops.stem_im2col(self.x_in, self.patches)
-        ops.conv_fwd(ops.conv_args(self.patches, st.y.view(1, 1, -1, 64), st.packed.w_fwd, k=1, bias=st.bias, relu=True))
+        ops.conv_fwd(ops.conv_args(self.patches, st.y.view(1, 1, -1, 64), st.packed.w_fwd, k=1, bias=st.bias, relu=True, algo_cin=147))
         ops.maxpool_fwd(st.y, self.p0)
         x = self.p0
         for blk in self.blocks:
@@ -327,5 +327,5 @@ class _BackboneEngine:
         g_stem = self.gbuf(("g", "stem"), st.y)
         ops.maxpool_bwd(st.y, self.p0, g_next, g_stem, relu_mask=True)
         dpatch = self.gbuf(("dpatch", 0), self.patches)
-        ops.conv_fwd(ops.conv_args(g_stem.view(1, 1, -1, 64), dpatch, st.packed.w_t, k=1))
+        ops.conv_fwd(ops.conv_args(g_stem.view(1, 1, -1, 64), dpatch, st.packed.w_t, k=1, algo_cout=147))
         ops.stem_col2im(dpatch, self.dx)

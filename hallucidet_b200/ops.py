@@ -14,6 +14,31 @@ from ._lib import HdAct, HdConvArgs, check
 STATS_REPLICAS = 16
 STEM_KPAD = 160          # 7*7*3 = 147 -> 5 k-blocks of 32
 
+LAUNCHES = 0             # kernels launched through this module (each C-ABI compute call launches exactly one kernel)
+PROFILE = None           # set to a list to record (name, algorithmic FLOPs, start event, end event) per launch
+
+
+class _Timed:
+    """Context manager that brackets one launch with CUDA events on the launching stream when PROFILE is on."""
+
+    def __init__(self, name, flops=0.0):
+        self.name, self.flops = name, flops
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        global LAUNCHES
+        LAUNCHES += 1
+        if PROFILE is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((self.name, self.flops, self.e0, e1))
+        return False
+
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -35,8 +60,10 @@ def round_up(a, b):
 
 
 def conv_args(x0, y0, w=None, k=3, stride=1, x1=None, y1=None, bias=None, add=None, mask=None, relu=False, sigmoid=False,
-              stats=None, out_f32=None, out_f32_channels=0, store_bf16=True, phase_mask=0, dw=None, split_k=0):
+              stats=None, out_f32=None, out_f32_channels=0, store_bf16=True, phase_mask=0, dw=None, split_k=0,
+              algo_cin=None, algo_cout=None):
     a = HdConvArgs()
+    a.algo = (algo_cin, algo_cout)
     a.x0, a.x1, a.y0, a.y1 = act(x0), act(x1), act(y0), act(y1)
     a.w = w.data_ptr() if w is not None else None
     a.kh = a.kw = k
@@ -56,16 +83,36 @@ def conv_args(x0, y0, w=None, k=3, stride=1, x1=None, y1=None, bias=None, add=No
     return a
 
 
+def _conv_flops(a, kind):
+    """Algorithmic FLOPs (2*MACs) of the convolution the launch implements (padding channels excluded)."""
+    k2 = a.kh * a.kw
+    if kind == "fwd":
+        cin, cout, pix = a.x0.c + a.x1.c, a.y0.c, a.y0.n * a.y0.h * a.y0.w
+    elif kind == "dgrad":       # x0 = dY (conv output), y = dX (conv input)
+        cin, cout, pix = a.y0.c + a.y1.c, a.x0.c, a.x0.n * a.x0.h * a.x0.w
+    else:                       # wgrad: x = conv input, y0 = dY
+        cin, cout, pix = a.x0.c + a.x1.c, a.y0.c, a.y0.n * a.y0.h * a.y0.w
+    algo = getattr(a, "algo", (None, None))
+    if algo[0] is not None:
+        cin, k2 = algo[0], 1
+    if algo[1] is not None:
+        cout = algo[1]
+    return 2.0 * pix * cin * cout * k2
+
+
 def conv_fwd(args):
-    check(_lib.load().hd_conv_fwd(ctypes.byref(args), _stream()), "hd_conv_fwd")
+    with _Timed("conv_fwd", _conv_flops(args, "fwd") if PROFILE is not None else 0.0):
+        check(_lib.load().hd_conv_fwd(ctypes.byref(args), _stream()), "hd_conv_fwd")
 
 
 def conv_dgrad(args):
-    check(_lib.load().hd_conv_dgrad(ctypes.byref(args), _stream()), "hd_conv_dgrad")
+    with _Timed("conv_dgrad", _conv_flops(args, "dgrad") if PROFILE is not None else 0.0):
+        check(_lib.load().hd_conv_dgrad(ctypes.byref(args), _stream()), "hd_conv_dgrad")
 
 
 def conv_wgrad(args):
-    check(_lib.load().hd_conv_wgrad(ctypes.byref(args), _stream()), "hd_conv_wgrad")
+    with _Timed("conv_wgrad", _conv_flops(args, "wgrad") if PROFILE is not None else 0.0):
+        check(_lib.load().hd_conv_wgrad(ctypes.byref(args), _stream()), "hd_conv_wgrad")
 
 
 class PackedConv:
@@ -82,121 +129,141 @@ class PackedConv:
 
     def pack(self, w_oihw, scale=None):
         assert w_oihw.dtype == torch.float32 and w_oihw.is_contiguous() and tuple(w_oihw.shape) == (self.cout, self.cin, self.k, self.k)
-        check(_lib.load().hd_pack_conv_weight(_ptr(w_oihw), _ptr(scale), self.cout, self.cin, self.k, self.k, _ptr(self.w_fwd),
-                                              self.cout_pad, self.k_pad, _ptr(self.w_dgrad), self.cin_pad, _ptr(self.w_t),
-                                              _stream()), "hd_pack_conv_weight")
+        with _Timed("pack_conv_weight"):
+            check(_lib.load().hd_pack_conv_weight(_ptr(w_oihw), _ptr(scale), self.cout, self.cin, self.k, self.k, _ptr(self.w_fwd),
+                                                  self.cout_pad, self.k_pad, _ptr(self.w_dgrad), self.cin_pad, _ptr(self.w_t),
+                                                  _stream()), "hd_pack_conv_weight")
         return self
 
 
 def unpack_wgrad(dw_packed, grad_oihw, cout, cin, k, tap_stride, row_stride, scale=1.0):
-    check(_lib.load().hd_unpack_wgrad(_ptr(dw_packed), _ptr(grad_oihw), cout, cin, k, k, tap_stride, row_stride, scale, _stream()),
-          "hd_unpack_wgrad")
+    with _Timed("unpack_wgrad"):
+        check(_lib.load().hd_unpack_wgrad(_ptr(dw_packed), _ptr(grad_oihw), cout, cin, k, k, tap_stride, row_stride, scale, _stream()),
+              "hd_unpack_wgrad")
 
 
 def stem_im2col(x_nchw, patches, k_pad=STEM_KPAD):
     n, c, h, w = x_nchw.shape
     assert c == 3 and x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()
-    check(_lib.load().hd_stem_im2col(_ptr(x_nchw), _ptr(patches), n, h, w, k_pad, _stream()), "hd_stem_im2col")
+    with _Timed("stem_im2col"):
+        check(_lib.load().hd_stem_im2col(_ptr(x_nchw), _ptr(patches), n, h, w, k_pad, _stream()), "hd_stem_im2col")
 
 
 def stem_col2im(dpatches, dx_nchw, k_pad=STEM_KPAD):
     n, c, h, w = dx_nchw.shape
     assert c == 3 and dx_nchw.dtype == torch.float32 and dx_nchw.is_contiguous()
-    check(_lib.load().hd_stem_col2im(_ptr(dpatches), _ptr(dx_nchw), n, h, w, k_pad, _stream()), "hd_stem_col2im")
+    with _Timed("stem_col2im"):
+        check(_lib.load().hd_stem_col2im(_ptr(dpatches), _ptr(dx_nchw), n, h, w, k_pad, _stream()), "hd_stem_col2im")
 
 
 def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale, shift):
     c = gamma.numel()
-    check(_lib.load().hd_bn_finalize(_ptr(stats), stats.shape[0], c, float(count), _ptr(gamma), _ptr(beta), eps, momentum,
-                                     _ptr(running_mean), _ptr(running_var), _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift),
-                                     _stream()), "hd_bn_finalize")
+    with _Timed("bn_finalize"):
+        check(_lib.load().hd_bn_finalize(_ptr(stats), stats.shape[0], c, float(count), _ptr(gamma), _ptr(beta), eps, momentum,
+                                         _ptr(running_mean), _ptr(running_var), _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift),
+                                         _stream()), "hd_bn_finalize")
 
 
 def bn_apply(z, scale, shift, y, relu=True, res=None, res_scale=None, res_shift=None):
     c = z.shape[-1]
-    check(_lib.load().hd_bn_apply(_ptr(z), _ptr(scale), _ptr(shift), _ptr(res), _ptr(res_scale), _ptr(res_shift), int(relu),
-                                  _ptr(y), z.numel() // c, c, _stream()), "hd_bn_apply")
+    with _Timed("bn_apply"):
+        check(_lib.load().hd_bn_apply(_ptr(z), _ptr(scale), _ptr(shift), _ptr(res), _ptr(res_scale), _ptr(res_shift), int(relu),
+                                      _ptr(y), z.numel() // c, c, _stream()), "hd_bn_apply")
 
 
 def bn_bwd_reduce(dy, y_relu, z, mean, invstd, sums):
     c = z.shape[-1]
-    check(_lib.load().hd_bn_bwd_reduce(_ptr(dy), _ptr(y_relu), _ptr(z), _ptr(mean), _ptr(invstd), _ptr(sums), z.numel() // c, c,
-                                       _stream()), "hd_bn_bwd_reduce")
+    with _Timed("bn_bwd_reduce"):
+        check(_lib.load().hd_bn_bwd_reduce(_ptr(dy), _ptr(y_relu), _ptr(z), _ptr(mean), _ptr(invstd), _ptr(sums), z.numel() // c, c,
+                                           _stream()), "hd_bn_bwd_reduce")
 
 
 def bn_bwd_apply(dy, y_relu, z, mean, invstd, gamma, sums, dz, g_out=None, dgamma=None, dbeta=None):
     c = z.shape[-1]
     n_pix = z.numel() // c
-    check(_lib.load().hd_bn_bwd_apply(_ptr(dy), _ptr(y_relu), _ptr(z), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(sums),
-                                      float(n_pix), _ptr(dz), _ptr(g_out), _ptr(dgamma), _ptr(dbeta), n_pix, c, _stream()),
-          "hd_bn_bwd_apply")
+    with _Timed("bn_bwd_apply"):
+        check(_lib.load().hd_bn_bwd_apply(_ptr(dy), _ptr(y_relu), _ptr(z), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(sums),
+                                          float(n_pix), _ptr(dz), _ptr(g_out), _ptr(dgamma), _ptr(dbeta), n_pix, c, _stream()),
+              "hd_bn_bwd_apply")
 
 
 def maxpool_fwd(x, y):
     ax, ay = act(x), act(y)
-    check(_lib.load().hd_maxpool_fwd(ctypes.byref(ax), ctypes.byref(ay), _stream()), "hd_maxpool_fwd")
+    with _Timed("maxpool_fwd"):
+        check(_lib.load().hd_maxpool_fwd(ctypes.byref(ax), ctypes.byref(ay), _stream()), "hd_maxpool_fwd")
 
 
 def maxpool_bwd(x, y, dy, dx, add=None, relu_mask=False):
     ax, ay = act(x), act(y)
-    check(_lib.load().hd_maxpool_bwd(ctypes.byref(ax), ctypes.byref(ay), _ptr(dy), _ptr(add), _ptr(dx), int(relu_mask), _stream()),
-          "hd_maxpool_bwd")
+    with _Timed("maxpool_bwd"):
+        check(_lib.load().hd_maxpool_bwd(ctypes.byref(ax), ctypes.byref(ay), _ptr(dy), _ptr(add), _ptr(dx), int(relu_mask), _stream()),
+              "hd_maxpool_bwd")
 
 
 def upsample2x_fwd(x, y):
     ax, ay = act(x), act(y)
-    check(_lib.load().hd_upsample2x_fwd(ctypes.byref(ax), ctypes.byref(ay), _stream()), "hd_upsample2x_fwd")
+    with _Timed("upsample2x_fwd"):
+        check(_lib.load().hd_upsample2x_fwd(ctypes.byref(ax), ctypes.byref(ay), _stream()), "hd_upsample2x_fwd")
 
 
 def upsample2x_bwd(dy, dx):
     ay, ax = act(dy), act(dx)
-    check(_lib.load().hd_upsample2x_bwd(ctypes.byref(ay), ctypes.byref(ax), _stream()), "hd_upsample2x_bwd")
+    with _Timed("upsample2x_bwd"):
+        check(_lib.load().hd_upsample2x_bwd(ctypes.byref(ay), ctypes.byref(ax), _stream()), "hd_upsample2x_bwd")
 
 
 def add_nearest_fwd(x, y):
     ax, ay = act(x), act(y)
-    check(_lib.load().hd_add_nearest_fwd(ctypes.byref(ax), ctypes.byref(ay), _stream()), "hd_add_nearest_fwd")
+    with _Timed("add_nearest_fwd"):
+        check(_lib.load().hd_add_nearest_fwd(ctypes.byref(ax), ctypes.byref(ay), _stream()), "hd_add_nearest_fwd")
 
 
 def add_nearest_bwd(dy, dx, accumulate=False):
     ay, ax = act(dy), act(dx)
-    check(_lib.load().hd_add_nearest_bwd(ctypes.byref(ay), ctypes.byref(ax), int(accumulate), _stream()), "hd_add_nearest_bwd")
+    with _Timed("add_nearest_bwd"):
+        check(_lib.load().hd_add_nearest_bwd(ctypes.byref(ay), ctypes.byref(ax), int(accumulate), _stream()), "hd_add_nearest_bwd")
 
 
 def nchw_f32_to_nhwc_bf16(x, y, accumulate=False):
     assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[0] == y.shape[0] and x.shape[2:] == y.shape[1:3]
     ay = act(y)
-    check(_lib.load().hd_nchw_f32_to_nhwc_bf16(_ptr(x), ctypes.byref(ay), x.shape[1], int(accumulate), _stream()),
-          "hd_nchw_f32_to_nhwc_bf16")
+    with _Timed("nchw_f32_to_nhwc_bf16"):
+        check(_lib.load().hd_nchw_f32_to_nhwc_bf16(_ptr(x), ctypes.byref(ay), x.shape[1], int(accumulate), _stream()),
+              "hd_nchw_f32_to_nhwc_bf16")
 
 
 def nhwc_bf16_to_nchw_f32(x, y):
     assert y.dtype == torch.float32 and y.is_contiguous()
     ax = act(x)
-    check(_lib.load().hd_nhwc_bf16_to_nchw_f32(ctypes.byref(ax), _ptr(y), y.shape[1], _stream()), "hd_nhwc_bf16_to_nchw_f32")
+    with _Timed("nhwc_bf16_to_nchw_f32"):
+        check(_lib.load().hd_nhwc_bf16_to_nchw_f32(ctypes.byref(ax), _ptr(y), y.shape[1], _stream()), "hd_nhwc_bf16_to_nchw_f32")
 
 
 def sigmoid_bwd_pack(dhal, hal, dlogits, dbias=None):
     ad = act(dlogits)
-    check(_lib.load().hd_sigmoid_bwd_pack(_ptr(dhal), _ptr(hal), ctypes.byref(ad), hal.shape[1], _ptr(dbias), _stream()),
-          "hd_sigmoid_bwd_pack")
+    with _Timed("sigmoid_bwd_pack"):
+        check(_lib.load().hd_sigmoid_bwd_pack(_ptr(dhal), _ptr(hal), ctypes.byref(ad), hal.shape[1], _ptr(dbias), _stream()),
+              "hd_sigmoid_bwd_pack")
 
 
 def resize_nearest_fwd(x, y, mean=None, std=None):
     n, c, hi, wi = x.shape
     ho, wo = y.shape[-2:]
-    check(_lib.load().hd_resize_nearest_fwd(_ptr(x), _ptr(y), n, c, hi, wi, ho, wo, _ptr(mean), _ptr(std), _stream()),
-          "hd_resize_nearest_fwd")
+    with _Timed("resize_nearest_fwd"):
+        check(_lib.load().hd_resize_nearest_fwd(_ptr(x), _ptr(y), n, c, hi, wi, ho, wo, _ptr(mean), _ptr(std), _stream()),
+              "hd_resize_nearest_fwd")
 
 
 def resize_nearest_bwd(dy, dx, std=None, accumulate=False):
     n, c, hi, wi = dx.shape
     ho, wo = dy.shape[-2:]
-    check(_lib.load().hd_resize_nearest_bwd(_ptr(dy), _ptr(dx), n, c, hi, wi, ho, wo, _ptr(std), int(accumulate), _stream()),
-          "hd_resize_nearest_bwd")
+    with _Timed("resize_nearest_bwd"):
+        check(_lib.load().hd_resize_nearest_bwd(_ptr(dy), _ptr(dx), n, c, hi, wi, ho, wo, _ptr(std), int(accumulate), _stream()),
+              "hd_resize_nearest_bwd")
 
 
 def regulariser(kind, hal, rgb, ir, w_rgb, w_ir, loss, dhal=None, grad_scale=1.0, accumulate=False):
     n, _, h, w = hal.shape
-    check(_lib.load().hd_regulariser({"mse": 0, "l1": 1}[kind], _ptr(hal), _ptr(rgb), _ptr(ir), w_rgb, w_ir, n, h, w, _ptr(loss),
-                                     _ptr(dhal), grad_scale, int(accumulate), _stream()), "hd_regulariser")
+    with _Timed("regulariser"):
+        check(_lib.load().hd_regulariser({"mse": 0, "l1": 1}[kind], _ptr(hal), _ptr(rgb), _ptr(ir), w_rgb, w_ir, n, h, w, _ptr(loss),
+                                         _ptr(dhal), grad_scale, int(accumulate), _stream()), "hd_regulariser")

@@ -374,13 +374,13 @@ class _UnetEngine:
         a_stem_flat = self.a_stem.view(1, 1, -1, 64)
         if self.training:
             st.stats.zero_()
-            ops.conv_fwd(ops.conv_args(self.patches, zs, st.packed.w_fwd, k=1, stats=st.stats))
+            ops.conv_fwd(ops.conv_args(self.patches, zs, st.packed.w_fwd, k=1, stats=st.stats, algo_cin=147))
             bn = st.bn
             ops.bn_finalize(st.stats, zs.shape[2], bn.weight.detach(), bn.bias.detach(), bn.eps, bn.momentum or 0.1,
                             bn.running_mean, bn.running_var, st.mean, st.invstd, st.scale, st.shift)
             ops.bn_apply(zs, st.scale, st.shift, a_stem_flat, relu=True)
         else:
-            ops.conv_fwd(ops.conv_args(self.patches, a_stem_flat, st.packed.w_fwd, k=1, bias=st.bias, relu=True))
+            ops.conv_fwd(ops.conv_args(self.patches, a_stem_flat, st.packed.w_fwd, k=1, bias=st.bias, relu=True, algo_cin=147))
         ops.maxpool_fwd(self.a_stem, self.p0)
         x_in = self.p0
         feats = {1: self.a_stem}
@@ -406,7 +406,7 @@ class _UnetEngine:
             xd = d["a2"]
         hd = self.head
         ops.conv_fwd(ops.conv_args(xd, hd.z, hd.packed.w_fwd, k=3, bias=self.head_bias_pad, sigmoid=sigmoid, out_f32=self.hal,
-                                   out_f32_channels=hd.cout, store_bf16=False))
+                                   out_f32_channels=hd.cout, store_bf16=False, algo_cout=hd.cout))
         self.head_in = xd
         if self.training:
             torch._foreach_add_(self.nbt, 1)
@@ -423,7 +423,7 @@ class _UnetEngine:
         return dz
 
     def _wgrad(self, l, x0, dz, x1=None):
-        ops.conv_wgrad(ops.conv_args(x0, dz, k=l.k, stride=l.stride, x1=x1, dw=l.dw))
+        ops.conv_wgrad(ops.conv_args(x0, dz, k=l.k, stride=l.stride, x1=x1, dw=l.dw, algo_cout=l.cout))
         ops.unpack_wgrad(l.dw, self.grad_views[l.name + ".weight"], l.cout, l.cin, l.k, l.cin, l.k * l.k * l.cin)
 
     def _backward_impl(self):
@@ -435,7 +435,7 @@ class _UnetEngine:
         ops.sigmoid_bwd_pack(dhal, self.hal, self.dlogits, gv["segmentation_head.0.bias"])
         self._wgrad(hd, self.head_in, self.dlogits)
         g = self.gbuf(("g", "head_in"), self.head_in)
-        ops.conv_dgrad(ops.conv_args(self.dlogits, g, hd.packed.w_dgrad, k=3))
+        ops.conv_dgrad(ops.conv_args(self.dlogits, g, hd.packed.w_dgrad, k=3, algo_cout=hd.cout))
         # ---- decoder
         skip_grads = {}
         for i in reversed(range(len(self.dblocks))):
@@ -483,5 +483,5 @@ class _UnetEngine:
         ops.maxpool_bwd(self.a_stem, self.p0, g, g_stem, add=skip_grads[3])
         zs = st.z.view(1, 1, -1, 64)
         dzs = self._bn_bwd(st, g_stem.view(1, 1, -1, 64), self.a_stem.view(1, 1, -1, 64), z=zs)
-        ops.conv_wgrad(ops.conv_args(self.patches, dzs, k=1, dw=st.dw))
+        ops.conv_wgrad(ops.conv_args(self.patches, dzs, k=1, dw=st.dw, algo_cin=147))
         ops.unpack_wgrad(st.dw, gv["encoder.conv1.weight"], 64, 3, 7, 3, ops.STEM_KPAD)
