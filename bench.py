@@ -212,7 +212,9 @@ def main():
     ops.PROFILE = []
     step_resident()
     torch.cuda.synchronize()
-    prof = [(name, flops, a.elapsed_time(b)) for name, flops, a, b in ops.PROFILE]
+    prof = [(name, flops, a.elapsed_time(b), desc) for name, flops, a, b, desc in ops.PROFILE]
+    if rank == 0 and os.environ.get("HD_PROFILE_DUMP"):
+        json.dump(prof, open(os.environ["HD_PROFILE_DUMP"], "w"))
     ops.PROFILE = None
     tr.encoder_decoder.use_cuda_graph = tr.detector.backbone.use_cuda_graph = was_graph
     for _ in range(2):

@@ -21,8 +21,8 @@ PROFILE = None           # set to a list to record (name, algorithmic FLOPs, sta
 class _Timed:
     """Context manager that brackets one launch with CUDA events on the launching stream when PROFILE is on."""
 
-    def __init__(self, name, flops=0.0):
-        self.name, self.flops = name, flops
+    def __init__(self, name, flops=0.0, desc=""):
+        self.name, self.flops, self.desc = name, flops, desc
 
     def __enter__(self):
         if PROFILE is not None:
@@ -36,7 +36,7 @@ class _Timed:
         if PROFILE is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            PROFILE.append((self.name, self.flops, self.e0, e1))
+            PROFILE.append((self.name, self.flops, self.e0, e1, self.desc))
         return False
 
 
@@ -100,18 +100,23 @@ def _conv_flops(a, kind):
     return 2.0 * pix * cin * cout * k2
 
 
+def _conv_desc(a):
+    return (f"x0[{a.x0.n},{a.x0.h},{a.x0.w},{a.x0.c}] x1c{a.x1.c} y0[{a.y0.n},{a.y0.h},{a.y0.w},{a.y0.c}] y1c{a.y1.c} "
+            f"k{a.kh} s{a.stride}")
+
+
 def conv_fwd(args):
-    with _Timed("conv_fwd", _conv_flops(args, "fwd") if PROFILE is not None else 0.0):
+    with _Timed("conv_fwd", _conv_flops(args, "fwd") if PROFILE is not None else 0.0, _conv_desc(args) if PROFILE is not None else ""):
         check(_lib.load().hd_conv_fwd(ctypes.byref(args), _stream()), "hd_conv_fwd")
 
 
 def conv_dgrad(args):
-    with _Timed("conv_dgrad", _conv_flops(args, "dgrad") if PROFILE is not None else 0.0):
+    with _Timed("conv_dgrad", _conv_flops(args, "dgrad") if PROFILE is not None else 0.0, _conv_desc(args) if PROFILE is not None else ""):
         check(_lib.load().hd_conv_dgrad(ctypes.byref(args), _stream()), "hd_conv_dgrad")
 
 
 def conv_wgrad(args):
-    with _Timed("conv_wgrad", _conv_flops(args, "wgrad") if PROFILE is not None else 0.0):
+    with _Timed("conv_wgrad", _conv_flops(args, "wgrad") if PROFILE is not None else 0.0, _conv_desc(args) if PROFILE is not None else ""):
         check(_lib.load().hd_conv_wgrad(ctypes.byref(args), _stream()), "hd_conv_wgrad")
 
 
