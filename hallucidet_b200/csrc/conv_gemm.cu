@@ -21,7 +21,9 @@
 namespace hd {
 
 constexpr int kMaxTaps = 9;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quadrant, each takes half of the N columns
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;
 
 struct ConvGemmParams {
     CUtensorMap tmA[2];
@@ -49,42 +51,60 @@ struct ConvGemmParams {
     int store_bf16;
     int stages, a_bytes, stage_bytes;
     int tmem_cols;
+    int m_tiles, n_tiles, nphases;
 };
 
-__global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_constant__ ConvGemmParams P) {
+__device__ __forceinline__ void decode_tile(const ConvGemmParams& P, int tile, int& z, int& n0, int& img, int& h0, int& w0) {
+    // m tiles fastest: CTAs running concurrently share the weight tile (L2) and walk neighbouring pixels
+    const int per_phase = P.m_tiles * P.n_tiles;
+    z = tile / per_phase;
+    const int rem = tile - z * per_phase;
+    const int nt = rem / P.m_tiles;
+    const int mt = rem - nt * P.m_tiles;
+    n0 = nt * P.BN;
+    const int tw_i = mt % P.tiles_w;
+    const int th_i = (mt / P.tiles_w) % P.tiles_h;
+    img = mt / (P.tiles_w * P.tiles_h);
+    w0 = tw_i * P.TW;
+    h0 = th_i * P.TH;
+}
+
+// Persistent CTA (one per SM): a static round-robin over output tiles; the TMA producer and the MMA issuer run
+// ahead across tile boundaries, the accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the
+// main loop of tile i+1.
+__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
     const int stages = P.stages;
-    const uint32_t bar_base = smem_base + static_cast<uint32_t>(max(stages * P.stage_bytes, 128 * P.BN * 2));
-    // barriers: full[s] at +8s, empty[s] at +8(stages+s), tmem_full at +16*stages, tmem ptr at +16*stages+8
-    const uint32_t full0 = bar_base, empty0 = bar_base + 8u * stages, tfull = bar_base + 16u * stages;
-    const uint32_t tmem_slot = tfull + 8u;
-
-    const int z = blockIdx.z;
-    const int tile = blockIdx.x;
-    const int tw_i = tile % P.tiles_w;
-    const int th_i = (tile / P.tiles_w) % P.tiles_h;
-    const int img = tile / (P.tiles_w * P.tiles_h);
-    const int w0 = tw_i * P.TW, h0 = th_i * P.TH;
-    const int n0 = blockIdx.y * P.BN;
-    const int tap_lo = P.tap_begin[z];
-    const int num_k = (P.tap_begin[z + 1] - tap_lo) * P.kpt;
+    const uint32_t stg_bytes = (128u * P.BN * 2u + 1023u) & ~1023u;
+    const uint32_t staging0 = smem_base + static_cast<uint32_t>(stages * P.stage_bytes);  // 2 x (128 x BN bf16), 1024-aligned
+    const uint32_t bias_s = staging0 + 2u * stg_bytes;                                     // BN floats
+    const uint32_t stat_s = bias_s + 512u;                                                 // 2 x BN floats (per-tile BN statistics)
+    const uint32_t bar_base = stat_s + 1024u;
+    // barriers: full[s], empty[s], tmem_full[2], tmem_empty[2], then the TMEM base-address slot
+    const uint32_t full0 = bar_base, empty0 = bar_base + 8u * stages;
+    const uint32_t tfull0 = bar_base + 16u * stages, tempty0 = tfull0 + 16u;
+    const uint32_t tmem_slot = tempty0 + 16u;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(full0 + 8u * s, 1);
             mbar_init(empty0 + 8u * s, 1);
         }
-        mbar_init(tfull, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull0 + 8u * a, 1);
+            mbar_init(tempty0 + 8u * a, kEpiWarps);         // one arrival per epilogue warp
+        }
         mbar_fence_init();
         tma_prefetch_desc(&P.tmA[0]);
         tma_prefetch_desc(&P.tmB);
+        tma_prefetch_desc(&P.tmOut[0]);
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, P.tmem_cols);
+        tmem_alloc(tmem_slot, 2 * P.tmem_cols);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -93,25 +113,32 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+    const int total_tiles = P.m_tiles * P.n_tiles * P.nphases;
+
     if (warp == 0) {
         // ================= TMA producer =================
         if (elect_one()) {
             const uint32_t tx_bytes = static_cast<uint32_t>((P.TW * P.TH + P.BN) * P.BK * 2);
             int stage = 0;
             uint32_t phase = 0;
-            int tap = tap_lo, kb = 0;
-            for (int ks = 0; ks < num_k; ++ks) {
-                mbar_wait(empty0 + 8u * stage, phase ^ 1u);
-                const uint32_t sa = smem_base + stage * P.stage_bytes;
-                const uint32_t sb = sa + P.a_bytes;
-                const uint32_t fb = full0 + 8u * stage;
-                mbar_expect_tx(fb, tx_bytes);
-                const int src = kb < P.kb_split ? 0 : 1;
-                const int c = (src ? kb - P.kb_split : kb) * P.BK + P.tap_q[tap] * P.a_qstride[src];
-                tma_load_5d(sa, &P.tmA[src], fb, c, w0 + P.tap_dw[tap], P.tap_p[tap], h0 + P.tap_dh[tap], img);
-                tma_load_2d(sb, &P.tmB, fb, P.tap_bk[tap] + kb * P.BK, n0);
-                if (++kb == P.kpt) { kb = 0; ++tap; }
-                if (++stage == stages) { stage = 0; phase ^= 1u; }
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int z, n0, img, h0, w0;
+                decode_tile(P, tile, z, n0, img, h0, w0);
+                int tap = P.tap_begin[z], kb = 0;
+                const int num_k = (P.tap_begin[z + 1] - tap) * P.kpt;
+                for (int ks = 0; ks < num_k; ++ks) {
+                    mbar_wait(empty0 + 8u * stage, phase ^ 1u);
+                    const uint32_t sa = smem_base + stage * P.stage_bytes;
+                    const uint32_t sb = sa + P.a_bytes;
+                    const uint32_t fb = full0 + 8u * stage;
+                    mbar_expect_tx(fb, tx_bytes);
+                    const int src = kb < P.kb_split ? 0 : 1;
+                    const int c = (src ? kb - P.kb_split : kb) * P.BK + P.tap_q[tap] * P.a_qstride[src];
+                    tma_load_5d(sa, &P.tmA[src], fb, c, w0 + P.tap_dw[tap], P.tap_p[tap], h0 + P.tap_dh[tap], img);
+                    tma_load_2d(sb, &P.tmB, fb, P.tap_bk[tap] + kb * P.BK, n0);
+                    if (++kb == P.kpt) { kb = 0; ++tap; }
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                }
             }
         }
     } else if (warp == 1) {
@@ -121,153 +148,228 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
             const uint32_t swz_bytes = P.BK * 2;
             const uint32_t lt = swizzle_layout_type(swz_bytes);
             const uint32_t sbo = 8u * swz_bytes;
+            const int ksub = P.BK / 16;
             int stage = 0;
             uint32_t phase = 0;
-            for (int ks = 0; ks < num_k; ++ks) {
-                mbar_wait(full0 + 8u * stage, phase);
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int z = tile / (P.m_tiles * P.n_tiles);
+                const int num_k = (P.tap_begin[z + 1] - P.tap_begin[z]) * P.kpt;
+                mbar_wait(tempty0 + 8u * acc, acc_phase ^ 1u);          // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t sa = smem_base + stage * P.stage_bytes;
-                const uint32_t sb = sa + P.a_bytes;
-                for (int k = 0; k < P.BK / 16; ++k) {
-                    const uint64_t da = make_smem_desc(sa + k * 32, 16, sbo, lt);
-                    const uint64_t db = make_smem_desc(sb + k * 32, 16, sbo, lt);
-                    umma_bf16(tmem_base, da, db, idesc, (ks | k) != 0);
+                const uint32_t d_tmem = tmem_base + acc * P.tmem_cols;
+                for (int ks = 0; ks < num_k; ++ks) {
+                    mbar_wait(full0 + 8u * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * P.stage_bytes;
+                    const uint32_t sb = sa + P.a_bytes;
+                    for (int k = 0; k < ksub; ++k) {
+                        const uint64_t da = make_smem_desc(sa + k * 32, 16, sbo, lt);
+                        const uint64_t db = make_smem_desc(sb + k * 32, 16, sbo, lt);
+                        umma_bf16(d_tmem, da, db, idesc, (ks | k) != 0);
+                    }
+                    umma_commit(empty0 + 8u * stage);
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(empty0 + 8u * stage);
-                if (++stage == stages) { stage = 0; phase ^= 1u; }
+                umma_commit(tfull0 + 8u * acc);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
-            umma_commit(tfull);
         }
     } else {
-        // ================= epilogue (4 warps = 4 TMEM lane quadrants) =================
+        // ================= epilogue: 8 warps, warp w drains TMEM lane quadrant (w & 3), half of the columns =========
+        const int ew = warp - 2;
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
-        const int et = (warp - 2) * 32 + lane;            // 0..127 epilogue thread id
+        const int et = ew * 32 + lane;                    // 0..255 epilogue thread id
         const int hl = row / P.TW, wl = row - hl * P.TW;
-        const int hg = h0 + hl, wg = w0 + wl;
-        const bool valid = (row < P.TW * P.TH) && hg < P.Hg && wg < P.Wg;
-        const int ho = hg * P.ostride + P.out_p[z], wo = wg * P.ostride + P.out_q[z];
-        const long pix = (static_cast<long>(img) * P.Hout + ho) * P.Wout + wo;
         const int sub_c = P.BN < 64 ? P.BN : 64;            // channels per staging sub-tile
         const uint32_t row_b = sub_c * 2;
         const uint32_t smask = row_b / 16 - 1;
+        const int nchunk = P.BN / 16;
+        const int c_begin = nchunk >= 2 ? (ew >> 2) * (nchunk / 2) : ((ew >> 2) ? 1 : 0);
+        const int c_end = nchunk >= 2 ? c_begin + nchunk / 2 : 1;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+            int z, n0, img, h0, w0;
+            decode_tile(P, tile, z, n0, img, h0, w0);
+            const int num_k = (P.tap_begin[z + 1] - P.tap_begin[z]) * P.kpt;
+            const int hg = h0 + hl, wg = w0 + wl;
+            const bool valid = (row < P.TW * P.TH) && hg < P.Hg && wg < P.Wg;
+            const int ho = hg * P.ostride + P.out_p[z], wo = wg * P.ostride + P.out_q[z];
+            const long pix = (static_cast<long>(img) * P.Hout + ho) * P.Wout + wo;
+            const uint32_t staging = staging0 + (iter & 1) * stg_bytes;
+            const __nv_bfloat16* add_row = P.add != nullptr ? P.add + pix * P.Cout_total + n0 : nullptr;
+            const __nv_bfloat16* mask_row = P.mask != nullptr ? P.mask + pix * P.Cout_total + n0 : nullptr;
 
-        mbar_wait(tfull, 0);
-        tc_fence_after();
-        for (int c16 = 0; c16 < P.BN / 16; ++c16) {
-            uint32_t acc[16];
-            if (num_k > 0) {
-                tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c16 * 16, acc);
-                tmem_ld_wait();
-            } else {                                       // phase without filter taps: epilogue-only (add / mask)
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] = 0u;
+            // this staging buffer was last used two tiles ago: its TMA store must have finished reading it
+            if (iter >= 2 && et == 0) tma_store_wait_read1();
+            named_bar_sync(1, kEpiThreads);
+            if (P.bias != nullptr && et < P.BN) {
+                const int ch = n0 + et;
+                const float b = ch < P.Cout_total ? __ldg(P.bias + ch) : 0.f;
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * et), "f"(b) : "memory");
             }
-            const int ch0 = n0 + c16 * 16;
-            float v[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
-            if (P.bias != nullptr) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (ch0 + j < P.Cout_total) v[j] += __ldg(P.bias + ch0 + j);
+            if (P.stats != nullptr && et < 2 * P.BN)
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(stat_s + 4u * et), "f"(0.f) : "memory");
+            // fused-operand loads are software-pipelined one 16-column chunk ahead of their use
+            uint4 na0 = make_uint4(0, 0, 0, 0), na1 = na0, nm0 = na0, nm1 = na0;
+            if (c_begin < c_end && valid && n0 + c_begin * 16 < P.Cout_total) {
+                if (add_row) { const uint4* ap = reinterpret_cast<const uint4*>(add_row + c_begin * 16); na0 = ap[0]; na1 = ap[1]; }
+                if (mask_row) { const uint4* mp = reinterpret_cast<const uint4*>(mask_row + c_begin * 16); nm0 = __ldg(mp); nm1 = __ldg(mp + 1); }
             }
-            if (P.add != nullptr && valid && ch0 < P.Cout_total) {
-                const uint4* ap = reinterpret_cast<const uint4*>(P.add + pix * P.Cout_total + ch0);
-                const uint4 a0 = ap[0], a1 = ap[1];
-                const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            named_bar_sync(2, kEpiThreads);
+
+            mbar_wait(tfull0 + 8u * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t t_acc = tmem_base + acc * P.tmem_cols + (static_cast<uint32_t>(quad * 32) << 16);
+            for (int c16 = c_begin; c16 < c_end; ++c16) {
+                const int ch0 = n0 + c16 * 16;
+                const bool ch_ok = ch0 < P.Cout_total;
+                const uint4 a0 = na0, a1 = na1, m0 = nm0, m1 = nm1;
+                const bool has_add = add_row != nullptr && valid && ch_ok;
+                const bool has_mask = mask_row != nullptr && valid && ch_ok;
+                if (c16 + 1 < c_end && valid && ch0 + 16 < P.Cout_total) {
+                    if (add_row) { const uint4* ap = reinterpret_cast<const uint4*>(add_row + (c16 + 1) * 16); na0 = ap[0]; na1 = ap[1]; }
+                    if (mask_row) { const uint4* mp = reinterpret_cast<const uint4*>(mask_row + (c16 + 1) * 16); nm0 = __ldg(mp); nm1 = __ldg(mp + 1); }
+                }
+                uint32_t acc_r[16];
+                if (num_k > 0) {
+                    tmem_ld16(t_acc + c16 * 16, acc_r);
+                    tmem_ld_wait();
+                } else {                                   // phase without filter taps: epilogue-only (add / mask)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    v[2 * j] += bf16_lo(aw[j]);
-                    v[2 * j + 1] += bf16_hi(aw[j]);
+                    for (int j = 0; j < 16; ++j) acc_r[j] = 0u;
+                }
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc_r[j]);
+                if (P.bias != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float b0, b1, b2, b3;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
+                                     : "r"(bias_s + 4u * (c16 * 16 + j)));
+                        v[j] += b0; v[j + 1] += b1; v[j + 2] += b2; v[j + 3] += b3;
+                    }
+                }
+                if (has_add) {
+                    const uint32_t aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        v[2 * j] += bf16_lo(aw[j]);
+                        v[2 * j + 1] += bf16_hi(aw[j]);
+                    }
+                }
+                if (P.relu) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+                }
+                if (has_mask) {
+                    const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (!(bf16_lo(mw[j]) > 0.f)) v[2 * j] = 0.f;
+                        if (!(bf16_hi(mw[j]) > 0.f)) v[2 * j + 1] = 0.f;
+                    }
+                }
+                if (!valid) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                }
+                if (P.out_f32 != nullptr && valid) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int ch = ch0 + j;
+                        if (ch < P.out_f32_c) {
+                            float o = v[j];
+                            if (P.sigmoid) o = 1.f / (1.f + __expf(-o));
+                            P.out_f32[((static_cast<long>(img) * P.out_f32_c + ch) * P.Hout + ho) * P.Wout + wo] = o;
+                        }
+                    }
+                }
+                if (P.store_bf16) {
+                    const int cl = c16 * 16;                   // channel offset inside the N tile
+                    const uint32_t sub = cl / sub_c;
+                    const uint32_t off = sub * 128u * row_b + row * row_b + (cl - sub * sub_c) * 2;
+                    const uint32_t q0x = pack_bf16x2(v[0], v[1]), q0y = pack_bf16x2(v[2], v[3]);
+                    const uint32_t q0z = pack_bf16x2(v[4], v[5]), q0w = pack_bf16x2(v[6], v[7]);
+                    const uint32_t q1x = pack_bf16x2(v[8], v[9]), q1y = pack_bf16x2(v[10], v[11]);
+                    const uint32_t q1z = pack_bf16x2(v[12], v[13]), q1w = pack_bf16x2(v[14], v[15]);
+                    const uint32_t d0 = staging + swz(off, smask), d1 = staging + swz(off + 16, smask);
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d0), "r"(q0x), "r"(q0y), "r"(q0z), "r"(q0w) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d1), "r"(q1x), "r"(q1y), "r"(q1z), "r"(q1w) : "memory");
                 }
             }
-            if (P.relu) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-            if (P.mask != nullptr && valid && ch0 < P.Cout_total) {
-                const uint4* mp = reinterpret_cast<const uint4*>(P.mask + pix * P.Cout_total + ch0);
-                const uint4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
-                const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (!(bf16_lo(mw[j]) > 0.f)) v[2 * j] = 0.f;
-                    if (!(bf16_hi(mw[j]) > 0.f)) v[2 * j + 1] = 0.f;
+            // accumulator drained: hand it back to the MMA issuer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+
+            if (P.store_bf16) {
+                fence_proxy_async_smem();
+                named_bar_sync(1, kEpiThreads);
+                if (et == 0) {
+                    const int nsub = (P.BN + sub_c - 1) / sub_c;
+                    for (int s = 0; s < nsub; ++s) {
+                        const int ch = n0 + s * sub_c;
+                        if (ch >= P.Cout_total) break;
+                        const int o = ch < P.out_C0 ? 0 : 1;
+                        const int cc = (o ? ch - P.out_C0 : ch) + P.out_q[z] * P.out_qstride[o];
+                        tma_store_5d(&P.tmOut[o], staging + s * 128u * row_b, cc, w0, P.out_p[z], h0, img);
+                    }
+                    tma_store_commit();
                 }
-            }
-            if (!valid) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = 0.f;
-            }
-            if (P.out_f32 != nullptr && valid) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int ch = ch0 + j;
-                    if (ch < P.out_f32_c) {
-                        float o = v[j];
-                        if (P.sigmoid) o = 1.f / (1.f + __expf(-o));
-                        P.out_f32[((static_cast<long>(img) * P.out_f32_c + ch) * P.Hout + ho) * P.Wout + wo] = o;
+                if (P.stats != nullptr) {
+                    // per-channel sum / sum-of-squares of the staged (bf16-rounded, invalid rows zeroed) tile
+                    const int pairs = P.BN / 2;
+                    const int cp = et % pairs, rg = et / pairs, nrg = kEpiThreads / pairs;
+                    const int cl = cp * 2;
+                    const uint32_t sub = cl / sub_c;
+                    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                    for (int r = rg; r < 128; r += nrg) {
+                        const uint32_t off = sub * 128u * row_b + r * row_b + (cl - sub * sub_c) * 2;
+                        uint32_t w;
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(staging + swz(off, smask)));
+                        const float a = bf16_lo(w), b = bf16_hi(w);
+                        s0 += a; q0 += a * a; s1 += b; q1 += b * b;
+                    }
+                    // reduce inside the CTA first: lanes sharing a channel pair (BN <= 32), then shared-memory atomics,
+                    // so that one tile issues only 2*BN global atomics
+                    if (pairs < 32) {
+                        for (int o = 16; o >= pairs; o >>= 1) {
+                            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                            q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+                            q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+                        }
+                    }
+                    if (pairs >= 32 || lane < pairs) {
+                        asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(stat_s + 4u * cl), "f"(s0) : "memory");
+                        asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(stat_s + 4u * (cl + 1)), "f"(s1) : "memory");
+                        asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(stat_s + 4u * (P.BN + cl)), "f"(q0) : "memory");
+                        asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(stat_s + 4u * (P.BN + cl + 1)), "f"(q1) : "memory");
+                    }
+                    named_bar_sync(3, kEpiThreads);
+                    if (et < 2 * P.BN) {
+                        const int which = et / P.BN, cch = et - which * P.BN;
+                        const int ch = n0 + cch;
+                        if (ch < P.Cout_total) {
+                            float v;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(stat_s + 4u * et));
+                            atomicAdd(P.stats + (static_cast<long>(tile % P.stats_replicas) * 2 + which) * P.Cout_total + ch, v);
+                        }
                     }
                 }
             }
-            if (P.store_bf16) {
-                const int cl = c16 * 16;                   // channel offset inside the N tile
-                const uint32_t sub = cl / sub_c;
-                const uint32_t off = sub * 128u * row_b + row * row_b + (cl - sub * sub_c) * 2;
-                uint4 q0, q1;
-                q0.x = pack_bf16x2(v[0], v[1]);   q0.y = pack_bf16x2(v[2], v[3]);
-                q0.z = pack_bf16x2(v[4], v[5]);   q0.w = pack_bf16x2(v[6], v[7]);
-                q1.x = pack_bf16x2(v[8], v[9]);   q1.y = pack_bf16x2(v[10], v[11]);
-                q1.z = pack_bf16x2(v[12], v[13]); q1.w = pack_bf16x2(v[14], v[15]);
-                const uint32_t d0 = smem_base + swz(off, smask), d1 = smem_base + swz(off + 16, smask);
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d0), "r"(q0.x), "r"(q0.y), "r"(q0.z), "r"(q0.w) : "memory");
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d1), "r"(q1.x), "r"(q1.y), "r"(q1.z), "r"(q1.w) : "memory");
-            }
         }
-        tc_fence_before();
-        if (P.store_bf16) {
-            fence_proxy_async_smem();
-            named_bar_sync(1, 128);
-            if (et == 0) {
-                const int nsub = (P.BN + sub_c - 1) / sub_c;
-                for (int s = 0; s < nsub; ++s) {
-                    const int ch = n0 + s * sub_c;
-                    if (ch >= P.Cout_total) break;
-                    const int o = ch < P.out_C0 ? 0 : 1;
-                    const int cc = (o ? ch - P.out_C0 : ch) + P.out_q[z] * P.out_qstride[o];
-                    tma_store_5d(&P.tmOut[o], smem_base + s * 128u * row_b, cc, w0, P.out_p[z], h0, img);
-                }
-                tma_store_commit();
-            }
-            if (P.stats != nullptr) {
-                // per-channel sum / sum-of-squares of the staged (bf16-rounded, invalid rows zeroed) tile
-                const int pairs = P.BN / 2;
-                const int cp = et % pairs, rg = et / pairs, nrg = 128 / pairs;
-                const int cl = cp * 2;
-                const uint32_t sub = cl / sub_c;
-                float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-                for (int r = rg; r < 128; r += nrg) {
-                    const uint32_t off = sub * 128u * row_b + r * row_b + (cl - sub * sub_c) * 2;
-                    uint32_t w;
-                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(smem_base + swz(off, smask)));
-                    const float a = bf16_lo(w), b = bf16_hi(w);
-                    s0 += a; q0 += a * a; s1 += b; q1 += b * b;
-                }
-                const int ch = n0 + cl;
-                if (ch < P.Cout_total) {
-                    float* st = P.stats + static_cast<long>(blockIdx.x % P.stats_replicas) * 2 * P.Cout_total;
-                    atomicAdd(st + ch, s0);
-                    atomicAdd(st + ch + 1, s1);
-                    atomicAdd(st + P.Cout_total + ch, q0);
-                    atomicAdd(st + P.Cout_total + ch + 1, q1);
-                }
-            }
-            if (et == 0) tma_store_wait_all();
-        }
+        if (et == 0) tma_store_wait_all();
     }
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * P.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -304,25 +406,39 @@ static int act_map(CUtensorMap* m, const hd_act& t, bool phase_view, int box_c, 
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
+static int num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = 148;
+    }
+    return sms;
+}
+
 static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStream_t stream) {
     P.a_bytes = round_up(128 * P.BK * 2, 1024);
     P.stage_bytes = P.a_bytes + round_up(P.BN * P.BK * 2, 1024);
-    int stages = (100 * 1024) / P.stage_bytes;
+    const int staging = 2 * round_up(128 * P.BN * 2, 1024);         // double-buffered output staging
+    const int fixed = 1024 + staging + 512 + 1024 + 16 * 8 + 64;   // alignment slack, staging, bias, stats, barriers
+    int stages = (226 * 1024 - fixed) / P.stage_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     P.stages = stages;
     int cols = 32;
     while (cols < P.BN) cols *= 2;
     P.tmem_cols = cols;
-    const int staging = 128 * P.BN * 2;
-    const int body = stages * P.stage_bytes > staging ? stages * P.stage_bytes : staging;
-    const size_t smem = 1024 + body + 16 * stages + 16;
+    P.m_tiles = P.tiles_w * P.tiles_h * n_img;
+    P.n_tiles = (P.Cout_total + P.BN - 1) / P.BN;
+    P.nphases = nphases;
+    const size_t smem = static_cast<size_t>(fixed) + static_cast<size_t>(stages) * P.stage_bytes;
     static bool attr_set = false;
     if (!attr_set) {
-        HD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        HD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
-    dim3 grid(P.tiles_w * P.tiles_h * n_img, (P.Cout_total + P.BN - 1) / P.BN, nphases);
+    const long total = static_cast<long>(P.m_tiles) * P.n_tiles * nphases;
+    const int grid = static_cast<int>(total < num_sms() ? total : num_sms());
     conv_gemm_kernel<<<grid, kThreads, smem, stream>>>(P);
     HD_CUDA_OK(cudaPeekAtLastError());
     return HD_OK;
