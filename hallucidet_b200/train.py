@@ -42,6 +42,28 @@ class _PixelRegulariser(torch.autograd.Function):
         return dhal * g[0], None, None, None, None, None
 
 
+def allreduce_mean_(tensors, world=None, group=None):
+    """In-place mean over ranks of a list of gradient tensors (one all-reduce per tensor; pass the flat block as a
+    single tensor).  Backend-agnostic: NCCL over NVLink on the GPUs, gloo in the CPU tests."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return tensors
+    world = world or dist.get_world_size(group)
+    if world == 1:
+        return tensors
+    for t in tensors:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        t.mul_(1.0 / world)
+    return tensors
+
+
+def shard_batch(global_batch, rank, world):
+    """Batch sharding of SURVEY.md 8(e): contiguous, equal slices of the global batch; identical replicas."""
+    if global_batch % world != 0:
+        raise ValueError(f"global batch {global_batch} is not divisible by the world size {world}")
+    per = global_batch // world
+    return slice(rank * per, (rank + 1) * per)
+
+
 def expand_one_channel_to_output_channels(imgs, output_channels=3):
     """src/utils/utils.py:52-53."""
     return imgs.repeat(1, output_channels, 1, 1)
@@ -110,13 +132,7 @@ class HalluciDetTrainer(nn.Module):
         params = [p for p in self.encoder_decoder.parameters() if p.grad is not None]
         eng = next(iter(self.encoder_decoder._engines.values()), None)
         flat = eng.flat_grad if eng is not None and params and params[0].grad.data_ptr() == eng.flat_grad.data_ptr() else None
-        if flat is not None:
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-            flat.mul_(1.0 / self.world)
-        else:
-            for p in params:
-                dist.all_reduce(p.grad, op=dist.ReduceOp.SUM)
-                p.grad.mul_(1.0 / self.world)
+        allreduce_mean_([flat] if flat is not None else [p.grad for p in params], self.world)
 
     def training_step(self, imgs_rgb, targets_rgb, imgs_ir, targets_ir, det_seed=None):
         self.encoder_decoder.train()
