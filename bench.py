@@ -156,6 +156,7 @@ def main():
     from oracle import step as ostep            # synthetic input generator only (no oracle compute on this arm)
 
     torch.backends.cudnn.benchmark = True       # train_hallucidet.py:28-29
+    torch.backends.cuda.matmul.allow_tf32 = True  # torchvision box head (fp32 Linear 12544->1024) on the TF32 tensor path
     B, H, W, S = args.batch, 512, 640, 640
     weights = {"pixel_rgb": 1.0, "pixel_ir": 1.0} if args.pixel else None
     tr = HalluciDetTrainer(detector_name=args.detector, size=S, pixel=args.pixel, weights=weights, seed=123, device=dev,
@@ -245,6 +246,7 @@ def main():
                                    f"batch {B}/GPU, 512x640 IR, S={S}, Adam + clip 0.5",
                        "detector": args.detector, "batch_per_gpu": B, "input": "512x640", "detector_size": S,
                        "parallelism": f"dp{world}", "cuda_graph": bool(was_graph), "pixel_regulariser": args.pixel,
+                       "detection_tail": "torchvision RPN/RoI heads + losses (fp32, TF32 matmul), per-image NMS on concurrent streams",
                        "l2": "working set (activations + weights, several GB per step) far exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,

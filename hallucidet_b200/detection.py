@@ -89,6 +89,83 @@ def _check_targets(targets):
                       f"Expected target boxes to be a tensor of shape [N, 4], got {boxes.shape}.")
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_streams(device, n):
+    key = (device.type, device.index)
+    pool = _SIDE_STREAMS.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
+
+
+def filter_proposals_concurrent(rpn, proposals, objectness, image_shapes, num_anchors_per_level):
+    """torchvision ``RegionProposalNetwork.filter_proposals`` (TV models/detection/rpn.py:242-295), same operators in the
+    same order per image -- but the per-image bodies (clip, small-box / score filters, batched NMS, top-n) are enqueued
+    on one CUDA stream per image, so the single-block NMS kernels of the images overlap instead of running back to
+    back.  No randomness is involved; results are identical to the sequential loop."""
+    from torchvision.ops import boxes as box_ops
+    num_images = proposals.shape[0]
+    device = proposals.device
+    objectness = objectness.detach().reshape(num_images, -1)
+    levels = torch.cat([torch.full((n,), idx, dtype=torch.int64, device=device) for idx, n in enumerate(num_anchors_per_level)], 0)
+    levels = levels.reshape(1, -1).expand_as(objectness)
+    top_n_idx = rpn._get_top_n_idx(objectness, num_anchors_per_level)
+    batch_idx = torch.arange(num_images, device=device)[:, None]
+    objectness = objectness[batch_idx, top_n_idx]
+    levels = levels[batch_idx, top_n_idx]
+    proposals = proposals[batch_idx, top_n_idx]
+    objectness_prob = torch.sigmoid(objectness)
+    if device.type != "cuda" or num_images == 1:
+        streams = [None] * num_images
+    else:
+        streams = _side_streams(device, num_images)
+    main = torch.cuda.current_stream(device) if device.type == "cuda" else None
+    def body(boxes, scores, lvl, img_shape, st):
+        # torchvision's nms op ends with a device->host read of the keep count, so overlapping the images needs one
+        # host thread per image as well (ATen releases the GIL while it waits)
+        ctx = torch.cuda.stream(st) if st is not None else torch.autograd.profiler.record_function("filter_proposals")
+        with torch.no_grad(), ctx:
+            boxes = box_ops.clip_boxes_to_image(boxes, img_shape)
+            keep = box_ops.remove_small_boxes(boxes, rpn.min_size)
+            boxes, scores, lvl = boxes[keep], scores[keep], lvl[keep]
+            keep = torch.where(scores >= rpn.score_thresh)[0]
+            boxes, scores, lvl = boxes[keep], scores[keep], lvl[keep]
+            keep = box_ops.batched_nms(boxes, scores, lvl, rpn.nms_thresh)
+            keep = keep[: rpn.post_nms_top_n()]
+            boxes, scores = boxes[keep], scores[keep]
+        if st is not None:
+            boxes.record_stream(main)
+            scores.record_stream(main)
+        return boxes, scores
+
+    work = list(zip(proposals, objectness_prob, levels, image_shapes, streams))
+    if streams[0] is None:
+        results = [body(*w) for w in work]
+    else:
+        for st in streams:
+            st.wait_stream(main)
+        results = list(_thread_pool(num_images).map(lambda w: body(*w), work))
+        for st in streams:
+            main.wait_stream(st)
+    return [r[0] for r in results], [r[1] for r in results]
+
+
+_POOL = None
+
+
+def _thread_pool(n):
+    global _POOL
+    if _POOL is None or _POOL._max_workers < n:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=max(n, 8))
+    return _POOL
+
+
+CONCURRENT_NMS = True
+
+
 def rpn_eval(model, images, features, targets):
     features = list(features.values())
     objectness, pred_bbox_deltas = model.rpn.head(features)
@@ -98,7 +175,10 @@ def rpn_eval(model, images, features, targets):
     objectness, pred_bbox_deltas = concat_box_prediction_layers(objectness, pred_bbox_deltas)
     proposals = model.rpn.box_coder.decode(pred_bbox_deltas.detach(), anchors)
     proposals = proposals.view(num_images, -1, 4)
-    boxes, scores = model.rpn.filter_proposals(proposals, objectness, images.image_sizes, num_anchors_per_level)
+    if CONCURRENT_NMS and proposals.is_cuda:
+        boxes, scores = filter_proposals_concurrent(model.rpn, proposals, objectness, images.image_sizes, num_anchors_per_level)
+    else:
+        boxes, scores = model.rpn.filter_proposals(proposals, objectness, images.image_sizes, num_anchors_per_level)
     if targets is None:
         raise ValueError("targets should not be None")
     labels, matched_gt_boxes = model.rpn.assign_targets_to_anchors(anchors, targets)

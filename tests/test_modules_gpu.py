@@ -341,3 +341,27 @@ def test_frozen_backbone_layers():
         if bi != 0:
             gx = gx * (xin > 0)
         close(nchw(gb[("gx", bi)]), gx, f"block {bi} input gradient", tol=2e-2)
+
+
+def test_concurrent_proposal_filter_equals_torchvision():
+    """The multi-stream per-image proposal filtering (hallucidet_b200.detection) returns exactly what torchvision's
+    sequential RegionProposalNetwork.filter_proposals returns."""
+    from torchvision.models.detection.image_list import ImageList
+    from torchvision.models.detection.rpn import concat_box_prediction_layers
+    from oracle import detector as odet
+    from hallucidet_b200 import detection as D
+    det = odet.build_detector("fasterrcnn", seed=1).cuda()
+    x = torch.rand(4, 3, 256, 256, generator=torch.Generator().manual_seed(0)).cuda()
+    with torch.no_grad():
+        feats = list(det.backbone(x).values())
+        il = ImageList(x, [(256, 256)] * 4)
+        obj, deltas = det.rpn.head(feats)
+        anchors = det.rpn.anchor_generator(il, feats)
+        napl = [o[0].shape[0] * o[0].shape[1] * o[0].shape[2] for o in obj]
+        o2, d2 = concat_box_prediction_layers(obj, deltas)
+        props = det.rpn.box_coder.decode(d2, anchors).view(4, -1, 4)
+        for _ in range(3):
+            a = det.rpn.filter_proposals(props, o2, il.image_sizes, napl)
+            b = D.filter_proposals_concurrent(det.rpn, props, o2, il.image_sizes, napl)
+            torch.cuda.synchronize()
+            assert all(torch.equal(p, q) for p, q in zip(a[0], b[0])) and all(torch.equal(p, q) for p, q in zip(a[1], b[1]))
