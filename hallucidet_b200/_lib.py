@@ -7,7 +7,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhallucidet_b200.so")
+LIB_PATH = os.environ.get("HD_LIB", os.path.join(HERE, "libhallucidet_b200.so"))   # HD_LIB: A/B builds while tuning
 
 c_int, c_float, c_double, c_void_p, c_int64 = ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_void_p, ctypes.c_int64
 
@@ -46,9 +46,9 @@ PROTOTYPES = {
     "hd_bn_finalize": [c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "hd_bn_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p],
-    "hd_bn_bwd_reduce": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p],
-    "hd_bn_bwd_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p,
-                        c_void_p, c_void_p, c_int64, c_int, c_void_p],
+    "hd_bn_bwd_reduce": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p],
+    "hd_bn_bwd_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
+                        c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p],
     "hd_maxpool_fwd": [P(HdAct), P(HdAct), c_void_p],
     "hd_maxpool_bwd": [P(HdAct), P(HdAct), c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "hd_upsample2x_fwd": [P(HdAct), P(HdAct), c_void_p],

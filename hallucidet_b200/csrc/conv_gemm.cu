@@ -23,7 +23,24 @@ namespace hd {
 constexpr int kMaxTaps = 9;
 constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quadrant, each takes half of the N columns
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kThreads = 64 + kEpiThreads;
+constexpr int kCpWarps = 4;                  // cp.async A-operand producers (narrow-channel layers only)
+constexpr int kCpThreads = kCpWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads + kCpThreads;
+
+// division by a runtime constant as multiply-high + shift (x < 2^31): q = (umulhi(x, mul) + x) >> shr
+struct FastDiv {
+    uint32_t mul, shr, d;
+};
+static FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.d = d;
+    uint32_t s = 0;
+    while ((1u << s) < d) ++s;
+    f.shr = s;
+    f.mul = static_cast<uint32_t>(((1ull << 32) * ((1ull << s) - d)) / d + 1);
+    return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t x, const FastDiv& f) { return (__umulhi(x, f.mul) + x) >> f.shr; }
 
 struct ConvGemmParams {
     CUtensorMap tmA[2];
@@ -52,19 +69,30 @@ struct ConvGemmParams {
     int stages, a_bytes, stage_bytes;
     int tmem_cols;
     int m_tiles, n_tiles, nphases;
+    // narrow-channel mode (BK < 64): TMA moves 32/64-byte rows one at a time (measured ~5-13 cycles per row), so the A
+    // tile is gathered by four cp.async warps instead (16-byte copies, coalesced along W, L1-cached across the 9 taps)
+    FastDiv fd_per_phase, fd_m_tiles, fd_tiles_w, fd_tiles_h, fd_TW;
+    int tps;                    // k-steps (tap x k-block) grouped into one pipeline stage (narrow-channel layers: fewer, fatter stages)
+    int a_sub, b_sub;           // bytes of one A / B sub-tile inside a stage
+    int direct_store;
+    __nv_bfloat16* out_ptr;
+    int cp_mode;
+    const __nv_bfloat16* a_ptr;
+    int a_H, a_W, a_C;
 };
 
 __device__ __forceinline__ void decode_tile(const ConvGemmParams& P, int tile, int& z, int& n0, int& img, int& h0, int& w0) {
     // m tiles fastest: CTAs running concurrently share the weight tile (L2) and walk neighbouring pixels
     const int per_phase = P.m_tiles * P.n_tiles;
-    z = tile / per_phase;
+    z = static_cast<int>(fdiv(tile, P.fd_per_phase));
     const int rem = tile - z * per_phase;
-    const int nt = rem / P.m_tiles;
+    const int nt = static_cast<int>(fdiv(rem, P.fd_m_tiles));
     const int mt = rem - nt * P.m_tiles;
     n0 = nt * P.BN;
-    const int tw_i = mt % P.tiles_w;
-    const int th_i = (mt / P.tiles_w) % P.tiles_h;
-    img = mt / (P.tiles_w * P.tiles_h);
+    const int t1 = static_cast<int>(fdiv(mt, P.fd_tiles_w));          // mt / tiles_w
+    const int tw_i = mt - t1 * P.tiles_w;
+    img = static_cast<int>(fdiv(t1, P.fd_tiles_h));                   // (mt / tiles_w) / tiles_h
+    const int th_i = t1 - img * P.tiles_h;
     w0 = tw_i * P.TW;
     h0 = th_i * P.TH;
 }
@@ -91,7 +119,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
-            mbar_init(full0 + 8u * s, 1);
+            mbar_init(full0 + 8u * s, P.cp_mode ? 1 + kCpThreads : 1);
             mbar_init(empty0 + 8u * s, 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -118,7 +146,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     if (warp == 0) {
         // ================= TMA producer =================
         if (elect_one()) {
-            const uint32_t tx_bytes = static_cast<uint32_t>((P.TW * P.TH + P.BN) * P.BK * 2);
+            const uint32_t tx_bytes = static_cast<uint32_t>(((P.cp_mode ? 0 : P.TW * P.TH) + P.BN) * P.BK * 2) * P.tps;
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -126,17 +154,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 decode_tile(P, tile, z, n0, img, h0, w0);
                 int tap = P.tap_begin[z], kb = 0;
                 const int num_k = (P.tap_begin[z + 1] - tap) * P.kpt;
-                for (int ks = 0; ks < num_k; ++ks) {
+                for (int ks = 0; ks < num_k; ks += P.tps) {
                     mbar_wait(empty0 + 8u * stage, phase ^ 1u);
                     const uint32_t sa = smem_base + stage * P.stage_bytes;
                     const uint32_t sb = sa + P.a_bytes;
                     const uint32_t fb = full0 + 8u * stage;
                     mbar_expect_tx(fb, tx_bytes);
-                    const int src = kb < P.kb_split ? 0 : 1;
-                    const int c = (src ? kb - P.kb_split : kb) * P.BK + P.tap_q[tap] * P.a_qstride[src];
-                    tma_load_5d(sa, &P.tmA[src], fb, c, w0 + P.tap_dw[tap], P.tap_p[tap], h0 + P.tap_dh[tap], img);
-                    tma_load_2d(sb, &P.tmB, fb, P.tap_bk[tap] + kb * P.BK, n0);
-                    if (++kb == P.kpt) { kb = 0; ++tap; }
+                    for (int j = 0; j < P.tps; ++j) {
+                        const int src = kb < P.kb_split ? 0 : 1;
+                        const int c = (src ? kb - P.kb_split : kb) * P.BK + P.tap_q[tap] * P.a_qstride[src];
+                        if (!P.cp_mode)
+                            tma_load_5d(sa + j * P.a_sub, &P.tmA[src], fb, c, w0 + P.tap_dw[tap], P.tap_p[tap], h0 + P.tap_dh[tap], img);
+                        tma_load_2d(sb + j * P.b_sub, &P.tmB, fb, P.tap_bk[tap] + kb * P.BK, n0);
+                        if (++kb == P.kpt) { kb = 0; ++tap; }
+                    }
                     if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -146,28 +177,43 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         if (elect_one()) {
             const uint32_t idesc = make_idesc_bf16(128, P.BN, 0, 0);
             const uint32_t swz_bytes = P.BK * 2;
-            const uint32_t lt = swizzle_layout_type(swz_bytes);
-            const uint32_t sbo = 8u * swz_bytes;
+            // descriptor halves: hi (SBO, version, swizzle) and the LBO bits of lo are loop invariant; per MMA only the
+            // 14-bit start-address field (16-byte units) moves -- keeps the single issuing thread off the critical path
+            const uint64_t d0 = make_smem_desc(0, 16, 8u * swz_bytes, swizzle_layout_type(swz_bytes));
+            const uint32_t d_hi = static_cast<uint32_t>(d0 >> 32), d_lo = static_cast<uint32_t>(d0);
             const int ksub = P.BK / 16;
+            const int tps = P.tps;
+            const uint32_t stage_u = P.stage_bytes >> 4, a_sub_u = P.a_sub >> 4, b_sub_u = P.b_sub >> 4, a_bytes_u = P.a_bytes >> 4;
+            const uint32_t base_u = d_lo + (smem_base >> 4);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int z = tile / (P.m_tiles * P.n_tiles);
-                const int num_k = (P.tap_begin[z + 1] - P.tap_begin[z]) * P.kpt;
+                const int z = static_cast<int>(fdiv(tile, P.fd_per_phase));
+                const int num_st = (P.tap_begin[z + 1] - P.tap_begin[z]) * P.kpt / tps;
                 mbar_wait(tempty0 + 8u * acc, acc_phase ^ 1u);          // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * P.tmem_cols;
-                for (int ks = 0; ks < num_k; ++ks) {
+                uint32_t accum = 0;
+                for (int st = 0; st < num_st; ++st) {
                     mbar_wait(full0 + 8u * stage, phase);
+                    if (P.cp_mode) fence_proxy_async_smem();   // cp.async wrote the A tile through the generic proxy
                     tc_fence_after();
-                    const uint32_t sa = smem_base + stage * P.stage_bytes;
-                    const uint32_t sb = sa + P.a_bytes;
-                    for (int k = 0; k < ksub; ++k) {
-                        const uint64_t da = make_smem_desc(sa + k * 32, 16, sbo, lt);
-                        const uint64_t db = make_smem_desc(sb + k * 32, 16, sbo, lt);
-                        umma_bf16(d_tmem, da, db, idesc, (ks | k) != 0);
+                    const uint32_t a_u = base_u + stage * stage_u, b_u = a_u + a_bytes_u;
+                    if (tps == 1 && ksub == 4) {               // the common 64-channel k-block: fully unrolled
+                        umma_bf16_lohi(d_tmem, a_u, d_hi, b_u, d_hi, idesc, accum);
+                        umma_bf16_lohi(d_tmem, a_u + 2, d_hi, b_u + 2, d_hi, idesc, 1);
+                        umma_bf16_lohi(d_tmem, a_u + 4, d_hi, b_u + 4, d_hi, idesc, 1);
+                        umma_bf16_lohi(d_tmem, a_u + 6, d_hi, b_u + 6, d_hi, idesc, 1);
+                        accum = 1;
+                    } else {
+                        for (int j = 0; j < tps; ++j) {
+                            for (int k = 0; k < ksub; ++k) {
+                                umma_bf16_lohi(d_tmem, a_u + j * a_sub_u + 2 * k, d_hi, b_u + j * b_sub_u + 2 * k, d_hi, idesc, accum);
+                                accum = 1;
+                            }
+                        }
                     }
                     umma_commit(empty0 + 8u * stage);
                     if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -175,6 +221,62 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 umma_commit(tfull0 + 8u * acc);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
+        }
+    } else if (warp >= 2 + kEpiWarps) {
+        // ================= cp.async A-tile producers (narrow-channel mode) =================
+        if (P.cp_mode) {
+            const int pt = threadIdx.x - (64 + kEpiThreads);      // 0..127
+            const int row_b = P.BK * 2;                            // 32 or 64 bytes per pixel row of the tile
+            const int cpr = row_b / 16;                            // 16-byte chunks per row
+            const uint32_t smask = cpr - 1;
+            const int per_thread = 128 * cpr / kCpThreads;         // 2 or 4
+            // everything that depends only on (thread, slot) is hoisted out of the tile / tap loops
+            int s_hl[4], s_wl[4];
+            uint32_t s_dst[4];
+            long s_off[4];
+            bool s_in[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int q = pt + kCpThreads * i;
+                const int r = q / cpr, ch = q - r * cpr;
+                s_hl[i] = r / P.TW;
+                s_wl[i] = r - s_hl[i] * P.TW;
+                s_in[i] = i < per_thread && r < P.TW * P.TH;
+                s_dst[i] = swz(static_cast<uint32_t>(r * row_b + ch * 16), smask);
+                s_off[i] = (static_cast<long>(s_hl[i]) * P.a_W + s_wl[i]) * P.a_C + ch * 8;
+            }
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int z, n0, img, h0, w0;
+                decode_tile(P, tile, z, n0, img, h0, w0);
+                int tap = P.tap_begin[z], kb = 0;
+                const int num_k = (P.tap_begin[z + 1] - tap) * P.kpt;
+                const __nv_bfloat16* tile_base = P.a_ptr + ((static_cast<long>(img) * P.a_H + h0) * P.a_W + w0) * P.a_C;
+                for (int ks = 0; ks < num_k; ks += P.tps) {
+                    mbar_wait(empty0 + 8u * stage, phase ^ 1u);
+                    const uint32_t sa = smem_base + stage * P.stage_bytes;
+                    for (int j = 0; j < P.tps; ++j) {
+                        const int dh = P.tap_dh[tap], dw = P.tap_dw[tap];
+                        const long tap_off = (static_cast<long>(dh) * P.a_W + dw) * P.a_C + kb * P.BK;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (i < per_thread) {
+                                const int hi = h0 + s_hl[i] + dh, wi = w0 + s_wl[i] + dw;
+                                const bool ok = s_in[i] && static_cast<unsigned>(hi) < static_cast<unsigned>(P.a_H) &&
+                                                static_cast<unsigned>(wi) < static_cast<unsigned>(P.a_W);
+                                const __nv_bfloat16* src = ok ? tile_base + s_off[i] + tap_off : P.a_ptr;
+                                // src-size 0 -> 16 bytes of zeros (padding / out-of-tile rows)
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sa + j * P.a_sub + s_dst[i]), "l"(src), "r"(ok ? 16 : 0) : "memory");
+                            }
+                        }
+                        if (++kb == P.kpt) { kb = 0; ++tap; }
+                    }
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full0 + 8u * stage) : "memory");
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
         }
     } else {
         // ================= epilogue: 8 warps, warp w drains TMEM lane quadrant (w & 3), half of the columns =========
@@ -189,6 +291,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         const int nchunk = P.BN / 16;
         const int c_begin = nchunk >= 2 ? (ew >> 2) * (nchunk / 2) : ((ew >> 2) ? 1 : 0);
         const int c_end = nchunk >= 2 ? c_begin + nchunk / 2 : 1;
+        // direct-store slots (narrow outputs): the 16-byte piece(s) of the staged tile this thread copies out
+        const int ds_cpr = static_cast<int>(row_b) / 16;
+        int ds_rh[2], ds_rw[2], ds_goff[2];
+        uint32_t ds_soff[2];
+        bool ds_on[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int q = et + kEpiThreads * i;
+            const int r = q / ds_cpr, ch = q - r * ds_cpr;
+            ds_rh[i] = r / P.TW;
+            ds_rw[i] = r - ds_rh[i] * P.TW;
+            ds_on[i] = P.direct_store && q < 128 * ds_cpr && r < P.TW * P.TH;
+            ds_soff[i] = swz(static_cast<uint32_t>(r * row_b + ch * 16), smask);
+            ds_goff[i] = ch * 8;
+        }
         int acc = 0;
         uint32_t acc_phase = 0;
         int iter = 0;
@@ -199,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const int hg = h0 + hl, wg = w0 + wl;
             const bool valid = (row < P.TW * P.TH) && hg < P.Hg && wg < P.Wg;
             const int ho = hg * P.ostride + P.out_p[z], wo = wg * P.ostride + P.out_q[z];
-            const long pix = (static_cast<long>(img) * P.Hout + ho) * P.Wout + wo;
+            const long pix = static_cast<long>((img * P.Hout + ho) * P.Wout + wo);
             const uint32_t staging = staging0 + (iter & 1) * stg_bytes;
             const __nv_bfloat16* add_row = P.add != nullptr ? P.add + pix * P.Cout_total + n0 : nullptr;
             const __nv_bfloat16* mask_row = P.mask != nullptr ? P.mask + pix * P.Cout_total + n0 : nullptr;
@@ -312,7 +429,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             if (P.store_bf16) {
                 fence_proxy_async_smem();
                 named_bar_sync(1, kEpiThreads);
-                if (et == 0) {
+                if (P.direct_store) {
+                    // narrow outputs (rows < 128 bytes): TMA would store them one 32/64-byte row at a time, so the staged
+                    // tile is copied out with coalesced 16-byte stores instead (single N tile, pixel rows contiguous)
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int gh = h0 + ds_rh[i], gw = w0 + ds_rw[i];
+                        if (ds_on[i] && gh < P.Hg && gw < P.Wg) {
+                            uint4 v;
+                            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                                         : "r"(staging + ds_soff[i]));
+                            const int opix = (img * P.Hout + gh * P.ostride + P.out_p[z]) * P.Wout + gw * P.ostride + P.out_q[z];
+                            *reinterpret_cast<uint4*>(P.out_ptr + static_cast<long>(opix) * P.Cout_total + n0 + ds_goff[i]) = v;
+                        }
+                    }
+                } else if (et == 0) {
                     const int nsub = (P.BN + sub_c - 1) / sub_c;
                     for (int s = 0; s < nsub; ++s) {
                         const int ch = n0 + s * sub_c;
@@ -417,11 +548,26 @@ static int num_sms() {
 }
 
 static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStream_t stream) {
-    P.a_bytes = round_up(128 * P.BK * 2, 1024);
-    P.stage_bytes = P.a_bytes + round_up(P.BN * P.BK * 2, 1024);
+    P.a_sub = round_up(128 * P.BK * 2, 1024);
+    P.b_sub = round_up(P.BN * P.BK * 2, 1024);
+    // narrow-channel layers: group several (tap, k-block) steps per stage so that one mbarrier round trip moves
+    // >= ~32 KB; tps must divide the k-step count of every phase
+    P.tps = 1;
+    if (P.BK < 64) {
+        for (int t = 9; t >= 2; --t) {
+            bool ok = (P.a_sub + P.b_sub) * t <= 48 * 1024;
+            for (int z = 0; z < nphases && ok; ++z) {
+                const int nk = (P.tap_begin[z + 1] - P.tap_begin[z]) * P.kpt;
+                ok = nk > 0 && nk % t == 0;
+            }
+            if (ok) { P.tps = t; break; }
+        }
+    }
+    P.a_bytes = P.a_sub * P.tps;
+    P.stage_bytes = (P.a_sub + P.b_sub) * P.tps;
     const int staging = 2 * round_up(128 * P.BN * 2, 1024);         // double-buffered output staging
     const int fixed = 1024 + staging + 512 + 1024 + 16 * 8 + 64;   // alignment slack, staging, bias, stats, barriers
-    int stages = (226 * 1024 - fixed) / P.stage_bytes;
+    int stages = (232448 - fixed) / P.stage_bytes;              // 227 KB = the sm_100 per-block maximum
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     P.stages = stages;
@@ -430,11 +576,17 @@ static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStrea
     P.tmem_cols = cols;
     P.m_tiles = P.tiles_w * P.tiles_h * n_img;
     P.n_tiles = (P.Cout_total + P.BN - 1) / P.BN;
+    P.fd_per_phase = make_fastdiv(static_cast<uint32_t>(P.m_tiles * P.n_tiles));
+    P.fd_m_tiles = make_fastdiv(static_cast<uint32_t>(P.m_tiles));
+    P.fd_tiles_w = make_fastdiv(static_cast<uint32_t>(P.tiles_w));
+    P.fd_tiles_h = make_fastdiv(static_cast<uint32_t>(P.tiles_h));
+    P.fd_TW = make_fastdiv(static_cast<uint32_t>(P.TW));
+    P.direct_store = (P.BN < 64 && P.Cout_total == P.BN && P.out_C0 == P.Cout_total && P.out_ptr != nullptr) ? 1 : 0;
     P.nphases = nphases;
     const size_t smem = static_cast<size_t>(fixed) + static_cast<size_t>(stages) * P.stage_bytes;
     static bool attr_set = false;
     if (!attr_set) {
-        HD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        HD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
         attr_set = true;
     }
     const long total = static_cast<long>(P.m_tiles) * P.n_tiles * nphases;
@@ -519,6 +671,9 @@ extern "C" int hd_conv_fwd(const hd_conv_args* a, hd_stream stream_) {
     P.tap_begin[0] = 0; P.tap_begin[1] = t;
     P.a_qstride[0] = a->x0.c; P.a_qstride[1] = two ? a->x1.c : 0;
     P.out_C0 = cout; P.Cout_total = cout;
+    P.cp_mode = (P.BK < 64 && s == 1 && !two) ? 1 : 0;
+    P.a_ptr = static_cast<const __nv_bfloat16*>(a->x0.ptr);
+    P.a_H = a->x0.h; P.a_W = a->x0.w; P.a_C = a->x0.c;
     if (int e = fill_epilogue(P, a)) return e;
 
     const int swz = P.BK * 2;
@@ -534,6 +689,7 @@ extern "C" int hd_conv_fwd(const hd_conv_args* a, hd_stream stream_) {
     const int sub_c = P.BN < 64 ? P.BN : 64;
     if (act_map(&P.tmOut[0], a->y0, false, sub_c, P.TW, P.TH, sub_c * 2)) return HD_ERR_CUDA;
     P.tmOut[1] = P.tmOut[0];
+    P.out_ptr = static_cast<__nv_bfloat16*>(a->y0.ptr);
     return launch_conv_gemm(P, N, 1, stream);
 }
 
@@ -603,6 +759,9 @@ extern "C" int hd_conv_dgrad(const hd_conv_args* a, hd_stream stream_) {
     }
     P.a_qstride[0] = 0; P.a_qstride[1] = 0;
     P.out_C0 = a->y0.c; P.Cout_total = cin;
+    P.cp_mode = (P.BK < 64 && s == 1) ? 1 : 0;
+    P.a_ptr = static_cast<const __nv_bfloat16*>(a->x0.ptr);
+    P.a_H = a->x0.h; P.a_W = a->x0.w; P.a_C = a->x0.c;
     P.out_qstride[0] = a->y0.c; P.out_qstride[1] = two ? a->y1.c : 0;
     if (int e = fill_epilogue(P, a)) return e;
 
@@ -619,5 +778,6 @@ extern "C" int hd_conv_dgrad(const hd_conv_args* a, hd_stream stream_) {
     if (act_map(&P.tmOut[0], a->y0, s == 2, sub_c, P.TW, P.TH, sub_c * 2)) return HD_ERR_CUDA;
     if (two) { if (act_map(&P.tmOut[1], a->y1, false, sub_c, P.TW, P.TH, sub_c * 2)) return HD_ERR_CUDA; }
     else P.tmOut[1] = P.tmOut[0];
+    P.out_ptr = two ? nullptr : static_cast<__nv_bfloat16*>(a->y0.ptr);
     return launch_conv_gemm(P, N, nph, stream);
 }

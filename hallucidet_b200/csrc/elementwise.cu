@@ -200,6 +200,7 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z, const float
 
 // sums[0][c] = sum g, sums[1][c] = sum g*xhat with g = dy*(y>0)
 __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ yrelu,
+                                     const float* __restrict__ rscale, const float* __restrict__ rshift,
                                      const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
                                      const float* __restrict__ invstd, float* __restrict__ sums, long n_pix, int C,
                                      long pix_per_block) {
@@ -209,9 +210,12 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const
     const int g = threadIdx.x % G, l = threadIdx.x / G;
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
     __syncthreads();
-    float a[8], b[8], mu[8], is[8];
+    float a[8], b[8], mu[8], is[8], rs[8], rb[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { a[j] = 0.f; b[j] = 0.f; mu[j] = mean[g * 8 + j]; is[j] = invstd[g * 8 + j]; }
+    for (int j = 0; j < 8; ++j) {
+        a[j] = 0.f; b[j] = 0.f; mu[j] = mean[g * 8 + j]; is[j] = invstd[g * 8 + j];
+        rs[j] = rscale ? rscale[g * 8 + j] : 0.f; rb[j] = rscale ? rshift[g * 8 + j] : 0.f;
+    }
     const long p0 = blockIdx.x * pix_per_block;
     long p1 = p0 + pix_per_block;
     if (p1 > n_pix) p1 = n_pix;
@@ -231,6 +235,9 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const
                 yy.unpack(yf);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) if (!(yf[j] > 0.f)) df[j] = 0.f;
+            } else if (rscale) {                      // ReLU directly after this BN: the mask is recomputed from z
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (!(fmaf(zf[j], rs[j], rb[j]) > 0.f)) df[j] = 0.f;
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) { a[j] += df[j]; b[j] += df[j] * (zf[j] - mu[j]) * is[j]; }
@@ -257,6 +264,7 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const
 }
 
 __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ yrelu,
+                                    const float* __restrict__ rscale, const float* __restrict__ rshift,
                                     const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
                                     const float* __restrict__ invstd, const float* __restrict__ gamma,
                                     const float* __restrict__ sums, float inv_count, __nv_bfloat16* __restrict__ dz,
@@ -285,6 +293,9 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const 
             yy.unpack(yf);
 #pragma unroll
             for (int j = 0; j < 8; ++j) if (!(yf[j] > 0.f)) df[j] = 0.f;
+        } else if (rscale) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (!(fmaf(zf[j], __ldg(rscale + c0 + j), __ldg(rshift + c0 + j)) > 0.f)) df[j] = 0.f;
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -772,8 +783,8 @@ extern "C" int hd_bn_apply(const void* z, const float* scale, const float* shift
     return HD_OK;
 }
 
-extern "C" int hd_bn_bwd_reduce(const void* dy, const void* yrelu, const void* z, const float* mean, const float* invstd,
-                                float* sums, int64_t n_pix, int C, hd_stream st) {
+extern "C" int hd_bn_bwd_reduce(const void* dy, const void* yrelu, const float* rscale, const float* rshift, const void* z,
+                                const float* mean, const float* invstd, float* sums, int64_t n_pix, int C, hd_stream st) {
     HD_CHECK_ARG(dy && z && mean && invstd && sums && C % 8 == 0 && C / 8 <= 256 && n_pix > 0);
     const int G = C / 8;
     int L = 256 / G;
@@ -784,18 +795,18 @@ extern "C" int hd_bn_bwd_reduce(const void* dy, const void* yrelu, const void* z
     if (ppb < L) ppb = L;
     blocks = (n_pix + ppb - 1) / ppb;
     bn_bwd_reduce_kernel<<<static_cast<int>(blocks), threads, 2 * C * sizeof(float), static_cast<cudaStream_t>(st)>>>(
-        static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(yrelu),
+        static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(yrelu), rscale, rshift,
         static_cast<const __nv_bfloat16*>(z), mean, invstd, sums, n_pix, C, ppb);
     HD_LAUNCH_OK();
     return HD_OK;
 }
 
-extern "C" int hd_bn_bwd_apply(const void* dy, const void* yrelu, const void* z, const float* mean, const float* invstd,
-                               const float* gamma, const float* sums, double count, void* dz, void* gout, float* dgamma,
-                               float* dbeta, int64_t n_pix, int C, hd_stream st) {
+extern "C" int hd_bn_bwd_apply(const void* dy, const void* yrelu, const float* rscale, const float* rshift, const void* z,
+                               const float* mean, const float* invstd, const float* gamma, const float* sums, double count,
+                               void* dz, void* gout, float* dgamma, float* dbeta, int64_t n_pix, int C, hd_stream st) {
     HD_CHECK_ARG(dy && z && mean && invstd && gamma && sums && dz && C % 8 == 0 && n_pix > 0 && count > 0);
     bn_bwd_apply_kernel<<<ew_blocks(n_pix * (C / 8)), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
-        static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(yrelu),
+        static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(yrelu), rscale, rshift,
         static_cast<const __nv_bfloat16*>(z), mean, invstd, gamma, sums, static_cast<float>(1.0 / count),
         static_cast<__nv_bfloat16*>(dz), static_cast<__nv_bfloat16*>(gout), dgamma, dbeta, n_pix, C);
     HD_LAUNCH_OK();

@@ -18,7 +18,8 @@
 namespace hd {
 
 constexpr int kWMaxTaps = 9;
-constexpr int kWThreads = 192;
+constexpr int kWCpThreads = 128;               // cp.async producers for narrow-channel operands (rows < 128 bytes)
+constexpr int kWThreads = 192 + kWCpThreads;
 
 struct WgradParams {
     CUtensorMap tmDY;
@@ -34,6 +35,11 @@ struct WgradParams {
     int taps;
     float* dw;
     int stages, a_bytes, stage_bytes, tmem_cols;
+    // narrow-channel operands are gathered with cp.async (TMA handles 32/64-byte rows one row at a time)
+    int cp_a, cp_b;
+    const __nv_bfloat16* dy_ptr;
+    const __nv_bfloat16* x_ptr;
+    int Ho, Wo, Hx, Wx, Cx;
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
@@ -58,8 +64,9 @@ __global__ void __launch_bounds__(kWThreads) wgrad_gemm_kernel(const __grid_cons
     const int num_k = static_cast<int>(t_hi - t_lo);
 
     if (threadIdx.x == 0) {
+        const int full_count = ((P.cp_a && P.cp_b) ? 0 : 1) + ((P.cp_a || P.cp_b) ? kWCpThreads : 0);
         for (int s = 0; s < stages; ++s) {
-            mbar_init(full0 + 8u * s, 1);
+            mbar_init(full0 + 8u * s, full_count);
             mbar_init(empty0 + 8u * s, 1);
         }
         mbar_init(tfull, 1);
@@ -79,10 +86,10 @@ __global__ void __launch_bounds__(kWThreads) wgrad_gemm_kernel(const __grid_cons
 
     const int n_chunks = P.BNt / P.cb;
     if (warp == 0) {
-        if (elect_one()) {
+        if (!(P.cp_a && P.cp_b) && elect_one()) {
             int nb = 0;                                        // X chunks inside the tensor
             for (int j = 0; j < n_chunks; ++j) nb += (ci0 + j * P.cb < P.Cin) ? 1 : 0;
-            const uint32_t tx_bytes = static_cast<uint32_t>(P.KP * 2 * (P.m_chunks * P.ca + nb * P.cb));
+            const uint32_t tx_bytes = static_cast<uint32_t>(P.KP * 2 * ((P.cp_a ? 0 : P.m_chunks * P.ca) + (P.cp_b ? 0 : nb * P.cb)));
             int stage = 0;
             uint32_t phase = 0;
             for (long t = t_lo; t < t_hi; ++t) {
@@ -95,9 +102,9 @@ __global__ void __launch_bounds__(kWThreads) wgrad_gemm_kernel(const __grid_cons
                 const uint32_t sb = sa + P.a_bytes;
                 const uint32_t fb = full0 + 8u * stage;
                 mbar_expect_tx(fb, tx_bytes);
-                for (int i = 0; i < P.m_chunks; ++i)
+                for (int i = 0; i < P.m_chunks && !P.cp_a; ++i)
                     tma_load_5d(sa + i * P.KP * P.ca * 2, &P.tmDY, fb, co0 + i * P.ca, w0, 0, h0, img);
-                for (int j = 0; j < n_chunks; ++j) {
+                for (int j = 0; j < n_chunks && !P.cp_b; ++j) {
                     const int cc = ci0 + j * P.cb;
                     if (cc >= P.Cin) break;
                     const int src = cc < P.C0 ? 0 : 1;
@@ -112,24 +119,98 @@ __global__ void __launch_bounds__(kWThreads) wgrad_gemm_kernel(const __grid_cons
         if (elect_one()) {
             const uint32_t idesc = make_idesc_bf16(P.M, P.BNt, 1, 1);
             const uint32_t lta = swizzle_layout_type(P.ca * 2), ltb = swizzle_layout_type(P.cb * 2);
-            const uint32_t lbo_a = P.KP * P.ca * 2, sbo_a = 8 * P.ca * 2, kstep_a = 16 * P.ca * 2;
+            // when fewer channel chunks were loaded than M=128 needs, the missing chunks alias chunk 0 (LBO = 0):
+            // their accumulator rows are duplicates that the epilogue never reads
+            const uint32_t lbo_a = (P.m_chunks * P.ca < P.M) ? 0u : P.KP * P.ca * 2;
+            const uint32_t sbo_a = 8 * P.ca * 2, kstep_a = 16 * P.ca * 2;
             const uint32_t lbo_b = P.KP * P.cb * 2, sbo_b = 8 * P.cb * 2, kstep_b = 16 * P.cb * 2;
+            // loop-invariant descriptor halves; only the start-address field of lo moves (16-byte units)
+            const uint64_t da0 = make_smem_desc(0, lbo_a, sbo_a, lta), db0 = make_smem_desc(0, lbo_b, sbo_b, ltb);
+            const uint32_t a_hi = static_cast<uint32_t>(da0 >> 32), b_hi = static_cast<uint32_t>(db0 >> 32);
+            const uint32_t a_lo0 = static_cast<uint32_t>(da0) + (smem_base >> 4);
+            const uint32_t b_lo0 = static_cast<uint32_t>(db0) + ((smem_base + P.a_bytes) >> 4);
+            const uint32_t stage_u = P.stage_bytes >> 4, ka_u = kstep_a >> 4, kb_u = kstep_b >> 4;
+            const int ksteps = P.KP / 16;
             int stage = 0;
             uint32_t phase = 0;
+            uint32_t accum = 0;
             for (int ks = 0; ks < num_k; ++ks) {
                 mbar_wait(full0 + 8u * stage, phase);
+                if (P.cp_a || P.cp_b) fence_proxy_async_smem();    // cp.async wrote through the generic proxy
                 tc_fence_after();
-                const uint32_t sa = smem_base + stage * P.stage_bytes;
-                const uint32_t sb = sa + P.a_bytes;
-                for (int k = 0; k < P.KP / 16; ++k) {
-                    const uint64_t da = make_smem_desc(sa + k * kstep_a, lbo_a, sbo_a, lta);
-                    const uint64_t db = make_smem_desc(sb + k * kstep_b, lbo_b, sbo_b, ltb);
-                    umma_bf16(tmem_base, da, db, idesc, (ks | k) != 0);
+                uint32_t a_lo = a_lo0 + stage * stage_u, b_lo = b_lo0 + stage * stage_u;
+                for (int k = 0; k < ksteps; ++k) {
+                    umma_bf16_lohi(tmem_base, a_lo, a_hi, b_lo, b_hi, idesc, accum);
+                    accum = 1;
+                    a_lo += ka_u;
+                    b_lo += kb_u;
                 }
                 umma_commit(empty0 + 8u * stage);
                 if (++stage == stages) { stage = 0; phase ^= 1u; }
             }
             umma_commit(tfull);
+        }
+    } else if (warp >= 6) {
+        // ================= cp.async producers for narrow-channel operands =================
+        if (P.cp_a || P.cp_b) {
+            const int pt = threadIdx.x - 192;
+            // per-(thread, slot) constants: row / chunk decomposition of the 16-byte pieces this thread copies
+            const int cpr_a = P.ca / 8, cpr_b = P.cb / 8;
+            int a_hl[4], a_wl[4], b_hl[4], b_wl[4];
+            uint32_t a_dst[4], b_dst[4];
+            long a_off[4], b_off[4];
+            bool a_on[4], b_on[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int q = pt + kWCpThreads * i;
+                int r = q / cpr_a, ch = q - r * cpr_a;
+                a_on[i] = P.cp_a && q < P.KP * cpr_a;
+                a_hl[i] = r / P.TW; a_wl[i] = r - a_hl[i] * P.TW;
+                a_dst[i] = swz(static_cast<uint32_t>(r * P.ca * 2 + ch * 16), cpr_a - 1);
+                a_off[i] = (static_cast<long>(a_hl[i]) * P.Wo + a_wl[i]) * P.Cout + co0 + ch * 8;
+                r = q / cpr_b; ch = q - r * cpr_b;
+                b_on[i] = P.cp_b && q < P.KP * cpr_b;
+                b_hl[i] = r / P.TW; b_wl[i] = r - b_hl[i] * P.TW;
+                b_dst[i] = swz(static_cast<uint32_t>(r * P.cb * 2 + ch * 16), cpr_b - 1);
+                b_off[i] = (static_cast<long>(b_hl[i]) * P.Wx + b_wl[i]) * P.Cx + ci0 + ch * 8;
+            }
+            const int dh = P.tap_dh[tap], dw = P.tap_dw[tap];
+            const long tap_off = (static_cast<long>(dh) * P.Wx + dw) * P.Cx;
+            int stage = 0;
+            uint32_t phase = 0;
+            // incremental tile coordinates (no divisions in the loop)
+            int tw_i = static_cast<int>(t_lo % P.tiles_w);
+            int th_i = static_cast<int>((t_lo / P.tiles_w) % P.tiles_h);
+            int img = static_cast<int>(t_lo / (P.tiles_w * P.tiles_h));
+            for (long t = t_lo; t < t_hi; ++t) {
+                const int w0 = tw_i * P.TW, h0 = th_i * P.TH;
+                mbar_wait(empty0 + 8u * stage, phase ^ 1u);
+                const uint32_t sa = smem_base + stage * P.stage_bytes;
+                const uint32_t sb = sa + P.a_bytes;
+                const __nv_bfloat16* dy_base = P.dy_ptr + ((static_cast<long>(img) * P.Ho + h0) * P.Wo + w0) * P.Cout;
+                const __nv_bfloat16* x_base = P.x_ptr + ((static_cast<long>(img) * P.Hx + h0) * P.Wx + w0) * P.Cx + tap_off;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (a_on[i]) {
+                        const bool ok = h0 + a_hl[i] < P.Ho && w0 + a_wl[i] < P.Wo;
+                        const __nv_bfloat16* src = ok ? dy_base + a_off[i] : P.dy_ptr;
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sa + a_dst[i]), "l"(src), "r"(ok ? 16 : 0) : "memory");
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (b_on[i]) {
+                        const int hi = h0 + b_hl[i] + dh, wi = w0 + b_wl[i] + dw;
+                        const bool ok = static_cast<unsigned>(hi) < static_cast<unsigned>(P.Hx) && static_cast<unsigned>(wi) < static_cast<unsigned>(P.Wx);
+                        const __nv_bfloat16* src = ok ? x_base + b_off[i] : P.x_ptr;
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sb + b_dst[i]), "l"(src), "r"(ok ? 16 : 0) : "memory");
+                    }
+                }
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full0 + 8u * stage) : "memory");
+                if (++stage == stages) { stage = 0; phase ^= 1u; }
+                if (++tw_i == P.tiles_w) { tw_i = 0; if (++th_i == P.tiles_h) { th_i = 0; ++img; } }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
         }
     } else if (num_k > 0) {
         const int quad = warp & 3;
@@ -204,7 +285,7 @@ extern "C" int hd_conv_wgrad(const hd_conv_args* a, hd_stream stream_) {
     P.C0 = x0.c;
     P.Cin = x0.c + (two ? a->x1.c : 0);
     P.taps = k * k;
-    P.M = P.Cout >= 128 ? 128 : 64;
+    P.M = 128;                                   // M=64 UMMAs (SS) expose the smem A-read latency; always issue M=128
     P.ca = chunk_of(P.Cout, P.Cout);
     P.cb = chunk_of(x0.c, two ? a->x1.c : x0.c);
     HD_CHECK_ARG(P.ca && P.cb);
@@ -250,7 +331,7 @@ extern "C" int hd_conv_wgrad(const hd_conv_args* a, hd_stream stream_) {
     P.x_qstride[0] = x0.c; P.x_qstride[1] = two ? a->x1.c : 0;
     P.dw = a->dw;
 
-    P.a_bytes = wround_up(P.KP * P.M * 2, 1024);
+    P.a_bytes = wround_up(P.KP * P.m_chunks * P.ca * 2, 1024);
     P.stage_bytes = P.a_bytes + wround_up(P.KP * P.BNt * 2, 1024);
     int stages = (190 * 1024) / P.stage_bytes;
     if (stages > 6) stages = 6;
@@ -271,6 +352,12 @@ extern "C" int hd_conv_wgrad(const hd_conv_args* a, hd_stream stream_) {
     if (splits < 1) splits = 1;
     P.splits = splits;
 
+    // cp.async gather for operands whose rows are narrower than 128 bytes (single chunk group, plain stride-1 view)
+    P.cp_a = (P.ca < 64 && P.Cout <= P.ca) ? 1 : 0;
+    P.cp_b = (P.cb < 64 && s == 1 && !two && P.Cin <= P.cb) ? 1 : 0;
+    P.dy_ptr = static_cast<const __nv_bfloat16*>(dy.ptr);
+    P.x_ptr = static_cast<const __nv_bfloat16*>(x0.ptr);
+    P.Ho = Ho; P.Wo = Wo; P.Hx = x0.h; P.Wx = x0.w; P.Cx = x0.c;
     if (wact_map(&P.tmDY, dy, false, P.ca, P.TW, P.TH)) return HD_ERR_CUDA;
     if (wact_map(&P.tmX[0], x0, s == 2, P.cb, P.TW, P.TH)) return HD_ERR_CUDA;
     if (two) { if (wact_map(&P.tmX[1], a->x1, s == 2, P.cb, P.TW, P.TH)) return HD_ERR_CUDA; }

@@ -176,18 +176,18 @@ def bn_apply(z, scale, shift, y, relu=True, res=None, res_scale=None, res_shift=
                                       _ptr(y), z.numel() // c, c, _stream()), "hd_bn_apply")
 
 
-def bn_bwd_reduce(dy, y_relu, z, mean, invstd, sums):
+def bn_bwd_reduce(dy, y_relu, z, mean, invstd, sums, relu_scale=None, relu_shift=None):
     c = z.shape[-1]
     with _Timed("bn_bwd_reduce"):
-        check(_lib.load().hd_bn_bwd_reduce(_ptr(dy), _ptr(y_relu), _ptr(z), _ptr(mean), _ptr(invstd), _ptr(sums), z.numel() // c, c,
+        check(_lib.load().hd_bn_bwd_reduce(_ptr(dy), _ptr(y_relu), _ptr(relu_scale), _ptr(relu_shift), _ptr(z), _ptr(mean), _ptr(invstd), _ptr(sums), z.numel() // c, c,
                                            _stream()), "hd_bn_bwd_reduce")
 
 
-def bn_bwd_apply(dy, y_relu, z, mean, invstd, gamma, sums, dz, g_out=None, dgamma=None, dbeta=None):
+def bn_bwd_apply(dy, y_relu, z, mean, invstd, gamma, sums, dz, g_out=None, dgamma=None, dbeta=None, relu_scale=None, relu_shift=None):
     c = z.shape[-1]
     n_pix = z.numel() // c
     with _Timed("bn_bwd_apply"):
-        check(_lib.load().hd_bn_bwd_apply(_ptr(dy), _ptr(y_relu), _ptr(z), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(sums),
+        check(_lib.load().hd_bn_bwd_apply(_ptr(dy), _ptr(y_relu), _ptr(relu_scale), _ptr(relu_shift), _ptr(z), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(sums),
                                           float(n_pix), _ptr(dz), _ptr(g_out), _ptr(dgamma), _ptr(dbeta), n_pix, c, _stream()),
               "hd_bn_bwd_apply")
 

@@ -412,14 +412,18 @@ class _UnetEngine:
             torch._foreach_add_(self.nbt, 1)
 
     # ---- backward --------------------------------------------------------------------------------------
-    def _bn_bwd(self, l, g, y_relu, z=None, g_out=None):
-        """BatchNorm backward for layer l given dL/d(post-BN, pre-ReLU-mask) = g masked by y_relu>0 -> l.dz."""
+    def _bn_bwd(self, l, g, y_relu, z=None, g_out=None, direct_relu=False):
+        """BatchNorm backward for layer l given g = dL/d(ReLU output); the ReLU mask comes from y_relu (residual blocks:
+        the block output) or, when the ReLU follows this BN directly, is recomputed from z (one tensor less to read)."""
         z = l.z if z is None else z
         l.sums.zero_()
-        ops.bn_bwd_reduce(g, y_relu, z, l.mean, l.invstd, l.sums)
+        rs, rb = (l.scale, l.shift) if direct_relu else (None, None)
+        yr = None if direct_relu else y_relu
+        ops.bn_bwd_reduce(g, yr, z, l.mean, l.invstd, l.sums, relu_scale=rs, relu_shift=rb)
         dz = self.gbuf(("dz", l.name), z)
-        ops.bn_bwd_apply(g, y_relu, z, l.mean, l.invstd, l.bn.weight.detach(), l.sums, dz, g_out,
-                         self.grad_views[l.bn_name + ".weight"], self.grad_views[l.bn_name + ".bias"])
+        ops.bn_bwd_apply(g, yr, z, l.mean, l.invstd, l.bn.weight.detach(), l.sums, dz, g_out,
+                         self.grad_views[l.bn_name + ".weight"], self.grad_views[l.bn_name + ".bias"],
+                         relu_scale=rs, relu_shift=rb)
         return dz
 
     def _wgrad(self, l, x0, dz, x1=None):
@@ -441,11 +445,11 @@ class _UnetEngine:
         for i in reversed(range(len(self.dblocks))):
             d = self.dblocks[i]
             c1, c2 = d["c1"], d["c2"]
-            dz2 = self._bn_bwd(c2, g, d["a2"])
+            dz2 = self._bn_bwd(c2, g, d["a2"], direct_relu=True)
             self._wgrad(c2, d["a1"], dz2)
             g_a1 = self.gbuf(("g", c2.name), d["a1"])
             ops.conv_dgrad(ops.conv_args(dz2, g_a1, c2.packed.w_dgrad, k=3))
-            dz1 = self._bn_bwd(c1, g_a1, d["a1"])
+            dz1 = self._bn_bwd(c1, g_a1, d["a1"], direct_relu=True)
             self._wgrad(c1, d["up"], dz1, x1=d["skip"])
             g_up = self.gbuf(("gup", i), d["up"])
             g_skip = self.gbuf(("gskip", i), d["skip"]) if d["skip"] is not None else None
@@ -465,7 +469,7 @@ class _UnetEngine:
             self._wgrad(c2, blk["a1"], dz2)
             g_a1 = self.gbuf(("g", c2.name), blk["a1"])
             ops.conv_dgrad(ops.conv_args(dz2, g_a1, c2.packed.w_dgrad, k=3))
-            dz1 = self._bn_bwd(c1, g_a1, blk["a1"])
+            dz1 = self._bn_bwd(c1, g_a1, blk["a1"], direct_relu=True)
             x_in = blk["x_in"]
             self._wgrad(c1, x_in, dz1)
             g_x = self.gbuf(("gx", c1.name), x_in)
@@ -482,6 +486,6 @@ class _UnetEngine:
         g_stem = self.gbuf(("g", "stem"), self.a_stem)
         ops.maxpool_bwd(self.a_stem, self.p0, g, g_stem, add=skip_grads[3])
         zs = st.z.view(1, 1, -1, 64)
-        dzs = self._bn_bwd(st, g_stem.view(1, 1, -1, 64), self.a_stem.view(1, 1, -1, 64), z=zs)
+        dzs = self._bn_bwd(st, g_stem.view(1, 1, -1, 64), self.a_stem.view(1, 1, -1, 64), z=zs, direct_relu=True)
         ops.conv_wgrad(ops.conv_args(self.patches, dzs, k=1, dw=st.dw, algo_cin=147))
         ops.unpack_wgrad(st.dw, gv["encoder.conv1.weight"], 64, 3, 7, 3, ops.STEM_KPAD)

@@ -105,13 +105,15 @@ int hd_bn_finalize(const float* stats, int stats_replicas, int channels, double 
 /* y = relu?( z*scale+shift + (res ? (res_scale ? res*res_scale+res_shift : res) : 0) ), all bf16 NHWC, n_pix pixels. */
 int hd_bn_apply(const void* z, const float* scale, const float* shift, const void* res, const float* res_scale,
                 const float* res_shift, int relu, void* y, int64_t n_pix, int channels, hd_stream stream);
-/* Backward, pass 1: with g = dy * (y>0 if relu_y given) : sums[0][c] = sum g, sums[1][c] = sum g*xhat (atomics; caller zeroes). */
-int hd_bn_bwd_reduce(const void* dy, const void* y_relu, const void* z, const float* mean, const float* invstd,
-                     float* sums, int64_t n_pix, int channels, hd_stream stream);
+/* Backward, pass 1: g = dy masked by the ReLU that followed the BN: (y_relu > 0) when y_relu is given (residual blocks:
+ * the block output), else (z*relu_scale+relu_shift > 0) recomputed from z when relu_scale is given, else no mask.
+ * sums[0][c] = sum g, sums[1][c] = sum g*xhat (atomics; caller zeroes). */
+int hd_bn_bwd_reduce(const void* dy, const void* y_relu, const float* relu_scale, const float* relu_shift, const void* z,
+                     const float* mean, const float* invstd, float* sums, int64_t n_pix, int channels, hd_stream stream);
 /* Backward, pass 2: dz = gamma*invstd*(g - sums0/count - xhat*sums1/count); optional g_out = g (masked dy);
  * dgamma = sums1, dbeta = sums0 are written (fp32, scaled by grad_scale) when non-NULL. */
-int hd_bn_bwd_apply(const void* dy, const void* y_relu, const void* z, const float* mean, const float* invstd,
-                    const float* gamma, const float* sums, double count, void* dz, void* g_out, float* dgamma,
+int hd_bn_bwd_apply(const void* dy, const void* y_relu, const float* relu_scale, const float* relu_shift, const void* z,
+                    const float* mean, const float* invstd, const float* gamma, const float* sums, double count, void* dz, void* g_out, float* dgamma,
                     float* dbeta, int64_t n_pix, int channels, hd_stream stream);
 
 /* ---- memory-bound glue ------------------------------------------------------------------------------ */

@@ -284,6 +284,17 @@ def test_batchnorm_train_fwd_bwd():
     dz, gout = torch.empty_like(z), torch.empty_like(z)
     dgamma, dbeta = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
     o.bn_bwd_apply(dy, y, z, mean, invstd, gamma, sums, dz, gout, dgamma, dbeta)
+    # ReLU mask recomputed from z (no residual): must equal the y_relu path on a residual-free layer
+    y2 = torch.empty_like(z)
+    o.bn_apply(z, scale, shift, y2, relu=True)
+    s_a, s_b = torch.zeros(2, c, device="cuda"), torch.zeros(2, c, device="cuda")
+    o.bn_bwd_reduce(dy, y2, z, mean, invstd, s_a)
+    o.bn_bwd_reduce(dy, None, z, mean, invstd, s_b, relu_scale=scale, relu_shift=shift)
+    dz_a, dz_b = torch.empty_like(z), torch.empty_like(z)
+    o.bn_bwd_apply(dy, y2, z, mean, invstd, gamma, s_a, dz_a)
+    o.bn_bwd_apply(dy, None, z, mean, invstd, gamma, s_b, dz_b, relu_scale=scale, relu_shift=shift)
+    torch.cuda.synchronize()
+    assert torch.allclose(s_a, s_b, rtol=1e-4, atol=1e-3) and (dz_a.float() - dz_b.float()).abs().max().item() < 1e-2
     torch.cuda.synchronize()
     # mask differences at exactly-rounded-to-zero outputs are possible; compare with a tolerance on the sums
     assert torch.allclose(dgamma, g_.grad, rtol=2e-2, atol=2e-1), (dgamma - g_.grad).abs().max()
