@@ -37,6 +37,7 @@ PROTOTYPES = {
     "hd_last_error": [],
     "hd_device_ok": [],
     "hd_conv_fwd": [P(HdConvArgs), c_void_p],
+    "hd_conv_fwd_tiles": [P(HdConvArgs)],
     "hd_conv_dgrad": [P(HdConvArgs), c_void_p],
     "hd_conv_wgrad": [P(HdConvArgs), c_void_p],
     "hd_pack_conv_weight": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p],

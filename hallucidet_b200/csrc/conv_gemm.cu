@@ -81,7 +81,7 @@ struct ConvGemmParams {
     int a_H, a_W, a_C;
 };
 
-__device__ __forceinline__ void decode_tile(const ConvGemmParams& P, int tile, int& z, int& n0, int& img, int& h0, int& w0) {
+__device__ __forceinline__ void decode_tile(const ConvGemmParams& P, int tile, int& z, int& n0, int& img, int& h0, int& w0, int* mt_out = nullptr) {
     // m tiles fastest: CTAs running concurrently share the weight tile (L2) and walk neighbouring pixels
     const int per_phase = P.m_tiles * P.n_tiles;
     z = static_cast<int>(fdiv(tile, P.fd_per_phase));
@@ -95,6 +95,7 @@ __device__ __forceinline__ void decode_tile(const ConvGemmParams& P, int tile, i
     const int th_i = t1 - img * P.tiles_h;
     w0 = tw_i * P.TW;
     h0 = th_i * P.TH;
+    if (mt_out) *mt_out = mt;
 }
 
 // Persistent CTA (one per SM): a static round-robin over output tiles; the TMA producer and the MMA issuer run
@@ -110,8 +111,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const uint32_t stg_bytes = (128u * P.BN * 2u + 1023u) & ~1023u;
     const uint32_t staging0 = smem_base + static_cast<uint32_t>(stages * P.stage_bytes);  // 2 x (128 x BN bf16), 1024-aligned
     const uint32_t bias_s = staging0 + 2u * stg_bytes;                                     // BN floats
-    const uint32_t stat_s = bias_s + 512u;                                                 // 2 x BN floats (per-tile BN statistics)
-    const uint32_t bar_base = stat_s + 1024u;
+    const uint32_t bar_base = bias_s + 512u;
     // barriers: full[s], empty[s], tmem_full[2], tmem_empty[2], then the TMEM base-address slot
     const uint32_t full0 = bar_base, empty0 = bar_base + 8u * stages;
     const uint32_t tfull0 = bar_base + 16u * stages, tempty0 = tfull0 + 16u;
@@ -310,8 +310,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         uint32_t acc_phase = 0;
         int iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-            int z, n0, img, h0, w0;
-            decode_tile(P, tile, z, n0, img, h0, w0);
+            int z, n0, img, h0, w0, mt;
+            decode_tile(P, tile, z, n0, img, h0, w0, &mt);
             const int num_k = (P.tap_begin[z + 1] - P.tap_begin[z]) * P.kpt;
             const int hg = h0 + hl, wg = w0 + wl;
             const bool valid = (row < P.TW * P.TH) && hg < P.Hg && wg < P.Wg;
@@ -329,8 +329,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 const float b = ch < P.Cout_total ? __ldg(P.bias + ch) : 0.f;
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * et), "f"(b) : "memory");
             }
-            if (P.stats != nullptr && et < 2 * P.BN)
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(stat_s + 4u * et), "f"(0.f) : "memory");
             // fused-operand loads are software-pipelined one 16-column chunk ahead of their use
             uint4 na0 = make_uint4(0, 0, 0, 0), na1 = na0, nm0 = na0, nm1 = na0;
             if (c_begin < c_end && valid && n0 + c_begin * 16 < P.Cout_total) {
@@ -455,10 +453,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     tma_store_commit();
                 }
                 if (P.stats != nullptr) {
-                    // per-channel sum / sum-of-squares of the staged (bf16-rounded, invalid rows zeroed) tile
-                    const int pairs = P.BN / 2;
-                    const int cp = et % pairs, rg = et / pairs, nrg = kEpiThreads / pairs;
-                    const int cl = cp * 2;
+                    // per-channel sum / sum-of-squares of the staged (bf16-rounded, invalid rows zeroed) tile.  Each warp owns
+                    // BN/16 channel pairs and all 128 rows of them, so the reduction is a fixed-order shuffle tree and the
+                    // result is written (not atomically added) to this tile's row of the statistics buffer: run-to-run
+                    // deterministic, no memset, bn_finalize sums the rows in a fixed order.
+                    const int ppw = (P.BN / 2) / kEpiWarps;            // channel pairs per warp: 8 / 4 / 2 / 1
+                    const int p_in_w = lane % ppw, rg = lane / ppw, nrg = 32 / ppw;
+                    const int cl = (ew * ppw + p_in_w) * 2;
                     const uint32_t sub = cl / sub_c;
                     float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
                     for (int r = rg; r < 128; r += nrg) {
@@ -468,31 +469,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         const float a = bf16_lo(w), b = bf16_hi(w);
                         s0 += a; q0 += a * a; s1 += b; q1 += b * b;
                     }
-                    // reduce inside the CTA first: lanes sharing a channel pair (BN <= 32), then shared-memory atomics,
-                    // so that one tile issues only 2*BN global atomics
-                    if (pairs < 32) {
-                        for (int o = 16; o >= pairs; o >>= 1) {
-                            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-                            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                            q0 += __shfl_xor_sync(0xffffffffu, q0, o);
-                            q1 += __shfl_xor_sync(0xffffffffu, q1, o);
-                        }
+                    for (int o = 16; o >= ppw; o >>= 1) {
+                        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                        q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+                        q1 += __shfl_xor_sync(0xffffffffu, q1, o);
                     }
-                    if (pairs >= 32 || lane < pairs) {
-                        asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(stat_s + 4u * cl), "f"(s0) : "memory");
-                        asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(stat_s + 4u * (cl + 1)), "f"(s1) : "memory");
-                        asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(stat_s + 4u * (P.BN + cl)), "f"(q0) : "memory");
-                        asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(stat_s + 4u * (P.BN + cl + 1)), "f"(q1) : "memory");
-                    }
-                    named_bar_sync(3, kEpiThreads);
-                    if (et < 2 * P.BN) {
-                        const int which = et / P.BN, cch = et - which * P.BN;
-                        const int ch = n0 + cch;
-                        if (ch < P.Cout_total) {
-                            float v;
-                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(stat_s + 4u * et));
-                            atomicAdd(P.stats + (static_cast<long>(tile % P.stats_replicas) * 2 + which) * P.Cout_total + ch, v);
-                        }
+                    const int ch = n0 + cl;
+                    if (lane < ppw && ch < P.Cout_total) {
+                        float* st = P.stats + static_cast<long>(mt) * 2 * P.Cout_total;
+                        st[ch] = s0;
+                        st[ch + 1] = s1;
+                        st[P.Cout_total + ch] = q0;
+                        st[P.Cout_total + ch + 1] = q1;
                     }
                 }
             }
@@ -566,7 +555,7 @@ static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStrea
     P.a_bytes = P.a_sub * P.tps;
     P.stage_bytes = (P.a_sub + P.b_sub) * P.tps;
     const int staging = 2 * round_up(128 * P.BN * 2, 1024);         // double-buffered output staging
-    const int fixed = 1024 + staging + 512 + 1024 + 16 * 8 + 64;   // alignment slack, staging, bias, stats, barriers
+    const int fixed = 1024 + staging + 512 + 16 * 8 + 64;          // alignment slack, staging, bias, barriers
     int stages = (232448 - fixed) / P.stage_bytes;              // 227 KB = the sm_100 per-block maximum
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
@@ -576,6 +565,10 @@ static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStrea
     P.tmem_cols = cols;
     P.m_tiles = P.tiles_w * P.tiles_h * n_img;
     P.n_tiles = (P.Cout_total + P.BN - 1) / P.BN;
+    if (P.stats != nullptr && P.stats_replicas < P.m_tiles) {
+        set_last_error(__FILE__, __LINE__, "stats buffer has fewer rows than output tiles (size it with hd_conv_fwd_tiles)");
+        return HD_ERR_BAD_ARG;
+    }
     P.fd_per_phase = make_fastdiv(static_cast<uint32_t>(P.m_tiles * P.n_tiles));
     P.fd_m_tiles = make_fastdiv(static_cast<uint32_t>(P.m_tiles));
     P.fd_tiles_w = make_fastdiv(static_cast<uint32_t>(P.tiles_w));
@@ -616,7 +609,7 @@ static int fill_epilogue(ConvGemmParams& P, const hd_conv_args* a) {
     P.relu = a->relu;
     P.sigmoid = a->sigmoid;
     P.stats = a->stats;
-    P.stats_replicas = a->stats_replicas > 0 ? a->stats_replicas : 1;
+    P.stats_replicas = a->stats_replicas;                  // rows available in the per-tile statistics buffer
     P.out_f32 = a->out_f32_nchw;
     P.out_f32_c = a->out_f32_channels;
     P.store_bf16 = a->store_bf16;
@@ -691,6 +684,15 @@ extern "C" int hd_conv_fwd(const hd_conv_args* a, hd_stream stream_) {
     P.tmOut[1] = P.tmOut[0];
     P.out_ptr = static_cast<__nv_bfloat16*>(a->y0.ptr);
     return launch_conv_gemm(P, N, 1, stream);
+}
+
+extern "C" int hd_conv_fwd_tiles(const hd_conv_args* a) {
+    // number of 128-pixel output tiles hd_conv_fwd uses for this problem == rows of the per-tile statistics buffer
+    if (a == nullptr || a->stride < 1 || a->x0.h <= 0 || a->x0.w <= 0) return HD_ERR_BAD_ARG;
+    const int Ho = a->x0.h / a->stride, Wo = a->x0.w / a->stride;
+    int TW, TH;
+    pick_tile(Ho, Wo, &TW, &TH);
+    return ((Wo + TW - 1) / TW) * ((Ho + TH - 1) / TH) * a->x0.n;
 }
 
 extern "C" int hd_conv_dgrad(const hd_conv_args* a, hd_stream stream_) {

@@ -136,16 +136,27 @@ __global__ void stem_col2im_kernel(const __nv_bfloat16* __restrict__ dp, float* 
 // -------------------------------------------------------------------------------------------------
 // train-mode BatchNorm
 // -------------------------------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(const float* __restrict__ stats, int reps, int C, double count, const float* gamma,
+// one block per channel: fixed-order reduction over the per-tile partial rows (deterministic), fp64 mean / variance
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, int rows, int C, double count, const float* gamma,
                                    const float* beta, float eps, float momentum, float* rm, float* rv, float* mean_out,
                                    float* invstd_out, float* scale_out, float* shift_out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
+    __shared__ double ss[128], sq[128];
+    const int c = blockIdx.x, t = threadIdx.x;
     double s = 0.0, q = 0.0;
-    for (int r = 0; r < reps; ++r) {
+    for (int r = t; r < rows; r += 128) {
         s += stats[(static_cast<long>(r) * 2) * C + c];
         q += stats[(static_cast<long>(r) * 2 + 1) * C + c];
     }
+    ss[t] = s;
+    sq[t] = q;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (t < o) { ss[t] += ss[t + o]; sq[t] += sq[t + o]; }
+        __syncthreads();
+    }
+    if (t != 0) return;
+    s = ss[0];
+    q = sq[0];
     const double mean = s / count;
     double var = q / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -766,7 +777,7 @@ extern "C" int hd_bn_finalize(const float* stats, int reps, int C, double count,
                               float eps, float momentum, float* rm, float* rv, float* mean_out, float* invstd_out,
                               float* scale_out, float* shift_out, hd_stream st) {
     HD_CHECK_ARG(stats && gamma && beta && scale_out && shift_out && C > 0 && reps > 0 && count > 0);
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(st)>>>(stats, reps, C, count, gamma, beta, eps,
+    bn_finalize_kernel<<<C, 128, 0, static_cast<cudaStream_t>(st)>>>(stats, reps, C, count, gamma, beta, eps,
                                                                                  momentum, rm, rv, mean_out, invstd_out,
                                                                                  scale_out, shift_out);
     HD_LAUNCH_OK();

@@ -11,7 +11,7 @@ import torch
 from . import _lib
 from ._lib import HdAct, HdConvArgs, check
 
-STATS_REPLICAS = 16
+STATS_REPLICAS = 16      # legacy name: default row count for small test problems (see conv_fwd_tiles)
 STEM_KPAD = 160          # 7*7*3 = 147 -> 5 k-blocks of 32
 
 LAUNCHES = 0             # kernels launched through this module (each C-ABI compute call launches exactly one kernel)
@@ -108,6 +108,18 @@ def _conv_desc(a):
 def conv_fwd(args):
     with _Timed("conv_fwd", _conv_flops(args, "fwd") if PROFILE is not None else 0.0, _conv_desc(args) if PROFILE is not None else ""):
         check(_lib.load().hd_conv_fwd(ctypes.byref(args), _stream()), "hd_conv_fwd")
+
+
+def conv_fwd_tiles(x0, k=3, stride=1):
+    """Rows the per-tile BN statistics buffer needs for a forward conv over x0 (host-only query)."""
+    a = HdConvArgs()
+    a.x0 = act(x0)
+    a.kh = a.kw = k
+    a.stride = stride
+    n = _lib.load().hd_conv_fwd_tiles(ctypes.byref(a))
+    if n <= 0:
+        raise RuntimeError(f"hd_conv_fwd_tiles failed ({n})")
+    return n
 
 
 def conv_dgrad(args):

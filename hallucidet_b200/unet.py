@@ -185,7 +185,7 @@ class _Layer:
         self.packed = packed if packed is not None else ops.PackedConv(self.cp, cin, k, dev, need_dgrad=True)
         self.z = eng.new_act(self.h, self.w, self.cp)
         if bn is not None:
-            self.stats = torch.zeros(ops.STATS_REPLICAS, 2, cout, device=dev)
+            self.stats = None                            # [tiles][2][cout] per-tile partials, sized at first use
             self.mean, self.invstd, self.scale, self.shift = (torch.empty(cout, device=dev) for _ in range(4))
             self.sums = torch.zeros(2, cout, device=dev)
             self.bias = torch.empty(cout, device=dev)    # eval-mode folded shift
@@ -306,7 +306,8 @@ class _UnetEngine:
     def _conv_bn(self, l, x0, a_out, x1=None, relu=True, res=None, res_layer=None, apply=True):
         """train: z = conv(x) (+stats) -> finalize -> a_out = relu(bn(z) + res).   eval: fused epilogue."""
         if self.training:
-            l.stats.zero_()
+            if l.stats is None:
+                l.stats = torch.zeros(ops.conv_fwd_tiles(x0, l.k, l.stride), 2, l.cout, device=self.device)
             ops.conv_fwd(ops.conv_args(x0, l.z, l.packed.w_fwd, k=l.k, stride=l.stride, x1=x1, stats=l.stats))
             bn = l.bn
             ops.bn_finalize(l.stats, self.B * l.h * l.w, bn.weight.detach(), bn.bias.detach(), bn.eps,
@@ -373,7 +374,8 @@ class _UnetEngine:
         zs = st.z.view(1, 1, -1, 64)
         a_stem_flat = self.a_stem.view(1, 1, -1, 64)
         if self.training:
-            st.stats.zero_()
+            if st.stats is None:
+                st.stats = torch.zeros(ops.conv_fwd_tiles(self.patches, 1, 1), 2, 64, device=self.device)
             ops.conv_fwd(ops.conv_args(self.patches, zs, st.packed.w_fwd, k=1, stats=st.stats, algo_cin=147))
             bn = st.bn
             ops.bn_finalize(st.stats, zs.shape[2], bn.weight.detach(), bn.bias.detach(), bn.eps, bn.momentum or 0.1,

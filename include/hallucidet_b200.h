@@ -61,8 +61,8 @@ typedef struct hd_conv_args {
     const void* mask;         /* bf16 NHWC tensor shaped like y0: result zeroed where mask <= 0 (ReLU backward) */
     int32_t relu;
     int32_t sigmoid;          /* applied to the fp32 NCHW output only */
-    float* stats;             /* fp32 [stats_replicas][2][channels]: per-channel sum / sum-of-squares of the (bf16-rounded) output, accumulated with atomics; NULL = off */
-    int32_t stats_replicas;
+    float* stats;             /* fp32 [stats_replicas][2][channels]: per-OUTPUT-TILE partial sum / sum-of-squares of the (bf16-rounded) output, one row per 128-pixel tile, written (not accumulated): deterministic, no memset needed; NULL = off */
+    int32_t stats_replicas;   /* rows available in `stats`; must be >= hd_conv_fwd_tiles(args) */
     float* out_f32_nchw;      /* optional fp32 NCHW copy of the output (first out_f32_channels channels) */
     int32_t out_f32_channels;
     int32_t store_bf16;       /* 1: write y0/y1 (bf16 NHWC); 0: only out_f32_nchw */
@@ -73,6 +73,7 @@ typedef struct hd_conv_args {
 } hd_conv_args;
 
 int hd_conv_fwd(const hd_conv_args* a, hd_stream stream);
+int hd_conv_fwd_tiles(const hd_conv_args* a);   /* number of output tiles (= statistics rows) hd_conv_fwd will use; host-only, no launch */
 int hd_conv_dgrad(const hd_conv_args* a, hd_stream stream);
 int hd_conv_wgrad(const hd_conv_args* a, hd_stream stream);
 
@@ -98,7 +99,8 @@ int hd_stem_im2col(const float* x_nchw, void* patches, int n, int h, int w, int 
 int hd_stem_col2im(const void* dpatches, float* dx_nchw, int n, int h, int w, int k_pad, hd_stream stream);
 
 /* ---- train-mode BatchNorm2d (U-Net; base/modules.py:42, TV: models/resnet.py:80-83) --------------------
- * stats -> per-channel scale/shift (+ running-stat update, momentum/unbiased var as nn.BatchNorm2d). */
+ * stats rows (per-tile partials from hd_conv_fwd, summed in a fixed order) -> per-channel scale/shift
+ * (+ running-stat update, momentum/unbiased var as nn.BatchNorm2d). */
 int hd_bn_finalize(const float* stats, int stats_replicas, int channels, double count, const float* gamma,
                    const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                    float* mean_out, float* invstd_out, float* scale_out, float* shift_out, hd_stream stream);

@@ -87,7 +87,7 @@ def test_conv_fwd_epilogue_bias_add_relu_stats():
     wt = (torch.randn(cout, cin, 3, 3, generator=torch.Generator().manual_seed(3)) / (cin * 9) ** 0.5).to(torch.bfloat16).float().cuda()
     pk = o.PackedConv(cout, cin, 3, "cuda").pack(wt)
     y = torch.empty(n, h, w, cout, dtype=torch.bfloat16, device="cuda")
-    stats = torch.zeros(o.STATS_REPLICAS, 2, cout, device="cuda")
+    stats = torch.full((o.conv_fwd_tiles(x, 3, 1), 2, cout), float("nan"), device="cuda")   # rows are written, not accumulated
     f32 = torch.zeros(n, cout, h, w, device="cuda")
     o.conv_fwd(o.conv_args(x, y, pk.w_fwd, k=3, bias=bias, add=res, relu=True, stats=stats, out_f32=f32, out_f32_channels=cout))
     torch.cuda.synchronize()

@@ -61,7 +61,7 @@ def main():
             args = ops.conv_args(x, y, pk.w_fwd, k=k, stride=s,
                                  bias=torch.randn(cout, device=dev) if "bias" in flags else None,
                                  add=bf(B, ho, wo, cout) if "add" in flags else None, relu="relu" in flags,
-                                 stats=torch.zeros(ops.STATS_REPLICAS, 2, cout, device=dev) if "stats" in flags else None)
+                                 stats=torch.zeros(ops.conv_fwd_tiles(x, k, s), 2, cout, device=dev) if "stats" in flags else None)
             fn = lambda: ops.conv_fwd(args)
             bytes_ = 2 * (x.numel() + y.numel() * (2 if "add" in flags else 1)) + 2 * wt.numel()
         elif kind == "dgrad":
