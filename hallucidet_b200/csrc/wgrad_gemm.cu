@@ -37,6 +37,9 @@ struct WgradParams {
     int stages, a_bytes, stage_bytes, tmem_cols;
     // narrow-channel operands are gathered with cp.async (TMA handles 32/64-byte rows one row at a time)
     int cp_a, cp_b;
+    int n_acc;                    // rotating sub-accumulators (dependent MMAs on one accumulator are latency-bound)
+    int group;                    // pixel tiles per pipeline stage (narrow-channel mode: fewer, fatter stages)
+    int sub_bytes;                // bytes of one (A + B) tile pair inside a stage
     const __nv_bfloat16* dy_ptr;
     const __nv_bfloat16* x_ptr;
     int Ho, Wo, Hx, Wx, Cx;
@@ -64,7 +67,7 @@ __global__ void __launch_bounds__(kWThreads) wgrad_gemm_kernel(const __grid_cons
     const int num_k = static_cast<int>(t_hi - t_lo);
 
     if (threadIdx.x == 0) {
-        const int full_count = ((P.cp_a && P.cp_b) ? 0 : 1) + ((P.cp_a || P.cp_b) ? kWCpThreads : 0);
+        const int full_count = ((P.cp_a && P.cp_b) ? 0 : 1) + ((P.cp_a || P.cp_b) ? kWCpThreads / 32 : 0);   // one arrival per producer warp
         for (int s = 0; s < stages; ++s) {
             mbar_init(full0 + 8u * s, full_count);
             mbar_init(empty0 + 8u * s, 1);
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(kWThreads) wgrad_gemm_kernel(const __grid_cons
         tma_prefetch_desc(&P.tmX[0]);
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, P.tmem_cols);
+        tmem_alloc(tmem_slot, P.n_acc * P.tmem_cols);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -133,17 +136,22 @@ __global__ void __launch_bounds__(kWThreads) wgrad_gemm_kernel(const __grid_cons
             const int ksteps = P.KP / 16;
             int stage = 0;
             uint32_t phase = 0;
-            uint32_t accum = 0;
-            for (int ks = 0; ks < num_k; ++ks) {
+            uint32_t u = 0;
+            const uint32_t n_acc = P.n_acc, cols = P.tmem_cols;
+            const int num_st = (num_k + P.group - 1) / P.group;
+            const uint32_t sub_u = P.sub_bytes >> 4;
+            for (int st = 0; st < num_st; ++st) {
                 mbar_wait(full0 + 8u * stage, phase);
                 if (P.cp_a || P.cp_b) fence_proxy_async_smem();    // cp.async wrote through the generic proxy
                 tc_fence_after();
-                uint32_t a_lo = a_lo0 + stage * stage_u, b_lo = b_lo0 + stage * stage_u;
-                for (int k = 0; k < ksteps; ++k) {
-                    umma_bf16_lohi(tmem_base, a_lo, a_hi, b_lo, b_hi, idesc, accum);
-                    accum = 1;
-                    a_lo += ka_u;
-                    b_lo += kb_u;
+                for (int g = 0; g < P.group; ++g) {
+                    uint32_t a_lo = a_lo0 + stage * stage_u + g * sub_u, b_lo = b_lo0 + stage * stage_u + g * sub_u;
+                    for (int k = 0; k < ksteps; ++k) {
+                        umma_bf16_lohi(tmem_base + (u % n_acc) * cols, a_lo, a_hi, b_lo, b_hi, idesc, u >= n_acc);
+                        ++u;
+                        a_lo += ka_u;
+                        b_lo += kb_u;
+                    }
                 }
                 umma_commit(empty0 + 8u * stage);
                 if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -154,61 +162,88 @@ __global__ void __launch_bounds__(kWThreads) wgrad_gemm_kernel(const __grid_cons
         // ================= cp.async producers for narrow-channel operands =================
         if (P.cp_a || P.cp_b) {
             const int pt = threadIdx.x - 192;
-            // per-(thread, slot) constants: row / chunk decomposition of the 16-byte pieces this thread copies
+            // all addressing state lives in registers: parameters are copied out of the constant bank once, the
+            // (thread, slot) decomposition of the 16-byte pieces is computed once, per tile only adds / compares remain
+            const int Ho = P.Ho, Wo = P.Wo, Hx = P.Hx, Wx = P.Wx, TW = P.TW, TH = P.TH, tiles_w = P.tiles_w, tiles_h = P.tiles_h;
+            const int Cout = P.Cout, Cx = P.Cx, KP = P.KP, group = P.group;
+            const uint32_t stage_bytes = P.stage_bytes, sub_bytes = P.sub_bytes, a_bytes = P.a_bytes;
+            const bool cp_a = P.cp_a != 0, cp_b = P.cp_b != 0;
+            const __nv_bfloat16* dy_ptr = P.dy_ptr;
+            const __nv_bfloat16* x_ptr = P.x_ptr;
+            const int dh = P.tap_dh[tap], dw = P.tap_dw[tap];
             const int cpr_a = P.ca / 8, cpr_b = P.cb / 8;
-            int a_hl[4], a_wl[4], b_hl[4], b_wl[4];
+            int a_hl[4], a_wl[4], b_hh[4], b_ww[4], a_off[4], b_off[4];
             uint32_t a_dst[4], b_dst[4];
-            long a_off[4], b_off[4];
             bool a_on[4], b_on[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int q = pt + kWCpThreads * i;
                 int r = q / cpr_a, ch = q - r * cpr_a;
-                a_on[i] = P.cp_a && q < P.KP * cpr_a;
-                a_hl[i] = r / P.TW; a_wl[i] = r - a_hl[i] * P.TW;
+                a_on[i] = cp_a && q < KP * cpr_a;
+                a_hl[i] = r / TW; a_wl[i] = r - a_hl[i] * TW;
                 a_dst[i] = swz(static_cast<uint32_t>(r * P.ca * 2 + ch * 16), cpr_a - 1);
-                a_off[i] = (static_cast<long>(a_hl[i]) * P.Wo + a_wl[i]) * P.Cout + co0 + ch * 8;
+                a_off[i] = (a_hl[i] * Wo + a_wl[i]) * Cout + co0 + ch * 8;
                 r = q / cpr_b; ch = q - r * cpr_b;
-                b_on[i] = P.cp_b && q < P.KP * cpr_b;
-                b_hl[i] = r / P.TW; b_wl[i] = r - b_hl[i] * P.TW;
-                b_dst[i] = swz(static_cast<uint32_t>(r * P.cb * 2 + ch * 16), cpr_b - 1);
-                b_off[i] = (static_cast<long>(b_hl[i]) * P.Wx + b_wl[i]) * P.Cx + ci0 + ch * 8;
+                b_on[i] = cp_b && q < KP * cpr_b;
+                b_hh[i] = r / TW + dh; b_ww[i] = r - (r / TW) * TW + dw;
+                b_dst[i] = a_bytes + swz(static_cast<uint32_t>(r * P.cb * 2 + ch * 16), cpr_b - 1);
+                b_off[i] = (b_hh[i] * Wx + b_ww[i]) * Cx + ci0 + ch * 8;
             }
-            const int dh = P.tap_dh[tap], dw = P.tap_dw[tap];
-            const long tap_off = (static_cast<long>(dh) * P.Wx + dw) * P.Cx;
             int stage = 0;
             uint32_t phase = 0;
-            // incremental tile coordinates (no divisions in the loop)
-            int tw_i = static_cast<int>(t_lo % P.tiles_w);
-            int th_i = static_cast<int>((t_lo / P.tiles_w) % P.tiles_h);
-            int img = static_cast<int>(t_lo / (P.tiles_w * P.tiles_h));
-            for (long t = t_lo; t < t_hi; ++t) {
-                const int w0 = tw_i * P.TW, h0 = th_i * P.TH;
+            int tw_i = static_cast<int>(t_lo % tiles_w);
+            int th_i = static_cast<int>((t_lo / tiles_w) % tiles_h);
+            int img = static_cast<int>(t_lo / (tiles_w * tiles_h));
+            // software pipeline inside each producer warp: copies of stage i are committed as one cp.async group; the warp
+            // signals stage i-(kLag) once that group has landed (cp.async.wait_group), with ONE mbarrier arrival per warp
+            // (128 per-thread arrivals on one shared-memory word serialise and cost more than the copies themselves)
+            constexpr int kLag = 2;                      // requires >= 3 pipeline stages
+            int sig_stage = 0, issued = 0;
+            for (long t = t_lo; t < t_hi; t += group) {
                 mbar_wait(empty0 + 8u * stage, phase ^ 1u);
-                const uint32_t sa = smem_base + stage * P.stage_bytes;
-                const uint32_t sb = sa + P.a_bytes;
-                const __nv_bfloat16* dy_base = P.dy_ptr + ((static_cast<long>(img) * P.Ho + h0) * P.Wo + w0) * P.Cout;
-                const __nv_bfloat16* x_base = P.x_ptr + ((static_cast<long>(img) * P.Hx + h0) * P.Wx + w0) * P.Cx + tap_off;
+                for (int g = 0; g < group; ++g) {
+                    const bool live = t + g < t_hi;                 // tiles past the range contribute zeros
+                    const int w0 = tw_i * TW, h0 = th_i * TH;
+                    const uint32_t sbase = smem_base + stage * stage_bytes + g * sub_bytes;
+                    const __nv_bfloat16* dy_base = dy_ptr + static_cast<long>((img * Ho + h0) * Wo + w0) * Cout;
+                    const __nv_bfloat16* x_base = x_ptr + static_cast<long>((img * Hx + h0) * Wx + w0) * Cx;
+                    const int a_hmax = live ? Ho - h0 : 0, a_wmax = Wo - w0;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (a_on[i]) {
-                        const bool ok = h0 + a_hl[i] < P.Ho && w0 + a_wl[i] < P.Wo;
-                        const __nv_bfloat16* src = ok ? dy_base + a_off[i] : P.dy_ptr;
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sa + a_dst[i]), "l"(src), "r"(ok ? 16 : 0) : "memory");
+                    for (int i = 0; i < 4; ++i) {
+                        if (a_on[i]) {
+                            const bool ok = a_hl[i] < a_hmax && a_wl[i] < a_wmax;
+                            cp_async16(sbase + a_dst[i], ok ? dy_base + a_off[i] : dy_ptr, ok ? 16 : 0);
+                        }
                     }
-                }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (b_on[i]) {
-                        const int hi = h0 + b_hl[i] + dh, wi = w0 + b_wl[i] + dw;
-                        const bool ok = static_cast<unsigned>(hi) < static_cast<unsigned>(P.Hx) && static_cast<unsigned>(wi) < static_cast<unsigned>(P.Wx);
-                        const __nv_bfloat16* src = ok ? x_base + b_off[i] : P.x_ptr;
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sb + b_dst[i]), "l"(src), "r"(ok ? 16 : 0) : "memory");
+                    for (int i = 0; i < 4; ++i) {
+                        if (b_on[i]) {
+                            const bool ok = live && static_cast<unsigned>(h0 + b_hh[i]) < static_cast<unsigned>(Hx) &&
+                                            static_cast<unsigned>(w0 + b_ww[i]) < static_cast<unsigned>(Wx);
+                            cp_async16(sbase + b_dst[i], ok ? x_base + b_off[i] : x_ptr, ok ? 16 : 0);
+                        }
                     }
+                    if (live) { if (++tw_i == tiles_w) { tw_i = 0; if (++th_i == tiles_h) { th_i = 0; ++img; } } }
                 }
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full0 + 8u * stage) : "memory");
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                ++issued;
+                if (issued > kLag) {
+                    asm volatile("cp.async.wait_group %0;" ::"n"(kLag) : "memory");
+                    __syncwarp();
+                    if ((threadIdx.x & 31) == 0) mbar_arrive(full0 + 8u * sig_stage);
+                    if (++sig_stage == stages) sig_stage = 0;
+                }
                 if (++stage == stages) { stage = 0; phase ^= 1u; }
-                if (++tw_i == P.tiles_w) { tw_i = 0; if (++th_i == P.tiles_h) { th_i = 0; ++img; } }
+            }
+            // drain: signal the last (up to kLag) stages
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            {
+                const int pending = issued < kLag ? issued : kLag;
+                for (int i = 0; i < pending; ++i) {
+                    if ((threadIdx.x & 31) == 0) mbar_arrive(full0 + 8u * sig_stage);
+                    if (++sig_stage == stages) sig_stage = 0;
+                }
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
         }
@@ -221,21 +256,28 @@ __global__ void __launch_bounds__(kWThreads) wgrad_gemm_kernel(const __grid_cons
         tc_fence_after();
         float* out_row = P.dw + (static_cast<long>(co0 + row) * P.taps + tap) * P.Cin;
         for (int c16 = 0; c16 < P.BNt / 16; ++c16) {
-            uint32_t acc[16];
-            tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c16 * 16, acc);
-            tmem_ld_wait();
+            float acc[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+            const long n_mma = static_cast<long>((num_k + P.group - 1) / P.group) * P.group * (P.KP / 16);
+            const int n_used = n_mma < P.n_acc ? static_cast<int>(n_mma) : P.n_acc;
+            for (int sa_i = 0; sa_i < n_used; ++sa_i) {
+                uint32_t r[16];
+                tmem_ld16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + sa_i * P.tmem_cols + c16 * 16, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
+            }
             const int ci = ci0 + c16 * 16;
             if (row_ok && ci < P.Cin) {
 #pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    red_add_v4(out_row + ci + j, __uint_as_float(acc[j]), __uint_as_float(acc[j + 1]),
-                               __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3]));
+                for (int j = 0; j < 16; j += 4) red_add_v4(out_row + ci + j, acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
             }
         }
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, P.tmem_cols);
+    if (warp == 1) tmem_dealloc(tmem_base, P.n_acc * P.tmem_cols);
 }
 
 static int wround_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -331,8 +373,18 @@ extern "C" int hd_conv_wgrad(const hd_conv_args* a, hd_stream stream_) {
     P.x_qstride[0] = x0.c; P.x_qstride[1] = two ? a->x1.c : 0;
     P.dw = a->dw;
 
+    // cp.async gather for operands whose rows are narrower than 128 bytes (single chunk group, plain stride-1 view)
+    P.cp_a = (P.ca < 64 && P.Cout <= P.ca) ? 1 : 0;
+    P.cp_b = (P.cb < 64 && s == 1 && !two && P.Cin <= P.cb) ? 1 : 0;
     P.a_bytes = wround_up(P.KP * P.m_chunks * P.ca * 2, 1024);
-    P.stage_bytes = P.a_bytes + wround_up(P.KP * P.BNt * 2, 1024);
+    P.sub_bytes = P.a_bytes + wround_up(P.KP * P.BNt * 2, 1024);
+    P.group = 1;
+    if (P.cp_a && P.cp_b) {                      // both operands narrow: ~32-48 KB per stage instead of 8-12 KB
+        P.group = (24 * 1024) / P.sub_bytes;
+        if (P.group > 4) P.group = 4;
+        if (P.group < 1) P.group = 1;
+    }
+    P.stage_bytes = P.sub_bytes * P.group;
     int stages = (190 * 1024) / P.stage_bytes;
     if (stages > 6) stages = 6;
     if (stages < 2) stages = 2;
@@ -340,6 +392,7 @@ extern "C" int hd_conv_wgrad(const hd_conv_args* a, hd_stream stream_) {
     int cols = 32;
     while (cols < P.BNt) cols *= 2;
     P.tmem_cols = cols;
+    P.n_acc = 1;   // measured: no gain from rotating sub-accumulators
 
     const int units = P.taps * co_tiles * P.ci_tiles;
     int splits = a->split_k;
@@ -352,9 +405,6 @@ extern "C" int hd_conv_wgrad(const hd_conv_args* a, hd_stream stream_) {
     if (splits < 1) splits = 1;
     P.splits = splits;
 
-    // cp.async gather for operands whose rows are narrower than 128 bytes (single chunk group, plain stride-1 view)
-    P.cp_a = (P.ca < 64 && P.Cout <= P.ca) ? 1 : 0;
-    P.cp_b = (P.cb < 64 && s == 1 && !two && P.Cin <= P.cb) ? 1 : 0;
     P.dy_ptr = static_cast<const __nv_bfloat16*>(dy.ptr);
     P.x_ptr = static_cast<const __nv_bfloat16*>(x0.ptr);
     P.Ho = Ho; P.Wo = Wo; P.Hx = x0.h; P.Wx = x0.w; P.Cx = x0.c;
