@@ -68,8 +68,6 @@ struct ConvGemmParams {
     int store_bf16;
     int stages, a_bytes, stage_bytes;
     int tmem_cols;
-    int n_acc;                  // sub-accumulators per tile: consecutive MMAs rotate over them (dependent tcgen05.mma on ONE
-                                // accumulator are latency-bound, ~140-165 cycles each); the epilogue adds them up
     int m_tiles, n_tiles, nphases;
     // narrow-channel mode (BK < 64): TMA moves 32/64-byte rows one at a time (measured ~5-13 cycles per row), so the A
     // tile is gathered by four cp.async warps instead (16-byte copies, coalesced along W, L1-cached across the 9 taps)
@@ -121,7 +119,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
-            mbar_init(full0 + 8u * s, P.cp_mode ? 1 + kCpWarps : 1);   // TMA (weights) + one arrival per cp.async warp
+            mbar_init(full0 + 8u * s, P.cp_mode ? 1 + kCpThreads : 1);
             mbar_init(empty0 + 8u * s, 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -134,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         tma_prefetch_desc(&P.tmOut[0]);
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, 2 * P.n_acc * P.tmem_cols);
+        tmem_alloc(tmem_slot, 2 * P.tmem_cols);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -187,7 +185,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const int tps = P.tps;
             const uint32_t stage_u = P.stage_bytes >> 4, a_sub_u = P.a_sub >> 4, b_sub_u = P.b_sub >> 4, a_bytes_u = P.a_bytes >> 4;
             const uint32_t base_u = d_lo + (smem_base >> 4);
-            const uint32_t n_acc = P.n_acc, cols = P.tmem_cols;
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -197,25 +194,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 const int num_st = (P.tap_begin[z + 1] - P.tap_begin[z]) * P.kpt / tps;
                 mbar_wait(tempty0 + 8u * acc, acc_phase ^ 1u);          // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * n_acc * cols;
-                uint32_t u = 0;                                          // MMAs issued for this tile
+                const uint32_t d_tmem = tmem_base + acc * P.tmem_cols;
+                uint32_t accum = 0;
                 for (int st = 0; st < num_st; ++st) {
                     mbar_wait(full0 + 8u * stage, phase);
                     if (P.cp_mode) fence_proxy_async_smem();   // cp.async wrote the A tile through the generic proxy
                     tc_fence_after();
                     const uint32_t a_u = base_u + stage * stage_u, b_u = a_u + a_bytes_u;
-                    if (tps == 1 && ksub == 4 && n_acc == 1) {   // the common 64-channel k-block: fully unrolled
-                        umma_bf16_lohi(d_tmem, a_u, d_hi, b_u, d_hi, idesc, u == 0 ? 0u : 1u);
+                    if (tps == 1 && ksub == 4) {               // the common 64-channel k-block: fully unrolled
+                        umma_bf16_lohi(d_tmem, a_u, d_hi, b_u, d_hi, idesc, accum);
                         umma_bf16_lohi(d_tmem, a_u + 2, d_hi, b_u + 2, d_hi, idesc, 1);
                         umma_bf16_lohi(d_tmem, a_u + 4, d_hi, b_u + 4, d_hi, idesc, 1);
                         umma_bf16_lohi(d_tmem, a_u + 6, d_hi, b_u + 6, d_hi, idesc, 1);
-                        u += 4;
+                        accum = 1;
                     } else {
                         for (int j = 0; j < tps; ++j) {
                             for (int k = 0; k < ksub; ++k) {
-                                umma_bf16_lohi(d_tmem + (u % n_acc) * cols, a_u + j * a_sub_u + 2 * k, d_hi, b_u + j * b_sub_u + 2 * k,
-                                               d_hi, idesc, u >= static_cast<uint32_t>(n_acc));
-                                ++u;
+                                umma_bf16_lohi(d_tmem, a_u + j * a_sub_u + 2 * k, d_hi, b_u + j * b_sub_u + 2 * k, d_hi, idesc, accum);
+                                accum = 1;
                             }
                         }
                     }
@@ -230,71 +226,55 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         // ================= cp.async A-tile producers (narrow-channel mode) =================
         if (P.cp_mode) {
             const int pt = threadIdx.x - (64 + kEpiThreads);      // 0..127
-            // parameters copied out of the constant bank once; per (thread, slot) decomposition hoisted out of all loops
-            const int TW = P.TW, TH = P.TH, aH = P.a_H, aW = P.a_W, aC = P.a_C, BK = P.BK, kpt = P.kpt, tps = P.tps;
-            const uint32_t stage_bytes = P.stage_bytes, a_sub = P.a_sub;
-            const __nv_bfloat16* a_ptr = P.a_ptr;
-            const int row_b = BK * 2;                              // 32 or 64 bytes per pixel row of the tile
+            const int row_b = P.BK * 2;                            // 32 or 64 bytes per pixel row of the tile
             const int cpr = row_b / 16;                            // 16-byte chunks per row
             const uint32_t smask = cpr - 1;
             const int per_thread = 128 * cpr / kCpThreads;         // 2 or 4
-            int s_hl[4], s_wl[4], s_off[4];
+            // everything that depends only on (thread, slot) is hoisted out of the tile / tap loops
+            int s_hl[4], s_wl[4];
             uint32_t s_dst[4];
+            long s_off[4];
             bool s_in[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int q = pt + kCpThreads * i;
                 const int r = q / cpr, ch = q - r * cpr;
-                s_hl[i] = r / TW;
-                s_wl[i] = r - s_hl[i] * TW;
-                s_in[i] = i < per_thread && r < TW * TH;
+                s_hl[i] = r / P.TW;
+                s_wl[i] = r - s_hl[i] * P.TW;
+                s_in[i] = i < per_thread && r < P.TW * P.TH;
                 s_dst[i] = swz(static_cast<uint32_t>(r * row_b + ch * 16), smask);
-                s_off[i] = (s_hl[i] * aW + s_wl[i]) * aC + ch * 8;
+                s_off[i] = (static_cast<long>(s_hl[i]) * P.a_W + s_wl[i]) * P.a_C + ch * 8;
             }
-            // each producer warp commits one cp.async group per stage and signals a stage (ONE mbarrier arrival per warp)
-            // once its group has landed, kLag stages behind the issue point
-            constexpr int kLag = 2;                              // requires >= 3 pipeline stages
-            int stage = 0, sig_stage = 0, issued = 0;
+            int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 int z, n0, img, h0, w0;
                 decode_tile(P, tile, z, n0, img, h0, w0);
                 int tap = P.tap_begin[z], kb = 0;
-                const int num_k = (P.tap_begin[z + 1] - tap) * kpt;
-                const __nv_bfloat16* tile_base = a_ptr + static_cast<long>((img * aH + h0) * aW + w0) * aC;
-                for (int ks = 0; ks < num_k; ks += tps) {
+                const int num_k = (P.tap_begin[z + 1] - tap) * P.kpt;
+                const __nv_bfloat16* tile_base = P.a_ptr + ((static_cast<long>(img) * P.a_H + h0) * P.a_W + w0) * P.a_C;
+                for (int ks = 0; ks < num_k; ks += P.tps) {
                     mbar_wait(empty0 + 8u * stage, phase ^ 1u);
-                    const uint32_t sa = smem_base + stage * stage_bytes;
-                    for (int j = 0; j < tps; ++j) {
+                    const uint32_t sa = smem_base + stage * P.stage_bytes;
+                    for (int j = 0; j < P.tps; ++j) {
                         const int dh = P.tap_dh[tap], dw = P.tap_dw[tap];
-                        const int tap_off = (dh * aW + dw) * aC + kb * BK;
-                        const int hb = h0 + dh, wb = w0 + dw;
+                        const long tap_off = (static_cast<long>(dh) * P.a_W + dw) * P.a_C + kb * P.BK;
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             if (i < per_thread) {
-                                const bool ok = s_in[i] && static_cast<unsigned>(hb + s_hl[i]) < static_cast<unsigned>(aH) &&
-                                                static_cast<unsigned>(wb + s_wl[i]) < static_cast<unsigned>(aW);
+                                const int hi = h0 + s_hl[i] + dh, wi = w0 + s_wl[i] + dw;
+                                const bool ok = s_in[i] && static_cast<unsigned>(hi) < static_cast<unsigned>(P.a_H) &&
+                                                static_cast<unsigned>(wi) < static_cast<unsigned>(P.a_W);
+                                const __nv_bfloat16* src = ok ? tile_base + s_off[i] + tap_off : P.a_ptr;
                                 // src-size 0 -> 16 bytes of zeros (padding / out-of-tile rows)
-                                cp_async16(sa + j * a_sub + s_dst[i], ok ? tile_base + (s_off[i] + tap_off) : a_ptr, ok ? 16 : 0);
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sa + j * P.a_sub + s_dst[i]), "l"(src), "r"(ok ? 16 : 0) : "memory");
                             }
                         }
-                        if (++kb == kpt) { kb = 0; ++tap; }
+                        if (++kb == P.kpt) { kb = 0; ++tap; }
                     }
-                    asm volatile("cp.async.commit_group;" ::: "memory");
-                    if (++issued > kLag) {
-                        asm volatile("cp.async.wait_group %0;" ::"n"(kLag) : "memory");
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(full0 + 8u * sig_stage);
-                        if (++sig_stage == stages) sig_stage = 0;
-                    }
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full0 + 8u * stage) : "memory");
                     if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
-            }
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncwarp();
-            for (int i = 0, pending = issued < kLag ? issued : kLag; i < pending; ++i) {
-                if (lane == 0) mbar_arrive(full0 + 8u * sig_stage);
-                if (++sig_stage == stages) sig_stage = 0;
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
         }
@@ -359,9 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
             mbar_wait(tfull0 + 8u * acc, acc_phase);
             tc_fence_after();
-            const uint32_t t_acc = tmem_base + acc * P.n_acc * P.tmem_cols + (static_cast<uint32_t>(quad * 32) << 16);
-            const int n_mma = num_k * (P.BK / 16);
-            const int n_used = n_mma < P.n_acc ? n_mma : P.n_acc;          // sub-accumulators this tile actually wrote
+            const uint32_t t_acc = tmem_base + acc * P.tmem_cols + (static_cast<uint32_t>(quad * 32) << 16);
             for (int c16 = c_begin; c16 < c_end; ++c16) {
                 const int ch0 = n0 + c16 * 16;
                 const bool ch_ok = ch0 < P.Cout_total;
@@ -372,21 +350,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     if (add_row) { const uint4* ap = reinterpret_cast<const uint4*>(add_row + (c16 + 1) * 16); na0 = ap[0]; na1 = ap[1]; }
                     if (mask_row) { const uint4* mp = reinterpret_cast<const uint4*>(mask_row + (c16 + 1) * 16); nm0 = __ldg(mp); nm1 = __ldg(mp + 1); }
                 }
+                uint32_t acc_r[16];
+                if (num_k > 0) {
+                    tmem_ld16(t_acc + c16 * 16, acc_r);
+                    tmem_ld_wait();
+                } else {                                   // phase without filter taps: epilogue-only (add / mask)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc_r[j] = 0u;
+                }
                 float v[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = 0.f;   // n_used == 0: phase without filter taps (epilogue-only add / mask)
-                for (int sa_i = 0; sa_i < n_used; sa_i += 2) {
-                    uint32_t r0[16], r1[16];
-                    tmem_ld16(t_acc + sa_i * P.tmem_cols + c16 * 16, r0);
-                    if (sa_i + 1 < n_used) tmem_ld16(t_acc + (sa_i + 1) * P.tmem_cols + c16 * 16, r1);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r0[j]);
-                    if (sa_i + 1 < n_used) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] += __uint_as_float(r1[j]);
-                    }
-                }
+                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc_r[j]);
                 if (P.bias != nullptr) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
@@ -515,7 +489,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         if (et == 0) tma_store_wait_all();
     }
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 2 * P.n_acc * P.tmem_cols);
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * P.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -585,12 +559,10 @@ static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStrea
     int stages = (232448 - fixed) / P.stage_bytes;              // 227 KB = the sm_100 per-block maximum
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
-    if (P.cp_mode && stages < 3) { set_last_error(__FILE__, __LINE__, "cp.async mode needs >= 3 stages"); return HD_ERR_UNSUPPORTED; }
     P.stages = stages;
     int cols = 32;
     while (cols < P.BN) cols *= 2;
     P.tmem_cols = cols;
-    P.n_acc = 1;   // measured: rotating MMAs over 2-4 sub-accumulators does not help (same-accumulator MMAs pipeline fine)
     P.m_tiles = P.tiles_w * P.tiles_h * n_img;
     P.n_tiles = (P.Cout_total + P.BN - 1) / P.BN;
     if (P.stats != nullptr && P.stats_replicas < P.m_tiles) {
