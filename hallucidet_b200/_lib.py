@@ -56,6 +56,8 @@ PROTOTYPES = {
     "hd_upsample2x_bwd": [P(HdAct), P(HdAct), c_void_p],
     "hd_add_nearest_fwd": [P(HdAct), P(HdAct), c_void_p],
     "hd_add_nearest_bwd": [P(HdAct), P(HdAct), c_int, c_void_p],
+    "hd_pad_hw": [P(HdAct), P(HdAct), c_void_p],
+    "hd_crop_add_mask": [P(HdAct), c_void_p, c_void_p, P(HdAct), c_void_p],
     "hd_nchw_f32_to_nhwc_bf16": [c_void_p, P(HdAct), c_int, c_int, c_void_p],
     "hd_nhwc_bf16_to_nchw_f32": [P(HdAct), c_void_p, c_int, c_void_p],
     "hd_sigmoid_bwd_pack": [c_void_p, c_void_p, P(HdAct), c_int, c_void_p, c_void_p],

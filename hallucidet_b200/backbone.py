@@ -26,7 +26,10 @@ class _FConv:
         self.cout, self.cin = conv.out_channels, conv.in_channels
         self.k, self.stride = conv.kernel_size[0], conv.stride[0]
         self.h_in, self.w_in = in_hw
-        self.h, self.w = in_hw[0] // self.stride, in_hw[1] // self.stride
+        # stride-2 convs on odd feature maps (S=300: 75, 19) run on an even zero-padded copy: out = ceil(in / 2) as torch
+        self.pad_in = self.stride == 2 and (in_hw[0] % 2 == 1 or in_hw[1] % 2 == 1) and not stem
+        self.hp, self.wp = in_hw[0] + in_hw[0] % 2, in_hw[1] + in_hw[1] % 2
+        self.h, self.w = (in_hw[0] + self.stride - 1) // self.stride, (in_hw[1] + self.stride - 1) // self.stride
         dev = eng.device
         w = conv.weight.detach().float().contiguous()
         if bn is not None:
@@ -41,6 +44,9 @@ class _FConv:
         else:
             self.packed = ops.PackedConv(self.cout, self.cin, self.k, dev, need_dgrad=True).pack(w, scale)
         self.y = eng.new_act(self.h, self.w, self.cout)
+        if self.pad_in:
+            self.x_pad = eng.new_act(self.hp, self.wp, self.cin)
+            self.dx_pad = None
 
 
 class FrozenBackbone(nn.Module):
@@ -122,9 +128,9 @@ class _BackboneFunction(torch.autograd.Function):
 
 class _BackboneEngine:
     def __init__(self, module, B, H, W, device):
-        if H % 64 != 0 or W % 64 != 0:
-            raise NotImplementedError(f"FrozenBackbone input {H}x{W}: sizes must be multiples of 64 in this build "
-                                      "(S=640 configuration); odd feature maps (S=300) are not implemented yet")
+        if H % 4 != 0 or W % 4 != 0 or H < 64 or W < 64:
+            raise NotImplementedError(f"FrozenBackbone input {H}x{W}: height and width must be multiples of 4 and >= 64 "
+                                      "(stem conv and max-pool run on even maps); HalluciDet uses 300 and 640")
         self.m, self.B, self.H, self.W, self.device = module, B, H, W, device
         self.variant = module.variant
         body, fpn = module.body, module.fpn
@@ -208,6 +214,9 @@ class _BackboneEngine:
 
     # ---- forward -------------------------------------------------------------------------------------
     def _conv(self, c, x, add=None, out_f32=None, store_bf16=True):
+        if c.pad_in:
+            ops.pad_hw(x, c.x_pad)
+            x = c.x_pad
         ops.conv_fwd(ops.conv_args(x, c.y, c.packed.w_fwd, k=c.k, stride=c.stride, bias=c.bias, add=add, relu=c.relu,
                                    out_f32=out_f32, out_f32_channels=c.cout if out_f32 is not None else 0, store_bf16=store_bf16))
 
@@ -260,6 +269,14 @@ class _BackboneEngine:
         return self.dx.clone()
 
     def _dgrad(self, c, dy, dx, add=None, mask=None):
+        if c.pad_in:
+            if c.dx_pad is None:
+                c.dx_pad = torch.empty_like(c.x_pad)
+            if c.k == 1:
+                c.dx_pad.zero_()                         # a 1x1 stride-2 dgrad only writes the (even, even) phase
+            ops.conv_dgrad(ops.conv_args(dy, c.dx_pad, c.packed.w_dgrad, k=c.k, stride=c.stride))
+            ops.crop_add_mask(c.dx_pad, dx, add=add, mask=mask)
+            return
         ops.conv_dgrad(ops.conv_args(dy, dx, c.packed.w_dgrad, k=c.k, stride=c.stride, add=add, mask=mask))
 
     def _backward_impl(self):

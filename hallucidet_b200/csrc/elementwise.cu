@@ -549,6 +549,61 @@ __global__ void add_nearest_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __n
 }
 
 // -------------------------------------------------------------------------------------------------
+// odd feature maps (detector size 300: 75 / 19 pixels): stride-2 convolutions run on an even, zero-padded copy
+// -------------------------------------------------------------------------------------------------
+__global__ void pad_hw_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int h, int w, int hp,
+                              int wp, int C) {
+    const int G = C / 8;
+    const long total = static_cast<long>(n) * hp * wp * G;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % G);
+        const long pix = i / G;
+        const int ow = static_cast<int>(pix % wp), oh = static_cast<int>((pix / wp) % hp), b = static_cast<int>(pix / (static_cast<long>(wp) * hp));
+        bf8 v;
+        if (oh < h && ow < w) v.load(x + ((static_cast<long>(b) * h + oh) * w + ow) * C + g * 8);
+        else v.u = make_uint4(0, 0, 0, 0);
+        v.store(y + pix * C + g * 8);
+    }
+}
+
+// dx = (crop(dxp) + add) * (mask > 0)
+__global__ void crop_add_mask_kernel(const __nv_bfloat16* __restrict__ dxp, const __nv_bfloat16* __restrict__ add,
+                                     const __nv_bfloat16* __restrict__ mask, __nv_bfloat16* __restrict__ dx, int n, int h, int w,
+                                     int hp, int wp, int C) {
+    const int G = C / 8;
+    const long total = static_cast<long>(n) * h * w * G;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % G);
+        const long pix = i / G;
+        const int ow = static_cast<int>(pix % w), oh = static_cast<int>((pix / w) % h), b = static_cast<int>(pix / (static_cast<long>(w) * h));
+        bf8 v;
+        v.load(dxp + ((static_cast<long>(b) * hp + oh) * wp + ow) * C + g * 8);
+        float f[8];
+        v.unpack(f);
+        if (add) {
+            bf8 a;
+            a.load(add + pix * C + g * 8);
+            float af[8];
+            a.unpack(af);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += af[j];
+        }
+        if (mask) {
+            bf8 m;
+            m.load(mask + pix * C + g * 8);
+            float mf[8];
+            m.unpack(mf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (!(mf[j] > 0.f)) f[j] = 0.f;
+        }
+        v.pack(f);
+        v.store(dx + pix * C + g * 8);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
 // layout converters
 // -------------------------------------------------------------------------------------------------
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int h, int w, int Cs,
@@ -883,6 +938,23 @@ extern "C" int hd_add_nearest_bwd(const hd_act* dy, const hd_act* dx, int accumu
                              static_cast<cudaStream_t>(st)>>>(static_cast<const __nv_bfloat16*>(dy->ptr),
                                                               static_cast<__nv_bfloat16*>(dx->ptr), dx->n, dx->h, dx->w,
                                                               dy->h, dy->w, dx->c, sh, sw, accumulate);
+    HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_pad_hw(const hd_act* x, const hd_act* y, hd_stream st) {
+    HD_CHECK_ARG(x && y && x->ptr && y->ptr && x->c == y->c && x->c % 8 == 0 && x->n == y->n && y->h >= x->h && y->w >= x->w);
+    pad_hw_kernel<<<ew_blocks(static_cast<long>(y->n) * y->h * y->w * (y->c / 8)), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
+        static_cast<const __nv_bfloat16*>(x->ptr), static_cast<__nv_bfloat16*>(y->ptr), x->n, x->h, x->w, y->h, y->w, x->c);
+    HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_crop_add_mask(const hd_act* dxp, const void* add, const void* mask, const hd_act* dx, hd_stream st) {
+    HD_CHECK_ARG(dxp && dx && dxp->ptr && dx->ptr && dx->c == dxp->c && dx->c % 8 == 0 && dx->n == dxp->n && dxp->h >= dx->h && dxp->w >= dx->w);
+    crop_add_mask_kernel<<<ew_blocks(static_cast<long>(dx->n) * dx->h * dx->w * (dx->c / 8)), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
+        static_cast<const __nv_bfloat16*>(dxp->ptr), static_cast<const __nv_bfloat16*>(add), static_cast<const __nv_bfloat16*>(mask),
+        static_cast<__nv_bfloat16*>(dx->ptr), dx->n, dx->h, dx->w, dxp->h, dxp->w, dx->c);
     HD_LAUNCH_OK();
     return HD_OK;
 }

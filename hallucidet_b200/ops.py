@@ -241,6 +241,18 @@ def add_nearest_bwd(dy, dx, accumulate=False):
         check(_lib.load().hd_add_nearest_bwd(ctypes.byref(ay), ctypes.byref(ax), int(accumulate), _stream()), "hd_add_nearest_bwd")
 
 
+def pad_hw(x, y):
+    ax, ay = act(x), act(y)
+    with _Timed("pad_hw"):
+        check(_lib.load().hd_pad_hw(ctypes.byref(ax), ctypes.byref(ay), _stream()), "hd_pad_hw")
+
+
+def crop_add_mask(dxp, dx, add=None, mask=None):
+    ap, ax = act(dxp), act(dx)
+    with _Timed("crop_add_mask"):
+        check(_lib.load().hd_crop_add_mask(ctypes.byref(ap), _ptr(add), _ptr(mask), ctypes.byref(ax), _stream()), "hd_crop_add_mask")
+
+
 def nchw_f32_to_nhwc_bf16(x, y, accumulate=False):
     assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[0] == y.shape[0] and x.shape[2:] == y.shape[1:3]
     ay = act(y)

@@ -129,6 +129,10 @@ int hd_upsample2x_bwd(const hd_act* dy, const hd_act* dx, hd_stream stream);
 /* FPN top-down (TV: ops/feature_pyramid_network.py:193-196): y += nearest_resize(x to y's size); backward dx = gather-sum(dy). */
 int hd_add_nearest_fwd(const hd_act* x, const hd_act* y, hd_stream stream);
 int hd_add_nearest_bwd(const hd_act* dy, const hd_act* dx, int accumulate, hd_stream stream);
+/* Odd feature maps (detector size 300 -> 75 / 19 pixels): stride-2 convolutions run on an even zero-padded copy.
+ * y = x zero-padded at the bottom / right to y's size;  dx = (crop(dxp) + add) masked by (mask > 0) (add / mask may be NULL). */
+int hd_pad_hw(const hd_act* x, const hd_act* y, hd_stream stream);
+int hd_crop_add_mask(const hd_act* dxp, const void* add, const void* mask, const hd_act* dx, hd_stream stream);
 /* Layout / dtype converters at the module edges. */
 int hd_nchw_f32_to_nhwc_bf16(const float* x, const hd_act* y, int channels, int accumulate, hd_stream stream);
 int hd_nhwc_bf16_to_nchw_f32(const hd_act* x, float* y, int channels, hd_stream stream);

@@ -151,8 +151,8 @@ def test_unet_train_cuda_graph_matches_eager():
     assert torch.allclose(m.state_dict()["encoder.bn1.running_var"], m2.state_dict()["encoder.bn1.running_var"], rtol=1e-3)
 
 
-@pytest.mark.parametrize("name", ["fasterrcnn", "retinanet"])
-def test_frozen_backbone_forward_and_dgrad(name):
+@pytest.mark.parametrize("name,size", [("fasterrcnn", 128), ("retinanet", 128), ("fasterrcnn", 300), ("retinanet", 300)])
+def test_frozen_backbone_forward_and_dgrad(name, size):
     from oracle import detector as odet, backbone as obb, unet as ou
     from hallucidet_b200.backbone import FrozenBackbone
     det = odet.build_detector(name, seed=123)
@@ -162,7 +162,7 @@ def test_frozen_backbone_forward_and_dgrad(name):
     fb = FrozenBackbone.from_torchvision(copy.deepcopy(det.backbone)).cuda()
     assert fb.out_channels == 256 and not any(p.requires_grad for p in fb.parameters())
     assert list(fb.state_dict().keys()) == list(det.backbone.state_dict().keys())
-    x = torch.rand(2, 3, 128, 128, generator=torch.Generator().manual_seed(11)).cuda().requires_grad_(True)
+    x = torch.rand(2, 3, size, size, generator=torch.Generator().manual_seed(11)).cuda().requires_grad_(True)
     feats = fb(x)
     xe = x.detach().clone().requires_grad_(True)
     feats_e = obb.backbone_forward(state, xe, variant=name, q=ou.round_bf16)
@@ -191,10 +191,10 @@ def test_frozen_backbone_forward_and_dgrad(name):
     print(f"[backbone {name}] d(loss)/d(image) cosine: vs bf16-storage oracle {c:.4f}, vs fp32 {c32:.4f}, noise floor {cfloor:.4f}")
     assert c >= 0.9 and c32 >= cfloor - 0.05
     # a second, gradient-free forward (the reference's extra RGB / IR passes) must not disturb a pending backward
-    x2 = torch.rand(2, 3, 128, 128).cuda().requires_grad_(True)
+    x2 = torch.rand(2, 3, size, size).cuda().requires_grad_(True)
     f2 = fb(x2)
     with torch.no_grad():
-        fb(torch.rand(2, 3, 128, 128).cuda())
+        fb(torch.rand(2, 3, size, size).cuda())
     sum(v.sum() for v in f2.values()).backward()
     assert x2.grad is not None and torch.isfinite(x2.grad).all()
 
@@ -279,7 +279,8 @@ def test_trainer_steps_and_reference_extra_passes():
     assert max(float(p.grad.abs().max()) for p in tr.encoder_decoder.parameters()) <= 0.5 + 1e-6
 
 
-def test_frozen_backbone_layers():
+@pytest.mark.parametrize("size", [128, 300])
+def test_frozen_backbone_layers(size):
     """Teacher-forced per-layer parity inside the frozen backbone: every conv forward and every dgrad re-derived
     in fp32 PyTorch from the tensors the engine stored (folded bf16 weights, bf16 activations / gradients)."""
     import torch.nn.functional as F
@@ -300,7 +301,7 @@ def test_frozen_backbone_layers():
     det = odet.build_detector("fasterrcnn", seed=123)
     odet.randomize_bn_stats(det, seed=7)
     fb = FrozenBackbone.from_torchvision(det.backbone).cuda()
-    x = torch.rand(2, 3, 128, 128, generator=torch.Generator().manual_seed(11)).cuda().requires_grad_(True)
+    x = torch.rand(2, 3, size, size, generator=torch.Generator().manual_seed(11)).cuda().requires_grad_(True)
     feats = fb(x)
     gen = torch.Generator().manual_seed(2)
     ws = {k: torch.randn(v.shape, generator=gen).cuda() for k, v in feats.items()}
