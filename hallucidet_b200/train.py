@@ -125,6 +125,22 @@ class HalluciDetTrainer(nn.Module):
         return {"total": total, "det_total": loss_det_total, "pixel_rgb": loss_pixel_rgb, "pixel_ir": loss_pixel_ir,
                 "losses_det": losses_det, "hal": hal, "detections": detections}
 
+    @torch.no_grad()
+    def test_step(self, imgs_rgb, targets_rgb, imgs_ir, targets_ir, det_seed=None):
+        """eval_hallucidet.py:135-161 -- eval-mode hallucination (folded BN) + detector losses / detections on it
+        (the reference also evaluates the RGB and IR images; enable with ``reference_extra_passes``)."""
+        self.encoder_decoder.eval()
+        ir3 = expand_one_channel_to_output_channels(imgs_ir, 3)
+        hal = self.encoder_decoder(ir3)
+        if det_seed is not None:
+            torch.manual_seed(det_seed)
+        losses_hal, det_hal = Detector.calculate_loss(self.detector, hal, targets_ir, train_det=False, model_name=self.detector_name)
+        out = {"hal": hal, "losses_hal": losses_hal, "detections_hal": det_hal}
+        if self.reference_extra_passes:
+            _, out["detections_rgb"] = Detector.calculate_loss(self.detector, imgs_rgb, targets_rgb, train_det=False, model_name=self.detector_name)
+            _, out["detections_ir"] = Detector.calculate_loss(self.detector, ir3, targets_ir, train_det=False, model_name=self.detector_name)
+        return out
+
     def allreduce_gradients(self):
         """Mean of the per-replica gradients: one all-reduce over the U-Net's flat gradient block."""
         if self.world == 1:

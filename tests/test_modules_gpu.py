@@ -366,3 +366,34 @@ def test_concurrent_proposal_filter_equals_torchvision():
             b = D.filter_proposals_concurrent(det.rpn, props, o2, il.image_sizes, napl)
             torch.cuda.synchronize()
             assert all(torch.equal(p, q) for p, q in zip(a[0], b[0])) and all(torch.equal(p, q) for p, q in zip(a[1], b[1]))
+
+
+def test_inference_pipeline_llvip_setting():
+    """BASELINE config 1 / 5 shape family: eval-mode U-Net (folded BN) -> detector at the reference's default size 300
+    (src/config/config.py:88) -> losses + detections, against the fp32 oracle with the same running statistics."""
+    from oracle import unet as ou, detector as odet, step as ostep, losses as olosses
+    from hallucidet_b200.train import HalluciDetTrainer
+    ir, rgb, targets = ostep.synthetic_batch(2, 256, 320, seed=5, device="cuda")
+    det_cpu = odet.build_detector("fasterrcnn", seed=123)
+    odet.randomize_bn_stats(det_cpu, seed=7)
+    tr = HalluciDetTrainer(detector_name="fasterrcnn", size=300, seed=123, detector_state=det_cpu.state_dict())
+    st = oracle_state(tr.encoder_decoder)
+    for _ in range(20):                                  # realistic running statistics
+        with torch.no_grad():
+            ou.unet_forward(st, ou.expand_ir(ir, 3) + 0.05 * torch.randn(2, 3, 256, 320, device="cuda"), training=True, update_stats=True)
+    tr.encoder_decoder.load_state_dict(st)
+    out = tr.test_step(rgb, targets, ir, targets, det_seed=7)
+    det = det_cpu.cuda()
+    with torch.no_grad():
+        hal32 = ou.unet_forward(st, ou.expand_ir(ir, 3), training=False)
+        hal_e = ou.unet_forward(st, ou.expand_ir(ir, 3), training=False, q=ou.round_bf16)
+        torch.manual_seed(7)
+        losses32, dets32 = odet.calculate_loss(det, hal32, targets, 300, "fasterrcnn")
+    e32, floor = (out["hal"] - hal32).abs().mean().item(), (hal_e - hal32).abs().mean().item()
+    tot = sum(float(v) for v in out["losses_hal"].values())
+    tot32 = sum(float(v) for v in losses32.values())
+    print(f"\n[infer S=300] hal mean err vs fp32 {e32:.5f} (bf16-storage noise floor {floor:.5f}); loss {tot:.5f} vs oracle {tot32:.5f}; "
+          f"detections {[len(d['boxes']) for d in out['detections_hal']]} vs {[len(d['boxes']) for d in dets32]}")
+    assert e32 <= 1.25 * floor + 2e-3
+    assert abs(tot - tot32) / abs(tot32) <= 5e-2      # RoI terms are piece-wise (discrete proposals): looser than the train-step gate
+    assert out["hal"].shape == (2, 3, 256, 320) and len(out["detections_hal"]) == 2
