@@ -91,7 +91,8 @@ class HalluciDetTrainer(nn.Module):
         install_b200_backbone(self.detector)
         self.encoder_decoder.use_cuda_graph = use_cuda_graph
         self.detector.backbone.use_cuda_graph = use_cuda_graph
-        self.optimizer = torch.optim.Adam(self.encoder_decoder.parameters(), lr=lr)   # train_hallucidet.py:429-435
+        # train_hallucidet.py:429-435 (Adam, lr 1e-4, default betas/eps); fused=True = one multi-tensor kernel, same maths
+        self.optimizer = torch.optim.Adam(self.encoder_decoder.parameters(), lr=lr, fused=True)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
     def forward_step(self, imgs_rgb, targets_rgb, imgs_ir, targets_ir, det_seed=None):
@@ -145,10 +146,25 @@ class HalluciDetTrainer(nn.Module):
         """Mean of the per-replica gradients: one all-reduce over the U-Net's flat gradient block."""
         if self.world == 1:
             return
+        flat = self._flat_grad()
+        allreduce_mean_([flat] if flat is not None else [p.grad for p in self.encoder_decoder.parameters() if p.grad is not None],
+                        self.world)
+
+    def _flat_grad(self):
+        """The U-Net engine's flat fp32 gradient block, if the parameters' .grad tensors are views into it."""
         params = [p for p in self.encoder_decoder.parameters() if p.grad is not None]
-        eng = next(iter(self.encoder_decoder._engines.values()), None)
-        flat = eng.flat_grad if eng is not None and params and params[0].grad.data_ptr() == eng.flat_grad.data_ptr() else None
-        allreduce_mean_([flat] if flat is not None else [p.grad for p in params], self.world)
+        eng = next((e for e in self.encoder_decoder._engines.values() if e.training), None)
+        if eng is not None and params and params[0].grad.data_ptr() == eng.flat_grad.data_ptr():
+            return eng.flat_grad
+        return None
+
+    def clip_gradients(self):
+        """clip_grad_value_(0.5) (train_hallucidet.py:498-499): one clamp over the flat block when possible."""
+        flat = self._flat_grad()
+        if flat is not None:
+            flat.clamp_(-self.clip_value, self.clip_value)
+        else:
+            torch.nn.utils.clip_grad_value_(self.encoder_decoder.parameters(), self.clip_value)
 
     def training_step(self, imgs_rgb, targets_rgb, imgs_ir, targets_ir, det_seed=None):
         self.encoder_decoder.train()
@@ -156,6 +172,6 @@ class HalluciDetTrainer(nn.Module):
         out = self.forward_step(imgs_rgb, targets_rgb, imgs_ir, targets_ir, det_seed=det_seed)
         out["total"].backward()
         self.allreduce_gradients()
-        torch.nn.utils.clip_grad_value_(self.encoder_decoder.parameters(), self.clip_value)     # train_hallucidet.py:498-499
+        self.clip_gradients()
         self.optimizer.step()
         return out

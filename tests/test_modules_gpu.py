@@ -397,3 +397,23 @@ def test_inference_pipeline_llvip_setting():
     assert e32 <= 1.25 * floor + 2e-3
     assert abs(tot - tot32) / abs(tot32) <= 5e-2      # RoI terms are piece-wise (discrete proposals): looser than the train-step gate
     assert out["hal"].shape == (2, 3, 256, 320) and len(out["detections_hal"]) == 2
+
+
+def test_concurrent_postprocess_equals_torchvision():
+    from oracle import detector as odet
+    from hallucidet_b200 import detection as D
+    det = odet.build_detector("fasterrcnn", seed=1).cuda()
+    g = torch.Generator().manual_seed(0)
+    n_img, per = 4, 300
+    logits = torch.randn(n_img * per, 2, generator=g).cuda() * 3
+    reg = torch.randn(n_img * per, 8, generator=g).cuda() * 0.5
+    xy = torch.rand(n_img * per, 2, generator=g) * 200
+    wh = torch.rand(n_img * per, 2, generator=g) * 60 + 4
+    props = torch.cat([xy, xy + wh], 1).cuda().split(per, 0)
+    shapes = [(256, 256)] * n_img
+    with torch.no_grad():
+        a = det.roi_heads.postprocess_detections(logits, reg, list(props), shapes)
+        b = D.postprocess_detections_concurrent(det.roi_heads, logits, reg, list(props), shapes)
+    torch.cuda.synchronize()
+    for x, y in zip(a, b):
+        assert all(torch.equal(p, q) for p, q in zip(x, y))
