@@ -27,21 +27,6 @@ constexpr int kCpWarps = 4;                  // cp.async A-operand producers (na
 constexpr int kCpThreads = kCpWarps * 32;
 constexpr int kThreads = 64 + kEpiThreads + kCpThreads;
 
-// division by a runtime constant as multiply-high + shift (x < 2^31): q = (umulhi(x, mul) + x) >> shr
-struct FastDiv {
-    uint32_t mul, shr, d;
-};
-static FastDiv make_fastdiv(uint32_t d) {
-    FastDiv f;
-    f.d = d;
-    uint32_t s = 0;
-    while ((1u << s) < d) ++s;
-    f.shr = s;
-    f.mul = static_cast<uint32_t>(((1ull << 32) * ((1ull << s) - d)) / d + 1);
-    return f;
-}
-__device__ __forceinline__ uint32_t fdiv(uint32_t x, const FastDiv& f) { return (__umulhi(x, f.mul) + x) >> f.shr; }
-
 struct ConvGemmParams {
     CUtensorMap tmA[2];
     CUtensorMap tmB;
@@ -635,6 +620,7 @@ extern "C" int hd_conv_fwd(const hd_conv_args* a, hd_stream stream_) {
     if (s == 2) HD_CHECK_ARG(H % 2 == 0 && W % 2 == 0);
     const int Ho = H / s, Wo = W / s;
     HD_CHECK_ARG(a->y0.n == N && a->y0.h == Ho && a->y0.w == Wo);
+    if (narrow_conv_eligible(a, false)) return narrow_conv_launch(a, false, stream);
     const int cin = a->x0.c + (two ? a->x1.c : 0), cout = a->y0.c;
 
     ConvGemmParams P;
@@ -689,6 +675,8 @@ extern "C" int hd_conv_fwd(const hd_conv_args* a, hd_stream stream_) {
 extern "C" int hd_conv_fwd_tiles(const hd_conv_args* a) {
     // number of 128-pixel output tiles hd_conv_fwd uses for this problem == rows of the per-tile statistics buffer
     if (a == nullptr || a->stride < 1 || a->x0.h <= 0 || a->x0.w <= 0) return HD_ERR_BAD_ARG;
+    // with the output channel count filled in (y0.c), 16/32-channel 3x3 layers report the rows of the narrow-layer kernel
+    if (narrow_conv_eligible(a, false)) return narrow_conv_stats_rows(a);
     const int Ho = a->x0.h / a->stride, Wo = a->x0.w / a->stride;
     int TW, TH;
     pick_tile(Ho, Wo, &TW, &TH);
@@ -707,6 +695,7 @@ extern "C" int hd_conv_dgrad(const hd_conv_args* a, hd_stream stream_) {
     const int H = a->y0.h, W = a->y0.w, N = a->y0.n;       // input-gradient geometry
     if (s == 2) HD_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && !two);
     HD_CHECK_ARG(a->x0.n == N && a->x0.h == H / s && a->x0.w == W / s);
+    if (narrow_conv_eligible(a, true)) return narrow_conv_launch(a, true, stream);
     const int cout = a->x0.c;                              // GEMM K per tap
     const int cin = a->y0.c + (two ? a->y1.c : 0);         // GEMM N
 

@@ -39,10 +39,34 @@ void set_last_error(const char* file, int line, const char* msg);
 int make_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
+// division by a runtime constant as multiply-high + shift (x < 2^31): q = (umulhi(x, mul) + x) >> shr
+struct FastDiv {
+    uint32_t mul, shr, d;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.d = d;
+    uint32_t s = 0;
+    while ((1u << s) < d) ++s;
+    f.shr = s;
+    f.mul = static_cast<uint32_t>(((1ull << 32) * ((1ull << s) - d)) / d + 1);
+    return f;
+}
+
+// narrow_conv.cu: HBM-bound 3x3 stride-1 layers with 16 / 32 channels (halo patch + mma.sync); the public entry points
+// in conv_gemm.cu / wgrad_gemm.cu route eligible problems there.
+bool narrow_conv_eligible(const hd_conv_args* a, bool dgrad);
+int narrow_conv_stats_rows(const hd_conv_args* a);
+int narrow_conv_launch(const hd_conv_args* a, bool dgrad, cudaStream_t stream);
+bool narrow_wgrad_eligible(const hd_conv_args* a);
+int narrow_wgrad_launch(const hd_conv_args* a, cudaStream_t stream);
+
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------------------
 // device-side PTX wrappers
 // ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fdiv(uint32_t x, const FastDiv& f) { return (__umulhi(x, f.mul) + x) >> f.shr; }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -320,6 +320,7 @@ extern "C" int hd_conv_wgrad(const hd_conv_args* a, hd_stream stream_) {
     if (s == 2) HD_CHECK_ARG(x0.h % 2 == 0 && x0.w % 2 == 0);
     const int Ho = x0.h / s, Wo = x0.w / s, N = x0.n;
     HD_CHECK_ARG(dy.n == N && dy.h == Ho && dy.w == Wo);
+    if (narrow_wgrad_eligible(a)) return narrow_wgrad_launch(a, stream);
 
     WgradParams P;
     memset(&P, 0, sizeof(P));

@@ -110,12 +110,15 @@ def conv_fwd(args):
         check(_lib.load().hd_conv_fwd(ctypes.byref(args), _stream()), "hd_conv_fwd")
 
 
-def conv_fwd_tiles(x0, k=3, stride=1):
-    """Rows the per-tile BN statistics buffer needs for a forward conv over x0 (host-only query)."""
+def conv_fwd_tiles(x0, k=3, stride=1, cout=None):
+    """Rows the partial BN statistics buffer needs for a forward conv over x0 (host-only query).  With ``cout`` the
+    library can tell which kernel will run (the 16/32-channel layers write one row per CTA instead of one per tile)."""
     a = HdConvArgs()
     a.x0 = act(x0)
     a.kh = a.kw = k
     a.stride = stride
+    if cout is not None:
+        a.y0.c = int(cout)
     n = _lib.load().hd_conv_fwd_tiles(ctypes.byref(a))
     if n <= 0:
         raise RuntimeError(f"hd_conv_fwd_tiles failed ({n})")

@@ -307,7 +307,7 @@ class _UnetEngine:
         """train: z = conv(x) (+stats) -> finalize -> a_out = relu(bn(z) + res).   eval: fused epilogue."""
         if self.training:
             if l.stats is None:
-                l.stats = torch.zeros(ops.conv_fwd_tiles(x0, l.k, l.stride), 2, l.cout, device=self.device)
+                l.stats = torch.zeros(ops.conv_fwd_tiles(x0, l.k, l.stride, cout=None if x1 is not None else l.cout), 2, l.cout, device=self.device)
             ops.conv_fwd(ops.conv_args(x0, l.z, l.packed.w_fwd, k=l.k, stride=l.stride, x1=x1, stats=l.stats))
             bn = l.bn
             ops.bn_finalize(l.stats, self.B * l.h * l.w, bn.weight.detach(), bn.bias.detach(), bn.eps,

@@ -52,6 +52,8 @@ CONV_CASES = [
     (2, 16, 16, 16, 16, 3, 1, 0),
     (1, 16, 16, 32, 32, 3, 1, 0),
     (1, 64, 64, 32, 16, 3, 1, 0),
+    (2, 20, 44, 16, 32, 3, 1, 0),       # narrow-layer kernel, partial 8x32 tiles
+    (3, 9, 70, 32, 32, 3, 1, 0),
     (2, 16, 24, 64, 128, 3, 2, 0),
     (2, 16, 24, 64, 128, 1, 2, 0),
     (1, 16, 16, 64, 32, 3, 1, 64),
@@ -100,6 +102,42 @@ def test_conv_fwd_epilogue_bias_add_relu_stats():
     assert torch.allclose(s[1], (yq * yq).sum((0, 2, 3)), rtol=2e-3, atol=1e-2)
 
 
+@pytest.mark.parametrize("cin,cout", [(16, 16), (32, 16), (16, 32), (32, 32)])
+def test_conv_fwd_narrow_epilogue_bias_relu_stats(cin, cout):
+    """The 16/32-channel 3x3 layers (decoder blocks 3-4, head) run on the halo-patch kernel: same epilogue contract."""
+    o = ops()
+    n, h, w = 2, 21, 75
+    x = rnd(n, h, w, cin, seed=1)
+    bias = torch.randn(cout, device="cuda")
+    wt = (torch.randn(cout, cin, 3, 3, generator=torch.Generator().manual_seed(3)) / (cin * 9) ** 0.5).to(torch.bfloat16).float().cuda()
+    pk = o.PackedConv(cout, cin, 3, "cuda").pack(wt)
+    y = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    stats = torch.full((o.conv_fwd_tiles(x, 3, 1, cout=cout), 2, cout), float("nan"), device="cuda")
+    o.conv_fwd(o.conv_args(x, y, pk.w_fwd, k=3, bias=bias, relu=True, stats=stats))
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(nchw(x), wt, bias, padding=1))
+    assert_close_bf16(nchw(y), ref, "narrow epilogue")
+    yq = nchw(y)
+    s = stats.sum(0)
+    assert torch.allclose(s[0], yq.sum((0, 2, 3)), rtol=2e-3, atol=1e-2)
+    assert torch.allclose(s[1], (yq * yq).sum((0, 2, 3)), rtol=2e-3, atol=1e-2)
+    # run-to-run deterministic statistics (fixed-order reductions, no atomics); a buffer sized without the channel hint
+    # (more rows than CTAs) has its surplus rows zeroed
+    stats2 = torch.full((o.conv_fwd_tiles(x, 3, 1), 2, cout), float("nan"), device="cuda")
+    assert stats2.shape[0] >= stats.shape[0]
+    o.conv_fwd(o.conv_args(x, y, pk.w_fwd, k=3, bias=bias, relu=True, stats=stats2))
+    torch.cuda.synchronize()
+    assert torch.equal(stats, stats2[:stats.shape[0]])
+    assert float(stats2[stats.shape[0]:].abs().sum()) == 0.0
+    # fp32 NCHW side output (the head's epilogue), without the bf16 store
+    f32 = torch.zeros(n, cout, h, w, device="cuda")
+    y2 = torch.zeros_like(y)
+    o.conv_fwd(o.conv_args(x, y2, pk.w_fwd, k=3, bias=bias, relu=True, out_f32=f32, out_f32_channels=cout, store_bf16=False))
+    torch.cuda.synchronize()
+    assert torch.allclose(f32, ref, rtol=1e-3, atol=1e-3 * ref.abs().max().item())
+    assert float(y2.float().abs().sum()) == 0.0
+
+
 def test_conv_fwd_head_sigmoid_nchw():
     o = ops()
     n, h, w = 2, 32, 64
@@ -124,6 +162,8 @@ DGRAD_CASES = [
     (2, 8, 8, 64, 256, 1, 1, 0),
     (2, 16, 16, 16, 16, 3, 1, 0),
     (1, 64, 64, 32, 16, 3, 1, 0),
+    (2, 20, 44, 32, 32, 3, 1, 0),       # narrow-layer kernel, partial 8x32 tiles
+    (3, 9, 70, 16, 32, 3, 1, 0),
     (2, 16, 24, 64, 128, 3, 2, 0),
     (1, 16, 16, 128, 64, 3, 1, 64),     # dX split into (64 | 64)
     (1, 16, 20, 192, 64, 3, 1, 64),     # (128 | 64)
@@ -178,6 +218,8 @@ WGRAD_CASES = [
     (2, 32, 32, 16, 16, 3, 1, 0),
     (1, 64, 64, 32, 16, 3, 1, 0),
     (2, 32, 32, 32, 32, 3, 1, 0),
+    (2, 20, 44, 16, 32, 3, 1, 0),       # narrow-layer kernel, partial 8x32 tiles
+    (3, 9, 70, 32, 32, 3, 1, 0),
     (2, 16, 24, 64, 128, 3, 2, 0),
     (2, 16, 24, 64, 128, 1, 2, 0),
     (1, 16, 16, 64, 32, 3, 1, 64),

@@ -29,16 +29,21 @@ CASES = [
     ("fwd3x3_512_512_16x20_stats", "fwd", 16, 20, 512, 512, 3, 1, "stats"),
     ("fwd3x3_16_16_512x640_stats", "fwd", 512, 640, 16, 16, 3, 1, "stats"),
     ("fwd3x3_32_16_512x640_stats", "fwd", 512, 640, 32, 16, 3, 1, "stats"),
+    ("fwd3x3_32_32_256x320_stats", "fwd", 256, 320, 32, 32, 3, 1, "stats"),
+    ("fwd3x3_16_16_512x640_head", "fwd", 512, 640, 16, 16, 3, 1, "bias"),
     ("fwd3x3_128_128_80_relu", "fwd", 80, 80, 128, 128, 3, 1, "bias,relu"),
     ("dgrad1x1_64to256_160_addmask", "dgrad", 160, 160, 256, 64, 1, 1, "add,mask"),
     ("dgrad3x3_64_64_160_mask", "dgrad", 160, 160, 64, 64, 3, 1, "mask"),
     ("dgrad3x3_256_256_40_mask", "dgrad", 40, 40, 256, 256, 3, 1, "mask"),
     ("dgrad3x3_16_16_512x640", "dgrad", 512, 640, 16, 16, 3, 1, ""),
+    ("dgrad3x3_32_16_512x640", "dgrad", 512, 640, 32, 16, 3, 1, ""),
+    ("dgrad3x3_32_32_256x320", "dgrad", 256, 320, 32, 32, 3, 1, ""),
     ("wgrad3x3_64_64_128x160", "wgrad", 128, 160, 64, 64, 3, 1, ""),
     ("wgrad3x3_128_128_64x80", "wgrad", 64, 80, 128, 128, 3, 1, ""),
     ("wgrad3x3_256_256_32x40", "wgrad", 32, 40, 256, 256, 3, 1, ""),
     ("wgrad3x3_512_512_16x20", "wgrad", 16, 20, 512, 512, 3, 1, ""),
     ("wgrad3x3_16_16_512x640", "wgrad", 512, 640, 16, 16, 3, 1, ""),
+    ("wgrad3x3_32_16_512x640", "wgrad", 512, 640, 32, 16, 3, 1, ""),
     ("wgrad3x3_32_32_256x320", "wgrad", 256, 320, 32, 32, 3, 1, ""),
 ]
 
