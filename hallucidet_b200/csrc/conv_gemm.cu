@@ -291,6 +291,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             ds_soff[i] = swz(static_cast<uint32_t>(r * row_b + ch * 16), smask);
             ds_goff[i] = ch * 8;
         }
+        // staging address of this thread's row: the 128B/64B/32B swizzle XOR depends on the row only
+        const uint32_t row_off = static_cast<uint32_t>(row) * row_b;
+        const uint32_t sw_x = ((row_off >> 7) & smask) << 4;
+        const bool fused = P.add != nullptr || P.mask != nullptr;
         int acc = 0;
         uint32_t acc_phase = 0;
         int iter = 0;
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
             // fused-operand loads are software-pipelined one 16-column chunk ahead of their use
             uint4 na0 = make_uint4(0, 0, 0, 0), na1 = na0, nm0 = na0, nm1 = na0;
-            if (c_begin < c_end && valid && n0 + c_begin * 16 < P.Cout_total) {
+            if (fused && c_begin < c_end && valid && n0 + c_begin * 16 < P.Cout_total) {
                 if (add_row) { const uint4* ap = reinterpret_cast<const uint4*>(add_row + c_begin * 16); na0 = ap[0]; na1 = ap[1]; }
                 if (mask_row) { const uint4* mp = reinterpret_cast<const uint4*>(mask_row + c_begin * 16); nm0 = __ldg(mp); nm1 = __ldg(mp + 1); }
             }
@@ -331,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 const uint4 a0 = na0, a1 = na1, m0 = nm0, m1 = nm1;
                 const bool has_add = add_row != nullptr && valid && ch_ok;
                 const bool has_mask = mask_row != nullptr && valid && ch_ok;
-                if (c16 + 1 < c_end && valid && ch0 + 16 < P.Cout_total) {
+                if (fused && c16 + 1 < c_end && valid && ch0 + 16 < P.Cout_total) {
                     if (add_row) { const uint4* ap = reinterpret_cast<const uint4*>(add_row + (c16 + 1) * 16); na0 = ap[0]; na1 = ap[1]; }
                     if (mask_row) { const uint4* mp = reinterpret_cast<const uint4*>(mask_row + (c16 + 1) * 16); nm0 = __ldg(mp); nm1 = __ldg(mp + 1); }
                 }
@@ -391,14 +395,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     }
                 }
                 if (P.store_bf16) {
-                    const int cl = c16 * 16;                   // channel offset inside the N tile
-                    const uint32_t sub = cl / sub_c;
-                    const uint32_t off = sub * 128u * row_b + row * row_b + (cl - sub * sub_c) * 2;
+                    // channel offset inside the N tile -> 64-channel staging sub-tile (BN < 64: one sub-tile) + byte in row
+                    const uint32_t cl = c16 * 16;
+                    const uint32_t inner = (cl & 63u) * 2u;
+                    const uint32_t sbase = staging + (cl >> 6) * 128u * row_b + row_off;
                     const uint32_t q0x = pack_bf16x2(v[0], v[1]), q0y = pack_bf16x2(v[2], v[3]);
                     const uint32_t q0z = pack_bf16x2(v[4], v[5]), q0w = pack_bf16x2(v[6], v[7]);
                     const uint32_t q1x = pack_bf16x2(v[8], v[9]), q1y = pack_bf16x2(v[10], v[11]);
                     const uint32_t q1z = pack_bf16x2(v[12], v[13]), q1w = pack_bf16x2(v[14], v[15]);
-                    const uint32_t d0 = staging + swz(off, smask), d1 = staging + swz(off + 16, smask);
+                    const uint32_t d0 = sbase + (inner ^ sw_x), d1 = sbase + ((inner + 16u) ^ sw_x);
                     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d0), "r"(q0x), "r"(q0y), "r"(q0z), "r"(q0w) : "memory");
                     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d1), "r"(q1x), "r"(q1y), "r"(q1z), "r"(q1w) : "memory");
                 }
