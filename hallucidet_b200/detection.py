@@ -18,6 +18,7 @@ import torchvision
 from torchvision.models.detection.roi_heads import fastrcnn_loss
 from torchvision.models.detection.rpn import concat_box_prediction_layers
 
+from . import ops
 from .backbone import FrozenBackbone
 from .transform import GeneralizedRCNNTransform
 
@@ -100,6 +101,20 @@ def _side_streams(device, n):
     return pool[:n]
 
 
+def batched_nms(boxes, scores, idxs, iou_threshold):
+    """``torchvision.ops.batched_nms`` (TV ops/boxes.py: the coordinate-offset trick, then nms) with the NMS itself on
+    this package's kernels (ops.nms: identical keep set).  Oversized / non-CUDA inputs go to torchvision unchanged."""
+    from torchvision.ops import boxes as box_ops
+    if (not boxes.is_cuda) or boxes.dtype != torch.float32 or boxes.shape[0] > ops.NMS_MAX_BOXES or boxes.numel() > 100_000:
+        return box_ops.batched_nms(boxes, scores, idxs, iou_threshold)
+    if boxes.numel() == 0:
+        return torch.empty((0,), dtype=torch.int64, device=boxes.device)
+    max_coordinate = boxes.max()
+    offsets = idxs.to(boxes) * (max_coordinate + torch.tensor(1).to(boxes))
+    boxes_for_nms = boxes + offsets[:, None]
+    return ops.nms(boxes_for_nms, scores, iou_threshold)
+
+
 def filter_proposals_concurrent(rpn, proposals, objectness, image_shapes, num_anchors_per_level):
     """torchvision ``RegionProposalNetwork.filter_proposals`` (TV models/detection/rpn.py:242-295), same operators in the
     same order per image -- but the per-image bodies (clip, small-box / score filters, batched NMS, top-n) are enqueued
@@ -132,7 +147,7 @@ def filter_proposals_concurrent(rpn, proposals, objectness, image_shapes, num_an
             boxes, scores, lvl = boxes[keep], scores[keep], lvl[keep]
             keep = torch.where(scores >= rpn.score_thresh)[0]
             boxes, scores, lvl = boxes[keep], scores[keep], lvl[keep]
-            keep = box_ops.batched_nms(boxes, scores, lvl, rpn.nms_thresh)
+            keep = batched_nms(boxes, scores, lvl, rpn.nms_thresh)
             keep = keep[: rpn.post_nms_top_n()]
             boxes, scores = boxes[keep], scores[keep]
         if st is not None:
@@ -163,8 +178,11 @@ def _thread_pool(n):
     return _POOL
 
 
-CONCURRENT_NMS = True              # proposal filtering: 8 x ~1 ms single-block NMS kernels overlap (rpn_eval 17.5 -> 13.3 ms, config 2)
-CONCURRENT_POSTPROCESS = False     # final detections: NMS inputs are small, the host-thread hand-off costs more than it saves
+import os as _os
+
+# Host threads + one CUDA stream per image for the per-image loops (A/B switches: HD_CONCURRENT_NMS / HD_CONCURRENT_POSTPROCESS)
+CONCURRENT_NMS = _os.environ.get("HD_CONCURRENT_NMS", "1") != "0"                   # proposal filtering
+CONCURRENT_POSTPROCESS = _os.environ.get("HD_CONCURRENT_POSTPROCESS", "0") != "0"   # final detections
 
 
 def rpn_eval(model, images, features, targets):
@@ -188,7 +206,7 @@ def rpn_eval(model, images, features, targets):
     return boxes, {"loss_objectness": loss_objectness, "loss_rpn_box_reg": loss_rpn_box_reg}
 
 
-def postprocess_detections_concurrent(roi_heads, class_logits, box_regression, proposals, image_shapes):
+def postprocess_detections_concurrent(roi_heads, class_logits, box_regression, proposals, image_shapes, threaded=True):
     """torchvision ``RoIHeads.postprocess_detections`` (TV models/detection/roi_heads.py:668-727), identical operators per
     image, with the per-image bodies (score filter, small-box filter, batched NMS, top-k) on one host thread + CUDA stream
     per image (see filter_proposals_concurrent).  No randomness; results equal the sequential loop."""
@@ -214,19 +232,22 @@ def postprocess_detections_concurrent(roi_heads, class_logits, box_regression, p
             boxes, scores, labels = boxes[inds], scores[inds], labels[inds]
             keep = box_ops.remove_small_boxes(boxes, min_size=1e-2)
             boxes, scores, labels = boxes[keep], scores[keep], labels[keep]
-            keep = box_ops.batched_nms(boxes, scores, labels, roi_heads.nms_thresh)
+            keep = batched_nms(boxes, scores, labels, roi_heads.nms_thresh)
             keep = keep[: roi_heads.detections_per_img]
             boxes, scores, labels = boxes[keep], scores[keep], labels[keep]
         for t in (boxes, scores, labels):
             t.record_stream(main)
         return boxes, scores, labels
 
-    for st in streams:
-        st.wait_stream(main)
     work = list(zip(pred_boxes_list, pred_scores_list, image_shapes, streams))
-    results = list(_thread_pool(n).map(lambda w: body(*w), work))
-    for st in streams:
-        main.wait_stream(st)
+    if not threaded:
+        results = [body(b, s_, sh, main) for b, s_, sh, _ in work]
+    else:
+        for st in streams:
+            st.wait_stream(main)
+        results = list(_thread_pool(n).map(lambda w: body(*w), work))
+        for st in streams:
+            main.wait_stream(st)
     return [r[0] for r in results], [r[1] for r in results], [r[2] for r in results]
 
 
@@ -242,10 +263,11 @@ def roi_heads_eval(model, features, proposals, image_shapes, targets=None, train
     class_logits, box_regression = model.roi_heads.box_predictor(box_features)
     loss_classifier, loss_box_reg = fastrcnn_loss(class_logits, box_regression, labels, regression_targets)
     losses = {"loss_classifier": loss_classifier, "loss_box_reg": loss_box_reg}
-    if CONCURRENT_POSTPROCESS and class_logits.is_cuda and len(proposals) > 1:
+    if class_logits.is_cuda:
         with torch.no_grad():
             boxes, scores, labels = postprocess_detections_concurrent(model.roi_heads, class_logits.detach(), box_regression.detach(),
-                                                                      proposals, image_shapes)
+                                                                      proposals, image_shapes,
+                                                                      threaded=CONCURRENT_POSTPROCESS and len(proposals) > 1)
     else:
         boxes, scores, labels = model.roi_heads.postprocess_detections(class_logits, box_regression, proposals, image_shapes)
     result = [{"boxes": boxes[i], "labels": labels[i], "scores": scores[i]} for i in range(len(boxes))]

@@ -299,3 +299,48 @@ def regulariser(kind, hal, rgb, ir, w_rgb, w_ir, loss, dhal=None, grad_scale=1.0
     with _Timed("regulariser"):
         check(_lib.load().hd_regulariser({"mse": 0, "l1": 1}[kind], _ptr(hal), _ptr(rgb), _ptr(ir), w_rgb, w_ir, n, h, w, _ptr(loss),
                                          _ptr(dhal), grad_scale, int(accumulate), _stream()), "hd_regulariser")
+
+
+NMS_MAX_BOXES = 8192     # per problem (shared-memory budget of the scan kernel)
+
+
+def nms(boxes, scores, iou_threshold):
+    """Drop-in for ``torchvision.ops.nms`` on CUDA fp32 boxes: same stable descending sort, same fp32 IoU predicate, same
+    greedy rule (include/hallucidet_b200.h: hd_nms), so the returned indices are identical -- without torchvision's
+    one-box-at-a-time mask walk."""
+    global LAUNCHES
+    n = boxes.shape[0]
+    if n == 0:
+        return torch.empty((0,), dtype=torch.int64, device=boxes.device)
+    assert boxes.is_cuda and boxes.dtype == torch.float32 and boxes.shape[1] == 4 and n <= NMS_MAX_BOXES
+    order = torch.sort(scores, dim=0, descending=True, stable=True)[1]
+    sorted_boxes = boxes.index_select(0, order).contiguous()
+    mask_ws = torch.empty(n * ((n + 63) // 64), dtype=torch.int64, device=boxes.device)
+    keep = torch.empty(n, dtype=torch.bool, device=boxes.device)
+    offsets = (ctypes.c_int * 2)(0, n)
+    with _Timed("nms"):
+        check(_lib.load().hd_nms(_ptr(sorted_boxes), offsets, 1, float(iou_threshold), _ptr(mask_ws), _ptr(keep), _stream()), "hd_nms")
+    LAUNCHES += 1            # two kernels: pairwise mask + scan
+    return order.masked_select(keep)
+
+
+def nms_sorted_batch(sorted_boxes_list, iou_threshold):
+    """Several independent NMS problems (boxes already sorted by descending score) in one pair of launches; returns the
+    boolean keep vector of every problem."""
+    global LAUNCHES
+    ns = [int(b.shape[0]) for b in sorted_boxes_list]
+    if sum(ns) == 0:
+        return [torch.empty(0, dtype=torch.bool, device=b.device) for b in sorted_boxes_list]
+    assert all(n <= NMS_MAX_BOXES for n in ns)
+    dev = sorted_boxes_list[0].device
+    allb = torch.cat([b.reshape(-1, 4) for b in sorted_boxes_list], 0).contiguous()
+    mask_ws = torch.empty(sum(n * ((n + 63) // 64) for n in ns), dtype=torch.int64, device=dev)
+    keep = torch.empty(sum(ns), dtype=torch.bool, device=dev)
+    offs = [0]
+    for n in ns:
+        offs.append(offs[-1] + n)
+    offsets = (ctypes.c_int * len(offs))(*offs)
+    with _Timed("nms"):
+        check(_lib.load().hd_nms(_ptr(allb), offsets, len(ns), float(iou_threshold), _ptr(mask_ws), _ptr(keep), _stream()), "hd_nms")
+    LAUNCHES += 1
+    return list(keep.split(ns))

@@ -155,6 +155,17 @@ int hd_resize_nearest_bwd(const float* dy, float* dx, int n, int c, int h_in, in
 int hd_regulariser(int kind, const float* hal, const float* rgb, const float* ir, float w_rgb, float w_ir,
                    int n, int h, int w, float* loss, float* dhal, float grad_scale, int accumulate, hd_stream stream);
 
+/* ---- greedy NMS of the detector's proposal filter / final detections -----------------------------------------
+ * Replaces the kernels behind torchvision.ops.nms (torchvision csrc/ops/cuda/nms_kernel.cu: nms_kernel_impl +
+ * gather_keep_from_mask), which the reference reaches through torchvision's RPN.filter_proposals and
+ * RoIHeads.postprocess_detections (src/models/detector.py builds torchvision detectors).  Same IoU predicate (fp32, same
+ * operation order), same greedy rule, so the keep set is identical.
+ * boxes_sorted: [total][4] fp32 x1,y1,x2,y2 -- `problems` independent box lists back to back, each sorted by descending
+ * score (the caller sorts: stable, descending, as torchvision does).  offsets: HOST array of problems+1 box offsets.
+ * mask_ws: device scratch of sum_p n_p*ceil(n_p/64) 64-bit words.  keep: [total] bytes, 1 = kept.  n_p <= 8192. */
+int hd_nms(const float* boxes_sorted, const int* offsets, int problems, float iou_threshold, void* mask_ws,
+           unsigned char* keep, hd_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

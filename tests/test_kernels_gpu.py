@@ -465,3 +465,45 @@ def test_regulariser(kind):
     (l0 + l1).backward()
     assert torch.allclose(loss, torch.stack([l0, l1]).detach(), rtol=1e-4)
     assert torch.allclose(dhal, hal.grad, rtol=1e-4, atol=1e-9)
+
+
+def _nms_boxes(n, seed, clusters=40):
+    g = torch.Generator().manual_seed(seed)
+    centers = torch.rand(clusters, 2, generator=g) * 600
+    c = centers[torch.randint(0, clusters, (n,), generator=g)] + torch.randn(n, 2, generator=g) * 12
+    wh = torch.rand(n, 2, generator=g) * 80 + 4
+    boxes = torch.cat([c - wh / 2, c + wh / 2], 1).cuda()
+    scores = torch.rand(n, generator=g)
+    if n:
+        scores[::7] = scores[0]                               # ties: the stable sort decides
+    return boxes, scores.cuda()
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 63, 64, 65, 130, 1000, 4300, 8192])
+@pytest.mark.parametrize("thr", [0.5, 0.7])
+def test_nms_matches_torchvision(n, thr):
+    """hd_nms vs torchvision.ops.nms (the op the reference's torchvision detectors call): identical indices, in order."""
+    import torchvision
+    o = ops()
+    boxes, scores = _nms_boxes(n, seed=n + 1)
+    ref = torchvision.ops.nms(boxes, scores, thr)
+    got = o.nms(boxes, scores, thr)
+    assert got.dtype == torch.int64 and torch.equal(got, ref)
+
+
+def test_nms_batched_problems_and_coordinate_trick():
+    import torchvision
+    from hallucidet_b200 import detection as D
+    o = ops()
+    probs = [_nms_boxes(n, seed=100 + n) for n in (700, 0, 64, 3000, 129)]
+    sorted_boxes, refs = [], []
+    for b, s in probs:
+        order = torch.sort(s, dim=0, descending=True, stable=True)[1] if b.shape[0] else torch.empty(0, dtype=torch.int64, device="cuda")
+        sorted_boxes.append(b[order])
+        refs.append((order, torchvision.ops.nms(b, s, 0.6)))
+    keeps = o.nms_sorted_batch(sorted_boxes, 0.6)
+    for (order, ref), keep in zip(refs, keeps):
+        assert torch.equal(order.masked_select(keep), ref)
+    b, s = _nms_boxes(2500, seed=9)
+    idxs = torch.randint(0, 5, (2500,), device="cuda")
+    assert torch.equal(D.batched_nms(b, s, idxs, 0.7), torchvision.ops.batched_nms(b, s, idxs, 0.7))
