@@ -65,7 +65,7 @@ PROTOTYPES = {
     "hd_resize_nearest_bwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
     "hd_regulariser": [c_int, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_int, c_int, c_void_p, c_void_p,
                        c_float, c_int, c_void_p],
-    "hd_nms": [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p],
+    "hd_nms": [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p],
 }
 _RESTYPES = {"hd_last_error": ctypes.c_char_p}
 

@@ -27,10 +27,19 @@ constexpr int kMaxColBlocks = 128;          // shared-memory budget of the scan 
 
 struct NmsBatch {
     int count;
+    int first;                              // index of the first problem of this launch (into counts)
+    const int* counts;                      // optional device array: actual box count per problem (<= capacity)
     int box_off[kMaxProblems];              // first box of the problem in the concatenated (sorted) box array
-    int n[kMaxProblems];
+    int n[kMaxProblems];                    // capacity (boxes reserved for the problem)
     long mask_off[kMaxProblems];            // first mask word of the problem
 };
+
+__device__ __forceinline__ int problem_size(const NmsBatch& B, int pb) {
+    const int cap = B.n[pb];
+    if (B.counts == nullptr) return cap;
+    const int c = B.counts[B.first + pb];
+    return c < 0 ? 0 : (c < cap ? c : cap);
+}
 
 __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, const float threshold) {
     const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
@@ -46,8 +55,9 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, const flo
 __global__ void __launch_bounds__(kNmsBox) nms_mask_kernel(const float4* __restrict__ boxes, unsigned long long* __restrict__ mask,
                                                           const NmsBatch B, float threshold) {
     const int pb = blockIdx.z;
-    const int n = B.n[pb];
+    const int n = problem_size(B, pb);
     const int col_blocks = (n + kNmsBox - 1) / kNmsBox;
+    const int pitch = (B.n[pb] + kNmsBox - 1) / kNmsBox;          // mask row pitch: from the capacity (host-known)
     const int row_start = blockIdx.y, col_start = blockIdx.x;
     if (row_start > col_start || col_start >= col_blocks) return;
     const float4* bx = boxes + B.box_off[pb];
@@ -62,7 +72,7 @@ __global__ void __launch_bounds__(kNmsBox) nms_mask_kernel(const float4* __restr
         const int start = row_start == col_start ? threadIdx.x + 1 : 0;
         for (int i = start; i < col_size; ++i)
             if (iou_gt(me, cb[i], threshold)) t |= 1ULL << i;
-        mask[B.mask_off[pb] + static_cast<long>(cur) * col_blocks + col_start] = t;
+        mask[B.mask_off[pb] + static_cast<long>(cur) * pitch + col_start] = t;
     }
 }
 
@@ -75,14 +85,16 @@ __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigne
                                                                   unsigned char* __restrict__ keep_all, const NmsBatch B) {
     extern __shared__ __align__(16) unsigned long long nsm[];
     const int pb = blockIdx.x;
-    const int n = B.n[pb];
+    const int n = problem_size(B, pb);
     const int col_blocks = (n + kNmsBox - 1) / kNmsBox;
+    const int pitch = (B.n[pb] + kNmsBox - 1) / kNmsBox;
     const unsigned long long* mask = mask_all + B.mask_off[pb];
     unsigned char* keep = keep_all + B.box_off[pb];
     unsigned long long* removed = nsm;                                   // [col_blocks]
     unsigned long long* rows = nsm + kMaxColBlocks;                      // [2][64][col_blocks]: words c.. of the rows of chunk c
     const int tid = threadIdx.x;
     for (int i = tid; i < col_blocks; i += kScanThreads) removed[i] = 0;
+    for (int i = n + tid; i < B.n[pb]; i += kScanThreads) keep[i] = 0;   // reserved but unused slots
 
     // rows of chunk c, words [c, col_blocks) -> rows[buf][i][0 .. col_blocks - c)
     auto prefetch = [&](int c, int buf) {
@@ -91,7 +103,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigne
         const uint32_t dst0 = smem_u32(rows + static_cast<long>(buf) * kNmsBox * col_blocks);
         for (int q = tid; q < nrow * wpr; q += kScanThreads) {
             const int i = q / wpr, j = q - i * wpr;
-            cp_async8(dst0 + (i * col_blocks + j) * 8, mask + static_cast<long>(c * kNmsBox + i) * col_blocks + c + j);
+            cp_async8(dst0 + (i * col_blocks + j) * 8, mask + static_cast<long>(c * kNmsBox + i) * pitch + c + j);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -138,10 +150,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigne
 using namespace hd;
 
 // boxes_sorted: [total][4] fp32 (x1, y1, x2, y2), the problems back to back, each sorted by descending score.
-// offsets (host): problems + 1 box offsets.  mask_ws: sum over problems of n * ceil(n / 64) 64-bit words (device scratch).
+// offsets (host): problems + 1 box offsets (the capacity of each problem); counts_dev (optional, device): the number of
+// boxes actually present in each problem (the rest of its slots get keep = 0) -- lets the caller stay sync-free.  mask_ws: sum over problems of n * ceil(n / 64) 64-bit words (device scratch).
 // keep: [total] bytes, 1 = the box survives.  Replaces torchvision.ops.nms's kernels (see the header of this file).
-extern "C" int hd_nms(const float* boxes_sorted, const int* offsets, int problems, float iou_threshold, void* mask_ws,
-                      unsigned char* keep, hd_stream stream_) {
+extern "C" int hd_nms(const float* boxes_sorted, const int* offsets, const int* counts_dev, int problems, float iou_threshold,
+                      void* mask_ws, unsigned char* keep, hd_stream stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     HD_CHECK_ARG(offsets != nullptr && problems >= 0);
     if (problems == 0) return HD_OK;
@@ -157,6 +170,8 @@ extern "C" int hd_nms(const float* boxes_sorted, const int* offsets, int problem
     for (int p0 = 0; p0 < problems; p0 += kMaxProblems) {
         NmsBatch B;
         memset(&B, 0, sizeof(B));
+        B.first = p0;
+        B.counts = counts_dev;
         int max_cb = 0;
         for (int p = p0; p < problems && p < p0 + kMaxProblems; ++p) {
             const int n = offsets[p + 1] - offsets[p];

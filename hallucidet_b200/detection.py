@@ -115,6 +115,108 @@ def batched_nms(boxes, scores, idxs, iou_threshold):
     return ops.nms(boxes_for_nms, scores, iou_threshold)
 
 
+def _clip_boxes_batched(boxes, image_shapes):
+    """``clip_boxes_to_image`` (TV ops/boxes.py) for a batch [B, ..., 4]: scalar clamp when every image has the same
+    size (what the detector transform produces), per-image bounds otherwise -- the same min(max(x, 0), size) either way."""
+    dim = boxes.dim()
+    bx, by = boxes[..., 0::2], boxes[..., 1::2]
+    if all(tuple(s) == tuple(image_shapes[0]) for s in image_shapes):
+        height, width = image_shapes[0]
+        bx = bx.clamp(min=0, max=width)
+        by = by.clamp(min=0, max=height)
+    else:
+        sizes = torch.tensor([list(s) for s in image_shapes], dtype=boxes.dtype, device=boxes.device)
+        shape = [len(image_shapes)] + [1] * (dim - 1)
+        h, w = sizes[:, 0].view(shape), sizes[:, 1].view(shape)
+        zero = torch.zeros((), dtype=boxes.dtype, device=boxes.device)
+        bx = torch.minimum(torch.maximum(bx, zero), w)
+        by = torch.minimum(torch.maximum(by, zero), h)
+    return torch.stack((bx, by), dim=dim).reshape(boxes.shape)
+
+
+def _filter_nms_batched(boxes, scores, idxs, valid, nms_thresh, top_n):
+    """The tail of torchvision's per-image loops -- drop the filtered boxes, ``batched_nms`` per category, keep the best
+    ``top_n`` -- for all images at once and without a host sync per image.  boxes [B, M, 4], scores / idxs / valid [B, M].
+    Instead of compacting each image (a ``nonzero`` + sync), filtered boxes get score -inf and sort to the end of the row;
+    the stable descending sort orders the surviving boxes exactly as the compacted per-image sort would, the coordinate
+    offset uses the maximum over the surviving boxes only, and hd_nms takes the survivor count from device memory.
+    Returns per-image tuples (boxes, scores, idxs), identical to the torchvision loop."""
+    B, M = scores.shape
+    neg_inf = float("-inf")
+    max_coord = boxes.masked_fill(~valid[..., None], neg_inf).amax(dim=(1, 2))                     # boxes.max() of the survivors
+    offsets = idxs.to(boxes) * (max_coord + torch.tensor(1).to(boxes))[:, None]
+    boxes_for_nms = boxes + offsets[..., None]
+    order = torch.sort(scores.masked_fill(~valid, neg_inf), dim=1, descending=True, stable=True)[1]
+    gidx = order[..., None].expand(-1, -1, 4)
+    sorted_for_nms = torch.gather(boxes_for_nms, 1, gidx).contiguous()
+    counts = valid.sum(1, dtype=torch.int32)
+    keep = ops.nms_sorted_flat(sorted_for_nms.view(-1, 4), [i * M for i in range(B + 1)], nms_thresh, counts=counts).view(B, M)
+    sel = keep & (keep.cumsum(1) <= top_n)
+    n_sel = sel.sum(1).tolist()                                                                    # the one host sync
+    out_boxes = torch.gather(boxes, 1, gidx)[sel].split(n_sel)
+    out_scores = torch.gather(scores, 1, order)[sel].split(n_sel)
+    out_idxs = torch.gather(idxs, 1, order)[sel].split(n_sel)
+    return out_boxes, out_scores, out_idxs
+
+
+def filter_proposals_batched(rpn, proposals, objectness, image_shapes, num_anchors_per_level):
+    """torchvision ``RegionProposalNetwork.filter_proposals`` (TV models/detection/rpn.py:242-295) with the per-image loop
+    (clip, small-box / score filters, per-level NMS, top-n) done for the whole batch: ~30 launches and one host sync
+    instead of ~25 launches and 3 syncs per image.  Results are identical (tests/test_modules_gpu.py)."""
+    num_images = proposals.shape[0]
+    device = proposals.device
+    objectness = objectness.detach().reshape(num_images, -1)
+    levels = torch.cat([torch.full((n,), idx, dtype=torch.int64, device=device) for idx, n in enumerate(num_anchors_per_level)], 0)
+    levels = levels.reshape(1, -1).expand_as(objectness)
+    top_n_idx = rpn._get_top_n_idx(objectness, num_anchors_per_level)
+    batch_idx = torch.arange(num_images, device=device)[:, None]
+    objectness = objectness[batch_idx, top_n_idx]
+    levels = levels[batch_idx, top_n_idx]
+    proposals = proposals[batch_idx, top_n_idx]
+    scores = torch.sigmoid(objectness)
+    with torch.no_grad():
+        boxes = _clip_boxes_batched(proposals, image_shapes)
+        ws, hs = boxes[..., 2] - boxes[..., 0], boxes[..., 3] - boxes[..., 1]
+        valid = (ws >= rpn.min_size) & (hs >= rpn.min_size) & (scores >= rpn.score_thresh)
+        out_boxes, out_scores, _ = _filter_nms_batched(boxes, scores, levels, valid, rpn.nms_thresh, rpn.post_nms_top_n())
+    return list(out_boxes), list(out_scores)
+
+
+def postprocess_detections_batched(roi_heads, class_logits, box_regression, proposals, image_shapes):
+    """torchvision ``RoIHeads.postprocess_detections`` (TV models/detection/roi_heads.py:668-727) for the whole batch at
+    once (see filter_proposals_batched); identical boxes / scores / labels."""
+    device = class_logits.device
+    num_classes = class_logits.shape[-1]
+    boxes_per_image = [b.shape[0] for b in proposals]
+    pred_boxes = roi_heads.box_coder.decode(box_regression, proposals)
+    pred_scores = F.softmax(class_logits, -1)
+    B, n_max = len(boxes_per_image), max(boxes_per_image)
+    if all(n == n_max for n in boxes_per_image):
+        boxes = pred_boxes.view(B, n_max, num_classes, 4)
+        scores = pred_scores.view(B, n_max, num_classes)
+        present = None
+    else:                                              # ragged: pad every image to the longest one
+        boxes = pred_boxes.new_zeros(B, n_max, num_classes, 4)
+        scores = pred_scores.new_zeros(B, n_max, num_classes)
+        present = torch.zeros(B, n_max, dtype=torch.bool, device=device)
+        for i, (pb, ps) in enumerate(zip(pred_boxes.split(boxes_per_image, 0), pred_scores.split(boxes_per_image, 0))):
+            boxes[i, :pb.shape[0]], scores[i, :ps.shape[0]], present[i, :pb.shape[0]] = pb, ps, True
+    boxes = _clip_boxes_batched(boxes, image_shapes)
+    labels = torch.arange(num_classes, device=device).view(1, 1, -1).expand_as(scores)
+    boxes, scores, labels = boxes[:, :, 1:], scores[:, :, 1:], labels[:, :, 1:]
+    boxes, scores, labels = boxes.reshape(B, -1, 4), scores.reshape(B, -1), labels.reshape(B, -1)
+    ws, hs = boxes[..., 2] - boxes[..., 0], boxes[..., 3] - boxes[..., 1]
+    valid = (scores > roi_heads.score_thresh) & (ws >= 1e-2) & (hs >= 1e-2)
+    if present is not None:
+        valid = valid & present[:, :, None].expand(-1, -1, num_classes - 1).reshape(B, -1)
+    out = _filter_nms_batched(boxes, scores, labels, valid, roi_heads.nms_thresh, roi_heads.detections_per_img)
+    return list(out[0]), list(out[1]), list(out[2])
+
+
+def _batched_ok(n_boxes):
+    return n_boxes <= ops.NMS_MAX_BOXES and n_boxes * 4 <= 100_000
+
+
 def filter_proposals_concurrent(rpn, proposals, objectness, image_shapes, num_anchors_per_level):
     """torchvision ``RegionProposalNetwork.filter_proposals`` (TV models/detection/rpn.py:242-295), same operators in the
     same order per image -- but the per-image bodies (clip, small-box / score filters, batched NMS, top-n) are enqueued
@@ -183,6 +285,7 @@ import os as _os
 # Host threads + one CUDA stream per image for the per-image loops (A/B switches: HD_CONCURRENT_NMS / HD_CONCURRENT_POSTPROCESS)
 CONCURRENT_NMS = _os.environ.get("HD_CONCURRENT_NMS", "1") != "0"                   # proposal filtering
 CONCURRENT_POSTPROCESS = _os.environ.get("HD_CONCURRENT_POSTPROCESS", "0") != "0"   # final detections
+BATCHED_TAIL = _os.environ.get("HD_BATCHED_TAIL", "1") != "0"   # whole-batch proposal filter / detections post-processing
 
 
 def rpn_eval(model, images, features, targets):
@@ -194,7 +297,10 @@ def rpn_eval(model, images, features, targets):
     objectness, pred_bbox_deltas = concat_box_prediction_layers(objectness, pred_bbox_deltas)
     proposals = model.rpn.box_coder.decode(pred_bbox_deltas.detach(), anchors)
     proposals = proposals.view(num_images, -1, 4)
-    if CONCURRENT_NMS and proposals.is_cuda:
+    pre_nms = sum(min(model.rpn.pre_nms_top_n(), n) for n in num_anchors_per_level)
+    if BATCHED_TAIL and proposals.is_cuda and proposals.dtype == torch.float32 and _batched_ok(pre_nms):
+        boxes, scores = filter_proposals_batched(model.rpn, proposals, objectness, images.image_sizes, num_anchors_per_level)
+    elif CONCURRENT_NMS and proposals.is_cuda:
         boxes, scores = filter_proposals_concurrent(model.rpn, proposals, objectness, images.image_sizes, num_anchors_per_level)
     else:
         boxes, scores = model.rpn.filter_proposals(proposals, objectness, images.image_sizes, num_anchors_per_level)
@@ -263,7 +369,12 @@ def roi_heads_eval(model, features, proposals, image_shapes, targets=None, train
     class_logits, box_regression = model.roi_heads.box_predictor(box_features)
     loss_classifier, loss_box_reg = fastrcnn_loss(class_logits, box_regression, labels, regression_targets)
     losses = {"loss_classifier": loss_classifier, "loss_box_reg": loss_box_reg}
-    if class_logits.is_cuda:
+    n_cand = max(p.shape[0] for p in proposals) * (class_logits.shape[-1] - 1)
+    if BATCHED_TAIL and class_logits.is_cuda and class_logits.dtype == torch.float32 and _batched_ok(n_cand):
+        with torch.no_grad():
+            boxes, scores, labels = postprocess_detections_batched(model.roi_heads, class_logits.detach(), box_regression.detach(),
+                                                                   proposals, image_shapes)
+    elif class_logits.is_cuda:
         with torch.no_grad():
             boxes, scores, labels = postprocess_detections_concurrent(model.roi_heads, class_logits.detach(), box_regression.detach(),
                                                                       proposals, image_shapes,

@@ -319,7 +319,7 @@ def nms(boxes, scores, iou_threshold):
     keep = torch.empty(n, dtype=torch.bool, device=boxes.device)
     offsets = (ctypes.c_int * 2)(0, n)
     with _Timed("nms"):
-        check(_lib.load().hd_nms(_ptr(sorted_boxes), offsets, 1, float(iou_threshold), _ptr(mask_ws), _ptr(keep), _stream()), "hd_nms")
+        check(_lib.load().hd_nms(_ptr(sorted_boxes), offsets, None, 1, float(iou_threshold), _ptr(mask_ws), _ptr(keep), _stream()), "hd_nms")
     LAUNCHES += 1            # two kernels: pairwise mask + scan
     return order.masked_select(keep)
 
@@ -327,20 +327,30 @@ def nms(boxes, scores, iou_threshold):
 def nms_sorted_batch(sorted_boxes_list, iou_threshold):
     """Several independent NMS problems (boxes already sorted by descending score) in one pair of launches; returns the
     boolean keep vector of every problem."""
-    global LAUNCHES
     ns = [int(b.shape[0]) for b in sorted_boxes_list]
     if sum(ns) == 0:
         return [torch.empty(0, dtype=torch.bool, device=b.device) for b in sorted_boxes_list]
-    assert all(n <= NMS_MAX_BOXES for n in ns)
-    dev = sorted_boxes_list[0].device
     allb = torch.cat([b.reshape(-1, 4) for b in sorted_boxes_list], 0).contiguous()
-    mask_ws = torch.empty(sum(n * ((n + 63) // 64) for n in ns), dtype=torch.int64, device=dev)
-    keep = torch.empty(sum(ns), dtype=torch.bool, device=dev)
     offs = [0]
     for n in ns:
         offs.append(offs[-1] + n)
-    offsets = (ctypes.c_int * len(offs))(*offs)
+    return list(nms_sorted_flat(allb, offs, iou_threshold).split(ns))
+
+
+def nms_sorted_flat(sorted_boxes, offsets, iou_threshold, counts=None):
+    """hd_nms over problems laid back to back in ``sorted_boxes`` [total, 4]; ``offsets`` = host list of problems+1 slot
+    offsets; ``counts`` = optional int32 device tensor with the live box count of each problem (no host sync needed)."""
+    global LAUNCHES
+    ns = [offsets[i + 1] - offsets[i] for i in range(len(offsets) - 1)]
+    assert sorted_boxes.is_cuda and sorted_boxes.dtype == torch.float32 and sorted_boxes.is_contiguous()
+    assert all(0 <= n <= NMS_MAX_BOXES for n in ns) and offsets[-1] == sorted_boxes.shape[0]
+    assert counts is None or (counts.dtype == torch.int32 and counts.is_cuda and counts.numel() == len(ns))
+    dev = sorted_boxes.device
+    mask_ws = torch.empty(max(1, sum(n * ((n + 63) // 64) for n in ns)), dtype=torch.int64, device=dev)
+    keep = torch.empty(offsets[-1], dtype=torch.bool, device=dev)
+    c_off = (ctypes.c_int * len(offsets))(*offsets)
     with _Timed("nms"):
-        check(_lib.load().hd_nms(_ptr(allb), offsets, len(ns), float(iou_threshold), _ptr(mask_ws), _ptr(keep), _stream()), "hd_nms")
+        check(_lib.load().hd_nms(_ptr(sorted_boxes), c_off, _ptr(counts), len(ns), float(iou_threshold), _ptr(mask_ws), _ptr(keep),
+                                 _stream()), "hd_nms")
     LAUNCHES += 1
-    return list(keep.split(ns))
+    return keep

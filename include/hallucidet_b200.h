@@ -161,10 +161,12 @@ int hd_regulariser(int kind, const float* hal, const float* rgb, const float* ir
  * RoIHeads.postprocess_detections (src/models/detector.py builds torchvision detectors).  Same IoU predicate (fp32, same
  * operation order), same greedy rule, so the keep set is identical.
  * boxes_sorted: [total][4] fp32 x1,y1,x2,y2 -- `problems` independent box lists back to back, each sorted by descending
- * score (the caller sorts: stable, descending, as torchvision does).  offsets: HOST array of problems+1 box offsets.
- * mask_ws: device scratch of sum_p n_p*ceil(n_p/64) 64-bit words.  keep: [total] bytes, 1 = kept.  n_p <= 8192. */
-int hd_nms(const float* boxes_sorted, const int* offsets, int problems, float iou_threshold, void* mask_ws,
-           unsigned char* keep, hd_stream stream);
+ * score (the caller sorts: stable, descending, as torchvision does).  offsets: HOST array of problems+1 box offsets
+ * (slots reserved per problem, n_p <= 8192).  counts_dev: optional DEVICE array with the number of boxes actually present
+ * in each problem (<= its slots; the remaining slots get keep = 0), so a caller with data-dependent counts needs no sync.
+ * mask_ws: device scratch of sum_p n_p*ceil(n_p/64) 64-bit words.  keep: [total] bytes, 1 = kept. */
+int hd_nms(const float* boxes_sorted, const int* offsets, const int* counts_dev, int problems, float iou_threshold,
+           void* mask_ws, unsigned char* keep, hd_stream stream);
 
 #ifdef __cplusplus
 }

@@ -364,8 +364,22 @@ def test_concurrent_proposal_filter_equals_torchvision():
         for _ in range(3):
             a = det.rpn.filter_proposals(props, o2, il.image_sizes, napl)
             b = D.filter_proposals_concurrent(det.rpn, props, o2, il.image_sizes, napl)
+            c = D.filter_proposals_batched(det.rpn, props, o2, il.image_sizes, napl)
             torch.cuda.synchronize()
-            assert all(torch.equal(p, q) for p, q in zip(a[0], b[0])) and all(torch.equal(p, q) for p, q in zip(a[1], b[1]))
+            for other in (b, c):
+                assert [t.shape for t in a[0]] == [t.shape for t in other[0]]
+                assert all(torch.equal(p, q) for p, q in zip(a[0], other[0])) and all(torch.equal(p, q) for p, q in zip(a[1], other[1]))
+        # images of different sizes, a score threshold that removes boxes, a minimum box size: the filters run as masks
+        det.rpn.score_thresh, det.rpn.min_size = 0.45, 6.0
+        sizes = [(256, 256), (200, 256), (256, 180), (130, 140)]
+        a = det.rpn.filter_proposals(props, o2, sizes, napl)
+        c = D.filter_proposals_batched(det.rpn, props, o2, sizes, napl)
+        assert [t.shape for t in a[0]] == [t.shape for t in c[0]] and min(t.shape[0] for t in a[0]) > 0
+        assert all(torch.equal(p, q) for p, q in zip(a[0], c[0])) and all(torch.equal(p, q) for p, q in zip(a[1], c[1]))
+        det.rpn.score_thresh = 2.0                        # nothing survives
+        a = det.rpn.filter_proposals(props, o2, sizes, napl)
+        c = D.filter_proposals_batched(det.rpn, props, o2, sizes, napl)
+        assert all(p.shape == q.shape == (0, 4) for p, q in zip(a[0], c[0]))
 
 
 def test_inference_pipeline_llvip_setting():
@@ -414,6 +428,17 @@ def test_concurrent_postprocess_equals_torchvision():
     with torch.no_grad():
         a = det.roi_heads.postprocess_detections(logits, reg, list(props), shapes)
         b = D.postprocess_detections_concurrent(det.roi_heads, logits, reg, list(props), shapes)
+        c = D.postprocess_detections_batched(det.roi_heads, logits, reg, list(props), shapes)
+        # ragged proposal counts and different image sizes
+        ragged = [props[0][:120], props[1], props[2][:7], props[3][:299]]
+        keep_rows = torch.cat([torch.arange(i * per, i * per + r.shape[0]) for i, r in enumerate(ragged)]).cuda()
+        shapes2 = [(256, 256), (180, 256), (256, 200), (90, 120)]
+        a2 = det.roi_heads.postprocess_detections(logits[keep_rows], reg[keep_rows], ragged, shapes2)
+        c2 = D.postprocess_detections_batched(det.roi_heads, logits[keep_rows], reg[keep_rows], ragged, shapes2)
     torch.cuda.synchronize()
-    for x, y in zip(a, b):
-        assert all(torch.equal(p, q) for p, q in zip(x, y))
+    for ref, others in ((a, (b, c)), (a2, (c2,))):
+        for other in others:
+            for x, y in zip(ref, other):
+                assert [p.shape for p in x] == [q.shape for q in y]
+                assert all(torch.equal(p, q) for p, q in zip(x, y))
+    assert sum(p.shape[0] for p in a[0]) > 0
