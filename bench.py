@@ -246,7 +246,7 @@ def main():
                                    f"batch {B}/GPU, 512x640 IR, S={S}, Adam + clip 0.5",
                        "detector": args.detector, "batch_per_gpu": B, "input": "512x640", "detector_size": S,
                        "parallelism": f"dp{world}", "cuda_graph": bool(was_graph), "pixel_regulariser": args.pixel,
-                       "detection_tail": "torchvision RPN/RoI heads + losses (fp32, TF32 matmul), per-image NMS on concurrent streams",
+                       "detection_tail": "torchvision RPN/RoI head modules + losses (fp32, TF32 matmul); proposal filter, target assignment, sampling and post-processing batched over the images; hd_nms kernels",
                        "l2": "working set (activations + weights, several GB per step) far exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,

@@ -213,6 +213,131 @@ def postprocess_detections_batched(roi_heads, class_logits, box_regression, prop
     return list(out[0]), list(out[1]), list(out[2])
 
 
+# ---- whole-batch target assignment and sampling (torchvision loops one image at a time: ~15 launches + 2-3 syncs each) ----
+
+def _pad_rows(rows, width, fill=0):
+    """List of [n_i, ...] tensors -> ([B, width, ...] padded with ``fill``, [B, width] bool presence mask), with one
+    concatenation and one scatter (the row counts are host-known shapes)."""
+    B = len(rows)
+    counts = [int(r.shape[0]) for r in rows]
+    ref = rows[0]
+    out = ref.new_full((B * width,) + tuple(ref.shape[1:]), fill)
+    present = torch.zeros(B * width, dtype=torch.bool, device=ref.device)
+    if sum(counts) > 0:
+        idx = torch.tensor([b * width + j for b, n in enumerate(counts) for j in range(n)], dtype=torch.int64).to(ref.device, non_blocking=True)
+        out[idx] = torch.cat(rows, 0)
+        present[idx] = True
+    return out.view((B, width) + tuple(ref.shape[1:])), present.view(B, width)
+
+
+def _match_batched(matcher, gt_boxes, gt_present, boxes):
+    """``det_utils.Matcher`` (TV models/detection/_utils.py) on ``box_iou(gt, boxes)`` for the whole batch.  gt_boxes
+    [B, G, 4] padded (gt_present marks real rows), boxes [B, N, 4] -> matches [B, N] int64 (gt index, -1 below the low
+    threshold, -2 between the thresholds).  Padded gt rows get quality -1, so they never win the arg-max, and they are
+    excluded from the low-quality rule; an image without ground truth comes out all -1 (background), which is what
+    torchvision's special case produces."""
+    from torchvision.ops import boxes as box_ops
+    mq = box_ops.box_iou(gt_boxes, boxes)                                    # [B, G, N]
+    mq = mq.masked_fill(~gt_present[..., None], -1.0)
+    matched_vals, matches = mq.max(dim=1)
+    all_matches = matches.clone() if matcher.allow_low_quality_matches else None
+    below = matched_vals < matcher.low_threshold
+    between = (matched_vals >= matcher.low_threshold) & (matched_vals < matcher.high_threshold)
+    matches = torch.where(below, matches.new_full((), matcher.BELOW_LOW_THRESHOLD), matches)
+    matches = torch.where(between, matches.new_full((), matcher.BETWEEN_THRESHOLDS), matches)
+    if matcher.allow_low_quality_matches:
+        highest = mq.max(dim=2)[0]                                          # best quality of every gt
+        update = ((mq == highest[..., None]) & gt_present[..., None]).any(dim=1)
+        matches = torch.where(update, all_matches, matches)
+    return matches
+
+
+def _sample_batched(sampler, labels):
+    """``det_utils.BalancedPositiveNegativeSampler`` for labels [B, N] (>= 1 positive, 0 negative, -1 ignored / padding).
+    Returns per-image (pos_idx, neg_idx) index tensors (unsorted, as drawn).  The two ``torch.randperm`` calls per image
+    are issued with the same sizes and in the same order as torchvision's loop, so the CUDA generator is consumed
+    identically and the samples are the same; everything else (counts, index lists) is computed once for the batch."""
+    B, N = labels.shape
+    pos_mask, neg_mask = labels >= 1, labels == 0
+    cnt = torch.stack([pos_mask.sum(1), neg_mask.sum(1)]).tolist()          # one host sync
+    n_pos_all, n_neg_all = cnt
+    pos_nz = torch.nonzero_static(pos_mask, size=sum(n_pos_all))[:, 1]
+    neg_nz = torch.nonzero_static(neg_mask, size=sum(n_neg_all))[:, 1]
+    out, po, no = [], 0, 0
+    for b in range(B):
+        positive, negative = pos_nz[po:po + n_pos_all[b]], neg_nz[no:no + n_neg_all[b]]
+        po, no = po + n_pos_all[b], no + n_neg_all[b]
+        num_pos = min(n_pos_all[b], int(sampler.batch_size_per_image * sampler.positive_fraction))
+        num_neg = min(n_neg_all[b], sampler.batch_size_per_image - num_pos)
+        perm1 = torch.randperm(n_pos_all[b], device=labels.device)[:num_pos]
+        perm2 = torch.randperm(n_neg_all[b], device=labels.device)[:num_neg]
+        out.append((positive[perm1], negative[perm2]))
+    return out
+
+
+def assign_targets_to_anchors_batched(rpn, anchors, targets):
+    """``RegionProposalNetwork.assign_targets_to_anchors`` (TV rpn.py) for the whole batch; returns [B, A] float labels
+    (1 / 0 / -1) and [B, A, 4] matched boxes (identical values; the per-image lists are rows of these)."""
+    A = torch.stack(anchors)                                                 # every image has the same anchor count
+    G = max(1, max(int(t["boxes"].shape[0]) for t in targets))
+    gt, present = _pad_rows([t["boxes"] for t in targets], G)
+    matches = _match_batched(rpn.proposal_matcher, gt, present, A)
+    matched_gt = torch.gather(gt, 1, matches.clamp(min=0)[..., None].expand(-1, -1, 4))
+    labels = (matches >= 0).to(torch.float32)
+    labels = torch.where(matches == rpn.proposal_matcher.BETWEEN_THRESHOLDS, labels.new_full((), -1.0), labels)
+    return labels, matched_gt.to(torch.float32) if matched_gt.dtype != torch.float32 else matched_gt
+
+
+def rpn_compute_loss_batched(rpn, objectness, pred_bbox_deltas, labels, regression_targets):
+    """``RegionProposalNetwork.compute_loss`` (TV rpn.py) with labels [B, A] / regression_targets [B*A, 4] from the batched
+    assignment.  Same samples (see _sample_batched), same reductions."""
+    B, A = labels.shape
+    samples = _sample_batched(rpn.fg_bg_sampler, labels)
+    pos = torch.sort(torch.cat([p + b * A for b, (p, _) in enumerate(samples)]))[0]      # == where(cat(pos masks))
+    neg = torch.sort(torch.cat([n + b * A for b, (_, n) in enumerate(samples)]))[0]
+    sampled = torch.cat([pos, neg], dim=0)
+    objectness = objectness.flatten()
+    labels = labels.reshape(-1)
+    box_loss = F.smooth_l1_loss(pred_bbox_deltas[pos], regression_targets[pos], beta=1 / 9, reduction="sum") / (sampled.numel())
+    objectness_loss = F.binary_cross_entropy_with_logits(objectness[sampled], labels[sampled])
+    return objectness_loss, box_loss
+
+
+def select_training_samples_batched(roi_heads, proposals, targets):
+    """``RoIHeads.select_training_samples`` (TV roi_heads.py: add_gt_proposals, assign_targets_to_proposals, subsample, the
+    per-image gathers and BoxCoder.encode) for the whole batch.  Returns the same four per-image lists."""
+    roi_heads.check_targets(targets)
+    dtype, device = proposals[0].dtype, proposals[0].device
+    B = len(proposals)
+    gt_boxes = [t["boxes"].to(dtype) for t in targets]
+    gt_labels = [t["labels"] for t in targets]
+    G = max(1, max(int(g.shape[0]) for g in gt_boxes))
+    gt, present = _pad_rows(gt_boxes, G)
+    gl, _ = _pad_rows(gt_labels, G)
+    with_gt = [torch.cat((p, g)) for p, g in zip(proposals, gt_boxes)]      # add_gt_proposals
+    N = max(int(p.shape[0]) for p in with_gt)
+    P, p_present = _pad_rows(with_gt, N)
+    matches = _match_batched(roi_heads.proposal_matcher, gt, present, P)
+    clamped = matches.clamp(min=0)
+    labels = torch.gather(gl, 1, clamped).to(torch.int64)
+    labels = torch.where(matches == roi_heads.proposal_matcher.BELOW_LOW_THRESHOLD, labels.new_zeros(()), labels)
+    labels = torch.where(matches == roi_heads.proposal_matcher.BETWEEN_THRESHOLDS, labels.new_full((), -1), labels)
+    labels = torch.where(p_present, labels, labels.new_full((), -1))        # padding is ignored by the sampler
+    samples = _sample_batched(roi_heads.fg_bg_sampler, labels)
+    per_image = [int(p.shape[0] + n.shape[0]) for p, n in samples]
+    flat = torch.sort(torch.cat([torch.cat((p, n)) + b * N for b, (p, n) in enumerate(samples)]))[0]   # == where(pos | neg) per image
+    out_props = P.view(-1, 4)[flat]
+    out_labels = labels.view(-1)[flat]
+    out_matched = clamped.view(-1)[flat]
+    img_of = torch.div(flat, N, rounding_mode="floor")
+    matched_gt = gt.view(-1, 4)[img_of * G + out_matched]
+    weights = torch.as_tensor(roi_heads.box_coder.weights, dtype=dtype, device=device)
+    from torchvision.models.detection._utils import encode_boxes
+    regression_targets = encode_boxes(matched_gt, out_props, weights)
+    return (list(out_props.split(per_image)), list(out_matched.split(per_image)), list(out_labels.split(per_image)),
+            list(regression_targets.split(per_image)))
+
+
 def _batched_ok(n_boxes):
     return n_boxes <= ops.NMS_MAX_BOXES and n_boxes * 4 <= 100_000
 
@@ -306,9 +431,15 @@ def rpn_eval(model, images, features, targets):
         boxes, scores = model.rpn.filter_proposals(proposals, objectness, images.image_sizes, num_anchors_per_level)
     if targets is None:
         raise ValueError("targets should not be None")
-    labels, matched_gt_boxes = model.rpn.assign_targets_to_anchors(anchors, targets)
-    regression_targets = model.rpn.box_coder.encode(matched_gt_boxes, anchors)
-    loss_objectness, loss_rpn_box_reg = model.rpn.compute_loss(objectness, pred_bbox_deltas, labels, regression_targets)
+    if BATCHED_TAIL and proposals.is_cuda and all(a.shape == anchors[0].shape for a in anchors):
+        with torch.no_grad():
+            labels, matched_gt_boxes = assign_targets_to_anchors_batched(model.rpn, anchors, targets)
+            regression_targets = model.rpn.box_coder.encode_single(matched_gt_boxes.reshape(-1, 4), torch.cat(anchors, dim=0))
+        loss_objectness, loss_rpn_box_reg = rpn_compute_loss_batched(model.rpn, objectness, pred_bbox_deltas, labels, regression_targets)
+    else:
+        labels, matched_gt_boxes = model.rpn.assign_targets_to_anchors(anchors, targets)
+        regression_targets = model.rpn.box_coder.encode(matched_gt_boxes, anchors)
+        loss_objectness, loss_rpn_box_reg = model.rpn.compute_loss(objectness, pred_bbox_deltas, labels, regression_targets)
     return boxes, {"loss_objectness": loss_objectness, "loss_rpn_box_reg": loss_rpn_box_reg}
 
 
@@ -363,7 +494,11 @@ def roi_heads_eval(model, features, proposals, image_shapes, targets=None, train
             raise TypeError(f"target boxes must of float type, instead got {t['boxes'].dtype}")
         if t["labels"].dtype != torch.int64:
             raise TypeError(f"target labels must of int64 type, instead got {t['labels'].dtype}")
-    proposals, matched_idxs, labels, regression_targets = model.roi_heads.select_training_samples(proposals, targets)
+    if BATCHED_TAIL and proposals[0].is_cuda:
+        with torch.no_grad():
+            proposals, matched_idxs, labels, regression_targets = select_training_samples_batched(model.roi_heads, proposals, targets)
+    else:
+        proposals, matched_idxs, labels, regression_targets = model.roi_heads.select_training_samples(proposals, targets)
     box_features = model.roi_heads.box_roi_pool(features, proposals, image_shapes)
     box_features = model.roi_heads.box_head(box_features)
     class_logits, box_regression = model.roi_heads.box_predictor(box_features)

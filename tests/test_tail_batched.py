@@ -1,0 +1,66 @@
+"""Whole-batch target assignment / sampling (hallucidet_b200.detection) against torchvision's per-image loops: same labels,
+same matched boxes, same random samples (generator consumed identically), same losses.  Runs on the CPU (host logic) and,
+marked gpu, on CUDA, where the CUDA generator and the CUDA arg-max tie rules are what matters."""
+import pytest
+import torch
+
+from oracle import detector as odet
+
+
+def _setup(device):
+    from torchvision.models.detection.image_list import ImageList
+    det = odet.build_detector("fasterrcnn", seed=1).to(device)
+    g = torch.Generator().manual_seed(0)
+    B = 3
+    x = torch.rand(B, 3, 128, 160, generator=g).to(device)
+    with torch.no_grad():
+        feats = list(det.backbone(x).values())
+    il = ImageList(x, [(128, 160)] * B)
+    anchors = det.rpn.anchor_generator(il, feats)
+
+    def mk(n):
+        xy, wh = torch.rand(n, 2, generator=g) * 80, torch.rand(n, 2, generator=g) * 60 + 8
+        return {"boxes": torch.cat([xy, xy + wh], 1).to(device), "labels": torch.ones(n, dtype=torch.int64, device=device)}
+    targets = [mk(3), {"boxes": torch.zeros(0, 4, device=device), "labels": torch.zeros(0, dtype=torch.int64, device=device)}, mk(5)]
+    return det, g, anchors, targets
+
+
+def _check(device):
+    from hallucidet_b200 import detection as D
+    det, g, anchors, targets = _setup(device)
+    B, A = len(anchors), anchors[0].shape[0]
+    la, ma = det.rpn.assign_targets_to_anchors(anchors, targets)
+    lb, mb = D.assign_targets_to_anchors_batched(det.rpn, anchors, targets)
+    assert all(torch.equal(a, b) for a, b in zip(la, lb)) and all(torch.equal(a, b) for a, b in zip(ma, mb))
+    assert sum(int((l == 1).sum()) for l in la) > 0 and sum(int((l == -1).sum()) for l in la) > 0
+    obj = torch.randn(B * A, 1, generator=g).to(device)
+    deltas = torch.randn(B * A, 4, generator=g).to(device)
+    rt = det.rpn.box_coder.encode(ma, anchors)
+    torch.manual_seed(5)
+    l1 = det.rpn.compute_loss(obj, deltas, la, rt)
+    after1 = torch.rand(1, device=device)
+    rtb = det.rpn.box_coder.encode_single(mb.reshape(-1, 4), torch.cat(anchors, 0))
+    torch.manual_seed(5)
+    l2 = D.rpn_compute_loss_batched(det.rpn, obj, deltas, lb, rtb)
+    after2 = torch.rand(1, device=device)
+    assert torch.equal(l1[0], l2[0]) and torch.equal(l1[1], l2[1])
+    assert torch.equal(after1, after2)                   # the generator is left in the same state
+    # RoI sampling: ragged proposal counts, one image without ground truth, more candidates than the 512-sample budget
+    for sizes in ((50, 37, 64), (900, 1000, 700)):
+        props = [torch.cat([torch.rand(n, 2, generator=g) * 100, torch.rand(n, 2, generator=g) * 60 + 100], 1).to(device) for n in sizes]
+        torch.manual_seed(9)
+        r1 = det.roi_heads.select_training_samples([p.clone() for p in props], targets)
+        torch.manual_seed(9)
+        r2 = D.select_training_samples_batched(det.roi_heads, [p.clone() for p in props], targets)
+        for a, b in zip(r1, r2):
+            assert [x.shape for x in a] == [y.shape for y in b]
+            assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_batched_targets_and_sampling_cpu():
+    _check("cpu")
+
+
+@pytest.mark.gpu
+def test_batched_targets_and_sampling_cuda():
+    _check("cuda")
