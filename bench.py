@@ -26,6 +26,14 @@ GFLOP_PER_IMAGE = 459.702        # SURVEY.md 8(d) / BASELINE.md section 2: U-Net
 METRIC = "train images/s (640x512 IR, bf16)"
 
 
+def load_traffic():
+    """DRAM bytes of the largest tcgen05 conv launch from the committed `ncu --set full` capture (profiles/)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+    except Exception:
+        return {}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -213,7 +221,7 @@ def main():
     ops.PROFILE = []
     step_resident()
     torch.cuda.synchronize()
-    prof = [(name, flops, a.elapsed_time(b), desc) for name, flops, a, b, desc in ops.PROFILE]
+    prof = [(name, flops, a.elapsed_time(b), desc, nbytes) for name, flops, a, b, desc, nbytes in ops.PROFILE]
     if rank == 0 and os.environ.get("HD_PROFILE_DUMP"):
         json.dump(prof, open(os.environ["HD_PROFILE_DUMP"], "w"))
     ops.PROFILE = None
@@ -233,11 +241,17 @@ def main():
         value = world * B * args.steps / (ms / 1e3)
         e2e_value = world * B * args.steps / (ms_e2e / 1e3)
         burst, sustained, hbm, which = load_peaks()
+        # dominant kernels: the tcgen05 implicit GEMMs (tensor bound); the 16/32-channel layers run on the halo-patch
+        # mma.sync kernels and are HBM bound -- reported separately in roofline_narrow
         conv = [p for p in prof if p[0] in ("conv_fwd", "conv_dgrad", "conv_wgrad")]
+        narrow = [p for p in prof if p[0].endswith("_narrow")]
         conv_flops = sum(p[1] for p in conv)
         conv_ms = sum(p[2] for p in conv)
         achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         gemm_only = [p for p in prof if p[0] in ("conv_fwd", "conv_dgrad")]
+        narrow_ms = sum(p[2] for p in narrow)
+        narrow_gbs = sum(p[4] for p in narrow) / (narrow_ms * 1e-3) / 1e9 if narrow_ms > 0 else 0.0
+        traffic = load_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -254,12 +268,17 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel + wgrad_gemm_kernel (tcgen05 implicit GEMM)",
                          "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "peak_source": which,
-                         "traffic": None, "conv_launches_per_step": len(conv), "conv_ms_per_step": conv_ms,
+                         "traffic": traffic.get("dram_bytes_per_launch"), "traffic_launch": traffic.get("launch"),
+                         "traffic_algorithmic_bytes": traffic.get("algorithmic_bytes"),
+                         "conv_launches_per_step": len(conv), "conv_ms_per_step": conv_ms,
                          "conv_gflop_per_step": conv_flops / 1e9,
                          "fwd_dgrad_tflops": (sum(p[1] for p in gemm_only) / (sum(p[2] for p in gemm_only) * 1e-3) / 1e12) if gemm_only else None,
                          "all_kernels_ms_per_step": sum(p[2] for p in prof),
                          "step_tflops_algorithmic": GFLOP_PER_IMAGE * value / world / 1e3,
                          "step_frac_of_sustained_peak": GFLOP_PER_IMAGE * value / world / 1e3 / sustained},
+            "roofline_narrow": {"bound": "hbm", "kernel": "narrow_conv_kernel + narrow_wgrad_kernel (16/32-channel 3x3 layers, halo patch + mma.sync)",
+                                "achieved": narrow_gbs, "peak": hbm, "unit": "GB/s", "frac": narrow_gbs / hbm if hbm else None,
+                                "launches_per_step": len(narrow), "ms_per_step": narrow_ms},
             "loss": host_loss[-1] if host_loss else None,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -36,7 +36,7 @@ class _Timed:
         if PROFILE is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            PROFILE.append((self.name, self.flops, self.e0, e1, self.desc))
+            PROFILE.append((self.name, self.flops, self.e0, e1, self.desc, getattr(self, "bytes", 0.0)))
         return False
 
 
@@ -100,13 +100,51 @@ def _conv_flops(a, kind):
     return 2.0 * pix * cin * cout * k2
 
 
+def _is_narrow(a, kind):
+    """Mirror of narrow_conv_eligible / narrow_wgrad_eligible (csrc/narrow_conv.cu): which kernel a launch runs on.
+    Only used to label PROFILE records."""
+    if a.kh != 3 or a.stride != 1 or a.x1.c or a.x0.c not in (16, 32) or a.y0.c not in (16, 32):
+        return False
+    if kind == "wgrad":
+        return True
+    if a.y1.c or a.add or a.mask or (kind == "dgrad" and a.stats) or (a.stats and a.out_f32_nchw):
+        return False
+    return True
+
+
+def _conv_bytes(a, kind):
+    """Algorithmic HBM bytes of a launch: every operand element once (bf16 activations, fp32 side outputs / gradients)."""
+    px = a.x0.n * a.x0.h * a.x0.w
+    py = a.y0.n * a.y0.h * a.y0.w
+    b = 2.0 * px * (a.x0.c + a.x1.c)
+    if kind == "wgrad":
+        return b + 2.0 * py * a.y0.c + 4.0 * a.kh * a.kw * (a.x0.c + a.x1.c) * a.y0.c
+    if a.store_bf16:
+        b += 2.0 * py * (a.y0.c + a.y1.c)
+    if a.out_f32_nchw:
+        b += 4.0 * py * a.out_f32_channels
+    if a.add:
+        b += 2.0 * py * a.y0.c
+    if a.mask:
+        b += 2.0 * py * a.y0.c
+    return b + 2.0 * a.kh * a.kw * (a.x0.c + a.x1.c) * (a.y0.c + a.y1.c)
+
+
+def _conv_timed(a, kind):
+    if PROFILE is None:
+        return _Timed("conv_" + kind)
+    t = _Timed("conv_" + kind + ("_narrow" if _is_narrow(a, kind) else ""), _conv_flops(a, kind), _conv_desc(a))
+    t.bytes = _conv_bytes(a, kind)
+    return t
+
+
 def _conv_desc(a):
     return (f"x0[{a.x0.n},{a.x0.h},{a.x0.w},{a.x0.c}] x1c{a.x1.c} y0[{a.y0.n},{a.y0.h},{a.y0.w},{a.y0.c}] y1c{a.y1.c} "
             f"k{a.kh} s{a.stride}")
 
 
 def conv_fwd(args):
-    with _Timed("conv_fwd", _conv_flops(args, "fwd") if PROFILE is not None else 0.0, _conv_desc(args) if PROFILE is not None else ""):
+    with _conv_timed(args, "fwd"):
         check(_lib.load().hd_conv_fwd(ctypes.byref(args), _stream()), "hd_conv_fwd")
 
 
@@ -126,12 +164,12 @@ def conv_fwd_tiles(x0, k=3, stride=1, cout=None):
 
 
 def conv_dgrad(args):
-    with _Timed("conv_dgrad", _conv_flops(args, "dgrad") if PROFILE is not None else 0.0, _conv_desc(args) if PROFILE is not None else ""):
+    with _conv_timed(args, "dgrad"):
         check(_lib.load().hd_conv_dgrad(ctypes.byref(args), _stream()), "hd_conv_dgrad")
 
 
 def conv_wgrad(args):
-    with _Timed("conv_wgrad", _conv_flops(args, "wgrad") if PROFILE is not None else 0.0, _conv_desc(args) if PROFILE is not None else ""):
+    with _conv_timed(args, "wgrad"):
         check(_lib.load().hd_conv_wgrad(ctypes.byref(args), _stream()), "hd_conv_wgrad")
 
 

@@ -11,6 +11,7 @@ from oracle import step as ostep  # noqa: E402
 B = int(os.environ.get("HD_BATCH", "8"))
 dev = torch.device("cuda", 0)
 torch.backends.cudnn.benchmark = True
+torch.backends.cuda.matmul.allow_tf32 = True   # as bench.py
 tr = HalluciDetTrainer(detector_name="fasterrcnn", size=640, seed=123, device=dev, use_cuda_graph=False)
 ir, rgb, targets = ostep.synthetic_batch(B, 512, 640, seed=123, device=dev)
 for _ in range(3):
