@@ -218,9 +218,13 @@ def main():
     torch.cuda.synchronize()
     launches_per_step = ops.LAUNCHES
     # per-launch device time of the conv GEMM kernels (CUDA events on the launching stream), for the roofline
+    # (weight gradients normally overlap the dgrad chain on a side stream; serialised here so that each launch is timed alone)
+    from hallucidet_b200 import unet as _unet
+    side_was, _unet.SIDE_STREAM_WGRAD = _unet.SIDE_STREAM_WGRAD, False
     ops.PROFILE = []
     step_resident()
     torch.cuda.synchronize()
+    _unet.SIDE_STREAM_WGRAD = side_was
     prof = [(name, flops, a.elapsed_time(b), desc, nbytes) for name, flops, a, b, desc, nbytes in ops.PROFILE]
     if rank == 0 and os.environ.get("HD_PROFILE_DUMP"):
         json.dump(prof, open(os.environ["HD_PROFILE_DUMP"], "w"))

@@ -14,6 +14,8 @@ Reference semantics followed: src/segmentation_models/base/model.py:24-38, encod
 decoders/unet/decoder.py:7-8,38-46,111-124, base/modules.py:10-47, base/heads.py:21-27,
 base/initialization.py:4-27; TV models/resnet.py:59-105 (BasicBlock).
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -172,6 +174,9 @@ class _UnetFunction(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------------
 # execution engine: static buffers + kernel program for one (B, H, W, mode)
 # ------------------------------------------------------------------------------------------------------
+SIDE_STREAM_WGRAD = os.environ.get("HD_SIDE_WGRAD", "1") != "0"
+
+
 class _Layer:
     """One convolution (+ optional BatchNorm) of the U-Net with its packed operands and saved tensors."""
 
@@ -269,6 +274,7 @@ class _UnetEngine:
         for l in self.all_layers:
             l.dw = self.dw_flat[l.dw_off:l.dw_off + l.dw_rows * l.dw_cols]
         self.grad_bufs = {}
+        self.side_stream, self.side_used = None, False
         self.graphs = {}
         self.sigmoid = None
         self.generation = 0
@@ -428,9 +434,26 @@ class _UnetEngine:
                          relu_scale=rs, relu_shift=rb)
         return dz
 
+    def _on_side(self, fn):
+        """Run ``fn`` (launches only) on the engine's side stream, ordered after everything enqueued so far on the current
+        stream.  The weight gradients are leaves of the backward dependency graph (nothing reads them before the end), so
+        they overlap the dgrad -> BN-backward critical path and fill the SMs the small layers leave idle.  Works eagerly
+        and under CUDA-graph capture (fork here, join at the end of ``_backward_impl``)."""
+        if not SIDE_STREAM_WGRAD:
+            fn()
+            return
+        if self.side_stream is None:
+            self.side_stream = torch.cuda.Stream(device=self.device)
+        self.side_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side_stream):
+            fn()
+        self.side_used = True
+
     def _wgrad(self, l, x0, dz, x1=None):
-        ops.conv_wgrad(ops.conv_args(x0, dz, k=l.k, stride=l.stride, x1=x1, dw=l.dw, algo_cout=l.cout))
-        ops.unpack_wgrad(l.dw, self.grad_views[l.name + ".weight"], l.cout, l.cin, l.k, l.cin, l.k * l.k * l.cin)
+        def launch():
+            ops.conv_wgrad(ops.conv_args(x0, dz, k=l.k, stride=l.stride, x1=x1, dw=l.dw, algo_cout=l.cout))
+            ops.unpack_wgrad(l.dw, self.grad_views[l.name + ".weight"], l.cout, l.cin, l.k, l.cin, l.k * l.k * l.cin)
+        self._on_side(launch)
 
     def _backward_impl(self):
         dhal = self.dhal_in
@@ -489,5 +512,10 @@ class _UnetEngine:
         ops.maxpool_bwd(self.a_stem, self.p0, g, g_stem, add=skip_grads[3])
         zs = st.z.view(1, 1, -1, 64)
         dzs = self._bn_bwd(st, g_stem.view(1, 1, -1, 64), self.a_stem.view(1, 1, -1, 64), z=zs, direct_relu=True)
-        ops.conv_wgrad(ops.conv_args(self.patches, dzs, k=1, dw=st.dw, algo_cin=147))
-        ops.unpack_wgrad(st.dw, gv["encoder.conv1.weight"], 64, 3, 7, 3, ops.STEM_KPAD)
+        def stem_wgrad():
+            ops.conv_wgrad(ops.conv_args(self.patches, dzs, k=1, dw=st.dw, algo_cin=147))
+            ops.unpack_wgrad(st.dw, gv["encoder.conv1.weight"], 64, 3, 7, 3, ops.STEM_KPAD)
+        self._on_side(stem_wgrad)
+        if self.side_used:                                   # join: the gradients are complete when the backward returns
+            torch.cuda.current_stream().wait_stream(self.side_stream)
+            self.side_used = False
