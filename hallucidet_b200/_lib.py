@@ -50,8 +50,8 @@ PROTOTYPES = {
     "hd_bn_bwd_reduce": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p],
     "hd_bn_bwd_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
                         c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p],
-    "hd_maxpool_fwd": [P(HdAct), P(HdAct), c_void_p],
-    "hd_maxpool_bwd": [P(HdAct), P(HdAct), c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "hd_maxpool_fwd": [P(HdAct), P(HdAct), c_void_p, c_int, c_void_p],
+    "hd_maxpool_bwd": [P(HdAct), P(HdAct), c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
     "hd_upsample2x_fwd": [P(HdAct), P(HdAct), c_void_p],
     "hd_upsample2x_bwd": [P(HdAct), P(HdAct), c_void_p],
     "hd_add_nearest_fwd": [P(HdAct), P(HdAct), c_void_p],

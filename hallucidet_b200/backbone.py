@@ -144,6 +144,7 @@ class _BackboneEngine:
         _FConv.__init__(st, self, body.conv1, body.bn1, (H, W), relu=True, stem=True)
         self.patches = torch.empty(1, 1, B * h2 * w2, ops.STEM_KPAD, dtype=torch.bfloat16, device=device)
         self.p0 = self.new_act(h2 // 2, w2 // 2, 64)
+        self.p0_idx = torch.empty(B, h2 // 2, w2 // 2, 64, dtype=torch.uint8, device=device)   # max-pool arg-max (ReLU mask folded in)
         # body
         self.blocks = []
         hw = (h2 // 2, w2 // 2)
@@ -230,7 +231,7 @@ class _BackboneEngine:
         st = self.stem
         ops.stem_im2col(self.x_in, self.patches)
         ops.conv_fwd(ops.conv_args(self.patches, st.y.view(1, 1, -1, 64), st.packed.w_fwd, k=1, bias=st.bias, relu=True, algo_cin=147))
-        ops.maxpool_fwd(st.y, self.p0)
+        ops.maxpool_fwd(st.y, self.p0, idx=self.p0_idx, mask_nonpositive=True)
         x = self.p0
         for blk in self.blocks:
             c1, c2, c3, cd = blk["c1"], blk["c2"], blk["c3"], blk["cd"]
@@ -342,7 +343,7 @@ class _BackboneEngine:
         # stem: max-pool backward with the stem ReLU mask, patch GEMM with W^T, col2im
         st = self.stem
         g_stem = self.gbuf(("g", "stem"), st.y)
-        ops.maxpool_bwd(st.y, self.p0, g_next, g_stem, relu_mask=True)
+        ops.maxpool_bwd(st.y, self.p0, g_next, g_stem, idx=self.p0_idx)
         dpatch = self.gbuf(("dpatch", 0), self.patches)
         ops.conv_fwd(ops.conv_args(g_stem.view(1, 1, -1, 64), dpatch, st.packed.w_t, k=1, algo_cout=147))
         ops.stem_col2im(dpatch, self.dx)

@@ -83,30 +83,43 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, float* __restr
 // -------------------------------------------------------------------------------------------------
 // stem 7x7/2 patches
 // -------------------------------------------------------------------------------------------------
-__global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ patches, int n, int h, int w,
-                                   int k_pad) {
+// One CTA = 8 x 32 output pixels: the (2*8+5) x (2*32+5) x 3 input patch is staged once in shared memory as HWC bf16 (so the
+// 21 values of a filter row are contiguous), then every thread assembles 8-value groups of the patch rows and writes them
+// with coalesced 16-byte stores.  (A direct gather issued 8 scattered global loads per 16 output bytes.)
+constexpr int kI2cTH = 8, kI2cTW = 32, kI2cPH = 2 * kI2cTH + 5, kI2cPW = 2 * kI2cTW + 5, kI2cPitch = kI2cPW * 3 + 1;
+
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ patches, int n,
+                                                          int h, int w, int k_pad) {
+    __shared__ __nv_bfloat16 sp[kI2cPH * kI2cPitch];
     const int ho = h / 2, wo = w / 2, groups = k_pad / 8;
-    const long total = static_cast<long>(n) * ho * wo * groups;
-    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long>(gridDim.x) * blockDim.x) {
-        const int g = static_cast<int>(i % groups);
-        const long pix = i / groups;
-        const int ow = static_cast<int>(pix % wo), oh = static_cast<int>((pix / wo) % ho), b = static_cast<int>(pix / (static_cast<long>(wo) * ho));
+    const int tiles_w = (wo + kI2cTW - 1) / kI2cTW, tiles_h = (ho + kI2cTH - 1) / kI2cTH;
+    const int tile = blockIdx.x;
+    const int b = tile / (tiles_w * tiles_h), t2 = tile - b * tiles_w * tiles_h;
+    const int oh0 = (t2 / tiles_w) * kI2cTH, ow0 = (t2 % tiles_w) * kI2cTW;
+    const int ih0 = 2 * oh0 - 3, iw0 = 2 * ow0 - 3;
+    for (int q = threadIdx.x; q < 3 * kI2cPH * kI2cPW; q += blockDim.x) {
+        const int col = q % kI2cPW, t3 = q / kI2cPW, row = t3 % kI2cPH, c = t3 / kI2cPH;
+        const int ih = ih0 + row, iw = iw0 + col;
+        float v = 0.f;
+        if (ih >= 0 && ih < h && iw >= 0 && iw < w) v = __ldg(x + ((static_cast<long>(b) * 3 + c) * h + ih) * w + iw);
+        sp[row * kI2cPitch + col * 3 + c] = __float2bfloat16(v);
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < kI2cTH * kI2cTW * groups; q += blockDim.x) {
+        const int g = q % groups, p = q / groups;
+        const int ohl = p / kI2cTW, owl = p - ohl * kI2cTW;
+        const int oh = oh0 + ohl, ow = ow0 + owl;
+        if (oh >= ho || ow >= wo) continue;
         float f[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int k = g * 8 + j;
-            float v = 0.f;
-            if (k < 147) {
-                const int c = k % 3, tap = k / 3, r = tap / 7, s = tap % 7;
-                const int ih = 2 * oh + r - 3, iw = 2 * ow + s - 3;
-                if (ih >= 0 && ih < h && iw >= 0 && iw < w) v = __ldg(x + ((static_cast<long>(b) * 3 + c) * h + ih) * w + iw);
-            }
-            f[j] = v;
+            const int k = g * 8 + j;                           // k = (r*7 + s)*3 + c = r*21 + (s*3 + c)
+            const int r = k / 21, rem = k - r * 21;
+            f[j] = k < 147 ? __bfloat162float(sp[(2 * ohl + r) * kI2cPitch + 2 * owl * 3 + rem]) : 0.f;
         }
         bf8 o;
         o.pack(f);
-        o.store(patches + pix * k_pad + g * 8);
+        o.store(patches + ((static_cast<long>(b) * ho + oh) * wo + ow) * k_pad + g * 8);
     }
 }
 
@@ -329,8 +342,8 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const 
 // -------------------------------------------------------------------------------------------------
 // max-pool 3x3 stride 2 pad 1 (NHWC)
 // -------------------------------------------------------------------------------------------------
-__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int h, int w,
-                                   int C) {
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                   unsigned char* __restrict__ idx, int mask_nonpositive, int n, int h, int w, int C) {
     const int ho = h / 2, wo = w / 2, G = C / 8;
     const long total = static_cast<long>(n) * ho * wo * G;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
@@ -339,8 +352,9 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
         const long pix = i / G;
         const int ow = static_cast<int>(pix % wo), oh = static_cast<int>((pix / wo) % ho), b = static_cast<int>(pix / (static_cast<long>(wo) * ho));
         float m[8];
+        unsigned am[8];                                    // window position (r*3+s) of the FIRST maximum, as ATen
 #pragma unroll
-        for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+        for (int j = 0; j < 8; ++j) { m[j] = -INFINITY; am[j] = 15u; }
         for (int r = 0; r < 3; ++r) {
             const int ih = 2 * oh + r - 1;
             if (ih < 0 || ih >= h) continue;
@@ -352,12 +366,70 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
                 float f[8];
                 v.unpack(f);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+                for (int j = 0; j < 8; ++j)
+                    if (f[j] > m[j]) { m[j] = f[j]; am[j] = r * 3 + s; }
             }
         }
         bf8 o;
         o.pack(m);
         o.store(y + pix * C + g * 8);
+        if (idx != nullptr) {
+            unsigned lo = 0, hi = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                lo |= ((mask_nonpositive && !(m[j] > 0.f)) ? 15u : am[j]) << (8 * j);
+                hi |= ((mask_nonpositive && !(m[j + 4] > 0.f)) ? 15u : am[j + 4]) << (8 * j);
+            }
+            *reinterpret_cast<uint2*>(idx + pix * C + g * 8) = make_uint2(lo, hi);
+        }
+    }
+}
+
+// backward from the stored arg-max positions: dx[ih,iw] = (add) + sum of dy over the (<= 4) windows whose arg-max is here
+__global__ void maxpool_bwd_idx_kernel(const unsigned char* __restrict__ idx, const __nv_bfloat16* __restrict__ dy,
+                                       const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ dx, int n, int h,
+                                       int w, int C) {
+    const int ho = h / 2, wo = w / 2, G = C / 8;
+    const long total = static_cast<long>(n) * h * w * G;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % G);
+        const long pix = i / G;
+        const int iw = static_cast<int>(pix % w), ih = static_cast<int>((pix / w) % h), b = static_cast<int>(pix / (static_cast<long>(w) * h));
+        float acc[8];
+        if (add) {
+            bf8 av;
+            av.load(add + pix * C + g * 8);
+            av.unpack(acc);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        }
+        for (int oh = ih / 2; oh <= (ih + 1) / 2; ++oh) {      // windows with 2*oh-1 <= ih <= 2*oh+1
+            if (oh >= ho) continue;
+            for (int ow = iw / 2; ow <= (iw + 1) / 2; ++ow) {
+                if (ow >= wo) continue;
+                const long opix = (static_cast<long>(b) * ho + oh) * wo + ow;
+                const unsigned pos = (ih - (2 * oh - 1)) * 3 + (iw - (2 * ow - 1));
+                const uint2 am = *reinterpret_cast<const uint2*>(idx + opix * C + g * 8);
+                unsigned hit = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    hit |= (((am.x >> (8 * j)) & 0xffu) == pos) ? (1u << j) : 0u;
+                    hit |= (((am.y >> (8 * j)) & 0xffu) == pos) ? (1u << (j + 4)) : 0u;
+                }
+                if (!hit) continue;
+                bf8 dv;
+                dv.load(dy + opix * C + g * 8);
+                float df[8];
+                dv.unpack(df);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (hit & (1u << j)) acc[j] += df[j];
+            }
+        }
+        bf8 o;
+        o.pack(acc);
+        o.store(dx + pix * C + g * 8);
     }
 }
 
@@ -814,8 +886,9 @@ extern "C" int hd_unpack_wgrad(const float* dw, float* g, int cout, int cin, int
 
 extern "C" int hd_stem_im2col(const float* x, void* patches, int n, int h, int w, int k_pad, hd_stream st) {
     HD_CHECK_ARG(x && patches && h % 2 == 0 && w % 2 == 0 && k_pad >= 152 && k_pad % 8 == 0);
-    stem_im2col_kernel<<<ew_blocks(static_cast<long>(n) * (h / 2) * (w / 2) * (k_pad / 8)), kEwThreads, 0,
-                         static_cast<cudaStream_t>(st)>>>(x, static_cast<__nv_bfloat16*>(patches), n, h, w, k_pad);
+    const int ho = h / 2, wo = w / 2;
+    const int tiles = n * ((ho + kI2cTH - 1) / kI2cTH) * ((wo + kI2cTW - 1) / kI2cTW);
+    stem_im2col_kernel<<<tiles, 256, 0, static_cast<cudaStream_t>(st)>>>(x, static_cast<__nv_bfloat16*>(patches), n, h, w, k_pad);
     HD_LAUNCH_OK();
     return HD_OK;
 }
@@ -879,20 +952,33 @@ extern "C" int hd_bn_bwd_apply(const void* dy, const void* yrelu, const float* r
     return HD_OK;
 }
 
-extern "C" int hd_maxpool_fwd(const hd_act* x, const hd_act* y, hd_stream st) {
+extern "C" int hd_maxpool_fwd(const hd_act* x, const hd_act* y, void* idx, int mask_nonpositive, hd_stream st) {
     HD_CHECK_ARG(x && y && x->ptr && y->ptr && x->c % 8 == 0 && x->c == y->c && x->h % 2 == 0 && x->w % 2 == 0);
     HD_CHECK_ARG(y->h == x->h / 2 && y->w == x->w / 2 && y->n == x->n);
+    HD_CHECK_ARG(idx == nullptr || (reinterpret_cast<uintptr_t>(idx) & 7) == 0);
     maxpool_fwd_kernel<<<ew_blocks(static_cast<long>(y->n) * y->h * y->w * (y->c / 8)), kEwThreads, 0,
                          static_cast<cudaStream_t>(st)>>>(static_cast<const __nv_bfloat16*>(x->ptr),
-                                                          static_cast<__nv_bfloat16*>(y->ptr), x->n, x->h, x->w, x->c);
+                                                          static_cast<__nv_bfloat16*>(y->ptr), static_cast<unsigned char*>(idx),
+                                                          mask_nonpositive, x->n, x->h, x->w, x->c);
     HD_LAUNCH_OK();
     return HD_OK;
 }
 
 extern "C" int hd_maxpool_bwd(const hd_act* x, const hd_act* y, const void* dy, const void* add, void* dx, int relu_mask,
-                              hd_stream st) {
-    HD_CHECK_ARG(x && y && x->ptr && y->ptr && dy && dx && x->c % 8 == 0 && x->c == y->c);
+                              const void* idx, hd_stream st) {
+    HD_CHECK_ARG(x && y && dy && dx && x->c % 8 == 0 && x->c == y->c);
     HD_CHECK_ARG(y->h == x->h / 2 && y->w == x->w / 2 && y->n == x->n);
+    if (idx != nullptr) {
+        // arg-max positions stored by hd_maxpool_fwd (with mask_nonpositive when relu_mask semantics are wanted): x / y are
+        // not read at all
+        maxpool_bwd_idx_kernel<<<ew_blocks(static_cast<long>(x->n) * x->h * x->w * (x->c / 8)), kEwThreads, 0,
+                                 static_cast<cudaStream_t>(st)>>>(
+            static_cast<const unsigned char*>(idx), static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(add),
+            static_cast<__nv_bfloat16*>(dx), x->n, x->h, x->w, x->c);
+        HD_LAUNCH_OK();
+        return HD_OK;
+    }
+    HD_CHECK_ARG(x->ptr && y->ptr);
     maxpool_bwd_kernel<<<ew_blocks(static_cast<long>(x->n) * x->h * x->w * (x->c / 8)), kEwThreads, 0,
                          static_cast<cudaStream_t>(st)>>>(
         static_cast<const __nv_bfloat16*>(x->ptr), static_cast<const __nv_bfloat16*>(y->ptr),

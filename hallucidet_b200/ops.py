@@ -245,17 +245,21 @@ def bn_bwd_apply(dy, y_relu, z, mean, invstd, gamma, sums, dz, g_out=None, dgamm
               "hd_bn_bwd_apply")
 
 
-def maxpool_fwd(x, y):
+def maxpool_fwd(x, y, idx=None, mask_nonpositive=False):
+    """idx: optional uint8 [N, H/2, W/2, C] receiving the arg-max window position of every output element (for
+    maxpool_bwd(idx=...)); mask_nonpositive folds a following ReLU mask into it."""
     ax, ay = act(x), act(y)
+    assert idx is None or (idx.dtype == torch.uint8 and idx.is_contiguous() and tuple(idx.shape) == tuple(y.shape))
     with _Timed("maxpool_fwd"):
-        check(_lib.load().hd_maxpool_fwd(ctypes.byref(ax), ctypes.byref(ay), _stream()), "hd_maxpool_fwd")
+        check(_lib.load().hd_maxpool_fwd(ctypes.byref(ax), ctypes.byref(ay), _ptr(idx), int(mask_nonpositive), _stream()), "hd_maxpool_fwd")
 
 
-def maxpool_bwd(x, y, dy, dx, add=None, relu_mask=False):
+def maxpool_bwd(x, y, dy, dx, add=None, relu_mask=False, idx=None):
     ax, ay = act(x), act(y)
+    assert idx is None or not relu_mask, "with idx the ReLU mask is folded in by maxpool_fwd(mask_nonpositive=True)"
     with _Timed("maxpool_bwd"):
-        check(_lib.load().hd_maxpool_bwd(ctypes.byref(ax), ctypes.byref(ay), _ptr(dy), _ptr(add), _ptr(dx), int(relu_mask), _stream()),
-              "hd_maxpool_bwd")
+        check(_lib.load().hd_maxpool_bwd(ctypes.byref(ax), ctypes.byref(ay), _ptr(dy), _ptr(add), _ptr(dx), int(relu_mask), _ptr(idx),
+                                         _stream()), "hd_maxpool_bwd")
 
 
 def upsample2x_fwd(x, y):

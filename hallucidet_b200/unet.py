@@ -218,6 +218,7 @@ class _UnetEngine:
         self.patches = torch.empty(1, 1, B * h2 * w2, ops.STEM_KPAD, dtype=torch.bfloat16, device=device)
         self.a_stem = self.new_act(h2, w2, 64)
         self.p0 = self.new_act(h2 // 2, w2 // 2, 64)
+        self.p0_idx = torch.empty(B, h2 // 2, w2 // 2, 64, dtype=torch.uint8, device=device)   # max-pool arg-max positions
         # ---- encoder layers
         self.blocks = []
         hw, cin = (h2 // 2, w2 // 2), 64
@@ -389,7 +390,7 @@ class _UnetEngine:
             ops.bn_apply(zs, st.scale, st.shift, a_stem_flat, relu=True)
         else:
             ops.conv_fwd(ops.conv_args(self.patches, a_stem_flat, st.packed.w_fwd, k=1, bias=st.bias, relu=True, algo_cin=147))
-        ops.maxpool_fwd(self.a_stem, self.p0)
+        ops.maxpool_fwd(self.a_stem, self.p0, idx=self.p0_idx if self.training else None)
         x_in = self.p0
         feats = {1: self.a_stem}
         for blk in self.blocks:
@@ -509,7 +510,7 @@ class _UnetEngine:
         # ---- stem: max-pool backward (+ decoder skip of f1), BN backward, weight gradient through the patch GEMM
         st = self.stem
         g_stem = self.gbuf(("g", "stem"), self.a_stem)
-        ops.maxpool_bwd(self.a_stem, self.p0, g, g_stem, add=skip_grads[3])
+        ops.maxpool_bwd(self.a_stem, self.p0, g, g_stem, add=skip_grads[3], idx=self.p0_idx)
         zs = st.z.view(1, 1, -1, 64)
         dzs = self._bn_bwd(st, g_stem.view(1, 1, -1, 64), self.a_stem.view(1, 1, -1, 64), z=zs, direct_relu=True)
         def stem_wgrad():

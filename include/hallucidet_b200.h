@@ -120,9 +120,13 @@ int hd_bn_bwd_apply(const void* dy, const void* y_relu, const float* relu_scale,
 
 /* ---- memory-bound glue ------------------------------------------------------------------------------ */
 /* MaxPool2d(3,2,1) after the stem ReLU (encoders/resnet.py:51, TV: models/resnet.py:199). */
-int hd_maxpool_fwd(const hd_act* x, const hd_act* y, hd_stream stream);
-/* dx = (add ? add : 0) + scatter of dy to the arg-max taps (first max in window order, as ATen); optional ReLU mask. */
-int hd_maxpool_bwd(const hd_act* x, const hd_act* y, const void* dy, const void* add, void* dx, int relu_mask, hd_stream stream);
+/* idx (optional, [n][h/2][w/2][c] bytes, 8-byte aligned): window position r*3+s of the first maximum of every output
+ * element, 15 = "nobody" (mask_nonpositive: also when the maximum is <= 0, i.e. a following ReLU mask would kill it). */
+int hd_maxpool_fwd(const hd_act* x, const hd_act* y, void* idx, int mask_nonpositive, hd_stream stream);
+/* dx = (add ? add : 0) + scatter of dy to the arg-max taps (first max in window order, as ATen); optional ReLU mask
+ * (x > 0).  With idx (from hd_maxpool_fwd; pass mask_nonpositive there instead of relu_mask here) x / y are not read. */
+int hd_maxpool_bwd(const hd_act* x, const hd_act* y, const void* dy, const void* add, void* dx, int relu_mask,
+                   const void* idx, hd_stream stream);
 /* Nearest upsample x2 (decoders/unet/decoder.py:7-8): y[h][w] = x[h/2][w/2]; backward = 2x2 sum. */
 int hd_upsample2x_fwd(const hd_act* x, const hd_act* y, hd_stream stream);
 int hd_upsample2x_bwd(const hd_act* dy, const hd_act* dx, hd_stream stream);

@@ -261,15 +261,22 @@ def test_pack_weight_layouts():
     assert torch.equal(pk.w_t, pk.w_fwd.t())
 
 
-def test_stem_im2col_gemm_col2im():
+@pytest.mark.parametrize("h,w", [(32, 64), (44, 100)])
+def test_stem_im2col_gemm_col2im(h, w):
     o = ops()
-    n, h, w = 2, 32, 64
+    n = 2
     x = torch.rand(n, 3, h, w, device="cuda").to(torch.bfloat16).float()
     wt = (torch.randn(64, 3, 7, 7, generator=torch.Generator().manual_seed(3)) / 12).to(torch.bfloat16).float().cuda()
     pk = o.PackedConv(64, 3, 7, "cuda", need_dgrad=False, need_t=True, k_pad=o.STEM_KPAD).pack(wt)
     ho, wo = h // 2, w // 2
     patches = torch.empty(1, 1, n * ho * wo, o.STEM_KPAD, dtype=torch.bfloat16, device="cuda")
+    patches.fill_(float("nan"))
     o.stem_im2col(x, patches)
+    torch.cuda.synchronize()
+    # exact patch matrix: k = (r*7 + s)*3 + c, zero padding of the image border and of the 147..159 tail
+    unf = F.unfold(x, 7, padding=3, stride=2).view(n, 3, 49, ho * wo).permute(0, 3, 2, 1).reshape(n * ho * wo, 147)
+    assert torch.equal(patches.view(-1, o.STEM_KPAD)[:, :147].float(), unf)
+    assert float(patches.view(-1, o.STEM_KPAD)[:, 147:].float().abs().sum()) == 0.0
     y = torch.empty(1, 1, n * ho * wo, 64, dtype=torch.bfloat16, device="cuda")
     o.conv_fwd(o.conv_args(patches, y, pk.w_fwd, k=1))
     torch.cuda.synchronize()
@@ -379,6 +386,19 @@ def test_maxpool_fwd_bwd():
     (ref * nchw(dy)).sum().backward()
     want = (xr.grad + nchw(add)) * (nchw(x) > 0)
     assert_close_bf16(nchw(dx), want, "maxpool_bwd")
+    # arg-max index path (what the engines use): forward stores the window position, backward never reads x / y
+    idx = torch.full((n, h // 2, w // 2, c), 255, dtype=torch.uint8, device="cuda")
+    y2 = torch.empty_like(y)
+    o.maxpool_fwd(x, y2, idx=idx)
+    dx2 = torch.empty_like(x)
+    o.maxpool_bwd(x, y2, dy, dx2, add=add, idx=idx)
+    torch.cuda.synchronize()
+    assert torch.equal(y2, y) and int(idx.max()) <= 8
+    assert_close_bf16(nchw(dx2), xr.grad + nchw(add), "maxpool_bwd(idx)")
+    o.maxpool_fwd(x, y2, idx=idx, mask_nonpositive=True)      # ReLU mask of the pooled tensor's producer folded in
+    o.maxpool_bwd(x, y2, dy, dx2, idx=idx)
+    torch.cuda.synchronize()
+    assert_close_bf16(nchw(dx2), xr.grad * (nchw(x) > 0), "maxpool_bwd(idx, masked)")
 
 
 def test_upsample_and_fpn_add():
