@@ -134,13 +134,31 @@ def _clip_boxes_batched(boxes, image_shapes):
     return torch.stack((bx, by), dim=dim).reshape(boxes.shape)
 
 
-def _filter_nms_batched(boxes, scores, idxs, valid, nms_thresh, top_n):
+class _Pending:
+    """Device work has been enqueued; the host still needs ``counts_dev`` (data-dependent sizes) to finish.  Several
+    pending results are resolved with ONE device->host read (``_resolve``), so independent parts of the tail share a sync."""
+
+    def __init__(self, counts_dev, finish):
+        self.counts_dev, self.finish = counts_dev.reshape(-1), finish
+
+
+def _resolve(*pending):
+    flat = torch.cat([p.counts_dev.to(torch.int64) for p in pending]).tolist()              # the one host sync
+    out, o = [], 0
+    for p in pending:
+        n = p.counts_dev.numel()
+        out.append(p.finish(flat[o:o + n]))
+        o += n
+    return out
+
+
+def _filter_nms_batched_begin(boxes, scores, idxs, valid, nms_thresh, top_n):
     """The tail of torchvision's per-image loops -- drop the filtered boxes, ``batched_nms`` per category, keep the best
     ``top_n`` -- for all images at once and without a host sync per image.  boxes [B, M, 4], scores / idxs / valid [B, M].
     Instead of compacting each image (a ``nonzero`` + sync), filtered boxes get score -inf and sort to the end of the row;
     the stable descending sort orders the surviving boxes exactly as the compacted per-image sort would, the coordinate
     offset uses the maximum over the surviving boxes only, and hd_nms takes the survivor count from device memory.
-    Returns per-image tuples (boxes, scores, idxs), identical to the torchvision loop."""
+    Resolves to per-image tuples (boxes, scores, idxs), identical to the torchvision loop."""
     B, M = scores.shape
     neg_inf = float("-inf")
     max_coord = boxes.masked_fill(~valid[..., None], neg_inf).amax(dim=(1, 2))                     # boxes.max() of the survivors
@@ -152,14 +170,20 @@ def _filter_nms_batched(boxes, scores, idxs, valid, nms_thresh, top_n):
     counts = valid.sum(1, dtype=torch.int32)
     keep = ops.nms_sorted_flat(sorted_for_nms.view(-1, 4), [i * M for i in range(B + 1)], nms_thresh, counts=counts).view(B, M)
     sel = keep & (keep.cumsum(1) <= top_n)
-    n_sel = sel.sum(1).tolist()                                                                    # the one host sync
-    out_boxes = torch.gather(boxes, 1, gidx)[sel].split(n_sel)
-    out_scores = torch.gather(scores, 1, order)[sel].split(n_sel)
-    out_idxs = torch.gather(idxs, 1, order)[sel].split(n_sel)
-    return out_boxes, out_scores, out_idxs
+
+    def finish(n_sel):
+        out_boxes = torch.gather(boxes, 1, gidx)[sel].split(n_sel)
+        out_scores = torch.gather(scores, 1, order)[sel].split(n_sel)
+        out_idxs = torch.gather(idxs, 1, order)[sel].split(n_sel)
+        return out_boxes, out_scores, out_idxs
+    return _Pending(sel.sum(1), finish)
 
 
-def filter_proposals_batched(rpn, proposals, objectness, image_shapes, num_anchors_per_level):
+def _filter_nms_batched(boxes, scores, idxs, valid, nms_thresh, top_n):
+    return _resolve(_filter_nms_batched_begin(boxes, scores, idxs, valid, nms_thresh, top_n))[0]
+
+
+def filter_proposals_batched_begin(rpn, proposals, objectness, image_shapes, num_anchors_per_level):
     """torchvision ``RegionProposalNetwork.filter_proposals`` (TV models/detection/rpn.py:242-295) with the per-image loop
     (clip, small-box / score filters, per-level NMS, top-n) done for the whole batch: ~30 launches and one host sync
     instead of ~25 launches and 3 syncs per image.  Results are identical (tests/test_modules_gpu.py)."""
@@ -178,11 +202,21 @@ def filter_proposals_batched(rpn, proposals, objectness, image_shapes, num_ancho
         boxes = _clip_boxes_batched(proposals, image_shapes)
         ws, hs = boxes[..., 2] - boxes[..., 0], boxes[..., 3] - boxes[..., 1]
         valid = (ws >= rpn.min_size) & (hs >= rpn.min_size) & (scores >= rpn.score_thresh)
-        out_boxes, out_scores, _ = _filter_nms_batched(boxes, scores, levels, valid, rpn.nms_thresh, rpn.post_nms_top_n())
-    return list(out_boxes), list(out_scores)
+        pend = _filter_nms_batched_begin(boxes, scores, levels, valid, rpn.nms_thresh, rpn.post_nms_top_n())
+    inner = pend.finish
+    pend.finish = lambda n_sel: (lambda r: (list(r[0]), list(r[1])))(inner(n_sel))
+    return pend
+
+
+def filter_proposals_batched(rpn, proposals, objectness, image_shapes, num_anchors_per_level):
+    return _resolve(filter_proposals_batched_begin(rpn, proposals, objectness, image_shapes, num_anchors_per_level))[0]
 
 
 def postprocess_detections_batched(roi_heads, class_logits, box_regression, proposals, image_shapes):
+    return _resolve(postprocess_detections_batched_begin(roi_heads, class_logits, box_regression, proposals, image_shapes))[0]
+
+
+def postprocess_detections_batched_begin(roi_heads, class_logits, box_regression, proposals, image_shapes):
     """torchvision ``RoIHeads.postprocess_detections`` (TV models/detection/roi_heads.py:668-727) for the whole batch at
     once (see filter_proposals_batched); identical boxes / scores / labels."""
     device = class_logits.device
@@ -209,8 +243,10 @@ def postprocess_detections_batched(roi_heads, class_logits, box_regression, prop
     valid = (scores > roi_heads.score_thresh) & (ws >= 1e-2) & (hs >= 1e-2)
     if present is not None:
         valid = valid & present[:, :, None].expand(-1, -1, num_classes - 1).reshape(B, -1)
-    out = _filter_nms_batched(boxes, scores, labels, valid, roi_heads.nms_thresh, roi_heads.detections_per_img)
-    return list(out[0]), list(out[1]), list(out[2])
+    pend = _filter_nms_batched_begin(boxes, scores, labels, valid, roi_heads.nms_thresh, roi_heads.detections_per_img)
+    inner = pend.finish
+    pend.finish = lambda n_sel: (lambda r: (list(r[0]), list(r[1]), list(r[2])))(inner(n_sel))
+    return pend
 
 
 # ---- whole-batch target assignment and sampling (torchvision loops one image at a time: ~15 launches + 2-3 syncs each) ----
@@ -252,27 +288,33 @@ def _match_batched(matcher, gt_boxes, gt_present, boxes):
     return matches
 
 
-def _sample_batched(sampler, labels):
+def _sample_batched_begin(sampler, labels):
     """``det_utils.BalancedPositiveNegativeSampler`` for labels [B, N] (>= 1 positive, 0 negative, -1 ignored / padding).
-    Returns per-image (pos_idx, neg_idx) index tensors (unsorted, as drawn).  The two ``torch.randperm`` calls per image
+    Resolves to per-image (pos_idx, neg_idx) index tensors (unsorted, as drawn).  The two ``torch.randperm`` calls per image
     are issued with the same sizes and in the same order as torchvision's loop, so the CUDA generator is consumed
     identically and the samples are the same; everything else (counts, index lists) is computed once for the batch."""
     B, N = labels.shape
     pos_mask, neg_mask = labels >= 1, labels == 0
-    cnt = torch.stack([pos_mask.sum(1), neg_mask.sum(1)]).tolist()          # one host sync
-    n_pos_all, n_neg_all = cnt
-    pos_nz = torch.nonzero_static(pos_mask, size=sum(n_pos_all))[:, 1]
-    neg_nz = torch.nonzero_static(neg_mask, size=sum(n_neg_all))[:, 1]
-    out, po, no = [], 0, 0
-    for b in range(B):
-        positive, negative = pos_nz[po:po + n_pos_all[b]], neg_nz[no:no + n_neg_all[b]]
-        po, no = po + n_pos_all[b], no + n_neg_all[b]
-        num_pos = min(n_pos_all[b], int(sampler.batch_size_per_image * sampler.positive_fraction))
-        num_neg = min(n_neg_all[b], sampler.batch_size_per_image - num_pos)
-        perm1 = torch.randperm(n_pos_all[b], device=labels.device)[:num_pos]
-        perm2 = torch.randperm(n_neg_all[b], device=labels.device)[:num_neg]
-        out.append((positive[perm1], negative[perm2]))
-    return out
+
+    def finish(cnt):
+        n_pos_all, n_neg_all = cnt[:B], cnt[B:]
+        pos_nz = torch.nonzero_static(pos_mask, size=sum(n_pos_all))[:, 1]
+        neg_nz = torch.nonzero_static(neg_mask, size=sum(n_neg_all))[:, 1]
+        out, po, no = [], 0, 0
+        for b in range(B):
+            positive, negative = pos_nz[po:po + n_pos_all[b]], neg_nz[no:no + n_neg_all[b]]
+            po, no = po + n_pos_all[b], no + n_neg_all[b]
+            num_pos = min(n_pos_all[b], int(sampler.batch_size_per_image * sampler.positive_fraction))
+            num_neg = min(n_neg_all[b], sampler.batch_size_per_image - num_pos)
+            perm1 = torch.randperm(n_pos_all[b], device=labels.device)[:num_pos]
+            perm2 = torch.randperm(n_neg_all[b], device=labels.device)[:num_neg]
+            out.append((positive[perm1], negative[perm2]))
+        return out
+    return _Pending(torch.cat([pos_mask.sum(1), neg_mask.sum(1)]), finish)
+
+
+def _sample_batched(sampler, labels):
+    return _resolve(_sample_batched_begin(sampler, labels))[0]
 
 
 def assign_targets_to_anchors_batched(rpn, anchors, targets):
@@ -288,11 +330,12 @@ def assign_targets_to_anchors_batched(rpn, anchors, targets):
     return labels, matched_gt.to(torch.float32) if matched_gt.dtype != torch.float32 else matched_gt
 
 
-def rpn_compute_loss_batched(rpn, objectness, pred_bbox_deltas, labels, regression_targets):
+def rpn_compute_loss_batched(rpn, objectness, pred_bbox_deltas, labels, regression_targets, samples=None):
     """``RegionProposalNetwork.compute_loss`` (TV rpn.py) with labels [B, A] / regression_targets [B*A, 4] from the batched
     assignment.  Same samples (see _sample_batched), same reductions."""
     B, A = labels.shape
-    samples = _sample_batched(rpn.fg_bg_sampler, labels)
+    if samples is None:
+        samples = _sample_batched(rpn.fg_bg_sampler, labels)
     pos = torch.sort(torch.cat([p + b * A for b, (p, _) in enumerate(samples)]))[0]      # == where(cat(pos masks))
     neg = torch.sort(torch.cat([n + b * A for b, (_, n) in enumerate(samples)]))[0]
     sampled = torch.cat([pos, neg], dim=0)
@@ -303,7 +346,7 @@ def rpn_compute_loss_batched(rpn, objectness, pred_bbox_deltas, labels, regressi
     return objectness_loss, box_loss
 
 
-def select_training_samples_batched(roi_heads, proposals, targets):
+def select_training_samples_batched(roi_heads, proposals, targets, return_num_pos=False):
     """``RoIHeads.select_training_samples`` (TV roi_heads.py: add_gt_proposals, assign_targets_to_proposals, subsample, the
     per-image gathers and BoxCoder.encode) for the whole batch.  Returns the same four per-image lists."""
     roi_heads.check_targets(targets)
@@ -334,8 +377,54 @@ def select_training_samples_batched(roi_heads, proposals, targets):
     weights = torch.as_tensor(roi_heads.box_coder.weights, dtype=dtype, device=device)
     from torchvision.models.detection._utils import encode_boxes
     regression_targets = encode_boxes(matched_gt, out_props, weights)
-    return (list(out_props.split(per_image)), list(out_matched.split(per_image)), list(out_labels.split(per_image)),
-            list(regression_targets.split(per_image)))
+    out = (list(out_props.split(per_image)), list(out_matched.split(per_image)), list(out_labels.split(per_image)),
+           list(regression_targets.split(per_image)))
+    if return_num_pos:                                   # sampled foreground boxes == entries with label > 0 (host-known)
+        return out + (sum(int(p.shape[0]) for p, _ in samples),)
+    return out
+
+
+def fastrcnn_loss_static(class_logits, box_regression, labels, regression_targets, num_pos):
+    """``torchvision.models.detection.roi_heads.fastrcnn_loss`` with the foreground count passed in (known on the host
+    from the sampler), so ``torch.where(labels > 0)`` needs no device->host sync.  Same indices, same reductions."""
+    labels = torch.cat(labels, dim=0)
+    regression_targets = torch.cat(regression_targets, dim=0)
+    classification_loss = F.cross_entropy(class_logits, labels)
+    sampled_pos_inds_subset = torch.nonzero_static(labels > 0, size=num_pos)[:, 0]
+    labels_pos = labels[sampled_pos_inds_subset]
+    N, num_classes = class_logits.shape
+    box_regression = box_regression.reshape(N, box_regression.size(-1) // 4, 4)
+    box_loss = F.smooth_l1_loss(box_regression[sampled_pos_inds_subset, labels_pos], regression_targets[sampled_pos_inds_subset],
+                                beta=1 / 9, reduction="sum")
+    box_loss = box_loss / labels.numel()
+    return classification_loss, box_loss
+
+
+def multiscale_roi_align_one_sync(pooler, features, boxes, image_shapes):
+    """``torchvision.ops.MultiScaleRoIAlign.forward`` (TV ops/poolers.py) with the per-level ``torch.where(levels == k)``
+    (one host sync per FPN level) replaced by a stable sort of the level ids and one ``bincount`` read: the index lists
+    are the same (ascending within a level), so the pooled features are identical."""
+    from torchvision.ops import poolers, roi_align
+    x_filtered = poolers._filter_input(features, pooler.featmap_names)
+    if pooler.scales is None or pooler.map_levels is None:
+        pooler.scales, pooler.map_levels = poolers._setup_scales(x_filtered, image_shapes, pooler.canonical_scale, pooler.canonical_level)
+    num_levels = len(x_filtered)
+    if num_levels == 1:
+        return pooler(features, boxes, image_shapes)
+    rois = poolers._convert_to_roi_format(boxes)
+    levels = pooler.map_levels(boxes)
+    order = torch.sort(levels, stable=True)[1]
+    counts = torch.bincount(levels, minlength=num_levels).tolist()                 # the one host sync
+    result = torch.zeros((len(rois), x_filtered[0].shape[1]) + tuple(pooler.output_size), dtype=x_filtered[0].dtype,
+                         device=x_filtered[0].device)
+    o = 0
+    for level, (feat, scale) in enumerate(zip(x_filtered, pooler.scales)):
+        idx_in_level = order[o:o + counts[level]]
+        o += counts[level]
+        pooled = roi_align(feat, rois[idx_in_level], output_size=pooler.output_size, spatial_scale=scale,
+                           sampling_ratio=pooler.sampling_ratio)
+        result[idx_in_level] = pooled.to(result.dtype)
+    return result
 
 
 def _batched_ok(n_boxes):
@@ -423,23 +512,28 @@ def rpn_eval(model, images, features, targets):
     proposals = model.rpn.box_coder.decode(pred_bbox_deltas.detach(), anchors)
     proposals = proposals.view(num_images, -1, 4)
     pre_nms = sum(min(model.rpn.pre_nms_top_n(), n) for n in num_anchors_per_level)
-    if BATCHED_TAIL and proposals.is_cuda and proposals.dtype == torch.float32 and _batched_ok(pre_nms):
-        boxes, scores = filter_proposals_batched(model.rpn, proposals, objectness, images.image_sizes, num_anchors_per_level)
-    elif CONCURRENT_NMS and proposals.is_cuda:
-        boxes, scores = filter_proposals_concurrent(model.rpn, proposals, objectness, images.image_sizes, num_anchors_per_level)
-    else:
-        boxes, scores = model.rpn.filter_proposals(proposals, objectness, images.image_sizes, num_anchors_per_level)
     if targets is None:
         raise ValueError("targets should not be None")
-    if BATCHED_TAIL and proposals.is_cuda and all(a.shape == anchors[0].shape for a in anchors):
+    if (BATCHED_TAIL and proposals.is_cuda and proposals.dtype == torch.float32 and _batched_ok(pre_nms)
+            and all(a.shape == anchors[0].shape for a in anchors)):
+        # everything that does not need a host-side size is enqueued first (target assignment, box encoding, the proposal
+        # filter up to its NMS); the proposal counts and the sampler's positive / negative counts then come back in ONE read
         with torch.no_grad():
             labels, matched_gt_boxes = assign_targets_to_anchors_batched(model.rpn, anchors, targets)
             regression_targets = model.rpn.box_coder.encode_single(matched_gt_boxes.reshape(-1, 4), torch.cat(anchors, dim=0))
-        loss_objectness, loss_rpn_box_reg = rpn_compute_loss_batched(model.rpn, objectness, pred_bbox_deltas, labels, regression_targets)
+            pend_samples = _sample_batched_begin(model.rpn.fg_bg_sampler, labels)
+        pend_boxes = filter_proposals_batched_begin(model.rpn, proposals, objectness, images.image_sizes, num_anchors_per_level)
+        (boxes, scores), samples = _resolve(pend_boxes, pend_samples)
+        loss_objectness, loss_rpn_box_reg = rpn_compute_loss_batched(model.rpn, objectness, pred_bbox_deltas, labels, regression_targets,
+                                                                     samples=samples)
+        return boxes, {"loss_objectness": loss_objectness, "loss_rpn_box_reg": loss_rpn_box_reg}
+    if CONCURRENT_NMS and proposals.is_cuda:
+        boxes, scores = filter_proposals_concurrent(model.rpn, proposals, objectness, images.image_sizes, num_anchors_per_level)
     else:
-        labels, matched_gt_boxes = model.rpn.assign_targets_to_anchors(anchors, targets)
-        regression_targets = model.rpn.box_coder.encode(matched_gt_boxes, anchors)
-        loss_objectness, loss_rpn_box_reg = model.rpn.compute_loss(objectness, pred_bbox_deltas, labels, regression_targets)
+        boxes, scores = model.rpn.filter_proposals(proposals, objectness, images.image_sizes, num_anchors_per_level)
+    labels, matched_gt_boxes = model.rpn.assign_targets_to_anchors(anchors, targets)
+    regression_targets = model.rpn.box_coder.encode(matched_gt_boxes, anchors)
+    loss_objectness, loss_rpn_box_reg = model.rpn.compute_loss(objectness, pred_bbox_deltas, labels, regression_targets)
     return boxes, {"loss_objectness": loss_objectness, "loss_rpn_box_reg": loss_rpn_box_reg}
 
 
@@ -494,15 +588,24 @@ def roi_heads_eval(model, features, proposals, image_shapes, targets=None, train
             raise TypeError(f"target boxes must of float type, instead got {t['boxes'].dtype}")
         if t["labels"].dtype != torch.int64:
             raise TypeError(f"target labels must of int64 type, instead got {t['labels'].dtype}")
+    from torchvision.ops import MultiScaleRoIAlign
+    num_pos = None
     if BATCHED_TAIL and proposals[0].is_cuda:
         with torch.no_grad():
-            proposals, matched_idxs, labels, regression_targets = select_training_samples_batched(model.roi_heads, proposals, targets)
+            proposals, matched_idxs, labels, regression_targets, num_pos = select_training_samples_batched(
+                model.roi_heads, proposals, targets, return_num_pos=True)
     else:
         proposals, matched_idxs, labels, regression_targets = model.roi_heads.select_training_samples(proposals, targets)
-    box_features = model.roi_heads.box_roi_pool(features, proposals, image_shapes)
+    if BATCHED_TAIL and proposals[0].is_cuda and type(model.roi_heads.box_roi_pool) is MultiScaleRoIAlign:
+        box_features = multiscale_roi_align_one_sync(model.roi_heads.box_roi_pool, features, proposals, image_shapes)
+    else:
+        box_features = model.roi_heads.box_roi_pool(features, proposals, image_shapes)
     box_features = model.roi_heads.box_head(box_features)
     class_logits, box_regression = model.roi_heads.box_predictor(box_features)
-    loss_classifier, loss_box_reg = fastrcnn_loss(class_logits, box_regression, labels, regression_targets)
+    if num_pos is not None:
+        loss_classifier, loss_box_reg = fastrcnn_loss_static(class_logits, box_regression, labels, regression_targets, num_pos)
+    else:
+        loss_classifier, loss_box_reg = fastrcnn_loss(class_logits, box_regression, labels, regression_targets)
     losses = {"loss_classifier": loss_classifier, "loss_box_reg": loss_box_reg}
     n_cand = max(p.shape[0] for p in proposals) * (class_logits.shape[-1] - 1)
     if BATCHED_TAIL and class_logits.is_cuda and class_logits.dtype == torch.float32 and _batched_ok(n_cand):

@@ -57,6 +57,38 @@ def _check(device):
             assert all(torch.equal(x, y) for x, y in zip(a, b))
 
 
+def _check_roi_pool_and_loss(device):
+    from collections import OrderedDict
+    from torchvision.models.detection.roi_heads import fastrcnn_loss
+    from hallucidet_b200 import detection as D
+    det = odet.build_detector("fasterrcnn", seed=1).to(device)
+    g = torch.Generator().manual_seed(0)
+    feats = OrderedDict((k, torch.randn(2, 256, s, s, generator=g).to(device)) for k, s in (("0", 64), ("1", 32), ("2", 16), ("3", 8), ("pool", 4)))
+
+    def boxes(n):
+        xy, wh = torch.rand(n, 2, generator=g) * 150, torch.rand(n, 2, generator=g) * 100 + 2
+        return torch.cat([xy, xy + wh], 1).to(device)
+    props = [boxes(200), boxes(137)]
+    a = det.roi_heads.box_roi_pool(feats, props, [(256, 256)] * 2)
+    b = D.multiscale_roi_align_one_sync(det.roi_heads.box_roi_pool, feats, props, [(256, 256)] * 2)
+    assert torch.equal(a, b) and a.shape == (337, 256, 7, 7)
+    cl, br = torch.randn(337, 2, generator=g).to(device), torch.randn(337, 8, generator=g).to(device)
+    labels = [(torch.rand(n, generator=g) > 0.7).long().to(device) for n in (200, 137)]
+    rt = [torch.randn(n, 4, generator=g).to(device) for n in (200, 137)]
+    l1 = fastrcnn_loss(cl, br, labels, rt)
+    l2 = D.fastrcnn_loss_static(cl, br, labels, rt, sum(int((l > 0).sum()) for l in labels))
+    assert torch.equal(l1[0], l2[0]) and torch.equal(l1[1], l2[1])
+
+
+def test_roi_pool_and_loss_cpu():
+    _check_roi_pool_and_loss("cpu")
+
+
+@pytest.mark.gpu
+def test_roi_pool_and_loss_cuda():
+    _check_roi_pool_and_loss("cuda")
+
+
 def test_batched_targets_and_sampling_cpu():
     _check("cpu")
 
