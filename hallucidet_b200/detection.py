@@ -500,6 +500,38 @@ import os as _os
 CONCURRENT_NMS = _os.environ.get("HD_CONCURRENT_NMS", "1") != "0"                   # proposal filtering
 CONCURRENT_POSTPROCESS = _os.environ.get("HD_CONCURRENT_POSTPROCESS", "0") != "0"   # final detections
 BATCHED_TAIL = _os.environ.get("HD_BATCHED_TAIL", "1") != "0"   # whole-batch proposal filter / detections post-processing
+DEFER_DETECTIONS = False    # set by HalluciDetTrainer.training_step: roi_heads_eval returns a DeferredDetections
+
+
+class DeferredDetections:
+    """Final detections whose per-image counts are still on their way to the host (pinned, non-blocking copy).
+    ``resolve()`` waits for that copy only, assembles the per-image ``{"boxes", "labels", "scores"}`` dicts and applies the
+    queued post-processing (the transform's rescaling to the original image size).  Used inside the train step, where the
+    detections are a by-product (train_hallucidet.py:181 logs them): the step's critical path then has one host sync less."""
+
+    def __init__(self, pending):
+        self._pending = pending
+        self._counts = torch.empty(pending.counts_dev.numel(), dtype=torch.int64, pin_memory=True)
+        self._counts.copy_(pending.counts_dev.to(torch.int64), non_blocking=True)
+        self._event = torch.cuda.Event()
+        self._event.record()
+        self._post = []
+        self._value = None
+
+    def then(self, fn):
+        self._post.append(fn)
+        return self
+
+    def resolve(self):
+        if self._value is None:
+            self._event.synchronize()
+            with torch.no_grad():
+                boxes, scores, labels = self._pending.finish(self._counts.tolist())
+                value = [{"boxes": boxes[i], "labels": labels[i], "scores": scores[i]} for i in range(len(boxes))]
+                for fn in self._post:
+                    value = fn(value)
+            self._value, self._pending = value, None
+        return self._value
 
 
 def rpn_eval(model, images, features, targets):
@@ -610,8 +642,13 @@ def roi_heads_eval(model, features, proposals, image_shapes, targets=None, train
     n_cand = max(p.shape[0] for p in proposals) * (class_logits.shape[-1] - 1)
     if BATCHED_TAIL and class_logits.is_cuda and class_logits.dtype == torch.float32 and _batched_ok(n_cand):
         with torch.no_grad():
-            boxes, scores, labels = postprocess_detections_batched(model.roi_heads, class_logits.detach(), box_regression.detach(),
-                                                                   proposals, image_shapes)
+            pend = postprocess_detections_batched_begin(model.roi_heads, class_logits.detach(), box_regression.detach(), proposals,
+                                                        image_shapes)
+            if DEFER_DETECTIONS:
+                # the detections feed no loss: their data-dependent sizes are read back asynchronously and the lists are
+                # assembled when the caller asks (HalluciDetTrainer.training_step: after the backward pass has been enqueued)
+                return DeferredDetections(pend), losses
+            boxes, scores, labels = _resolve(pend)[0]
     elif class_logits.is_cuda:
         with torch.no_grad():
             boxes, scores, labels = postprocess_detections_concurrent(model.roi_heads, class_logits.detach(), box_regression.detach(),
@@ -641,7 +678,11 @@ def eval_forward_fasterrcnn(model, images, targets, train_det=False, model_name=
         features = OrderedDict([("0", features)])
     proposals, proposal_losses = rpn_eval(model, images, features, targets)
     detections, detector_losses = roi_heads_eval(model, features, proposals, images.image_sizes, targets)
-    detections = model.transform.postprocess(detections, images.image_sizes, original_image_sizes)
+    if isinstance(detections, DeferredDetections):
+        image_sizes = images.image_sizes
+        detections.then(lambda d: model.transform.postprocess(d, image_sizes, original_image_sizes))
+    else:
+        detections = model.transform.postprocess(detections, images.image_sizes, original_image_sizes)
     losses = {}
     losses.update(detector_losses)
     losses.update(proposal_losses)

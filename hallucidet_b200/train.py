@@ -64,6 +64,40 @@ def shard_batch(global_batch, rank, world):
     return slice(rank * per, (rank + 1) * per)
 
 
+class DevicePrefetcher:
+    """Host (pinned) -> device copies of the NEXT batch on a copy stream, overlapped with the current step (what a
+    DataLoader with pinned memory + non_blocking copies gives the reference's Lightning loop).  ``put`` enqueues the
+    copies into one of two persistent device slots, ``get`` makes the compute stream wait for them and hands the
+    device tensors over (valid until the second ``put`` after it)."""
+
+    def __init__(self, device="cuda"):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.slots = [None, None]
+        self.turn = 0
+        self.pending = None
+
+    def put(self, *host_tensors):
+        slot = self.slots[self.turn]
+        if slot is None or any(d.shape != h.shape or d.dtype != h.dtype for d, h in zip(slot, host_tensors)):
+            slot = self.slots[self.turn] = [torch.empty(h.shape, dtype=h.dtype, device=self.device) for h in host_tensors]
+        # the slot was last read two steps ago; everything enqueued so far on the compute stream is older than that read
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            for d, h in zip(slot, host_tensors):
+                d.copy_(h, non_blocking=True)
+        event = torch.cuda.Event()
+        event.record(self.stream)
+        self.pending = (slot, event)
+        self.turn ^= 1
+
+    def get(self):
+        dev, event = self.pending
+        self.pending = None
+        torch.cuda.current_stream(self.device).wait_event(event)
+        return dev
+
+
 def expand_one_channel_to_output_channels(imgs, output_channels=3):
     """src/utils/utils.py:52-53."""
     return imgs.repeat(1, output_channels, 1, 1)
@@ -110,8 +144,10 @@ class HalluciDetTrainer(nn.Module):
         losses_det, detections = Detector.calculate_loss(self.detector, hal, targets_ir, train_det=False, model_name=self.detector_name)
         if self.reference_extra_passes:
             with torch.no_grad():
-                Detector.calculate_loss(self.detector, imgs_rgb, targets_rgb, train_det=False, model_name=self.detector_name)
-                Detector.calculate_loss(self.detector, ir3, targets_ir, train_det=False, model_name=self.detector_name)
+                for imgs, tg in ((imgs_rgb, targets_rgb), (ir3, targets_ir)):
+                    _, extra = Detector.calculate_loss(self.detector, imgs, tg, train_det=False, model_name=self.detector_name)
+                    if hasattr(extra, "resolve"):
+                        extra.resolve()
         frcnn = "fasterrcnn" in self.detector_name
         if frcnn:
             losses_det["classification"] = losses_det["loss_classifier"]
@@ -167,11 +203,18 @@ class HalluciDetTrainer(nn.Module):
             torch.nn.utils.clip_grad_value_(self.encoder_decoder.parameters(), self.clip_value)
 
     def training_step(self, imgs_rgb, targets_rgb, imgs_ir, targets_ir, det_seed=None):
+        from . import detection
         self.encoder_decoder.train()
         self.optimizer.zero_grad(set_to_none=True)
-        out = self.forward_step(imgs_rgb, targets_rgb, imgs_ir, targets_ir, det_seed=det_seed)
+        detection.DEFER_DETECTIONS = True           # the detections are a by-product here: assemble them after the backward
+        try:
+            out = self.forward_step(imgs_rgb, targets_rgb, imgs_ir, targets_ir, det_seed=det_seed)
+        finally:
+            detection.DEFER_DETECTIONS = False
         out["total"].backward()
         self.allreduce_gradients()
         self.clip_gradients()
         self.optimizer.step()
+        if isinstance(out["detections"], detection.DeferredDetections):
+            out["detections"] = out["detections"].resolve()
         return out
