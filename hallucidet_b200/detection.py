@@ -252,18 +252,23 @@ def postprocess_detections_batched_begin(roi_heads, class_logits, box_regression
 # ---- whole-batch target assignment and sampling (torchvision loops one image at a time: ~15 launches + 2-3 syncs each) ----
 
 def _pad_rows(rows, width, fill=0):
-    """List of [n_i, ...] tensors -> ([B, width, ...] padded with ``fill``, [B, width] bool presence mask), with one
-    concatenation and one scatter (the row counts are host-known shapes)."""
+    """List of [n_i, ...] tensors -> ([B, width, ...] padded with ``fill``, [B, width] bool presence mask).  The row
+    counts are host-known shapes; no Python loop over elements (``pad_sequence`` copies row by row in C++)."""
     B = len(rows)
     counts = [int(r.shape[0]) for r in rows]
     ref = rows[0]
-    out = ref.new_full((B * width,) + tuple(ref.shape[1:]), fill)
-    present = torch.zeros(B * width, dtype=torch.bool, device=ref.device)
-    if sum(counts) > 0:
-        idx = torch.tensor([b * width + j for b, n in enumerate(counts) for j in range(n)], dtype=torch.int64).to(ref.device, non_blocking=True)
-        out[idx] = torch.cat(rows, 0)
-        present[idx] = True
-    return out.view((B, width) + tuple(ref.shape[1:])), present.view(B, width)
+    if all(c == width for c in counts):
+        return torch.stack(rows), torch.ones(B, width, dtype=torch.bool, device=ref.device)
+    if max(counts) == 0:
+        out = ref.new_full((B, width) + tuple(ref.shape[1:]), fill)
+    else:
+        out = torch.nn.utils.rnn.pad_sequence(rows, batch_first=True, padding_value=fill)
+        if out.shape[1] < width:
+            extra = out.new_full((B, width - out.shape[1]) + tuple(out.shape[2:]), fill)
+            out = torch.cat([out, extra], dim=1)
+    cnt = torch.tensor(counts, dtype=torch.int64).to(ref.device, non_blocking=True)
+    present = torch.arange(width, device=ref.device)[None, :] < cnt[:, None]
+    return out, present
 
 
 def _match_batched(matcher, gt_boxes, gt_present, boxes):
