@@ -16,6 +16,18 @@ class HdAct(ctypes.Structure):
     _fields_ = [("ptr", c_void_p), ("n", ctypes.c_int32), ("h", ctypes.c_int32), ("w", ctypes.c_int32), ("c", ctypes.c_int32)]
 
 
+class HdPackDesc(ctypes.Structure):
+    _fields_ = [("w", c_void_p), ("scale", c_void_p), ("w_fwd", c_void_p), ("w_dgrad", c_void_p), ("w_t", c_void_p),
+                ("cout", ctypes.c_int32), ("cin", ctypes.c_int32), ("kh", ctypes.c_int32), ("kw", ctypes.c_int32),
+                ("cout_pad", ctypes.c_int32), ("k_pad", ctypes.c_int32), ("cin_pad", ctypes.c_int32), ("first_block", ctypes.c_int32)]
+
+
+class HdUnpackDesc(ctypes.Structure):
+    _fields_ = [("dw", c_void_p), ("g", c_void_p),
+                ("cout", ctypes.c_int32), ("cin", ctypes.c_int32), ("taps", ctypes.c_int32), ("tap_stride", ctypes.c_int32),
+                ("row_stride", ctypes.c_int32), ("first_block", ctypes.c_int32), ("scale", ctypes.c_float), ("pad_", ctypes.c_int32)]
+
+
 class HdConvArgs(ctypes.Structure):
     _fields_ = [
         ("x0", HdAct), ("x1", HdAct), ("y0", HdAct), ("y1", HdAct),
@@ -65,6 +77,9 @@ PROTOTYPES = {
     "hd_resize_nearest_bwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
     "hd_regulariser": [c_int, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_int, c_int, c_void_p, c_void_p,
                        c_float, c_int, c_void_p],
+    "hd_multi_blocks": [ctypes.c_int64],
+    "hd_pack_conv_weights": [c_void_p, c_int, c_int, c_void_p],
+    "hd_unpack_wgrads": [c_void_p, c_int, c_int, c_void_p],
     "hd_nms": [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p],
 }
 _RESTYPES = {"hd_last_error": ctypes.c_char_p}

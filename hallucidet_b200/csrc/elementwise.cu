@@ -80,6 +80,75 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, float* __restr
     }
 }
 
+// All layers of a network in one launch (the per-layer kernels above are 5-10 us of launch + DRAM latency each, 47 of
+// them per step): block -> layer through the prefix of block counts stored in the descriptor table.
+constexpr int kMultiItems = 4;                           // elements per thread
+
+__device__ __forceinline__ int find_desc(const int* first_block, int stride_ints, int n, int block) {
+    int lo = 0, hi = n - 1;                              // last descriptor whose first_block <= block
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (first_block[static_cast<long>(mid) * stride_ints] <= block) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void pack_weights_multi_kernel(const hd_pack_desc* __restrict__ descs, int n) {
+    const int li = find_desc(&descs[0].first_block, sizeof(hd_pack_desc) / sizeof(int), n, blockIdx.x);
+    const hd_pack_desc d = descs[li];
+    const int taps = d.kh * d.kw;
+    const long n_fwd = static_cast<long>(d.cout_pad) * d.k_pad;
+    const long n_dg = d.w_dgrad ? static_cast<long>(d.cin_pad) * taps * d.cout : 0;
+    __nv_bfloat16* w_fwd = static_cast<__nv_bfloat16*>(d.w_fwd);
+    __nv_bfloat16* w_dgrad = static_cast<__nv_bfloat16*>(d.w_dgrad);
+    __nv_bfloat16* w_t = static_cast<__nv_bfloat16*>(d.w_t);
+    const long base = static_cast<long>(blockIdx.x - d.first_block) * blockDim.x * kMultiItems;
+#pragma unroll
+    for (int it = 0; it < kMultiItems; ++it) {
+        const long i = base + it * blockDim.x + threadIdx.x;
+        if (i >= n_fwd + n_dg) break;
+        if (i < n_fwd) {
+            const int co = static_cast<int>(i / d.k_pad), k = static_cast<int>(i % d.k_pad);
+            float v = 0.f;
+            if (co < d.cout && k < taps * d.cin) {
+                const int tap = k / d.cin, ci = k % d.cin;
+                v = d.w[(static_cast<long>(co) * d.cin + ci) * taps + tap];
+                if (d.scale) v *= d.scale[co];
+            }
+            const __nv_bfloat16 b = __float2bfloat16_rn(v);
+            if (w_fwd) w_fwd[i] = b;
+            if (w_t) w_t[static_cast<long>(k) * d.cout_pad + co] = b;
+        } else {
+            const long j = i - n_fwd;
+            const int ci = static_cast<int>(j / (taps * d.cout));
+            const int rem = static_cast<int>(j % (taps * d.cout));
+            const int tap = rem / d.cout, co = rem % d.cout;
+            float v = 0.f;
+            if (ci < d.cin) {
+                v = d.w[(static_cast<long>(co) * d.cin + ci) * taps + tap];
+                if (d.scale) v *= d.scale[co];
+            }
+            w_dgrad[j] = __float2bfloat16_rn(v);
+        }
+    }
+}
+
+__global__ void unpack_wgrads_multi_kernel(const hd_unpack_desc* __restrict__ descs, int n) {
+    const int li = find_desc(&descs[0].first_block, sizeof(hd_unpack_desc) / sizeof(int), n, blockIdx.x);
+    const hd_unpack_desc d = descs[li];
+    const long total = static_cast<long>(d.cout) * d.cin * d.taps;
+    const long base = static_cast<long>(blockIdx.x - d.first_block) * blockDim.x * kMultiItems;
+#pragma unroll
+    for (int it = 0; it < kMultiItems; ++it) {
+        const long i = base + it * blockDim.x + threadIdx.x;
+        if (i >= total) break;
+        const int tap = static_cast<int>(i % d.taps);
+        const int ci = static_cast<int>((i / d.taps) % d.cin);
+        const int co = static_cast<int>(i / (static_cast<long>(d.taps) * d.cin));
+        d.g[i] = d.dw[static_cast<long>(co) * d.row_stride + static_cast<long>(tap) * d.tap_stride + ci] * d.scale;
+    }
+}
+
 // -------------------------------------------------------------------------------------------------
 // stem 7x7/2 patches
 // -------------------------------------------------------------------------------------------------
@@ -880,6 +949,25 @@ extern "C" int hd_unpack_wgrad(const float* dw, float* g, int cout, int cin, int
     HD_CHECK_ARG(dw && g && cout > 0 && cin > 0);
     unpack_wgrad_kernel<<<ew_blocks(static_cast<long>(cout) * cin * kh * kw), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
         dw, g, cout, cin, kh * kw, tap_stride, row_stride, scale);
+    HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_multi_blocks(int64_t elements) {
+    // blocks a layer with `elements` work items occupies in hd_pack_conv_weights / hd_unpack_wgrads (for first_block)
+    return static_cast<int>((elements + static_cast<int64_t>(kEwThreads) * kMultiItems - 1) / (static_cast<int64_t>(kEwThreads) * kMultiItems));
+}
+
+extern "C" int hd_pack_conv_weights(const hd_pack_desc* descs_dev, int n_layers, int total_blocks, hd_stream st) {
+    HD_CHECK_ARG(descs_dev && n_layers > 0 && total_blocks > 0);
+    pack_weights_multi_kernel<<<total_blocks, kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(descs_dev, n_layers);
+    HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_unpack_wgrads(const hd_unpack_desc* descs_dev, int n_layers, int total_blocks, hd_stream st) {
+    HD_CHECK_ARG(descs_dev && n_layers > 0 && total_blocks > 0);
+    unpack_wgrads_multi_kernel<<<total_blocks, kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(descs_dev, n_layers);
     HD_LAUNCH_OK();
     return HD_OK;
 }

@@ -200,6 +200,60 @@ def unpack_wgrad(dw_packed, grad_oihw, cout, cin, k, tap_stride, row_stride, sca
               "hd_unpack_wgrad")
 
 
+class _DescTable:
+    """Device-resident descriptor table for the whole-network pack / unpack launches."""
+
+    def __init__(self, descs, device):
+        arr = (type(descs[0]) * len(descs))(*descs)
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
+        self.dev = raw.to(device)
+        self.n = len(descs)
+        self.total_blocks = descs[-1].first_block + descs[-1]._blocks
+        self.keys = [d._key for d in descs]
+
+
+def multi_blocks(elements):
+    return int(_lib.load().hd_multi_blocks(ctypes.c_int64(int(elements))))
+
+
+def pack_table(packed_convs, weights, device):
+    """Descriptor table packing every (PackedConv, fp32 OIHW weight) pair in one launch (training mode: no BN scale)."""
+    descs, first = [], 0
+    for pk, w in zip(packed_convs, weights):
+        assert w.dtype == torch.float32 and w.is_contiguous() and tuple(w.shape) == (pk.cout, pk.cin, pk.k, pk.k)
+        d = _lib.HdPackDesc(w.data_ptr(), None, pk.w_fwd.data_ptr(), pk.w_dgrad.data_ptr() if pk.w_dgrad is not None else None,
+                            pk.w_t.data_ptr() if pk.w_t is not None else None, pk.cout, pk.cin, pk.k, pk.k, pk.cout_pad, pk.k_pad,
+                            pk.cin_pad, first)
+        work = pk.cout_pad * pk.k_pad + (pk.cin_pad * pk.k * pk.k * pk.cout if pk.w_dgrad is not None else 0)
+        d._blocks = multi_blocks(work)
+        d._key = w.data_ptr()
+        first += d._blocks
+        descs.append(d)
+    return _DescTable(descs, device)
+
+
+def pack_conv_weights(table):
+    with _Timed("pack_conv_weights"):
+        check(_lib.load().hd_pack_conv_weights(_ptr(table.dev), table.n, table.total_blocks, _stream()), "hd_pack_conv_weights")
+
+
+def unpack_table(entries, device):
+    """entries: (dw_packed, grad_oihw, cout, cin, k, tap_stride, row_stride) per layer."""
+    descs, first = [], 0
+    for dw, g, cout, cin, k, tap_stride, row_stride in entries:
+        d = _lib.HdUnpackDesc(dw.data_ptr(), g.data_ptr(), cout, cin, k * k, tap_stride, row_stride, first, 1.0, 0)
+        d._blocks = multi_blocks(cout * cin * k * k)
+        d._key = g.data_ptr()
+        first += d._blocks
+        descs.append(d)
+    return _DescTable(descs, device)
+
+
+def unpack_wgrads(table):
+    with _Timed("unpack_wgrads"):
+        check(_lib.load().hd_unpack_wgrads(_ptr(table.dev), table.n, table.total_blocks, _stream()), "hd_unpack_wgrads")
+
+
 def stem_im2col(x_nchw, patches, k_pad=STEM_KPAD):
     n, c, h, w = x_nchw.shape
     assert c == 3 and x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()

@@ -276,6 +276,7 @@ class _UnetEngine:
             l.dw = self.dw_flat[l.dw_off:l.dw_off + l.dw_rows * l.dw_cols]
         self.grad_bufs = {}
         self.side_stream, self.side_used = None, False
+        self.pack_tab = self.unpack_tab = None
         self.graphs = {}
         self.sigmoid = None
         self.generation = 0
@@ -296,13 +297,39 @@ class _UnetEngine:
             self.grad_bufs[key] = t
         return t
 
+    def _pack_sources(self):
+        return [self.head_w_pad if l is self.head else l.conv.weight.detach() for l in self.all_layers]
+
+    def _check_tables(self):
+        """(Re)build the device descriptor tables of the one-launch weight packing / gradient unpacking.  They hold raw
+        parameter pointers, so a parameter that was re-allocated (``.to()``, ``load_state_dict(assign=True)``) invalidates
+        them -- and any captured CUDA graph."""
+        if not self.training:
+            return
+        srcs = self._pack_sources()
+        if self.pack_tab is not None and self.pack_tab.keys == [w.data_ptr() for w in srcs]:
+            return
+        assert all(w.is_contiguous() for w in srcs)
+        self.pack_tab = ops.pack_table([l.packed for l in self.all_layers], srcs, self.device)
+        gv = self.grad_views
+        entries = [(l.dw, gv[l.name + ".weight"], l.cout, l.cin, l.k, l.cin, l.k * l.k * l.cin) for l in self.all_layers if l is not self.stem]
+        entries.append((self.stem.dw, gv["encoder.conv1.weight"], 64, 3, 7, 3, ops.STEM_KPAD))
+        self.unpack_tab = ops.unpack_table(entries, self.device)
+        self.graphs.clear()
+
     def _pack_weights(self):
+        if self.training:                                 # one launch for all layers (fp32 masters -> bf16 GEMM operands)
+            hd = self.head
+            self.head_w_pad[:hd.cout].copy_(hd.conv.weight.detach())
+            self.head_bias_pad[:hd.cout].copy_(hd.conv.bias.detach())
+            ops.pack_conv_weights(self.pack_tab)
+            return
         for l in self.all_layers:
             if l is self.head:
                 self.head_w_pad[:l.cout].copy_(l.conv.weight.detach())
                 self.head_bias_pad[:l.cout].copy_(l.conv.bias.detach())
                 l.packed.pack(self.head_w_pad)
-            elif self.training or l.bn is None:
+            elif l.bn is None:
                 l.packed.pack(l.conv.weight.detach().contiguous())
             else:                                         # eval: fold running statistics (TV ops/misc.py-style affine)
                 bn = l.bn
@@ -354,6 +381,7 @@ class _UnetEngine:
         if self.sigmoid is not None and self.sigmoid != sigmoid:
             self.graphs.clear()
         self.sigmoid = sigmoid
+        self._check_tables()
         self.x_in.copy_(x)
         self._run("fwd", self._forward_impl)
         self.generation += 1
@@ -451,10 +479,7 @@ class _UnetEngine:
         self.side_used = True
 
     def _wgrad(self, l, x0, dz, x1=None):
-        def launch():
-            ops.conv_wgrad(ops.conv_args(x0, dz, k=l.k, stride=l.stride, x1=x1, dw=l.dw, algo_cout=l.cout))
-            ops.unpack_wgrad(l.dw, self.grad_views[l.name + ".weight"], l.cout, l.cin, l.k, l.cin, l.k * l.k * l.cin)
-        self._on_side(launch)
+        self._on_side(lambda: ops.conv_wgrad(ops.conv_args(x0, dz, k=l.k, stride=l.stride, x1=x1, dw=l.dw, algo_cout=l.cout)))
 
     def _backward_impl(self):
         dhal = self.dhal_in
@@ -513,10 +538,8 @@ class _UnetEngine:
         ops.maxpool_bwd(self.a_stem, self.p0, g, g_stem, add=skip_grads[3], idx=self.p0_idx)
         zs = st.z.view(1, 1, -1, 64)
         dzs = self._bn_bwd(st, g_stem.view(1, 1, -1, 64), self.a_stem.view(1, 1, -1, 64), z=zs, direct_relu=True)
-        def stem_wgrad():
-            ops.conv_wgrad(ops.conv_args(self.patches, dzs, k=1, dw=st.dw, algo_cin=147))
-            ops.unpack_wgrad(st.dw, gv["encoder.conv1.weight"], 64, 3, 7, 3, ops.STEM_KPAD)
-        self._on_side(stem_wgrad)
-        if self.side_used:                                   # join: the gradients are complete when the backward returns
+        self._on_side(lambda: ops.conv_wgrad(ops.conv_args(self.patches, dzs, k=1, dw=st.dw, algo_cin=147)))
+        if self.side_used:                                   # join: every weight-gradient accumulator is complete
             torch.cuda.current_stream().wait_stream(self.side_stream)
             self.side_used = False
+        ops.unpack_wgrads(self.unpack_tab)                   # all layers: packed fp32 accumulators -> the flat OIHW gradient block

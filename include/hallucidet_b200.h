@@ -91,6 +91,28 @@ int hd_pack_conv_weight(const float* w_oihw, const float* scale, int cout, int c
 int hd_unpack_wgrad(const float* dw_packed, float* grad_oihw, int cout, int cin, int kh, int kw, int tap_stride,
                     int row_stride, float scale, hd_stream stream);
 
+/* Whole-network variants of the two calls above: one launch for every layer.  The descriptor tables live in DEVICE
+ * memory; first_block is the running sum of hd_multi_blocks(work) over the preceding layers (work = cout_pad*k_pad +
+ * (w_dgrad ? cin_pad*kh*kw*cout : 0) for packing, cout*cin*taps for unpacking); total_blocks is the grand total. */
+typedef struct hd_pack_desc {
+    const float* w;       /* fp32 OIHW master weight */
+    const float* scale;   /* optional per-cout scale (folded BN) */
+    void* w_fwd;          /* [cout_pad][k_pad] bf16 */
+    void* w_dgrad;        /* [cin_pad][kh*kw*cout] bf16 or NULL */
+    void* w_t;            /* [k_pad][cout_pad] bf16 or NULL */
+    int32_t cout, cin, kh, kw, cout_pad, k_pad, cin_pad, first_block;
+} hd_pack_desc;
+typedef struct hd_unpack_desc {
+    const float* dw;      /* packed fp32 weight gradient (see hd_conv_wgrad) */
+    float* g;             /* fp32 OIHW gradient */
+    int32_t cout, cin, taps, tap_stride, row_stride, first_block;
+    float scale;
+    int32_t pad_;
+} hd_unpack_desc;
+int hd_multi_blocks(int64_t elements);
+int hd_pack_conv_weights(const hd_pack_desc* descs_dev, int n_layers, int total_blocks, hd_stream stream);
+int hd_unpack_wgrads(const hd_unpack_desc* descs_dev, int n_layers, int total_blocks, hd_stream stream);
+
 /* ---- stem 7x7 stride-2 pad-3 conv via explicit patches (cin = 3 is not TMA-addressable) --------------
  * Replaces encoder.conv1 (encoders/resnet.py:50) and body.conv1 (TV: models/resnet.py:197) im2col/col2im.
  * x fp32 NCHW [n][3][h][w] -> patches bf16 [n*ho*wo][k_pad], k = (r*7+s)*3 + c, ho = h/2, wo = w/2. */

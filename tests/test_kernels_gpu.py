@@ -527,3 +527,37 @@ def test_nms_batched_problems_and_coordinate_trick():
     b, s = _nms_boxes(2500, seed=9)
     idxs = torch.randint(0, 5, (2500,), device="cuda")
     assert torch.equal(D.batched_nms(b, s, idxs, 0.7), torchvision.ops.batched_nms(b, s, idxs, 0.7))
+
+
+def test_multi_layer_pack_and_unpack_match_single_layer_calls():
+    """hd_pack_conv_weights / hd_unpack_wgrads (one launch for every layer) against the per-layer entry points."""
+    o = ops()
+    g = torch.Generator().manual_seed(0)
+    shapes = [(64, 3, 7, 160, False), (64, 64, 3, None, True), (16, 32, 3, None, True), (256, 128, 1, None, True), (16, 16, 3, None, True)]
+    ws, singles, multis = [], [], []
+    for cout, cin, k, k_pad, dg in shapes:
+        w = torch.randn(cout, cin, k, k, generator=g).cuda()
+        ws.append(w)
+        singles.append(o.PackedConv(cout, cin, k, "cuda", need_dgrad=dg, need_t=not dg, k_pad=k_pad).pack(w))
+        multis.append(o.PackedConv(cout, cin, k, "cuda", need_dgrad=dg, need_t=not dg, k_pad=k_pad))
+        for t in (multis[-1].w_fwd, multis[-1].w_dgrad, multis[-1].w_t):
+            if t is not None:
+                t.fill_(float("nan"))
+    o.pack_conv_weights(o.pack_table(multis, ws, "cuda"))
+    torch.cuda.synchronize()
+    for a, b in zip(singles, multis):
+        for x, y in ((a.w_fwd, b.w_fwd), (a.w_dgrad, b.w_dgrad), (a.w_t, b.w_t)):
+            assert (x is None) == (y is None)
+            if x is not None:
+                assert torch.equal(x, y)
+    entries, refs = [], []
+    for cout, cin, k, k_pad, dg in shapes:
+        row = k_pad if k_pad else k * k * cin
+        dw = torch.randn(cout, row, generator=g).cuda()
+        ga, gb = torch.empty(cout, cin, k, k, device="cuda"), torch.full((cout, cin, k, k), float("nan"), device="cuda")
+        o.unpack_wgrad(dw, ga, cout, cin, k, cin, row)
+        entries.append((dw, gb, cout, cin, k, cin, row))
+        refs.append(ga)
+    o.unpack_wgrads(o.unpack_table(entries, "cuda"))
+    torch.cuda.synchronize()
+    assert all(torch.equal(r, e[1]) for r, e in zip(refs, entries))

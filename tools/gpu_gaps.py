@@ -1,6 +1,6 @@
-"""Ad-hoc: GPU idle gaps in one train step (torch.profiler kernel timeline)."""
+"""GPU idle gaps in one train step (torch.profiler kernel timeline)."""
 import os, sys, time, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hallucidet_b200.train import HalluciDetTrainer
 from oracle import step as ostep
 from torch.profiler import profile, ProfilerActivity

@@ -1,6 +1,6 @@
-"""Ad-hoc: torch.profiler view of one train step -- total GPU kernel time vs wall, top kernels, launch count."""
+"""torch.profiler view of one train step -- total GPU kernel time vs wall, top kernels, launch count."""
 import os, sys, time, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hallucidet_b200.train import HalluciDetTrainer
 from oracle import step as ostep
 from torch.profiler import profile, ProfilerActivity

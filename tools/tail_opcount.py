@@ -1,6 +1,6 @@
-"""Ad-hoc: kernels launched and CPU time per section of the detection tail."""
+"""kernels launched and CPU time per section of the detection tail."""
 import os, sys, time, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hallucidet_b200.train import HalluciDetTrainer, expand_one_channel_to_output_channels
 from hallucidet_b200 import detection as D
 from oracle import step as ostep

@@ -1,6 +1,6 @@
-"""Ad-hoc: time the tcgen05 wgrad for one shape across split_k values."""
+"""time the tcgen05 wgrad for one shape across split_k values."""
 import os, sys, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hallucidet_b200 import ops
 dev = torch.device("cuda", 0)
 B = 8
