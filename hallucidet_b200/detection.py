@@ -110,7 +110,7 @@ def batched_nms(boxes, scores, idxs, iou_threshold):
     if boxes.numel() == 0:
         return torch.empty((0,), dtype=torch.int64, device=boxes.device)
     max_coordinate = boxes.max()
-    offsets = idxs.to(boxes) * (max_coordinate + torch.tensor(1).to(boxes))
+    offsets = idxs.to(boxes) * (max_coordinate + 1)
     boxes_for_nms = boxes + offsets[:, None]
     return ops.nms(boxes_for_nms, scores, iou_threshold)
 
@@ -132,6 +132,24 @@ def _clip_boxes_batched(boxes, image_shapes):
         bx = torch.minimum(torch.maximum(bx, zero), w)
         by = torch.minimum(torch.maximum(by, zero), h)
     return torch.stack((bx, by), dim=dim).reshape(boxes.shape)
+
+
+_CODER_WEIGHTS = {}
+
+
+def _coder_weights(box_coder, dtype, device):
+    """BoxCoder.weights as a cached device tensor (torchvision's encode_single re-creates it -- a host->device copy --
+    on every call)."""
+    key = (tuple(box_coder.weights), dtype, str(device))
+    w = _CODER_WEIGHTS.get(key)
+    if w is None:
+        w = _CODER_WEIGHTS[key] = torch.as_tensor(box_coder.weights, dtype=dtype, device=device)
+    return w
+
+
+def _encode_single(box_coder, reference_boxes, proposals):
+    from torchvision.models.detection._utils import encode_boxes
+    return encode_boxes(reference_boxes, proposals, _coder_weights(box_coder, reference_boxes.dtype, reference_boxes.device))
 
 
 class _Pending:
@@ -162,7 +180,7 @@ def _filter_nms_batched_begin(boxes, scores, idxs, valid, nms_thresh, top_n):
     B, M = scores.shape
     neg_inf = float("-inf")
     max_coord = boxes.masked_fill(~valid[..., None], neg_inf).amax(dim=(1, 2))                     # boxes.max() of the survivors
-    offsets = idxs.to(boxes) * (max_coord + torch.tensor(1).to(boxes))[:, None]
+    offsets = idxs.to(boxes) * (max_coord + 1)[:, None]
     boxes_for_nms = boxes + offsets[..., None]
     order = torch.sort(scores.masked_fill(~valid, neg_inf), dim=1, descending=True, stable=True)[1]
     gidx = order[..., None].expand(-1, -1, 4)
@@ -172,9 +190,13 @@ def _filter_nms_batched_begin(boxes, scores, idxs, valid, nms_thresh, top_n):
     sel = keep & (keep.cumsum(1) <= top_n)
 
     def finish(n_sel):
-        out_boxes = torch.gather(boxes, 1, gidx)[sel].split(n_sel)
-        out_scores = torch.gather(scores, 1, order)[sel].split(n_sel)
-        out_idxs = torch.gather(idxs, 1, order)[sel].split(n_sel)
+        # sel is row-major, so the flat positions of its set bits are the per-image results back to back; their number is
+        # known on the host now, so no boolean-mask indexing (each would be a nonzero + host sync)
+        pos = torch.nonzero_static(sel.reshape(-1), size=sum(n_sel))[:, 0]
+        src = (order + torch.arange(B, device=order.device)[:, None] * M).reshape(-1)[pos]      # flat index into [B*M]
+        out_boxes = boxes.reshape(-1, 4)[src].split(n_sel)
+        out_scores = scores.reshape(-1)[src].split(n_sel)
+        out_idxs = idxs.reshape(-1)[src].split(n_sel)
         return out_boxes, out_scores, out_idxs
     return _Pending(sel.sum(1), finish)
 
@@ -379,9 +401,7 @@ def select_training_samples_batched(roi_heads, proposals, targets, return_num_po
     out_matched = clamped.view(-1)[flat]
     img_of = torch.div(flat, N, rounding_mode="floor")
     matched_gt = gt.view(-1, 4)[img_of * G + out_matched]
-    weights = torch.as_tensor(roi_heads.box_coder.weights, dtype=dtype, device=device)
-    from torchvision.models.detection._utils import encode_boxes
-    regression_targets = encode_boxes(matched_gt, out_props, weights)
+    regression_targets = _encode_single(roi_heads.box_coder, matched_gt, out_props)
     out = (list(out_props.split(per_image)), list(out_matched.split(per_image)), list(out_labels.split(per_image)),
            list(regression_targets.split(per_image)))
     if return_num_pos:                                   # sampled foreground boxes == entries with label > 0 (host-known)
@@ -557,7 +577,7 @@ def rpn_eval(model, images, features, targets):
         # filter up to its NMS); the proposal counts and the sampler's positive / negative counts then come back in ONE read
         with torch.no_grad():
             labels, matched_gt_boxes = assign_targets_to_anchors_batched(model.rpn, anchors, targets)
-            regression_targets = model.rpn.box_coder.encode_single(matched_gt_boxes.reshape(-1, 4), torch.cat(anchors, dim=0))
+            regression_targets = _encode_single(model.rpn.box_coder, matched_gt_boxes.reshape(-1, 4), torch.cat(anchors, dim=0))
             pend_samples = _sample_batched_begin(model.rpn.fg_bg_sampler, labels)
         pend_boxes = filter_proposals_batched_begin(model.rpn, proposals, objectness, images.image_sizes, num_anchors_per_level)
         (boxes, scores), samples = _resolve(pend_boxes, pend_samples)
@@ -665,12 +685,12 @@ def roi_heads_eval(model, features, proposals, image_shapes, targets=None, train
     return result, losses
 
 
-def eval_forward_fasterrcnn(model, images, targets, train_det=False, model_name="fasterrcnn"):
-    if not train_det:
-        model.eval()
-    _check_targets(targets)
-    original_image_sizes = [tuple(img.shape[-2:]) for img in images]
-    images, targets = model.transform(images, targets)
+def _assert_no_degenerate_boxes(targets):
+    """The reference's per-image check (src/utils/eval_forward_fasterrcnn.py:40-53, one host sync per image) with one sync
+    for the batch; the per-image search only runs to build the error message."""
+    all_boxes = torch.cat([t["boxes"].reshape(-1, 4) for t in targets], 0)
+    if all_boxes.numel() == 0 or not bool((all_boxes[:, 2:] <= all_boxes[:, :2]).any()):
+        return
     for target_idx, target in enumerate(targets):
         boxes = target["boxes"]
         degenerate_boxes = boxes[:, 2:] <= boxes[:, :2]
@@ -678,6 +698,15 @@ def eval_forward_fasterrcnn(model, images, targets, train_det=False, model_name=
             bb_idx = torch.where(degenerate_boxes.any(dim=1))[0][0]
             torch._assert(False, "All bounding boxes should have positive height and width."
                                  f" Found invalid box {boxes[bb_idx].tolist()} for target at index {target_idx}.")
+
+
+def eval_forward_fasterrcnn(model, images, targets, train_det=False, model_name="fasterrcnn"):
+    if not train_det and model.training:                 # (Module.eval() walks every sub-module: only when the mode changes)
+        model.eval()
+    _check_targets(targets)
+    original_image_sizes = [tuple(img.shape[-2:]) for img in images]
+    images, targets = model.transform(images, targets)
+    _assert_no_degenerate_boxes(targets)
     features = model.backbone(images.tensors)
     if isinstance(features, torch.Tensor):
         features = OrderedDict([("0", features)])

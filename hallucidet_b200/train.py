@@ -188,9 +188,11 @@ class HalluciDetTrainer(nn.Module):
 
     def _flat_grad(self):
         """The U-Net engine's flat fp32 gradient block, if the parameters' .grad tensors are views into it."""
-        params = [p for p in self.encoder_decoder.parameters() if p.grad is not None]
+        first = getattr(self, "_first_param", None)
+        if first is None:
+            first = self._first_param = next(iter(self.encoder_decoder.parameters()))
         eng = next((e for e in self.encoder_decoder._engines.values() if e.training), None)
-        if eng is not None and params and params[0].grad.data_ptr() == eng.flat_grad.data_ptr():
+        if eng is not None and first.grad is not None and first.grad.data_ptr() == eng.flat_grad.data_ptr():
             return eng.flat_grad
         return None
 
@@ -204,7 +206,8 @@ class HalluciDetTrainer(nn.Module):
 
     def training_step(self, imgs_rgb, targets_rgb, imgs_ir, targets_ir, det_seed=None):
         from . import detection
-        self.encoder_decoder.train()
+        if not self.encoder_decoder.training:
+            self.encoder_decoder.train()
         self.optimizer.zero_grad(set_to_none=True)
         detection.DEFER_DETECTIONS = True           # the detections are a by-product here: assemble them after the backward
         try:
