@@ -152,6 +152,52 @@ def _encode_single(box_coder, reference_boxes, proposals):
     return encode_boxes(reference_boxes, proposals, _coder_weights(box_coder, reference_boxes.dtype, reference_boxes.device))
 
 
+def _decode(box_coder, rel_codes, boxes):
+    """``BoxCoder.decode`` + ``decode_single`` (TV models/detection/_utils.py:162-226) with the two 0.5 factors as Python
+    scalars: torchvision builds ``torch.tensor(0.5, device=...)`` twice per call, i.e. two blocking host->device copies.
+    0.5 is exact in every float type, so the products are identical."""
+    boxes_per_image = [b.size(0) for b in boxes]
+    concat_boxes = torch.cat(boxes, dim=0)
+    box_sum = sum(boxes_per_image)
+    if box_sum > 0:
+        rel_codes = rel_codes.reshape(box_sum, -1)
+    b = concat_boxes.to(rel_codes.dtype)
+    widths = b[:, 2] - b[:, 0]
+    heights = b[:, 3] - b[:, 1]
+    ctr_x = b[:, 0] + 0.5 * widths
+    ctr_y = b[:, 1] + 0.5 * heights
+    wx, wy, ww, wh = box_coder.weights
+    dx = rel_codes[:, 0::4] / wx
+    dy = rel_codes[:, 1::4] / wy
+    dw = rel_codes[:, 2::4] / ww
+    dh = rel_codes[:, 3::4] / wh
+    dw = torch.clamp(dw, max=box_coder.bbox_xform_clip)
+    dh = torch.clamp(dh, max=box_coder.bbox_xform_clip)
+    pred_ctr_x = dx * widths[:, None] + ctr_x[:, None]
+    pred_ctr_y = dy * heights[:, None] + ctr_y[:, None]
+    pred_w = torch.exp(dw) * widths[:, None]
+    pred_h = torch.exp(dh) * heights[:, None]
+    c_to_c_h = 0.5 * pred_h
+    c_to_c_w = 0.5 * pred_w
+    pred_boxes = torch.stack((pred_ctr_x - c_to_c_w, pred_ctr_y - c_to_c_h, pred_ctr_x + c_to_c_w, pred_ctr_y + c_to_c_h), dim=2).flatten(1)
+    if box_sum > 0:
+        pred_boxes = pred_boxes.reshape(box_sum, -1, 4)
+    return pred_boxes
+
+
+_DEFERRED_CHECKS = []
+
+
+def _run_deferred_checks():
+    """Asynchronous input checks (flag copied to pinned memory when the check was issued) are evaluated at the next host
+    sync the step performs anyway."""
+    while _DEFERRED_CHECKS:
+        event, flag, on_fail = _DEFERRED_CHECKS.pop(0)
+        event.synchronize()
+        if bool(flag.item()):
+            on_fail()
+
+
 class _Pending:
     """Device work has been enqueued; the host still needs ``counts_dev`` (data-dependent sizes) to finish.  Several
     pending results are resolved with ONE device->host read (``_resolve``), so independent parts of the tail share a sync."""
@@ -162,6 +208,7 @@ class _Pending:
 
 def _resolve(*pending):
     flat = torch.cat([p.counts_dev.to(torch.int64) for p in pending]).tolist()              # the one host sync
+    _run_deferred_checks()
     out, o = [], 0
     for p in pending:
         n = p.counts_dev.numel()
@@ -244,7 +291,7 @@ def postprocess_detections_batched_begin(roi_heads, class_logits, box_regression
     device = class_logits.device
     num_classes = class_logits.shape[-1]
     boxes_per_image = [b.shape[0] for b in proposals]
-    pred_boxes = roi_heads.box_coder.decode(box_regression, proposals)
+    pred_boxes = _decode(roi_heads.box_coder, box_regression, proposals)
     pred_scores = F.softmax(class_logits, -1)
     B, n_max = len(boxes_per_image), max(boxes_per_image)
     if all(n == n_max for n in boxes_per_image):
@@ -566,7 +613,7 @@ def rpn_eval(model, images, features, targets):
     num_images = len(anchors)
     num_anchors_per_level = [o[0].shape[0] * o[0].shape[1] * o[0].shape[2] for o in objectness]
     objectness, pred_bbox_deltas = concat_box_prediction_layers(objectness, pred_bbox_deltas)
-    proposals = model.rpn.box_coder.decode(pred_bbox_deltas.detach(), anchors)
+    proposals = _decode(model.rpn.box_coder, pred_bbox_deltas.detach(), anchors)
     proposals = proposals.view(num_images, -1, 4)
     pre_nms = sum(min(model.rpn.pre_nms_top_n(), n) for n in num_anchors_per_level)
     if targets is None:
@@ -686,18 +733,32 @@ def roi_heads_eval(model, features, proposals, image_shapes, targets=None, train
 
 
 def _assert_no_degenerate_boxes(targets):
-    """The reference's per-image check (src/utils/eval_forward_fasterrcnn.py:40-53, one host sync per image) with one sync
-    for the batch; the per-image search only runs to build the error message."""
+    """The reference's per-image check (src/utils/eval_forward_fasterrcnn.py:40-53: one blocking host sync per image, the
+    first of which waits for the whole U-Net forward).  Here the "any degenerate box" flag of the batch is computed on the
+    device, copied to pinned memory without blocking, and examined at the step's next host sync (``_resolve``); the same
+    assertion with the same message is raised there."""
     all_boxes = torch.cat([t["boxes"].reshape(-1, 4) for t in targets], 0)
-    if all_boxes.numel() == 0 or not bool((all_boxes[:, 2:] <= all_boxes[:, :2]).any()):
+    if all_boxes.numel() == 0:
         return
-    for target_idx, target in enumerate(targets):
-        boxes = target["boxes"]
-        degenerate_boxes = boxes[:, 2:] <= boxes[:, :2]
-        if degenerate_boxes.any():
-            bb_idx = torch.where(degenerate_boxes.any(dim=1))[0][0]
-            torch._assert(False, "All bounding boxes should have positive height and width."
-                                 f" Found invalid box {boxes[bb_idx].tolist()} for target at index {target_idx}.")
+
+    def fail():
+        for target_idx, target in enumerate(targets):
+            boxes = target["boxes"]
+            degenerate_boxes = boxes[:, 2:] <= boxes[:, :2]
+            if degenerate_boxes.any():
+                bb_idx = torch.where(degenerate_boxes.any(dim=1))[0][0]
+                torch._assert(False, "All bounding boxes should have positive height and width."
+                                     f" Found invalid box {boxes[bb_idx].tolist()} for target at index {target_idx}.")
+    bad = (all_boxes[:, 2:] <= all_boxes[:, :2]).any()
+    if not all_boxes.is_cuda:
+        if bool(bad):
+            fail()
+        return
+    flag = torch.empty((), dtype=torch.bool, pin_memory=True)
+    flag.copy_(bad, non_blocking=True)
+    event = torch.cuda.Event()
+    event.record()
+    _DEFERRED_CHECKS.append((event, flag, fail))
 
 
 def eval_forward_fasterrcnn(model, images, targets, train_det=False, model_name="fasterrcnn"):
@@ -717,6 +778,7 @@ def eval_forward_fasterrcnn(model, images, targets, train_det=False, model_name=
         detections.then(lambda d: model.transform.postprocess(d, image_sizes, original_image_sizes))
     else:
         detections = model.transform.postprocess(detections, images.image_sizes, original_image_sizes)
+    _run_deferred_checks()                                # (already evaluated at the first host sync on the batched path)
     losses = {}
     losses.update(detector_losses)
     losses.update(proposal_losses)

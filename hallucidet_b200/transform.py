@@ -8,6 +8,7 @@ batched CUDA kernel with a gather backward (hd_resize_nearest_fwd/bwd), instead 
 import math
 from typing import Dict, List, Optional, Tuple
 
+import numpy as np
 import torch
 import torch.nn as nn
 from torchvision.models.detection.image_list import ImageList
@@ -19,8 +20,7 @@ def resize_boxes(boxes, original_size, new_size):
     """custom_generalized_transform.py:325-338."""
     # the reference divides two fp32 device scalars per box list (4 host->device copies per call, 16 calls per step); the
     # same fp32 quotient computed on the host and passed as a Python scalar multiplies the fp32 boxes identically
-    ratio_height, ratio_width = [float(torch.tensor(float(s), dtype=torch.float32) / torch.tensor(float(s_orig), dtype=torch.float32))
-                                 for s, s_orig in zip(new_size, original_size)]
+    ratio_height, ratio_width = [float(np.float32(s) / np.float32(s_orig)) for s, s_orig in zip(new_size, original_size)]
     xmin, ymin, xmax, ymax = boxes.unbind(1)
     return torch.stack((xmin * ratio_width, ymin * ratio_height, xmax * ratio_width, ymax * ratio_height), dim=1)
 

@@ -442,3 +442,21 @@ def test_concurrent_postprocess_equals_torchvision():
                 assert [p.shape for p in x] == [q.shape for q in y]
                 assert all(torch.equal(p, q) for p, q in zip(x, y))
     assert sum(p.shape[0] for p in a[0]) > 0
+
+
+def test_degenerate_target_box_still_raises():
+    """The reference asserts on zero-area target boxes before the detector runs (src/utils/eval_forward_fasterrcnn.py:40-53);
+    the batched, non-blocking version of that check must still raise within the step."""
+    from oracle import step as ostep
+    from hallucidet_b200.train import HalluciDetTrainer
+    ir, rgb, targets = ostep.synthetic_batch(2, 128, 128, seed=3, device="cuda")
+    tr = HalluciDetTrainer(detector_name="fasterrcnn", size=128, seed=123)
+    tr.training_step(rgb, targets, ir, targets)                      # sane targets: fine
+    bad = [dict(t) for t in targets]
+    bad[1]["boxes"] = bad[1]["boxes"].clone()
+    bad[1]["boxes"][0, 2] = bad[1]["boxes"][0, 0]                    # zero width
+    with pytest.raises(AssertionError, match="positive height and width"):
+        tr.training_step(rgb, bad, ir, bad)
+    torch.cuda.synchronize()
+    out = tr.training_step(rgb, targets, ir, targets)                # the trainer stays usable
+    assert torch.isfinite(out["total"])
