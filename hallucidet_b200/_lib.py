@@ -80,6 +80,8 @@ PROTOTYPES = {
     "hd_multi_blocks": [ctypes.c_int64],
     "hd_pack_conv_weights": [c_void_p, c_int, c_int, c_void_p],
     "hd_unpack_wgrads": [c_void_p, c_int, c_int, c_void_p],
+    "hd_roi_align_bwd_nhwc": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
+    "hd_nhwc_to_nchw_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "hd_nms": [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p],
 }
 _RESTYPES = {"hd_last_error": ctypes.c_char_p}

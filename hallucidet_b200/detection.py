@@ -472,6 +472,32 @@ def fastrcnn_loss_static(class_logits, box_regression, labels, regression_target
     return classification_loss, box_loss
 
 
+class _RoIAlign(torch.autograd.Function):
+    """torchvision's roi_align forward op unchanged; backward on hd_roi_align_bwd_nhwc (ops.roi_align_bwd)."""
+
+    @staticmethod
+    def forward(ctx, feat, rois, spatial_scale, output_size, sampling_ratio):
+        ctx.save_for_backward(rois)
+        ctx.cfg = (tuple(feat.shape), float(spatial_scale), int(sampling_ratio))
+        return torch.ops.torchvision.roi_align(feat, rois, float(spatial_scale), int(output_size[0]), int(output_size[1]),
+                                               int(sampling_ratio), False)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (rois,) = ctx.saved_tensors
+        shape, spatial_scale, sampling_ratio = ctx.cfg
+        return ops.roi_align_bwd(grad.contiguous(), rois.contiguous(), shape, spatial_scale, sampling_ratio), None, None, None, None
+
+
+def _roi_align(feat, rois, output_size, spatial_scale, sampling_ratio):
+    from torchvision.ops import roi_align
+    c = feat.shape[1]
+    if (ROI_ALIGN_BWD and feat.is_cuda and feat.dtype == torch.float32 and rois.dtype == torch.float32 and feat.requires_grad
+            and 1 <= sampling_ratio <= 2 and output_size[0] * output_size[1] <= 49 and c % 4 == 0 and c <= 256 and 256 % (c // 4) == 0):
+        return _RoIAlign.apply(feat, rois, spatial_scale, tuple(output_size), sampling_ratio)
+    return roi_align(feat, rois, output_size=output_size, spatial_scale=spatial_scale, sampling_ratio=sampling_ratio)
+
+
 def multiscale_roi_align_one_sync(pooler, features, boxes, image_shapes):
     """``torchvision.ops.MultiScaleRoIAlign.forward`` (TV ops/poolers.py) with the per-level ``torch.where(levels == k)``
     (one host sync per FPN level) replaced by a stable sort of the level ids and one ``bincount`` read: the index lists
@@ -493,8 +519,7 @@ def multiscale_roi_align_one_sync(pooler, features, boxes, image_shapes):
     for level, (feat, scale) in enumerate(zip(x_filtered, pooler.scales)):
         idx_in_level = order[o:o + counts[level]]
         o += counts[level]
-        pooled = roi_align(feat, rois[idx_in_level], output_size=pooler.output_size, spatial_scale=scale,
-                           sampling_ratio=pooler.sampling_ratio)
+        pooled = _roi_align(feat, rois[idx_in_level], pooler.output_size, scale, pooler.sampling_ratio)
         result[idx_in_level] = pooled.to(result.dtype)
     return result
 
@@ -572,6 +597,7 @@ import os as _os
 CONCURRENT_NMS = _os.environ.get("HD_CONCURRENT_NMS", "1") != "0"                   # proposal filtering
 CONCURRENT_POSTPROCESS = _os.environ.get("HD_CONCURRENT_POSTPROCESS", "0") != "0"   # final detections
 BATCHED_TAIL = _os.environ.get("HD_BATCHED_TAIL", "1") != "0"   # whole-batch proposal filter / detections post-processing
+ROI_ALIGN_BWD = _os.environ.get("HD_ROI_ALIGN_BWD", "1") != "0"   # RoIAlign backward on hd_roi_align_bwd_nhwc
 DEFER_DETECTIONS = False    # set by HalluciDetTrainer.training_step: roi_heads_eval returns a DeferredDetections
 
 

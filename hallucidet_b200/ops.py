@@ -450,3 +450,21 @@ def nms_sorted_flat(sorted_boxes, offsets, iou_threshold, counts=None):
                                  _stream()), "hd_nms")
     LAUNCHES += 1
     return keep
+
+
+def roi_align_bwd(grad_out, rois, input_shape, spatial_scale, sampling_ratio):
+    """Gradient of torchvision.ops.roi_align(aligned=False) w.r.t. its fp32 NCHW input of shape ``input_shape``, for grad_out
+    [K, C, PH, PW]: channels-last vector reductions (hd_roi_align_bwd_nhwc) + one layout conversion.  Returns NCHW fp32."""
+    global LAUNCHES
+    k, c, ph, pw = grad_out.shape
+    n, c2, h, w = input_shape
+    assert c == c2 and grad_out.dtype == torch.float32 and rois.dtype == torch.float32
+    assert grad_out.is_contiguous() and rois.is_contiguous() and tuple(rois.shape) == (k, 5)
+    scratch = torch.zeros(n, h, w, c, dtype=torch.float32, device=grad_out.device)
+    out = torch.empty(n, c, h, w, dtype=torch.float32, device=grad_out.device)
+    with _Timed("roi_align_bwd"):
+        check(_lib.load().hd_roi_align_bwd_nhwc(_ptr(grad_out), _ptr(rois), _ptr(scratch), k, c, h, w, ph, pw, float(spatial_scale),
+                                                int(sampling_ratio), _stream()), "hd_roi_align_bwd_nhwc")
+        check(_lib.load().hd_nhwc_to_nchw_f32(_ptr(scratch), _ptr(out), n, c, h, w, _stream()), "hd_nhwc_to_nchw_f32")
+    LAUNCHES += 1
+    return out

@@ -194,6 +194,18 @@ int hd_regulariser(int kind, const float* hal, const float* rgb, const float* ir
 int hd_nms(const float* boxes_sorted, const int* offsets, const int* counts_dev, int problems, float iou_threshold,
            void* mask_ws, unsigned char* keep, hd_stream stream);
 
+/* ---- RoIAlign backward (box head pooling over the FPN levels) ------------------------------------------------
+ * grad_in_nhwc ([n][h][w][c] fp32 channels-last scratch, zeroed by the caller) += gradient of
+ * torchvision.ops.roi_align(input, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio, aligned = False) -- the op
+ * torchvision's MultiScaleRoIAlign calls per FPN level inside the reference's roi_heads_eval
+ * (src/utils/eval_forward_fasterrcnn.py:130) -- for grad_out [num_rois][c][pooled_h][pooled_w]; rois [num_rois][5] =
+ * (batch index, x1, y1, x2, y2).  Same per-contribution arithmetic as torchvision's roi_align_backward_kernel_impl, issued
+ * as coalesced 16-byte vector reductions over the channels.  c % 4 == 0, c <= 256, pooled_h*pooled_w <= 49, ratio 1..2.
+ * hd_nhwc_to_nchw_f32 converts the scratch to the [n][c][h][w] layout autograd expects. */
+int hd_roi_align_bwd_nhwc(const float* grad_out, const float* rois, float* grad_in_nhwc, int num_rois, int channels, int height,
+                          int width, int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio, hd_stream stream);
+int hd_nhwc_to_nchw_f32(const float* x_nhwc, float* y_nchw, int n, int channels, int height, int width, hd_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -561,3 +561,27 @@ def test_multi_layer_pack_and_unpack_match_single_layer_calls():
     o.unpack_wgrads(o.unpack_table(entries, "cuda"))
     torch.cuda.synchronize()
     assert all(torch.equal(r, e[1]) for r, e in zip(refs, entries))
+
+
+@pytest.mark.parametrize("h,w,scale,c", [(160, 160, 0.25, 256), (40, 40, 1.0 / 16, 256), (20, 24, 1.0 / 32, 64)])
+def test_roi_align_bwd_matches_torchvision(h, w, scale, c):
+    """hd_roi_align_bwd_nhwc (+ layout conversion) against the autograd of torchvision.ops.roi_align (aligned=False,
+    sampling_ratio 2, 7x7): RoIs of all sizes, partly outside the image, degenerate, larger than the image."""
+    import torchvision
+    o = ops()
+    g = torch.Generator().manual_seed(h)
+    n, k = 3, 200
+    feat = torch.randn(n, c, h, w, generator=g).cuda().requires_grad_(True)
+    img_w, img_h = w / scale, h / scale
+    xy = torch.rand(k, 2, generator=g) * torch.tensor([img_w, img_h]) - 20
+    wh = torch.rand(k, 2, generator=g) ** 2 * torch.tensor([img_w, img_h]) * 1.2 + 0.5
+    wh[:5] = 0.0                                               # degenerate boxes (width / height clamp to one pixel)
+    wh[5:8] = torch.tensor([img_w, img_h]) * 1.5               # larger than the image
+    rois = torch.cat([torch.randint(0, n, (k, 1), generator=g).float(), xy, xy + wh], 1).cuda()
+    out = torchvision.ops.roi_align(feat, rois, (7, 7), scale, 2, False)
+    gout = torch.randn(out.shape, generator=g).cuda()
+    (ref,) = torch.autograd.grad(out, feat, gout)
+    got = o.roi_align_bwd(gout.contiguous(), rois, tuple(feat.shape), scale, 2)
+    torch.cuda.synchronize()
+    assert float(ref.abs().max()) > 0 and got.shape == ref.shape
+    assert torch.allclose(got, ref, rtol=1e-4, atol=1e-5 * float(ref.abs().max()))
