@@ -255,39 +255,57 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, int rows, in
     }
 }
 
-__global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ scale,
+// The channel group of a thread is loop invariant (G = C/8 divides the 256-thread block, hence the grid stride), so the
+// per-channel coefficients live in registers; two 16-byte groups are in flight per thread and iteration.
+__global__ void __launch_bounds__(kEwThreads) bn_apply_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ scale,
                                 const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
                                 const float* __restrict__ rscale, const float* __restrict__ rshift, int relu,
                                 __nv_bfloat16* __restrict__ y, long n_pix, int C) {
     const int G = C / 8;
     const long total = n_pix * G;
-    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long>(gridDim.x) * blockDim.x) {
-        const int c0 = static_cast<int>(i % G) * 8;
-        bf8 v;
-        v.load(z + i * 8);
-        float f[8];
-        v.unpack(f);
+    const int c0 = static_cast<int>(threadIdx.x % G) * 8;
+    float sc[8], sh[8], rs[8], rb[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], __ldg(scale + c0 + j), __ldg(shift + c0 + j));
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = __ldg(scale + c0 + j); sh[j] = __ldg(shift + c0 + j);
+        rs[j] = rscale ? __ldg(rscale + c0 + j) : 1.f; rb[j] = rscale ? __ldg(rshift + c0 + j) : 0.f;
+    }
+    const long stride = static_cast<long>(gridDim.x) * blockDim.x;
+    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += 2 * stride) {
+        const long i2 = i + stride;
+        const bool two = i2 < total;
+        bf8 v[2], rv[2];
+        v[0].load(z + i * 8);
+        if (two) v[1].load(z + i2 * 8);
         if (res) {
-            bf8 rv;
-            rv.load(res + i * 8);
-            float r[8];
-            rv.unpack(r);
-            if (rscale) {
+            rv[0].load(res + i * 8);
+            if (two) rv[1].load(res + i2 * 8);
+        }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) r[j] = fmaf(r[j], __ldg(rscale + c0 + j), __ldg(rshift + c0 + j));
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+            float f[8];
+            v[u].unpack(f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+            if (res) {
+                float r[8];
+                rv[u].unpack(r);
+                if (rscale) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r[j] = fmaf(r[j], rs[j], rb[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] += r[j];
             }
+            if (relu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] += r[j];
+                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            bf8 o;
+            o.pack(f);
+            o.store(y + (u ? i2 : i) * 8);
         }
-        if (relu) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        v.pack(f);
-        v.store(y + i * 8);
     }
 }
 
@@ -313,27 +331,36 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const
     long p1 = p0 + pix_per_block;
     if (p1 > n_pix) p1 = n_pix;
     if (l < L) {
-        for (long p = p0 + l; p < p1; p += L) {
-            const long off = p * C + g * 8;
-            bf8 d, zz;
-            d.load(dy + off);
-            zz.load(z + off);
-            float df[8], zf[8];
-            d.unpack(df);
-            zz.unpack(zf);
-            if (yrelu) {
-                bf8 yy;
-                yy.load(yrelu + off);
-                float yf[8];
-                yy.unpack(yf);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) if (!(yf[j] > 0.f)) df[j] = 0.f;
-            } else if (rscale) {                      // ReLU directly after this BN: the mask is recomputed from z
-#pragma unroll
-                for (int j = 0; j < 8; ++j) if (!(fmaf(zf[j], rs[j], rb[j]) > 0.f)) df[j] = 0.f;
+        for (long p = p0 + l; p < p1; p += 2 * L) {   // two pixels (16-byte groups) in flight per thread
+            const bool two = p + L < p1;
+            const long offs[2] = {p * C + g * 8, (p + L) * C + g * 8};
+            bf8 d[2], zz[2], yy[2];
+            d[0].load(dy + offs[0]);
+            zz[0].load(z + offs[0]);
+            if (yrelu) yy[0].load(yrelu + offs[0]);
+            if (two) {
+                d[1].load(dy + offs[1]);
+                zz[1].load(z + offs[1]);
+                if (yrelu) yy[1].load(yrelu + offs[1]);
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { a[j] += df[j]; b[j] += df[j] * (zf[j] - mu[j]) * is[j]; }
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && !two) break;
+                float df[8], zf[8];
+                d[u].unpack(df);
+                zz[u].unpack(zf);
+                if (yrelu) {
+                    float yf[8];
+                    yy[u].unpack(yf);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) if (!(yf[j] > 0.f)) df[j] = 0.f;
+                } else if (rscale) {                  // ReLU directly after this BN: the mask is recomputed from z
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) if (!(fmaf(zf[j], rs[j], rb[j]) > 0.f)) df[j] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { a[j] += df[j]; b[j] += df[j] * (zf[j] - mu[j]) * is[j]; }
+            }
         }
         if (G < 32 && (G & (G - 1)) == 0) {              // lanes sharing a channel group inside the warp
             for (int o = 16; o >= G; o >>= 1) {
@@ -356,7 +383,7 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[i], sacc[i]);
 }
 
-__global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ yrelu,
+__global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ yrelu,
                                     const float* __restrict__ rscale, const float* __restrict__ rshift,
                                     const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
                                     const float* __restrict__ invstd, const float* __restrict__ gamma,
@@ -370,9 +397,21 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const 
             if (dgamma) dgamma[c] = sums[C + c];
         }
     }
+    // loop-invariant channel group (see bn_apply_kernel): coefficients in registers
+    const int c0 = static_cast<int>(threadIdx.x % G) * 8;
+    // dz = k1 * (g - m1 - xhat * m2), xhat = (z - mu) * is  ==  A * g + B * z + D  (three coefficients per channel)
+    float ca[8], cb[8], cd[8], rs[8], rb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        const float is = __ldg(invstd + c), mu = __ldg(mean + c);
+        const float k1 = __ldg(gamma + c) * is;
+        const float m1 = __ldg(sums + c) * inv_count, m2 = __ldg(sums + C + c) * inv_count;
+        ca[j] = k1; cb[j] = -k1 * is * m2; cd[j] = k1 * (is * m2 * mu - m1);
+        rs[j] = rscale ? __ldg(rscale + c) : 0.f; rb[j] = rscale ? __ldg(rshift + c) : 0.f;
+    }
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
-        const int c0 = static_cast<int>(i % G) * 8;
         bf8 d, zz;
         d.load(dy + i * 8);
         zz.load(z + i * 8);
@@ -388,15 +427,10 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const 
             for (int j = 0; j < 8; ++j) if (!(yf[j] > 0.f)) df[j] = 0.f;
         } else if (rscale) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) if (!(fmaf(zf[j], __ldg(rscale + c0 + j), __ldg(rshift + c0 + j)) > 0.f)) df[j] = 0.f;
+            for (int j = 0; j < 8; ++j) if (!(fmaf(zf[j], rs[j], rb[j]) > 0.f)) df[j] = 0.f;
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = c0 + j;
-            const float is = __ldg(invstd + c);
-            const float xh = (zf[j] - __ldg(mean + c)) * is;
-            o[j] = __ldg(gamma + c) * is * (df[j] - __ldg(sums + c) * inv_count - xh * __ldg(sums + C + c) * inv_count);
-        }
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(ca[j], df[j], fmaf(cb[j], zf[j], cd[j]));
         bf8 ov;
         ov.pack(o);
         ov.store(dz + i * 8);
@@ -1002,7 +1036,7 @@ extern "C" int hd_bn_finalize(const float* stats, int reps, int C, double count,
 
 extern "C" int hd_bn_apply(const void* z, const float* scale, const float* shift, const void* res, const float* rscale,
                            const float* rshift, int relu, void* y, int64_t n_pix, int C, hd_stream st) {
-    HD_CHECK_ARG(z && scale && shift && y && C % 8 == 0 && n_pix > 0);
+    HD_CHECK_ARG(z && scale && shift && y && C % 8 == 0 && n_pix > 0 && kEwThreads % (C / 8) == 0);
     bn_apply_kernel<<<ew_blocks(n_pix * (C / 8)), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
         static_cast<const __nv_bfloat16*>(z), scale, shift, static_cast<const __nv_bfloat16*>(res), rscale, rshift, relu,
         static_cast<__nv_bfloat16*>(y), n_pix, C);
@@ -1018,6 +1052,7 @@ extern "C" int hd_bn_bwd_reduce(const void* dy, const void* yrelu, const float* 
     if (L < 1) L = 1;
     const int threads = G * L;
     long blocks = 148L * 4;
+    if (blocks > n_pix / 128) blocks = n_pix / 128 > 0 ? n_pix / 128 : 1;   // small maps: fewer, fatter blocks (2C atomics each)
     long ppb = (n_pix + blocks - 1) / blocks;
     if (ppb < L) ppb = L;
     blocks = (n_pix + ppb - 1) / ppb;
@@ -1031,7 +1066,7 @@ extern "C" int hd_bn_bwd_reduce(const void* dy, const void* yrelu, const float* 
 extern "C" int hd_bn_bwd_apply(const void* dy, const void* yrelu, const float* rscale, const float* rshift, const void* z,
                                const float* mean, const float* invstd, const float* gamma, const float* sums, double count,
                                void* dz, void* gout, float* dgamma, float* dbeta, int64_t n_pix, int C, hd_stream st) {
-    HD_CHECK_ARG(dy && z && mean && invstd && gamma && sums && dz && C % 8 == 0 && n_pix > 0 && count > 0);
+    HD_CHECK_ARG(dy && z && mean && invstd && gamma && sums && dz && C % 8 == 0 && n_pix > 0 && count > 0 && kEwThreads % (C / 8) == 0);
     bn_bwd_apply_kernel<<<ew_blocks(n_pix * (C / 8)), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
         static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(yrelu), rscale, rshift,
         static_cast<const __nv_bfloat16*>(z), mean, invstd, gamma, sums, static_cast<float>(1.0 / count),
