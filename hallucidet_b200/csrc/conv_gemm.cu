@@ -14,6 +14,10 @@
 // * input-gradient of a stride-2 convolution = 4 output phases (grid.z), each a dense stride-1 problem.
 //
 // Reference operators replaced: see include/hallucidet_b200.h (hd_conv_fwd / hd_conv_dgrad).
+#include <stdlib.h>
+
+#include <type_traits>
+
 #include "hd_common.cuh"
 
 #include <cstring>
@@ -61,6 +65,9 @@ struct ConvGemmParams {
     int a_sub, b_sub;           // bytes of one A / B sub-tile inside a stage
     int direct_store;
     __nv_bfloat16* out_ptr;
+    __nv_bfloat16* out_ptr2[2];  // both outputs (register-store epilogue)
+    int reg_store;              // epilogue writes its rows straight from registers (no staging / TMA store / CTA barriers)
+    int bias_floats;            // floats reserved for the bias of ALL output channels in shared memory
     int cp_mode;
     const __nv_bfloat16* a_ptr;
     int a_H, a_W, a_C;
@@ -96,7 +103,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const uint32_t stg_bytes = (128u * P.BN * 2u + 1023u) & ~1023u;
     const uint32_t staging0 = smem_base + static_cast<uint32_t>(stages * P.stage_bytes);  // 2 x (128 x BN bf16), 1024-aligned
     const uint32_t bias_s = staging0 + 2u * stg_bytes;                                     // BN floats
-    const uint32_t bar_base = bias_s + 512u;
+    const uint32_t bar_base = bias_s + 4u * static_cast<uint32_t>(P.bias_floats);
     // barriers: full[s], empty[s], tmem_full[2], tmem_empty[2], then the TMEM base-address slot
     const uint32_t full0 = bar_base, empty0 = bar_base + 8u * stages;
     const uint32_t tfull0 = bar_base + 16u * stages, tempty0 = tfull0 + 16u;
@@ -295,6 +302,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         const uint32_t row_off = static_cast<uint32_t>(row) * row_b;
         const uint32_t sw_x = ((row_off >> 7) & smask) << 4;
         const bool fused = P.add != nullptr || P.mask != nullptr;
+        // bias of every output channel (zero past Cout), once per CTA: no per-tile hand-off between the epilogue warps
+        if (P.bias != nullptr) {
+            for (int i = et; i < P.bias_floats; i += kEpiThreads) {
+                const float b = i < P.Cout_total ? __ldg(P.bias + i) : 0.f;
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * i), "f"(b) : "memory");
+            }
+        }
+        named_bar_sync(2, kEpiThreads);
         int acc = 0;
         uint32_t acc_phase = 0;
         int iter = 0;
@@ -310,13 +325,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const __nv_bfloat16* add_row = P.add != nullptr ? P.add + pix * P.Cout_total + n0 : nullptr;
             const __nv_bfloat16* mask_row = P.mask != nullptr ? P.mask + pix * P.Cout_total + n0 : nullptr;
 
-            // this staging buffer was last used two tiles ago: its TMA store must have finished reading it
-            if (iter >= 2 && et == 0) tma_store_wait_read1();
-            named_bar_sync(1, kEpiThreads);
-            if (P.bias != nullptr && et < P.BN) {
-                const int ch = n0 + et;
-                const float b = ch < P.Cout_total ? __ldg(P.bias + ch) : 0.f;
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * et), "f"(b) : "memory");
+            if (!P.reg_store) {
+                // this staging buffer was last used two tiles ago: its TMA store must have finished reading it
+                if (iter >= 2 && et == 0) tma_store_wait_read1();
+                named_bar_sync(1, kEpiThreads);
             }
             // fused-operand loads are software-pipelined one 16-column chunk ahead of their use
             uint4 na0 = make_uint4(0, 0, 0, 0), na1 = na0, nm0 = na0, nm1 = na0;
@@ -324,18 +336,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 if (add_row) { const uint4* ap = reinterpret_cast<const uint4*>(add_row + c_begin * 16); na0 = ap[0]; na1 = ap[1]; }
                 if (mask_row) { const uint4* mp = reinterpret_cast<const uint4*>(mask_row + c_begin * 16); nm0 = __ldg(mp); nm1 = __ldg(mp + 1); }
             }
-            named_bar_sync(2, kEpiThreads);
-
             mbar_wait(tfull0 + 8u * acc, acc_phase);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + acc * P.tmem_cols + (static_cast<uint32_t>(quad * 32) << 16);
+            // the chunk loop is instantiated twice: the common plain epilogue (bias / ReLU / bf16 store) carries none of the
+            // fused-operand or fp32-output bookkeeping
+            auto chunk_loop = [&](auto fused_tag, auto f32_tag) {
+            constexpr bool kFused = decltype(fused_tag)::value, kF32 = decltype(f32_tag)::value;
             for (int c16 = c_begin; c16 < c_end; ++c16) {
                 const int ch0 = n0 + c16 * 16;
                 const bool ch_ok = ch0 < P.Cout_total;
                 const uint4 a0 = na0, a1 = na1, m0 = nm0, m1 = nm1;
-                const bool has_add = add_row != nullptr && valid && ch_ok;
-                const bool has_mask = mask_row != nullptr && valid && ch_ok;
-                if (fused && c16 + 1 < c_end && valid && ch0 + 16 < P.Cout_total) {
+                const bool has_add = kFused && add_row != nullptr && valid && ch_ok;
+                const bool has_mask = kFused && mask_row != nullptr && valid && ch_ok;
+                if (kFused && c16 + 1 < c_end && valid && ch0 + 16 < P.Cout_total) {
                     if (add_row) { const uint4* ap = reinterpret_cast<const uint4*>(add_row + (c16 + 1) * 16); na0 = ap[0]; na1 = ap[1]; }
                     if (mask_row) { const uint4* mp = reinterpret_cast<const uint4*>(mask_row + (c16 + 1) * 16); nm0 = __ldg(mp); nm1 = __ldg(mp + 1); }
                 }
@@ -355,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     for (int j = 0; j < 16; j += 4) {
                         float b0, b1, b2, b3;
                         asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3)
-                                     : "r"(bias_s + 4u * (c16 * 16 + j)));
+                                     : "r"(bias_s + 4u * (ch0 + j)));
                         v[j] += b0; v[j + 1] += b1; v[j + 2] += b2; v[j + 3] += b3;
                     }
                 }
@@ -383,7 +397,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = 0.f;
                 }
-                if (P.out_f32 != nullptr && valid) {
+                if (kF32 && P.out_f32 != nullptr && valid) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int ch = ch0 + j;
@@ -394,7 +408,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         }
                     }
                 }
-                if (P.store_bf16) {
+                if (P.reg_store) {
+                    // one pixel row x 16 channels = 32 contiguous bytes = one full sector per thread: written straight from
+                    // registers; the epilogue warps never meet (no staging tile, fence, CTA barrier or TMA store)
+                    if (valid && ch_ok) {
+                        const int o = ch0 < P.out_C0 ? 0 : 1;
+                        const int co = o ? P.Cout_total - P.out_C0 : P.out_C0;
+                        uint4* dst = reinterpret_cast<uint4*>(P.out_ptr2[o] + pix * co + (o ? ch0 - P.out_C0 : ch0));
+                        dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                        dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+                    }
+                } else if (!kF32 || P.store_bf16) {
                     // channel offset inside the N tile -> 64-channel staging sub-tile (BN < 64: one sub-tile) + byte in row
                     const uint32_t cl = c16 * 16;
                     const uint32_t inner = (cl & 63u) * 2u;
@@ -408,13 +432,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d1), "r"(q1x), "r"(q1y), "r"(q1z), "r"(q1w) : "memory");
                 }
             }
+            };
+            if (!fused && P.out_f32 == nullptr) chunk_loop(std::false_type{}, std::false_type{});
+            else chunk_loop(std::true_type{}, std::true_type{});
             // accumulator drained: hand it back to the MMA issuer
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
 
-            if (P.store_bf16) {
+            if (P.store_bf16 && !P.reg_store) {
                 fence_proxy_async_smem();
                 named_bar_sync(1, kEpiThreads);
                 if (P.direct_store) {
@@ -526,6 +553,15 @@ static int num_sms() {
     return sms;
 }
 
+static bool reg_store_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("HD_REG_STORE");
+        on = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
+}
+
 static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStream_t stream) {
     P.a_sub = round_up(128 * P.BK * 2, 1024);
     P.b_sub = round_up(P.BN * P.BK * 2, 1024);
@@ -545,7 +581,11 @@ static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStrea
     P.a_bytes = P.a_sub * P.tps;
     P.stage_bytes = (P.a_sub + P.b_sub) * P.tps;
     const int staging = 2 * round_up(128 * P.BN * 2, 1024);         // double-buffered output staging
-    const int fixed = 1024 + staging + 512 + 16 * 8 + 64;          // alignment slack, staging, bias, barriers
+    P.n_tiles = (P.Cout_total + P.BN - 1) / P.BN;
+    P.bias_floats = round_up(P.n_tiles * P.BN, 128);               // bias of all (padded) output channels
+    // without BatchNorm statistics (which are reduced from the staged tile) the epilogue stores from registers
+    P.reg_store = (P.stats == nullptr && P.store_bf16 && P.out_ptr2[0] != nullptr && reg_store_enabled()) ? 1 : 0;
+    const int fixed = 1024 + staging + 4 * P.bias_floats + 16 * 8 + 64;   // alignment slack, staging, bias, barriers
     int stages = (232448 - fixed) / P.stage_bytes;              // 227 KB = the sm_100 per-block maximum
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
@@ -674,6 +714,7 @@ extern "C" int hd_conv_fwd(const hd_conv_args* a, hd_stream stream_) {
     if (act_map(&P.tmOut[0], a->y0, false, sub_c, P.TW, P.TH, sub_c * 2)) return HD_ERR_CUDA;
     P.tmOut[1] = P.tmOut[0];
     P.out_ptr = static_cast<__nv_bfloat16*>(a->y0.ptr);
+    P.out_ptr2[0] = P.out_ptr; P.out_ptr2[1] = nullptr;
     return launch_conv_gemm(P, N, 1, stream);
 }
 
@@ -775,5 +816,7 @@ extern "C" int hd_conv_dgrad(const hd_conv_args* a, hd_stream stream_) {
     if (two) { if (act_map(&P.tmOut[1], a->y1, false, sub_c, P.TW, P.TH, sub_c * 2)) return HD_ERR_CUDA; }
     else P.tmOut[1] = P.tmOut[0];
     P.out_ptr = two ? nullptr : static_cast<__nv_bfloat16*>(a->y0.ptr);
+    P.out_ptr2[0] = static_cast<__nv_bfloat16*>(a->y0.ptr);
+    P.out_ptr2[1] = two ? static_cast<__nv_bfloat16*>(a->y1.ptr) : nullptr;
     return launch_conv_gemm(P, N, nph, stream);
 }
