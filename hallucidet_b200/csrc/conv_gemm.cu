@@ -66,6 +66,8 @@ struct ConvGemmParams {
     int direct_store;
     __nv_bfloat16* out_ptr;
     __nv_bfloat16* out_ptr2[2];  // both outputs (register-store epilogue)
+    int aux_mode;               // fused add / mask tiles are prefetched into a shared-memory ring by the cp.async warps
+    int ring_bytes;             // bytes of the output-staging region (register-store: reused as the add / mask ring)
     int reg_store;              // epilogue writes its rows straight from registers (no staging / TMA store / CTA barriers)
     int bias_floats;            // floats reserved for the bias of ALL output channels in shared memory
     int cp_mode;
@@ -102,12 +104,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int stages = P.stages;
     const uint32_t stg_bytes = (128u * P.BN * 2u + 1023u) & ~1023u;
     const uint32_t staging0 = smem_base + static_cast<uint32_t>(stages * P.stage_bytes);  // 2 x (128 x BN bf16), 1024-aligned
-    const uint32_t bias_s = staging0 + 2u * stg_bytes;                                     // BN floats
+    const uint32_t bias_s = staging0 + static_cast<uint32_t>(P.ring_bytes);               // bias of all output channels
     const uint32_t bar_base = bias_s + 4u * static_cast<uint32_t>(P.bias_floats);
     // barriers: full[s], empty[s], tmem_full[2], tmem_empty[2], then the TMEM base-address slot
     const uint32_t full0 = bar_base, empty0 = bar_base + 8u * stages;
     const uint32_t tfull0 = bar_base + 16u * stages, tempty0 = tfull0 + 16u;
-    const uint32_t tmem_slot = tempty0 + 16u;
+    const uint32_t afull0 = tempty0 + 16u, aempty0 = afull0 + 16u;        // add / mask ring (aux_mode)
+    const uint32_t tmem_slot = aempty0 + 16u;
+    const int aux_ops = (P.add != nullptr ? 1 : 0) + (P.mask != nullptr ? 1 : 0);
+    const uint32_t aux_buf_bytes = static_cast<uint32_t>(aux_ops) * stg_bytes;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -115,6 +120,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             mbar_init(empty0 + 8u * s, 1);
         }
         for (int a = 0; a < 2; ++a) {
+            mbar_init(afull0 + 8u * a, kCpThreads);
+            mbar_init(aempty0 + 8u * a, kEpiWarps);
             mbar_init(tfull0 + 8u * a, 1);
             mbar_init(tempty0 + 8u * a, kEpiWarps);         // one arrival per epilogue warp
         }
@@ -215,6 +222,46 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
         }
     } else if (warp >= 2 + kEpiWarps) {
+        if (P.aux_mode) {
+            // ================= add / mask tile prefetchers (fused register-store epilogue) =================
+            // The residual / ReLU-mask operands of an output tile (128 rows x BN channels each) stream into a two-deep
+            // shared-memory ring one to two tiles ahead of the epilogue, so their HBM latency is off the epilogue's
+            // critical path.  Two threads per pixel row take alternating 16-byte chunks (full sectors); chunks are
+            // XOR-swizzled by the row so that the epilogue's per-row 16-byte reads are bank-conflict free.
+            const int pt = threadIdx.x - (64 + kEpiThreads);      // 0..127
+            const int cpr = P.BN / 8;                              // 16-byte chunks per row
+            const uint32_t row_bytes = static_cast<uint32_t>(P.BN) * 2u;
+            int b = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int z, n0, img, h0, w0;
+                decode_tile(P, tile, z, n0, img, h0, w0);
+                mbar_wait(aempty0 + 8u * b, ph ^ 1u);
+                const uint32_t dst_add = staging0 + b * aux_buf_bytes;
+                const uint32_t dst_mask = dst_add + (P.add != nullptr ? stg_bytes : 0u);
+#pragma unroll
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int r = (pt >> 1) + 64 * pass;
+                    const int rh = static_cast<int>(fdiv(r, P.fd_TW)), rw = r - rh * P.TW;
+                    const int hg = h0 + rh, wg = w0 + rw;
+                    const bool ok_row = (r < P.TW * P.TH) && hg < P.Hg && wg < P.Wg;
+                    const long pix = static_cast<long>((img * P.Hout + hg * P.ostride + P.out_p[z]) * P.Wout + wg * P.ostride + P.out_q[z]);
+                    const long goff = pix * P.Cout_total + n0;
+                    const uint32_t srow = static_cast<uint32_t>(r) * row_bytes;
+                    for (int c = pt & 1; c < cpr; c += 2) {
+                        const bool ok = ok_row && n0 + c * 8 < P.Cout_total;
+                        const uint32_t so = srow + (static_cast<uint32_t>(c ^ (r & (cpr - 1))) << 4);
+                        if (P.add != nullptr)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_add + so), "l"(ok ? P.add + goff + c * 8 : P.add), "r"(ok ? 16 : 0) : "memory");
+                        if (P.mask != nullptr)
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_mask + so), "l"(ok ? P.mask + goff + c * 8 : P.mask), "r"(ok ? 16 : 0) : "memory");
+                    }
+                }
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(afull0 + 8u * b) : "memory");
+                if (++b == 2) { b = 0; ph ^= 1u; }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+        } else
         // ================= cp.async A-tile producers (narrow-channel mode) =================
         if (P.cp_mode) {
             const int pt = threadIdx.x - (64 + kEpiThreads);      // 0..127
@@ -310,6 +357,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
         }
         named_bar_sync(2, kEpiThreads);
+        int ab = 0;                                            // add / mask ring position (aux_mode)
+        uint32_t aph = 0;
+        const int aux_cpr = P.BN / 8;
+        const uint32_t aux_row = static_cast<uint32_t>(row) * static_cast<uint32_t>(P.BN) * 2u;
+        const uint32_t aux_xr = static_cast<uint32_t>(row & (aux_cpr - 1));
         int acc = 0;
         uint32_t acc_phase = 0;
         int iter = 0;
@@ -332,10 +384,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
             // fused-operand loads are software-pipelined one 16-column chunk ahead of their use
             uint4 na0 = make_uint4(0, 0, 0, 0), na1 = na0, nm0 = na0, nm1 = na0;
-            if (fused && c_begin < c_end && valid && n0 + c_begin * 16 < P.Cout_total) {
+            if (fused && !P.aux_mode && c_begin < c_end && valid && n0 + c_begin * 16 < P.Cout_total) {
                 if (add_row) { const uint4* ap = reinterpret_cast<const uint4*>(add_row + c_begin * 16); na0 = ap[0]; na1 = ap[1]; }
                 if (mask_row) { const uint4* mp = reinterpret_cast<const uint4*>(mask_row + c_begin * 16); nm0 = __ldg(mp); nm1 = __ldg(mp + 1); }
             }
+            const uint32_t aux_add = staging0 + ab * aux_buf_bytes, aux_mask = aux_add + (P.add != nullptr ? stg_bytes : 0u);
+            if (P.aux_mode) mbar_wait(afull0 + 8u * ab, aph);
             mbar_wait(tfull0 + 8u * acc, acc_phase);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + acc * P.tmem_cols + (static_cast<uint32_t>(quad * 32) << 16);
@@ -346,10 +400,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             for (int c16 = c_begin; c16 < c_end; ++c16) {
                 const int ch0 = n0 + c16 * 16;
                 const bool ch_ok = ch0 < P.Cout_total;
-                const uint4 a0 = na0, a1 = na1, m0 = nm0, m1 = nm1;
+                uint4 a0 = na0, a1 = na1, m0 = nm0, m1 = nm1;
                 const bool has_add = kFused && add_row != nullptr && valid && ch_ok;
                 const bool has_mask = kFused && mask_row != nullptr && valid && ch_ok;
-                if (kFused && c16 + 1 < c_end && valid && ch0 + 16 < P.Cout_total) {
+                if (kFused && P.aux_mode) {
+                    const uint32_t o0 = aux_row + ((static_cast<uint32_t>(2 * c16) ^ aux_xr) << 4);
+                    const uint32_t o1 = aux_row + ((static_cast<uint32_t>(2 * c16 + 1) ^ aux_xr) << 4);
+                    if (has_add) {
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a0.x), "=r"(a0.y), "=r"(a0.z), "=r"(a0.w) : "r"(aux_add + o0));
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a1.x), "=r"(a1.y), "=r"(a1.z), "=r"(a1.w) : "r"(aux_add + o1));
+                    }
+                    if (has_mask) {
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(m0.x), "=r"(m0.y), "=r"(m0.z), "=r"(m0.w) : "r"(aux_mask + o0));
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(m1.x), "=r"(m1.y), "=r"(m1.z), "=r"(m1.w) : "r"(aux_mask + o1));
+                    }
+                }
+                if (kFused && !P.aux_mode && c16 + 1 < c_end && valid && ch0 + 16 < P.Cout_total) {
                     if (add_row) { const uint4* ap = reinterpret_cast<const uint4*>(add_row + (c16 + 1) * 16); na0 = ap[0]; na1 = ap[1]; }
                     if (mask_row) { const uint4* mp = reinterpret_cast<const uint4*>(mask_row + (c16 + 1) * 16); nm0 = __ldg(mp); nm1 = __ldg(mp + 1); }
                 }
@@ -435,10 +501,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             };
             if (!fused && P.out_f32 == nullptr) chunk_loop(std::false_type{}, std::false_type{});
             else chunk_loop(std::true_type{}, std::true_type{});
-            // accumulator drained: hand it back to the MMA issuer
+            // accumulator drained: hand it back to the MMA issuer (and the add / mask ring slot to its prefetchers)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+            if (P.aux_mode) {
+                if (lane == 0) mbar_arrive(aempty0 + 8u * ab);
+                if (++ab == 2) { ab = 0; aph ^= 1u; }
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
 
             if (P.store_bf16 && !P.reg_store) {
@@ -562,6 +632,15 @@ static bool reg_store_enabled() {
     return on != 0;
 }
 
+static bool aux_mode_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("HD_AUX_RING");
+        on = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
+}
+
 static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStream_t stream) {
     P.a_sub = round_up(128 * P.BK * 2, 1024);
     P.b_sub = round_up(P.BN * P.BK * 2, 1024);
@@ -585,7 +664,11 @@ static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStrea
     P.bias_floats = round_up(P.n_tiles * P.BN, 128);               // bias of all (padded) output channels
     // without BatchNorm statistics (which are reduced from the staged tile) the epilogue stores from registers
     P.reg_store = (P.stats == nullptr && P.store_bf16 && P.out_ptr2[0] != nullptr && reg_store_enabled()) ? 1 : 0;
-    const int fixed = 1024 + staging + 4 * P.bias_floats + 16 * 8 + 64;   // alignment slack, staging, bias, barriers
+    const int n_ops = (P.add != nullptr ? 1 : 0) + (P.mask != nullptr ? 1 : 0);
+    P.aux_mode = (P.reg_store && n_ops > 0 && !P.cp_mode && P.BN >= 16 && aux_mode_enabled()) ? 1 : 0;
+    // register-store epilogues need no output staging: the region becomes the two-deep add / mask ring (or nothing)
+    P.ring_bytes = P.reg_store ? (P.aux_mode ? 2 * n_ops * (staging / 2) : 0) : staging;
+    const int fixed = 1024 + P.ring_bytes + 4 * P.bias_floats + 20 * 8 + 64;   // alignment slack, ring, bias, barriers
     int stages = (232448 - fixed) / P.stage_bytes;              // 227 KB = the sm_100 per-block maximum
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
