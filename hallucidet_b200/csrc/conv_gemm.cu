@@ -66,6 +66,7 @@ struct ConvGemmParams {
     int direct_store;
     __nv_bfloat16* out_ptr;
     __nv_bfloat16* out_ptr2[2];  // both outputs (register-store epilogue)
+    int stg_bufs;               // output staging buffers (2; 1 for the 256-wide tiles)
     int aux_mode;               // fused add / mask tiles are prefetched into a shared-memory ring by the cp.async warps
     int ring_bytes;             // bytes of the output-staging region (register-store: reused as the add / mask ring)
     int reg_store;              // epilogue writes its rows straight from registers (no staging / TMA store / CTA barriers)
@@ -373,13 +374,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const bool valid = (row < P.TW * P.TH) && hg < P.Hg && wg < P.Wg;
             const int ho = hg * P.ostride + P.out_p[z], wo = wg * P.ostride + P.out_q[z];
             const long pix = static_cast<long>((img * P.Hout + ho) * P.Wout + wo);
-            const uint32_t staging = staging0 + (iter & 1) * stg_bytes;
+            const uint32_t staging = staging0 + (P.stg_bufs == 2 ? (iter & 1) : 0) * stg_bytes;
             const __nv_bfloat16* add_row = P.add != nullptr ? P.add + pix * P.Cout_total + n0 : nullptr;
             const __nv_bfloat16* mask_row = P.mask != nullptr ? P.mask + pix * P.Cout_total + n0 : nullptr;
 
             if (!P.reg_store) {
                 // this staging buffer was last used two tiles ago: its TMA store must have finished reading it
-                if (iter >= 2 && et == 0) tma_store_wait_read1();
+                if (et == 0) {
+                    if (P.stg_bufs == 2) { if (iter >= 2) tma_store_wait_read1(); }
+                    else if (iter >= 1) tma_store_wait_read();
+                }
                 named_bar_sync(1, kEpiThreads);
             }
             // fused-operand loads are software-pipelined one 16-column chunk ahead of their use
@@ -659,15 +663,25 @@ static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStrea
     }
     P.a_bytes = P.a_sub * P.tps;
     P.stage_bytes = (P.a_sub + P.b_sub) * P.tps;
-    const int staging = 2 * round_up(128 * P.BN * 2, 1024);         // double-buffered output staging
+    P.stg_bufs = P.BN > 128 ? 1 : 2;
+    const int staging = P.stg_bufs * round_up(128 * P.BN * 2, 1024);   // output staging (double-buffered up to BN = 128)
     P.n_tiles = (P.Cout_total + P.BN - 1) / P.BN;
     P.bias_floats = round_up(P.n_tiles * P.BN, 128);               // bias of all (padded) output channels
     // without BatchNorm statistics (which are reduced from the staged tile) the epilogue stores from registers
     P.reg_store = (P.stats == nullptr && P.store_bf16 && P.out_ptr2[0] != nullptr && reg_store_enabled()) ? 1 : 0;
     const int n_ops = (P.add != nullptr ? 1 : 0) + (P.mask != nullptr ? 1 : 0);
-    P.aux_mode = (P.reg_store && n_ops > 0 && !P.cp_mode && P.BN >= 16 && aux_mode_enabled()) ? 1 : 0;
+    const int tile_bytes = round_up(128 * P.BN * 2, 1024);
+    // the ring must leave the main loop enough stages: 3, or 2 when a tile has at most two k-steps (1x1 layers, K <= 128)
+    int max_steps = 0;
+    for (int z = 0; z < nphases; ++z) {
+        const int nk = (P.tap_begin[z + 1] - P.tap_begin[z]) * P.kpt / P.tps;
+        if (nk > max_steps) max_steps = nk;
+    }
+    const int stages_with_ring = (232448 - (1024 + 2 * n_ops * tile_bytes + 4 * P.bias_floats + 20 * 8 + 64)) / P.stage_bytes;
+    P.aux_mode = (P.reg_store && n_ops > 0 && !P.cp_mode && P.BN >= 16 && aux_mode_enabled() &&
+                  stages_with_ring >= (max_steps <= 2 ? 2 : 3)) ? 1 : 0;
     // register-store epilogues need no output staging: the region becomes the two-deep add / mask ring (or nothing)
-    P.ring_bytes = P.reg_store ? (P.aux_mode ? 2 * n_ops * (staging / 2) : 0) : staging;
+    P.ring_bytes = P.reg_store ? (P.aux_mode ? 2 * n_ops * tile_bytes : 0) : staging;
     const int fixed = 1024 + P.ring_bytes + 4 * P.bias_floats + 20 * 8 + 64;   // alignment slack, ring, bias, barriers
     int stages = (232448 - fixed) / P.stage_bytes;              // 227 KB = the sm_100 per-block maximum
     if (stages > 8) stages = 8;
@@ -709,6 +723,23 @@ static int pick_bk(int c0, int c1) {
 }
 
 static int pick_bn(int c) { return c >= 128 ? 128 : (c >= 64 ? 64 : (c >= 32 ? 32 : 16)); }
+
+// 256-wide N tiles for the main-loop-bound 3x3 layers with >= 256 output channels: the A tile is fetched once per 256
+// (not 128) output channels, i.e. 48 KB instead of 64 KB of L2 -> smem traffic per k-block and 256 columns, and the
+// tile count halves (160 tiles on 148 SMs = two waves become 80 = one).  Estimated cost per tile 1.5x; taken when the
+// wave count makes up for it.
+static int maybe_bn256(int bn, int k, int n_out, int m_tiles) {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("HD_BN256");
+        on = (e != nullptr && e[0] >= '0' && e[0] <= '9') ? e[0] - '0' : 1;      // 0 off, 1 = 3x3 layers, 2 = also 1x1 (experiments)
+    }
+    if (!on || bn != 128 || (k != 3 && on < 2) || n_out % 256 != 0) return bn;
+    const int sms = num_sms();
+    const long w128 = (static_cast<long>(m_tiles) * (n_out / 128) + sms - 1) / sms;
+    const long w256 = (static_cast<long>(m_tiles) * (n_out / 256) + sms - 1) / sms;
+    return (3 * w256 < 2 * w128) ? 256 : bn;
+}
 
 static int check_act(const hd_act& t) {
     return t.ptr != nullptr && t.n > 0 && t.h > 0 && t.w > 0 && t.c > 0 && t.c % 16 == 0 &&
@@ -762,6 +793,7 @@ extern "C" int hd_conv_fwd(const hd_conv_args* a, hd_stream stream_) {
     pick_tile(P.Hg, P.Wg, &P.TW, &P.TH);
     P.tiles_w = (P.Wg + P.TW - 1) / P.TW;
     P.tiles_h = (P.Hg + P.TH - 1) / P.TH;
+    P.BN = maybe_bn256(P.BN, k, cout, P.tiles_w * P.tiles_h * N);
     int t = 0;
     for (int r = 0; r < k; ++r)
         for (int c = 0; c < k; ++c, ++t) {
@@ -846,6 +878,7 @@ extern "C" int hd_conv_dgrad(const hd_conv_args* a, hd_stream stream_) {
     pick_tile(P.Hg, P.Wg, &P.TW, &P.TH);
     P.tiles_w = (P.Wg + P.TW - 1) / P.TW;
     P.tiles_h = (P.Hg + P.TH - 1) / P.TH;
+    if (!two && s == 1) P.BN = maybe_bn256(P.BN, k, cin, P.tiles_w * P.tiles_h * N);
     int nph = 0, t = 0;
     if (s == 1) {
         for (int r = 0; r < k; ++r)

@@ -54,6 +54,8 @@ CONV_CASES = [
     (1, 64, 64, 32, 16, 3, 1, 0),
     (2, 20, 44, 16, 32, 3, 1, 0),       # narrow-layer kernel, partial 8x32 tiles
     (3, 9, 70, 32, 32, 3, 1, 0),
+    (2, 64, 80, 64, 256, 3, 1, 0),      # 160 tiles of 128 channels > 148 SMs -> 256-wide N tiles
+    (2, 64, 84, 64, 512, 3, 1, 0),
     (2, 16, 24, 64, 128, 3, 2, 0),
     (2, 16, 24, 64, 128, 1, 2, 0),
     (1, 16, 16, 64, 32, 3, 1, 64),
@@ -80,9 +82,9 @@ def test_conv_fwd(n, h, w, cin, cout, k, s, cin2):
     assert_close_bf16(nchw(y), ref, "conv_fwd")
 
 
-def test_conv_fwd_epilogue_bias_add_relu_stats():
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 24, 40, 64, 128), (2, 64, 80, 64, 256)])
+def test_conv_fwd_epilogue_bias_add_relu_stats(n, h, w, cin, cout):
     o = ops()
-    n, h, w, cin, cout = 2, 24, 40, 64, 128
     x = rnd(n, h, w, cin, seed=1)
     res = rnd(n, h, w, cout, seed=5)
     bias = torch.randn(cout, device="cuda")
@@ -164,6 +166,7 @@ DGRAD_CASES = [
     (1, 64, 64, 32, 16, 3, 1, 0),
     (2, 20, 44, 32, 32, 3, 1, 0),       # narrow-layer kernel, partial 8x32 tiles
     (3, 9, 70, 16, 32, 3, 1, 0),
+    (2, 64, 80, 256, 64, 3, 1, 0),      # 256-wide N tiles (dX has 256 channels)
     (2, 16, 24, 64, 128, 3, 2, 0),
     (1, 16, 16, 128, 64, 3, 1, 64),     # dX split into (64 | 64)
     (1, 16, 20, 192, 64, 3, 1, 64),     # (128 | 64)
