@@ -81,6 +81,8 @@ PROTOTYPES = {
     "hd_pack_conv_weights": [c_void_p, c_int, c_int, c_void_p],
     "hd_unpack_wgrads": [c_void_p, c_int, c_int, c_void_p],
     "hd_roi_align_bwd_nhwc": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
+    "hd_roi_align_fwd_nhwc": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
+    "hd_nchw_to_nhwc_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "hd_nhwc_to_nchw_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "hd_nms": [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p],
 }

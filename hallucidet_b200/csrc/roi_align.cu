@@ -91,6 +91,97 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_nhwc_kernel(const f
     }
 }
 
+// Forward on a channels-last copy of the feature map: every (sample, corner) read is 64 lanes x 16 bytes = the 256
+// channels of one pixel (torchvision gathers 16 scattered 4-byte values per output element from NCHW).  Same expression
+// per output element as torchvision's roi_align_forward_kernel_impl: val += w1*v1 + w2*v2 + w3*v3 + w4*v4 over the samples
+// in (iy, ix) order, then val /= count.  The [C][PH*PW] result of a RoI is staged in shared memory and written coalesced.
+__global__ void __launch_bounds__(kRoiThreads) roi_align_fwd_nhwc_kernel(const float* __restrict__ feat, const float* __restrict__ rois,
+                                                                         float* __restrict__ out, int C, int H, int W, int PH, int PW,
+                                                                         float spatial_scale, int sampling_ratio) {
+    extern __shared__ __align__(16) float gsm[];        // [C][nbins] output tile of this RoI
+    __shared__ float s_w[kMaxSamples * 4];
+    __shared__ int s_off[kMaxSamples * 4];
+    const int k = blockIdx.x;
+    const float* roi = rois + static_cast<long>(k) * 5;
+    const int n = static_cast<int>(roi[0]);
+    const float roi_start_w = roi[1] * spatial_scale, roi_start_h = roi[2] * spatial_scale;
+    const float roi_end_w = roi[3] * spatial_scale, roi_end_h = roi[4] * spatial_scale;
+    const float roi_width = fmaxf(roi_end_w - roi_start_w, 1.f), roi_height = fmaxf(roi_end_h - roi_start_h, 1.f);
+    const float bin_size_h = roi_height / static_cast<float>(PH), bin_size_w = roi_width / static_cast<float>(PW);
+    const int grid_h = sampling_ratio, grid_w = sampling_ratio;
+    const float count = fmaxf(static_cast<float>(grid_h * grid_w), 1.f);
+    const int nbins = PH * PW, per_bin = grid_h * grid_w, nsamp = nbins * per_bin;
+    for (int s = threadIdx.x; s < nsamp; s += kRoiThreads) {
+        const int bin = s / per_bin, r = s - bin * per_bin;
+        const int ph = bin / PW, pw = bin - ph * PW, iy = r / grid_w, ix = r - iy * grid_w;
+        float y = roi_start_h + ph * bin_size_h + (iy + .5f) * bin_size_h / static_cast<float>(grid_h);
+        float x = roi_start_w + pw * bin_size_w + (ix + .5f) * bin_size_w / static_cast<float>(grid_w);
+        float w[4] = {0.f, 0.f, 0.f, 0.f};
+        int off[4] = {-1, -1, -1, -1};
+        if (!(y < -1.0f || y > H || x < -1.0f || x > W)) {     // torchvision bilinear_interpolate: out of range -> 0
+            if (y <= 0) y = 0;
+            if (x <= 0) x = 0;
+            int y_low = static_cast<int>(y), x_low = static_cast<int>(x), y_high, x_high;
+            if (y_low >= H - 1) { y_high = y_low = H - 1; y = static_cast<float>(y_low); } else y_high = y_low + 1;
+            if (x_low >= W - 1) { x_high = x_low = W - 1; x = static_cast<float>(x_low); } else x_high = x_low + 1;
+            const float ly = y - y_low, lx = x - x_low, hy = 1.f - ly, hx = 1.f - lx;
+            w[0] = hy * hx; w[1] = hy * lx; w[2] = ly * hx; w[3] = ly * lx;
+            off[0] = y_low * W + x_low; off[1] = y_low * W + x_high; off[2] = y_high * W + x_low; off[3] = y_high * W + x_high;
+        }
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) { s_w[s * 4 + c4] = w[c4]; s_off[s * 4 + c4] = off[c4]; }
+    }
+    __syncthreads();
+    const int lanes = C / 4, groups = kRoiThreads / lanes;
+    const int grp = threadIdx.x / lanes, c0 = (threadIdx.x - grp * lanes) * 4;
+    const float* fin = feat + static_cast<long>(n) * H * W * C + c0;
+    if (grp < groups) {
+        for (int bin = grp; bin < nbins; bin += groups) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < per_bin; ++r) {
+                const int s4 = (bin * per_bin + r) * 4;
+                if (s_off[s4] < 0) continue;                   // sample outside the map contributes 0
+                const float w1 = s_w[s4], w2 = s_w[s4 + 1], w3 = s_w[s4 + 2], w4 = s_w[s4 + 3];
+                const float4 v1 = *reinterpret_cast<const float4*>(fin + static_cast<long>(s_off[s4]) * C);
+                const float4 v2 = *reinterpret_cast<const float4*>(fin + static_cast<long>(s_off[s4 + 1]) * C);
+                const float4 v3 = *reinterpret_cast<const float4*>(fin + static_cast<long>(s_off[s4 + 2]) * C);
+                const float4 v4 = *reinterpret_cast<const float4*>(fin + static_cast<long>(s_off[s4 + 3]) * C);
+                acc.x += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
+                acc.y += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
+                acc.z += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
+                acc.w += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
+            }
+            gsm[(c0 + 0) * nbins + bin] = acc.x / count;
+            gsm[(c0 + 1) * nbins + bin] = acc.y / count;
+            gsm[(c0 + 2) * nbins + bin] = acc.z / count;
+            gsm[(c0 + 3) * nbins + bin] = acc.w / count;
+        }
+    }
+    __syncthreads();
+    float* o = out + static_cast<long>(k) * C * nbins;
+    for (int i = threadIdx.x; i < C * nbins; i += kRoiThreads) o[i] = gsm[i];
+}
+
+// [N][C][H][W] fp32 -> [N][H][W][C] fp32 through a 32 x 32 shared-memory tile
+__global__ void __launch_bounds__(256) nchw_to_nhwc_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW) {
+    __shared__ float t[32][33];
+    const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float* xs = x + static_cast<long>(n) * C * HW;
+    float* ys = y + static_cast<long>(n) * HW * C;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int c = c0 + ty + j, p = p0 + tx;
+        t[ty + j][tx] = (p < HW && c < C) ? xs[static_cast<long>(c) * HW + p] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int p = p0 + ty + j, c = c0 + tx;
+        if (p < HW && c < C) ys[static_cast<long>(p) * C + c] = t[tx][ty + j];
+    }
+}
+
 // [N][H][W][C] fp32 -> [N][C][H][W] fp32 through a 32 x 32 shared-memory tile
 __global__ void __launch_bounds__(256) nhwc_to_nchw_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW) {
     __shared__ float t[32][33];
@@ -149,6 +240,39 @@ extern "C" int hd_nhwc_to_nchw_f32(const float* x_nhwc, float* y_nchw, int n, in
     const int hw = height * width;
     dim3 grid((hw + 31) / 32, (channels + 31) / 32, n);
     nhwc_to_nchw_f32_kernel<<<grid, 256, 0, stream>>>(x_nhwc, y_nchw, channels, hw);
+    HD_CUDA_OK(cudaPeekAtLastError());
+    return HD_OK;
+}
+
+// out [K][C][PH][PW] = torchvision.ops.roi_align(input, rois, spatial_scale, PH, PW, sampling_ratio, aligned = False), with the
+// input given channels-last (feat_nhwc [N][H][W][C] fp32, see hd_nchw_to_nhwc_f32).  Same constraints as the backward.
+extern "C" int hd_roi_align_fwd_nhwc(const float* feat_nhwc, const float* rois, float* out, int num_rois, int channels, int height,
+                                     int width, int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio, hd_stream stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    HD_CHECK_ARG(num_rois >= 0 && channels > 0 && channels % 4 == 0 && channels <= kMaxC && height > 0 && width > 0);
+    HD_CHECK_ARG(kRoiThreads % (channels / 4) == 0);
+    if (num_rois == 0) return HD_OK;
+    HD_CHECK_ARG(feat_nhwc != nullptr && rois != nullptr && out != nullptr && (reinterpret_cast<uintptr_t>(feat_nhwc) & 15) == 0);
+    HD_CHECK_ARG(pooled_h > 0 && pooled_w > 0 && pooled_h * pooled_w <= kMaxBins && sampling_ratio >= 1 && sampling_ratio <= 2);
+    const size_t smem = static_cast<size_t>(channels) * pooled_h * pooled_w * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        HD_CUDA_OK(cudaFuncSetAttribute(roi_align_fwd_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(kMaxC * kMaxBins * sizeof(float))));
+        attr_set = true;
+    }
+    roi_align_fwd_nhwc_kernel<<<num_rois, kRoiThreads, smem, stream>>>(feat_nhwc, rois, out, channels, height, width, pooled_h, pooled_w,
+                                                                       spatial_scale, sampling_ratio);
+    HD_CUDA_OK(cudaPeekAtLastError());
+    return HD_OK;
+}
+
+extern "C" int hd_nchw_to_nhwc_f32(const float* x_nchw, float* y_nhwc, int n, int channels, int height, int width, hd_stream stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    HD_CHECK_ARG(x_nchw != nullptr && y_nhwc != nullptr && n > 0 && channels > 0 && height > 0 && width > 0 && n < 65536);
+    const int hw = height * width;
+    dim3 grid((hw + 31) / 32, (channels + 31) / 32, n);
+    nchw_to_nhwc_f32_kernel<<<grid, 256, 0, stream>>>(x_nchw, y_nhwc, channels, hw);
     HD_CUDA_OK(cudaPeekAtLastError());
     return HD_OK;
 }

@@ -473,12 +473,15 @@ def fastrcnn_loss_static(class_logits, box_regression, labels, regression_target
 
 
 class _RoIAlign(torch.autograd.Function):
-    """torchvision's roi_align forward op unchanged; backward on hd_roi_align_bwd_nhwc (ops.roi_align_bwd)."""
+    """RoIAlign of one FPN level: forward on hd_roi_align_fwd_nhwc (bit-identical to torchvision's op, which is the
+    fallback), backward on hd_roi_align_bwd_nhwc (ops.roi_align_bwd)."""
 
     @staticmethod
-    def forward(ctx, feat, rois, spatial_scale, output_size, sampling_ratio):
+    def forward(ctx, feat, rois, spatial_scale, output_size, sampling_ratio, feat_nhwc):
         ctx.save_for_backward(rois)
         ctx.cfg = (tuple(feat.shape), float(spatial_scale), int(sampling_ratio))
+        if feat_nhwc is not None:            # channels-last copy of feat: coalesced gathers, bit-identical pooled features
+            return ops.roi_align_fwd(feat_nhwc, rois.contiguous(), output_size, spatial_scale, sampling_ratio)
         return torch.ops.torchvision.roi_align(feat, rois, float(spatial_scale), int(output_size[0]), int(output_size[1]),
                                                int(sampling_ratio), False)
 
@@ -486,7 +489,7 @@ class _RoIAlign(torch.autograd.Function):
     def backward(ctx, grad):
         (rois,) = ctx.saved_tensors
         shape, spatial_scale, sampling_ratio = ctx.cfg
-        return ops.roi_align_bwd(grad.contiguous(), rois.contiguous(), shape, spatial_scale, sampling_ratio), None, None, None, None
+        return ops.roi_align_bwd(grad.contiguous(), rois.contiguous(), shape, spatial_scale, sampling_ratio), None, None, None, None, None
 
 
 def _roi_align(feat, rois, output_size, spatial_scale, sampling_ratio):
@@ -494,7 +497,8 @@ def _roi_align(feat, rois, output_size, spatial_scale, sampling_ratio):
     c = feat.shape[1]
     if (ROI_ALIGN_BWD and feat.is_cuda and feat.dtype == torch.float32 and rois.dtype == torch.float32 and feat.requires_grad
             and 1 <= sampling_ratio <= 2 and output_size[0] * output_size[1] <= 49 and c % 4 == 0 and c <= 256 and 256 % (c // 4) == 0):
-        return _RoIAlign.apply(feat, rois, spatial_scale, tuple(output_size), sampling_ratio)
+        nhwc = ops.nchw_to_nhwc_f32(feat.detach().contiguous()) if ROI_ALIGN_FWD and rois.shape[0] > 0 else None
+        return _RoIAlign.apply(feat, rois, spatial_scale, tuple(output_size), sampling_ratio, nhwc)
     return roi_align(feat, rois, output_size=output_size, spatial_scale=spatial_scale, sampling_ratio=sampling_ratio)
 
 
@@ -598,6 +602,7 @@ CONCURRENT_NMS = _os.environ.get("HD_CONCURRENT_NMS", "1") != "0"               
 CONCURRENT_POSTPROCESS = _os.environ.get("HD_CONCURRENT_POSTPROCESS", "0") != "0"   # final detections
 BATCHED_TAIL = _os.environ.get("HD_BATCHED_TAIL", "1") != "0"   # whole-batch proposal filter / detections post-processing
 ROI_ALIGN_BWD = _os.environ.get("HD_ROI_ALIGN_BWD", "1") != "0"   # RoIAlign backward on hd_roi_align_bwd_nhwc
+ROI_ALIGN_FWD = _os.environ.get("HD_ROI_ALIGN_FWD", "1") != "0"   # ... and forward on hd_roi_align_fwd_nhwc (bit-identical)
 DEFER_DETECTIONS = False    # set by HalluciDetTrainer.training_step: roi_heads_eval returns a DeferredDetections
 
 

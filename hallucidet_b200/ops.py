@@ -468,3 +468,25 @@ def roi_align_bwd(grad_out, rois, input_shape, spatial_scale, sampling_ratio):
         check(_lib.load().hd_nhwc_to_nchw_f32(_ptr(scratch), _ptr(out), n, c, h, w, _stream()), "hd_nhwc_to_nchw_f32")
     LAUNCHES += 1
     return out
+
+
+def nchw_to_nhwc_f32(x):
+    """fp32 [N, C, H, W] -> fp32 [N, H, W, C] (channels-last copy for the RoIAlign forward)."""
+    n, c, h, w = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    y = torch.empty(n, h, w, c, dtype=torch.float32, device=x.device)
+    with _Timed("nchw_to_nhwc_f32"):
+        check(_lib.load().hd_nchw_to_nhwc_f32(_ptr(x), _ptr(y), n, c, h, w, _stream()), "hd_nchw_to_nhwc_f32")
+    return y
+
+
+def roi_align_fwd(feat_nhwc, rois, output_size, spatial_scale, sampling_ratio):
+    """torchvision.ops.roi_align(aligned=False) forward on a channels-last fp32 feature map; returns [K, C, PH, PW]."""
+    n, h, w, c = feat_nhwc.shape
+    k = rois.shape[0]
+    assert feat_nhwc.dtype == torch.float32 and feat_nhwc.is_contiguous() and rois.dtype == torch.float32 and rois.is_contiguous()
+    out = torch.empty(k, c, int(output_size[0]), int(output_size[1]), dtype=torch.float32, device=rois.device)
+    with _Timed("roi_align_fwd"):
+        check(_lib.load().hd_roi_align_fwd_nhwc(_ptr(feat_nhwc), _ptr(rois), _ptr(out), k, c, h, w, int(output_size[0]), int(output_size[1]),
+                                                float(spatial_scale), int(sampling_ratio), _stream()), "hd_roi_align_fwd_nhwc")
+    return out

@@ -205,6 +205,12 @@ int hd_nms(const float* boxes_sorted, const int* offsets, const int* counts_dev,
 int hd_roi_align_bwd_nhwc(const float* grad_out, const float* rois, float* grad_in_nhwc, int num_rois, int channels, int height,
                           int width, int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio, hd_stream stream);
 int hd_nhwc_to_nchw_f32(const float* x_nhwc, float* y_nchw, int n, int channels, int height, int width, hd_stream stream);
+/* Forward of the same op on a channels-last copy of the input (hd_nchw_to_nhwc_f32): out [num_rois][c][pooled_h][pooled_w].
+ * Same expression per output element as torchvision's roi_align_forward_kernel_impl (samples in (iy, ix) order, then / count);
+ * every sample read is a coalesced 16-byte-per-lane access over the channels instead of 16 scattered 4-byte gathers. */
+int hd_roi_align_fwd_nhwc(const float* feat_nhwc, const float* rois, float* out, int num_rois, int channels, int height,
+                          int width, int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio, hd_stream stream);
+int hd_nchw_to_nhwc_f32(const float* x_nchw, float* y_nhwc, int n, int channels, int height, int width, hd_stream stream);
 
 #ifdef __cplusplus
 }

@@ -588,3 +588,29 @@ def test_roi_align_bwd_matches_torchvision(h, w, scale, c):
     torch.cuda.synchronize()
     assert float(ref.abs().max()) > 0 and got.shape == ref.shape
     assert torch.allclose(got, ref, rtol=1e-4, atol=1e-5 * float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("h,w,scale,c", [(160, 160, 0.25, 256), (40, 40, 1.0 / 16, 256), (20, 24, 1.0 / 32, 64)])
+def test_roi_align_fwd_matches_torchvision(h, w, scale, c):
+    """hd_roi_align_fwd_nhwc against torchvision.ops.roi_align: the same per-element expression, so the pooled features
+    are expected to be bit-identical (reported if not; gated at 1e-6 relative)."""
+    import torchvision
+    o = ops()
+    g = torch.Generator().manual_seed(h + 1)
+    n, k = 3, 300
+    feat = torch.randn(n, c, h, w, generator=g).cuda()
+    img_w, img_h = w / scale, h / scale
+    xy = torch.rand(k, 2, generator=g) * torch.tensor([img_w, img_h]) - 20
+    wh = torch.rand(k, 2, generator=g) ** 2 * torch.tensor([img_w, img_h]) * 1.2 + 0.5
+    wh[:5] = 0.0
+    wh[5:8] = torch.tensor([img_w, img_h]) * 1.5
+    rois = torch.cat([torch.randint(0, n, (k, 1), generator=g).float(), xy, xy + wh], 1).cuda()
+    ref = torchvision.ops.roi_align(feat, rois, (7, 7), scale, 2, False)
+    nhwc = o.nchw_to_nhwc_f32(feat)
+    assert torch.equal(nhwc, feat.permute(0, 2, 3, 1).contiguous())
+    got = o.roi_align_fwd(nhwc, rois, (7, 7), scale, 2)
+    torch.cuda.synchronize()
+    diff = (got - ref).abs().max().item()
+    print(f"\n[roi_align fwd {h}x{w} c{c}] bit-identical: {torch.equal(got, ref)}, max |diff| {diff:.3e}")
+    assert torch.allclose(got, ref, rtol=1e-6, atol=1e-6 * float(ref.abs().max()))
+    assert torch.equal(got, ref)         # holds with this toolchain: same expression, same contraction
