@@ -2,7 +2,8 @@
 
 Activations are ``torch.bfloat16`` tensors of shape ``[N, H, W, C]`` (NHWC, contiguous, C % 16 == 0);
 module-edge tensors are ``torch.float32`` NCHW.  All launches go to ``torch.cuda.current_stream()``.
-Nothing here computes on the CPU or through PyTorch operators: a missing library / wrong device raises.
+Nothing here computes on the CPU; PyTorch operators only appear around the NMS / RoIAlign calls (sort, gather, allocation),
+exactly as in the torchvision ops they replace.  A missing library / wrong device raises.
 """
 import ctypes
 
@@ -14,8 +15,8 @@ from ._lib import HdAct, HdConvArgs, check
 STATS_REPLICAS = 16      # legacy name: default row count for small test problems (see conv_fwd_tiles)
 STEM_KPAD = 160          # 7*7*3 = 147 -> 5 k-blocks of 32
 
-LAUNCHES = 0             # kernels launched through this module (each C-ABI compute call launches exactly one kernel)
-PROFILE = None           # set to a list to record (name, algorithmic FLOPs, start event, end event) per launch
+LAUNCHES = 0             # kernels launched through this module (one per C-ABI compute call; nms / roi_align_bwd add their second)
+PROFILE = None           # set to a list to record (name, algorithmic FLOPs, start event, end event, shape, bytes) per launch
 
 
 class _Timed:
