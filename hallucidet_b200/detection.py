@@ -830,15 +830,45 @@ def sigmoid_focal_loss(inputs, targets, alpha=0.25, gamma=2, reduction="none"):
     return loss
 
 
-def compute_retinanet_loss(targets, head_outputs, anchors, model):
-    matched_idxs = []
-    for anchors_per_image, targets_per_image in zip(anchors, targets):
-        if targets_per_image["boxes"].numel() == 0:
-            matched_idxs.append(torch.full((anchors_per_image.size(0),), -1, dtype=torch.int64, device=anchors_per_image.device))
-            continue
-        matched_idxs.append(model.proposal_matcher(torchvision.ops.box_iou(targets_per_image["boxes"], anchors_per_image)))
+def compute_retinanet_loss(targets, head_outputs, anchors, model, batched=True):
+    """``RetinaNet.compute_loss`` -> head ``compute_loss`` (TV models/detection/retinanet.py; reference copy
+    src/utils/eval_forward_retinanet.py:64-122).  On CUDA the anchor matching runs for the whole batch (_match_batched) and
+    the data-dependent counts (foreground / valid anchors per image) come back in one host read; the per-image index lists
+    are then built with count-known ``nonzero`` -- same indices, same order, same reductions as the per-image loop."""
+    cuda = batched and BATCHED_TAIL and anchors[0].is_cuda and all(a.shape == anchors[0].shape for a in anchors)
+    if cuda:
+        with torch.no_grad():
+            G = max(1, max(int(t["boxes"].shape[0]) for t in targets))
+            gt, present = _pad_rows([t["boxes"] for t in targets], G)
+            midx_all = _match_batched(model.proposal_matcher, gt, present, torch.stack(anchors))          # [B, A]
+            fg_all = midx_all >= 0
+            valid_all = midx_all != model.head.classification_head.BETWEEN_THRESHOLDS
+            fg_count = fg_all.sum(1)
+            counts = torch.cat([fg_count, valid_all.sum(1)]).tolist()                                     # the one host sync
+        B = len(targets)
+        matched_idxs = list(midx_all)
+    else:
+        matched_idxs = []
+        for anchors_per_image, targets_per_image in zip(anchors, targets):
+            if targets_per_image["boxes"].numel() == 0:
+                matched_idxs.append(torch.full((anchors_per_image.size(0),), -1, dtype=torch.int64, device=anchors_per_image.device))
+                continue
+            matched_idxs.append(model.proposal_matcher(torchvision.ops.box_iou(targets_per_image["boxes"], anchors_per_image)))
     cls_losses, reg_losses = [], []
-    for t, logits, reg, anc, midx in zip(targets, head_outputs["cls_logits"], head_outputs["bbox_regression"], anchors, matched_idxs):
+    for b, (t, logits, reg, anc, midx) in enumerate(zip(targets, head_outputs["cls_logits"], head_outputs["bbox_regression"], anchors, matched_idxs)):
+        if cuda:
+            n_fg, n_valid = counts[b], counts[B + b]
+            fg_idx = torch.nonzero_static(fg_all[b], size=n_fg)[:, 0]
+            valid_idx = torch.nonzero_static(valid_all[b], size=n_valid)[:, 0]
+            gt_cls = torch.zeros_like(logits)
+            if n_fg:
+                gt_cls[fg_idx, t["labels"][midx[fg_idx]]] = 1.0
+            # (tensor / 0-dim tensor as in the reference: ATen divides; tensor / Python scalar multiplies by the reciprocal)
+            cls_losses.append(sigmoid_focal_loss(logits[valid_idx], gt_cls[valid_idx], reduction="sum") / (fg_count[b] if n_fg > 1 else 1))
+            matched_gt = t["boxes"][midx[fg_idx]] if n_fg else t["boxes"].new_zeros((0, 4))
+            target_regression = _encode_single(model.box_coder, matched_gt, anc[fg_idx, :])
+            reg_losses.append(F.smooth_l1_loss(reg[fg_idx, :], target_regression, reduction="sum", beta=1.0) / max(1, n_fg))
+            continue
         fg = midx >= 0
         num_fg = fg.sum()
         gt = torch.zeros_like(logits)
@@ -852,8 +882,47 @@ def compute_retinanet_loss(targets, head_outputs, anchors, model):
             "bbox_regression": sum(reg_losses[1:], reg_losses[0]) / max(1, len(targets))}
 
 
+def retinanet_postprocess_detections(model, head_outputs, anchors, image_shapes):
+    """``RetinaNet.postprocess_detections`` (TV models/detection/retinanet.py), same operators in the same order, with the
+    box decoding on ``_decode`` (no per-call host->device scalars) and the final per-image NMS on ``batched_nms`` (hd_nms):
+    identical detections."""
+    from torchvision.models.detection import _utils as det_utils
+    from torchvision.ops import boxes as box_ops
+    class_logits, box_regression = head_outputs["cls_logits"], head_outputs["bbox_regression"]
+    detections = []
+    for index in range(len(image_shapes)):
+        box_regression_per_image = [br[index] for br in box_regression]
+        logits_per_image = [cl[index] for cl in class_logits]
+        anchors_per_image, image_shape = anchors[index], image_shapes[index]
+        image_boxes, image_scores, image_labels = [], [], []
+        for box_regression_per_level, logits_per_level, anchors_per_level in zip(box_regression_per_image, logits_per_image, anchors_per_image):
+            num_classes = logits_per_level.shape[-1]
+            scores_per_level = torch.sigmoid(logits_per_level).flatten()
+            keep_idxs = scores_per_level > model.score_thresh
+            scores_per_level = scores_per_level[keep_idxs]
+            topk_idxs = torch.where(keep_idxs)[0]
+            num_topk = det_utils._topk_min(topk_idxs, model.topk_candidates, 0)
+            scores_per_level, idxs = scores_per_level.topk(num_topk)
+            topk_idxs = topk_idxs[idxs]
+            anchor_idxs = torch.div(topk_idxs, num_classes, rounding_mode="floor")
+            labels_per_level = topk_idxs % num_classes
+            boxes_per_level = _decode(model.box_coder, box_regression_per_level[anchor_idxs], [anchors_per_level[anchor_idxs]])
+            boxes_per_level = boxes_per_level.reshape(-1, 4)
+            boxes_per_level = box_ops.clip_boxes_to_image(boxes_per_level, image_shape)
+            image_boxes.append(boxes_per_level)
+            image_scores.append(scores_per_level)
+            image_labels.append(labels_per_level)
+        image_boxes = torch.cat(image_boxes, dim=0)
+        image_scores = torch.cat(image_scores, dim=0)
+        image_labels = torch.cat(image_labels, dim=0)
+        keep = batched_nms(image_boxes, image_scores, image_labels, model.nms_thresh)
+        keep = keep[: model.detections_per_img]
+        detections.append({"boxes": image_boxes[keep], "scores": image_scores[keep], "labels": image_labels[keep]})
+    return detections
+
+
 def eval_forward_retinanet(model, images, targets, train_det=False, model_name="retinanet"):
-    if not train_det:
+    if not train_det and model.training:
         model.eval()
     _check_targets(targets)
     original_image_sizes = [tuple(img.shape[-2:]) for img in images]
@@ -871,6 +940,10 @@ def eval_forward_retinanet(model, images, targets, train_det=False, model_name="
     num_anchors_per_level = [n * a for n in num_anchors_per_level]
     split_head_outputs = {k: list(v.split(num_anchors_per_level, dim=1)) for k, v in head_outputs.items()}
     split_anchors = [list(x.split(num_anchors_per_level)) for x in anchors]
-    detections = model.postprocess_detections(split_head_outputs, split_anchors, images.image_sizes)
+    if BATCHED_TAIL and images.tensors.is_cuda:
+        with torch.no_grad():
+            detections = retinanet_postprocess_detections(model, split_head_outputs, split_anchors, images.image_sizes)
+    else:
+        detections = model.postprocess_detections(split_head_outputs, split_anchors, images.image_sizes)
     detections = model.transform.postprocess(detections, images.image_sizes, original_image_sizes)
     return losses, detections
