@@ -260,6 +260,7 @@ def main():
         conv_ms = sum(p[2] for p in conv)
         achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         gemm_only = [p for p in prof if p[0] in ("conv_fwd", "conv_dgrad")]
+        best = max(conv, key=lambda p: p[1] / max(p[2], 1e-9)) if conv else None      # the most tensor-bound launch of the step
         narrow_ms = sum(p[2] for p in narrow)
         narrow_gbs = sum(p[4] for p in narrow) / (narrow_ms * 1e-3) / 1e9 if narrow_ms > 0 else 0.0
         traffic = load_traffic()
@@ -281,6 +282,8 @@ def main():
                          "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "peak_source": which,
                          "traffic": traffic.get("dram_bytes_per_launch"), "traffic_launch": traffic.get("launch"),
                          "traffic_algorithmic_bytes": traffic.get("algorithmic_bytes"),
+                         "best_launch": ({"tflops": best[1] / (best[2] * 1e-3) / 1e12, "frac": best[1] / (best[2] * 1e-3) / 1e12 / burst,
+                                          "launch": best[0] + " " + best[3]} if best else None),
                          "conv_launches_per_step": len(conv), "conv_ms_per_step": conv_ms,
                          "conv_gflop_per_step": conv_flops / 1e9,
                          "fwd_dgrad_tflops": (sum(p[1] for p in gemm_only) / (sum(p[2] for p in gemm_only) * 1e-3) / 1e12) if gemm_only else None,
