@@ -261,6 +261,10 @@ def main():
         achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         gemm_only = [p for p in prof if p[0] in ("conv_fwd", "conv_dgrad")]
         best = max(conv, key=lambda p: p[1] / max(p[2], 1e-9)) if conv else None      # the most tensor-bound launch of the step
+        # the 1x1 layers of the ResNet-50 bottlenecks move 4-8 bytes per FLOP-pair more than the 3x3 ones: HBM bound
+        c1 = [p for p in conv if " k1 " in p[3]]
+        c3 = [p for p in conv if " k1 " not in p[3]]
+        c1_ms, c3_ms = sum(p[2] for p in c1), sum(p[2] for p in c3)
         narrow_ms = sum(p[2] for p in narrow)
         narrow_gbs = sum(p[4] for p in narrow) / (narrow_ms * 1e-3) / 1e9 if narrow_ms > 0 else 0.0
         traffic = load_traffic()
@@ -293,6 +297,12 @@ def main():
             "roofline_narrow": {"bound": "hbm", "kernel": "narrow_conv_kernel + narrow_wgrad_kernel (16/32-channel 3x3 layers, halo patch + mma.sync)",
                                 "achieved": narrow_gbs, "peak": hbm, "unit": "GB/s", "frac": narrow_gbs / hbm if hbm else None,
                                 "launches_per_step": len(narrow), "ms_per_step": narrow_ms},
+            "roofline_split": {"k3_tensor": {"launches": len(c3), "ms_per_step": c3_ms,
+                                             "tflops": sum(p[1] for p in c3) / (c3_ms * 1e-3) / 1e12 if c3_ms else None,
+                                             "frac": sum(p[1] for p in c3) / (c3_ms * 1e-3) / 1e12 / burst if c3_ms else None},
+                               "k1_hbm": {"launches": len(c1), "ms_per_step": c1_ms,
+                                          "gbs": sum(p[4] for p in c1) / (c1_ms * 1e-3) / 1e9 if c1_ms else None,
+                                          "frac": sum(p[4] for p in c1) / (c1_ms * 1e-3) / 1e9 / hbm if c1_ms and hbm else None}},
             "loss": host_loss[-1] if host_loss else None,
         }
         if world == 1 and not args.no_cpu_baseline:
