@@ -28,6 +28,11 @@ class HdUnpackDesc(ctypes.Structure):
                 ("row_stride", ctypes.c_int32), ("first_block", ctypes.c_int32), ("scale", ctypes.c_float), ("pad_", ctypes.c_int32)]
 
 
+class HdRoiLevel(ctypes.Structure):
+    _fields_ = [("feat_nhwc", c_void_p), ("grad_nhwc", c_void_p), ("h", ctypes.c_int32), ("w", ctypes.c_int32),
+                ("scale", ctypes.c_float), ("pad_", ctypes.c_int32)]
+
+
 class HdConvArgs(ctypes.Structure):
     _fields_ = [
         ("x0", HdAct), ("x1", HdAct), ("y0", HdAct), ("y1", HdAct),
@@ -82,6 +87,8 @@ PROTOTYPES = {
     "hd_unpack_wgrads": [c_void_p, c_int, c_int, c_void_p],
     "hd_roi_align_bwd_nhwc": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
     "hd_roi_align_fwd_nhwc": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
+    "hd_roi_align_ml_fwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "hd_roi_align_ml_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "hd_nchw_to_nhwc_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "hd_nhwc_to_nchw_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "hd_nms": [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p],

@@ -21,6 +21,15 @@ namespace hd {
 namespace {
 
 constexpr int kRoiThreads = 256;
+constexpr int kMaxLevels = 8;
+
+// feature-pyramid levels a RoI can be pooled from (level_of_roi selects one; a single-level call passes level_of_roi = NULL)
+struct RoiLevels {
+    const float* feat[kMaxLevels];      // forward: channels-last feature maps [N][H][W][C]
+    float* grad[kMaxLevels];            // backward: channels-last gradient scratch (zeroed by the caller)
+    int h[kMaxLevels], w[kMaxLevels];
+    float scale[kMaxLevels];
+};
 constexpr int kMaxBins = 7 * 7;
 constexpr int kMaxSamples = kMaxBins * 4;       // sampling_ratio <= 2
 constexpr int kMaxC = 256;
@@ -31,14 +40,18 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 
 // grad_in: [N][H][W][C] fp32 (channels last)
 __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_nhwc_kernel(const float* __restrict__ grad_out, const float* __restrict__ rois,
-                                                                         float* __restrict__ grad_in, int C, int H, int W, int PH, int PW,
-                                                                         float spatial_scale, int sampling_ratio) {
+                                                                         const long long* __restrict__ level_of_roi, const RoiLevels L,
+                                                                         int C, int PH, int PW, int sampling_ratio) {
     extern __shared__ __align__(16) float gsm[];        // [nbins][C + 4]: one float4 per thread and item, conflict free
     __shared__ float s_w[kMaxSamples * 4];
     __shared__ int s_off[kMaxSamples * 4];              // pixel index y * W + x, or -1
     const int k = blockIdx.x;
     const float* roi = rois + static_cast<long>(k) * 5;
     const int n = static_cast<int>(roi[0]);
+    const int lvl = level_of_roi != nullptr ? static_cast<int>(level_of_roi[k]) : 0;
+    const int H = L.h[lvl], W = L.w[lvl];
+    const float spatial_scale = L.scale[lvl];
+    float* __restrict__ grad_in = L.grad[lvl];
     // torchvision, aligned = false
     const float roi_start_w = roi[1] * spatial_scale, roi_start_h = roi[2] * spatial_scale;
     const float roi_end_w = roi[3] * spatial_scale, roi_end_h = roi[4] * spatial_scale;
@@ -95,15 +108,19 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_nhwc_kernel(const f
 // channels of one pixel (torchvision gathers 16 scattered 4-byte values per output element from NCHW).  Same expression
 // per output element as torchvision's roi_align_forward_kernel_impl: val += w1*v1 + w2*v2 + w3*v3 + w4*v4 over the samples
 // in (iy, ix) order, then val /= count.  The [C][PH*PW] result of a RoI is staged in shared memory and written coalesced.
-__global__ void __launch_bounds__(kRoiThreads) roi_align_fwd_nhwc_kernel(const float* __restrict__ feat, const float* __restrict__ rois,
-                                                                         float* __restrict__ out, int C, int H, int W, int PH, int PW,
-                                                                         float spatial_scale, int sampling_ratio) {
+__global__ void __launch_bounds__(kRoiThreads) roi_align_fwd_nhwc_kernel(const float* __restrict__ rois, const long long* __restrict__ level_of_roi,
+                                                                         const RoiLevels L, float* __restrict__ out, int C, int PH, int PW,
+                                                                         int sampling_ratio) {
     extern __shared__ __align__(16) float gsm[];        // [C][nbins] output tile of this RoI
     __shared__ float s_w[kMaxSamples * 4];
     __shared__ int s_off[kMaxSamples * 4];
     const int k = blockIdx.x;
     const float* roi = rois + static_cast<long>(k) * 5;
     const int n = static_cast<int>(roi[0]);
+    const int lvl = level_of_roi != nullptr ? static_cast<int>(level_of_roi[k]) : 0;
+    const int H = L.h[lvl], W = L.w[lvl];
+    const float spatial_scale = L.scale[lvl];
+    const float* __restrict__ feat = L.feat[lvl];
     const float roi_start_w = roi[1] * spatial_scale, roi_start_h = roi[2] * spatial_scale;
     const float roi_end_w = roi[3] * spatial_scale, roi_end_h = roi[4] * spatial_scale;
     const float roi_width = fmaxf(roi_end_w - roi_start_w, 1.f), roi_height = fmaxf(roi_end_h - roi_start_h, 1.f);
@@ -208,19 +225,14 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_f32_kernel(const float* __re
 
 using namespace hd;
 
-// grad_in_nhwc ([N][H][W][C] fp32 channels-last scratch, zeroed by the caller) += d/d(input) of
-// torchvision.ops.roi_align(input, rois, spatial_scale, PH, PW, sampling_ratio, aligned = False) for grad_out [K][C][PH][PW];
-// rois [K][5] = (batch index, x1, y1, x2, y2).  C % 4 == 0, C <= 256, PH * PW <= 49, sampling_ratio in {1, 2}.
-extern "C" int hd_roi_align_bwd_nhwc(const float* grad_out, const float* rois, float* grad_in_nhwc, int num_rois, int channels,
-                                     int height, int width, int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio,
-                                     hd_stream stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    HD_CHECK_ARG(num_rois >= 0 && channels > 0 && channels % 4 == 0 && channels <= kMaxC && height > 0 && width > 0);
-    HD_CHECK_ARG(kRoiThreads % (channels / 4) == 0);
-    if (num_rois == 0) return HD_OK;
-    HD_CHECK_ARG(grad_out != nullptr && rois != nullptr && grad_in_nhwc != nullptr);
-    HD_CHECK_ARG((reinterpret_cast<uintptr_t>(grad_in_nhwc) & 15) == 0);
+static int roi_check(int num_rois, int channels, int pooled_h, int pooled_w, int sampling_ratio) {
+    HD_CHECK_ARG(num_rois >= 0 && channels > 0 && channels % 4 == 0 && channels <= kMaxC && kRoiThreads % (channels / 4) == 0);
     HD_CHECK_ARG(pooled_h > 0 && pooled_w > 0 && pooled_h * pooled_w <= kMaxBins && sampling_ratio >= 1 && sampling_ratio <= 2);
+    return HD_OK;
+}
+
+static int roi_bwd_launch(const float* grad_out, const float* rois, const long long* level_of_roi, const RoiLevels& L, int num_rois,
+                          int channels, int pooled_h, int pooled_w, int sampling_ratio, cudaStream_t stream) {
     const size_t smem = static_cast<size_t>(pooled_h * pooled_w) * (channels + 4) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set) {
@@ -228,10 +240,75 @@ extern "C" int hd_roi_align_bwd_nhwc(const float* grad_out, const float* rois, f
                                         static_cast<int>(kMaxBins * (kMaxC + 4) * sizeof(float))));
         attr_set = true;
     }
-    roi_align_bwd_nhwc_kernel<<<num_rois, kRoiThreads, smem, stream>>>(grad_out, rois, grad_in_nhwc, channels, height, width, pooled_h,
-                                                                       pooled_w, spatial_scale, sampling_ratio);
+    roi_align_bwd_nhwc_kernel<<<num_rois, kRoiThreads, smem, stream>>>(grad_out, rois, level_of_roi, L, channels, pooled_h, pooled_w,
+                                                                       sampling_ratio);
     HD_CUDA_OK(cudaPeekAtLastError());
     return HD_OK;
+}
+
+static int roi_fwd_launch(const float* rois, const long long* level_of_roi, const RoiLevels& L, float* out, int num_rois, int channels,
+                          int pooled_h, int pooled_w, int sampling_ratio, cudaStream_t stream) {
+    const size_t smem = static_cast<size_t>(channels) * pooled_h * pooled_w * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        HD_CUDA_OK(cudaFuncSetAttribute(roi_align_fwd_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(kMaxC * kMaxBins * sizeof(float))));
+        attr_set = true;
+    }
+    roi_align_fwd_nhwc_kernel<<<num_rois, kRoiThreads, smem, stream>>>(rois, level_of_roi, L, out, channels, pooled_h, pooled_w, sampling_ratio);
+    HD_CUDA_OK(cudaPeekAtLastError());
+    return HD_OK;
+}
+
+// grad_in_nhwc ([N][H][W][C] fp32 channels-last scratch, zeroed by the caller) += d/d(input) of
+// torchvision.ops.roi_align(input, rois, spatial_scale, PH, PW, sampling_ratio, aligned = False) for grad_out [K][C][PH][PW];
+// rois [K][5] = (batch index, x1, y1, x2, y2).  C % 4 == 0, C <= 256, PH * PW <= 49, sampling_ratio in {1, 2}.
+extern "C" int hd_roi_align_bwd_nhwc(const float* grad_out, const float* rois, float* grad_in_nhwc, int num_rois, int channels,
+                                     int height, int width, int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio,
+                                     hd_stream stream_) {
+    if (int e = roi_check(num_rois, channels, pooled_h, pooled_w, sampling_ratio)) return e;
+    HD_CHECK_ARG(height > 0 && width > 0);
+    if (num_rois == 0) return HD_OK;
+    HD_CHECK_ARG(grad_out != nullptr && rois != nullptr && grad_in_nhwc != nullptr && (reinterpret_cast<uintptr_t>(grad_in_nhwc) & 15) == 0);
+    RoiLevels L;
+    memset(&L, 0, sizeof(L));
+    L.grad[0] = grad_in_nhwc; L.h[0] = height; L.w[0] = width; L.scale[0] = spatial_scale;
+    return roi_bwd_launch(grad_out, rois, nullptr, L, num_rois, channels, pooled_h, pooled_w, sampling_ratio, static_cast<cudaStream_t>(stream_));
+}
+
+// Multi-level variants (torchvision MultiScaleRoIAlign): RoI k is pooled from level level_of_roi[k] (device int64), so the
+// whole pyramid is one launch and no per-level index lists (host syncs) are needed.  levels: HOST array of n_levels entries.
+extern "C" int hd_roi_align_ml_fwd(const hd_roi_level* levels, int n_levels, const float* rois, const int64_t* level_of_roi, float* out,
+                                   int num_rois, int channels, int pooled_h, int pooled_w, int sampling_ratio, hd_stream stream_) {
+    if (int e = roi_check(num_rois, channels, pooled_h, pooled_w, sampling_ratio)) return e;
+    HD_CHECK_ARG(levels != nullptr && n_levels >= 1 && n_levels <= kMaxLevels);
+    if (num_rois == 0) return HD_OK;
+    HD_CHECK_ARG(rois != nullptr && level_of_roi != nullptr && out != nullptr);
+    RoiLevels L;
+    memset(&L, 0, sizeof(L));
+    for (int i = 0; i < n_levels; ++i) {
+        HD_CHECK_ARG(levels[i].feat_nhwc != nullptr && (reinterpret_cast<uintptr_t>(levels[i].feat_nhwc) & 15) == 0 && levels[i].h > 0 && levels[i].w > 0);
+        L.feat[i] = levels[i].feat_nhwc; L.h[i] = levels[i].h; L.w[i] = levels[i].w; L.scale[i] = levels[i].scale;
+    }
+    return roi_fwd_launch(rois, reinterpret_cast<const long long*>(level_of_roi), L, out, num_rois, channels, pooled_h, pooled_w,
+                          sampling_ratio, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int hd_roi_align_ml_bwd(const hd_roi_level* levels, int n_levels, const float* grad_out, const float* rois,
+                                   const int64_t* level_of_roi, int num_rois, int channels, int pooled_h, int pooled_w, int sampling_ratio,
+                                   hd_stream stream_) {
+    if (int e = roi_check(num_rois, channels, pooled_h, pooled_w, sampling_ratio)) return e;
+    HD_CHECK_ARG(levels != nullptr && n_levels >= 1 && n_levels <= kMaxLevels);
+    if (num_rois == 0) return HD_OK;
+    HD_CHECK_ARG(rois != nullptr && level_of_roi != nullptr && grad_out != nullptr);
+    RoiLevels L;
+    memset(&L, 0, sizeof(L));
+    for (int i = 0; i < n_levels; ++i) {
+        HD_CHECK_ARG(levels[i].grad_nhwc != nullptr && (reinterpret_cast<uintptr_t>(levels[i].grad_nhwc) & 15) == 0 && levels[i].h > 0 && levels[i].w > 0);
+        L.grad[i] = levels[i].grad_nhwc; L.h[i] = levels[i].h; L.w[i] = levels[i].w; L.scale[i] = levels[i].scale;
+    }
+    return roi_bwd_launch(grad_out, rois, reinterpret_cast<const long long*>(level_of_roi), L, num_rois, channels, pooled_h, pooled_w,
+                          sampling_ratio, static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int hd_nhwc_to_nchw_f32(const float* x_nhwc, float* y_nchw, int n, int channels, int height, int width, hd_stream stream_) {
@@ -248,23 +325,14 @@ extern "C" int hd_nhwc_to_nchw_f32(const float* x_nhwc, float* y_nchw, int n, in
 // input given channels-last (feat_nhwc [N][H][W][C] fp32, see hd_nchw_to_nhwc_f32).  Same constraints as the backward.
 extern "C" int hd_roi_align_fwd_nhwc(const float* feat_nhwc, const float* rois, float* out, int num_rois, int channels, int height,
                                      int width, int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio, hd_stream stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    HD_CHECK_ARG(num_rois >= 0 && channels > 0 && channels % 4 == 0 && channels <= kMaxC && height > 0 && width > 0);
-    HD_CHECK_ARG(kRoiThreads % (channels / 4) == 0);
+    if (int e = roi_check(num_rois, channels, pooled_h, pooled_w, sampling_ratio)) return e;
+    HD_CHECK_ARG(height > 0 && width > 0);
     if (num_rois == 0) return HD_OK;
     HD_CHECK_ARG(feat_nhwc != nullptr && rois != nullptr && out != nullptr && (reinterpret_cast<uintptr_t>(feat_nhwc) & 15) == 0);
-    HD_CHECK_ARG(pooled_h > 0 && pooled_w > 0 && pooled_h * pooled_w <= kMaxBins && sampling_ratio >= 1 && sampling_ratio <= 2);
-    const size_t smem = static_cast<size_t>(channels) * pooled_h * pooled_w * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        HD_CUDA_OK(cudaFuncSetAttribute(roi_align_fwd_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(kMaxC * kMaxBins * sizeof(float))));
-        attr_set = true;
-    }
-    roi_align_fwd_nhwc_kernel<<<num_rois, kRoiThreads, smem, stream>>>(feat_nhwc, rois, out, channels, height, width, pooled_h, pooled_w,
-                                                                       spatial_scale, sampling_ratio);
-    HD_CUDA_OK(cudaPeekAtLastError());
-    return HD_OK;
+    RoiLevels L;
+    memset(&L, 0, sizeof(L));
+    L.feat[0] = feat_nhwc; L.h[0] = height; L.w[0] = width; L.scale[0] = spatial_scale;
+    return roi_fwd_launch(rois, nullptr, L, out, num_rois, channels, pooled_h, pooled_w, sampling_ratio, static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int hd_nchw_to_nhwc_f32(const float* x_nchw, float* y_nhwc, int n, int channels, int height, int width, hd_stream stream_) {

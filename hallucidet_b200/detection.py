@@ -502,6 +502,32 @@ def _roi_align(feat, rois, output_size, spatial_scale, sampling_ratio):
     return roi_align(feat, rois, output_size=output_size, spatial_scale=spatial_scale, sampling_ratio=sampling_ratio)
 
 
+class _MultiLevelRoIAlign(torch.autograd.Function):
+    """All FPN levels of MultiScaleRoIAlign in one launch each way (ops.roi_align_ml_fwd / _bwd): the level of every
+    RoI is read on the device, so no per-level index lists and no host sync."""
+
+    @staticmethod
+    def forward(ctx, rois, levels, scales, output_size, sampling_ratio, *feats):
+        nhwc = [ops.nchw_to_nhwc_f32(f.detach().contiguous()) for f in feats]
+        ctx.save_for_backward(rois, levels)
+        ctx.cfg = ([tuple(f.shape) for f in feats], tuple(scales), int(sampling_ratio), [f.requires_grad for f in feats])
+        return ops.roi_align_ml_fwd(nhwc, scales, rois, levels, output_size, sampling_ratio)
+
+    @staticmethod
+    def backward(ctx, grad):
+        rois, levels = ctx.saved_tensors
+        shapes, scales, sampling_ratio, _ = ctx.cfg
+        grads = ops.roi_align_ml_bwd(grad.contiguous(), rois, levels, shapes, scales, sampling_ratio)
+        return (None, None, None, None, None) + tuple(grads)
+
+
+def _ml_roi_align_ok(feats, output_size, sampling_ratio):
+    c = feats[0].shape[1]
+    return (ROI_ALIGN_FUSED_LEVELS and ROI_ALIGN_FWD and ROI_ALIGN_BWD and len(feats) <= 8
+            and all(f.is_cuda and f.dtype == torch.float32 and f.shape[1] == c for f in feats)
+            and 1 <= sampling_ratio <= 2 and output_size[0] * output_size[1] <= 49 and c % 4 == 0 and c <= 256 and 256 % (c // 4) == 0)
+
+
 def multiscale_roi_align_one_sync(pooler, features, boxes, image_shapes):
     """``torchvision.ops.MultiScaleRoIAlign.forward`` (TV ops/poolers.py) with the per-level ``torch.where(levels == k)``
     (one host sync per FPN level) replaced by a stable sort of the level ids and one ``bincount`` read: the index lists
@@ -515,6 +541,9 @@ def multiscale_roi_align_one_sync(pooler, features, boxes, image_shapes):
         return pooler(features, boxes, image_shapes)
     rois = poolers._convert_to_roi_format(boxes)
     levels = pooler.map_levels(boxes)
+    if len(rois) > 0 and _ml_roi_align_ok(x_filtered, pooler.output_size, pooler.sampling_ratio):    # no host sync at all
+        return _MultiLevelRoIAlign.apply(rois.contiguous(), levels.contiguous(), tuple(float(sc) for sc in pooler.scales),
+                                         tuple(pooler.output_size), int(pooler.sampling_ratio), *x_filtered)
     order = torch.sort(levels, stable=True)[1]
     counts = torch.bincount(levels, minlength=num_levels).tolist()                 # the one host sync
     result = torch.zeros((len(rois), x_filtered[0].shape[1]) + tuple(pooler.output_size), dtype=x_filtered[0].dtype,
@@ -602,6 +631,7 @@ CONCURRENT_NMS = _os.environ.get("HD_CONCURRENT_NMS", "1") != "0"               
 CONCURRENT_POSTPROCESS = _os.environ.get("HD_CONCURRENT_POSTPROCESS", "0") != "0"   # final detections
 BATCHED_TAIL = _os.environ.get("HD_BATCHED_TAIL", "1") != "0"   # whole-batch proposal filter / detections post-processing
 ROI_ALIGN_BWD = _os.environ.get("HD_ROI_ALIGN_BWD", "1") != "0"   # RoIAlign backward on hd_roi_align_bwd_nhwc
+ROI_ALIGN_FUSED_LEVELS = _os.environ.get("HD_ROI_FUSED", "1") == "1"   # all FPN levels in one launch, no host sync
 ROI_ALIGN_FWD = _os.environ.get("HD_ROI_ALIGN_FWD", "1") != "0"   # ... and forward on hd_roi_align_fwd_nhwc (bit-identical)
 DEFER_DETECTIONS = False    # set by HalluciDetTrainer.training_step: roi_heads_eval returns a DeferredDetections
 

@@ -491,3 +491,46 @@ def roi_align_fwd(feat_nhwc, rois, output_size, spatial_scale, sampling_ratio):
         check(_lib.load().hd_roi_align_fwd_nhwc(_ptr(feat_nhwc), _ptr(rois), _ptr(out), k, c, h, w, int(output_size[0]), int(output_size[1]),
                                                 float(spatial_scale), int(sampling_ratio), _stream()), "hd_roi_align_fwd_nhwc")
     return out
+
+
+def _roi_level_table(tensors_nhwc, scales, grads=False):
+    table = (_lib.HdRoiLevel * len(tensors_nhwc))()
+    for i, (t, sc) in enumerate(zip(tensors_nhwc, scales)):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+        if grads:
+            table[i].grad_nhwc = _ptr(t)
+        else:
+            table[i].feat_nhwc = _ptr(t)
+        table[i].h, table[i].w, table[i].scale = t.shape[1], t.shape[2], float(sc)
+    return table
+
+
+def roi_align_ml_fwd(feats_nhwc, scales, rois, levels, output_size, sampling_ratio):
+    """torchvision MultiScaleRoIAlign's per-level roi_align calls as ONE launch: RoI k is pooled from the channels-last
+    level ``levels[k]`` (device int64).  Returns [K, C, PH, PW] fp32, rows in RoI order (bit-identical to the per-level op)."""
+    k, c = rois.shape[0], feats_nhwc[0].shape[3]
+    assert rois.dtype == torch.float32 and rois.is_contiguous() and levels.dtype == torch.int64 and levels.is_contiguous()
+    out = torch.empty(k, c, int(output_size[0]), int(output_size[1]), dtype=torch.float32, device=rois.device)
+    table = _roi_level_table(feats_nhwc, scales)
+    with _Timed("roi_align_fwd"):
+        check(_lib.load().hd_roi_align_ml_fwd(table, len(feats_nhwc), _ptr(rois), _ptr(levels), _ptr(out), k, c, int(output_size[0]),
+                                              int(output_size[1]), int(sampling_ratio), _stream()), "hd_roi_align_ml_fwd")
+    return out
+
+
+def roi_align_ml_bwd(grad_out, rois, levels, shapes, scales, sampling_ratio):
+    """Gradients of roi_align_ml_fwd w.r.t. the NCHW fp32 feature maps of ``shapes``: one reduction launch into zeroed
+    channels-last scratch for all levels, then one layout conversion per level."""
+    global LAUNCHES
+    k, c, ph, pw = grad_out.shape
+    assert grad_out.dtype == torch.float32 and grad_out.is_contiguous()
+    scratch = [torch.zeros(n, h, w, c2, dtype=torch.float32, device=grad_out.device) for (n, c2, h, w) in shapes]
+    outs = [torch.empty(tuple(sh), dtype=torch.float32, device=grad_out.device) for sh in shapes]
+    table = _roi_level_table(scratch, scales, grads=True)
+    with _Timed("roi_align_bwd"):
+        check(_lib.load().hd_roi_align_ml_bwd(table, len(shapes), _ptr(grad_out), _ptr(rois), _ptr(levels), k, c, ph, pw,
+                                              int(sampling_ratio), _stream()), "hd_roi_align_ml_bwd")
+        for sc, o, (n, c2, h, w) in zip(scratch, outs, shapes):
+            check(_lib.load().hd_nhwc_to_nchw_f32(_ptr(sc), _ptr(o), n, c2, h, w, _stream()), "hd_nhwc_to_nchw_f32")
+    LAUNCHES += 1
+    return outs

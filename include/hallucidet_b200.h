@@ -211,6 +211,22 @@ int hd_nhwc_to_nchw_f32(const float* x_nhwc, float* y_nchw, int n, int channels,
 int hd_roi_align_fwd_nhwc(const float* feat_nhwc, const float* rois, float* out, int num_rois, int channels, int height,
                           int width, int pooled_h, int pooled_w, float spatial_scale, int sampling_ratio, hd_stream stream);
 int hd_nchw_to_nhwc_f32(const float* x_nchw, float* y_nhwc, int n, int channels, int height, int width, hd_stream stream);
+/* Whole-pyramid variants (torchvision.ops.MultiScaleRoIAlign, TV ops/poolers.py): RoI k is pooled from level
+ * level_of_roi[k] (DEVICE int64 array, the output of torchvision's LevelMapper), so all levels are one launch and the
+ * per-level index lists -- one host sync per level in torchvision -- disappear.  levels: HOST array of n_levels (<= 8)
+ * entries; forward reads feat_nhwc, backward accumulates into grad_nhwc (zeroed by the caller). */
+typedef struct hd_roi_level {
+    const float* feat_nhwc;   /* [n][h][w][c] fp32 */
+    float* grad_nhwc;         /* [n][h][w][c] fp32 */
+    int32_t h, w;
+    float scale;              /* spatial_scale of the level */
+    int32_t pad_;
+} hd_roi_level;
+int hd_roi_align_ml_fwd(const hd_roi_level* levels, int n_levels, const float* rois, const int64_t* level_of_roi, float* out,
+                        int num_rois, int channels, int pooled_h, int pooled_w, int sampling_ratio, hd_stream stream);
+int hd_roi_align_ml_bwd(const hd_roi_level* levels, int n_levels, const float* grad_out, const float* rois,
+                        const int64_t* level_of_roi, int num_rois, int channels, int pooled_h, int pooled_w, int sampling_ratio,
+                        hd_stream stream);
 
 #ifdef __cplusplus
 }

@@ -72,17 +72,22 @@ def _check_roi_pool_and_loss(device):
     a = det.roi_heads.box_roi_pool(feats, props, [(256, 256)] * 2)
     b = D.multiscale_roi_align_one_sync(det.roi_heads.box_roi_pool, feats, props, [(256, 256)] * 2)
     assert torch.equal(a, b) and a.shape == (337, 256, 7, 7)
-    if device == "cuda":                     # with gradients: the hd_roi_align_* kernels run (forward bit-identical, backward close)
-        fg = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in feats.items())
-        fr = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in feats.items())
-        w = torch.randn(a.shape, generator=g).to(device)
-        c = D.multiscale_roi_align_one_sync(det.roi_heads.box_roi_pool, fg, props, [(256, 256)] * 2)
-        r = det.roi_heads.box_roi_pool(fr, props, [(256, 256)] * 2)
-        assert torch.equal(c, r)
-        (c * w).sum().backward()
-        (r * w).sum().backward()
-        for k in ("0", "1", "2", "3"):
-            assert torch.allclose(fg[k].grad, fr[k].grad, rtol=1e-4, atol=1e-5 * float(fr[k].grad.abs().max()) + 1e-12)
+    for fused in ((True, False) if device == "cuda" else ()):   # with gradients: the hd_roi_align_* kernels run (forward bit-identical,
+        D.ROI_ALIGN_FUSED_LEVELS = fused                         # backward close), all levels in one launch or level by level
+        try:
+            fg = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in feats.items())
+            fr = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in feats.items())
+            w = torch.randn(a.shape, generator=g).to(device)
+            c = D.multiscale_roi_align_one_sync(det.roi_heads.box_roi_pool, fg, props, [(256, 256)] * 2)
+            r = det.roi_heads.box_roi_pool(fr, props, [(256, 256)] * 2)
+            assert torch.equal(c, r)
+            (c * w).sum().backward()
+            (r * w).sum().backward()
+            for k in ("0", "1", "2", "3"):
+                assert torch.allclose(fg[k].grad, fr[k].grad, rtol=1e-4, atol=1e-5 * float(fr[k].grad.abs().max()) + 1e-12)
+            assert fg["pool"].grad is None
+        finally:
+            D.ROI_ALIGN_FUSED_LEVELS = True
     cl, br = torch.randn(337, 2, generator=g).to(device), torch.randn(337, 8, generator=g).to(device)
     labels = [(torch.rand(n, generator=g) > 0.7).long().to(device) for n in (200, 137)]
     rt = [torch.randn(n, 4, generator=g).to(device) for n in (200, 137)]
