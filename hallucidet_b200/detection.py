@@ -631,6 +631,7 @@ CONCURRENT_NMS = _os.environ.get("HD_CONCURRENT_NMS", "1") != "0"               
 CONCURRENT_POSTPROCESS = _os.environ.get("HD_CONCURRENT_POSTPROCESS", "0") != "0"   # final detections
 BATCHED_TAIL = _os.environ.get("HD_BATCHED_TAIL", "1") != "0"   # whole-batch proposal filter / detections post-processing
 ROI_ALIGN_BWD = _os.environ.get("HD_ROI_ALIGN_BWD", "1") != "0"   # RoIAlign backward on hd_roi_align_bwd_nhwc
+EARLY_RPN_TARGETS = _os.environ.get("HD_EARLY_RPN", "1") == "1"   # anchor targets + sampler on a side stream under the backbone forward
 ROI_ALIGN_FUSED_LEVELS = _os.environ.get("HD_ROI_FUSED", "1") == "1"   # all FPN levels in one launch, no host sync
 ROI_ALIGN_FWD = _os.environ.get("HD_ROI_ALIGN_FWD", "1") != "0"   # ... and forward on hd_roi_align_fwd_nhwc (bit-identical)
 DEFER_DETECTIONS = False    # set by HalluciDetTrainer.training_step: roi_heads_eval returns a DeferredDetections
@@ -667,10 +668,31 @@ class DeferredDetections:
         return self._value
 
 
-def rpn_eval(model, images, features, targets):
+_ANCHOR_CACHE = {}
+
+
+def _anchors(model, images, features):
+    """``AnchorGenerator.forward`` is a pure function of the image / feature-map shapes: cached per shape set, so that
+    from the second step on the anchors do not queue behind the backbone forward on the stream (see rpn_eval)."""
+    gen = model.rpn.anchor_generator
+    key = (id(gen), tuple(images.tensors.shape), tuple(map(tuple, images.image_sizes)), tuple(tuple(f.shape) for f in features),
+           features[0].dtype, features[0].device)
+    hit = _ANCHOR_CACHE.get(key)
+    if hit is None:
+        if len(_ANCHOR_CACHE) > 16:
+            _ANCHOR_CACHE.clear()
+        hit = _ANCHOR_CACHE[key] = (gen, gen(images, features))        # (the generator is kept alive so its id stays unique)
+    return hit[1]
+
+
+def rpn_eval(model, images, features, targets, targets_event=None):
+    """``RegionProposalNetwork.forward`` in training mode (TV rpn.py:337-388) as the reference's eval_forward uses it
+    (src/utils/eval_forward_fasterrcnn.py:62-99).  ``targets_event``: CUDA event recorded once ``targets`` are final on
+    the current stream; lets the anchor-target work start before the backbone forward has finished."""
     features = list(features.values())
     objectness, pred_bbox_deltas = model.rpn.head(features)
-    anchors = model.rpn.anchor_generator(images, features)
+    batched = BATCHED_TAIL and features[0].is_cuda
+    anchors = _anchors(model, images, features) if batched else model.rpn.anchor_generator(images, features)
     num_images = len(anchors)
     num_anchors_per_level = [o[0].shape[0] * o[0].shape[1] * o[0].shape[2] for o in objectness]
     objectness, pred_bbox_deltas = concat_box_prediction_layers(objectness, pred_bbox_deltas)
@@ -679,16 +701,36 @@ def rpn_eval(model, images, features, targets):
     pre_nms = sum(min(model.rpn.pre_nms_top_n(), n) for n in num_anchors_per_level)
     if targets is None:
         raise ValueError("targets should not be None")
-    if (BATCHED_TAIL and proposals.is_cuda and proposals.dtype == torch.float32 and _batched_ok(pre_nms)
+    if (batched and proposals.dtype == torch.float32 and _batched_ok(pre_nms)
             and all(a.shape == anchors[0].shape for a in anchors)):
-        # everything that does not need a host-side size is enqueued first (target assignment, box encoding, the proposal
-        # filter up to its NMS); the proposal counts and the sampler's positive / negative counts then come back in ONE read
-        with torch.no_grad():
-            labels, matched_gt_boxes = assign_targets_to_anchors_batched(model.rpn, anchors, targets)
-            regression_targets = _encode_single(model.rpn.box_coder, matched_gt_boxes.reshape(-1, 4), torch.cat(anchors, dim=0))
-            pend_samples = _sample_batched_begin(model.rpn.fg_bg_sampler, labels)
+        # The proposal filter (up to its NMS) is enqueued on the main stream.  Target assignment, box encoding and the
+        # anchor sampler depend only on the anchors and the targets, not on the network: they run on a side stream as soon
+        # as the targets exist -- i.e. underneath the backbone forward -- including the sampler's host read and its
+        # randperm calls, which therefore leave the critical path (same calls in the same order: same CUDA generator use).
         pend_boxes = filter_proposals_batched_begin(model.rpn, proposals, objectness, images.image_sizes, num_anchors_per_level)
-        (boxes, scores), samples = _resolve(pend_boxes, pend_samples)
+        main = torch.cuda.current_stream(proposals.device)
+        if EARLY_RPN_TARGETS:
+            side = _side_streams(proposals.device, 1)[0]
+            if targets_event is None:
+                targets_event = torch.cuda.Event()
+                targets_event.record(main)
+            side.wait_event(targets_event)
+            with torch.cuda.stream(side), torch.no_grad():
+                labels, matched_gt_boxes = assign_targets_to_anchors_batched(model.rpn, anchors, targets)
+                regression_targets = _encode_single(model.rpn.box_coder, matched_gt_boxes.reshape(-1, 4), torch.cat(anchors, dim=0))
+                (samples,) = _resolve(_sample_batched_begin(model.rpn.fg_bg_sampler, labels))      # waits for the side stream only
+                done = torch.cuda.Event()
+                done.record(side)
+            ((boxes, scores),) = _resolve(pend_boxes)
+            main.wait_event(done)
+            for t in [labels, regression_targets] + [x for pn in samples for x in pn]:
+                t.record_stream(main)
+        else:
+            with torch.no_grad():
+                labels, matched_gt_boxes = assign_targets_to_anchors_batched(model.rpn, anchors, targets)
+                regression_targets = _encode_single(model.rpn.box_coder, matched_gt_boxes.reshape(-1, 4), torch.cat(anchors, dim=0))
+                pend_samples = _sample_batched_begin(model.rpn.fg_bg_sampler, labels)
+            (boxes, scores), samples = _resolve(pend_boxes, pend_samples)
         loss_objectness, loss_rpn_box_reg = rpn_compute_loss_batched(model.rpn, objectness, pred_bbox_deltas, labels, regression_targets,
                                                                      samples=samples)
         return boxes, {"loss_objectness": loss_objectness, "loss_rpn_box_reg": loss_rpn_box_reg}
@@ -829,10 +871,14 @@ def eval_forward_fasterrcnn(model, images, targets, train_det=False, model_name=
     original_image_sizes = [tuple(img.shape[-2:]) for img in images]
     images, targets = model.transform(images, targets)
     _assert_no_degenerate_boxes(targets)
+    targets_event = None
+    if images.tensors.is_cuda:
+        targets_event = torch.cuda.Event()
+        targets_event.record()
     features = model.backbone(images.tensors)
     if isinstance(features, torch.Tensor):
         features = OrderedDict([("0", features)])
-    proposals, proposal_losses = rpn_eval(model, images, features, targets)
+    proposals, proposal_losses = rpn_eval(model, images, features, targets, targets_event)
     detections, detector_losses = roi_heads_eval(model, features, proposals, images.image_sizes, targets)
     if isinstance(detections, DeferredDetections):
         image_sizes = images.image_sizes
