@@ -9,6 +9,7 @@ The RPN / RoI heads / RetinaNet head, anchor generator, matcher, samplers, box c
 torchvision's own objects ("stay as the reference implements them"); only ``model.transform`` and
 ``model.backbone`` are the B200 modules.
 """
+import contextlib
 import math
 from collections import OrderedDict
 
@@ -631,6 +632,7 @@ CONCURRENT_NMS = _os.environ.get("HD_CONCURRENT_NMS", "1") != "0"               
 CONCURRENT_POSTPROCESS = _os.environ.get("HD_CONCURRENT_POSTPROCESS", "0") != "0"   # final detections
 BATCHED_TAIL = _os.environ.get("HD_BATCHED_TAIL", "1") != "0"   # whole-batch proposal filter / detections post-processing
 ROI_ALIGN_BWD = _os.environ.get("HD_ROI_ALIGN_BWD", "1") != "0"   # RoIAlign backward on hd_roi_align_bwd_nhwc
+POSTPROCESS_SIDE_STREAM = _os.environ.get("HD_POST_SIDE", "1") == "1"   # deferred train-time detections on a side stream
 EARLY_RPN_TARGETS = _os.environ.get("HD_EARLY_RPN", "1") == "1"   # anchor targets + sampler on a side stream under the backbone forward
 ROI_ALIGN_FUSED_LEVELS = _os.environ.get("HD_ROI_FUSED", "1") == "1"   # all FPN levels in one launch, no host sync
 ROI_ALIGN_FWD = _os.environ.get("HD_ROI_ALIGN_FWD", "1") != "0"   # ... and forward on hd_roi_align_fwd_nhwc (bit-identical)
@@ -643,8 +645,9 @@ class DeferredDetections:
     queued post-processing (the transform's rescaling to the original image size).  Used inside the train step, where the
     detections are a by-product (train_hallucidet.py:181 logs them): the step's critical path then has one host sync less."""
 
-    def __init__(self, pending):
+    def __init__(self, pending, stream=None):
         self._pending = pending
+        self._stream = stream             # side stream the detections are computed on (None: the current stream)
         self._counts = torch.empty(pending.counts_dev.numel(), dtype=torch.int64, pin_memory=True)
         self._counts.copy_(pending.counts_dev.to(torch.int64), non_blocking=True)
         self._event = torch.cuda.Event()
@@ -659,11 +662,19 @@ class DeferredDetections:
     def resolve(self):
         if self._value is None:
             self._event.synchronize()
-            with torch.no_grad():
+            side = self._stream
+            with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()), torch.no_grad():
                 boxes, scores, labels = self._pending.finish(self._counts.tolist())
                 value = [{"boxes": boxes[i], "labels": labels[i], "scores": scores[i]} for i in range(len(boxes))]
                 for fn in self._post:
                     value = fn(value)
+            if side is not None:                      # hand the results over to the caller's stream
+                main = torch.cuda.current_stream(side.device)
+                main.wait_stream(side)
+                for d in value:
+                    for t in d.values():
+                        if torch.is_tensor(t) and t.is_cuda:
+                            t.record_stream(main)
             self._value, self._pending = value, None
         return self._value
 
@@ -721,10 +732,14 @@ def rpn_eval(model, images, features, targets, targets_event=None):
                 (samples,) = _resolve(_sample_batched_begin(model.rpn.fg_bg_sampler, labels))      # waits for the side stream only
                 done = torch.cuda.Event()
                 done.record(side)
-            ((boxes, scores),) = _resolve(pend_boxes)
             main.wait_event(done)
             for t in [labels, regression_targets] + [x for pn in samples for x in pn]:
                 t.record_stream(main)
+            # the loss does not need the proposals: enqueue it before waiting for their counts
+            loss_objectness, loss_rpn_box_reg = rpn_compute_loss_batched(model.rpn, objectness, pred_bbox_deltas, labels,
+                                                                         regression_targets, samples=samples)
+            ((boxes, scores),) = _resolve(pend_boxes)
+            return boxes, {"loss_objectness": loss_objectness, "loss_rpn_box_reg": loss_rpn_box_reg}
         else:
             with torch.no_grad():
                 labels, matched_gt_boxes = assign_targets_to_anchors_batched(model.rpn, anchors, targets)
@@ -817,11 +832,22 @@ def roi_heads_eval(model, features, proposals, image_shapes, targets=None, train
     n_cand = max(p.shape[0] for p in proposals) * (class_logits.shape[-1] - 1)
     if BATCHED_TAIL and class_logits.is_cuda and class_logits.dtype == torch.float32 and _batched_ok(n_cand):
         with torch.no_grad():
+            if DEFER_DETECTIONS and POSTPROCESS_SIDE_STREAM:
+                # the detections feed no loss: they are computed on a side stream (underneath the backward pass), their
+                # data-dependent sizes are read back asynchronously and the lists are assembled when the caller asks
+                # (HalluciDetTrainer.training_step: after the backward pass and the optimizer step have been enqueued)
+                main = torch.cuda.current_stream(class_logits.device)
+                side = _side_streams(class_logits.device, 1)[0]
+                side.wait_stream(main)
+                cl, br = class_logits.detach(), box_regression.detach()
+                for t in [cl, br] + list(proposals):
+                    t.record_stream(side)
+                with torch.cuda.stream(side):
+                    pend = postprocess_detections_batched_begin(model.roi_heads, cl, br, proposals, image_shapes)
+                    return DeferredDetections(pend, side), losses
             pend = postprocess_detections_batched_begin(model.roi_heads, class_logits.detach(), box_regression.detach(), proposals,
                                                         image_shapes)
             if DEFER_DETECTIONS:
-                # the detections feed no loss: their data-dependent sizes are read back asynchronously and the lists are
-                # assembled when the caller asks (HalluciDetTrainer.training_step: after the backward pass has been enqueued)
                 return DeferredDetections(pend), losses
             boxes, scores, labels = _resolve(pend)[0]
     elif class_logits.is_cuda:

@@ -462,28 +462,35 @@ def test_degenerate_target_box_still_raises():
     assert torch.isfinite(out["total"])
 
 
-def test_early_rpn_targets_equal_in_order_path():
-    """Anchor-target assignment + sampling on a side stream under the backbone forward (detection.EARLY_RPN_TARGETS) is the
-    same computation with the same CUDA generator use: losses of consecutive steps are bit-identical to the in-order path."""
+def test_side_stream_tail_equals_in_order_path():
+    """Anchor-target assignment + sampling on a side stream under the backbone forward (detection.EARLY_RPN_TARGETS) and
+    the train-time detections on a side stream under the backward pass (detection.POSTPROCESS_SIDE_STREAM) are the same
+    computations with the same CUDA generator use: first-step losses and detections are bit-identical to the in-order path."""
     from oracle import step as ostep
     from hallucidet_b200 import detection as D
     from hallucidet_b200.train import HalluciDetTrainer
     ir, rgb, targets = ostep.synthetic_batch(4, 160, 192, seed=5, device="cuda")
-    runs = []
-    for early in (True, False, True):
-        D.EARLY_RPN_TARGETS = early
+    runs, dets = [], []
+    for side in (True, False, True):
+        D.EARLY_RPN_TARGETS = D.POSTPROCESS_SIDE_STREAM = side
         try:
             tr = HalluciDetTrainer(detector_name="fasterrcnn", size=192, seed=123)
             torch.manual_seed(77)
             torch.cuda.manual_seed(77)
             losses = []
-            for _ in range(3):
+            for i in range(3):
                 out = tr.training_step(rgb, targets, ir, targets)
                 losses.append(torch.stack([out[k].detach().float() for k in sorted(out) if torch.is_tensor(out[k]) and out[k].numel() == 1]))
+                if i == 0:
+                    dets.append([{k: v.detach().cpu() for k, v in d.items()} for d in out["detections"]])
             torch.cuda.synchronize()
             runs.append(torch.stack(losses).cpu())
         finally:
-            D.EARLY_RPN_TARGETS = True
+            D.EARLY_RPN_TARGETS = D.POSTPROCESS_SIDE_STREAM = True
     # the first step is identical by construction; later steps also see the (atomics-ordered) gradients of the first
     assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][0], runs[2][0])
     assert torch.allclose(runs[0], runs[1], rtol=2e-2) and torch.allclose(runs[0], runs[2], rtol=2e-2)
+    for other in dets[1:]:
+        assert len(other) == len(dets[0]) == 4
+        for x, y in zip(dets[0], other):
+            assert all(torch.equal(x[k], y[k]) for k in ("boxes", "labels", "scores"))
