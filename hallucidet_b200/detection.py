@@ -11,6 +11,8 @@ torchvision's own objects ("stay as the reference implements them"); only ``mode
 """
 import contextlib
 import math
+
+import numpy as np
 from collections import OrderedDict
 
 import torch
@@ -321,24 +323,41 @@ def postprocess_detections_batched_begin(roi_heads, class_logits, box_regression
 
 # ---- whole-batch target assignment and sampling (torchvision loops one image at a time: ~15 launches + 2-3 syncs each) ----
 
-def _pad_rows(rows, width, fill=0):
-    """List of [n_i, ...] tensors -> ([B, width, ...] padded with ``fill``, [B, width] bool presence mask).  The row
-    counts are host-known shapes; no Python loop over elements (``pad_sequence`` copies row by row in C++)."""
-    B = len(rows)
-    counts = [int(r.shape[0]) for r in rows]
+def _pad_rows(rows, width, fill=0, counts=None):
+    """List of [n_i, ...] tensors -> ([B, width, ...] padded with ``fill``, [B, width] bool presence mask).  With ``counts``
+    (rows per image), ``rows`` may hold several pieces per image, image-major.  The row counts are host-known shapes: the
+    destination row of every source row is computed on the host, so the padding is one concatenation + one index_copy for
+    the whole batch (instead of a copy per image)."""
+    if counts is None:
+        counts = [int(r.shape[0]) for r in rows]
+    B = len(counts)
     ref = rows[0]
-    if all(c == width for c in counts):
+    if len(rows) == B and all(c == width for c in counts):
         return torch.stack(rows), torch.ones(B, width, dtype=torch.bool, device=ref.device)
-    if max(counts) == 0:
-        out = ref.new_full((B, width) + tuple(ref.shape[1:]), fill)
-    else:
-        out = torch.nn.utils.rnn.pad_sequence(rows, batch_first=True, padding_value=fill)
-        if out.shape[1] < width:
-            extra = out.new_full((B, width - out.shape[1]) + tuple(out.shape[2:]), fill)
-            out = torch.cat([out, extra], dim=1)
-    cnt = torch.tensor(counts, dtype=torch.int64).to(ref.device, non_blocking=True)
-    present = torch.arange(width, device=ref.device)[None, :] < cnt[:, None]
-    return out, present
+    out = ref.new_full((B * width,) + tuple(ref.shape[1:]), fill)
+    present = torch.zeros(B * width, dtype=torch.bool, device=ref.device)
+    if sum(counts) > 0:
+        dst = np.concatenate([np.arange(b * width, b * width + c, dtype=np.int64) for b, c in enumerate(counts)])
+        dst = torch.from_numpy(dst).to(ref.device, non_blocking=True)
+        out.index_copy_(0, dst, torch.cat(rows))
+        present.index_fill_(0, dst, True)
+    return out.view((B, width) + tuple(ref.shape[1:])), present.view(B, width)
+
+
+_GT_PAD = {"key": None, "val": None}
+
+
+def _padded_gt(targets, dtype):
+    """Ground-truth boxes / labels of the batch padded to [B, G, 4] / [B, G] (+ presence mask); the RPN and the RoI heads
+    both need them, so the last result is kept (keyed by the identity and version of the target tensors)."""
+    key = (dtype,) + tuple((id(t["boxes"]), t["boxes"]._version, id(t["labels"]), t["labels"]._version) for t in targets)
+    if _GT_PAD["key"] != key:
+        boxes = [t["boxes"].to(dtype) for t in targets]
+        G = max(1, max(int(g.shape[0]) for g in boxes))
+        gt, present = _pad_rows(boxes, G)
+        gl, _ = _pad_rows([t["labels"] for t in targets], G)
+        _GT_PAD["key"], _GT_PAD["val"] = key, (gt, present, gl, [(t["boxes"], t["labels"]) for t in targets])   # (keeps the ids alive)
+    return _GT_PAD["val"][:3]
 
 
 def _match_batched(matcher, gt_boxes, gt_present, boxes):
@@ -363,28 +382,52 @@ def _match_batched(matcher, gt_boxes, gt_present, boxes):
     return matches
 
 
+class _Samples:
+    """Result of the batched sampler: flat indices into the [B * N] label array (image-major, in the order drawn within an
+    image) of the sampled positives / negatives, and their per-image counts (host ints)."""
+
+    def __init__(self, pos, neg, n_pos, n_neg):
+        self.pos, self.neg, self.n_pos, self.n_neg = pos, neg, n_pos, n_neg
+
+    def tensors(self):
+        return [self.pos, self.neg]
+
+
+def _gather_perms(nz, perms, starts, width):
+    """nz: nonzero_static rows (image, column) of a [B, N] mask; perms[b] indexes the entries of image b (which start at row
+    starts[b]).  Returns the selected entries as flat indices image * width + column -- one gather for the whole batch."""
+    if len(perms) == 1:
+        rows = perms[0] + starts[0] if starts[0] else perms[0]
+    else:
+        rows = torch.cat(torch._foreach_add(perms, starts))
+    sel = nz[rows]
+    return sel[:, 0] * width + sel[:, 1]
+
+
 def _sample_batched_begin(sampler, labels):
     """``det_utils.BalancedPositiveNegativeSampler`` for labels [B, N] (>= 1 positive, 0 negative, -1 ignored / padding).
-    Resolves to per-image (pos_idx, neg_idx) index tensors (unsorted, as drawn).  The two ``torch.randperm`` calls per image
-    are issued with the same sizes and in the same order as torchvision's loop, so the CUDA generator is consumed
-    identically and the samples are the same; everything else (counts, index lists) is computed once for the batch."""
+    Resolves to a ``_Samples``.  The two ``torch.randperm`` calls per image are issued with the same sizes and in the same
+    order as torchvision's loop, so the CUDA generator is consumed identically and the samples are the same; everything
+    else (counts, index lists, the gathers) is computed once for the batch."""
     B, N = labels.shape
     pos_mask, neg_mask = labels >= 1, labels == 0
 
     def finish(cnt):
         n_pos_all, n_neg_all = cnt[:B], cnt[B:]
-        pos_nz = torch.nonzero_static(pos_mask, size=sum(n_pos_all))[:, 1]
-        neg_nz = torch.nonzero_static(neg_mask, size=sum(n_neg_all))[:, 1]
-        out, po, no = [], 0, 0
+        pos_nz = torch.nonzero_static(pos_mask, size=sum(n_pos_all))
+        neg_nz = torch.nonzero_static(neg_mask, size=sum(n_neg_all))
+        perms_p, perms_n, starts_p, starts_n, num_p, num_n, po, no = [], [], [], [], [], [], 0, 0
         for b in range(B):
-            positive, negative = pos_nz[po:po + n_pos_all[b]], neg_nz[no:no + n_neg_all[b]]
-            po, no = po + n_pos_all[b], no + n_neg_all[b]
             num_pos = min(n_pos_all[b], int(sampler.batch_size_per_image * sampler.positive_fraction))
             num_neg = min(n_neg_all[b], sampler.batch_size_per_image - num_pos)
-            perm1 = torch.randperm(n_pos_all[b], device=labels.device)[:num_pos]
-            perm2 = torch.randperm(n_neg_all[b], device=labels.device)[:num_neg]
-            out.append((positive[perm1], negative[perm2]))
-        return out
+            perms_p.append(torch.randperm(n_pos_all[b], device=labels.device)[:num_pos])
+            perms_n.append(torch.randperm(n_neg_all[b], device=labels.device)[:num_neg])
+            starts_p.append(po)
+            starts_n.append(no)
+            num_p.append(num_pos)
+            num_n.append(num_neg)
+            po, no = po + n_pos_all[b], no + n_neg_all[b]
+        return _Samples(_gather_perms(pos_nz, perms_p, starts_p, N), _gather_perms(neg_nz, perms_n, starts_n, N), num_p, num_n)
     return _Pending(torch.cat([pos_mask.sum(1), neg_mask.sum(1)]), finish)
 
 
@@ -396,8 +439,7 @@ def assign_targets_to_anchors_batched(rpn, anchors, targets):
     """``RegionProposalNetwork.assign_targets_to_anchors`` (TV rpn.py) for the whole batch; returns [B, A] float labels
     (1 / 0 / -1) and [B, A, 4] matched boxes (identical values; the per-image lists are rows of these)."""
     A = torch.stack(anchors)                                                 # every image has the same anchor count
-    G = max(1, max(int(t["boxes"].shape[0]) for t in targets))
-    gt, present = _pad_rows([t["boxes"] for t in targets], G)
+    gt, present, _ = _padded_gt(targets, targets[0]["boxes"].dtype)
     matches = _match_batched(rpn.proposal_matcher, gt, present, A)
     matched_gt = torch.gather(gt, 1, matches.clamp(min=0)[..., None].expand(-1, -1, 4))
     labels = (matches >= 0).to(torch.float32)
@@ -411,8 +453,8 @@ def rpn_compute_loss_batched(rpn, objectness, pred_bbox_deltas, labels, regressi
     B, A = labels.shape
     if samples is None:
         samples = _sample_batched(rpn.fg_bg_sampler, labels)
-    pos = torch.sort(torch.cat([p + b * A for b, (p, _) in enumerate(samples)]))[0]      # == where(cat(pos masks))
-    neg = torch.sort(torch.cat([n + b * A for b, (_, n) in enumerate(samples)]))[0]
+    pos = torch.sort(samples.pos)[0]                                                     # == where(cat(pos masks))
+    neg = torch.sort(samples.neg)[0]
     sampled = torch.cat([pos, neg], dim=0)
     objectness = objectness.flatten()
     labels = labels.reshape(-1)
@@ -428,13 +470,11 @@ def select_training_samples_batched(roi_heads, proposals, targets, return_num_po
     dtype, device = proposals[0].dtype, proposals[0].device
     B = len(proposals)
     gt_boxes = [t["boxes"].to(dtype) for t in targets]
-    gt_labels = [t["labels"] for t in targets]
-    G = max(1, max(int(g.shape[0]) for g in gt_boxes))
-    gt, present = _pad_rows(gt_boxes, G)
-    gl, _ = _pad_rows(gt_labels, G)
-    with_gt = [torch.cat((p, g)) for p, g in zip(proposals, gt_boxes)]      # add_gt_proposals
-    N = max(int(p.shape[0]) for p in with_gt)
-    P, p_present = _pad_rows(with_gt, N)
+    gt, present, gl = _padded_gt(targets, dtype)
+    G = gt.shape[1]
+    per_image_rows = [int(p.shape[0]) + int(g.shape[0]) for p, g in zip(proposals, gt_boxes)]
+    N = max(per_image_rows)
+    P, p_present = _pad_rows([x for pg in zip(proposals, gt_boxes) for x in pg], N, counts=per_image_rows)   # add_gt_proposals
     matches = _match_batched(roi_heads.proposal_matcher, gt, present, P)
     clamped = matches.clamp(min=0)
     labels = torch.gather(gl, 1, clamped).to(torch.int64)
@@ -442,8 +482,8 @@ def select_training_samples_batched(roi_heads, proposals, targets, return_num_po
     labels = torch.where(matches == roi_heads.proposal_matcher.BETWEEN_THRESHOLDS, labels.new_full((), -1), labels)
     labels = torch.where(p_present, labels, labels.new_full((), -1))        # padding is ignored by the sampler
     samples = _sample_batched(roi_heads.fg_bg_sampler, labels)
-    per_image = [int(p.shape[0] + n.shape[0]) for p, n in samples]
-    flat = torch.sort(torch.cat([torch.cat((p, n)) + b * N for b, (p, n) in enumerate(samples)]))[0]   # == where(pos | neg) per image
+    per_image = [p + n for p, n in zip(samples.n_pos, samples.n_neg)]
+    flat = torch.sort(torch.cat((samples.pos, samples.neg)))[0]                 # == where(pos | neg) per image, back to back
     out_props = P.view(-1, 4)[flat]
     out_labels = labels.view(-1)[flat]
     out_matched = clamped.view(-1)[flat]
@@ -453,7 +493,7 @@ def select_training_samples_batched(roi_heads, proposals, targets, return_num_po
     out = (list(out_props.split(per_image)), list(out_matched.split(per_image)), list(out_labels.split(per_image)),
            list(regression_targets.split(per_image)))
     if return_num_pos:                                   # sampled foreground boxes == entries with label > 0 (host-known)
-        return out + (sum(int(p.shape[0]) for p, _ in samples),)
+        return out + (sum(samples.n_pos),)
     return out
 
 
@@ -533,18 +573,29 @@ def multiscale_roi_align_one_sync(pooler, features, boxes, image_shapes):
     """``torchvision.ops.MultiScaleRoIAlign.forward`` (TV ops/poolers.py) with the per-level ``torch.where(levels == k)``
     (one host sync per FPN level) replaced by a stable sort of the level ids and one ``bincount`` read: the index lists
     are the same (ascending within a level), so the pooled features are identical."""
-    from torchvision.ops import poolers, roi_align
+    from torchvision.ops import boxes as box_ops, poolers, roi_align
     x_filtered = poolers._filter_input(features, pooler.featmap_names)
     if pooler.scales is None or pooler.map_levels is None:
         pooler.scales, pooler.map_levels = poolers._setup_scales(x_filtered, image_shapes, pooler.canonical_scale, pooler.canonical_level)
     num_levels = len(x_filtered)
     if num_levels == 1:
         return pooler(features, boxes, image_shapes)
+    if sum(len(b) for b in boxes) > 0 and _ml_roi_align_ok(x_filtered, pooler.output_size, pooler.sampling_ratio):    # no host sync at all
+        # _convert_to_roi_format and LevelMapper.__call__ (TV ops/poolers.py) on the concatenated boxes: the same
+        # element-wise operations in the same order, without the per-image launches
+        lm = pooler.map_levels
+        concat = torch.cat(boxes, dim=0)
+        ids = np.repeat(np.arange(len(boxes), dtype=np.float32), [len(b) for b in boxes])
+        ids = torch.from_numpy(ids).to(concat.device, non_blocking=True).to(concat.dtype)
+        rois = torch.cat([ids[:, None], concat], dim=1)
+        s = torch.sqrt(box_ops.box_area(concat))
+        target_lvls = torch.floor(lm.lvl0 + torch.log2(s / lm.s0) + torch.tensor(lm.eps, dtype=s.dtype))
+        target_lvls = torch.clamp(target_lvls, min=lm.k_min, max=lm.k_max)
+        levels = (target_lvls.to(torch.int64) - lm.k_min).to(torch.int64)
+        return _MultiLevelRoIAlign.apply(rois, levels, tuple(float(sc) for sc in pooler.scales),
+                                         tuple(pooler.output_size), int(pooler.sampling_ratio), *x_filtered)
     rois = poolers._convert_to_roi_format(boxes)
     levels = pooler.map_levels(boxes)
-    if len(rois) > 0 and _ml_roi_align_ok(x_filtered, pooler.output_size, pooler.sampling_ratio):    # no host sync at all
-        return _MultiLevelRoIAlign.apply(rois.contiguous(), levels.contiguous(), tuple(float(sc) for sc in pooler.scales),
-                                         tuple(pooler.output_size), int(pooler.sampling_ratio), *x_filtered)
     order = torch.sort(levels, stable=True)[1]
     counts = torch.bincount(levels, minlength=num_levels).tolist()                 # the one host sync
     result = torch.zeros((len(rois), x_filtered[0].shape[1]) + tuple(pooler.output_size), dtype=x_filtered[0].dtype,
@@ -733,7 +784,7 @@ def rpn_eval(model, images, features, targets, targets_event=None):
                 done = torch.cuda.Event()
                 done.record(side)
             main.wait_event(done)
-            for t in [labels, regression_targets] + [x for pn in samples for x in pn]:
+            for t in [labels, regression_targets] + samples.tensors() + list(_padded_gt(targets, targets[0]["boxes"].dtype)):
                 t.record_stream(main)
             # the loss does not need the proposals: enqueue it before waiting for their counts
             loss_objectness, loss_rpn_box_reg = rpn_compute_loss_batched(model.rpn, objectness, pred_bbox_deltas, labels,
