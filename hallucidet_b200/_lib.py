@@ -43,7 +43,7 @@ class HdConvArgs(ctypes.Structure):
         ("stats", c_void_p), ("stats_replicas", ctypes.c_int32),
         ("out_f32_nchw", c_void_p), ("out_f32_channels", ctypes.c_int32),
         ("store_bf16", ctypes.c_int32), ("phase_mask", ctypes.c_int32),
-        ("dw", c_void_p), ("split_k", ctypes.c_int32),
+        ("dw", c_void_p), ("split_k", ctypes.c_int32), ("out_f32_nhwc", ctypes.c_int32),
     ]
 
 

@@ -10,12 +10,18 @@ The weights are frozen: BatchNorm is an affine constant folded into the bf16 GEM
 ONLY the input gradient (dgrad) -- never weight gradients -- with the ReLU masks fused into the dgrad epilogues.
 No PyTorch/CPU fallback.
 """
+import os
 from collections import OrderedDict
 
 import torch
 import torch.nn as nn
 
 from . import ops
+
+# FPN outputs / their gradients cross the module boundary as logical NCHW fp32 tensors with CHANNELS-LAST strides: the conv
+# epilogue writes them that way (no transpose), cuDNN's RPN / RetinaNet head convolutions and the RoIAlign kernels read
+# channels-last natively (no nchwToNhwc / nhwcToNchw passes), and the incoming gradients are a plain cast to bf16.
+CHANNELS_LAST_FEATURES = os.environ.get("HD_CL_FEATURES", "1") == "1"
 
 
 class _FConv:
@@ -167,7 +173,7 @@ class _BackboneEngine:
             c = self.c_out[li]
             inner = _FConv(self, fpn.inner_blocks[i][0], None, (c.shape[1], c.shape[2]), relu=False)
             layer = _FConv(self, fpn.layer_blocks[i][0], None, (c.shape[1], c.shape[2]), relu=False)
-            out = torch.empty(B, layer.cout, layer.h, layer.w, device=device)
+            out = self._new_out(layer.cout, layer.h, layer.w)
             self.levels.append(dict(li=li, inner=inner, layer=layer, out=out, name=str(i)))
         self.level_names = [lv["name"] for lv in self.levels]
         self.extra = []
@@ -176,14 +182,32 @@ class _BackboneEngine:
             p6 = _FConv(self, fpn.extra_blocks.p6, None, (top.h, top.w), relu=False)
             self.p6_relu = self.new_act(p6.h, p6.w, p6.cout)
             p7 = _FConv(self, fpn.extra_blocks.p7, None, (p6.h, p6.w), relu=False)
-            self.extra = [dict(conv=p6, out=torch.empty(B, 256, p6.h, p6.w, device=device), name="p6"),
-                          dict(conv=p7, out=torch.empty(B, 256, p7.h, p7.w, device=device), name="p7")]
+            self.extra = [dict(conv=p6, out=self._new_out(256, p6.h, p6.w), name="p6"),
+                          dict(conv=p7, out=self._new_out(256, p7.h, p7.w), name="p7")]
             self.level_names += ["p6", "p7"]
             self.ones = torch.ones(256, device=device)
             self.zeros = torch.zeros(256, device=device)
         self.grad_bufs = {}
         self.dx = torch.empty(B, 3, H, W, device=device)
         self.dP_in = [torch.empty_like(lv["out"]) for lv in self.levels] + [torch.empty_like(e["out"]) for e in self.extra]
+
+    def _new_out(self, c, h, w):
+        """fp32 [B, C, H, W] output buffer (channels-last strides when CHANNELS_LAST_FEATURES)."""
+        self.cl = CHANNELS_LAST_FEATURES and c % 16 == 0
+        if self.cl:
+            return torch.empty(self.B, h, w, c, device=self.device).permute(0, 3, 1, 2)
+        return torch.empty(self.B, c, h, w, device=self.device)
+
+    def _grad_to_nhwc_bf16(self, src, dst, accumulate=False):
+        """fp32 gradient of an output (layout of the output buffers) -> bf16 NHWC ``dst`` (captured in the CUDA graph)."""
+        if self.cl:
+            nhwc = src.permute(0, 2, 3, 1)
+            if accumulate:
+                dst.add_(nhwc)
+            else:
+                dst.copy_(nhwc)
+        else:
+            ops.nchw_f32_to_nhwc_bf16(src, dst, accumulate=accumulate)
 
     def new_act(self, h, w, c):
         return torch.empty(self.B, h, w, c, dtype=torch.bfloat16, device=self.device)
@@ -219,7 +243,8 @@ class _BackboneEngine:
             ops.pad_hw(x, c.x_pad)
             x = c.x_pad
         ops.conv_fwd(ops.conv_args(x, c.y, c.packed.w_fwd, k=c.k, stride=c.stride, bias=c.bias, add=add, relu=c.relu,
-                                   out_f32=out_f32, out_f32_channels=c.cout if out_f32 is not None else 0, store_bf16=store_bf16))
+                                   out_f32=out_f32, out_f32_channels=c.cout if out_f32 is not None else 0, store_bf16=store_bf16,
+                                   out_f32_nhwc=out_f32 is not None and self.cl))
 
     def forward(self, x):
         self.x_in.copy_(x)
@@ -261,8 +286,16 @@ class _BackboneEngine:
 
     # ---- backward (input gradient only) ---------------------------------------------------------------
     def backward(self, grads):
-        for buf, g in zip(self.dP_in, grads):
-            if g is None:
+        nl = len(self.levels)
+        for i, (buf, g) in enumerate(zip(self.dP_in, grads)):
+            if self.cl and i < nl:
+                # channels-last: the fp32 gradient is cast straight into the graph's static bf16 NHWC buffer (any strides)
+                dst = self.gbuf(("gP", i), self.levels[i]["layer"].y)
+                if g is None:
+                    dst.zero_()
+                else:
+                    dst.copy_(g.permute(0, 2, 3, 1))
+            elif g is None:
                 buf.zero_()
             else:
                 buf.copy_(g)
@@ -287,15 +320,16 @@ class _BackboneEngine:
         gP = []
         for i, lv in enumerate(self.levels):
             g = self.gbuf(("gP", i), lv["layer"].y)
-            ops.nchw_f32_to_nhwc_bf16(self.dP_in[i], g)
+            if not self.cl:                                          # (channels-last: filled by backward() before the graph runs)
+                ops.nchw_f32_to_nhwc_bf16(self.dP_in[i], g)
             gP.append(g)
         if self.extra:
             p6, p7 = self.extra[0]["conv"], self.extra[1]["conv"]
             g7 = self.gbuf(("gP", "p7"), p7.y)
-            ops.nchw_f32_to_nhwc_bf16(self.dP_in[nl + 1], g7)
+            self._grad_to_nhwc_bf16(self.dP_in[nl + 1], g7)
             g6 = self.gbuf(("gP", "p6"), p6.y)
             self._dgrad(p7, g7, g6, mask=p6.y)                       # through ReLU(p6)
-            ops.nchw_f32_to_nhwc_bf16(self.dP_in[nl], g6, accumulate=True)
+            self._grad_to_nhwc_bf16(self.dP_in[nl], g6, accumulate=True)
             g5 = self.gbuf(("g5x", 0), gP[top])
             self._dgrad(p6, g6, g5, add=gP[top])
             gP[top] = g5

@@ -54,6 +54,7 @@ struct ConvGemmParams {
     int stats_replicas;
     float* out_f32;
     int out_f32_c;
+    int out_f32_nhwc;           // fp32 copy is [N][H][W][out_f32_c] (channels-last) instead of NCHW
     int store_bf16;
     int stages, a_bytes, stage_bytes;
     int tmem_cols;
@@ -467,7 +468,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = 0.f;
                 }
-                if (kF32 && P.out_f32 != nullptr && valid) {
+                if (kF32 && P.out_f32 != nullptr && valid && P.out_f32_nhwc) {
+                    // channels-last fp32 copy: 16 channels of one pixel = 64 contiguous bytes per thread
+                    if (ch0 + 16 <= P.out_f32_c) {
+                        float4* dst = reinterpret_cast<float4*>(P.out_f32 + pix * P.out_f32_c + ch0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                } else if (kF32 && P.out_f32 != nullptr && valid) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int ch = ch0 + j;
@@ -756,6 +764,9 @@ static int fill_epilogue(ConvGemmParams& P, const hd_conv_args* a) {
     P.stats_replicas = a->stats_replicas;                  // rows available in the per-tile statistics buffer
     P.out_f32 = a->out_f32_nchw;
     P.out_f32_c = a->out_f32_channels;
+    P.out_f32_nhwc = a->out_f32_nhwc;
+    HD_CHECK_ARG(!a->out_f32_nhwc || (a->out_f32_nchw != nullptr && a->out_f32_channels % 16 == 0 && !a->sigmoid &&
+                                      (reinterpret_cast<uintptr_t>(a->out_f32_nchw) & 15) == 0));
     P.store_bf16 = a->store_bf16;
     HD_CHECK_ARG(a->store_bf16 || a->out_f32_nchw != nullptr);
     HD_CHECK_ARG(!(a->y1.ptr != nullptr && (a->add != nullptr || a->mask != nullptr || a->stats != nullptr)));

@@ -544,6 +544,7 @@ bool narrow_conv_eligible(const hd_conv_args* a, bool dgrad) {
     if (!narrow_c(a->x0.c) || !narrow_c(a->y0.c)) return false;
     if (dgrad && a->stats != nullptr) return false;
     if (a->stats != nullptr && a->out_f32_nchw != nullptr) return false;      // one specialised epilogue per launch
+    if (a->out_f32_nhwc) return false;
     return true;
 }
 

@@ -82,6 +82,16 @@ def install_b200_backbone(detector):
         p.requires_grad_(False)
     if not isinstance(detector.backbone, FrozenBackbone):
         detector.backbone = FrozenBackbone.from_torchvision(detector.backbone)
+    from . import backbone as _bb
+    if _bb.CHANNELS_LAST_FEATURES:
+        # the backbone hands over channels-last feature maps: keep the head convolutions' weights in the same format so
+        # cuDNN runs them without per-call layout conversions (values and state_dict are unchanged)
+        for name in ("rpn", "head"):
+            head = getattr(detector, name, None)
+            if isinstance(head, torch.nn.Module):
+                for m in head.modules():
+                    if isinstance(m, torch.nn.Conv2d):
+                        m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
     return detector
 
 
@@ -549,16 +559,20 @@ class _MultiLevelRoIAlign(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, rois, levels, scales, output_size, sampling_ratio, *feats):
-        nhwc = [ops.nchw_to_nhwc_f32(f.detach().contiguous()) for f in feats]
+        nhwc, cl = [], []
+        for f in feats:
+            v = f.detach().permute(0, 2, 3, 1)
+            cl.append(v.is_contiguous())           # channels-last feature map (backbone.CHANNELS_LAST_FEATURES): used in place
+            nhwc.append(v if cl[-1] else ops.nchw_to_nhwc_f32(f.detach().contiguous()))
         ctx.save_for_backward(rois, levels)
-        ctx.cfg = ([tuple(f.shape) for f in feats], tuple(scales), int(sampling_ratio), [f.requires_grad for f in feats])
+        ctx.cfg = ([tuple(f.shape) for f in feats], tuple(scales), int(sampling_ratio), cl)
         return ops.roi_align_ml_fwd(nhwc, scales, rois, levels, output_size, sampling_ratio)
 
     @staticmethod
     def backward(ctx, grad):
         rois, levels = ctx.saved_tensors
-        shapes, scales, sampling_ratio, _ = ctx.cfg
-        grads = ops.roi_align_ml_bwd(grad.contiguous(), rois, levels, shapes, scales, sampling_ratio)
+        shapes, scales, sampling_ratio, cl = ctx.cfg
+        grads = ops.roi_align_ml_bwd(grad.contiguous(), rois, levels, shapes, scales, sampling_ratio, channels_last=cl)
         return (None, None, None, None, None) + tuple(grads)
 
 

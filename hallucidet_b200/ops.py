@@ -61,7 +61,7 @@ def round_up(a, b):
 
 
 def conv_args(x0, y0, w=None, k=3, stride=1, x1=None, y1=None, bias=None, add=None, mask=None, relu=False, sigmoid=False,
-              stats=None, out_f32=None, out_f32_channels=0, store_bf16=True, phase_mask=0, dw=None, split_k=0,
+              stats=None, out_f32=None, out_f32_channels=0, store_bf16=True, phase_mask=0, dw=None, split_k=0, out_f32_nhwc=False,
               algo_cin=None, algo_cout=None):
     a = HdConvArgs()
     a.algo = (algo_cin, algo_cout)
@@ -77,6 +77,7 @@ def conv_args(x0, y0, w=None, k=3, stride=1, x1=None, y1=None, bias=None, add=No
     a.stats_replicas = stats.shape[0] if stats is not None else 0
     a.out_f32_nchw = out_f32.data_ptr() if out_f32 is not None else None
     a.out_f32_channels = out_f32_channels
+    a.out_f32_nhwc = int(bool(out_f32_nhwc))
     a.store_bf16 = int(store_bf16)
     a.phase_mask = phase_mask
     a.dw = dw.data_ptr() if dw is not None else None
@@ -518,19 +519,23 @@ def roi_align_ml_fwd(feats_nhwc, scales, rois, levels, output_size, sampling_rat
     return out
 
 
-def roi_align_ml_bwd(grad_out, rois, levels, shapes, scales, sampling_ratio):
+def roi_align_ml_bwd(grad_out, rois, levels, shapes, scales, sampling_ratio, channels_last=None):
     """Gradients of roi_align_ml_fwd w.r.t. the NCHW fp32 feature maps of ``shapes``: one reduction launch into zeroed
-    channels-last scratch for all levels, then one layout conversion per level."""
+    channels-last scratch for all levels, then one layout conversion per level -- none for the levels flagged
+    ``channels_last``, whose gradient is returned as the NCHW view of the scratch."""
     global LAUNCHES
     k, c, ph, pw = grad_out.shape
     assert grad_out.dtype == torch.float32 and grad_out.is_contiguous()
+    channels_last = channels_last or [False] * len(shapes)
     scratch = [torch.zeros(n, h, w, c2, dtype=torch.float32, device=grad_out.device) for (n, c2, h, w) in shapes]
-    outs = [torch.empty(tuple(sh), dtype=torch.float32, device=grad_out.device) for sh in shapes]
+    outs = [sc.permute(0, 3, 1, 2) if cl else torch.empty(tuple(sh), dtype=torch.float32, device=grad_out.device)
+            for sc, sh, cl in zip(scratch, shapes, channels_last)]
     table = _roi_level_table(scratch, scales, grads=True)
     with _Timed("roi_align_bwd"):
         check(_lib.load().hd_roi_align_ml_bwd(table, len(shapes), _ptr(grad_out), _ptr(rois), _ptr(levels), k, c, ph, pw,
                                               int(sampling_ratio), _stream()), "hd_roi_align_ml_bwd")
-        for sc, o, (n, c2, h, w) in zip(scratch, outs, shapes):
-            check(_lib.load().hd_nhwc_to_nchw_f32(_ptr(sc), _ptr(o), n, c2, h, w, _stream()), "hd_nhwc_to_nchw_f32")
+        for sc, o, (n, c2, h, w), cl in zip(scratch, outs, shapes, channels_last):
+            if not cl:
+                check(_lib.load().hd_nhwc_to_nchw_f32(_ptr(sc), _ptr(o), n, c2, h, w, _stream()), "hd_nhwc_to_nchw_f32")
     LAUNCHES += 1
     return outs

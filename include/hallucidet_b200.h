@@ -70,6 +70,8 @@ typedef struct hd_conv_args {
     /* wgrad only */
     float* dw;                /* fp32 [cout][kh*kw][cin] accumulated with atomics (caller zeroes) */
     int32_t split_k;          /* 0 = auto */
+    int32_t out_f32_nhwc;     /* fwd: 1 = the fp32 copy (out_f32_nchw) is channels-last [n][h][w][out_f32_channels] instead of NCHW
+                                 (out_f32_channels % 16 == 0, no sigmoid): what cuDNN and the RoIAlign kernels read without a transpose */
 } hd_conv_args;
 
 int hd_conv_fwd(const hd_conv_args* a, hd_stream stream);

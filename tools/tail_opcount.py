@@ -51,3 +51,25 @@ launches = [e for e in evs if e.name in ("cudaLaunchKernel", "cudaMemcpyAsync", 
 for s in secs:
     n = sum(1 for l in launches if s.time_range.start <= l.time_range.start <= s.time_range.end)
     print(f"{s.name:24s} cpu {s.cpu_time_total / 1e3:7.2f} ms  launches {n}")
+want = os.environ.get("HD_SECTION")
+if want:
+    from collections import Counter
+    sec = [s for s in secs if s.name == "S:" + want][0]
+    names = Counter()
+    for e in evs:
+        if e.device_type == torch.autograd.DeviceType.CUDA and False:
+            pass
+    kern = [e for e in evs if e.device_type == torch.autograd.DeviceType.CPU and e.name.startswith("aten::")
+            and sec.time_range.start <= e.time_range.start <= sec.time_range.end]
+    # top-level aten ops only (not nested inside another aten op of the section)
+    kern.sort(key=lambda e: e.time_range.start)
+    top, end = [], -1
+    for e in kern:
+        if e.time_range.start >= end:
+            top.append(e)
+            end = e.time_range.end
+    for e in top:
+        n = sum(1 for l in launches if e.time_range.start <= l.time_range.start <= e.time_range.end)
+        names[(e.name, n)] += 1
+    for (nm, n), c in sorted(names.items(), key=lambda kv: -kv[1] * max(kv[0][1], 1)):
+        print(f"  {nm:40s} launches/op {n}  x{c}")
