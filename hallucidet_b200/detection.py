@@ -11,6 +11,7 @@ torchvision's own objects ("stay as the reference implements them"); only ``mode
 """
 import contextlib
 import math
+import os as _os
 
 import numpy as np
 from collections import OrderedDict
@@ -75,6 +76,53 @@ class Detector:
         raise NotImplementedError(model_name)
 
 
+FUSED_HEAD_CONV_RELU = _os.environ.get("HD_FUSED_HEAD", "1") == "1"
+
+
+class _ConvBiasReLU(torch.autograd.Function):
+    """conv + bias + ReLU of a FROZEN head convolution as one cuDNN call (the bias add and the ReLU are otherwise two more
+    passes over the largest feature maps of the step); backward: ReLU mask, then the input gradient only."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, dilation, groups):
+        out = torch.cudnn_convolution_relu(x, weight, bias, stride, padding, dilation, groups)
+        ctx.save_for_backward(x, weight, out)
+        ctx.cfg = (stride, padding, dilation, groups)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, weight, out = ctx.saved_tensors
+        stride, padding, dilation, groups = ctx.cfg
+        grad = torch.ops.aten.threshold_backward(grad, out, 0)
+        gx = torch.ops.aten.convolution_backward(grad, x, weight, None, stride, padding, dilation, False, [0, 0], groups,
+                                                 [True, False, False])[0]
+        return gx, None, None, None, None, None, None
+
+
+class _FusedConvReLU(torch.nn.Sequential):
+    """Drop-in for torchvision's ``Conv2dNormActivation(conv, ReLU)`` inside the frozen detector heads (same children, same
+    state_dict keys); forward = _ConvBiasReLU when the convolution is frozen and the input is an fp32 CUDA tensor."""
+
+    def forward(self, x):
+        conv = self[0]
+        if (FUSED_HEAD_CONV_RELU and x.is_cuda and x.dtype == torch.float32 and not conv.weight.requires_grad
+                and (conv.bias is None or not conv.bias.requires_grad) and conv.padding_mode == "zeros"
+                and not isinstance(conv.padding, str)):
+            bias = conv.bias if conv.bias is not None else conv.weight.new_zeros(conv.out_channels)
+            return _ConvBiasReLU.apply(x, conv.weight, bias, list(conv.stride), list(conv.padding), list(conv.dilation), conv.groups)
+        return super().forward(x)
+
+
+def _fuse_head_conv_relu(module):
+    for name, child in list(module.named_children()):
+        if (isinstance(child, torch.nn.Sequential) and not isinstance(child, _FusedConvReLU) and len(child) == 2
+                and isinstance(child[0], torch.nn.Conv2d) and isinstance(child[1], torch.nn.ReLU)):
+            setattr(module, name, _FusedConvReLU(child[0], child[1]))
+        else:
+            _fuse_head_conv_relu(child)
+
+
 def install_b200_backbone(detector):
     """Freeze the detector and replace ``detector.backbone`` by the B200 dgrad-only module (call AFTER weights are loaded)."""
     detector.eval()
@@ -92,6 +140,10 @@ def install_b200_backbone(detector):
                 for m in head.modules():
                     if isinstance(m, torch.nn.Conv2d):
                         m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
+    for name in ("rpn", "head"):
+        head = getattr(detector, name, None)
+        if isinstance(head, torch.nn.Module):
+            _fuse_head_conv_relu(head)
     return detector
 
 

@@ -494,3 +494,29 @@ def test_side_stream_tail_equals_in_order_path():
         assert len(other) == len(dets[0]) == 4
         for x, y in zip(dets[0], other):
             assert all(torch.equal(x[k], y[k]) for k in ("boxes", "labels", "scores"))
+
+
+def test_fused_head_conv_relu_matches_unfused():
+    """The frozen head convolutions run conv + bias + ReLU as one cuDNN call (detection._FusedConvReLU): same outputs and same
+    input gradient as torchvision's Conv2dNormActivation, and the state_dict keys are unchanged."""
+    from torchvision.models.detection.rpn import RPNHead
+    from hallucidet_b200 import detection as D
+    torch.manual_seed(0)
+    ref = RPNHead(256, 3).cuda()
+    for p in ref.parameters():
+        p.requires_grad_(False)
+    fused = copy.deepcopy(ref)
+    D._fuse_head_conv_relu(fused)
+    assert isinstance(fused.conv[0], D._FusedConvReLU) and list(fused.state_dict()) == list(ref.state_dict())
+    for memory_format in (torch.contiguous_format, torch.channels_last):
+        xs = [torch.randn(2, 256, s, s, device="cuda").contiguous(memory_format=memory_format) for s in (40, 20)]
+        xa = [x.clone().requires_grad_(True) for x in xs]
+        xb = [x.clone().requires_grad_(True) for x in xs]
+        oa, da = ref(xa)
+        ob, db = fused(xb)
+        for a, b in zip(oa + da, ob + db):
+            assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+        sum((o * o).sum() for o in oa + da).backward()
+        sum((o * o).sum() for o in ob + db).backward()
+        for a, b in zip(xa, xb):
+            assert torch.allclose(a.grad, b.grad, rtol=1e-3, atol=1e-4 * float(a.grad.abs().max()))

@@ -29,5 +29,5 @@ agg = {}
 for e in ev:
     d = e.device_time if hasattr(e, "device_time") else e.cuda_time
     a = agg.setdefault(e.name[:90], [0, 0.0]); a[0] += 1; a[1] += d
-for k, (n, d) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
+for k, (n, d) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:int(os.environ.get("HD_TOP", "45"))]:
     print(f"{d / N / 1e3:8.3f} ms  n={n / N:7.1f}  {k}")
