@@ -813,12 +813,37 @@ def _anchors(model, images, features):
     return hit[1]
 
 
+FUSED_RPN_PREDICTORS = _os.environ.get("HD_FUSED_RPN_PRED", "1") == "1"
+
+
+def _rpn_head(head, features):
+    """``RPNHead.forward`` (TV rpn.py:61-68) with the two frozen 1x1 predictors (objectness, box deltas) evaluated as ONE
+    convolution over the concatenated output channels: the shared hidden map -- the largest activation of the tail -- is
+    read once instead of twice, and its gradient is written once instead of being the sum of two full-size tensors."""
+    cls, reg = head.cls_logits, head.bbox_pred
+    ok = (FUSED_RPN_PREDICTORS and features[0].is_cuda and isinstance(cls, torch.nn.Conv2d) and isinstance(reg, torch.nn.Conv2d)
+          and cls.kernel_size == reg.kernel_size == (1, 1) and cls.stride == reg.stride == (1, 1)
+          and cls.padding == reg.padding == (0, 0) and cls.groups == reg.groups == 1
+          and cls.bias is not None and reg.bias is not None
+          and not any(p.requires_grad for p in (cls.weight, cls.bias, reg.weight, reg.bias)))
+    if not ok:
+        return head(features)
+    weight, bias = torch.cat([cls.weight, reg.weight], 0), torch.cat([cls.bias, reg.bias], 0)
+    a = cls.out_channels
+    logits, bbox_reg = [], []
+    for feature in features:
+        y = F.conv2d(head.conv(feature), weight, bias)
+        logits.append(y[:, :a])
+        bbox_reg.append(y[:, a:])
+    return logits, bbox_reg
+
+
 def rpn_eval(model, images, features, targets, targets_event=None):
     """``RegionProposalNetwork.forward`` in training mode (TV rpn.py:337-388) as the reference's eval_forward uses it
     (src/utils/eval_forward_fasterrcnn.py:62-99).  ``targets_event``: CUDA event recorded once ``targets`` are final on
     the current stream; lets the anchor-target work start before the backbone forward has finished."""
     features = list(features.values())
-    objectness, pred_bbox_deltas = model.rpn.head(features)
+    objectness, pred_bbox_deltas = _rpn_head(model.rpn.head, features)
     batched = BATCHED_TAIL and features[0].is_cuda
     anchors = _anchors(model, images, features) if batched else model.rpn.anchor_generator(images, features)
     num_images = len(anchors)

@@ -520,3 +520,27 @@ def test_fused_head_conv_relu_matches_unfused():
         sum((o * o).sum() for o in ob + db).backward()
         for a, b in zip(xa, xb):
             assert torch.allclose(a.grad, b.grad, rtol=1e-3, atol=1e-4 * float(a.grad.abs().max()))
+
+
+def test_fused_rpn_predictors_match_two_convolutions():
+    """detection._rpn_head evaluates objectness and box deltas as one 1x1 convolution: same values, same input gradient."""
+    from torchvision.models.detection.rpn import RPNHead, concat_box_prediction_layers
+    from hallucidet_b200 import detection as D
+    torch.manual_seed(1)
+    head = RPNHead(256, 3).cuda()
+    for p in head.parameters():
+        p.requires_grad_(False)
+    for memory_format in (torch.contiguous_format, torch.channels_last):
+        xs = [torch.randn(2, 256, s, s + 4, device="cuda").contiguous(memory_format=memory_format) for s in (40, 20, 10)]
+        xa = [x.clone().requires_grad_(True) for x in xs]
+        xb = [x.clone().requires_grad_(True) for x in xs]
+        oa, da = head(xa)
+        ob, db = D._rpn_head(head, xb)
+        assert [t.shape for t in oa + da] == [t.shape for t in ob + db]
+        fa, ga = concat_box_prediction_layers(oa, da)
+        fb, gb = concat_box_prediction_layers(ob, db)
+        assert torch.allclose(fa, fb, rtol=1e-4, atol=1e-5) and torch.allclose(ga, gb, rtol=1e-4, atol=1e-5)
+        ((fa * fa).sum() + (ga * ga).sum()).backward()
+        ((fb * fb).sum() + (gb * gb).sum()).backward()
+        for a, b in zip(xa, xb):
+            assert torch.allclose(a.grad, b.grad, rtol=1e-3, atol=1e-4 * float(a.grad.abs().max()))
