@@ -211,7 +211,9 @@ def main():
         ir, rgb = prefetch.get()
         prefetch.put(ir_h, rgb_h)
         out = tr.training_step(rgb, targets, ir, targets)
-        host_loss.append(float(out["total"].detach()))          # device -> host read of the step's result
+        # device -> host read of the step's result: the loss, copied to pinned memory where the step computes it (before
+        # the backward pass) and waited for here, every step
+        host_loss.append(float(out["total_host"]))
 
     ops.LAUNCHES = 0
     for _ in range(max(args.warmup, 3)):

@@ -98,6 +98,24 @@ class DevicePrefetcher:
         return dev
 
 
+class HostScalar:
+    """A device scalar on its way to the host: copied to pinned memory (non-blocking) at the point of the step where it
+    exists; ``float()`` waits for THAT copy only, not for whatever the stream was given afterwards.  The train step's loss
+    is final before the backward pass starts, so logging it every step does not have to wait for backward + optimizer."""
+
+    def __init__(self, value, slot):
+        slot.copy_(value.detach().reshape(()), non_blocking=True)
+        self._slot = slot
+        self._event = torch.cuda.Event()
+        self._event.record()
+
+    def __float__(self):
+        self._event.synchronize()
+        return float(self._slot)
+
+    item = __float__
+
+
 def expand_one_channel_to_output_channels(imgs, output_channels=3):
     """src/utils/utils.py:52-53."""
     return imgs.repeat(1, output_channels, 1, 1)
@@ -214,6 +232,14 @@ class HalluciDetTrainer(nn.Module):
             out = self.forward_step(imgs_rgb, targets_rgb, imgs_ir, targets_ir, det_seed=det_seed)
         finally:
             detection.DEFER_DETECTIONS = False
+        if out["total"].is_cuda:
+            # the loss as a host number (for logging): read back from here, ahead of the backward pass
+            slots = getattr(self, "_loss_slots", None)
+            if slots is None:
+                slots = self._loss_slots = [torch.empty((), dtype=torch.float32, pin_memory=True) for _ in range(4)]
+                self._loss_turn = 0
+            self._loss_turn = (self._loss_turn + 1) % len(slots)
+            out["total_host"] = HostScalar(out["total"].float(), slots[self._loss_turn])
         out["total"].backward()
         self.allreduce_gradients()
         self.clip_gradients()

@@ -544,3 +544,15 @@ def test_fused_rpn_predictors_match_two_convolutions():
         ((fb * fb).sum() + (gb * gb).sum()).backward()
         for a, b in zip(xa, xb):
             assert torch.allclose(a.grad, b.grad, rtol=1e-3, atol=1e-4 * float(a.grad.abs().max()))
+
+
+def test_training_step_host_loss_matches_device_loss():
+    """training_step also hands the loss back as a HostScalar (pinned copy issued before the backward pass): same number."""
+    from oracle import step as ostep
+    from hallucidet_b200.train import HalluciDetTrainer, HostScalar
+    ir, rgb, targets = ostep.synthetic_batch(2, 128, 128, seed=3, device="cuda")
+    tr = HalluciDetTrainer(detector_name="fasterrcnn", size=128, seed=123)
+    for _ in range(3):
+        out = tr.training_step(rgb, targets, ir, targets)
+        assert isinstance(out["total_host"], HostScalar)
+        assert float(out["total_host"]) == float(out["total"].detach()) == out["total_host"].item()
