@@ -98,6 +98,7 @@ __device__ __forceinline__ void decode_tile(const ConvGemmParams& P, int tile, i
 // ahead across tile boundaries, the accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the
 // main loop of tile i+1.
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams P) {
+    pdl_trigger();                 // the next kernel may become resident as our CTAs drain (it waits for our results itself)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5;
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_wait();                    // everything above overlapped the previous kernel's tail; its results are needed from here on
 
     const int total_tiles = P.m_tiles * P.n_tiles * P.nphases;
 
@@ -719,7 +721,7 @@ static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStrea
     }
     const long total = static_cast<long>(P.m_tiles) * P.n_tiles * nphases;
     const int grid = static_cast<int>(total < num_sms() ? total : num_sms());
-    conv_gemm_kernel<<<grid, kThreads, smem, stream>>>(P);
+    HD_CUDA_OK(hd::launch(conv_gemm_kernel, dim3(grid), dim3(kThreads), smem, stream, P));
     HD_CUDA_OK(cudaPeekAtLastError());
     return HD_OK;
 }

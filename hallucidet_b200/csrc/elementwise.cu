@@ -37,6 +37,8 @@ struct bf8 {                                          // 8 bf16 channels = one 1
 __global__ void pack_weight_kernel(const float* __restrict__ w, const float* __restrict__ scale, int cout, int cin,
                                    int kh, int kw, __nv_bfloat16* w_fwd, int cout_pad, int k_pad,
                                    __nv_bfloat16* w_dgrad, int cin_pad, __nv_bfloat16* w_t) {
+    pdl_trigger();
+    pdl_wait();
     const int taps = kh * kw;
     const long n_fwd = static_cast<long>(cout_pad) * k_pad;
     const long n_dg = static_cast<long>(cin_pad) * taps * cout;
@@ -70,6 +72,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, const float* __r
 
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dw, float* __restrict__ g, int cout, int cin, int taps,
                                     int tap_stride, int row_stride, float scale) {
+    pdl_trigger();
+    pdl_wait();
     const long n = static_cast<long>(cout) * cin * taps;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -94,6 +98,8 @@ __device__ __forceinline__ int find_desc(const int* first_block, int stride_ints
 }
 
 __global__ void pack_weights_multi_kernel(const hd_pack_desc* __restrict__ descs, int n) {
+    pdl_trigger();
+    pdl_wait();
     const int li = find_desc(&descs[0].first_block, sizeof(hd_pack_desc) / sizeof(int), n, blockIdx.x);
     const hd_pack_desc d = descs[li];
     const int taps = d.kh * d.kw;
@@ -134,6 +140,8 @@ __global__ void pack_weights_multi_kernel(const hd_pack_desc* __restrict__ descs
 }
 
 __global__ void unpack_wgrads_multi_kernel(const hd_unpack_desc* __restrict__ descs, int n) {
+    pdl_trigger();
+    pdl_wait();
     const int li = find_desc(&descs[0].first_block, sizeof(hd_unpack_desc) / sizeof(int), n, blockIdx.x);
     const hd_unpack_desc d = descs[li];
     const long total = static_cast<long>(d.cout) * d.cin * d.taps;
@@ -159,6 +167,8 @@ constexpr int kI2cTH = 8, kI2cTW = 32, kI2cPH = 2 * kI2cTH + 5, kI2cPW = 2 * kI2
 
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ patches, int n,
                                                           int h, int w, int k_pad) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ __nv_bfloat16 sp[kI2cPH * kI2cPitch];
     const int ho = h / 2, wo = w / 2, groups = k_pad / 8;
     const int tiles_w = (wo + kI2cTW - 1) / kI2cTW, tiles_h = (ho + kI2cTH - 1) / kI2cTH;
@@ -193,6 +203,8 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
 }
 
 __global__ void stem_col2im_kernel(const __nv_bfloat16* __restrict__ dp, float* __restrict__ dx, int n, int h, int w, int k_pad) {
+    pdl_trigger();
+    pdl_wait();
     const int ho = h / 2, wo = w / 2;
     const long total = static_cast<long>(n) * h * w;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
@@ -222,6 +234,8 @@ __global__ void stem_col2im_kernel(const __nv_bfloat16* __restrict__ dp, float* 
 __global__ void bn_finalize_kernel(const float* __restrict__ stats, int rows, int C, double count, const float* gamma,
                                    const float* beta, float eps, float momentum, float* rm, float* rv, float* mean_out,
                                    float* invstd_out, float* scale_out, float* shift_out) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ double ss[128], sq[128];
     const int c = blockIdx.x, t = threadIdx.x;
     double s = 0.0, q = 0.0;
@@ -261,6 +275,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_apply_kernel(const __nv_bfloat1
                                 const float* __restrict__ shift, const __nv_bfloat16* __restrict__ res,
                                 const float* __restrict__ rscale, const float* __restrict__ rshift, int relu,
                                 __nv_bfloat16* __restrict__ y, long n_pix, int C) {
+    pdl_trigger();
+    pdl_wait();
     const int G = C / 8;
     const long total = n_pix * G;
     const int c0 = static_cast<int>(threadIdx.x % G) * 8;
@@ -315,6 +331,8 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const
                                      const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
                                      const float* __restrict__ invstd, float* __restrict__ sums, long n_pix, int C,
                                      long pix_per_block) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float sacc[];                    // [2][C]
     const int G = C / 8;
     const int L = blockDim.x / G;                      // pixel lanes
@@ -389,6 +407,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(const __nv_bfl
                                     const float* __restrict__ invstd, const float* __restrict__ gamma,
                                     const float* __restrict__ sums, float inv_count, __nv_bfloat16* __restrict__ dz,
                                     __nv_bfloat16* __restrict__ gout, float* dgamma, float* dbeta, long n_pix, int C) {
+    pdl_trigger();
+    pdl_wait();
     const int G = C / 8;
     const long total = n_pix * G;
     if (blockIdx.x == 0) {
@@ -447,6 +467,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(const __nv_bfl
 // -------------------------------------------------------------------------------------------------
 __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                    unsigned char* __restrict__ idx, int mask_nonpositive, int n, int h, int w, int C) {
+    pdl_trigger();
+    pdl_wait();
     const int ho = h / 2, wo = w / 2, G = C / 8;
     const long total = static_cast<long>(n) * ho * wo * G;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
@@ -492,6 +514,8 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
 __global__ void maxpool_bwd_idx_kernel(const unsigned char* __restrict__ idx, const __nv_bfloat16* __restrict__ dy,
                                        const __nv_bfloat16* __restrict__ add, __nv_bfloat16* __restrict__ dx, int n, int h,
                                        int w, int C) {
+    pdl_trigger();
+    pdl_wait();
     const int ho = h / 2, wo = w / 2, G = C / 8;
     const long total = static_cast<long>(n) * h * w * G;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
@@ -540,6 +564,8 @@ __global__ void maxpool_bwd_idx_kernel(const unsigned char* __restrict__ idx, co
 __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
                                    const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ add,
                                    __nv_bfloat16* __restrict__ dx, int n, int h, int w, int C, int relu_mask) {
+    pdl_trigger();
+    pdl_wait();
     const int ho = h / 2, wo = w / 2, G = C / 8;
     const long total = static_cast<long>(n) * h * w * G;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
@@ -611,7 +637,9 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __
 // nearest up-sampling x2 and FPN top-down add
 // -------------------------------------------------------------------------------------------------
 __global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int h, int w,
-                                      int C) {            // h,w = OUTPUT size
+                                      int C) {
+    pdl_trigger();
+    pdl_wait();            // h,w = OUTPUT size
     const int G = C / 8;
     const long total = static_cast<long>(n) * h * w * G;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
@@ -626,7 +654,9 @@ __global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_
 }
 
 __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int n, int h, int w,
-                                      int C) {            // h,w = INPUT (small) size
+                                      int C) {
+    pdl_trigger();
+    pdl_wait();            // h,w = INPUT (small) size
     const int G = C / 8;
     const long total = static_cast<long>(n) * h * w * G;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
@@ -659,6 +689,8 @@ __device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
 
 __global__ void add_nearest_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int hi, int wi,
                                        int ho, int wo, int C, float sh, float sw) {
+    pdl_trigger();
+    pdl_wait();
     const int G = C / 8;
     const long total = static_cast<long>(n) * ho * wo * G;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
@@ -682,6 +714,8 @@ __global__ void add_nearest_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv
 
 __global__ void add_nearest_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int n, int hi,
                                        int wi, int ho, int wo, int C, float sh, float sw, int accumulate) {
+    pdl_trigger();
+    pdl_wait();
     const int G = C / 8;
     const long total = static_cast<long>(n) * hi * wi * G;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
@@ -728,6 +762,8 @@ __global__ void add_nearest_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __n
 // -------------------------------------------------------------------------------------------------
 __global__ void pad_hw_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int h, int w, int hp,
                               int wp, int C) {
+    pdl_trigger();
+    pdl_wait();
     const int G = C / 8;
     const long total = static_cast<long>(n) * hp * wp * G;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
@@ -746,6 +782,8 @@ __global__ void pad_hw_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16
 __global__ void crop_add_mask_kernel(const __nv_bfloat16* __restrict__ dxp, const __nv_bfloat16* __restrict__ add,
                                      const __nv_bfloat16* __restrict__ mask, __nv_bfloat16* __restrict__ dx, int n, int h, int w,
                                      int hp, int wp, int C) {
+    pdl_trigger();
+    pdl_wait();
     const int G = C / 8;
     const long total = static_cast<long>(n) * h * w * G;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
@@ -783,6 +821,8 @@ __global__ void crop_add_mask_kernel(const __nv_bfloat16* __restrict__ dxp, cons
 // -------------------------------------------------------------------------------------------------
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int h, int w, int Cs,
                                     int Cd, int accumulate) {
+    pdl_trigger();
+    pdl_wait();
     // thread = (pixel, 8-channel group); consecutive threads -> consecutive pixels (coalesced fp32 reads)
     const int G = Cd / 8;
     const long plane = static_cast<long>(h) * w;
@@ -813,6 +853,8 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* 
 
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int n, int h, int w, int Cs,
                                     int Cd) {
+    pdl_trigger();
+    pdl_wait();
     const int G = (Cd + 7) / 8;
     const long plane = static_cast<long>(h) * w;
     const long total = static_cast<long>(n) * plane * G;
@@ -835,6 +877,8 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* 
 
 __global__ void sigmoid_bwd_pack_kernel(const float* __restrict__ dhal, const float* __restrict__ hal,
                                         __nv_bfloat16* __restrict__ dl, int n, int h, int w, int ch, int Cd, float* dbias) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float sb[4];
     if (threadIdx.x < 4) sb[threadIdx.x] = 0.f;
     __syncthreads();
@@ -877,6 +921,8 @@ __global__ void sigmoid_bwd_pack_kernel(const float* __restrict__ dhal, const fl
 // -------------------------------------------------------------------------------------------------
 __global__ void resize_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int c, int hi, int wi, int ho,
                                   int wo, float sh, float sw, const float* mean, const float* stdv) {
+    pdl_trigger();
+    pdl_wait();
     const long total = static_cast<long>(n) * c * ho * wo;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -892,6 +938,8 @@ __global__ void resize_fwd_kernel(const float* __restrict__ x, float* __restrict
 
 __global__ void resize_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int n, int c, int hi, int wi, int ho,
                                   int wo, float sh, float sw, const float* stdv, int accumulate) {
+    pdl_trigger();
+    pdl_wait();
     const long total = static_cast<long>(n) * c * hi * wi;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -924,6 +972,8 @@ __global__ void resize_bwd_kernel(const float* __restrict__ dy, float* __restric
 __global__ void regulariser_kernel(int kind, const float* __restrict__ hal, const float* __restrict__ rgb,
                                    const float* __restrict__ ir, float w_rgb, float w_ir, int n, long plane, float* loss,
                                    float* dhal, float grad_scale, int accumulate) {
+    pdl_trigger();
+    pdl_wait();
     const long total = static_cast<long>(n) * 3 * plane;
     const float inv_n = 1.f / static_cast<float>(total);
     float l_rgb = 0.f, l_ir = 0.f;
@@ -971,9 +1021,8 @@ extern "C" int hd_pack_conv_weight(const float* w, const float* scale, int cout,
     HD_CHECK_ARG(w != nullptr && cout > 0 && cin > 0 && kh > 0 && kw > 0);
     HD_CHECK_ARG(cout_pad >= cout && k_pad >= kh * kw * cin && cin_pad >= cin);
     const long work = static_cast<long>(cout_pad) * k_pad + (w_dgrad ? static_cast<long>(cin_pad) * kh * kw * cout : 0);
-    pack_weight_kernel<<<ew_blocks(work), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
-        w, scale, cout, cin, kh, kw, static_cast<__nv_bfloat16*>(w_fwd), cout_pad, k_pad,
-        static_cast<__nv_bfloat16*>(w_dgrad), cin_pad, static_cast<__nv_bfloat16*>(w_t));
+    HD_CUDA_OK(hd::launch(pack_weight_kernel, dim3(ew_blocks(work)), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), w, scale, cout, cin, kh, kw, static_cast<__nv_bfloat16*>(w_fwd), cout_pad, k_pad,
+        static_cast<__nv_bfloat16*>(w_dgrad), cin_pad, static_cast<__nv_bfloat16*>(w_t)));
     HD_LAUNCH_OK();
     return HD_OK;
 }
@@ -981,8 +1030,7 @@ extern "C" int hd_pack_conv_weight(const float* w, const float* scale, int cout,
 extern "C" int hd_unpack_wgrad(const float* dw, float* g, int cout, int cin, int kh, int kw, int tap_stride, int row_stride,
                                float scale, hd_stream st) {
     HD_CHECK_ARG(dw && g && cout > 0 && cin > 0);
-    unpack_wgrad_kernel<<<ew_blocks(static_cast<long>(cout) * cin * kh * kw), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
-        dw, g, cout, cin, kh * kw, tap_stride, row_stride, scale);
+    HD_CUDA_OK(hd::launch(unpack_wgrad_kernel, dim3(ew_blocks(static_cast<long>(cout) * cin * kh * kw)), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), dw, g, cout, cin, kh * kw, tap_stride, row_stride, scale));
     HD_LAUNCH_OK();
     return HD_OK;
 }
@@ -994,14 +1042,14 @@ extern "C" int hd_multi_blocks(int64_t elements) {
 
 extern "C" int hd_pack_conv_weights(const hd_pack_desc* descs_dev, int n_layers, int total_blocks, hd_stream st) {
     HD_CHECK_ARG(descs_dev && n_layers > 0 && total_blocks > 0);
-    pack_weights_multi_kernel<<<total_blocks, kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(descs_dev, n_layers);
+    HD_CUDA_OK(hd::launch(pack_weights_multi_kernel, dim3(total_blocks), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), descs_dev, n_layers));
     HD_LAUNCH_OK();
     return HD_OK;
 }
 
 extern "C" int hd_unpack_wgrads(const hd_unpack_desc* descs_dev, int n_layers, int total_blocks, hd_stream st) {
     HD_CHECK_ARG(descs_dev && n_layers > 0 && total_blocks > 0);
-    unpack_wgrads_multi_kernel<<<total_blocks, kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(descs_dev, n_layers);
+    HD_CUDA_OK(hd::launch(unpack_wgrads_multi_kernel, dim3(total_blocks), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), descs_dev, n_layers));
     HD_LAUNCH_OK();
     return HD_OK;
 }
@@ -1010,15 +1058,14 @@ extern "C" int hd_stem_im2col(const float* x, void* patches, int n, int h, int w
     HD_CHECK_ARG(x && patches && h % 2 == 0 && w % 2 == 0 && k_pad >= 152 && k_pad % 8 == 0);
     const int ho = h / 2, wo = w / 2;
     const int tiles = n * ((ho + kI2cTH - 1) / kI2cTH) * ((wo + kI2cTW - 1) / kI2cTW);
-    stem_im2col_kernel<<<tiles, 256, 0, static_cast<cudaStream_t>(st)>>>(x, static_cast<__nv_bfloat16*>(patches), n, h, w, k_pad);
+    HD_CUDA_OK(hd::launch(stem_im2col_kernel, dim3(tiles), dim3(256), 0, static_cast<cudaStream_t>(st), x, static_cast<__nv_bfloat16*>(patches), n, h, w, k_pad));
     HD_LAUNCH_OK();
     return HD_OK;
 }
 
 extern "C" int hd_stem_col2im(const void* dp, float* dx, int n, int h, int w, int k_pad, hd_stream st) {
     HD_CHECK_ARG(dp && dx && h % 2 == 0 && w % 2 == 0);
-    stem_col2im_kernel<<<ew_blocks(static_cast<long>(n) * h * w), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
-        static_cast<const __nv_bfloat16*>(dp), dx, n, h, w, k_pad);
+    HD_CUDA_OK(hd::launch(stem_col2im_kernel, dim3(ew_blocks(static_cast<long>(n) * h * w)), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), static_cast<const __nv_bfloat16*>(dp), dx, n, h, w, k_pad));
     HD_LAUNCH_OK();
     return HD_OK;
 }
@@ -1027,9 +1074,9 @@ extern "C" int hd_bn_finalize(const float* stats, int reps, int C, double count,
                               float eps, float momentum, float* rm, float* rv, float* mean_out, float* invstd_out,
                               float* scale_out, float* shift_out, hd_stream st) {
     HD_CHECK_ARG(stats && gamma && beta && scale_out && shift_out && C > 0 && reps > 0 && count > 0);
-    bn_finalize_kernel<<<C, 128, 0, static_cast<cudaStream_t>(st)>>>(stats, reps, C, count, gamma, beta, eps,
+    HD_CUDA_OK(hd::launch(bn_finalize_kernel, dim3(C), dim3(128), 0, static_cast<cudaStream_t>(st), stats, reps, C, count, gamma, beta, eps,
                                                                                  momentum, rm, rv, mean_out, invstd_out,
-                                                                                 scale_out, shift_out);
+                                                                                 scale_out, shift_out));
     HD_LAUNCH_OK();
     return HD_OK;
 }
@@ -1037,9 +1084,8 @@ extern "C" int hd_bn_finalize(const float* stats, int reps, int C, double count,
 extern "C" int hd_bn_apply(const void* z, const float* scale, const float* shift, const void* res, const float* rscale,
                            const float* rshift, int relu, void* y, int64_t n_pix, int C, hd_stream st) {
     HD_CHECK_ARG(z && scale && shift && y && C % 8 == 0 && n_pix > 0 && kEwThreads % (C / 8) == 0);
-    bn_apply_kernel<<<ew_blocks(n_pix * (C / 8)), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
-        static_cast<const __nv_bfloat16*>(z), scale, shift, static_cast<const __nv_bfloat16*>(res), rscale, rshift, relu,
-        static_cast<__nv_bfloat16*>(y), n_pix, C);
+    HD_CUDA_OK(hd::launch(bn_apply_kernel, dim3(ew_blocks(n_pix * (C / 8))), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), static_cast<const __nv_bfloat16*>(z), scale, shift, static_cast<const __nv_bfloat16*>(res), rscale, rshift, relu,
+        static_cast<__nv_bfloat16*>(y), n_pix, C));
     HD_LAUNCH_OK();
     return HD_OK;
 }
@@ -1056,9 +1102,8 @@ extern "C" int hd_bn_bwd_reduce(const void* dy, const void* yrelu, const float* 
     long ppb = (n_pix + blocks - 1) / blocks;
     if (ppb < L) ppb = L;
     blocks = (n_pix + ppb - 1) / ppb;
-    bn_bwd_reduce_kernel<<<static_cast<int>(blocks), threads, 2 * C * sizeof(float), static_cast<cudaStream_t>(st)>>>(
-        static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(yrelu), rscale, rshift,
-        static_cast<const __nv_bfloat16*>(z), mean, invstd, sums, n_pix, C, ppb);
+    HD_CUDA_OK(hd::launch(bn_bwd_reduce_kernel, dim3(static_cast<int>(blocks)), dim3(threads), 2 * C * sizeof(float), static_cast<cudaStream_t>(st), static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(yrelu), rscale, rshift,
+        static_cast<const __nv_bfloat16*>(z), mean, invstd, sums, n_pix, C, ppb));
     HD_LAUNCH_OK();
     return HD_OK;
 }
@@ -1067,10 +1112,9 @@ extern "C" int hd_bn_bwd_apply(const void* dy, const void* yrelu, const float* r
                                const float* mean, const float* invstd, const float* gamma, const float* sums, double count,
                                void* dz, void* gout, float* dgamma, float* dbeta, int64_t n_pix, int C, hd_stream st) {
     HD_CHECK_ARG(dy && z && mean && invstd && gamma && sums && dz && C % 8 == 0 && n_pix > 0 && count > 0 && kEwThreads % (C / 8) == 0);
-    bn_bwd_apply_kernel<<<ew_blocks(n_pix * (C / 8)), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
-        static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(yrelu), rscale, rshift,
+    HD_CUDA_OK(hd::launch(bn_bwd_apply_kernel, dim3(ew_blocks(n_pix * (C / 8))), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(yrelu), rscale, rshift,
         static_cast<const __nv_bfloat16*>(z), mean, invstd, gamma, sums, static_cast<float>(1.0 / count),
-        static_cast<__nv_bfloat16*>(dz), static_cast<__nv_bfloat16*>(gout), dgamma, dbeta, n_pix, C);
+        static_cast<__nv_bfloat16*>(dz), static_cast<__nv_bfloat16*>(gout), dgamma, dbeta, n_pix, C));
     HD_LAUNCH_OK();
     return HD_OK;
 }
@@ -1079,10 +1123,9 @@ extern "C" int hd_maxpool_fwd(const hd_act* x, const hd_act* y, void* idx, int m
     HD_CHECK_ARG(x && y && x->ptr && y->ptr && x->c % 8 == 0 && x->c == y->c && x->h % 2 == 0 && x->w % 2 == 0);
     HD_CHECK_ARG(y->h == x->h / 2 && y->w == x->w / 2 && y->n == x->n);
     HD_CHECK_ARG(idx == nullptr || (reinterpret_cast<uintptr_t>(idx) & 7) == 0);
-    maxpool_fwd_kernel<<<ew_blocks(static_cast<long>(y->n) * y->h * y->w * (y->c / 8)), kEwThreads, 0,
-                         static_cast<cudaStream_t>(st)>>>(static_cast<const __nv_bfloat16*>(x->ptr),
+    HD_CUDA_OK(hd::launch(maxpool_fwd_kernel, dim3(ew_blocks(static_cast<long>(y->n) * y->h * y->w * (y->c / 8))), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), static_cast<const __nv_bfloat16*>(x->ptr),
                                                           static_cast<__nv_bfloat16*>(y->ptr), static_cast<unsigned char*>(idx),
-                                                          mask_nonpositive, x->n, x->h, x->w, x->c);
+                                                          mask_nonpositive, x->n, x->h, x->w, x->c));
     HD_LAUNCH_OK();
     return HD_OK;
 }
@@ -1094,37 +1137,31 @@ extern "C" int hd_maxpool_bwd(const hd_act* x, const hd_act* y, const void* dy, 
     if (idx != nullptr) {
         // arg-max positions stored by hd_maxpool_fwd (with mask_nonpositive when relu_mask semantics are wanted): x / y are
         // not read at all
-        maxpool_bwd_idx_kernel<<<ew_blocks(static_cast<long>(x->n) * x->h * x->w * (x->c / 8)), kEwThreads, 0,
-                                 static_cast<cudaStream_t>(st)>>>(
-            static_cast<const unsigned char*>(idx), static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(add),
-            static_cast<__nv_bfloat16*>(dx), x->n, x->h, x->w, x->c);
+        HD_CUDA_OK(hd::launch(maxpool_bwd_idx_kernel, dim3(ew_blocks(static_cast<long>(x->n) * x->h * x->w * (x->c / 8))), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), static_cast<const unsigned char*>(idx), static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(add),
+            static_cast<__nv_bfloat16*>(dx), x->n, x->h, x->w, x->c));
         HD_LAUNCH_OK();
         return HD_OK;
     }
     HD_CHECK_ARG(x->ptr && y->ptr);
-    maxpool_bwd_kernel<<<ew_blocks(static_cast<long>(x->n) * x->h * x->w * (x->c / 8)), kEwThreads, 0,
-                         static_cast<cudaStream_t>(st)>>>(
-        static_cast<const __nv_bfloat16*>(x->ptr), static_cast<const __nv_bfloat16*>(y->ptr),
+    HD_CUDA_OK(hd::launch(maxpool_bwd_kernel, dim3(ew_blocks(static_cast<long>(x->n) * x->h * x->w * (x->c / 8))), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), static_cast<const __nv_bfloat16*>(x->ptr), static_cast<const __nv_bfloat16*>(y->ptr),
         static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(add), static_cast<__nv_bfloat16*>(dx),
-        x->n, x->h, x->w, x->c, relu_mask);
+        x->n, x->h, x->w, x->c, relu_mask));
     HD_LAUNCH_OK();
     return HD_OK;
 }
 
 extern "C" int hd_upsample2x_fwd(const hd_act* x, const hd_act* y, hd_stream st) {
     HD_CHECK_ARG(x && y && x->ptr && y->ptr && x->c == y->c && x->c % 8 == 0 && y->h == 2 * x->h && y->w == 2 * x->w && x->n == y->n);
-    upsample2x_fwd_kernel<<<ew_blocks(static_cast<long>(y->n) * y->h * y->w * (y->c / 8)), kEwThreads, 0,
-                            static_cast<cudaStream_t>(st)>>>(static_cast<const __nv_bfloat16*>(x->ptr),
-                                                             static_cast<__nv_bfloat16*>(y->ptr), y->n, y->h, y->w, y->c);
+    HD_CUDA_OK(hd::launch(upsample2x_fwd_kernel, dim3(ew_blocks(static_cast<long>(y->n) * y->h * y->w * (y->c / 8))), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), static_cast<const __nv_bfloat16*>(x->ptr),
+                                                             static_cast<__nv_bfloat16*>(y->ptr), y->n, y->h, y->w, y->c));
     HD_LAUNCH_OK();
     return HD_OK;
 }
 
 extern "C" int hd_upsample2x_bwd(const hd_act* dy, const hd_act* dx, hd_stream st) {
     HD_CHECK_ARG(dy && dx && dy->ptr && dx->ptr && dx->c == dy->c && dx->c % 8 == 0 && dy->h == 2 * dx->h && dy->w == 2 * dx->w && dx->n == dy->n);
-    upsample2x_bwd_kernel<<<ew_blocks(static_cast<long>(dx->n) * dx->h * dx->w * (dx->c / 8)), kEwThreads, 0,
-                            static_cast<cudaStream_t>(st)>>>(static_cast<const __nv_bfloat16*>(dy->ptr),
-                                                             static_cast<__nv_bfloat16*>(dx->ptr), dx->n, dx->h, dx->w, dx->c);
+    HD_CUDA_OK(hd::launch(upsample2x_bwd_kernel, dim3(ew_blocks(static_cast<long>(dx->n) * dx->h * dx->w * (dx->c / 8))), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), static_cast<const __nv_bfloat16*>(dy->ptr),
+                                                             static_cast<__nv_bfloat16*>(dx->ptr), dx->n, dx->h, dx->w, dx->c));
     HD_LAUNCH_OK();
     return HD_OK;
 }
@@ -1132,10 +1169,9 @@ extern "C" int hd_upsample2x_bwd(const hd_act* dy, const hd_act* dx, hd_stream s
 extern "C" int hd_add_nearest_fwd(const hd_act* x, const hd_act* y, hd_stream st) {
     HD_CHECK_ARG(x && y && x->ptr && y->ptr && x->c == y->c && x->c % 8 == 0 && x->n == y->n);
     const float sh = static_cast<float>(x->h) / static_cast<float>(y->h), sw = static_cast<float>(x->w) / static_cast<float>(y->w);
-    add_nearest_fwd_kernel<<<ew_blocks(static_cast<long>(y->n) * y->h * y->w * (y->c / 8)), kEwThreads, 0,
-                             static_cast<cudaStream_t>(st)>>>(static_cast<const __nv_bfloat16*>(x->ptr),
+    HD_CUDA_OK(hd::launch(add_nearest_fwd_kernel, dim3(ew_blocks(static_cast<long>(y->n) * y->h * y->w * (y->c / 8))), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), static_cast<const __nv_bfloat16*>(x->ptr),
                                                               static_cast<__nv_bfloat16*>(y->ptr), y->n, x->h, x->w, y->h,
-                                                              y->w, y->c, sh, sw);
+                                                              y->w, y->c, sh, sw));
     HD_LAUNCH_OK();
     return HD_OK;
 }
@@ -1143,51 +1179,45 @@ extern "C" int hd_add_nearest_fwd(const hd_act* x, const hd_act* y, hd_stream st
 extern "C" int hd_add_nearest_bwd(const hd_act* dy, const hd_act* dx, int accumulate, hd_stream st) {
     HD_CHECK_ARG(dy && dx && dy->ptr && dx->ptr && dx->c == dy->c && dx->c % 8 == 0 && dx->n == dy->n);
     const float sh = static_cast<float>(dx->h) / static_cast<float>(dy->h), sw = static_cast<float>(dx->w) / static_cast<float>(dy->w);
-    add_nearest_bwd_kernel<<<ew_blocks(static_cast<long>(dx->n) * dx->h * dx->w * (dx->c / 8)), kEwThreads, 0,
-                             static_cast<cudaStream_t>(st)>>>(static_cast<const __nv_bfloat16*>(dy->ptr),
+    HD_CUDA_OK(hd::launch(add_nearest_bwd_kernel, dim3(ew_blocks(static_cast<long>(dx->n) * dx->h * dx->w * (dx->c / 8))), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), static_cast<const __nv_bfloat16*>(dy->ptr),
                                                               static_cast<__nv_bfloat16*>(dx->ptr), dx->n, dx->h, dx->w,
-                                                              dy->h, dy->w, dx->c, sh, sw, accumulate);
+                                                              dy->h, dy->w, dx->c, sh, sw, accumulate));
     HD_LAUNCH_OK();
     return HD_OK;
 }
 
 extern "C" int hd_pad_hw(const hd_act* x, const hd_act* y, hd_stream st) {
     HD_CHECK_ARG(x && y && x->ptr && y->ptr && x->c == y->c && x->c % 8 == 0 && x->n == y->n && y->h >= x->h && y->w >= x->w);
-    pad_hw_kernel<<<ew_blocks(static_cast<long>(y->n) * y->h * y->w * (y->c / 8)), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
-        static_cast<const __nv_bfloat16*>(x->ptr), static_cast<__nv_bfloat16*>(y->ptr), x->n, x->h, x->w, y->h, y->w, x->c);
+    HD_CUDA_OK(hd::launch(pad_hw_kernel, dim3(ew_blocks(static_cast<long>(y->n) * y->h * y->w * (y->c / 8))), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), static_cast<const __nv_bfloat16*>(x->ptr), static_cast<__nv_bfloat16*>(y->ptr), x->n, x->h, x->w, y->h, y->w, x->c));
     HD_LAUNCH_OK();
     return HD_OK;
 }
 
 extern "C" int hd_crop_add_mask(const hd_act* dxp, const void* add, const void* mask, const hd_act* dx, hd_stream st) {
     HD_CHECK_ARG(dxp && dx && dxp->ptr && dx->ptr && dx->c == dxp->c && dx->c % 8 == 0 && dx->n == dxp->n && dxp->h >= dx->h && dxp->w >= dx->w);
-    crop_add_mask_kernel<<<ew_blocks(static_cast<long>(dx->n) * dx->h * dx->w * (dx->c / 8)), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
-        static_cast<const __nv_bfloat16*>(dxp->ptr), static_cast<const __nv_bfloat16*>(add), static_cast<const __nv_bfloat16*>(mask),
-        static_cast<__nv_bfloat16*>(dx->ptr), dx->n, dx->h, dx->w, dxp->h, dxp->w, dx->c);
+    HD_CUDA_OK(hd::launch(crop_add_mask_kernel, dim3(ew_blocks(static_cast<long>(dx->n) * dx->h * dx->w * (dx->c / 8))), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), static_cast<const __nv_bfloat16*>(dxp->ptr), static_cast<const __nv_bfloat16*>(add), static_cast<const __nv_bfloat16*>(mask),
+        static_cast<__nv_bfloat16*>(dx->ptr), dx->n, dx->h, dx->w, dxp->h, dxp->w, dx->c));
     HD_LAUNCH_OK();
     return HD_OK;
 }
 
 extern "C" int hd_nchw_f32_to_nhwc_bf16(const float* x, const hd_act* y, int channels, int accumulate, hd_stream st) {
     HD_CHECK_ARG(x && y && y->ptr && y->c % 8 == 0 && channels <= y->c && channels > 0);
-    nchw_to_nhwc_kernel<<<ew_blocks(static_cast<long>(y->n) * y->h * y->w * (y->c / 8)), kEwThreads, 0,
-                          static_cast<cudaStream_t>(st)>>>(x, static_cast<__nv_bfloat16*>(y->ptr), y->n, y->h, y->w, channels, y->c, accumulate);
+    HD_CUDA_OK(hd::launch(nchw_to_nhwc_kernel, dim3(ew_blocks(static_cast<long>(y->n) * y->h * y->w * (y->c / 8))), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), x, static_cast<__nv_bfloat16*>(y->ptr), y->n, y->h, y->w, channels, y->c, accumulate));
     HD_LAUNCH_OK();
     return HD_OK;
 }
 
 extern "C" int hd_nhwc_bf16_to_nchw_f32(const hd_act* x, float* y, int channels, hd_stream st) {
     HD_CHECK_ARG(x && y && x->ptr && x->c % 8 == 0 && channels <= x->c && channels > 0);
-    nhwc_to_nchw_kernel<<<ew_blocks(static_cast<long>(x->n) * x->h * x->w * ((channels + 7) / 8)), kEwThreads, 0,
-                          static_cast<cudaStream_t>(st)>>>(static_cast<const __nv_bfloat16*>(x->ptr), y, x->n, x->h, x->w, x->c, channels);
+    HD_CUDA_OK(hd::launch(nhwc_to_nchw_kernel, dim3(ew_blocks(static_cast<long>(x->n) * x->h * x->w * ((channels + 7) / 8))), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), static_cast<const __nv_bfloat16*>(x->ptr), y, x->n, x->h, x->w, x->c, channels));
     HD_LAUNCH_OK();
     return HD_OK;
 }
 
 extern "C" int hd_sigmoid_bwd_pack(const float* dhal, const float* hal, const hd_act* dl, int channels, float* dbias, hd_stream st) {
     HD_CHECK_ARG(dhal && hal && dl && dl->ptr && dl->c == 16 && channels >= 1 && channels <= 4);
-    sigmoid_bwd_pack_kernel<<<ew_blocks(static_cast<long>(dl->n) * dl->h * dl->w), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
-        dhal, hal, static_cast<__nv_bfloat16*>(dl->ptr), dl->n, dl->h, dl->w, channels, dl->c, dbias);
+    HD_CUDA_OK(hd::launch(sigmoid_bwd_pack_kernel, dim3(ew_blocks(static_cast<long>(dl->n) * dl->h * dl->w)), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), dhal, hal, static_cast<__nv_bfloat16*>(dl->ptr), dl->n, dl->h, dl->w, channels, dl->c, dbias));
     HD_LAUNCH_OK();
     return HD_OK;
 }
@@ -1196,8 +1226,7 @@ extern "C" int hd_resize_nearest_fwd(const float* x, float* y, int n, int c, int
                                      const float* stdv, hd_stream st) {
     HD_CHECK_ARG(x && y && n > 0 && c > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0 && ((mean == nullptr) == (stdv == nullptr)));
     const float sh = static_cast<float>(hi) / static_cast<float>(ho), sw = static_cast<float>(wi) / static_cast<float>(wo);
-    resize_fwd_kernel<<<ew_blocks(static_cast<long>(n) * c * ho * wo), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
-        x, y, n, c, hi, wi, ho, wo, sh, sw, mean, stdv);
+    HD_CUDA_OK(hd::launch(resize_fwd_kernel, dim3(ew_blocks(static_cast<long>(n) * c * ho * wo)), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), x, y, n, c, hi, wi, ho, wo, sh, sw, mean, stdv));
     HD_LAUNCH_OK();
     return HD_OK;
 }
@@ -1206,8 +1235,7 @@ extern "C" int hd_resize_nearest_bwd(const float* dy, float* dx, int n, int c, i
                                      int accumulate, hd_stream st) {
     HD_CHECK_ARG(dy && dx && n > 0 && c > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0);
     const float sh = static_cast<float>(hi) / static_cast<float>(ho), sw = static_cast<float>(wi) / static_cast<float>(wo);
-    resize_bwd_kernel<<<ew_blocks(static_cast<long>(n) * c * hi * wi), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
-        dy, dx, n, c, hi, wi, ho, wo, sh, sw, stdv, accumulate);
+    HD_CUDA_OK(hd::launch(resize_bwd_kernel, dim3(ew_blocks(static_cast<long>(n) * c * hi * wi)), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), dy, dx, n, c, hi, wi, ho, wo, sh, sw, stdv, accumulate));
     HD_LAUNCH_OK();
     return HD_OK;
 }
@@ -1219,8 +1247,7 @@ extern "C" int hd_regulariser(int kind, const float* hal, const float* rgb, cons
     long blocks = (static_cast<long>(n) * 3 * plane + kEwThreads * 8 - 1) / (kEwThreads * 8);
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    regulariser_kernel<<<static_cast<int>(blocks), kEwThreads, 0, static_cast<cudaStream_t>(st)>>>(
-        kind, hal, rgb, ir, w_rgb, w_ir, n, plane, loss, dhal, grad_scale, accumulate);
+    HD_CUDA_OK(hd::launch(regulariser_kernel, dim3(static_cast<int>(blocks)), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), kind, hal, rgb, ir, w_rgb, w_ir, n, plane, loss, dhal, grad_scale, accumulate));
     HD_LAUNCH_OK();
     return HD_OK;
 }

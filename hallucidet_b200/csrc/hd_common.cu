@@ -2,11 +2,21 @@
 #include "hd_common.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace hd {
 
 static thread_local char g_err[512] = "";
+
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("HD_PDL");
+        on = (e == nullptr || e[0] != '0') ? 1 : 0;
+    }
+    return on == 1;
+}
 
 void set_last_error(const char* file, int line, const char* msg) {
     const char* base = strrchr(file, '/');

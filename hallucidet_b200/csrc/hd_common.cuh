@@ -67,6 +67,32 @@ int narrow_wgrad_launch(const hd_conv_args* a, cudaStream_t stream);
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t fdiv(uint32_t x, const FastDiv& f) { return (__umulhi(x, f.mul) + x) >> f.shr; }
 
+// Programmatic dependent launch (PDL): every kernel of this library lets its successor start launching right away
+// (pdl_trigger at the top) and waits for its predecessor's results before touching global memory (pdl_wait: returns once
+// the preceding grid has completed and flushed).  With the launch attribute set (hd::launch), the successor's CTAs become
+// resident in the predecessor's tail and run their prologue (barrier init, TMEM allocation, descriptor prefetch) there;
+// without the attribute both instructions are no-ops.  Every kernel executes pdl_wait before any exit, so "grid N+1
+// complete" always implies "grid N complete".
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();   // env HD_PDL (default on)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

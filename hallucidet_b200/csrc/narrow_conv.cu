@@ -133,6 +133,8 @@ enum { kModePlain = 0, kModeStats = 1, kModeF32 = 2 };
 // ------------------------------------------------------------------------------------------------
 template <int K, int NC, int MODE>
 __global__ void __launch_bounds__(kNThreads, 2) narrow_conv_kernel(const NarrowParams P) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(128) uint8_t nsm[];
     constexpr int KS = K / 16;                       // k16 slices per tap
     constexpr int ROLES = NC / 16;
@@ -361,6 +363,8 @@ __global__ void __launch_bounds__(kNThreads, 2) narrow_conv_kernel(const NarrowP
 // ------------------------------------------------------------------------------------------------
 template <int KX, int KY>
 __global__ void __launch_bounds__(kNThreads, 2) narrow_wgrad_kernel(const NarrowWgradParams P) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(128) uint8_t nsm[];
     constexpr int XR = KX / 16, YR = KY / 16, ROLES = XR * YR;
     constexpr int HALO_BYTES = NHH * NHW * KX * 2;
@@ -507,7 +511,7 @@ int launch_fwd_mode(const NarrowParams& P, cudaStream_t stream) {
         HD_CUDA_OK(cudaFuncSetAttribute(narrow_conv_kernel<K, NC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         attr = true;
     }
-    narrow_conv_kernel<K, NC, MODE><<<narrow_grid(P.total_tiles), kNThreads, smem, stream>>>(P);
+    HD_CUDA_OK(hd::launch(narrow_conv_kernel<K, NC, MODE>, dim3(narrow_grid(P.total_tiles)), dim3(kNThreads), smem, stream, P));
     HD_CUDA_OK(cudaPeekAtLastError());
     return HD_OK;
 }
@@ -529,7 +533,7 @@ int launch_wgrad(const NarrowWgradParams& P, cudaStream_t stream) {
         HD_CUDA_OK(cudaFuncSetAttribute(narrow_wgrad_kernel<KX, KY>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         attr = true;
     }
-    narrow_wgrad_kernel<KX, KY><<<narrow_grid(P.total_tiles), kNThreads, smem, stream>>>(P);
+    HD_CUDA_OK(hd::launch(narrow_wgrad_kernel<KX, KY>, dim3(narrow_grid(P.total_tiles)), dim3(kNThreads), smem, stream, P));
     HD_CUDA_OK(cudaPeekAtLastError());
     return HD_OK;
 }

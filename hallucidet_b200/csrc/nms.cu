@@ -54,6 +54,8 @@ __device__ __forceinline__ bool iou_gt(const float4 a, const float4 b, const flo
 // grid (col_blocks, col_blocks, problems), 64 threads: word (row box, column block) of the upper triangle
 __global__ void __launch_bounds__(kNmsBox) nms_mask_kernel(const float4* __restrict__ boxes, unsigned long long* __restrict__ mask,
                                                           const NmsBatch B, float threshold) {
+    pdl_trigger();
+    pdl_wait();
     const int pb = blockIdx.z;
     const int n = problem_size(B, pb);
     const int col_blocks = (n + kNmsBox - 1) / kNmsBox;
@@ -83,6 +85,8 @@ __device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
 // one CTA per problem: keep[i] = 1 iff sorted box i survives
 __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigned long long* __restrict__ mask_all,
                                                                   unsigned char* __restrict__ keep_all, const NmsBatch B) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned long long nsm[];
     const int pb = blockIdx.x;
     const int n = problem_size(B, pb);
@@ -186,11 +190,11 @@ extern "C" int hd_nms(const float* boxes_sorted, const int* offsets, const int* 
             ++B.count;
         }
         if (max_cb == 0) continue;
-        nms_mask_kernel<<<dim3(max_cb, max_cb, B.count), kNmsBox, 0, stream>>>(reinterpret_cast<const float4*>(boxes_sorted),
-                                                                            static_cast<unsigned long long*>(mask_ws), B, iou_threshold);
+        HD_CUDA_OK(hd::launch(nms_mask_kernel, dim3(dim3(max_cb, max_cb, B.count)), dim3(kNmsBox), 0, stream, reinterpret_cast<const float4*>(boxes_sorted),
+                                                                            static_cast<unsigned long long*>(mask_ws), B, iou_threshold));
         HD_CUDA_OK(cudaPeekAtLastError());
         const size_t sm = (kMaxColBlocks + 2 * static_cast<size_t>(kNmsBox) * max_cb) * sizeof(unsigned long long);
-        nms_scan_kernel<<<B.count, kScanThreads, sm, stream>>>(static_cast<const unsigned long long*>(mask_ws), keep, B);
+        HD_CUDA_OK(hd::launch(nms_scan_kernel, dim3(B.count), dim3(kScanThreads), sm, stream, static_cast<const unsigned long long*>(mask_ws), keep, B));
         HD_CUDA_OK(cudaPeekAtLastError());
     }
     return HD_OK;

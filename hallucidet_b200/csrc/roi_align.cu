@@ -42,6 +42,8 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_nhwc_kernel(const float* __restrict__ grad_out, const float* __restrict__ rois,
                                                                          const long long* __restrict__ level_of_roi, const RoiLevels L,
                                                                          int C, int PH, int PW, int sampling_ratio) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) float gsm[];        // [nbins][C + 4]: one float4 per thread and item, conflict free
     __shared__ float s_w[kMaxSamples * 4];
     __shared__ int s_off[kMaxSamples * 4];              // pixel index y * W + x, or -1
@@ -111,6 +113,8 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_nhwc_kernel(const f
 __global__ void __launch_bounds__(kRoiThreads) roi_align_fwd_nhwc_kernel(const float* __restrict__ rois, const long long* __restrict__ level_of_roi,
                                                                          const RoiLevels L, float* __restrict__ out, int C, int PH, int PW,
                                                                          int sampling_ratio) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) float gsm[];        // [C][nbins] output tile of this RoI
     __shared__ float s_w[kMaxSamples * 4];
     __shared__ int s_off[kMaxSamples * 4];
@@ -181,6 +185,8 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_fwd_nhwc_kernel(const f
 
 // [N][C][H][W] fp32 -> [N][H][W][C] fp32 through a 32 x 32 shared-memory tile
 __global__ void __launch_bounds__(256) nchw_to_nhwc_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float t[32][33];
     const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -201,6 +207,8 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_f32_kernel(const float* __re
 
 // [N][H][W][C] fp32 -> [N][C][H][W] fp32 through a 32 x 32 shared-memory tile
 __global__ void __launch_bounds__(256) nhwc_to_nchw_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int HW) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float t[32][33];
     const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
@@ -240,8 +248,8 @@ static int roi_bwd_launch(const float* grad_out, const float* rois, const long l
                                         static_cast<int>(kMaxBins * (kMaxC + 4) * sizeof(float))));
         attr_set = true;
     }
-    roi_align_bwd_nhwc_kernel<<<num_rois, kRoiThreads, smem, stream>>>(grad_out, rois, level_of_roi, L, channels, pooled_h, pooled_w,
-                                                                       sampling_ratio);
+    HD_CUDA_OK(hd::launch(roi_align_bwd_nhwc_kernel, dim3(num_rois), dim3(kRoiThreads), smem, stream, grad_out, rois, level_of_roi, L, channels, pooled_h, pooled_w,
+                                                                       sampling_ratio));
     HD_CUDA_OK(cudaPeekAtLastError());
     return HD_OK;
 }
@@ -255,7 +263,7 @@ static int roi_fwd_launch(const float* rois, const long long* level_of_roi, cons
                                         static_cast<int>(kMaxC * kMaxBins * sizeof(float))));
         attr_set = true;
     }
-    roi_align_fwd_nhwc_kernel<<<num_rois, kRoiThreads, smem, stream>>>(rois, level_of_roi, L, out, channels, pooled_h, pooled_w, sampling_ratio);
+    HD_CUDA_OK(hd::launch(roi_align_fwd_nhwc_kernel, dim3(num_rois), dim3(kRoiThreads), smem, stream, rois, level_of_roi, L, out, channels, pooled_h, pooled_w, sampling_ratio));
     HD_CUDA_OK(cudaPeekAtLastError());
     return HD_OK;
 }
@@ -316,7 +324,7 @@ extern "C" int hd_nhwc_to_nchw_f32(const float* x_nhwc, float* y_nchw, int n, in
     HD_CHECK_ARG(x_nhwc != nullptr && y_nchw != nullptr && n > 0 && channels > 0 && height > 0 && width > 0 && n < 65536);
     const int hw = height * width;
     dim3 grid((hw + 31) / 32, (channels + 31) / 32, n);
-    nhwc_to_nchw_f32_kernel<<<grid, 256, 0, stream>>>(x_nhwc, y_nchw, channels, hw);
+    HD_CUDA_OK(hd::launch(nhwc_to_nchw_f32_kernel, dim3(grid), dim3(256), 0, stream, x_nhwc, y_nchw, channels, hw));
     HD_CUDA_OK(cudaPeekAtLastError());
     return HD_OK;
 }
@@ -340,7 +348,7 @@ extern "C" int hd_nchw_to_nhwc_f32(const float* x_nchw, float* y_nhwc, int n, in
     HD_CHECK_ARG(x_nchw != nullptr && y_nhwc != nullptr && n > 0 && channels > 0 && height > 0 && width > 0 && n < 65536);
     const int hw = height * width;
     dim3 grid((hw + 31) / 32, (channels + 31) / 32, n);
-    nchw_to_nhwc_f32_kernel<<<grid, 256, 0, stream>>>(x_nchw, y_nhwc, channels, hw);
+    HD_CUDA_OK(hd::launch(nchw_to_nhwc_f32_kernel, dim3(grid), dim3(256), 0, stream, x_nchw, y_nhwc, channels, hw));
     HD_CUDA_OK(cudaPeekAtLastError());
     return HD_OK;
 }

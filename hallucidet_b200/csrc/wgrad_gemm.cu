@@ -50,6 +50,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 }
 
 __global__ void __launch_bounds__(kWThreads) wgrad_gemm_kernel(const __grid_constant__ WgradParams P) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5;
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(kWThreads) wgrad_gemm_kernel(const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();                    // prologue above overlaps the previous kernel's tail
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -428,7 +430,7 @@ extern "C" int hd_conv_wgrad(const hd_conv_args* a, hd_stream stream_) {
         attr_set = true;
     }
     dim3 grid(splits, co_tiles * P.ci_tiles, P.taps);
-    wgrad_gemm_kernel<<<grid, kWThreads, smem, stream>>>(P);
+    HD_CUDA_OK(hd::launch(wgrad_gemm_kernel, dim3(grid), dim3(kWThreads), smem, stream, P));
     HD_CUDA_OK(cudaPeekAtLastError());
     return HD_OK;
 }
