@@ -271,9 +271,16 @@ class _UnetEngine:
             l.dw_rows = l.cp
             l.dw_cols = l.k * l.k * l.cin if l is not self.stem else ops.STEM_KPAD
             tot += l.dw_rows * l.dw_cols
+        # ... followed by the BatchNorm backward sums of every layer, so that the same fill zeroes them too
+        bn_layers = [l for l in self.all_layers if getattr(l, "sums", None) is not None]
+        for l in bn_layers:
+            l.sums_off = tot
+            tot += (l.sums.numel() + 3) // 4 * 4
         self.dw_flat = torch.zeros(tot, device=device)
         for l in self.all_layers:
             l.dw = self.dw_flat[l.dw_off:l.dw_off + l.dw_rows * l.dw_cols]
+        for l in bn_layers:
+            l.sums = self.dw_flat[l.sums_off:l.sums_off + l.sums.numel()].view_as(l.sums)
         self.grad_bufs = {}
         self.side_stream, self.side_used = None, False
         self.pack_tab = self.unpack_tab = None
@@ -452,8 +459,7 @@ class _UnetEngine:
     def _bn_bwd(self, l, g, y_relu, z=None, g_out=None, direct_relu=False):
         """BatchNorm backward for layer l given g = dL/d(ReLU output); the ReLU mask comes from y_relu (residual blocks:
         the block output) or, when the ReLU follows this BN directly, is recomputed from z (one tensor less to read)."""
-        z = l.z if z is None else z
-        l.sums.zero_()
+        z = l.z if z is None else z                   # (l.sums was zeroed with dw_flat at the start of the backward)
         rs, rb = (l.scale, l.shift) if direct_relu else (None, None)
         yr = None if direct_relu else y_relu
         ops.bn_bwd_reduce(g, yr, z, l.mean, l.invstd, l.sums, relu_scale=rs, relu_shift=rb)
