@@ -148,3 +148,75 @@ def test_retinanet_tail_cuda():
     assert sum(d["boxes"].shape[0] for d in d1) > 0
     for p, q in zip(d1, d2):
         assert all(torch.equal(p[k], q[k]) for k in ("boxes", "scores", "labels"))
+
+
+def test_pad_rows_matches_pad_sequence_cpu():
+    """detection._pad_rows (one concatenation + index_copy) == row-by-row padding, incl. empty rows and several pieces per image."""
+    from hallucidet_b200 import detection as D
+    g = torch.Generator().manual_seed(3)
+    rows = [torch.randn(n, 4, generator=g) for n in (5, 0, 3, 7)]
+    out, present = D._pad_rows(rows, 9, fill=-1.0)
+    ref = torch.full((4, 9, 4), -1.0)
+    for b, r in enumerate(rows):
+        ref[b, :r.shape[0]] = r
+    assert torch.equal(out, ref)
+    assert torch.equal(present, torch.arange(9)[None, :] < torch.tensor([5, 0, 3, 7])[:, None])
+    # all rows full: stack
+    full = [torch.randn(6, 4, generator=g) for _ in range(3)]
+    out, present = D._pad_rows(full, 6)
+    assert torch.equal(out, torch.stack(full)) and bool(present.all())
+    # nothing at all
+    out, present = D._pad_rows([torch.zeros(0, 4), torch.zeros(0, 4)], 2, fill=0)
+    assert out.shape == (2, 2, 4) and not bool(present.any()) and float(out.abs().sum()) == 0.0
+    # two pieces per image (proposals followed by ground truth), image-major
+    pieces = [torch.randn(n, 4, generator=g) for n in (4, 2, 0, 1, 3, 0)]
+    out, present = D._pad_rows(pieces, 7, counts=[6, 1, 3])
+    ref = torch.zeros(3, 7, 4)
+    ref[0, :6] = torch.cat(pieces[0:2]); ref[1, :1] = torch.cat(pieces[2:4]); ref[2, :3] = torch.cat(pieces[4:6])
+    assert torch.equal(out, ref) and present.sum(1).tolist() == [6, 1, 3]
+    labels = [torch.arange(n) + 10 for n in (2, 0, 4)]
+    out, _ = D._pad_rows(labels, 4)
+    assert out.dtype == torch.int64 and out.tolist() == [[10, 11, 0, 0], [0, 0, 0, 0], [10, 11, 12, 13]]
+
+
+def test_padded_gt_cache_follows_the_targets_cpu():
+    from hallucidet_b200 import detection as D
+    t = [{"boxes": torch.tensor([[0., 0., 4., 4.], [1., 1., 3., 5.]]), "labels": torch.tensor([1, 1])},
+         {"boxes": torch.zeros(0, 4), "labels": torch.zeros(0, dtype=torch.int64)}]
+    gt, present, gl = D._padded_gt(t, torch.float32)
+    assert gt.shape == (2, 2, 4) and present.tolist() == [[True, True], [False, False]] and gl.tolist() == [[1, 1], [0, 0]]
+    assert D._padded_gt(t, torch.float32)[0] is gt                          # same targets: cached
+    t[0]["boxes"][0, 2] = 9.0                                                # in-place change bumps the version
+    gt2, _, _ = D._padded_gt(t, torch.float32)
+    assert gt2 is not gt and float(gt2[0, 0, 2]) == 9.0
+    t2 = [{"boxes": x["boxes"].clone(), "labels": x["labels"].clone()} for x in t]
+    assert D._padded_gt(t2, torch.float32)[0] is not gt2                     # other tensors: recomputed
+
+
+def test_fused_head_modules_keep_state_dict_and_cpu_results():
+    """install_b200_backbone swaps Conv2dNormActivation(conv, ReLU) of the frozen heads for detection._FusedConvReLU: the
+    state_dict keys do not change and, off the GPU, the module computes exactly what it replaced."""
+    import copy
+    from torchvision.models.detection.rpn import RPNHead
+    from torchvision.models.detection.retinanet import RetinaNetClassificationHead
+    from hallucidet_b200 import detection as D
+    for head in (RPNHead(16, 3), RetinaNetClassificationHead(16, 3, 2)):
+        for p in head.parameters():
+            p.requires_grad_(False)
+        fused = copy.deepcopy(head)
+        D._fuse_head_conv_relu(fused)
+        assert any(isinstance(m, D._FusedConvReLU) for m in fused.modules())
+        assert list(fused.state_dict()) == list(head.state_dict())
+        xs = [torch.randn(2, 16, 12, 10), torch.randn(2, 16, 6, 5)]
+        a, b = head(xs), fused(xs)
+        a = a if isinstance(a, torch.Tensor) else [t for part in a for t in part]
+        b = b if isinstance(b, torch.Tensor) else [t for part in b for t in part]
+        if isinstance(a, torch.Tensor):
+            assert torch.equal(a, b)
+        else:
+            assert all(torch.equal(x, y) for x, y in zip(a, b))
+    rpn = RPNHead(16, 3)
+    xs = [torch.randn(1, 16, 8, 8)]
+    o1, d1 = rpn(xs)
+    o2, d2 = D._rpn_head(rpn, xs)                                            # CPU: falls back to the module
+    assert torch.equal(o1[0], o2[0]) and torch.equal(d1[0], d2[0])
