@@ -82,6 +82,7 @@ PROTOTYPES = {
     "hd_resize_nearest_bwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
     "hd_regulariser": [c_int, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_int, c_int, c_void_p, c_void_p,
                        c_float, c_int, c_void_p],
+    "hd_pack_blocks": [c_void_p],
     "hd_multi_blocks": [ctypes.c_int64],
     "hd_pack_conv_weights": [c_void_p, c_int, c_int, c_void_p],
     "hd_unpack_wgrads": [c_void_p, c_int, c_int, c_void_p],

@@ -97,12 +97,64 @@ __device__ __forceinline__ int find_desc(const int* first_block, int stride_ints
     return lo;
 }
 
-__global__ void pack_weights_multi_kernel(const hd_pack_desc* __restrict__ descs, int n) {
+// Tiled path of the multi-layer packer: a block stages 16 output channels x TCI input channels x taps of the OIHW master
+// weight (contiguous 4 * TCI * taps bytes per output channel) in shared memory and writes both bf16 layouts from there --
+// the forward rows as 2 * TCI contiguous bytes per (cout, tap), the dgrad rows as full 32-byte sectors (16 couts) per
+// (cin, tap).  The element-per-thread path below reads the master weight with a stride of `taps` (forward) or
+// `cin * taps` (dgrad) floats: one 32-byte sector per element, 8x the traffic.
+constexpr int kPackCo = 16, kPackCiMax = 64, kPackTapsMax = 9;
+
+__host__ __device__ __forceinline__ bool pack_tiled_ok(const hd_pack_desc& d, int taps) {
+    return d.w_fwd != nullptr && d.w_dgrad != nullptr && d.w_t == nullptr && taps <= kPackTapsMax && d.cout % kPackCo == 0 &&
+           d.cin % 16 == 0 && d.cout_pad == d.cout && d.cin_pad == d.cin && d.k_pad == taps * d.cin;
+}
+
+__device__ void pack_tiled(const hd_pack_desc& d, int taps, int blk, int nblk, float* sm) {
+    const int tci = d.cin % 64 == 0 ? 64 : (d.cin % 32 == 0 ? 32 : 16);
+    const int ci_tiles = d.cin / tci, tiles = (d.cout / kPackCo) * ci_tiles;
+    const int row = tci * taps, pitch = row + 1;                     // +1: the dgrad pass reads a column of 16 rows
+    __nv_bfloat16* w_fwd = static_cast<__nv_bfloat16*>(d.w_fwd);
+    __nv_bfloat16* w_dgrad = static_cast<__nv_bfloat16*>(d.w_dgrad);
+    for (int t = blk; t < tiles; t += nblk) {
+        const int co0 = (t / ci_tiles) * kPackCo, ci0 = (t % ci_tiles) * tci;
+        __syncthreads();                                             // previous tile fully consumed
+        for (int i = threadIdx.x; i < kPackCo * row; i += blockDim.x) {
+            const int r = i / row, c = i - r * row;
+            float v = d.w[(static_cast<long>(co0 + r) * d.cin + ci0) * taps + c];
+            if (d.scale) v *= d.scale[co0 + r];
+            sm[r * pitch + c] = v;
+        }
+        __syncthreads();
+        // forward layout [cout][tap * cin + ci]: pairs of consecutive input channels
+        const int half = tci / 2;
+        for (int i = threadIdx.x; i < kPackCo * taps * half; i += blockDim.x) {
+            const int cp = i % half, tap = (i / half) % taps, r = i / (half * taps);
+            const float a = sm[r * pitch + (2 * cp) * taps + tap], b = sm[r * pitch + (2 * cp + 1) * taps + tap];
+            *reinterpret_cast<__nv_bfloat162*>(w_fwd + static_cast<long>(co0 + r) * d.k_pad + tap * d.cin + ci0 + 2 * cp) =
+                __floats2bfloat162_rn(a, b);
+        }
+        // dgrad layout [cin][tap * cout + co]: pairs of consecutive output channels
+        for (int i = threadIdx.x; i < tci * taps * (kPackCo / 2); i += blockDim.x) {
+            const int rp = i % (kPackCo / 2), tap = (i / (kPackCo / 2)) % taps, c = i / ((kPackCo / 2) * taps);
+            const float a = sm[(2 * rp) * pitch + c * taps + tap], b = sm[(2 * rp + 1) * pitch + c * taps + tap];
+            *reinterpret_cast<__nv_bfloat162*>(w_dgrad + (static_cast<long>(ci0 + c) * taps + tap) * d.cout + co0 + 2 * rp) =
+                __floats2bfloat162_rn(a, b);
+        }
+    }
+}
+
+__global__ void pack_weights_multi_kernel(const hd_pack_desc* __restrict__ descs, int n, int total_blocks) {
     pdl_trigger();
     pdl_wait();
+    __shared__ float pack_sm[kPackCo * (kPackCiMax * kPackTapsMax + 1)];
     const int li = find_desc(&descs[0].first_block, sizeof(hd_pack_desc) / sizeof(int), n, blockIdx.x);
     const hd_pack_desc d = descs[li];
     const int taps = d.kh * d.kw;
+    if (pack_tiled_ok(d, taps)) {
+        const int next = li + 1 < n ? descs[li + 1].first_block : total_blocks;
+        pack_tiled(d, taps, blockIdx.x - d.first_block, next - d.first_block, pack_sm);
+        return;
+    }
     const long n_fwd = static_cast<long>(d.cout_pad) * d.k_pad;
     const long n_dg = d.w_dgrad ? static_cast<long>(d.cin_pad) * taps * d.cout : 0;
     __nv_bfloat16* w_fwd = static_cast<__nv_bfloat16*>(d.w_fwd);
@@ -1040,9 +1092,21 @@ extern "C" int hd_multi_blocks(int64_t elements) {
     return static_cast<int>((elements + static_cast<int64_t>(kEwThreads) * kMultiItems - 1) / (static_cast<int64_t>(kEwThreads) * kMultiItems));
 }
 
+extern "C" int hd_pack_blocks(const hd_pack_desc* d) {
+    // blocks layer `d` (a HOST copy of its descriptor; first_block ignored) occupies in hd_pack_conv_weights
+    if (d == nullptr) return 0;
+    const int taps = d->kh * d->kw;
+    if (pack_tiled_ok(*d, taps)) {
+        const int tci = d->cin % 64 == 0 ? 64 : (d->cin % 32 == 0 ? 32 : 16);
+        return (d->cout / kPackCo) * (d->cin / tci);                    // one block per (16 cout, tci cin) tile
+    }
+    const int64_t work = static_cast<int64_t>(d->cout_pad) * d->k_pad + (d->w_dgrad ? static_cast<int64_t>(d->cin_pad) * taps * d->cout : 0);
+    return hd_multi_blocks(work);
+}
+
 extern "C" int hd_pack_conv_weights(const hd_pack_desc* descs_dev, int n_layers, int total_blocks, hd_stream st) {
     HD_CHECK_ARG(descs_dev && n_layers > 0 && total_blocks > 0);
-    HD_CUDA_OK(hd::launch(pack_weights_multi_kernel, dim3(total_blocks), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), descs_dev, n_layers));
+    HD_CUDA_OK(hd::launch(pack_weights_multi_kernel, dim3(total_blocks), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), descs_dev, n_layers, total_blocks));
     HD_LAUNCH_OK();
     return HD_OK;
 }

@@ -226,8 +226,7 @@ def pack_table(packed_convs, weights, device):
         d = _lib.HdPackDesc(w.data_ptr(), None, pk.w_fwd.data_ptr(), pk.w_dgrad.data_ptr() if pk.w_dgrad is not None else None,
                             pk.w_t.data_ptr() if pk.w_t is not None else None, pk.cout, pk.cin, pk.k, pk.k, pk.cout_pad, pk.k_pad,
                             pk.cin_pad, first)
-        work = pk.cout_pad * pk.k_pad + (pk.cin_pad * pk.k * pk.k * pk.cout if pk.w_dgrad is not None else 0)
-        d._blocks = multi_blocks(work)
+        d._blocks = int(_lib.load().hd_pack_blocks(ctypes.byref(d)))
         d._key = w.data_ptr()
         first += d._blocks
         descs.append(d)

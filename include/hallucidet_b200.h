@@ -94,8 +94,8 @@ int hd_unpack_wgrad(const float* dw_packed, float* grad_oihw, int cout, int cin,
                     int row_stride, float scale, hd_stream stream);
 
 /* Whole-network variants of the two calls above: one launch for every layer.  The descriptor tables live in DEVICE
- * memory; first_block is the running sum of hd_multi_blocks(work) over the preceding layers (work = cout_pad*k_pad +
- * (w_dgrad ? cin_pad*kh*kw*cout : 0) for packing, cout*cin*taps for unpacking); total_blocks is the grand total. */
+ * memory; first_block is the running sum, over the preceding layers, of hd_pack_blocks(desc) for packing and of
+ * hd_multi_blocks(cout*cin*taps) for unpacking; total_blocks is the grand total. */
 typedef struct hd_pack_desc {
     const float* w;       /* fp32 OIHW master weight */
     const float* scale;   /* optional per-cout scale (folded BN) */
@@ -112,6 +112,7 @@ typedef struct hd_unpack_desc {
     int32_t pad_;
 } hd_unpack_desc;
 int hd_multi_blocks(int64_t elements);
+int hd_pack_blocks(const hd_pack_desc* desc_host);   /* blocks one layer occupies in hd_pack_conv_weights (for first_block) */
 int hd_pack_conv_weights(const hd_pack_desc* descs_dev, int n_layers, int total_blocks, hd_stream stream);
 int hd_unpack_wgrads(const hd_unpack_desc* descs_dev, int n_layers, int total_blocks, hd_stream stream);
 

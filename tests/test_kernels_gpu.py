@@ -536,7 +536,8 @@ def test_multi_layer_pack_and_unpack_match_single_layer_calls():
     """hd_pack_conv_weights / hd_unpack_wgrads (one launch for every layer) against the per-layer entry points."""
     o = ops()
     g = torch.Generator().manual_seed(0)
-    shapes = [(64, 3, 7, 160, False), (64, 64, 3, None, True), (16, 32, 3, None, True), (256, 128, 1, None, True), (16, 16, 3, None, True)]
+    shapes = [(64, 3, 7, 160, False), (64, 64, 3, None, True), (16, 32, 3, None, True), (256, 128, 1, None, True), (16, 16, 3, None, True),
+              (128, 64, 3, None, True), (48, 32, 1, None, True), (32, 128, 3, None, True)]     # (tiled path: no padding, cout % 16 == 0)
     ws, singles, multis = [], [], []
     for cout, cin, k, k_pad, dg in shapes:
         w = torch.randn(cout, cin, k, k, generator=g).cuda()
