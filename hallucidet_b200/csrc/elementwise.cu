@@ -568,47 +568,58 @@ __global__ void maxpool_bwd_idx_kernel(const unsigned char* __restrict__ idx, co
                                        int w, int C) {
     pdl_trigger();
     pdl_wait();
+    // 32-bit index arithmetic (the host checks n*h*w*C/8 < 2^31); the arg-max bytes of all candidate windows are loaded
+    // first, the dy vectors only for windows that hit
     const int ho = h / 2, wo = w / 2, G = C / 8;
-    const long total = static_cast<long>(n) * h * w * G;
-    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long>(gridDim.x) * blockDim.x) {
-        const int g = static_cast<int>(i % G);
-        const long pix = i / G;
-        const int iw = static_cast<int>(pix % w), ih = static_cast<int>((pix / w) % h), b = static_cast<int>(pix / (static_cast<long>(w) * h));
+    const unsigned total = static_cast<unsigned>(n) * h * w * G;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned g = i % G, pix = i / G;
+        const unsigned iw = pix % w, t = pix / w, ih = t % h, b = t / h;
         float acc[8];
         if (add) {
             bf8 av;
-            av.load(add + pix * C + g * 8);
+            av.load(add + static_cast<size_t>(pix) * C + g * 8);
             av.unpack(acc);
         } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] = 0.f;
         }
-        for (int oh = ih / 2; oh <= (ih + 1) / 2; ++oh) {      // windows with 2*oh-1 <= ih <= 2*oh+1
-            if (oh >= ho) continue;
-            for (int ow = iw / 2; ow <= (iw + 1) / 2; ++ow) {
-                if (ow >= wo) continue;
-                const long opix = (static_cast<long>(b) * ho + oh) * wo + ow;
-                const unsigned pos = (ih - (2 * oh - 1)) * 3 + (iw - (2 * ow - 1));
-                const uint2 am = *reinterpret_cast<const uint2*>(idx + opix * C + g * 8);
-                unsigned hit = 0;
+        // windows with 2*oh-1 <= ih <= 2*oh+1: oh = ih/2 and, for odd ih, also (ih+1)/2
+        const unsigned oh0 = ih >> 1, ow0 = iw >> 1;
+        uint2 am[4];
+        unsigned hit[4];
+        size_t off[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    hit |= (((am.x >> (8 * j)) & 0xffu) == pos) ? (1u << j) : 0u;
-                    hit |= (((am.y >> (8 * j)) & 0xffu) == pos) ? (1u << (j + 4)) : 0u;
-                }
-                if (!hit) continue;
-                bf8 dv;
-                dv.load(dy + opix * C + g * 8);
-                float df[8];
-                dv.unpack(df);
+        for (int q = 0; q < 4; ++q) {
+            const unsigned oh = oh0 + (q >> 1), ow = ow0 + (q & 1);
+            const bool on = ((q >> 1) == 0 || (ih & 1u)) && ((q & 1) == 0 || (iw & 1u)) && oh < static_cast<unsigned>(ho) &&
+                            ow < static_cast<unsigned>(wo);
+            off[q] = (static_cast<size_t>(b * ho + oh) * wo + ow) * C + g * 8;
+            am[q] = on ? *reinterpret_cast<const uint2*>(idx + off[q]) : make_uint2(0xffffffffu, 0xffffffffu);
+            const unsigned pos = (ih + 1 - 2 * oh) * 3 + (iw + 1 - 2 * ow);
+            const unsigned pat = pos * 0x01010101u;                    // pos in every byte
+            const unsigned x0 = am[q].x ^ pat, x1 = am[q].y ^ pat;     // a zero byte = arg-max here
+            unsigned hbits = 0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) if (hit & (1u << j)) acc[j] += df[j];
+            for (int j = 0; j < 4; ++j) {
+                hbits |= (((x0 >> (8 * j)) & 0xffu) == 0u) ? (1u << j) : 0u;
+                hbits |= (((x1 >> (8 * j)) & 0xffu) == 0u) ? (1u << (j + 4)) : 0u;
             }
+            hit[q] = on ? hbits : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (!hit[q]) continue;
+            bf8 dv;
+            dv.load(dy + off[q]);
+            float df[8];
+            dv.unpack(df);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (hit[q] & (1u << j)) acc[j] += df[j];
         }
         bf8 o;
         o.pack(acc);
-        o.store(dx + pix * C + g * 8);
+        o.store(dx + static_cast<size_t>(pix) * C + g * 8);
     }
 }
 
@@ -1201,6 +1212,7 @@ extern "C" int hd_maxpool_bwd(const hd_act* x, const hd_act* y, const void* dy, 
     if (idx != nullptr) {
         // arg-max positions stored by hd_maxpool_fwd (with mask_nonpositive when relu_mask semantics are wanted): x / y are
         // not read at all
+        HD_CHECK_ARG(static_cast<long>(x->n) * x->h * x->w * (x->c / 8) < (1L << 31));     // 32-bit index arithmetic in the kernel
         HD_CUDA_OK(hd::launch(maxpool_bwd_idx_kernel, dim3(ew_blocks(static_cast<long>(x->n) * x->h * x->w * (x->c / 8))), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), static_cast<const unsigned char*>(idx), static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(add),
             static_cast<__nv_bfloat16*>(dx), x->n, x->h, x->w, x->c));
         HD_LAUNCH_OK();
