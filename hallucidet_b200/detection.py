@@ -806,11 +806,12 @@ def _anchors(model, images, features):
     key = (id(gen), tuple(images.tensors.shape), tuple(map(tuple, images.image_sizes)), tuple(tuple(f.shape) for f in features),
            features[0].dtype, features[0].device)
     hit = _ANCHOR_CACHE.get(key)
-    if hit is None:
+    fresh = hit is None
+    if fresh:
         if len(_ANCHOR_CACHE) > 16:
             _ANCHOR_CACHE.clear()
         hit = _ANCHOR_CACHE[key] = (gen, gen(images, features))        # (the generator is kept alive so its id stays unique)
-    return hit[1]
+    return hit[1], fresh
 
 
 FUSED_RPN_PREDICTORS = _os.environ.get("HD_FUSED_RPN_PRED", "1") == "1"
@@ -845,7 +846,7 @@ def rpn_eval(model, images, features, targets, targets_event=None):
     features = list(features.values())
     objectness, pred_bbox_deltas = _rpn_head(model.rpn.head, features)
     batched = BATCHED_TAIL and features[0].is_cuda
-    anchors = _anchors(model, images, features) if batched else model.rpn.anchor_generator(images, features)
+    anchors, anchors_fresh = _anchors(model, images, features) if batched else (model.rpn.anchor_generator(images, features), True)
     num_images = len(anchors)
     num_anchors_per_level = [o[0].shape[0] * o[0].shape[1] * o[0].shape[2] for o in objectness]
     objectness, pred_bbox_deltas = concat_box_prediction_layers(objectness, pred_bbox_deltas)
@@ -864,7 +865,8 @@ def rpn_eval(model, images, features, targets, targets_event=None):
         main = torch.cuda.current_stream(proposals.device)
         if EARLY_RPN_TARGETS:
             side = _side_streams(proposals.device, 1)[0]
-            if targets_event is None:
+            if targets_event is None or anchors_fresh:
+                # (anchors computed just now are queued on the main stream behind the backbone: wait for them as well)
                 targets_event = torch.cuda.Event()
                 targets_event.record(main)
             side.wait_event(targets_event)
