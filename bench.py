@@ -161,7 +161,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     from hallucidet_b200 import ops
     from hallucidet_b200.train import HalluciDetTrainer
-    from oracle import step as ostep            # synthetic input generator only (no oracle compute on this arm)
+    from hallucidet_b200.synthetic import synthetic_batch
 
     torch.backends.cudnn.benchmark = True       # train_hallucidet.py:28-29
     torch.backends.cuda.matmul.allow_tf32 = True  # torchvision box head (fp32 Linear 12544->1024) on the TF32 tensor path
@@ -169,7 +169,7 @@ def main():
     weights = {"pixel_rgb": 1.0, "pixel_ir": 1.0} if args.pixel else None
     tr = HalluciDetTrainer(detector_name=args.detector, size=S, pixel=args.pixel, weights=weights, seed=123, device=dev,
                            use_cuda_graph=not args.no_graph)
-    ir_h, rgb_h, targets = ostep.synthetic_batch(B, H, W, seed=123 + rank)
+    ir_h, rgb_h, targets = synthetic_batch(B, H, W, seed=123 + rank)
     ir_h, rgb_h = ir_h.pin_memory(), rgb_h.pin_memory()
     targets = [{k: v.to(dev) for k, v in t.items()} for t in targets]
     ir_d, rgb_d = ir_h.to(dev), rgb_h.to(dev)

@@ -714,11 +714,8 @@ static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStrea
     P.direct_store = (P.BN < 64 && P.Cout_total == P.BN && P.out_C0 == P.Cout_total && P.out_ptr != nullptr) ? 1 : 0;
     P.nphases = nphases;
     const size_t smem = static_cast<size_t>(fixed) + static_cast<size_t>(stages) * P.stage_bytes;
-    static bool attr_set = false;
-    if (!attr_set) {
-        HD_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        attr_set = true;
-    }
+    static SmemAttrOnce smem_attr;
+    HD_CUDA_OK(ensure_dyn_smem(smem_attr, conv_gemm_kernel, 232448));
     const long total = static_cast<long>(P.m_tiles) * P.n_tiles * nphases;
     const int grid = static_cast<int>(total < num_sms() ? total : num_sms());
     HD_CUDA_OK(hd::launch(conv_gemm_kernel, dim3(grid), dim3(kThreads), smem, stream, P));

@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/hallucidet_b200.h"
 
 namespace hd {
@@ -51,6 +53,23 @@ inline FastDiv make_fastdiv(uint32_t d) {
     f.shr = s;
     f.mul = static_cast<uint32_t>(((1ull << 32) * ((1ull << s) - d)) / d + 1);
     return f;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: set it once per (kernel, device), from any host
+// thread (the concurrent NMS path launches from a thread pool; a process may drive several GPUs).
+struct SmemAttrOnce {
+    std::atomic<uint64_t> done{0};
+};
+template <typename F>
+inline cudaError_t ensure_dyn_smem(SmemAttrOnce& once, F* kernel, int bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t bit = 1ull << (dev & 63);
+    if (once.done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) once.done.fetch_or(bit, std::memory_order_release);
+    return e;
 }
 
 // narrow_conv.cu: HBM-bound 3x3 stride-1 layers with 16 / 32 channels (halo patch + mma.sync); the public entry points

@@ -506,11 +506,8 @@ template <int K, int NC, int MODE>
 int launch_fwd_mode(const NarrowParams& P, cudaStream_t stream) {
     const size_t smem = fwd_stages(K) * NHH * NHW * K * 2 + kNWarps * 512 + kNWarps * 16 * 2 * sizeof(float) +
                         (K == 32 ? NC * (9 * K * 2 + 16) : 0);
-    static bool attr = false;
-    if (!attr) {
-        HD_CUDA_OK(cudaFuncSetAttribute(narrow_conv_kernel<K, NC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        attr = true;
-    }
+    static SmemAttrOnce smem_attr;
+    HD_CUDA_OK(ensure_dyn_smem(smem_attr, narrow_conv_kernel<K, NC, MODE>, static_cast<int>(smem)));
     HD_CUDA_OK(hd::launch(narrow_conv_kernel<K, NC, MODE>, dim3(narrow_grid(P.total_tiles)), dim3(kNThreads), smem, stream, P));
     HD_CUDA_OK(cudaPeekAtLastError());
     return HD_OK;
@@ -528,11 +525,8 @@ int launch_wgrad(const NarrowWgradParams& P, cudaStream_t stream) {
     size_t smem = static_cast<size_t>(wgrad_stages(KX, KY)) * (NHH * NHW * KX * 2 + NTH * NTW * KY * 2);
     const size_t red = static_cast<size_t>(KX / 16) * (KY / 16) * 72 * 32 * sizeof(float);
     if (smem < red) smem = red;
-    static bool attr = false;
-    if (!attr) {
-        HD_CUDA_OK(cudaFuncSetAttribute(narrow_wgrad_kernel<KX, KY>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        attr = true;
-    }
+    static SmemAttrOnce smem_attr;
+    HD_CUDA_OK(ensure_dyn_smem(smem_attr, narrow_wgrad_kernel<KX, KY>, static_cast<int>(smem)));
     HD_CUDA_OK(hd::launch(narrow_wgrad_kernel<KX, KY>, dim3(narrow_grid(P.total_tiles)), dim3(kNThreads), smem, stream, P));
     HD_CUDA_OK(cudaPeekAtLastError());
     return HD_OK;

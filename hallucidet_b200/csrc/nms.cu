@@ -164,12 +164,9 @@ extern "C" int hd_nms(const float* boxes_sorted, const int* offsets, const int* 
     if (problems == 0) return HD_OK;
     HD_CHECK_ARG(boxes_sorted != nullptr && mask_ws != nullptr && keep != nullptr);
     HD_CHECK_ARG((reinterpret_cast<uintptr_t>(boxes_sorted) & 15) == 0);
-    static bool attr_set = false;
     const size_t smem = (kMaxColBlocks + 2 * kNmsBox * kMaxColBlocks) * sizeof(unsigned long long);
-    if (!attr_set) {
-        HD_CUDA_OK(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        attr_set = true;
-    }
+    static SmemAttrOnce smem_attr;
+    HD_CUDA_OK(ensure_dyn_smem(smem_attr, nms_scan_kernel, static_cast<int>(smem)));
     long mask_off = 0;
     for (int p0 = 0; p0 < problems; p0 += kMaxProblems) {
         NmsBatch B;

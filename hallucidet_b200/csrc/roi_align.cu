@@ -242,12 +242,8 @@ static int roi_check(int num_rois, int channels, int pooled_h, int pooled_w, int
 static int roi_bwd_launch(const float* grad_out, const float* rois, const long long* level_of_roi, const RoiLevels& L, int num_rois,
                           int channels, int pooled_h, int pooled_w, int sampling_ratio, cudaStream_t stream) {
     const size_t smem = static_cast<size_t>(pooled_h * pooled_w) * (channels + 4) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        HD_CUDA_OK(cudaFuncSetAttribute(roi_align_bwd_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(kMaxBins * (kMaxC + 4) * sizeof(float))));
-        attr_set = true;
-    }
+    static SmemAttrOnce smem_attr;
+    HD_CUDA_OK(ensure_dyn_smem(smem_attr, roi_align_bwd_nhwc_kernel, static_cast<int>(kMaxBins * (kMaxC + 4) * sizeof(float))));
     HD_CUDA_OK(hd::launch(roi_align_bwd_nhwc_kernel, dim3(num_rois), dim3(kRoiThreads), smem, stream, grad_out, rois, level_of_roi, L, channels, pooled_h, pooled_w,
                                                                        sampling_ratio));
     HD_CUDA_OK(cudaPeekAtLastError());
@@ -257,12 +253,8 @@ static int roi_bwd_launch(const float* grad_out, const float* rois, const long l
 static int roi_fwd_launch(const float* rois, const long long* level_of_roi, const RoiLevels& L, float* out, int num_rois, int channels,
                           int pooled_h, int pooled_w, int sampling_ratio, cudaStream_t stream) {
     const size_t smem = static_cast<size_t>(channels) * pooled_h * pooled_w * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        HD_CUDA_OK(cudaFuncSetAttribute(roi_align_fwd_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(kMaxC * kMaxBins * sizeof(float))));
-        attr_set = true;
-    }
+    static SmemAttrOnce smem_attr;
+    HD_CUDA_OK(ensure_dyn_smem(smem_attr, roi_align_fwd_nhwc_kernel, static_cast<int>(kMaxC * kMaxBins * sizeof(float))));
     HD_CUDA_OK(hd::launch(roi_align_fwd_nhwc_kernel, dim3(num_rois), dim3(kRoiThreads), smem, stream, rois, level_of_roi, L, out, channels, pooled_h, pooled_w, sampling_ratio));
     HD_CUDA_OK(cudaPeekAtLastError());
     return HD_OK;

@@ -424,11 +424,8 @@ extern "C" int hd_conv_wgrad(const hd_conv_args* a, hd_stream stream_) {
     else P.tmX[1] = P.tmX[0];
 
     const size_t smem = 1024 + static_cast<size_t>(stages) * P.stage_bytes + 16 * stages + 16;
-    static bool attr_set = false;
-    if (!attr_set) {
-        HD_CUDA_OK(cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-        attr_set = true;
-    }
+    static SmemAttrOnce smem_attr;
+    HD_CUDA_OK(ensure_dyn_smem(smem_attr, wgrad_gemm_kernel, 225 * 1024));
     dim3 grid(splits, co_tiles * P.ci_tiles, P.taps);
     HD_CUDA_OK(hd::launch(wgrad_gemm_kernel, dim3(grid), dim3(kWThreads), smem, stream, P));
     HD_CUDA_OK(cudaPeekAtLastError());

@@ -1091,6 +1091,7 @@ def compute_retinanet_loss(targets, head_outputs, anchors, model, batched=True):
             valid_all = midx_all != model.head.classification_head.BETWEEN_THRESHOLDS
             fg_count = fg_all.sum(1)
             counts = torch.cat([fg_count, valid_all.sum(1)]).tolist()                                     # the one host sync
+            _run_deferred_checks()
         B = len(targets)
         matched_idxs = list(midx_all)
     else:
@@ -1173,6 +1174,7 @@ def eval_forward_retinanet(model, images, targets, train_det=False, model_name="
     _check_targets(targets)
     original_image_sizes = [tuple(img.shape[-2:]) for img in images]
     images, targets = model.transform(images, targets)
+    _assert_no_degenerate_boxes(targets)                  # src/utils/eval_forward_retinanet.py "Check for degenerate boxes"
     features = model.backbone(images.tensors)
     if isinstance(features, torch.Tensor):
         features = OrderedDict([("0", features)])
@@ -1192,4 +1194,5 @@ def eval_forward_retinanet(model, images, targets, train_det=False, model_name="
     else:
         detections = model.postprocess_detections(split_head_outputs, split_anchors, images.image_sizes)
     detections = model.transform.postprocess(detections, images.image_sizes, original_image_sizes)
+    _run_deferred_checks()
     return losses, detections

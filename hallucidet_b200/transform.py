@@ -41,7 +41,7 @@ class _ResizeFunction(torch.autograd.Function):
         return dx, None, None, None, None
 
 
-class GeneralizedRCNNTransform(nn.Module):
+class CustomGeneralizedRCNNTransform(nn.Module):
     def __init__(self, min_size, max_size, image_mean, image_std, size_divisible=32, fixed_size=None, **kwargs):
         super().__init__()
         if not isinstance(min_size, (list, tuple)):
@@ -118,3 +118,6 @@ class GeneralizedRCNNTransform(nn.Module):
     def __repr__(self):
         return (f"{self.__class__.__name__}(Normalize(mean={self.image_mean}, std={self.image_std}), "
                 f"Resize(fixed_size={self.fixed_size}, mode='nearest'))")
+
+
+GeneralizedRCNNTransform = CustomGeneralizedRCNNTransform      # round-1 name, kept for callers

@@ -136,6 +136,11 @@ class Unet(nn.Module):
             sigmoid = False
         else:
             raise NotImplementedError(f"segmentation head activation {type(head_act).__name__} is not implemented in the B200 path")
+        if x.requires_grad and torch.is_grad_enabled():
+            # HalluciDet feeds the IR image (a leaf without gradient, train_hallucidet.py:170-171); the stem computes no
+            # input gradient, so asking for one must not silently return zeros
+            raise NotImplementedError("hallucidet_b200.Unet does not compute the gradient w.r.t. its input image; "
+                                      "detach() the input (the reference never differentiates through the IR frame)")
         x = x.contiguous().float()
         eng = self._engine(x)
         params = [p for _, p in eng.named_params]
@@ -394,12 +399,25 @@ class _UnetEngine:
         self.generation += 1
         return self.hal.clone()
 
+    def _grads_alias_flat(self, params):
+        """True if some parameter's ``.grad`` lives inside ``flat_grad`` (autograd kept the views returned by an earlier
+        backward: ``zero_grad(set_to_none=False)``, gradient accumulation, Lightning's ``accumulate_grad_batches``)."""
+        lo = self.flat_grad.data_ptr()
+        hi = lo + self.flat_grad.numel() * 4
+        return any(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in params)
+
     def backward(self, dhal):
         self.dhal_in.copy_(dhal)
-        self._run("bwd", self._backward_impl)
         params = [p for _, p in self.named_params]
-        alias_ok = all(p.grad is None for p in params)
+        # The kernels OVERWRITE flat_grad.  If accumulated gradients live in it, they are set aside, the new gradients are
+        # handed to autograd as a separate tensor, and AccumulateGrad adds them in place: p.grad (still a view of
+        # flat_grad) ends up as old + new, as with any other module.
+        saved = self.flat_grad.clone() if self._grads_alias_flat(params) else None
+        self._run("bwd", self._backward_impl)
+        alias_ok = saved is None and all(p.grad is None for p in params)
         src = self.flat_grad if alias_ok else self.flat_grad.clone()
+        if saved is not None:
+            self.flat_grad.copy_(saved)
         out, off = [], 0
         for p in params:
             n = p.numel()

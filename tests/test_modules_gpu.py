@@ -556,3 +556,36 @@ def test_training_step_host_loss_matches_device_loss():
         out = tr.training_step(rgb, targets, ir, targets)
         assert isinstance(out["total_host"], HostScalar)
         assert float(out["total_host"]) == float(out["total"].detach()) == out["total_host"].item()
+
+
+def test_unet_grad_accumulation_and_zero_grad_in_place():
+    """``p.grad`` may alias the engine's flat gradient block.  A second backward without ``zero_grad`` must ADD
+    (gradient accumulation / Lightning accumulate_grad_batches), and ``zero_grad(set_to_none=False)`` followed by one backward
+    must leave exactly that backward's gradient -- as with the reference's ``smp.Unet``."""
+    m = make_unet().train()
+    gen = torch.Generator().manual_seed(5)
+    x1 = torch.rand(2, 3, 64, 64, generator=gen).cuda()
+    x2 = torch.rand(2, 3, 64, 64, generator=gen).cuda()
+
+    def grads_of(x, zero=True, set_to_none=True):
+        if zero:
+            m.zero_grad(set_to_none=set_to_none)
+        m(x).square().sum().backward()
+        torch.cuda.synchronize()
+        return torch.cat([p.grad.flatten() for p in m.parameters()]).clone()
+
+    def rel(a, b):
+        return float((a - b).norm() / (b.norm() + 1e-30))
+
+    g1, g2 = grads_of(x1), grads_of(x2)
+    grads_of(x1)
+    acc = grads_of(x2, zero=False)                       # second backward on top of the first
+    assert rel(acc, g1 + g2) < 2e-3, rel(acc, g1 + g2)
+    acc3 = grads_of(x1, zero=False)                      # and a third
+    assert rel(acc3, 2 * g1 + g2) < 2e-3
+    g1_again = grads_of(x1, zero=True, set_to_none=False)   # zeroed in place: p.grad still aliases the flat block
+    assert rel(g1_again, g1) < 2e-3, rel(g1_again, g1)
+    g2_again = grads_of(x2, zero=True, set_to_none=False)
+    assert rel(g2_again, g2) < 2e-3
+    with pytest.raises(NotImplementedError):
+        m(x1.clone().requires_grad_(True))
