@@ -28,8 +28,12 @@ METRIC = "train images/s (640x512 IR, bf16)"
 
 def load_traffic():
     """DRAM bytes of the largest tcgen05 conv launch from the committed `ncu --set full` capture (profiles/)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        d = json.load(open(files[-1]))
+        d["source"] = os.path.relpath(files[-1], ROOT)
+        return d
     except Exception:
         return {}
 
@@ -134,6 +138,84 @@ def cpu_baseline_sample(budget_s=25.0):
             "sample": f"{len(times)} train steps of B=1 512x640 S=640 (fp32 oracle port, torch CPU, {cores} threads), median"}
 
 
+def parity_step0(tr, ir, rgb, targets, detector_name, S):
+    """Checker leg (outside every timed region): the loss of the FIRST step -- the benchmark's own weights, inputs and
+    detector seed, before any optimizer update -- through the B200 path, next to the fp32 oracle's loss (oracle/step.py on the
+    same GPU, TF32 off) for the same state.  North-star gate: within 1 %."""
+    import torch
+    from oracle import detector as odet, step as ostep
+    dev = ir.device
+    state = {k: v.detach().clone() for k, v in tr.encoder_decoder.state_dict().items()}
+    was_training = tr.encoder_decoder.training
+    tr.encoder_decoder.train()
+    with torch.no_grad():
+        mine = float(tr.forward_step(rgb, targets, ir, targets, det_seed=7)["total"])
+    tr.encoder_decoder.load_state_dict(state)             # (the train-mode pass moved the BN running statistics)
+    tr.encoder_decoder.train(was_training)
+    tr.detector.backbone._engines.clear()                 # drop the no-grad activation set this pass allocated
+    det = odet.build_detector(detector_name, seed=123)
+    det.load_state_dict(tr.detector.state_dict())
+    det = det.to(dev)
+    flags = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = torch.backends.cudnn.benchmark = False
+    try:
+        ref = ostep.train_step(state, det, ir, rgb, targets, size=S, detector_name=detector_name, det_seed=7)
+        want = float(ref["loss"])
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = flags
+    del ref, det, state
+    torch.cuda.empty_cache()
+    return {"loss_step0": mine, "oracle_loss_step0": want, "rel": abs(mine - want) / abs(want), "tolerance": 0.01,
+            "oracle": "oracle/step.py fp32 on the same GPU, TF32 off, same weights / batch / detector seed 7"}
+
+
+def gpu_baseline_sample(B, S, detector_name, dev, steps=5):
+    """Baseline leg (after the timed regions; rank 0, N=1): the SAME train step through stock PyTorch on the same GPU -- the
+    oracle's restatement of the reference's modules via ATen / cuDNN with torch.autocast(bf16) + channels_last weights +
+    cudnn.benchmark + TF32 (SURVEY.md 8d iii: the best stock path, "the kernel to beat").  Not the product path."""
+    import torch
+    from oracle import unet as ou, detector as odet, step as ostep
+    from hallucidet_b200.synthetic import synthetic_batch
+    ir, rgb, targets = synthetic_batch(B, 512, 640, seed=123, device=dev)
+    state = {k: (v.to(dev).contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v.to(dev))
+             for k, v in ou.init_unet_state(123).items()}
+    det = odet.build_detector(detector_name, seed=123).to(dev).to(memory_format=torch.channels_last)
+    params = [v for k, v in state.items() if ou.is_param(k)]
+    opt = torch.optim.Adam(params, lr=1e-4, fused=True)
+    flags = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = torch.backends.cudnn.benchmark = True
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = ostep.train_step(state, det, ir, rgb, targets, size=S, detector_name=detector_name, det_seed=7)
+        torch.nn.utils.clip_grad_value_(params, 0.5)
+        opt.step()
+        return out["loss"]
+
+    try:
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        res = {"ms_per_step": ms, "value": B / ms * 1e3, "unit": "images/s", "steps": steps,
+               "kind": "stock PyTorch (oracle restatement through ATen/cuDNN): autocast(bf16) + channels_last + cudnn.benchmark + TF32, "
+                       "torchvision per-image detection tail, fused Adam + clip"}
+    except Exception as e:                                    # an op without a bf16 / channels_last kernel
+        res = {"error": repr(e)[:300]}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = flags
+    del state, det, opt, params
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -144,6 +226,8 @@ def main():
     ap.add_argument("--detector", default="fasterrcnn")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the step-0 loss check against the fp32 oracle")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-PyTorch (autocast bf16 + channels_last) leg")
     ap.add_argument("--pixel", default=None, help="enable the pixel regulariser (mse / l1); default off as in the reference config")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -173,6 +257,9 @@ def main():
     ir_h, rgb_h = ir_h.pin_memory(), rgb_h.pin_memory()
     targets = [{k: v.to(dev) for k, v in t.items()} for t in targets]
     ir_d, rgb_d = ir_h.to(dev), rgb_h.to(dev)
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_step0(tr, ir_d, rgb_d, targets, args.detector, S)
 
     def barrier():
         if world > 1:
@@ -306,7 +393,13 @@ def main():
                                           "gbs": sum(p[4] for p in c1) / (c1_ms * 1e-3) / 1e9 if c1_ms else None,
                                           "frac": sum(p[4] for p in c1) / (c1_ms * 1e-3) / 1e9 / hbm if c1_ms and hbm else None}},
             "loss": host_loss[-1] if host_loss else None,
+            "loss_note": "loss of the last timed step (the weights have moved by warm-up + timed optimizer steps); parity.* is step 0",
+            "parity": parity,
         }
+        if world == 1 and not args.no_gpu_baseline:
+            del tr
+            torch.cuda.empty_cache()
+            line["gpu_baseline"] = gpu_baseline_sample(B, S, args.detector, dev)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()
         else:

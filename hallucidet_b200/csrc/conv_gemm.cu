@@ -19,6 +19,7 @@
 #include <type_traits>
 
 #include "hd_common.cuh"
+#include "bn_tail.cuh"
 
 #include <cstring>
 
@@ -75,6 +76,8 @@ struct ConvGemmParams {
     int cp_mode;
     const __nv_bfloat16* a_ptr;
     int a_H, a_W, a_C;
+    int stat_floats;            // 2 x (padded output channels): this CTA's running BatchNorm partial sums, in shared memory
+    BnFin fin;                  // fused BatchNorm finalize (last CTA), fin.counter == nullptr: off
 };
 
 __device__ __forceinline__ void decode_tile(const ConvGemmParams& P, int tile, int& z, int& n0, int& img, int& h0, int& w0, int* mt_out = nullptr) {
@@ -108,12 +111,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const uint32_t stg_bytes = (128u * P.BN * 2u + 1023u) & ~1023u;
     const uint32_t staging0 = smem_base + static_cast<uint32_t>(stages * P.stage_bytes);  // 2 x (128 x BN bf16), 1024-aligned
     const uint32_t bias_s = staging0 + static_cast<uint32_t>(P.ring_bytes);               // bias of all output channels
-    const uint32_t bar_base = bias_s + 4u * static_cast<uint32_t>(P.bias_floats);
+    const uint32_t stat_s = bias_s + 4u * static_cast<uint32_t>(P.bias_floats);            // per-CTA BatchNorm partial sums
+    const uint32_t bar_base = stat_s + 4u * static_cast<uint32_t>(P.stat_floats);
     // barriers: full[s], empty[s], tmem_full[2], tmem_empty[2], then the TMEM base-address slot
     const uint32_t full0 = bar_base, empty0 = bar_base + 8u * stages;
     const uint32_t tfull0 = bar_base + 16u * stages, tempty0 = tfull0 + 16u;
     const uint32_t afull0 = tempty0 + 16u, aempty0 = afull0 + 16u;        // add / mask ring (aux_mode)
     const uint32_t tmem_slot = aempty0 + 16u;
+    const uint32_t fin_flag = tmem_slot + 8u;
     const int aux_ops = (P.add != nullptr ? 1 : 0) + (P.mask != nullptr ? 1 : 0);
     const uint32_t aux_buf_bytes = static_cast<uint32_t>(aux_ops) * stg_bytes;
 
@@ -360,6 +365,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * i), "f"(b) : "memory");
             }
         }
+        for (int i = et; i < P.stat_floats; i += kEpiThreads)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(stat_s + 4u * i), "f"(0.f) : "memory");
+        const uint32_t stat_half = 2u * static_cast<uint32_t>(P.stat_floats);      // byte offset of the sum-of-squares half
         named_bar_sync(2, kEpiThreads);
         int ab = 0;                                            // add / mask ring position (aux_mode)
         uint32_t aph = 0;
@@ -578,14 +586,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     }
                     const int ch = n0 + cl;
                     if (lane < ppw && ch < P.Cout_total) {
-                        float* st = P.stats + static_cast<long>(mt) * 2 * P.Cout_total;
-                        st[ch] = s0;
-                        st[ch + 1] = s1;
-                        st[P.Cout_total + ch] = q0;
-                        st[P.Cout_total + ch + 1] = q1;
+                        // added to this CTA's running sums: a channel of an N tile always belongs to the same (warp, lane),
+                        // tiles are visited in a fixed order -> deterministic, no synchronisation
+                        const uint32_t sa = stat_s + 4u * static_cast<uint32_t>(ch);
+                        float o0, o1, p0, p1;
+                        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(o0), "=f"(o1) : "r"(sa));
+                        asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(p0), "=f"(p1) : "r"(sa + stat_half));
+                        asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(sa), "f"(o0 + s0), "f"(o1 + s1) : "memory");
+                        asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(sa + stat_half), "f"(p0 + q0), "f"(p1 + q1) : "memory");
                     }
                 }
             }
+        }
+        if (P.stats != nullptr) {
+            // this CTA's statistics row (one per CTA of the persistent grid); surplus rows of the buffer are zeroed
+            named_bar_sync(1, kEpiThreads);
+            const int C = P.Cout_total;
+            for (int i = et; i < 2 * C; i += kEpiThreads) {
+                const int half = i >= C ? 1 : 0, c = i - half * C;
+                float v;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(stat_s + (half ? stat_half : 0u) + 4u * c));
+                P.stats[static_cast<long>(blockIdx.x) * 2 * C + i] = v;
+                for (int r = gridDim.x + blockIdx.x; r < P.stats_replicas; r += gridDim.x) P.stats[static_cast<long>(r) * 2 * C + i] = 0.f;
+            }
+            if (P.fin.counter != nullptr) bn_finalize_tail(P.fin, P.stats, gridDim.x, C, et, kEpiThreads, 1, fin_flag);
         }
         if (et == 0) tma_store_wait_all();
     }
@@ -677,6 +701,7 @@ static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStrea
     const int staging = P.stg_bufs * round_up(128 * P.BN * 2, 1024);   // output staging (double-buffered up to BN = 128)
     P.n_tiles = (P.Cout_total + P.BN - 1) / P.BN;
     P.bias_floats = round_up(P.n_tiles * P.BN, 128);               // bias of all (padded) output channels
+    P.stat_floats = P.stats != nullptr ? 2 * P.bias_floats : 0;    // per-CTA BatchNorm partial sums (sum | sum of squares)
     // without BatchNorm statistics (which are reduced from the staged tile) the epilogue stores from registers
     P.reg_store = (P.stats == nullptr && P.store_bf16 && P.out_ptr2[0] != nullptr && reg_store_enabled()) ? 1 : 0;
     const int n_ops = (P.add != nullptr ? 1 : 0) + (P.mask != nullptr ? 1 : 0);
@@ -687,12 +712,12 @@ static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStrea
         const int nk = (P.tap_begin[z + 1] - P.tap_begin[z]) * P.kpt / P.tps;
         if (nk > max_steps) max_steps = nk;
     }
-    const int stages_with_ring = (232448 - (1024 + 2 * n_ops * tile_bytes + 4 * P.bias_floats + 20 * 8 + 64)) / P.stage_bytes;
+    const int stages_with_ring = (232448 - (1024 + 2 * n_ops * tile_bytes + 4 * P.bias_floats + 4 * P.stat_floats + 20 * 8 + 64)) / P.stage_bytes;
     P.aux_mode = (P.reg_store && n_ops > 0 && !P.cp_mode && P.BN >= 16 && aux_mode_enabled() &&
                   stages_with_ring >= (max_steps <= 2 ? 2 : 3)) ? 1 : 0;
     // register-store epilogues need no output staging: the region becomes the two-deep add / mask ring (or nothing)
     P.ring_bytes = P.reg_store ? (P.aux_mode ? 2 * n_ops * tile_bytes : 0) : staging;
-    const int fixed = 1024 + P.ring_bytes + 4 * P.bias_floats + 20 * 8 + 64;   // alignment slack, ring, bias, barriers
+    const int fixed = 1024 + P.ring_bytes + 4 * P.bias_floats + 4 * P.stat_floats + 20 * 8 + 64;   // alignment slack, ring, bias, stats, barriers
     int stages = (232448 - fixed) / P.stage_bytes;              // 227 KB = the sm_100 per-block maximum
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
@@ -702,9 +727,13 @@ static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStrea
     P.tmem_cols = cols;
     P.m_tiles = P.tiles_w * P.tiles_h * n_img;
     P.n_tiles = (P.Cout_total + P.BN - 1) / P.BN;
-    if (P.stats != nullptr && P.stats_replicas < P.m_tiles) {
-        set_last_error(__FILE__, __LINE__, "stats buffer has fewer rows than output tiles (size it with hd_conv_fwd_tiles)");
-        return HD_ERR_BAD_ARG;
+    {
+        const long total_units = static_cast<long>(P.m_tiles) * P.n_tiles * nphases;
+        const int grid_rows = static_cast<int>(total_units < num_sms() ? total_units : num_sms());
+        if (P.stats != nullptr && P.stats_replicas < grid_rows) {
+            set_last_error(__FILE__, __LINE__, "stats buffer has fewer rows than CTAs (size it with hd_conv_fwd_tiles)");
+            return HD_ERR_BAD_ARG;
+        }
     }
     P.fd_per_phase = make_fastdiv(static_cast<uint32_t>(P.m_tiles * P.n_tiles));
     P.fd_m_tiles = make_fastdiv(static_cast<uint32_t>(P.m_tiles));
@@ -760,7 +789,10 @@ static int fill_epilogue(ConvGemmParams& P, const hd_conv_args* a) {
     P.relu = a->relu;
     P.sigmoid = a->sigmoid;
     P.stats = a->stats;
-    P.stats_replicas = a->stats_replicas;                  // rows available in the per-tile statistics buffer
+    P.stats_replicas = a->stats_replicas;                  // rows available in the statistics buffer (one per CTA is used)
+    P.fin = make_bn_fin(a->stats != nullptr ? a->bn_fin : nullptr);
+    HD_CHECK_ARG(a->bn_fin == nullptr || (a->stats != nullptr && a->bn_fin->counter != nullptr && a->bn_fin->scale != nullptr &&
+                                          a->bn_fin->shift != nullptr && a->bn_fin->gamma != nullptr && a->bn_fin->beta != nullptr));
     P.out_f32 = a->out_f32_nchw;
     P.out_f32_c = a->out_f32_channels;
     P.out_f32_nhwc = a->out_f32_nhwc;
@@ -851,7 +883,12 @@ extern "C" int hd_conv_fwd_tiles(const hd_conv_args* a) {
     const int Ho = a->x0.h / a->stride, Wo = a->x0.w / a->stride;
     int TW, TH;
     pick_tile(Ho, Wo, &TW, &TH);
-    return ((Wo + TW - 1) / TW) * ((Ho + TH - 1) / TH) * a->x0.n;
+    const long m_tiles = static_cast<long>((Wo + TW - 1) / TW) * ((Ho + TH - 1) / TH) * a->x0.n;
+    // one row per CTA of the persistent grid (<= SM count); without the output channel count the N-tile count is unknown
+    if (a->y0.c <= 0) return num_sms();
+    const int bn = maybe_bn256(pick_bn(a->y0.c), a->kh, a->y0.c, static_cast<int>(m_tiles));
+    const long units = m_tiles * ((a->y0.c + bn - 1) / bn);
+    return static_cast<int>(units < num_sms() ? units : num_sms());
 }
 
 extern "C" int hd_conv_dgrad(const hd_conv_args* a, hd_stream stream_) {

@@ -17,6 +17,7 @@
 #include <string.h>
 
 #include "hd_common.cuh"
+#include "bn_tail.cuh"
 
 namespace hd {
 
@@ -34,6 +35,7 @@ struct NarrowParams {
     const float* bias;
     float* stats;                // [stats_rows][2][NC] partial sum / sum of squares, one row per CTA (deterministic)
     int stats_rows;              // rows of the buffer (>= grid; the rows past the grid are written as zeros)
+    BnFin fin;                   // fused BatchNorm finalize by the last CTA (fin.counter == nullptr: off)
     float* out_f32;              // [N, out_f32_c, H, W]
     int out_f32_c;
     int relu, sigmoid, store_bf16, flip;
@@ -353,6 +355,10 @@ __global__ void __launch_bounds__(kNThreads, 2) narrow_conv_kernel(const NarrowP
                 P.stats[static_cast<long>(r) * 2 * NC + NC + ch] = 0.f;
             }
         }
+        if (P.fin.counter != nullptr) {
+            __syncthreads();                                  // `red` has been consumed: its first word becomes the "last CTA" flag
+            bn_finalize_tail(P.fin, P.stats, gridDim.x, NC, threadIdx.x, kNThreads, 1, smem_u32(red));
+        }
     }
 }
 
@@ -564,6 +570,7 @@ int narrow_conv_launch(const hd_conv_args* a, bool dgrad, cudaStream_t stream) {
     P.bias = a->bias;
     P.stats = a->stats;
     P.stats_rows = a->stats_replicas;
+    P.fin = make_bn_fin(a->stats != nullptr ? a->bn_fin : nullptr);
     P.out_f32 = a->out_f32_nchw;
     P.out_f32_c = a->out_f32_channels;
     P.relu = a->relu; P.sigmoid = a->sigmoid; P.store_bf16 = a->store_bf16;

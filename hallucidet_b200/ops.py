@@ -17,6 +17,7 @@ STEM_KPAD = 160          # 7*7*3 = 147 -> 5 k-blocks of 32
 
 LAUNCHES = 0             # kernels launched through this module (one per C-ABI compute call; nms / roi_align_bwd add their second)
 PROFILE = None           # set to a list to record (name, algorithmic FLOPs, start event, end event, shape, bytes) per launch
+RECORD = None            # set to a list to record the signature of every conv launch (launch_signature) -- parity tests replay them
 
 
 class _Timed:
@@ -132,7 +133,18 @@ def _conv_bytes(a, kind):
     return b + 2.0 * a.kh * a.kw * (a.x0.c + a.x1.c) * (a.y0.c + a.y1.c)
 
 
+def launch_signature(a, kind):
+    """Everything that selects a code path inside hd_conv_fwd / hd_conv_dgrad / hd_conv_wgrad for one launch: operand shapes,
+    filter, stride and which fused epilogue operands are present (hashable; the config-size parity tests replay each distinct one)."""
+    sh = lambda t: (t.n, t.h, t.w, t.c)
+    return (kind, sh(a.x0), a.x1.c, sh(a.y0), a.y1.c, a.kh, a.stride, bool(a.bias), bool(a.add), bool(a.mask), int(a.relu),
+            int(a.sigmoid), bool(a.stats), bool(a.out_f32_nchw), int(a.out_f32_channels), int(a.out_f32_nhwc), int(a.store_bf16),
+            int(a.phase_mask), bool(a.add) and a.add == a.y0.ptr)
+
+
 def _conv_timed(a, kind):
+    if RECORD is not None:
+        RECORD.append(launch_signature(a, kind))
     if PROFILE is None:
         return _Timed("conv_" + kind)
     t = _Timed("conv_" + kind + ("_narrow" if _is_narrow(a, kind) else ""), _conv_flops(a, kind), _conv_desc(a))

@@ -50,6 +50,24 @@ int hd_device_ok(void);               /* HD_OK iff the current device is sm_100 
  * The input may be the channel-concatenation of two tensors (x0 | x1) -- the U-Net skip concat
  * (decoders/unet/decoder.py:41) without materialising it; the dgrad output may be split the same way (y0 | y1).
  */
+/* Train-mode BatchNorm finalize fused into the tail of the producing convolution (hd_conv_args.bn_fin): the LAST CTA of
+ * hd_conv_fwd to finish sums the per-CTA statistics rows in a fixed order (fp64) and writes what hd_bn_finalize would:
+ * mean, invstd, scale = gamma*invstd, shift = beta - mean*scale, and the running statistics (momentum, unbiased variance)
+ * exactly as nn.BatchNorm2d (base/modules.py:42, TV: models/resnet.py:80-83).  Removes one latency-bound launch per layer. */
+typedef struct hd_bn_fin {
+    double count;             /* elements per channel (n*h*w of the conv output) */
+    const float* gamma;
+    const float* beta;
+    float* running_mean;      /* may be NULL */
+    float* running_var;       /* may be NULL */
+    float* mean;              /* outputs, fp32 [channels] */
+    float* invstd;
+    float* scale;
+    float* shift;
+    uint32_t* counter;        /* one device word per layer, zero before the first launch; the kernel leaves it zero */
+    float eps, momentum;
+} hd_bn_fin;
+
 typedef struct hd_conv_args {
     hd_act x0, x1;            /* fwd: input (x1.ptr NULL if unused).  dgrad: x0 = dY.  wgrad: input X */
     hd_act y0, y1;            /* fwd: output.  dgrad: dX (optionally split).  wgrad: y0 = dY (y1 unused) */
@@ -61,7 +79,7 @@ typedef struct hd_conv_args {
     const void* mask;         /* bf16 NHWC tensor shaped like y0: result zeroed where mask <= 0 (ReLU backward) */
     int32_t relu;
     int32_t sigmoid;          /* applied to the fp32 NCHW output only */
-    float* stats;             /* fp32 [stats_replicas][2][channels]: per-OUTPUT-TILE partial sum / sum-of-squares of the (bf16-rounded) output, one row per 128-pixel tile, written (not accumulated): deterministic, no memset needed; NULL = off */
+    float* stats;             /* fp32 [stats_replicas][2][channels]: partial sum / sum-of-squares of the (bf16-rounded) output, ONE ROW PER CTA of the persistent grid (each CTA adds up its own tiles in a fixed order), written (not accumulated), surplus rows zeroed: deterministic, no memset needed; NULL = off */
     int32_t stats_replicas;   /* rows available in `stats`; must be >= hd_conv_fwd_tiles(args) */
     float* out_f32_nchw;      /* optional fp32 NCHW copy of the output (first out_f32_channels channels) */
     int32_t out_f32_channels;
@@ -72,10 +90,11 @@ typedef struct hd_conv_args {
     int32_t split_k;          /* 0 = auto */
     int32_t out_f32_nhwc;     /* fwd: 1 = the fp32 copy (out_f32_nchw) is channels-last [n][h][w][out_f32_channels] instead of NCHW
                                  (out_f32_channels % 16 == 0, no sigmoid): what cuDNN and the RoIAlign kernels read without a transpose */
+    const hd_bn_fin* bn_fin;  /* fwd with stats: optional fused BatchNorm finalize (host pointer, copied at launch); NULL = off */
 } hd_conv_args;
 
 int hd_conv_fwd(const hd_conv_args* a, hd_stream stream);
-int hd_conv_fwd_tiles(const hd_conv_args* a);   /* number of output tiles (= statistics rows) hd_conv_fwd will use; host-only, no launch */
+int hd_conv_fwd_tiles(const hd_conv_args* a);   /* statistics rows hd_conv_fwd needs for this problem (= CTAs of its grid; with y0.c unset: an upper bound); host-only, no launch */
 int hd_conv_dgrad(const hd_conv_args* a, hd_stream stream);
 int hd_conv_wgrad(const hd_conv_args* a, hd_stream stream);
 

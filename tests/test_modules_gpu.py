@@ -578,14 +578,20 @@ def test_unet_grad_accumulation_and_zero_grad_in_place():
         return float((a - b).norm() / (b.norm() + 1e-30))
 
     g1, g2 = grads_of(x1), grads_of(x2)
+    # run-to-run noise of one gradient (fp32 atomics in the BatchNorm-backward sums and the split-K weight gradients are
+    # summed in a different order every run; the random-init network amplifies it, cf. test_unet_train_cuda_graph_matches_eager)
+    noise = max(rel(grads_of(x1), g1), rel(grads_of(x2), g2))
+    tol = max(2e-3, 4 * noise)
     grads_of(x1)
     acc = grads_of(x2, zero=False)                       # second backward on top of the first
-    assert rel(acc, g1 + g2) < 2e-3, rel(acc, g1 + g2)
+    print(f"\n[accumulate] run-to-run noise {noise:.2e}; acc vs g1+g2 {rel(acc, g1 + g2):.2e}; vs g2 alone {rel(acc, g2):.2e}")
+    assert rel(acc, g1 + g2) < tol, (rel(acc, g1 + g2), noise)
+    assert rel(acc, g2) > 10 * tol and rel(acc, 2 * g2) > 10 * tol        # neither "overwritten" nor "doubled" (the r1 bug)
     acc3 = grads_of(x1, zero=False)                      # and a third
-    assert rel(acc3, 2 * g1 + g2) < 2e-3
+    assert rel(acc3, 2 * g1 + g2) < tol
     g1_again = grads_of(x1, zero=True, set_to_none=False)   # zeroed in place: p.grad still aliases the flat block
-    assert rel(g1_again, g1) < 2e-3, rel(g1_again, g1)
+    assert rel(g1_again, g1) < tol, (rel(g1_again, g1), noise)
     g2_again = grads_of(x2, zero=True, set_to_none=False)
-    assert rel(g2_again, g2) < 2e-3
+    assert rel(g2_again, g2) < tol
     with pytest.raises(NotImplementedError):
         m(x1.clone().requires_grad_(True))
