@@ -33,6 +33,15 @@ class HdRoiLevel(ctypes.Structure):
                 ("scale", ctypes.c_float), ("pad_", ctypes.c_int32)]
 
 
+P_ = ctypes.POINTER
+
+
+class HdBnFin(ctypes.Structure):
+    _fields_ = [("count", c_double), ("gamma", c_void_p), ("beta", c_void_p), ("running_mean", c_void_p), ("running_var", c_void_p),
+                ("mean", c_void_p), ("invstd", c_void_p), ("scale", c_void_p), ("shift", c_void_p), ("counter", c_void_p),
+                ("eps", c_float), ("momentum", c_float)]
+
+
 class HdConvArgs(ctypes.Structure):
     _fields_ = [
         ("x0", HdAct), ("x1", HdAct), ("y0", HdAct), ("y1", HdAct),
@@ -44,6 +53,8 @@ class HdConvArgs(ctypes.Structure):
         ("out_f32_nchw", c_void_p), ("out_f32_channels", ctypes.c_int32),
         ("store_bf16", ctypes.c_int32), ("phase_mask", ctypes.c_int32),
         ("dw", c_void_p), ("split_k", ctypes.c_int32), ("out_f32_nhwc", ctypes.c_int32),
+        ("bn_fin", P_(HdBnFin)),
+        ("workspace", c_void_p), ("workspace_bytes", c_int64),
     ]
 
 
@@ -56,6 +67,8 @@ PROTOTYPES = {
     "hd_conv_fwd": [P(HdConvArgs), c_void_p],
     "hd_conv_fwd_tiles": [P(HdConvArgs)],
     "hd_conv_dgrad": [P(HdConvArgs), c_void_p],
+    "hd_conv_workspace_bytes": [],
+    "hd_conv_debug_timestamps": [c_void_p],
     "hd_conv_wgrad": [P(HdConvArgs), c_void_p],
     "hd_pack_conv_weight": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p],
     "hd_unpack_wgrad": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
@@ -67,6 +80,8 @@ PROTOTYPES = {
     "hd_bn_bwd_reduce": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p],
     "hd_bn_bwd_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
                         c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p],
+    "hd_bn_bwd_fused": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
+                        c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p],
     "hd_maxpool_fwd": [P(HdAct), P(HdAct), c_void_p, c_int, c_void_p],
     "hd_maxpool_bwd": [P(HdAct), P(HdAct), c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
     "hd_upsample2x_fwd": [P(HdAct), P(HdAct), c_void_p],
@@ -94,7 +109,7 @@ PROTOTYPES = {
     "hd_nhwc_to_nchw_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "hd_nms": [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p],
 }
-_RESTYPES = {"hd_last_error": ctypes.c_char_p}
+_RESTYPES = {"hd_last_error": ctypes.c_char_p, "hd_conv_workspace_bytes": ctypes.c_int64}
 
 _lib = None
 

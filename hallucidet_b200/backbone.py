@@ -64,6 +64,7 @@ class FrozenBackbone(nn.Module):
         for p in self.parameters():
             p.requires_grad_(False)
         self._engines = {}
+        self._last_engine = None
         self.use_cuda_graph = False
 
     @classmethod
@@ -80,6 +81,18 @@ class FrozenBackbone(nn.Module):
         else:
             raise NotImplementedError(f"FPN extra block {type(extra).__name__}")
         return cls(backbone.body, backbone.fpn, variant)
+
+    def bf16_features(self):
+        """The bf16 NHWC pyramid of the LATEST forward, in the order of the returned dict (valid until the next forward of the
+        same engine): what the frozen-head kernels read instead of the fp32 copies."""
+        last = getattr(self, "_last_engine", None)
+        if last is None or last[0].generation != last[1]:
+            return None
+        eng = last[0]
+        feats = [lv["layer"].y for lv in eng.levels] + [e["conv"].y for e in eng.extra]
+        if self.variant == "fasterrcnn":
+            feats.append(eng.pool_bf16)
+        return feats
 
     def refold(self):
         """Re-fold BatchNorm / re-pack operands after the frozen weights were (re)loaded."""
@@ -107,6 +120,7 @@ class FrozenBackbone(nn.Module):
             raise RuntimeError("hallucidet_b200.FrozenBackbone runs only on a CUDA (B200) device; there is no CPU path")
         x = x.contiguous().float()
         eng = self._engine(x)
+        self._last_engine = (eng, eng.generation + 1)
         outs = _BackboneFunction.apply(x, eng)
         names = list(eng.level_names)
         res = OrderedDict(zip(names, outs))
@@ -187,6 +201,9 @@ class _BackboneEngine:
             self.level_names += ["p6", "p7"]
             self.ones = torch.ones(256, device=device)
             self.zeros = torch.zeros(256, device=device)
+        else:
+            top = self.levels[-1]["layer"]
+            self.pool_bf16 = self.new_act((top.h + 1) // 2, (top.w + 1) // 2, top.cout)
         self.grad_bufs = {}
         self.dx = torch.empty(B, 3, H, W, device=device)
         self.dP_in = [torch.empty_like(lv["out"]) for lv in self.levels] + [torch.empty_like(e["out"]) for e in self.extra]
@@ -276,13 +293,15 @@ class _BackboneEngine:
             self._conv(lv["inner"], self.c_out[lv["li"]])
             if i < top:
                 ops.add_nearest_fwd(self.levels[i + 1]["inner"].y, lv["inner"].y)
-            need_bf16 = (i == top and self.variant == "retinanet")
-            self._conv(lv["layer"], lv["inner"].y, out_f32=lv["out"], store_bf16=need_bf16)
+            # bf16 copy of every pyramid level: the frozen heads (hallucidet_b200/heads.py) read it directly
+            self._conv(lv["layer"], lv["inner"].y, out_f32=lv["out"], store_bf16=True)
         if self.extra:
             p6, p7 = self.extra[0]["conv"], self.extra[1]["conv"]
             self._conv(p6, self.levels[top]["layer"].y, out_f32=self.extra[0]["out"])
             ops.bn_apply(p6.y, self.ones, self.zeros, self.p6_relu, relu=True)
-            self._conv(p7, self.p6_relu, out_f32=self.extra[1]["out"], store_bf16=False)
+            self._conv(p7, self.p6_relu, out_f32=self.extra[1]["out"], store_bf16=True)
+        else:
+            self.pool_bf16.copy_(self.levels[top]["layer"].y[:, ::2, ::2, :])            # LastLevelMaxPool of the bf16 pyramid
 
     # ---- backward (input gradient only) ---------------------------------------------------------------
     def backward(self, grads):

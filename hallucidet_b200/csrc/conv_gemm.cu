@@ -76,6 +76,16 @@ struct ConvGemmParams {
     int cp_mode;
     const __nv_bfloat16* a_ptr;
     int a_H, a_W, a_C;
+    // stream-K: the (tile, k-stage) iteration space is cut into gridDim.x equal contiguous ranges, one per CTA.  A range
+    // that starts inside a tile produces a PARTIAL accumulator (fp32, dumped to the CTA's workspace slot); the CTA that
+    // holds a tile's first k-stage adds the partials of the following CTAs in CTA order and runs the epilogue.
+    int streamk;                // 0 = off, else the grid size
+    int sk_nst;                 // k-stages per tile
+    int sk_tiles;               // m_tiles * n_tiles
+    FastDiv fd_sk_nst;
+    float* sk_ws;               // [gridDim.x][BN/16][4][128][4] fp32
+    unsigned int* sk_flags;     // [gridDim.x] 1 = the partial of CTA j is complete (reset by its consumer)
+    long long* dbg;             // optional [gridDim.x][8] globaltimer stamps (hd_conv_debug_timestamps; nullptr in production)
     int stat_floats;            // 2 x (padded output channels): this CTA's running BatchNorm partial sums, in shared memory
     BnFin fin;                  // fused BatchNorm finalize (last CTA), fin.counter == nullptr: off
 };
@@ -97,11 +107,60 @@ __device__ __forceinline__ void decode_tile(const ConvGemmParams& P, int tile, i
     if (mt_out) *mt_out = mt;
 }
 
+__device__ __forceinline__ void dbg_stamp(const ConvGemmParams& P, int slot) {
+    if (P.dbg != nullptr) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.dbg[static_cast<long>(blockIdx.x) * 8 + slot] = t;
+    }
+}
+
+// Work walker shared by all warp roles: classic mode = whole tiles, round-robin over the persistent CTAs; stream-K mode =
+// this CTA's contiguous range of the linearised (tile, k-stage) space, cut at tile boundaries into segments.
+struct Seg {
+    int tile, sb, se, nst;      // k-stages [sb, se) of `tile`, which has nst stages in total
+};
+struct SegWalk {
+    long it, it_end;
+    int tile;
+};
+__device__ __forceinline__ long sk_range_begin(const ConvGemmParams& P, int cta) {
+    return static_cast<long>(cta) * (static_cast<long>(P.sk_tiles) * P.sk_nst) / gridDim.x;
+}
+__device__ __forceinline__ void walk_init(const ConvGemmParams& P, SegWalk& w) {
+    if (P.streamk) {
+        w.it = sk_range_begin(P, blockIdx.x);
+        w.it_end = sk_range_begin(P, blockIdx.x + 1);
+    }
+    w.tile = blockIdx.x;
+}
+__device__ __forceinline__ bool walk_next(const ConvGemmParams& P, SegWalk& w, Seg& s) {
+    if (P.streamk) {
+        if (w.it >= w.it_end) return false;
+        s.tile = static_cast<int>(fdiv(static_cast<uint32_t>(w.it), P.fd_sk_nst));
+        s.sb = static_cast<int>(w.it - static_cast<long>(s.tile) * P.sk_nst);
+        s.nst = P.sk_nst;
+        const long rem = w.it_end - w.it;
+        s.se = (rem < P.sk_nst - s.sb) ? s.sb + static_cast<int>(rem) : P.sk_nst;
+        w.it += s.se - s.sb;
+        return true;
+    }
+    if (w.tile >= P.m_tiles * P.n_tiles * P.nphases) return false;
+    s.tile = w.tile;
+    w.tile += gridDim.x;
+    const int z = static_cast<int>(fdiv(s.tile, P.fd_per_phase));
+    s.nst = (P.tap_begin[z + 1] - P.tap_begin[z]) * P.kpt / P.tps;
+    s.sb = 0;
+    s.se = s.nst;
+    return true;
+}
+
 // Persistent CTA (one per SM): a static round-robin over output tiles; the TMA producer and the MMA issuer run
 // ahead across tile boundaries, the accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the
 // main loop of tile i+1.
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams P) {
     pdl_trigger();                 // the next kernel may become resident as our CTAs drain (it waits for our results itself)
+    if (threadIdx.x == 0) dbg_stamp(P, 0);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5;
@@ -148,6 +207,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
     pdl_wait();                    // everything above overlapped the previous kernel's tail; its results are needed from here on
+    if (threadIdx.x == 0) dbg_stamp(P, 1);
 
     const int total_tiles = P.m_tiles * P.n_tiles * P.nphases;
 
@@ -157,12 +217,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const uint32_t tx_bytes = static_cast<uint32_t>(((P.cp_mode ? 0 : P.TW * P.TH) + P.BN) * P.BK * 2) * P.tps;
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            SegWalk wk;
+            Seg sg;
+            walk_init(P, wk);
+            while (walk_next(P, wk, sg)) {
                 int z, n0, img, h0, w0;
-                decode_tile(P, tile, z, n0, img, h0, w0);
-                int tap = P.tap_begin[z], kb = 0;
-                const int num_k = (P.tap_begin[z + 1] - tap) * P.kpt;
-                for (int ks = 0; ks < num_k; ks += P.tps) {
+                decode_tile(P, sg.tile, z, n0, img, h0, w0);
+                const int ks0 = sg.sb * P.tps;
+                int tap = P.tap_begin[z] + ks0 / P.kpt, kb = ks0 % P.kpt;
+                for (int st = sg.sb; st < sg.se; ++st) {
                     mbar_wait(empty0 + 8u * stage, phase ^ 1u);
                     const uint32_t sa = smem_base + stage * P.stage_bytes;
                     const uint32_t sb = sa + P.a_bytes;
@@ -179,6 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
             }
+            dbg_stamp(P, 2);                                         // last TMA load issued
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
@@ -197,15 +261,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int z = static_cast<int>(fdiv(tile, P.fd_per_phase));
-                const int num_st = (P.tap_begin[z + 1] - P.tap_begin[z]) * P.kpt / tps;
+            SegWalk wk;
+            Seg sg;
+            walk_init(P, wk);
+            while (walk_next(P, wk, sg)) {
+                const int num_st = sg.se - sg.sb;
                 mbar_wait(tempty0 + 8u * acc, acc_phase ^ 1u);          // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * P.tmem_cols;
                 uint32_t accum = 0;
                 for (int st = 0; st < num_st; ++st) {
                     mbar_wait(full0 + 8u * stage, phase);
+                    if (P.dbg != nullptr && P.dbg[static_cast<long>(blockIdx.x) * 8 + 3] == 0) dbg_stamp(P, 3);   // first operands landed
                     if (P.cp_mode) fence_proxy_async_smem();   // cp.async wrote the A tile through the generic proxy
                     tc_fence_after();
                     const uint32_t a_u = base_u + stage * stage_u, b_u = a_u + a_bytes_u;
@@ -229,6 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 umma_commit(tfull0 + 8u * acc);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
+            dbg_stamp(P, 4);                                         // last MMA issued
         }
     } else if (warp >= 2 + kEpiWarps) {
         if (P.aux_mode) {
@@ -242,9 +310,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const uint32_t row_bytes = static_cast<uint32_t>(P.BN) * 2u;
             int b = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            SegWalk wk;
+            Seg sg;
+            walk_init(P, wk);                                     // (aux_mode is never combined with stream-K: whole tiles)
+            while (walk_next(P, wk, sg)) {
                 int z, n0, img, h0, w0;
-                decode_tile(P, tile, z, n0, img, h0, w0);
+                decode_tile(P, sg.tile, z, n0, img, h0, w0);
                 mbar_wait(aempty0 + 8u * b, ph ^ 1u);
                 const uint32_t dst_add = staging0 + b * aux_buf_bytes;
                 const uint32_t dst_mask = dst_add + (P.add != nullptr ? stg_bytes : 0u);
@@ -295,9 +366,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            SegWalk wk;
+            Seg sg;
+            walk_init(P, wk);                                     // (cp_mode is never combined with stream-K: whole tiles)
+            while (walk_next(P, wk, sg)) {
                 int z, n0, img, h0, w0;
-                decode_tile(P, tile, z, n0, img, h0, w0);
+                decode_tile(P, sg.tile, z, n0, img, h0, w0);
                 int tap = P.tap_begin[z], kb = 0;
                 const int num_k = (P.tap_begin[z + 1] - tap) * P.kpt;
                 const __nv_bfloat16* tile_base = P.a_ptr + ((static_cast<long>(img) * P.a_H + h0) * P.a_W + w0) * P.a_C;
@@ -377,10 +451,52 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         int acc = 0;
         uint32_t acc_phase = 0;
         int iter = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        SegWalk wk;
+        Seg sg;
+        walk_init(P, wk);
+        const long sk_slot_floats = 128L * P.BN;
+        while (walk_next(P, wk, sg)) {
+            if (P.streamk && sg.sb != 0) {
+                // ---- stream-K partial: this CTA's range starts inside the tile.  Dump the raw fp32 accumulator into this
+                // CTA's workspace slot ([chunk][quarter][row][4 floats]: every warp store is 512 contiguous bytes) and flag it.
+                mbar_wait(tfull0 + 8u * acc, acc_phase);
+                tc_fence_after();
+                const uint32_t t_acc = tmem_base + acc * P.tmem_cols + (static_cast<uint32_t>(quad * 32) << 16);
+                float4* slot = reinterpret_cast<float4*>(P.sk_ws + static_cast<long>(blockIdx.x) * sk_slot_floats);
+                for (int c16 = c_begin; c16 < c_end; ++c16) {
+                    uint32_t r[16];
+                    tmem_ld16(t_acc + c16 * 16, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        slot[(c16 * 4 + q) * 128 + row] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                                      __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                __threadfence();
+                named_bar_sync(1, kEpiThreads);
+                if (et == 0) {
+                    __threadfence();
+                    atomicExch(P.sk_flags + blockIdx.x, 1u);
+                }
+                continue;
+            }
+            // stream-K head segment that does not cover the whole tile: the following CTAs hold the rest (their first segment)
+            int np = 0, pj[4];
+            if (P.streamk && sg.se < sg.nst) {
+                int rem = sg.nst - sg.se;
+                for (int j = blockIdx.x + 1; rem > 0 && np < 4; ++j) {
+                    const long len = sk_range_begin(P, j + 1) - sk_range_begin(P, j);
+                    pj[np++] = j;
+                    rem -= static_cast<int>(len < rem ? len : rem);
+                }
+            }
             int z, n0, img, h0, w0, mt;
-            decode_tile(P, tile, z, n0, img, h0, w0, &mt);
-            const int num_k = (P.tap_begin[z + 1] - P.tap_begin[z]) * P.kpt;
+            decode_tile(P, sg.tile, z, n0, img, h0, w0, &mt);
+            const int num_k = sg.se - sg.sb;
             const int hg = h0 + hl, wg = w0 + wl;
             const bool valid = (row < P.TW * P.TH) && hg < P.Hg && wg < P.Wg;
             const int ho = hg * P.ostride + P.out_p[z], wo = wg * P.ostride + P.out_q[z];
@@ -389,11 +505,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const __nv_bfloat16* add_row = P.add != nullptr ? P.add + pix * P.Cout_total + n0 : nullptr;
             const __nv_bfloat16* mask_row = P.mask != nullptr ? P.mask + pix * P.Cout_total + n0 : nullptr;
 
-            if (!P.reg_store) {
-                // this staging buffer was last used two tiles ago: its TMA store must have finished reading it
+            if (!P.reg_store || np > 0) {
                 if (et == 0) {
-                    if (P.stg_bufs == 2) { if (iter >= 2) tma_store_wait_read1(); }
-                    else if (iter >= 1) tma_store_wait_read();
+                    if (!P.reg_store) {
+                        // this staging buffer was last used two tiles ago: its TMA store must have finished reading it
+                        if (P.stg_bufs == 2) { if (iter >= 2) tma_store_wait_read1(); }
+                        else if (iter >= 1) tma_store_wait_read();
+                    }
+                    for (int i = 0; i < np; ++i) {                      // stream-K: the partner partials have landed
+                        const volatile unsigned int* f = P.sk_flags + pj[i];
+                        while (*f == 0u) __nanosleep(32);
+                    }
+                    if (np > 0) __threadfence();
                 }
                 named_bar_sync(1, kEpiThreads);
             }
@@ -407,6 +530,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             if (P.aux_mode) mbar_wait(afull0 + 8u * ab, aph);
             mbar_wait(tfull0 + 8u * acc, acc_phase);
             tc_fence_after();
+            if (et == 0) dbg_stamp(P, 5);                            // accumulator of this (so far last) tile complete
             const uint32_t t_acc = tmem_base + acc * P.tmem_cols + (static_cast<uint32_t>(quad * 32) << 16);
             // the chunk loop is instantiated twice: the common plain epilogue (bias / ReLU / bf16 store) carries none of the
             // fused-operand or fp32-output bookkeeping
@@ -445,6 +569,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 float v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc_r[j]);
+                for (int i = 0; i < np; ++i) {                          // + the partner partials, in CTA order (deterministic)
+                    const float4* slot = reinterpret_cast<const float4*>(P.sk_ws + static_cast<long>(pj[i]) * sk_slot_floats);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 t = __ldcg(slot + (c16 * 4 + q) * 128 + row);
+                        v[4 * q] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+                    }
+                }
                 if (P.bias != nullptr) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
@@ -532,6 +664,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 if (++ab == 2) { ab = 0; aph ^= 1u; }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            if (np > 0) {
+                // every epilogue thread has consumed the partner partials: hand the slots back (next launch / next tile)
+                named_bar_sync(3, kEpiThreads);
+                if (et == 0)
+                    for (int i = 0; i < np; ++i) atomicExch(P.sk_flags + pj[i], 0u);
+            }
+            ++iter;
 
             if (P.store_bf16 && !P.reg_store) {
                 fence_proxy_async_smem();
@@ -612,8 +751,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             if (P.fin.counter != nullptr) bn_finalize_tail(P.fin, P.stats, gridDim.x, C, et, kEpiThreads, 1, fin_flag);
         }
         if (et == 0) tma_store_wait_all();
+        if (et == 0) dbg_stamp(P, 6);                                // epilogue (incl. statistics / finalize) done
     }
     __syncthreads();
+    if (threadIdx.x == 0) dbg_stamp(P, 7);
     if (warp == 1) tmem_dealloc(tmem_base, 2 * P.tmem_cols);
 }
 
@@ -679,7 +820,23 @@ static bool aux_mode_enabled() {
     return on != 0;
 }
 
-static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStream_t stream) {
+static long long* g_conv_dbg = nullptr;
+
+static bool streamk_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("HD_STREAMK");
+        on = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
+}
+
+// Workspace layout (caller-owned, zero-initialised once): [0, 4 KB) = per-CTA flags, then one 128 x 256 fp32 slot per CTA.
+constexpr size_t kSkFlagBytes = 4096;
+constexpr size_t kSkSlotBytes = 128 * 256 * sizeof(float);
+
+static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStream_t stream, void* workspace = nullptr,
+                            size_t workspace_bytes = 0) {
     P.a_sub = round_up(128 * P.BK * 2, 1024);
     P.b_sub = round_up(P.BN * P.BK * 2, 1024);
     // narrow-channel layers: group several (tap, k-block) steps per stage so that one mbarrier round trip moves
@@ -702,6 +859,30 @@ static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStrea
     P.n_tiles = (P.Cout_total + P.BN - 1) / P.BN;
     P.bias_floats = round_up(P.n_tiles * P.BN, 128);               // bias of all (padded) output channels
     P.stat_floats = P.stats != nullptr ? 2 * P.bias_floats : 0;    // per-CTA BatchNorm partial sums (sum | sum of squares)
+    // stream-K when whole tiles quantise badly onto the SMs (one or two under-filled waves) and K is long enough to cut
+    P.streamk = 0;
+    P.m_tiles = P.tiles_w * P.tiles_h * n_img;
+    if (nphases == 1 && !P.cp_mode && P.tps == 1 && workspace != nullptr && streamk_enabled()) {
+        const int sms = num_sms();
+        const int nst = (P.tap_begin[1] - P.tap_begin[0]) * P.kpt;
+        const long tiles = static_cast<long>(P.m_tiles) * P.n_tiles;
+        const long waves = (tiles + sms - 1) / sms;
+        const long T = tiles * nst;
+        // a tile is shared by at most 4 CTAs (head + 3 partials): every CTA range covers at least a third of a tile
+        long G = sms;
+        if (G > 3 * tiles) G = 3 * tiles;
+        if (G > T / 4) G = T / 4;
+        const long per = G > 0 ? T / G : 0;
+        if (tiles * 100 < waves * sms * 85 && nst >= 8 && G > tiles && per >= 4 && per * 3 >= nst && T < (1l << 31) / sms &&
+            workspace_bytes >= kSkFlagBytes + static_cast<size_t>(sms) * kSkSlotBytes && sms * sizeof(unsigned int) <= kSkFlagBytes) {
+            P.streamk = static_cast<int>(G);            // = grid size
+            P.sk_nst = nst;
+            P.sk_tiles = static_cast<int>(tiles);
+            P.fd_sk_nst = make_fastdiv(static_cast<uint32_t>(nst));
+            P.sk_flags = static_cast<unsigned int*>(workspace);
+            P.sk_ws = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + kSkFlagBytes);
+        }
+    }
     // without BatchNorm statistics (which are reduced from the staged tile) the epilogue stores from registers
     P.reg_store = (P.stats == nullptr && P.store_bf16 && P.out_ptr2[0] != nullptr && reg_store_enabled()) ? 1 : 0;
     const int n_ops = (P.add != nullptr ? 1 : 0) + (P.mask != nullptr ? 1 : 0);
@@ -713,7 +894,7 @@ static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStrea
         if (nk > max_steps) max_steps = nk;
     }
     const int stages_with_ring = (232448 - (1024 + 2 * n_ops * tile_bytes + 4 * P.bias_floats + 4 * P.stat_floats + 20 * 8 + 64)) / P.stage_bytes;
-    P.aux_mode = (P.reg_store && n_ops > 0 && !P.cp_mode && P.BN >= 16 && aux_mode_enabled() &&
+    P.aux_mode = (P.reg_store && n_ops > 0 && !P.cp_mode && !P.streamk && P.BN >= 16 && aux_mode_enabled() &&
                   stages_with_ring >= (max_steps <= 2 ? 2 : 3)) ? 1 : 0;
     // register-store epilogues need no output staging: the region becomes the two-deep add / mask ring (or nothing)
     P.ring_bytes = P.reg_store ? (P.aux_mode ? 2 * n_ops * tile_bytes : 0) : staging;
@@ -729,7 +910,7 @@ static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStrea
     P.n_tiles = (P.Cout_total + P.BN - 1) / P.BN;
     {
         const long total_units = static_cast<long>(P.m_tiles) * P.n_tiles * nphases;
-        const int grid_rows = static_cast<int>(total_units < num_sms() ? total_units : num_sms());
+        const int grid_rows = P.streamk ? num_sms() : static_cast<int>(total_units < num_sms() ? total_units : num_sms());
         if (P.stats != nullptr && P.stats_replicas < grid_rows) {
             set_last_error(__FILE__, __LINE__, "stats buffer has fewer rows than CTAs (size it with hd_conv_fwd_tiles)");
             return HD_ERR_BAD_ARG;
@@ -742,11 +923,13 @@ static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStrea
     P.fd_TW = make_fastdiv(static_cast<uint32_t>(P.TW));
     P.direct_store = (P.BN < 64 && P.Cout_total == P.BN && P.out_C0 == P.Cout_total && P.out_ptr != nullptr) ? 1 : 0;
     P.nphases = nphases;
+    P.dbg = g_conv_dbg;
     const size_t smem = static_cast<size_t>(fixed) + static_cast<size_t>(stages) * P.stage_bytes;
     static SmemAttrOnce smem_attr;
     HD_CUDA_OK(ensure_dyn_smem(smem_attr, conv_gemm_kernel, 232448));
     const long total = static_cast<long>(P.m_tiles) * P.n_tiles * nphases;
-    const int grid = static_cast<int>(total < num_sms() ? total : num_sms());
+    int grid = static_cast<int>(total < num_sms() ? total : num_sms());
+    if (P.streamk) grid = P.streamk;
     HD_CUDA_OK(hd::launch(conv_gemm_kernel, dim3(grid), dim3(kThreads), smem, stream, P));
     HD_CUDA_OK(cudaPeekAtLastError());
     return HD_OK;
@@ -872,7 +1055,7 @@ extern "C" int hd_conv_fwd(const hd_conv_args* a, hd_stream stream_) {
     P.tmOut[1] = P.tmOut[0];
     P.out_ptr = static_cast<__nv_bfloat16*>(a->y0.ptr);
     P.out_ptr2[0] = P.out_ptr; P.out_ptr2[1] = nullptr;
-    return launch_conv_gemm(P, N, 1, stream);
+    return launch_conv_gemm(P, N, 1, stream, a->workspace, static_cast<size_t>(a->workspace_bytes));
 }
 
 extern "C" int hd_conv_fwd_tiles(const hd_conv_args* a) {
@@ -888,6 +1071,7 @@ extern "C" int hd_conv_fwd_tiles(const hd_conv_args* a) {
     if (a->y0.c <= 0) return num_sms();
     const int bn = maybe_bn256(pick_bn(a->y0.c), a->kh, a->y0.c, static_cast<int>(m_tiles));
     const long units = m_tiles * ((a->y0.c + bn - 1) / bn);
+    if (streamk_enabled()) return num_sms();              // stream-K launches use every SM whatever the tile count
     return static_cast<int>(units < num_sms() ? units : num_sms());
 }
 
@@ -981,5 +1165,17 @@ extern "C" int hd_conv_dgrad(const hd_conv_args* a, hd_stream stream_) {
     P.out_ptr = two ? nullptr : static_cast<__nv_bfloat16*>(a->y0.ptr);
     P.out_ptr2[0] = static_cast<__nv_bfloat16*>(a->y0.ptr);
     P.out_ptr2[1] = two ? static_cast<__nv_bfloat16*>(a->y1.ptr) : nullptr;
-    return launch_conv_gemm(P, N, nph, stream);
+    return launch_conv_gemm(P, N, nph, stream, a->workspace, static_cast<size_t>(a->workspace_bytes));
+}
+
+extern "C" int64_t hd_conv_workspace_bytes(void) {
+    // stream-K scratch for hd_conv_fwd / hd_conv_dgrad (hd_conv_args.workspace): flags + one fp32 partial tile per SM
+    return static_cast<int64_t>(kSkFlagBytes + static_cast<size_t>(num_sms() > 148 ? num_sms() : 148) * kSkSlotBytes);
+}
+
+extern "C" int hd_conv_debug_timestamps(void* buf) {
+    // development aid: subsequent hd_conv_fwd / hd_conv_dgrad launches write 8 %globaltimer stamps per CTA into buf
+    // ([grid][8] int64, zeroed by the caller; slot 3 must be zero before each launch); NULL turns it off
+    g_conv_dbg = static_cast<long long*>(buf);
+    return HD_OK;
 }

@@ -515,6 +515,188 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(const __nv_bfl
 }
 
 // -------------------------------------------------------------------------------------------------
+// Fused train-mode BatchNorm backward: reduce + apply in ONE persistent kernel (one CTA per SM, all co-resident).
+//   phase 1: every CTA reduces its contiguous pixel slice (sum g, sum g*xhat with the ReLU mask folded into g) and adds its
+//            partial sums to sums[2][C]; when the slice fits, the masked g and z stay in shared memory;
+//   grid barrier (sense-reversing counter, self-resetting: safe under stream order and CUDA-graph replay);
+//   phase 2: dz = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)) from shared memory (small layers: g and z are read from
+//            HBM/L2 exactly once) or by re-reading the slice (large layers: second read served mostly by the 126 MB L2).
+// One launch instead of two per BatchNorm layer, 3 instead of 5 tensor passes for the 33 layers whose slice fits on chip.
+// -------------------------------------------------------------------------------------------------
+constexpr int kBnFusedThreads = 512;
+constexpr int kBnUnroll = 4;
+
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile unsigned int* vgen = bar + 1;
+        const unsigned int gen = *vgen;                    // generation before arriving: the release cannot be missed
+        __threadfence();
+        const unsigned int prev = atomicAdd(bar, 1u);
+        if (prev == nblocks - 1u) {
+            bar[0] = 0u;                                   // nobody arrives again before the release below
+            __threadfence();
+            atomicAdd(bar + 1, 1u);
+        } else {
+            while (*vgen == gen) __nanosleep(40);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kBnFusedThreads, 1)
+bn_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ yrelu, const float* __restrict__ rscale,
+                    const float* __restrict__ rshift, const __nv_bfloat16* __restrict__ z, const float* __restrict__ mean,
+                    const float* __restrict__ invstd, const float* __restrict__ gamma, float* sums, float inv_count,
+                    __nv_bfloat16* __restrict__ dz, __nv_bfloat16* __restrict__ gout, float* dgamma, float* dbeta, long n_pix, int C,
+                    long pix_per_block, int cache, unsigned int* bar) {
+    pdl_trigger();
+    extern __shared__ __align__(16) uint8_t bsm[];
+    float* sacc = reinterpret_cast<float*>(bsm);                       // [2][C]
+    uint4* cache_g = reinterpret_cast<uint4*>(bsm + 2 * C * sizeof(float));
+    const int G = C / 8;
+    const int L = kBnFusedThreads / G;                                 // pixel lanes
+    const int g = threadIdx.x % G, l = threadIdx.x / G;
+    const long p0 = blockIdx.x * pix_per_block;
+    long p1 = p0 + pix_per_block;
+    if (p1 > n_pix) p1 = n_pix;
+    const int iters = static_cast<int>((pix_per_block + L - 1) / L);   // slice-local steps of this thread (cache index)
+    uint4* cache_z = cache_g + static_cast<long>(iters) * kBnFusedThreads;
+    for (int i = threadIdx.x; i < 2 * C; i += kBnFusedThreads) sacc[i] = 0.f;
+    pdl_wait();
+    float a[8], b[8], mu[8], is[8], rs[8], rb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        a[j] = 0.f; b[j] = 0.f; mu[j] = __ldg(mean + g * 8 + j); is[j] = __ldg(invstd + g * 8 + j);
+        rs[j] = rscale ? __ldg(rscale + g * 8 + j) : 0.f; rb[j] = rscale ? __ldg(rshift + g * 8 + j) : 0.f;
+    }
+    __syncthreads();
+    // ---- phase 1
+    for (int it0 = 0; it0 < iters; it0 += kBnUnroll) {
+        bf8 d[kBnUnroll], zz[kBnUnroll], yy[kBnUnroll];
+        bool on[kBnUnroll];
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            const long p = p0 + l + static_cast<long>(it0 + u) * L;
+            on[u] = (it0 + u) < iters && p < p1;
+            if (on[u]) {
+                const long off = p * C + g * 8;
+                d[u].load(dy + off);
+                zz[u].load(z + off);
+                if (yrelu) yy[u].load(yrelu + off);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            if (!on[u]) continue;
+            float df[8], zf[8];
+            d[u].unpack(df);
+            zz[u].unpack(zf);
+            if (yrelu) {
+                float yf[8];
+                yy[u].unpack(yf);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (!(yf[j] > 0.f)) df[j] = 0.f;
+            } else if (rscale) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (!(fmaf(zf[j], rs[j], rb[j]) > 0.f)) df[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a[j] += df[j]; b[j] += df[j] * (zf[j] - mu[j]) * is[j]; }
+            if (cache) {
+                bf8 gm;
+                gm.pack(df);                                           // masking only zeroes values: exact in bf16
+                cache_g[static_cast<long>(it0 + u) * kBnFusedThreads + threadIdx.x] = gm.u;
+                cache_z[static_cast<long>(it0 + u) * kBnFusedThreads + threadIdx.x] = zz[u].u;
+            }
+        }
+    }
+    if (G < 32) {                                                      // lanes sharing a channel group inside the warp
+        for (int o = 16; o >= G; o >>= 1) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                a[j] += __shfl_xor_sync(0xffffffffu, a[j], o);
+                b[j] += __shfl_xor_sync(0xffffffffu, b[j], o);
+            }
+        }
+        if ((threadIdx.x & 31) < G) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { atomicAdd(&sacc[g * 8 + j], a[j]); atomicAdd(&sacc[C + g * 8 + j], b[j]); }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { atomicAdd(&sacc[g * 8 + j], a[j]); atomicAdd(&sacc[C + g * 8 + j], b[j]); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += kBnFusedThreads) atomicAdd(&sums[i], sacc[i]);
+    grid_barrier(bar, gridDim.x);
+    // ---- phase 2
+    if (blockIdx.x == 0) {
+        for (int c = threadIdx.x; c < C; c += kBnFusedThreads) {
+            if (dbeta) dbeta[c] = __ldcg(sums + c);
+            if (dgamma) dgamma[c] = __ldcg(sums + C + c);
+        }
+    }
+    float ca[8], cb[8], cd[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = g * 8 + j;
+        const float k1 = __ldg(gamma + c) * is[j];
+        const float m1 = __ldcg(sums + c) * inv_count, m2 = __ldcg(sums + C + c) * inv_count;
+        ca[j] = k1; cb[j] = -k1 * is[j] * m2; cd[j] = k1 * (is[j] * m2 * mu[j] - m1);
+    }
+    for (int it0 = 0; it0 < iters; it0 += kBnUnroll) {
+        bf8 d[kBnUnroll], zz[kBnUnroll], yy[kBnUnroll];
+        bool on[kBnUnroll];
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            const long p = p0 + l + static_cast<long>(it0 + u) * L;
+            on[u] = (it0 + u) < iters && p < p1;
+            if (!on[u]) continue;
+            if (cache) {
+                d[u].u = cache_g[static_cast<long>(it0 + u) * kBnFusedThreads + threadIdx.x];
+                zz[u].u = cache_z[static_cast<long>(it0 + u) * kBnFusedThreads + threadIdx.x];
+            } else {
+                const long off = p * C + g * 8;
+                d[u].load(dy + off);
+                zz[u].load(z + off);
+                if (yrelu) yy[u].load(yrelu + off);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            if (!on[u]) continue;
+            const long off = (p0 + l + static_cast<long>(it0 + u) * L) * C + g * 8;
+            float df[8], zf[8], o[8];
+            d[u].unpack(df);
+            zz[u].unpack(zf);
+            if (!cache) {
+                if (yrelu) {
+                    float yf[8];
+                    yy[u].unpack(yf);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) if (!(yf[j] > 0.f)) df[j] = 0.f;
+                } else if (rscale) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) if (!(fmaf(zf[j], rs[j], rb[j]) > 0.f)) df[j] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(ca[j], df[j], fmaf(cb[j], zf[j], cd[j]));
+            bf8 ov;
+            ov.pack(o);
+            ov.store(dz + off);
+            if (gout) {
+                bf8 gv;
+                gv.pack(df);
+                gv.store(gout + off);
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
 // max-pool 3x3 stride 2 pad 1 (NHWC)
 // -------------------------------------------------------------------------------------------------
 __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
@@ -1191,6 +1373,40 @@ extern "C" int hd_bn_bwd_apply(const void* dy, const void* yrelu, const float* r
         static_cast<const __nv_bfloat16*>(z), mean, invstd, gamma, sums, static_cast<float>(1.0 / count),
         static_cast<__nv_bfloat16*>(dz), static_cast<__nv_bfloat16*>(gout), dgamma, dbeta, n_pix, C));
     HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_bn_bwd_fused(const void* dy, const void* yrelu, const float* rscale, const float* rshift, const void* z,
+                               const float* mean, const float* invstd, const float* gamma, float* sums, double count, void* dz,
+                               void* g_out, float* dgamma, float* dbeta, int64_t n_pix, int C, uint32_t* barrier_words, hd_stream st) {
+    HD_CHECK_ARG(dy != nullptr && z != nullptr && dz != nullptr && mean != nullptr && invstd != nullptr && gamma != nullptr &&
+                 sums != nullptr && barrier_words != nullptr);
+    HD_CHECK_ARG(C % 8 == 0 && kBnFusedThreads % (C / 8) == 0 && n_pix > 0);
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = 148;
+    }
+    const int L = kBnFusedThreads / (C / 8);
+    long blocks = (n_pix + L - 1) / L;                       // at least one step of every pixel lane per CTA
+    if (blocks > sms) blocks = sms;
+    const long per = (n_pix + blocks - 1) / blocks;
+    blocks = (n_pix + per - 1) / per;
+    const long iters = (per + L - 1) / L;
+    const size_t base = 2 * static_cast<size_t>(C) * sizeof(float);
+    const size_t cache_bytes = static_cast<size_t>(iters) * kBnFusedThreads * 16 * 2;
+    const size_t limit = 200 * 1024;
+    const int cache = base + cache_bytes <= limit ? 1 : 0;
+    const size_t smem = base + (cache ? cache_bytes : 0);
+    static SmemAttrOnce smem_attr;
+    HD_CUDA_OK(ensure_dyn_smem(smem_attr, bn_bwd_fused_kernel, static_cast<int>(limit)));
+    HD_CUDA_OK(hd::launch(bn_bwd_fused_kernel, dim3(static_cast<int>(blocks)), dim3(kBnFusedThreads), smem, static_cast<cudaStream_t>(st),
+                          static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(yrelu), rscale, rshift,
+                          static_cast<const __nv_bfloat16*>(z), mean, invstd, gamma, sums, static_cast<float>(1.0 / count),
+                          static_cast<__nv_bfloat16*>(dz), static_cast<__nv_bfloat16*>(g_out), dgamma, dbeta, static_cast<long>(n_pix), C,
+                          per, cache, barrier_words));
+    HD_CUDA_OK(cudaPeekAtLastError());
     return HD_OK;
 }
 

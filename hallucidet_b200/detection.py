@@ -22,7 +22,7 @@ import torchvision
 from torchvision.models.detection.roi_heads import fastrcnn_loss
 from torchvision.models.detection.rpn import concat_box_prediction_layers
 
-from . import ops
+from . import heads, ops
 from .backbone import FrozenBackbone
 from .transform import GeneralizedRCNNTransform
 
@@ -815,6 +815,7 @@ def _anchors(model, images, features):
 
 
 FUSED_RPN_PREDICTORS = _os.environ.get("HD_FUSED_RPN_PRED", "1") == "1"
+B200_HEADS = _os.environ.get("HD_B200_HEADS", "1") == "1"       # frozen RPN / RetinaNet heads on the B200 conv kernels (heads.py)
 
 
 def _rpn_head(head, features):
@@ -844,7 +845,14 @@ def rpn_eval(model, images, features, targets, targets_event=None):
     (src/utils/eval_forward_fasterrcnn.py:62-99).  ``targets_event``: CUDA event recorded once ``targets`` are final on
     the current stream; lets the anchor-target work start before the backbone forward has finished."""
     features = list(features.values())
-    objectness, pred_bbox_deltas = _rpn_head(model.rpn.head, features)
+    objectness = None
+    if B200_HEADS and features[0].is_cuda and isinstance(model.backbone, FrozenBackbone):
+        # the frozen RPN head on the tcgen05 conv kernels, reading the backbone's bf16 pyramid (forward + input gradient only)
+        bf16 = model.backbone.bf16_features()
+        if bf16 is not None and len(bf16) == len(features) and heads.rpn_head_tower(model.rpn.head) is not None:
+            objectness, pred_bbox_deltas = heads.rpn_head_forward(model.rpn.head, features, bf16)
+    if objectness is None:
+        objectness, pred_bbox_deltas = _rpn_head(model.rpn.head, features)
     batched = BATCHED_TAIL and features[0].is_cuda
     anchors, anchors_fresh = _anchors(model, images, features) if batched else (model.rpn.anchor_generator(images, features), True)
     num_images = len(anchors)
@@ -1179,7 +1187,13 @@ def eval_forward_retinanet(model, images, targets, train_det=False, model_name="
     if isinstance(features, torch.Tensor):
         features = OrderedDict([("0", features)])
     features = list(features.values())
-    head_outputs = model.head(features)
+    head_outputs = None
+    if B200_HEADS and features[0].is_cuda and isinstance(model.backbone, FrozenBackbone):
+        bf16 = model.backbone.bf16_features()
+        if bf16 is not None and len(bf16) == len(features) and heads.retinanet_head_towers(model.head) is not None:
+            head_outputs = heads.retinanet_head_forward(model.head, features, bf16)
+    if head_outputs is None:
+        head_outputs = model.head(features)
     anchors = model.anchor_generator(images, features)
     losses = compute_retinanet_loss(targets, head_outputs, anchors, model)
     num_anchors_per_level = [x.size(2) * x.size(3) for x in features]

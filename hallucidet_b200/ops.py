@@ -10,10 +10,11 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import HdAct, HdConvArgs, check
+from ._lib import HdAct, HdBnFin, HdConvArgs, check
 
 STATS_REPLICAS = 16      # legacy name: default row count for small test problems (see conv_fwd_tiles)
 STEM_KPAD = 160          # 7*7*3 = 147 -> 5 k-blocks of 32
+STREAMK = True           # hand every fwd / dgrad launch the stream-K workspace (the library decides per problem)
 
 LAUNCHES = 0             # kernels launched through this module (one per C-ABI compute call; nms / roi_align_bwd add their second)
 PROFILE = None           # set to a list to record (name, algorithmic FLOPs, start event, end event, shape, bytes) per launch
@@ -63,10 +64,16 @@ def round_up(a, b):
 
 def conv_args(x0, y0, w=None, k=3, stride=1, x1=None, y1=None, bias=None, add=None, mask=None, relu=False, sigmoid=False,
               stats=None, out_f32=None, out_f32_channels=0, store_bf16=True, phase_mask=0, dw=None, split_k=0, out_f32_nhwc=False,
-              algo_cin=None, algo_cout=None):
+              algo_cin=None, algo_cout=None, bn_fin=None):
     a = HdConvArgs()
+    if bn_fin is not None:
+        a.bn_fin = ctypes.pointer(bn_fin)
+        a._bn_fin_keepalive = bn_fin
     a.algo = (algo_cin, algo_cout)
     a.x0, a.x1, a.y0, a.y1 = act(x0), act(x1), act(y0), act(y1)
+    if w is not None and STREAMK and x0.is_cuda:
+        ws = conv_workspace(x0.device)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
     a.w = w.data_ptr() if w is not None else None
     a.kh = a.kw = k
     a.stride = stride
@@ -155,6 +162,20 @@ def _conv_timed(a, kind):
 def _conv_desc(a):
     return (f"x0[{a.x0.n},{a.x0.h},{a.x0.w},{a.x0.c}] x1c{a.x1.c} y0[{a.y0.n},{a.y0.h},{a.y0.w},{a.y0.c}] y1c{a.y1.c} "
             f"k{a.kh} s{a.stride}")
+
+
+_WORKSPACES = {}
+
+
+def conv_workspace(device):
+    """The stream-K scratch of hd_conv_fwd / hd_conv_dgrad (hd_conv_args.workspace): one zero-initialised buffer per device,
+    shared by all convolution launches -- they are all issued on one stream (weight gradients, the only side-stream
+    convolutions, do not use it)."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        ws = _WORKSPACES[key] = torch.zeros(int(_lib.load().hd_conv_workspace_bytes()), dtype=torch.uint8, device=device)
+    return ws
 
 
 def conv_fwd(args):
@@ -281,6 +302,23 @@ def stem_col2im(dpatches, dx_nchw, k_pad=STEM_KPAD):
         check(_lib.load().hd_stem_col2im(_ptr(dpatches), _ptr(dx_nchw), n, h, w, k_pad, _stream()), "hd_stem_col2im")
 
 
+def bn_fin(count, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale, shift, counter):
+    """hd_bn_fin for conv_args(bn_fin=...): the BatchNorm finalize runs in the tail of the convolution that produces the
+    statistics (last CTA), instead of a separate hd_bn_finalize launch.  ``counter``: one zeroed int32 device word per layer.
+    The struct holds raw pointers: the caller keeps the tensors alive."""
+    assert counter.dtype == torch.int32 and counter.numel() == 1 and counter.is_cuda
+    f = HdBnFin()
+    f.count = float(count)
+    f.gamma, f.beta = gamma.data_ptr(), beta.data_ptr()
+    f.running_mean = running_mean.data_ptr() if running_mean is not None else None
+    f.running_var = running_var.data_ptr() if running_var is not None else None
+    f.mean, f.invstd, f.scale, f.shift = mean.data_ptr(), invstd.data_ptr(), scale.data_ptr(), shift.data_ptr()
+    f.counter = counter.data_ptr()
+    f.eps, f.momentum = float(eps), float(momentum)
+    f._key = (gamma.data_ptr(), beta.data_ptr(), f.running_mean, f.running_var)
+    return f
+
+
 def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, mean, invstd, scale, shift):
     c = gamma.numel()
     with _Timed("bn_finalize"):
@@ -310,6 +348,18 @@ def bn_bwd_apply(dy, y_relu, z, mean, invstd, gamma, sums, dz, g_out=None, dgamm
         check(_lib.load().hd_bn_bwd_apply(_ptr(dy), _ptr(y_relu), _ptr(relu_scale), _ptr(relu_shift), _ptr(z), _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(sums),
                                           float(n_pix), _ptr(dz), _ptr(g_out), _ptr(dgamma), _ptr(dbeta), n_pix, c, _stream()),
               "hd_bn_bwd_apply")
+
+
+def bn_bwd_fused(dy, y_relu, z, mean, invstd, gamma, sums, dz, barrier, g_out=None, dgamma=None, dbeta=None, relu_scale=None, relu_shift=None):
+    """bn_bwd_reduce + bn_bwd_apply as one persistent launch (hd_bn_bwd_fused).  ``sums`` zeroed by the caller; ``barrier``:
+    int32[2] device tensor, zero-initialised once and then left to the kernel."""
+    c = z.shape[-1]
+    n_pix = z.numel() // c
+    assert barrier.dtype == torch.int32 and barrier.numel() >= 2
+    with _Timed("bn_bwd_fused"):
+        check(_lib.load().hd_bn_bwd_fused(_ptr(dy), _ptr(y_relu), _ptr(relu_scale), _ptr(relu_shift), _ptr(z), _ptr(mean), _ptr(invstd),
+                                          _ptr(gamma), _ptr(sums), float(n_pix), _ptr(dz), _ptr(g_out), _ptr(dgamma), _ptr(dbeta),
+                                          n_pix, c, _ptr(barrier), _stream()), "hd_bn_bwd_fused")
 
 
 def maxpool_fwd(x, y, idx=None, mask_nonpositive=False):

@@ -180,6 +180,7 @@ class _UnetFunction(torch.autograd.Function):
 # execution engine: static buffers + kernel program for one (B, H, W, mode)
 # ------------------------------------------------------------------------------------------------------
 SIDE_STREAM_WGRAD = os.environ.get("HD_SIDE_WGRAD", "1") != "0"
+FUSED_BN_BWD = os.environ.get("HD_BN_FUSED", "1") != "0"
 
 
 class _Layer:
@@ -281,6 +282,10 @@ class _UnetEngine:
         for l in bn_layers:
             l.sums_off = tot
             tot += (l.sums.numel() + 3) // 4 * 4
+        self.bn_barrier = torch.zeros(2, dtype=torch.int32, device=device)     # grid barrier of the fused BatchNorm backward
+        self.bn_counters = torch.zeros(len(bn_layers), dtype=torch.int32, device=device)   # "last CTA" counters of the fused finalize
+        for i, l in enumerate(bn_layers):
+            l.counter = self.bn_counters[i:i + 1]
         self.dw_flat = torch.zeros(tot, device=device)
         for l in self.all_layers:
             l.dw = self.dw_flat[l.dw_off:l.dw_off + l.dw_rows * l.dw_cols]
@@ -289,6 +294,7 @@ class _UnetEngine:
         self.grad_bufs = {}
         self.side_stream, self.side_used = None, False
         self.pack_tab = self.unpack_tab = None
+        self._bn_keys = None
         self.graphs = {}
         self.sigmoid = None
         self.generation = 0
@@ -319,8 +325,10 @@ class _UnetEngine:
         if not self.training:
             return
         srcs = self._pack_sources()
-        if self.pack_tab is not None and self.pack_tab.keys == [w.data_ptr() for w in srcs]:
+        bn_keys = [l.bn.weight.data_ptr() for l in self.all_layers if l.bn is not None]
+        if self.pack_tab is not None and self.pack_tab.keys == [w.data_ptr() for w in srcs] and bn_keys == self._bn_keys:
             return
+        self._bn_keys = bn_keys
         assert all(w.is_contiguous() for w in srcs)
         self.pack_tab = ops.pack_table([l.packed for l in self.all_layers], srcs, self.device)
         gv = self.grad_views
@@ -349,16 +357,25 @@ class _UnetEngine:
                 l.bias.copy_(bn.bias.detach() - bn.running_mean * scale)
                 l.packed.pack(l.conv.weight.detach().contiguous(), scale.contiguous())
 
+    def _bn_fin(self, l, count):
+        """The layer's hd_bn_fin descriptor (raw pointers to its BatchNorm parameters / buffers; rebuilt if they moved)."""
+        bn = l.bn
+        key = (bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(), bn.running_var.data_ptr())
+        fin = getattr(l, "fin", None)
+        if fin is None or fin._key != key:
+            fin = l.fin = ops.bn_fin(count, bn.weight.detach(), bn.bias.detach(), bn.eps,
+                                     bn.momentum if bn.momentum is not None else 0.1, bn.running_mean, bn.running_var,
+                                     l.mean, l.invstd, l.scale, l.shift, l.counter)
+        return fin
+
     def _conv_bn(self, l, x0, a_out, x1=None, relu=True, res=None, res_layer=None, apply=True):
         """train: z = conv(x) (+stats) -> finalize -> a_out = relu(bn(z) + res).   eval: fused epilogue."""
         if self.training:
             if l.stats is None:
                 l.stats = torch.zeros(ops.conv_fwd_tiles(x0, l.k, l.stride, cout=None if x1 is not None else l.cout), 2, l.cout, device=self.device)
-            ops.conv_fwd(ops.conv_args(x0, l.z, l.packed.w_fwd, k=l.k, stride=l.stride, x1=x1, stats=l.stats))
-            bn = l.bn
-            ops.bn_finalize(l.stats, self.B * l.h * l.w, bn.weight.detach(), bn.bias.detach(), bn.eps,
-                            bn.momentum if bn.momentum is not None else 0.1, bn.running_mean, bn.running_var,
-                            l.mean, l.invstd, l.scale, l.shift)
+            # statistics + BatchNorm finalize (scale / shift / running statistics) in the tail of the convolution itself
+            ops.conv_fwd(ops.conv_args(x0, l.z, l.packed.w_fwd, k=l.k, stride=l.stride, x1=x1, stats=l.stats,
+                                       bn_fin=self._bn_fin(l, self.B * l.h * l.w)))
             if apply:
                 if res_layer is not None:
                     ops.bn_apply(l.z, l.scale, l.shift, a_out, relu=relu, res=res_layer.z, res_scale=res_layer.scale, res_shift=res_layer.shift)
@@ -436,10 +453,8 @@ class _UnetEngine:
         if self.training:
             if st.stats is None:
                 st.stats = torch.zeros(ops.conv_fwd_tiles(self.patches, 1, 1), 2, 64, device=self.device)
-            ops.conv_fwd(ops.conv_args(self.patches, zs, st.packed.w_fwd, k=1, stats=st.stats, algo_cin=147))
-            bn = st.bn
-            ops.bn_finalize(st.stats, zs.shape[2], bn.weight.detach(), bn.bias.detach(), bn.eps, bn.momentum or 0.1,
-                            bn.running_mean, bn.running_var, st.mean, st.invstd, st.scale, st.shift)
+            ops.conv_fwd(ops.conv_args(self.patches, zs, st.packed.w_fwd, k=1, stats=st.stats, algo_cin=147,
+                                       bn_fin=self._bn_fin(st, zs.shape[2])))
             ops.bn_apply(zs, st.scale, st.shift, a_stem_flat, relu=True)
         else:
             ops.conv_fwd(ops.conv_args(self.patches, a_stem_flat, st.packed.w_fwd, k=1, bias=st.bias, relu=True, algo_cin=147))
@@ -480,8 +495,13 @@ class _UnetEngine:
         z = l.z if z is None else z                   # (l.sums was zeroed with dw_flat at the start of the backward)
         rs, rb = (l.scale, l.shift) if direct_relu else (None, None)
         yr = None if direct_relu else y_relu
-        ops.bn_bwd_reduce(g, yr, z, l.mean, l.invstd, l.sums, relu_scale=rs, relu_shift=rb)
         dz = self.gbuf(("dz", l.name), z)
+        if FUSED_BN_BWD:                              # one persistent launch: reduce, grid barrier, apply
+            ops.bn_bwd_fused(g, yr, z, l.mean, l.invstd, l.bn.weight.detach(), l.sums, dz, self.bn_barrier, g_out,
+                             self.grad_views[l.bn_name + ".weight"], self.grad_views[l.bn_name + ".bias"],
+                             relu_scale=rs, relu_shift=rb)
+            return dz
+        ops.bn_bwd_reduce(g, yr, z, l.mean, l.invstd, l.sums, relu_scale=rs, relu_shift=rb)
         ops.bn_bwd_apply(g, yr, z, l.mean, l.invstd, l.bn.weight.detach(), l.sums, dz, g_out,
                          self.grad_views[l.bn_name + ".weight"], self.grad_views[l.bn_name + ".bias"],
                          relu_scale=rs, relu_shift=rb)

@@ -91,11 +91,20 @@ typedef struct hd_conv_args {
     int32_t out_f32_nhwc;     /* fwd: 1 = the fp32 copy (out_f32_nchw) is channels-last [n][h][w][out_f32_channels] instead of NCHW
                                  (out_f32_channels % 16 == 0, no sigmoid): what cuDNN and the RoIAlign kernels read without a transpose */
     const hd_bn_fin* bn_fin;  /* fwd with stats: optional fused BatchNorm finalize (host pointer, copied at launch); NULL = off */
+    void* workspace;          /* fwd / dgrad: optional device scratch of >= hd_conv_workspace_bytes() bytes, zero-initialised ONCE by the
+                                 caller and then left to the library (flags are restored by the kernels); enables stream-K for
+                                 problems whose tiles under-fill the SMs.  One workspace per stream of convolution launches. NULL = off */
+    int64_t workspace_bytes;
 } hd_conv_args;
 
 int hd_conv_fwd(const hd_conv_args* a, hd_stream stream);
 int hd_conv_fwd_tiles(const hd_conv_args* a);   /* statistics rows hd_conv_fwd needs for this problem (= CTAs of its grid; with y0.c unset: an upper bound); host-only, no launch */
 int hd_conv_dgrad(const hd_conv_args* a, hd_stream stream);
+int64_t hd_conv_workspace_bytes(void);           /* size of hd_conv_args.workspace */
+/* Development aid (tools/conv_timeline.py): later hd_conv_fwd / hd_conv_dgrad launches write 8 %globaltimer stamps per CTA
+ * into buf ([grid][8] int64, zeroed by the caller before each launch): kernel start, dependencies resolved, last TMA issued,
+ * first operands landed, last MMA issued, last accumulator complete, epilogue done, CTA exit.  NULL = off (default). */
+int hd_conv_debug_timestamps(void* buf);
 int hd_conv_wgrad(const hd_conv_args* a, hd_stream stream);
 
 /* Weight packing (once per optimizer step for the U-Net, once at load for the frozen detector).
@@ -161,6 +170,14 @@ int hd_bn_bwd_reduce(const void* dy, const void* y_relu, const float* relu_scale
 int hd_bn_bwd_apply(const void* dy, const void* y_relu, const float* relu_scale, const float* relu_shift, const void* z,
                     const float* mean, const float* invstd, const float* gamma, const float* sums, double count, void* dz, void* g_out, float* dgamma,
                     float* dbeta, int64_t n_pix, int channels, hd_stream stream);
+
+/* Both backward passes in ONE persistent kernel (one CTA per SM, grid barrier in the middle): same arithmetic as
+ * hd_bn_bwd_reduce + hd_bn_bwd_apply; layers whose per-CTA slice of (g, z) fits in shared memory read them from HBM once.
+ * sums: fp32 [2][channels], zeroed by the caller; barrier_words: two zero-initialised device words (count, generation), kept
+ * by the caller across launches (the kernel restores count = 0 itself). */
+int hd_bn_bwd_fused(const void* dy, const void* y_relu, const float* relu_scale, const float* relu_shift, const void* z,
+                    const float* mean, const float* invstd, const float* gamma, float* sums, double count, void* dz, void* g_out,
+                    float* dgamma, float* dbeta, int64_t n_pix, int channels, uint32_t* barrier_words, hd_stream stream);
 
 /* ---- memory-bound glue ------------------------------------------------------------------------------ */
 /* MaxPool2d(3,2,1) after the stem ReLU (encoders/resnet.py:51, TV: models/resnet.py:199). */

@@ -63,6 +63,13 @@ CONV_CASES = [
     (1, 20, 20, 512, 512, 3, 1, 0),
     (1, 10, 10, 2048, 256, 1, 1, 0),
     (1, 6, 6, 256, 256, 3, 2, 0),
+    # stream-K (tiles under-fill the SMs, long K): config-2 deep-layer shapes and a ragged one
+    (8, 32, 40, 256, 256, 3, 1, 0),
+    (8, 16, 20, 512, 512, 3, 1, 0),
+    (8, 64, 80, 128, 128, 3, 1, 0),
+    (8, 32, 40, 512, 256, 3, 1, 256),
+    (3, 20, 20, 512, 512, 3, 1, 0),
+    (5, 40, 40, 1024, 256, 1, 1, 0),
 ]
 
 
@@ -170,6 +177,9 @@ DGRAD_CASES = [
     (2, 16, 24, 64, 128, 3, 2, 0),
     (1, 16, 16, 128, 64, 3, 1, 64),     # dX split into (64 | 64)
     (1, 16, 20, 192, 64, 3, 1, 64),     # (128 | 64)
+    (8, 32, 40, 256, 256, 3, 1, 0),     # stream-K
+    (8, 16, 20, 512, 512, 3, 1, 0),
+    (8, 32, 40, 768, 256, 3, 1, 256),   # stream-K with a split gradient (512 | 256)
 ]
 
 
@@ -615,3 +625,135 @@ def test_roi_align_fwd_matches_torchvision(h, w, scale, c):
     print(f"\n[roi_align fwd {h}x{w} c{c}] bit-identical: {torch.equal(got, ref)}, max |diff| {diff:.3e}")
     assert torch.allclose(got, ref, rtol=1e-6, atol=1e-6 * float(ref.abs().max()))
     assert torch.equal(got, ref)         # holds with this toolchain: same expression, same contraction
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 24, 40, 64, 128), (8, 32, 40, 256, 256), (2, 64, 64, 16, 16), (2, 40, 64, 32, 32),
+                                            (4, 64, 80, 64, 64)])
+def test_conv_fwd_fused_bn_finalize(n, h, w, cin, cout):
+    """hd_conv_args.bn_fin: the last CTA of the convolution finalizes train-mode BatchNorm (mean / invstd / scale / shift and
+    the running statistics, nn.BatchNorm2d semantics) from the per-CTA statistics rows -- against fp32 PyTorch on the
+    bf16-rounded conv output, twice in a row (the per-layer counter must be left at zero), and bit-identical run to run."""
+    o = ops()
+    x = rnd(n, h, w, cin, seed=1)
+    wt = (torch.randn(cout, cin, 3, 3, generator=torch.Generator().manual_seed(3)) / (cin * 9) ** 0.5).to(torch.bfloat16).float().cuda()
+    pk = o.PackedConv(cout, cin, 3, "cuda").pack(wt)
+    y = torch.empty(n, h, w, cout, dtype=torch.bfloat16, device="cuda")
+    stats = torch.full((o.conv_fwd_tiles(x, 3, 1, cout=cout), 2, cout), float("nan"), device="cuda")
+    gamma = torch.rand(cout, device="cuda") + 0.5
+    beta = torch.randn(cout, device="cuda")
+    rm, rv = torch.zeros(cout, device="cuda"), torch.ones(cout, device="cuda")
+    mean, invstd, scale, shift = (torch.full((cout,), float("nan"), device="cuda") for _ in range(4))
+    counter = torch.zeros(1, dtype=torch.int32, device="cuda")
+    fin = o.bn_fin(n * h * w, gamma, beta, 1e-5, 0.1, rm, rv, mean, invstd, scale, shift, counter)
+    o.conv_fwd(o.conv_args(x, y, pk.w_fwd, k=3, stats=stats, bn_fin=fin))
+    torch.cuda.synchronize()
+    assert int(counter) == 0
+    yq = nchw(y).double()
+    m_ref = yq.mean((0, 2, 3))
+    v_ref = yq.var((0, 2, 3), unbiased=False)
+    is_ref = (v_ref + 1e-5).rsqrt()
+    assert torch.allclose(mean.double(), m_ref, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(invstd.double(), is_ref, rtol=1e-4)
+    assert torch.allclose(scale.double(), gamma.double() * is_ref, rtol=1e-4)
+    assert torch.allclose(shift.double(), beta.double() - m_ref * gamma.double() * is_ref, rtol=1e-4, atol=1e-5)
+    cnt = n * h * w
+    assert torch.allclose(rm.double(), 0.1 * m_ref, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(rv.double(), 0.9 + 0.1 * v_ref * cnt / (cnt - 1), rtol=1e-4)
+    first = [t.clone() for t in (mean, invstd, scale, shift, stats)]
+    o.conv_fwd(o.conv_args(x, y, pk.w_fwd, k=3, stats=stats, bn_fin=fin))     # second launch: counter was reset, results identical
+    torch.cuda.synchronize()
+    assert int(counter) == 0
+    for a, b in zip(first, (mean, invstd, scale, shift, stats)):
+        assert torch.equal(a, b)
+    assert torch.allclose(rm.double(), 0.19 * m_ref, rtol=1e-4, atol=1e-6)
+    # the separate finalize kernel on the same rows gives the same coefficients
+    mean2, invstd2, scale2, shift2 = (torch.empty(cout, device="cuda") for _ in range(4))
+    o.bn_finalize(stats, cnt, gamma, beta, 1e-5, 0.1, None, None, mean2, invstd2, scale2, shift2)
+    torch.cuda.synchronize()
+    assert torch.allclose(scale2, scale, rtol=1e-6) and torch.allclose(shift2, shift, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("n,h,w,c,mode", [(4, 16, 20, 64, "yrelu"), (2, 8, 12, 16, "direct"), (2, 8, 12, 512, "plain"),
+                                          (8, 64, 80, 128, "direct"),     # slice kept in shared memory (config-2 layer2 size)
+                                          (8, 128, 160, 64, "yrelu"),     # re-read mode (config-2 layer1 size)
+                                          (3, 50, 70, 32, "direct")])
+def test_bn_bwd_fused_matches_two_pass_and_torch(n, h, w, c, mode):
+    """hd_bn_bwd_fused (reduce + grid barrier + apply in one persistent kernel) against the two-launch path and autograd,
+    for the three ReLU-mask sources; launched several times to exercise the self-resetting barrier."""
+    o = ops()
+    z = rnd(n, h, w, c, seed=1, scale=2.0) + 0.5
+    dy = rnd(n, h, w, c, seed=3)
+    gamma = torch.rand(c, device="cuda") + 0.5
+    beta = torch.randn(c, device="cuda") * 0.1
+    zf = nchw(z)
+    mean = zf.mean((0, 2, 3)).contiguous()
+    invstd = (zf.var((0, 2, 3), unbiased=False) + 1e-5).rsqrt().contiguous()
+    scale = (gamma * invstd).contiguous()
+    shift = (beta - mean * scale).contiguous()
+    res = rnd(n, h, w, c, seed=2)
+    y = torch.empty_like(z)
+    o.bn_apply(z, scale, shift, y, relu=True, res=res if mode == "yrelu" else None)
+    kw = {}
+    yr = None
+    if mode == "yrelu":
+        yr = y
+    elif mode == "direct":
+        kw = dict(relu_scale=scale, relu_shift=shift)
+    s_ref = torch.zeros(2, c, device="cuda")
+    o.bn_bwd_reduce(dy, yr, z, mean, invstd, s_ref, **kw)
+    dz_ref, g_ref = torch.empty_like(z), torch.empty_like(z)
+    dg_ref, db_ref = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+    o.bn_bwd_apply(dy, yr, z, mean, invstd, gamma, s_ref, dz_ref, g_ref, dg_ref, db_ref, **kw)
+    barrier = torch.zeros(2, dtype=torch.int32, device="cuda")
+    for rep in range(3):
+        sums = torch.zeros(2, c, device="cuda")
+        dz, gout = torch.full_like(z, float("nan")), torch.full_like(z, float("nan"))
+        dgamma, dbeta = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+        o.bn_bwd_fused(dy, yr, z, mean, invstd, gamma, sums, dz, barrier, gout, dgamma, dbeta, **kw)
+        torch.cuda.synchronize()
+        assert int(barrier[0]) == 0 and int(barrier[1]) == rep + 1
+        assert torch.equal(gout, g_ref)
+        assert torch.allclose(sums, s_ref, rtol=1e-4, atol=1e-2 * max(1.0, s_ref.abs().max().item() * 1e-3))
+        assert torch.allclose(dgamma, dg_ref, rtol=1e-4, atol=1e-2) and torch.allclose(dbeta, db_ref, rtol=1e-4, atol=1e-2)
+        err = (dz.float() - dz_ref.float()).abs().max().item()
+        assert err <= 2 ** -7 * dz_ref.float().abs().max().item() + 1e-6, err      # same formula; fp32 sums differ in the last bits
+    if mode == "plain":                                                             # autograd cross-check (no mask)
+        zr = zf.clone().requires_grad_(True)
+        out = F.batch_norm(zr, None, None, gamma, beta, training=True, eps=1e-5)
+        (out * nchw(dy)).sum().backward()
+        assert_close_bf16(nchw(dz), zr.grad, "bn_bwd_fused vs autograd")
+
+
+def test_conv_streamk_epilogue_stats_add_mask_deterministic():
+    """Stream-K launches (partial accumulators through the workspace, reduced in CTA order): fused epilogue operands and the
+    BatchNorm statistics are unaffected, results are bit-identical run to run, and HD-level parity holds vs fp32 PyTorch."""
+    o = ops()
+    n, h, w, cin, cout = 8, 32, 40, 256, 256
+    x = rnd(n, h, w, cin, seed=1)
+    wt = (torch.randn(cout, cin, 3, 3, generator=torch.Generator().manual_seed(3)) / (cin * 9) ** 0.5).to(torch.bfloat16).float().cuda()
+    pk = o.PackedConv(cout, cin, 3, "cuda").pack(wt)
+    ref = F.conv2d(nchw(x), wt, padding=1)
+    # (a) statistics epilogue (staged store)
+    outs = []
+    for _ in range(2):
+        y = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+        stats = torch.full((o.conv_fwd_tiles(x, 3, 1, cout=cout), 2, cout), float("nan"), device="cuda")
+        o.conv_fwd(o.conv_args(x, y, pk.w_fwd, k=3, stats=stats))
+        torch.cuda.synchronize()
+        outs.append((y, stats))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert_close_bf16(nchw(outs[0][0]), ref, "stream-K fwd")
+    yq = nchw(outs[0][0])
+    ssum = outs[0][1].sum(0)
+    assert torch.allclose(ssum[0], yq.sum((0, 2, 3)), rtol=2e-3, atol=1e-2)
+    assert torch.allclose(ssum[1], (yq * yq).sum((0, 2, 3)), rtol=2e-3, atol=1e-2)
+    # (b) register-store epilogue with bias + add + relu + mask
+    bias = torch.randn(cout, device="cuda")
+    add, mask = rnd(n, h, w, cout, seed=5), rnd(n, h, w, cout, seed=6)
+    y2 = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    o.conv_fwd(o.conv_args(x, y2, pk.w_fwd, k=3, bias=bias, add=add, relu=True, mask=mask))
+    torch.cuda.synchronize()
+    ref2 = F.relu(ref + bias.view(1, -1, 1, 1) + nchw(add)) * (nchw(mask) > 0)
+    assert_close_bf16(nchw(y2), ref2, "stream-K fused epilogue")
+    ws = o.conv_workspace(x.device)
+    assert int(ws[:4096].view(torch.int32).abs().sum()) == 0        # every partial flag was handed back

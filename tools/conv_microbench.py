@@ -62,17 +62,23 @@ def main():
         ho, wo = h // s, w // s
         x = bf(B, h, w, cin)
         y = bf(B, ho, wo, cout)
+        keep = []                                          # conv_args holds raw pointers: keep every operand alive
+
+        def own(t):
+            keep.append(t)
+            return t
+
         if kind == "fwd":
             args = ops.conv_args(x, y, pk.w_fwd, k=k, stride=s,
-                                 bias=torch.randn(cout, device=dev) if "bias" in flags else None,
-                                 add=bf(B, ho, wo, cout) if "add" in flags else None, relu="relu" in flags,
-                                 stats=torch.zeros(ops.conv_fwd_tiles(x, k, s), 2, cout, device=dev) if "stats" in flags else None)
+                                 bias=own(torch.randn(cout, device=dev)) if "bias" in flags else None,
+                                 add=own(bf(B, ho, wo, cout)) if "add" in flags else None, relu="relu" in flags,
+                                 stats=own(torch.zeros(ops.conv_fwd_tiles(x, k, s), 2, cout, device=dev)) if "stats" in flags else None)
             fn = lambda: ops.conv_fwd(args)
             bytes_ = 2 * (x.numel() + y.numel() * (2 if "add" in flags else 1)) + 2 * wt.numel()
         elif kind == "dgrad":
             dx = bf(B, h, w, cin)
-            args = ops.conv_args(y, dx, pk.w_dgrad, k=k, stride=s, add=bf(B, h, w, cin) if "add" in flags else None,
-                                 mask=bf(B, h, w, cin) if "mask" in flags else None)
+            args = ops.conv_args(y, dx, pk.w_dgrad, k=k, stride=s, add=own(bf(B, h, w, cin)) if "add" in flags else None,
+                                 mask=own(bf(B, h, w, cin)) if "mask" in flags else None)
             fn = lambda: ops.conv_dgrad(args)
             bytes_ = 2 * (y.numel() + dx.numel() * (1 + ("add" in flags) + ("mask" in flags))) + 2 * wt.numel()
         else:
@@ -95,8 +101,26 @@ def main():
             ts.append(e0.elapsed_time(e1) * 1e3)
         ts.sort()
         us = ts[len(ts) // 2]
-        results.append({"name": name, "us": us, "tflops": flops / us / 1e6, "gbs": bytes_ / us / 1e3, "min_us": ts[0]})
-        print(f"{name:34s} {us:9.1f} us  {flops / us / 1e6:8.1f} TFLOP/s  {bytes_ / us / 1e3:8.1f} GB/s (algorithmic)")
+        # GPU time without host launch cost: 10 back-to-back launches in a CUDA graph (operands L2-warm, PDL-chained)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(10):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        gts = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            gts.append(e0.elapsed_time(e1) * 1e2)
+        gts.sort()
+        gus = gts[len(gts) // 2]
+        results.append({"name": name, "us": us, "graph_us": gus, "tflops": flops / us / 1e6, "graph_tflops": flops / gus / 1e6,
+                        "gbs": bytes_ / us / 1e3, "min_us": ts[0]})
+        print(f"{name:34s} {us:9.1f} us  {flops / us / 1e6:8.1f} TFLOP/s  {bytes_ / us / 1e3:8.1f} GB/s (algorithmic) | in-graph {gus:7.1f} us {flops / gus / 1e6:8.1f} TFLOP/s")
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(results, open("gpurun_out/conv_microbench.json", "w"), indent=1)
 

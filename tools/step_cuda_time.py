@@ -2,7 +2,7 @@
 import os, sys, time, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hallucidet_b200.train import HalluciDetTrainer
-from oracle import step as ostep
+from hallucidet_b200 import synthetic as ostep
 from torch.profiler import profile, ProfilerActivity
 dev = torch.device("cuda", 0)
 torch.backends.cudnn.benchmark = True
