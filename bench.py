@@ -146,6 +146,7 @@ def parity_step0(tr, ir, rgb, targets, detector_name, S):
     from oracle import detector as odet, step as ostep
     dev = ir.device
     state = {k: v.detach().clone() for k, v in tr.encoder_decoder.state_dict().items()}
+    ir_f = ir.float().div(255.0) if ir.dtype == torch.uint8 else ir      # the oracle sees what ToTensor would hand the reference
     was_training = tr.encoder_decoder.training
     tr.encoder_decoder.train()
     with torch.no_grad():
@@ -159,7 +160,7 @@ def parity_step0(tr, ir, rgb, targets, detector_name, S):
     flags = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark)
     torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = torch.backends.cudnn.benchmark = False
     try:
-        ref = ostep.train_step(state, det, ir, rgb, targets, size=S, detector_name=detector_name, det_seed=7)
+        ref = ostep.train_step(state, det, ir_f, rgb, targets, size=S, detector_name=detector_name, det_seed=7)
         want = float(ref["loss"])
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.benchmark = flags
@@ -216,6 +217,84 @@ def gpu_baseline_sample(B, S, detector_name, dev, steps=5):
     return res
 
 
+def main_inference(args):
+    """BASELINE.json config 5: inference-only hallucination + detection at full LLVIP resolution (1280x1024 IR -> S=300,
+    eval_hallucidet.py:135-161), batch 64 on one GPU.  Same JSON contract; metric = inference images/s."""
+    import torch
+    from hallucidet_b200 import ops
+    from hallucidet_b200.synthetic import synthetic_batch
+    from hallucidet_b200.train import DevicePrefetcher, HalluciDetTrainer
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    B, H, W, S = args.batch if args.batch != 8 else 64, 1024, 1280, 300
+    tr = HalluciDetTrainer(detector_name=args.detector, size=S, seed=123, device=dev, use_cuda_graph=not args.no_graph)
+    ir_h, rgb_h, targets = synthetic_batch(B, H, W, seed=123 + rank, ir_uint8=True)
+    ir_h = ir_h.pin_memory()
+    targets = [{k: v.to(dev) for k, v in t.items()} for t in targets]
+    ir_d = ir_h.to(dev)
+    rgb_d = torch.empty(0, device=dev)                      # test_step evaluates the hallucination only (no RGB pass)
+    prefetch = DevicePrefetcher(dev)
+
+    def step_resident():
+        return tr.test_step(rgb_d, targets, ir_d, targets)
+
+    n_det = []
+
+    def step_e2e():
+        if prefetch.pending is None:
+            prefetch.put(ir_h)
+        (ir,) = prefetch.get()
+        prefetch.put(ir_h)
+        out = tr.test_step(rgb_d, targets, ir, targets)
+        n_det.append(sum(int(d["boxes"].shape[0]) for d in out["detections_hal"]))     # device -> host: the detections' sizes
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    ops.LAUNCHES = 0
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+    launches = ops.LAUNCHES // max(args.warmup, 3)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = timed(step_resident, args.steps)
+    clocks = sampler.stop()
+    ms_e2e = timed(step_e2e, args.steps)
+    line = {
+        "metric": "inference images/s (1280x1024 IR -> hallucination + detection, bf16)", "value": world * B * args.steps / (ms / 1e3),
+        "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"BASELINE config 5: inference-only hallucination (U-Net eval mode) + {args.detector} detection, batch {B}, "
+                               f"1024x1280 IR, S={S}", "batch_per_gpu": B, "input": "1024x1280", "detector_size": S,
+                   "unet_chunk": "eval-mode U-Net runs the batch in chunks of 8 images through one engine (exact: folded BatchNorm)",
+                   "l2": "working set far exceeds the 126 MB L2; no explicit flush"},
+        "clocks": clocks,
+        "e2e": {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": ir_h.numel() * ir_h.element_size(), "d2h_bytes_per_step": 8 * B},
+        "gpu_launches": launches * args.steps,
+        "peak_mem_GB": torch.cuda.max_memory_allocated() / 2 ** 30,
+        "detections_per_batch": n_det[-1] if n_det else None,
+    }
+    if rank == 0:
+        print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -223,13 +302,22 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8)
-    ap.add_argument("--detector", default="fasterrcnn")
+    ap.add_argument("--detector", default=None)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5],
+                    help="BASELINE.json configuration: 2 = Faster R-CNN train step (default, the metric), 4 = RetinaNet train step, "
+                         "5 = inference at 1280x1024, batch 64")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--float-ir", action="store_true", help="feed the IR frames as fp32 [0,1] tensors instead of uint8 camera planes")
     ap.add_argument("--no-parity", action="store_true", help="skip the step-0 loss check against the fp32 oracle")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-PyTorch (autocast bf16 + channels_last) leg")
     ap.add_argument("--pixel", default=None, help="enable the pixel regulariser (mse / l1); default off as in the reference config")
     args = ap.parse_args()
+    if args.detector is None:
+        args.detector = "retinanet" if args.config == 4 else "fasterrcnn"
+    if args.config == 5 and args.impl != "reference":
+        main_inference(args)
+        return
     if args.impl == "reference":
         run_reference(args)
         return
@@ -253,7 +341,8 @@ def main():
     weights = {"pixel_rgb": 1.0, "pixel_ir": 1.0} if args.pixel else None
     tr = HalluciDetTrainer(detector_name=args.detector, size=S, pixel=args.pixel, weights=weights, seed=123, device=dev,
                            use_cuda_graph=not args.no_graph)
-    ir_h, rgb_h, targets = synthetic_batch(B, H, W, seed=123 + rank)
+    # IR as the uint8 camera plane (what the reference's dataloader decodes; /255 and the 1 -> 3 replication run in the stem kernel)
+    ir_h, rgb_h, targets = synthetic_batch(B, H, W, seed=123 + rank, ir_uint8=not args.float_ir)
     ir_h, rgb_h = ir_h.pin_memory(), rgb_h.pin_memory()
     targets = [{k: v.to(dev) for k, v in t.items()} for t in targets]
     ir_d, rgb_d = ir_h.to(dev), rgb_h.to(dev)
@@ -365,11 +454,12 @@ def main():
                                    f"batch {B}/GPU, 512x640 IR, S={S}, Adam + clip 0.5",
                        "detector": args.detector, "batch_per_gpu": B, "input": "512x640", "detector_size": S,
                        "parallelism": f"dp{world}", "cuda_graph": bool(was_graph), "pixel_regulariser": args.pixel,
+                       "ir_input": "uint8 camera plane, /255 + 1->3 replication fused into the stem kernel" if not args.float_ir else "fp32 [0,1]",
                        "detection_tail": "torchvision RPN/RoI head modules + losses (fp32, TF32 matmul); proposal filter, target assignment, sampling and post-processing batched over the images; hd_nms kernels",
                        "l2": "working set (activations + weights, several GB per step) far exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": ir_h.numel() * 4 + rgb_h.numel() * 4, "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": ir_h.numel() * ir_h.element_size() + rgb_h.numel() * rgb_h.element_size(), "d2h_bytes_per_step": 4},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel + wgrad_gemm_kernel (tcgen05 implicit GEMM)",
                          "achieved": achieved, "peak": burst, "unit": "TFLOP/s", "frac": achieved / burst, "peak_source": which,

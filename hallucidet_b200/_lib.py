@@ -19,7 +19,18 @@ class HdAct(ctypes.Structure):
 class HdPackDesc(ctypes.Structure):
     _fields_ = [("w", c_void_p), ("scale", c_void_p), ("w_fwd", c_void_p), ("w_dgrad", c_void_p), ("w_t", c_void_p),
                 ("cout", ctypes.c_int32), ("cin", ctypes.c_int32), ("kh", ctypes.c_int32), ("kw", ctypes.c_int32),
-                ("cout_pad", ctypes.c_int32), ("k_pad", ctypes.c_int32), ("cin_pad", ctypes.c_int32), ("first_block", ctypes.c_int32)]
+                ("cout_pad", ctypes.c_int32), ("k_pad", ctypes.c_int32), ("cin_pad", ctypes.c_int32), ("first_block", ctypes.c_int32),
+                ("g", c_void_p), ("m", c_void_p), ("v", c_void_p)]
+
+
+class HdAdamArgs(ctypes.Structure):
+    _fields_ = [("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("bias_correction1", c_float),
+                ("bias_correction2", c_float), ("grad_scale", c_float), ("clip", c_float), ("one_minus_beta1", c_float),
+                ("one_minus_beta2", c_float)]
+
+
+class HdAdamDesc(ctypes.Structure):
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("m", c_void_p), ("v", c_void_p), ("n", ctypes.c_int32), ("first_block", ctypes.c_int32)]
 
 
 class HdUnpackDesc(ctypes.Structure):
@@ -68,12 +79,14 @@ PROTOTYPES = {
     "hd_conv_fwd_tiles": [P(HdConvArgs)],
     "hd_conv_dgrad": [P(HdConvArgs), c_void_p],
     "hd_conv_workspace_bytes": [],
+    "hd_conv_has_streamk": [],
     "hd_conv_debug_timestamps": [c_void_p],
     "hd_conv_wgrad": [P(HdConvArgs), c_void_p],
     "hd_pack_conv_weight": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p],
     "hd_unpack_wgrad": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
     "hd_stem_im2col": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "hd_stem_col2im": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "hd_stem_im2col_1ch": [c_void_p, c_int, c_float, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "hd_bn_finalize": [c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     "hd_bn_apply": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p],
@@ -101,6 +114,8 @@ PROTOTYPES = {
     "hd_multi_blocks": [ctypes.c_int64],
     "hd_pack_conv_weights": [c_void_p, c_int, c_int, c_void_p],
     "hd_unpack_wgrads": [c_void_p, c_int, c_int, c_void_p],
+    "hd_adam_pack_conv_weights": [c_void_p, c_int, c_int, P(HdAdamArgs), c_void_p],
+    "hd_adam_multi": [c_void_p, c_int, c_int, P(HdAdamArgs), c_void_p],
     "hd_roi_align_bwd_nhwc": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
     "hd_roi_align_fwd_nhwc": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
     "hd_roi_align_ml_fwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],

@@ -22,6 +22,7 @@ from . import ops
 # epilogue writes them that way (no transpose), cuDNN's RPN / RetinaNet head convolutions and the RoIAlign kernels read
 # channels-last natively (no nchwToNhwc / nhwcToNchw passes), and the incoming gradients are a plain cast to bf16.
 CHANNELS_LAST_FEATURES = os.environ.get("HD_CL_FEATURES", "1") == "1"
+EVAL_CHUNK = int(os.environ.get("HD_EVAL_BACKBONE_CHUNK", "16"))      # images per engine pass when no gradient is needed
 
 
 class _FConv:
@@ -118,6 +119,11 @@ class FrozenBackbone(nn.Module):
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("hallucidet_b200.FrozenBackbone runs only on a CUDA (B200) device; there is no CPU path")
+        if not (x.requires_grad and torch.is_grad_enabled()) and x.shape[0] > EVAL_CHUNK:
+            # gradient-free pass over a large batch (inference): chunks through one engine, concatenated per level
+            parts = [self.forward(c) for c in x.split(EVAL_CHUNK)]
+            self._last_engine = None                       # (the bf16 pyramid only holds the last chunk)
+            return OrderedDict((k, torch.cat([p[k] for p in parts], 0)) for k in parts[0])
         x = x.contiguous().float()
         eng = self._engine(x)
         self._last_engine = (eng, eng.generation + 1)

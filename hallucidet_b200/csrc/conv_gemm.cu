@@ -28,7 +28,8 @@ namespace hd {
 constexpr int kMaxTaps = 9;
 constexpr int kEpiWarps = 8;                 // two warps per TMEM lane quadrant, each takes half of the N columns
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kCpWarps = 4;                  // cp.async A-operand producers (narrow-channel layers only)
+constexpr int kCpWarps = 2;                  // cp.async producers (A operand of the narrow-channel layers / add-mask ring); 12 warps in
+                                             // total = 384 threads, which lets ptxas give every thread 168 registers (448 -> 128)
 constexpr int kCpThreads = kCpWarps * 32;
 constexpr int kThreads = 64 + kEpiThreads + kCpThreads;
 
@@ -41,6 +42,7 @@ struct ConvGemmParams {
     int BN, BK;
     int kpt, kb_split;          // k-blocks per tap (all sources), k-blocks served by source 0
     int tap_begin[5];
+    int nst_phase[4];           // pipeline stages (k-steps / tps) of one tile, per phase
     int tap_dh[kMaxTaps], tap_dw[kMaxTaps], tap_p[kMaxTaps], tap_q[kMaxTaps], tap_bk[kMaxTaps];
     int a_qstride[2];
     int out_p[4], out_q[4];
@@ -60,6 +62,7 @@ struct ConvGemmParams {
     int stages, a_bytes, stage_bytes;
     int tmem_cols;
     int m_tiles, n_tiles, nphases;
+    int total_units;            // m_tiles * n_tiles * nphases
     // narrow-channel mode (BK < 64): TMA moves 32/64-byte rows one at a time (measured ~5-13 cycles per row), so the A
     // tile is gathered by four cp.async warps instead (16-byte copies, coalesced along W, L1-cached across the 9 taps)
     FastDiv fd_per_phase, fd_m_tiles, fd_tiles_w, fd_tiles_h, fd_TW;
@@ -107,8 +110,20 @@ __device__ __forceinline__ void decode_tile(const ConvGemmParams& P, int tile, i
     if (mt_out) *mt_out = mt;
 }
 
+// Compile-time switches (measured on the config-2 launch set, profiles/r2_conv_variants.txt):
+//   HD_CONV_SK  stream-K code paths.  OFF by default: with them compiled in, the short-K 1x1 layers lose ~12 % (44.7 -> 50 us at
+//               64 -> 256 channels, 160x160) even when stream-K is not selected, and where it IS selected the fp32 partial tiles
+//               through L2 cost more than the shorter main loop saves (profiles/r2_conv_timeline_v1.txt).  Build with
+//               HD_BUILD_STREAMK=1 (hallucidet_b200/build.py) + run with HD_STREAMK=1 to experiment.
+//   HD_CONV_DBG per-CTA %globaltimer stamps for tools/conv_timeline.py (free when the buffer pointer is null).
+#ifndef HD_CONV_DBG
+#define HD_CONV_DBG 1
+#endif
+#ifndef HD_CONV_SK
+#define HD_CONV_SK 0
+#endif
 __device__ __forceinline__ void dbg_stamp(const ConvGemmParams& P, int slot) {
-    if (P.dbg != nullptr) {
+    if (HD_CONV_DBG && P.dbg != nullptr) {
         long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         P.dbg[static_cast<long>(blockIdx.x) * 8 + slot] = t;
@@ -128,14 +143,14 @@ __device__ __forceinline__ long sk_range_begin(const ConvGemmParams& P, int cta)
     return static_cast<long>(cta) * (static_cast<long>(P.sk_tiles) * P.sk_nst) / gridDim.x;
 }
 __device__ __forceinline__ void walk_init(const ConvGemmParams& P, SegWalk& w) {
-    if (P.streamk) {
+    if (HD_CONV_SK && P.streamk) {
         w.it = sk_range_begin(P, blockIdx.x);
         w.it_end = sk_range_begin(P, blockIdx.x + 1);
     }
     w.tile = blockIdx.x;
 }
 __device__ __forceinline__ bool walk_next(const ConvGemmParams& P, SegWalk& w, Seg& s) {
-    if (P.streamk) {
+    if (HD_CONV_SK && P.streamk) {
         if (w.it >= w.it_end) return false;
         s.tile = static_cast<int>(fdiv(static_cast<uint32_t>(w.it), P.fd_sk_nst));
         s.sb = static_cast<int>(w.it - static_cast<long>(s.tile) * P.sk_nst);
@@ -145,11 +160,10 @@ __device__ __forceinline__ bool walk_next(const ConvGemmParams& P, SegWalk& w, S
         w.it += s.se - s.sb;
         return true;
     }
-    if (w.tile >= P.m_tiles * P.n_tiles * P.nphases) return false;
+    if (w.tile >= P.total_units) return false;
     s.tile = w.tile;
     w.tile += gridDim.x;
-    const int z = static_cast<int>(fdiv(s.tile, P.fd_per_phase));
-    s.nst = (P.tap_begin[z + 1] - P.tap_begin[z]) * P.kpt / P.tps;
+    s.nst = P.nphases == 1 ? P.nst_phase[0] : P.nst_phase[fdiv(s.tile, P.fd_per_phase)];
     s.sb = 0;
     s.se = s.nst;
     return true;
@@ -223,8 +237,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             while (walk_next(P, wk, sg)) {
                 int z, n0, img, h0, w0;
                 decode_tile(P, sg.tile, z, n0, img, h0, w0);
-                const int ks0 = sg.sb * P.tps;
-                int tap = P.tap_begin[z] + ks0 / P.kpt, kb = ks0 % P.kpt;
+                int tap = P.tap_begin[z], kb = 0;
+                if (sg.sb != 0) {                                    // (stream-K only: a range that starts inside the tile)
+                    const int ks0 = sg.sb * P.tps;
+                    tap += ks0 / P.kpt;
+                    kb = ks0 % P.kpt;
+                }
                 for (int st = sg.sb; st < sg.se; ++st) {
                     mbar_wait(empty0 + 8u * stage, phase ^ 1u);
                     const uint32_t sa = smem_base + stage * P.stage_bytes;
@@ -272,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 uint32_t accum = 0;
                 for (int st = 0; st < num_st; ++st) {
                     mbar_wait(full0 + 8u * stage, phase);
-                    if (P.dbg != nullptr && P.dbg[static_cast<long>(blockIdx.x) * 8 + 3] == 0) dbg_stamp(P, 3);   // first operands landed
+                    if (HD_CONV_DBG && P.dbg != nullptr && P.dbg[static_cast<long>(blockIdx.x) * 8 + 3] == 0) dbg_stamp(P, 3);   // first operands landed
                     if (P.cp_mode) fence_proxy_async_smem();   // cp.async wrote the A tile through the generic proxy
                     tc_fence_after();
                     const uint32_t a_u = base_u + stage * stage_u, b_u = a_u + a_bytes_u;
@@ -320,8 +338,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 const uint32_t dst_add = staging0 + b * aux_buf_bytes;
                 const uint32_t dst_mask = dst_add + (P.add != nullptr ? stg_bytes : 0u);
 #pragma unroll
-                for (int pass = 0; pass < 2; ++pass) {
-                    const int r = (pt >> 1) + 64 * pass;
+                for (int pass = 0; pass < 256 / kCpThreads; ++pass) {
+                    const int r = (pt >> 1) + (kCpThreads / 2) * pass;
                     const int rh = static_cast<int>(fdiv(r, P.fd_TW)), rw = r - rh * P.TW;
                     const int hg = h0 + rh, wg = w0 + rw;
                     const bool ok_row = (r < P.TW * P.TH) && hg < P.Hg && wg < P.Wg;
@@ -348,14 +366,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const int row_b = P.BK * 2;                            // 32 or 64 bytes per pixel row of the tile
             const int cpr = row_b / 16;                            // 16-byte chunks per row
             const uint32_t smask = cpr - 1;
-            const int per_thread = 128 * cpr / kCpThreads;         // 2 or 4
+            const int per_thread = 128 * cpr / kCpThreads;         // 4 or 8
             // everything that depends only on (thread, slot) is hoisted out of the tile / tap loops
-            int s_hl[4], s_wl[4];
-            uint32_t s_dst[4];
-            long s_off[4];
-            bool s_in[4];
+            constexpr int kSlots = 512 / kCpThreads;
+            int s_hl[kSlots], s_wl[kSlots];
+            uint32_t s_dst[kSlots];
+            long s_off[kSlots];
+            bool s_in[kSlots];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < kSlots; ++i) {
                 const int q = pt + kCpThreads * i;
                 const int r = q / cpr, ch = q - r * cpr;
                 s_hl[i] = r / P.TW;
@@ -382,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         const int dh = P.tap_dh[tap], dw = P.tap_dw[tap];
                         const long tap_off = (static_cast<long>(dh) * P.a_W + dw) * P.a_C + kb * P.BK;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
+                        for (int i = 0; i < kSlots; ++i) {
                             if (i < per_thread) {
                                 const int hi = h0 + s_hl[i] + dh, wi = w0 + s_wl[i] + dw;
                                 const bool ok = s_in[i] && static_cast<unsigned>(hi) < static_cast<unsigned>(P.a_H) &&
@@ -456,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         walk_init(P, wk);
         const long sk_slot_floats = 128L * P.BN;
         while (walk_next(P, wk, sg)) {
-            if (P.streamk && sg.sb != 0) {
+            if (HD_CONV_SK && P.streamk && sg.sb != 0) {
                 // ---- stream-K partial: this CTA's range starts inside the tile.  Dump the raw fp32 accumulator into this
                 // CTA's workspace slot ([chunk][quarter][row][4 floats]: every warp store is 512 contiguous bytes) and flag it.
                 mbar_wait(tfull0 + 8u * acc, acc_phase);
@@ -486,7 +505,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
             // stream-K head segment that does not cover the whole tile: the following CTAs hold the rest (their first segment)
             int np = 0, pj[4];
-            if (P.streamk && sg.se < sg.nst) {
+            if (HD_CONV_SK && P.streamk && sg.se < sg.nst) {
                 int rem = sg.nst - sg.se;
                 for (int j = blockIdx.x + 1; rem > 0 && np < 4; ++j) {
                     const long len = sk_range_begin(P, j + 1) - sk_range_begin(P, j);
@@ -505,7 +524,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const __nv_bfloat16* add_row = P.add != nullptr ? P.add + pix * P.Cout_total + n0 : nullptr;
             const __nv_bfloat16* mask_row = P.mask != nullptr ? P.mask + pix * P.Cout_total + n0 : nullptr;
 
-            if (!P.reg_store || np > 0) {
+            if (!P.reg_store || (HD_CONV_SK && np > 0)) {
                 if (et == 0) {
                     if (!P.reg_store) {
                         // this staging buffer was last used two tiles ago: its TMA store must have finished reading it
@@ -536,7 +555,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             // fused-operand or fp32-output bookkeeping
             auto chunk_loop = [&](auto fused_tag, auto f32_tag) {
             constexpr bool kFused = decltype(fused_tag)::value, kF32 = decltype(f32_tag)::value;
-            for (int c16 = c_begin; c16 < c_end; ++c16) {
+            // (kBatch > 1 puts several tcgen05.ld in flight before the wait; measured neutral -- 44.1 vs 44.7 us on the 64 -> 256
+            // 1x1 layer: that epilogue is bound by its scattered 32-byte sector stores, not by the TMEM round trip)
+            constexpr int kBatch = 1;
+            for (int cb = c_begin; cb < c_end; cb += kBatch) {
+            uint32_t acc_b[kBatch][16];
+            if (num_k > 0) {
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u)
+                    if (cb + u < c_end) tmem_ld16(t_acc + (cb + u) * 16, acc_b[u]);
+                tmem_ld_wait();
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int c16 = cb + u;
+                if (c16 < c_end) {
                 const int ch0 = n0 + c16 * 16;
                 const bool ch_ok = ch0 < P.Cout_total;
                 uint4 a0 = na0, a1 = na1, m0 = nm0, m1 = nm1;
@@ -558,18 +591,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     if (add_row) { const uint4* ap = reinterpret_cast<const uint4*>(add_row + (c16 + 1) * 16); na0 = ap[0]; na1 = ap[1]; }
                     if (mask_row) { const uint4* mp = reinterpret_cast<const uint4*>(mask_row + (c16 + 1) * 16); nm0 = __ldg(mp); nm1 = __ldg(mp + 1); }
                 }
-                uint32_t acc_r[16];
-                if (num_k > 0) {
-                    tmem_ld16(t_acc + c16 * 16, acc_r);
-                    tmem_ld_wait();
-                } else {                                   // phase without filter taps: epilogue-only (add / mask)
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) acc_r[j] = 0u;
-                }
                 float v[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc_r[j]);
-                for (int i = 0; i < np; ++i) {                          // + the partner partials, in CTA order (deterministic)
+                for (int j = 0; j < 16; ++j) v[j] = num_k > 0 ? __uint_as_float(acc_b[u][j]) : 0.f;   // (phase without taps: epilogue only)
+                for (int i = 0; HD_CONV_SK && i < np; ++i) {            // + the partner partials, in CTA order (deterministic)
                     const float4* slot = reinterpret_cast<const float4*>(P.sk_ws + static_cast<long>(pj[i]) * sk_slot_floats);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -651,6 +676,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d0), "r"(q0x), "r"(q0y), "r"(q0z), "r"(q0w) : "memory");
                     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(d1), "r"(q1x), "r"(q1y), "r"(q1z), "r"(q1w) : "memory");
                 }
+                }
+            }
             }
             };
             if (!fused && P.out_f32 == nullptr) chunk_loop(std::false_type{}, std::false_type{});
@@ -664,7 +691,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 if (++ab == 2) { ab = 0; aph ^= 1u; }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-            if (np > 0) {
+            if (HD_CONV_SK && np > 0) {
                 // every epilogue thread has consumed the partner partials: hand the slots back (next launch / next tile)
                 named_bar_sync(3, kEpiThreads);
                 if (et == 0)
@@ -862,7 +889,7 @@ static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStrea
     // stream-K when whole tiles quantise badly onto the SMs (one or two under-filled waves) and K is long enough to cut
     P.streamk = 0;
     P.m_tiles = P.tiles_w * P.tiles_h * n_img;
-    if (nphases == 1 && !P.cp_mode && P.tps == 1 && workspace != nullptr && streamk_enabled()) {
+    if (HD_CONV_SK && nphases == 1 && !P.cp_mode && P.tps == 1 && workspace != nullptr && streamk_enabled()) {
         const int sms = num_sms();
         const int nst = (P.tap_begin[1] - P.tap_begin[0]) * P.kpt;
         const long tiles = static_cast<long>(P.m_tiles) * P.n_tiles;
@@ -923,6 +950,8 @@ static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStrea
     P.fd_TW = make_fastdiv(static_cast<uint32_t>(P.TW));
     P.direct_store = (P.BN < 64 && P.Cout_total == P.BN && P.out_C0 == P.Cout_total && P.out_ptr != nullptr) ? 1 : 0;
     P.nphases = nphases;
+    P.total_units = static_cast<int>(static_cast<long>(P.m_tiles) * P.n_tiles * nphases);
+    for (int z = 0; z < nphases && z < 4; ++z) P.nst_phase[z] = (P.tap_begin[z + 1] - P.tap_begin[z]) * P.kpt / P.tps;
     P.dbg = g_conv_dbg;
     const size_t smem = static_cast<size_t>(fixed) + static_cast<size_t>(stages) * P.stage_bytes;
     static SmemAttrOnce smem_attr;
@@ -1071,7 +1100,7 @@ extern "C" int hd_conv_fwd_tiles(const hd_conv_args* a) {
     if (a->y0.c <= 0) return num_sms();
     const int bn = maybe_bn256(pick_bn(a->y0.c), a->kh, a->y0.c, static_cast<int>(m_tiles));
     const long units = m_tiles * ((a->y0.c + bn - 1) / bn);
-    if (streamk_enabled()) return num_sms();              // stream-K launches use every SM whatever the tile count
+    if (HD_CONV_SK && streamk_enabled()) return num_sms();   // stream-K launches use every SM whatever the tile count
     return static_cast<int>(units < num_sms() ? units : num_sms());
 }
 
@@ -1179,3 +1208,5 @@ extern "C" int hd_conv_debug_timestamps(void* buf) {
     g_conv_dbg = static_cast<long long*>(buf);
     return HD_OK;
 }
+
+extern "C" int hd_conv_has_streamk(void) { return HD_CONV_SK; }   // 1 if the library was built with the stream-K code paths

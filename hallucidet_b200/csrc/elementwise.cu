@@ -109,7 +109,18 @@ __host__ __device__ __forceinline__ bool pack_tiled_ok(const hd_pack_desc& d, in
            d.cin % 16 == 0 && d.cout_pad == d.cout && d.cin_pad == d.cin && d.k_pad == taps * d.cin;
 }
 
-__device__ void pack_tiled(const hd_pack_desc& d, int taps, int blk, int nblk, float* sm) {
+// One Adam step of one element (torch.optim.Adam: lerp of the moments, bias-corrected step) after scale + clip of the gradient.
+__device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, const hd_adam_args& A) {
+    g *= A.grad_scale;
+    if (A.clip > 0.f) g = fminf(fmaxf(g, -A.clip), A.clip);
+    m = m + (g - m) * A.one_minus_beta1;
+    v = A.beta2 * v + A.one_minus_beta2 * g * g;
+    const float denom = sqrtf(v) / sqrtf(A.bias_correction2) + A.eps;
+    return p - (A.lr / A.bias_correction1) * (m / denom);
+}
+
+template <bool kAdam>
+__device__ void pack_tiled(const hd_pack_desc& d, int taps, int blk, int nblk, float* sm, const hd_adam_args& A) {
     const int tci = d.cin % 64 == 0 ? 64 : (d.cin % 32 == 0 ? 32 : 16);
     const int ci_tiles = d.cin / tci, tiles = (d.cout / kPackCo) * ci_tiles;
     const int row = tci * taps, pitch = row + 1;                     // +1: the dgrad pass reads a column of 16 rows
@@ -120,7 +131,15 @@ __device__ void pack_tiled(const hd_pack_desc& d, int taps, int blk, int nblk, f
         __syncthreads();                                             // previous tile fully consumed
         for (int i = threadIdx.x; i < kPackCo * row; i += blockDim.x) {
             const int r = i / row, c = i - r * row;
-            float v = d.w[(static_cast<long>(co0 + r) * d.cin + ci0) * taps + c];
+            const long gi = (static_cast<long>(co0 + r) * d.cin + ci0) * taps + c;
+            float v = d.w[gi];
+            if (kAdam && d.g != nullptr) {                       // the optimizer step happens on the one read of the master weight
+                float mm = d.m[gi], vv = d.v[gi];
+                v = adam_update(v, d.g[gi], mm, vv, A);
+                const_cast<float*>(d.w)[gi] = v;
+                d.m[gi] = mm;
+                d.v[gi] = vv;
+            }
             if (d.scale) v *= d.scale[co0 + r];
             sm[r * pitch + c] = v;
         }
@@ -143,7 +162,8 @@ __device__ void pack_tiled(const hd_pack_desc& d, int taps, int blk, int nblk, f
     }
 }
 
-__global__ void pack_weights_multi_kernel(const hd_pack_desc* __restrict__ descs, int n, int total_blocks) {
+template <bool kAdam>
+__global__ void pack_weights_multi_kernel(const hd_pack_desc* __restrict__ descs, int n, int total_blocks, const hd_adam_args A) {
     pdl_trigger();
     pdl_wait();
     __shared__ float pack_sm[kPackCo * (kPackCiMax * kPackTapsMax + 1)];
@@ -152,7 +172,7 @@ __global__ void pack_weights_multi_kernel(const hd_pack_desc* __restrict__ descs
     const int taps = d.kh * d.kw;
     if (pack_tiled_ok(d, taps)) {
         const int next = li + 1 < n ? descs[li + 1].first_block : total_blocks;
-        pack_tiled(d, taps, blockIdx.x - d.first_block, next - d.first_block, pack_sm);
+        pack_tiled<kAdam>(d, taps, blockIdx.x - d.first_block, next - d.first_block, pack_sm, A);
         return;
     }
     const long n_fwd = static_cast<long>(d.cout_pad) * d.k_pad;
@@ -209,6 +229,23 @@ __global__ void unpack_wgrads_multi_kernel(const hd_unpack_desc* __restrict__ de
     }
 }
 
+__global__ void adam_multi_kernel(const hd_adam_desc* __restrict__ descs, int n, const hd_adam_args A) {
+    pdl_trigger();
+    pdl_wait();
+    const int li = find_desc(&descs[0].first_block, sizeof(hd_adam_desc) / sizeof(int), n, blockIdx.x);
+    const hd_adam_desc d = descs[li];
+    const long base = static_cast<long>(blockIdx.x - d.first_block) * blockDim.x * kMultiItems;
+#pragma unroll
+    for (int it = 0; it < kMultiItems; ++it) {
+        const long i = base + it * blockDim.x + threadIdx.x;
+        if (i >= d.n) break;
+        float mm = d.m[i], vv = d.v[i];
+        d.p[i] = adam_update(d.p[i], d.g[i], mm, vv, A);
+        d.m[i] = mm;
+        d.v[i] = vv;
+    }
+}
+
 // -------------------------------------------------------------------------------------------------
 // stem 7x7/2 patches
 // -------------------------------------------------------------------------------------------------
@@ -247,6 +284,49 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
             const int k = g * 8 + j;                           // k = (r*7 + s)*3 + c = r*21 + (s*3 + c)
             const int r = k / 21, rem = k - r * 21;
             f[j] = k < 147 ? __bfloat162float(sp[(2 * ohl + r) * kI2cPitch + 2 * owl * 3 + rem]) : 0.f;
+        }
+        bf8 o;
+        o.pack(f);
+        o.store(patches + ((static_cast<long>(b) * ho + oh) * wo + ow) * k_pad + g * 8);
+    }
+}
+
+// Single-channel variant for the hallucination U-Net: HalluciDet feeds the IR plane replicated three times
+// (src/utils/utils.py:52-53), so conv(W, [x, x, x]) == conv(sum_c W[:, c], x) exactly; the stem runs with K = 49 (padded to 64)
+// instead of 147 (padded to 160): 2.5x less patch traffic.  The input may be the uint8 camera plane itself (scale = 1/255:
+// the dataloader's ToTensor division, src/dataloader/dataloader.py:13-73) -- one byte per pixel over PCIe instead of four.
+template <typename T>
+__global__ void __launch_bounds__(256) stem_im2col1_kernel(const T* __restrict__ x, float scale, __nv_bfloat16* __restrict__ patches,
+                                                           int n, int h, int w, int k_pad) {
+    pdl_trigger();
+    pdl_wait();
+    constexpr int pitch = kI2cPW + 1;
+    __shared__ __nv_bfloat16 sp[kI2cPH * pitch];
+    const int ho = h / 2, wo = w / 2, groups = k_pad / 8;
+    const int tiles_w = (wo + kI2cTW - 1) / kI2cTW, tiles_h = (ho + kI2cTH - 1) / kI2cTH;
+    const int tile = blockIdx.x;
+    const int b = tile / (tiles_w * tiles_h), t2 = tile - b * tiles_w * tiles_h;
+    const int oh0 = (t2 / tiles_w) * kI2cTH, ow0 = (t2 % tiles_w) * kI2cTW;
+    const int ih0 = 2 * oh0 - 3, iw0 = 2 * ow0 - 3;
+    for (int q = threadIdx.x; q < kI2cPH * kI2cPW; q += blockDim.x) {
+        const int col = q % kI2cPW, row = q / kI2cPW;
+        const int ih = ih0 + row, iw = iw0 + col;
+        float v = 0.f;
+        if (ih >= 0 && ih < h && iw >= 0 && iw < w) v = static_cast<float>(x[(static_cast<long>(b) * h + ih) * w + iw]) * scale;
+        sp[row * pitch + col] = __float2bfloat16(v);
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < kI2cTH * kI2cTW * groups; q += blockDim.x) {
+        const int g = q % groups, p = q / groups;
+        const int ohl = p / kI2cTW, owl = p - ohl * kI2cTW;
+        const int oh = oh0 + ohl, ow = ow0 + owl;
+        if (oh >= ho || ow >= wo) continue;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = g * 8 + j;                           // k = r*7 + s
+            const int r = k / 7, c = k - r * 7;
+            f[j] = k < 49 ? __bfloat162float(sp[(2 * ohl + r) * pitch + 2 * owl + c]) : 0.f;
         }
         bf8 o;
         o.pack(f);
@@ -1297,9 +1377,25 @@ extern "C" int hd_pack_blocks(const hd_pack_desc* d) {
     return hd_multi_blocks(work);
 }
 
+extern "C" int hd_adam_pack_conv_weights(const hd_pack_desc* descs_dev, int n_layers, int total_blocks, const hd_adam_args* adam, hd_stream st) {
+    HD_CHECK_ARG(descs_dev != nullptr && adam != nullptr && n_layers > 0 && total_blocks > 0);
+    HD_CHECK_ARG(adam->bias_correction1 > 0.f && adam->bias_correction2 > 0.f);
+    HD_CUDA_OK(hd::launch(pack_weights_multi_kernel<true>, dim3(total_blocks), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), descs_dev, n_layers, total_blocks, *adam));
+    HD_CUDA_OK(cudaPeekAtLastError());
+    return HD_OK;
+}
+
+extern "C" int hd_adam_multi(const hd_adam_desc* descs_dev, int n_tensors, int total_blocks, const hd_adam_args* adam, hd_stream st) {
+    HD_CHECK_ARG(descs_dev != nullptr && adam != nullptr && n_tensors > 0 && total_blocks > 0);
+    HD_CHECK_ARG(adam->bias_correction1 > 0.f && adam->bias_correction2 > 0.f);
+    HD_CUDA_OK(hd::launch(adam_multi_kernel, dim3(total_blocks), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), descs_dev, n_tensors, *adam));
+    HD_CUDA_OK(cudaPeekAtLastError());
+    return HD_OK;
+}
+
 extern "C" int hd_pack_conv_weights(const hd_pack_desc* descs_dev, int n_layers, int total_blocks, hd_stream st) {
     HD_CHECK_ARG(descs_dev && n_layers > 0 && total_blocks > 0);
-    HD_CUDA_OK(hd::launch(pack_weights_multi_kernel, dim3(total_blocks), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), descs_dev, n_layers, total_blocks));
+    HD_CUDA_OK(hd::launch(pack_weights_multi_kernel<false>, dim3(total_blocks), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), descs_dev, n_layers, total_blocks, hd_adam_args{}));
     HD_LAUNCH_OK();
     return HD_OK;
 }
@@ -1317,6 +1413,20 @@ extern "C" int hd_stem_im2col(const float* x, void* patches, int n, int h, int w
     const int tiles = n * ((ho + kI2cTH - 1) / kI2cTH) * ((wo + kI2cTW - 1) / kI2cTW);
     HD_CUDA_OK(hd::launch(stem_im2col_kernel, dim3(tiles), dim3(256), 0, static_cast<cudaStream_t>(st), x, static_cast<__nv_bfloat16*>(patches), n, h, w, k_pad));
     HD_LAUNCH_OK();
+    return HD_OK;
+}
+
+extern "C" int hd_stem_im2col_1ch(const void* x, int x_dtype, float scale, void* patches, int n, int h, int w, int k_pad, hd_stream st) {
+    HD_CHECK_ARG(x != nullptr && patches != nullptr && n > 0 && h % 2 == 0 && w % 2 == 0 && k_pad % 8 == 0 && k_pad >= 56);
+    HD_CHECK_ARG(x_dtype == 0 || x_dtype == 1);
+    const int tiles = n * ((h / 2 + kI2cTH - 1) / kI2cTH) * ((w / 2 + kI2cTW - 1) / kI2cTW);
+    if (x_dtype == 0)
+        HD_CUDA_OK(hd::launch(stem_im2col1_kernel<float>, dim3(tiles), dim3(256), 0, static_cast<cudaStream_t>(st), static_cast<const float*>(x), scale,
+                              static_cast<__nv_bfloat16*>(patches), n, h, w, k_pad));
+    else
+        HD_CUDA_OK(hd::launch(stem_im2col1_kernel<unsigned char>, dim3(tiles), dim3(256), 0, static_cast<cudaStream_t>(st), static_cast<const unsigned char*>(x),
+                              scale, static_cast<__nv_bfloat16*>(patches), n, h, w, k_pad));
+    HD_CUDA_OK(cudaPeekAtLastError());
     return HD_OK;
 }
 

@@ -14,7 +14,9 @@ from ._lib import HdAct, HdBnFin, HdConvArgs, check
 
 STATS_REPLICAS = 16      # legacy name: default row count for small test problems (see conv_fwd_tiles)
 STEM_KPAD = 160          # 7*7*3 = 147 -> 5 k-blocks of 32
-STREAMK = True           # hand every fwd / dgrad launch the stream-K workspace (the library decides per problem)
+# Stream-K (hd_conv_args.workspace) is opt-in (HD_STREAMK=1): measured on the config-2 deep layers it shortens the main loop
+# (12.5 -> 8.7 us at 256 ch, 32x40) but the fp32 partial tiles through L2 cost more than that (profiles/r2_conv_timeline_v1.txt)
+STREAMK = __import__("os").environ.get("HD_STREAMK", "0") == "1"
 
 LAUNCHES = 0             # kernels launched through this module (one per C-ABI compute call; nms / roi_align_bwd add their second)
 PROFILE = None           # set to a list to record (name, algorithmic FLOPs, start event, end event, shape, bytes) per launch
@@ -251,14 +253,25 @@ def multi_blocks(elements):
     return int(_lib.load().hd_multi_blocks(ctypes.c_int64(int(elements))))
 
 
-def pack_table(packed_convs, weights, device):
-    """Descriptor table packing every (PackedConv, fp32 OIHW weight) pair in one launch (training mode: no BN scale)."""
+def pack_tiled_ok(pk):
+    """Mirror of pack_tiled_ok (csrc/elementwise.cu): layers whose master weight is read exactly once by the pack launch -- the
+    ones hd_adam_pack_conv_weights can update in place."""
+    return (pk.w_dgrad is not None and pk.w_t is None and pk.k * pk.k <= 9 and pk.cout % 16 == 0 and pk.cin % 16 == 0
+            and pk.cout_pad == pk.cout and pk.cin_pad == pk.cin and pk.k_pad == pk.k * pk.k * pk.cin)
+
+
+def pack_table(packed_convs, weights, device, adam=None):
+    """Descriptor table packing every (PackedConv, fp32 OIHW weight) pair in one launch (training mode: no BN scale).
+    ``adam``: optional list of (grad, exp_avg, exp_avg_sq) per layer (None entries = pack only) for adam_pack_conv_weights."""
     descs, first = [], 0
-    for pk, w in zip(packed_convs, weights):
+    for i, (pk, w) in enumerate(zip(packed_convs, weights)):
         assert w.dtype == torch.float32 and w.is_contiguous() and tuple(w.shape) == (pk.cout, pk.cin, pk.k, pk.k)
+        gmv = adam[i] if adam is not None else None
+        if gmv is not None:
+            assert pack_tiled_ok(pk) and all(t.dtype == torch.float32 and t.is_contiguous() and t.numel() == w.numel() for t in gmv)
         d = _lib.HdPackDesc(w.data_ptr(), None, pk.w_fwd.data_ptr(), pk.w_dgrad.data_ptr() if pk.w_dgrad is not None else None,
                             pk.w_t.data_ptr() if pk.w_t is not None else None, pk.cout, pk.cin, pk.k, pk.k, pk.cout_pad, pk.k_pad,
-                            pk.cin_pad, first)
+                            pk.cin_pad, first, *([t.data_ptr() for t in gmv] if gmv is not None else [None, None, None]))
         d._blocks = int(_lib.load().hd_pack_blocks(ctypes.byref(d)))
         d._key = w.data_ptr()
         first += d._blocks
@@ -269,6 +282,40 @@ def pack_table(packed_convs, weights, device):
 def pack_conv_weights(table):
     with _Timed("pack_conv_weights"):
         check(_lib.load().hd_pack_conv_weights(_ptr(table.dev), table.n, table.total_blocks, _stream()), "hd_pack_conv_weights")
+
+
+def adam_args(lr, beta1, beta2, eps, step, grad_scale=1.0, clip=0.0):
+    a = _lib.HdAdamArgs()
+    a.lr, a.beta1, a.beta2, a.eps = float(lr), float(beta1), float(beta2), float(eps)
+    a.bias_correction1, a.bias_correction2 = 1.0 - beta1 ** step, 1.0 - beta2 ** step
+    a.grad_scale, a.clip = float(grad_scale), float(clip)
+    a.one_minus_beta1, a.one_minus_beta2 = 1.0 - beta1, 1.0 - beta2
+    return a
+
+
+def adam_pack_conv_weights(table, args):
+    """clip + Adam + bf16 re-pack of every tiled layer in one pass over its master weight (hd_adam_pack_conv_weights)."""
+    with _Timed("adam_pack_conv_weights"):
+        check(_lib.load().hd_adam_pack_conv_weights(_ptr(table.dev), table.n, table.total_blocks, ctypes.byref(args), _stream()),
+              "hd_adam_pack_conv_weights")
+
+
+def adam_table(entries, device):
+    """entries: (param, grad, exp_avg, exp_avg_sq) fp32 contiguous tensors -> descriptor table of hd_adam_multi."""
+    descs, first = [], 0
+    for p, g, m, v in entries:
+        assert all(t.dtype == torch.float32 and t.is_contiguous() and t.numel() == p.numel() for t in (p, g, m, v))
+        d = _lib.HdAdamDesc(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), first)
+        d._blocks = multi_blocks(p.numel())
+        d._key = p.data_ptr()
+        first += d._blocks
+        descs.append(d)
+    return _DescTable(descs, device)
+
+
+def adam_multi(table, args):
+    with _Timed("adam_multi"):
+        check(_lib.load().hd_adam_multi(_ptr(table.dev), table.n, table.total_blocks, ctypes.byref(args), _stream()), "hd_adam_multi")
 
 
 def unpack_table(entries, device):
@@ -293,6 +340,18 @@ def stem_im2col(x_nchw, patches, k_pad=STEM_KPAD):
     assert c == 3 and x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()
     with _Timed("stem_im2col"):
         check(_lib.load().hd_stem_im2col(_ptr(x_nchw), _ptr(patches), n, h, w, k_pad, _stream()), "hd_stem_im2col")
+
+
+STEM1_KPAD = 64          # single-channel stem: 7*7 = 49 -> one k-block of 64
+
+
+def stem_im2col_1ch(x, patches, scale=1.0, k_pad=STEM1_KPAD):
+    """x: [n, 1, h, w] float32 or uint8 (the IR plane; ``scale`` = 1/255 for camera bytes) -> bf16 patches [n*ho*wo][k_pad]."""
+    n, c, h, w = x.shape
+    assert c == 1 and x.is_contiguous() and x.dtype in (torch.float32, torch.uint8)
+    with _Timed("stem_im2col"):
+        check(_lib.load().hd_stem_im2col_1ch(_ptr(x), 0 if x.dtype == torch.float32 else 1, float(scale), _ptr(patches), n, h, w, k_pad,
+                                             _stream()), "hd_stem_im2col_1ch")
 
 
 def stem_col2im(dpatches, dx_nchw, k_pad=STEM_KPAD):

@@ -17,6 +17,11 @@ from . import ops
 from .detection import Detector, install_b200_backbone
 from .unet import Unet
 
+import os as _os
+
+OVERLAP_ALLREDUCE = _os.environ.get("HD_OVERLAP_ALLREDUCE", "1") != "0"   # bucketed all-reduce underneath the backward pass
+FUSED_OPTIMIZER = _os.environ.get("HD_FUSED_ADAM", "1") != "0"     # clip + Adam + bf16 re-pack as one pass (optim.FusedAdam)
+
 LOSS_WEIGHTS = {                       # src/config/config.py:58-69
     "pixel_rgb": 0.0, "pixel_ir": 0.0, "perceptual_rgb": 0.0, "perceptual_ir": 0.0,
     "det_regression": 0.1, "det_classification": 0.1, "det_objectness": 0.1, "det_rpn_box_reg": 0.1,
@@ -117,7 +122,10 @@ class HostScalar:
 
 
 def expand_one_channel_to_output_channels(imgs, output_channels=3):
-    """src/utils/utils.py:52-53."""
+    """src/utils/utils.py:52-53 (``imgs.repeat(1, C, 1, 1)``) as a zero-copy broadcast view: same values for every reader; the
+    B200 U-Net recognises the broadcast (channel stride 0) and runs its stem on the single plane."""
+    if imgs.shape[1] == 1:
+        return imgs.expand(-1, output_channels, -1, -1)
     return imgs.repeat(1, output_channels, 1, 1)
 
 
@@ -143,15 +151,34 @@ class HalluciDetTrainer(nn.Module):
         install_b200_backbone(self.detector)
         self.encoder_decoder.use_cuda_graph = use_cuda_graph
         self.detector.backbone.use_cuda_graph = use_cuda_graph
-        # train_hallucidet.py:429-435 (Adam, lr 1e-4, default betas/eps); fused=True = one multi-tensor kernel, same maths
-        self.optimizer = torch.optim.Adam(self.encoder_decoder.parameters(), lr=lr, fused=True)
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self._bucket_works = []
+        if self.world > 1 and OVERLAP_ALLREDUCE:
+            # gradient buckets in reverse-forward order: [head, decoder, layer4] is all-reduced while the
+            # backward pass of layer3 .. stem is still running, [stem .. layer3] right after it
+            self.encoder_decoder.grad_bucket_hook = self._allreduce_bucket
+        # train_hallucidet.py:429-435 (Adam, lr 1e-4, default betas/eps) + clip_grad_value_(0.5) (:498-499) + the 1/world of the
+        # gradient mean: one pass over the parameters that also re-packs the bf16 operands (hallucidet_b200/optim.py)
+        if FUSED_OPTIMIZER:
+            from .optim import FusedAdam
+            self.optimizer = FusedAdam(self.encoder_decoder, lr=lr, clip_value=clip_value, grad_scale=1.0 / self.world)
+        else:
+            self.optimizer = torch.optim.Adam(self.encoder_decoder.parameters(), lr=lr, fused=True)
 
     def forward_step(self, imgs_rgb, targets_rgb, imgs_ir, targets_ir, det_seed=None):
         """train_hallucidet.py:161-240 -> dict(total, parts, hal)."""
         w = self.weights
-        ir3 = expand_one_channel_to_output_channels(imgs_ir, 3)
-        hal = self.encoder_decoder(ir3)
+        if imgs_ir.dtype == torch.uint8:
+            # the camera plane as the dataloader reads it (src/dataloader/dataloader.py:13-73): the /255 of ToTensor and the
+            # 1 -> 3 channel replication happen inside the U-Net's stem kernel; a float copy is made only if something else
+            # (regulariser, the reference's extra detector passes) needs it
+            hal = self.encoder_decoder.forward_ir(imgs_ir)
+            need_float = self.pixel is not None or self.reference_extra_passes
+            imgs_ir = imgs_ir.float().mul_(1.0 / 255.0) if need_float else None
+            ir3 = expand_one_channel_to_output_channels(imgs_ir, 3) if need_float else None
+        else:
+            ir3 = expand_one_channel_to_output_channels(imgs_ir, 3)
+            hal = self.encoder_decoder(ir3)
         if self.pixel is not None:
             reg = _PixelRegulariser.apply(hal, imgs_rgb, imgs_ir, self.pixel, w["pixel_rgb"], w["pixel_ir"])
             loss_pixel_rgb, loss_pixel_ir = reg[0], reg[1]
@@ -185,8 +212,12 @@ class HalluciDetTrainer(nn.Module):
         """eval_hallucidet.py:135-161 -- eval-mode hallucination (folded BN) + detector losses / detections on it
         (the reference also evaluates the RGB and IR images; enable with ``reference_extra_passes``)."""
         self.encoder_decoder.eval()
-        ir3 = expand_one_channel_to_output_channels(imgs_ir, 3)
-        hal = self.encoder_decoder(ir3)
+        if imgs_ir.dtype == torch.uint8:
+            hal = self.encoder_decoder.forward_ir(imgs_ir)
+            ir3 = expand_one_channel_to_output_channels(imgs_ir.float().mul_(1.0 / 255.0), 3) if self.reference_extra_passes else None
+        else:
+            ir3 = expand_one_channel_to_output_channels(imgs_ir, 3)
+            hal = self.encoder_decoder(ir3)
         if det_seed is not None:
             torch.manual_seed(det_seed)
         losses_hal, det_hal = Detector.calculate_loss(self.detector, hal, targets_ir, train_det=False, model_name=self.detector_name)
@@ -196,13 +227,34 @@ class HalluciDetTrainer(nn.Module):
             _, out["detections_ir"] = Detector.calculate_loss(self.detector, ir3, targets_ir, train_det=False, model_name=self.detector_name)
         return out
 
-    def allreduce_gradients(self):
-        """Mean of the per-replica gradients: one all-reduce over the U-Net's flat gradient block."""
+    def _allreduce_bucket(self, flat_slice):
+        """grad_bucket_hook of the U-Net engine: asynchronous all-reduce(sum) of one finished bucket.  NCCL orders it after the
+        work already enqueued on the current stream (the backward segment that produced the bucket) and runs it on its own
+        stream, next to the following segment."""
+        self._bucket_works.append((dist.all_reduce(flat_slice, op=dist.ReduceOp.SUM, async_op=True), flat_slice))
+
+    def allreduce_gradients(self, scale=True):
+        """Mean (``scale``) or sum of the per-replica gradients: one all-reduce over the U-Net's flat gradient block -- or, if the
+        buckets were already reduced during the backward pass (grad_bucket_hook), just the wait for them."""
         if self.world == 1:
             return
+        if self._bucket_works:
+            works, self._bucket_works = self._bucket_works, []
+            for w, _ in works:
+                w.wait()                                   # the compute stream waits for the communication stream (no host block)
+            if self._flat_grad() is not None:              # p.grad are views of the reduced block
+                if scale:
+                    for _, t in works:
+                        t.mul_(1.0 / self.world)
+                return
+            # (p.grad does not alias the flat block -- gradient accumulation: reduce the real gradients below)
         flat = self._flat_grad()
-        allreduce_mean_([flat] if flat is not None else [p.grad for p in self.encoder_decoder.parameters() if p.grad is not None],
-                        self.world)
+        tensors = [flat] if flat is not None else [p.grad for p in self.encoder_decoder.parameters() if p.grad is not None]
+        if scale:
+            allreduce_mean_(tensors, self.world)
+        else:
+            for t in tensors:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
     def _flat_grad(self):
         """The U-Net engine's flat fp32 gradient block, if the parameters' .grad tensors are views into it."""
@@ -241,8 +293,11 @@ class HalluciDetTrainer(nn.Module):
             self._loss_turn = (self._loss_turn + 1) % len(slots)
             out["total_host"] = HostScalar(out["total"].float(), slots[self._loss_turn])
         out["total"].backward()
-        self.allreduce_gradients()
-        self.clip_gradients()
+        if FUSED_OPTIMIZER:
+            self.allreduce_gradients(scale=False)        # sum over ranks; the 1/world, the clip and Adam run in the fused pass
+        else:
+            self.allreduce_gradients()
+            self.clip_gradients()
         self.optimizer.step()
         if isinstance(out["detections"], detection.DeferredDetections):
             out["detections"] = out["detections"].resolve()

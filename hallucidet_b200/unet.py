@@ -116,16 +116,16 @@ class Unet(nn.Module):
                                f"divisible by 32. Consider pad your images to shape ({new_h}, {new_w}).")
 
     def _engine(self, x):
-        key = (tuple(x.shape), x.device.index, self.training, self.segmentation_head[0].weight.data_ptr())
+        key = (tuple(x.shape), x.dtype, x.device.index, self.training, self.segmentation_head[0].weight.data_ptr())
         eng = self._engines.get(key)
         if eng is None:
             if len(self._engines) >= 4:
                 self._engines.clear()
-            eng = _UnetEngine(self, x.shape[0], x.shape[2], x.shape[3], x.device, self.training)
+            eng = _UnetEngine(self, x.shape[0], x.shape[2], x.shape[3], x.device, self.training, in_channels=x.shape[1], in_dtype=x.dtype)
             self._engines[key] = eng
         return eng
 
-    def forward(self, x):
+    def forward(self, x, in_scale=None):
         self.check_input_shape(x)
         if not x.is_cuda:
             raise RuntimeError("hallucidet_b200.Unet runs only on a CUDA (B200) device; there is no CPU path")
@@ -141,10 +141,35 @@ class Unet(nn.Module):
             # input gradient, so asking for one must not silently return zeros
             raise NotImplementedError("hallucidet_b200.Unet does not compute the gradient w.r.t. its input image; "
                                       "detach() the input (the reference never differentiates through the IR frame)")
-        x = x.contiguous().float()
+        if not self.training and not torch.is_grad_enabled() and x.shape[0] > EVAL_CHUNK:
+            # inference over a large batch (BASELINE config 5: 64 x 1024x1280): eval-mode BatchNorm is a per-pixel affine
+            # map, so the batch is run through ONE engine in chunks -- identical results, activation memory of one chunk
+            return torch.cat([self.forward(c, in_scale=in_scale) for c in x.split(EVAL_CHUNK)], 0)
+        if ONE_CHANNEL_STEM and x.shape[1] == 3 and x.stride(1) == 0:
+            # the IR plane broadcast to three channels (expand_one_channel_to_output_channels as a zero-copy view): the stem
+            # runs on the single plane with the channel-summed filter -- conv(W, [x, x, x]) == conv(sum_c W[:, c], x)
+            x = x[:, :1]
+        if x.shape[1] == 1:
+            if x.dtype != torch.uint8:
+                x = x.float()
+            x = x.contiguous()
+        else:
+            if x.shape[1] != 3:
+                raise RuntimeError(f"hallucidet_b200.Unet expects 3 input channels (or the single IR plane), got {x.shape[1]}")
+            x = x.contiguous().float()
         eng = self._engine(x)
+        eng.in_scale = float(in_scale) if in_scale is not None else (1.0 / 255.0 if x.dtype == torch.uint8 else 1.0)
         params = [p for _, p in eng.named_params]
         return _UnetFunction.apply(x, eng, sigmoid, *params)
+
+    def forward_ir(self, ir, in_scale=None):
+        """The hallucination of a SINGLE-channel IR batch ``[B, 1, H, W]`` -- float in [0, 1], or the uint8 camera plane
+        (then ``in_scale`` defaults to 1/255, the dataloader's division: src/dataloader/dataloader.py:13-73).  Equals
+        ``forward(ir.repeat(1, 3, 1, 1))`` (src/utils/utils.py:52-53 + train_hallucidet.py:170-171) without materialising
+        the copies: the stem convolves the plane with the channel-summed filter."""
+        if ir.dim() != 4 or ir.shape[1] != 1:
+            raise RuntimeError(f"forward_ir expects [B, 1, H, W], got {tuple(ir.shape)}")
+        return self.forward(ir, in_scale=in_scale)
 
     @torch.no_grad()
     def predict(self, x):
@@ -179,8 +204,12 @@ class _UnetFunction(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------------
 # execution engine: static buffers + kernel program for one (B, H, W, mode)
 # ------------------------------------------------------------------------------------------------------
+ONE_CHANNEL_STEM = os.environ.get("HD_STEM_1CH", "1") != "0"   # replicated IR plane -> single-channel stem (K = 49 instead of 147)
+EVAL_CHUNK = int(os.environ.get("HD_EVAL_CHUNK", "8"))       # images per engine pass in eval / no-grad mode
 SIDE_STREAM_WGRAD = os.environ.get("HD_SIDE_WGRAD", "1") != "0"
-FUSED_BN_BWD = os.environ.get("HD_BN_FUSED", "1") != "0"
+# one persistent launch for the BatchNorm backward (hd_bn_bwd_fused) is opt-in: 0.38 ms less GPU time per step, but its
+# full-register-file CTAs keep the side-stream work (weight gradients, detections) off the SMs: +1.4 ms per step measured
+FUSED_BN_BWD = os.environ.get("HD_BN_FUSED", "0") == "1"
 
 
 class _Layer:
@@ -204,8 +233,10 @@ class _Layer:
 
 
 class _UnetEngine:
-    def __init__(self, module, B, H, W, device, training):
+    def __init__(self, module, B, H, W, device, training, in_channels=3, in_dtype=torch.float32):
         self.m, self.B, self.H, self.W, self.device, self.training = module, B, H, W, device, training
+        self.one_ch = in_channels == 1
+        self.in_scale = 1.0
         self.acts = []
         enc, dec = module.encoder, module.decoder
         self.named_params = [(n, p) for n, p in module.named_parameters()]
@@ -213,15 +244,22 @@ class _UnetEngine:
         sizes = [p.numel() for _, p in self.named_params]
         self.flat_grad = torch.zeros(sum(sizes), device=device)
         self.grad_views, off = {}, 0
+        self.bucket_split = None                            # first element of the "late" bucket (encoder.layer4 onwards)
         for (n, p), s in zip(self.named_params, sizes):
+            if self.bucket_split is None and n.startswith("encoder.layer4."):
+                self.bucket_split = off
             self.grad_views[n] = self.flat_grad[off:off + s].view_as(p)
             off += s
 
         h2, w2 = H // 2, W // 2
         # ---- stem (7x7/2 via patches GEMM)
-        self.stem = _Layer(self, "encoder.conv1", enc.conv1, enc.bn1, 3, 64, 7, 2, (H, W),
-                           packed=ops.PackedConv(64, 3, 7, device, need_dgrad=False, k_pad=ops.STEM_KPAD))
-        self.patches = torch.empty(1, 1, B * h2 * w2, ops.STEM_KPAD, dtype=torch.bfloat16, device=device)
+        self.stem_kpad = ops.STEM1_KPAD if self.one_ch else ops.STEM_KPAD
+        self.stem = _Layer(self, "encoder.conv1", enc.conv1, enc.bn1, 1 if self.one_ch else 3, 64, 7, 2, (H, W),
+                           packed=ops.PackedConv(64, 1 if self.one_ch else 3, 7, device, need_dgrad=False, k_pad=self.stem_kpad))
+        self.patches = torch.empty(1, 1, B * h2 * w2, self.stem_kpad, dtype=torch.bfloat16, device=device)
+        if self.one_ch:
+            self.stem_w1 = torch.empty(64, 1, 7, 7, device=device)      # channel-summed stem filter (re-summed at every pack)
+            self.stem_g1 = torch.empty(64, 1, 7, 7, device=device)      # its gradient (== the gradient of every input channel's filter)
         self.a_stem = self.new_act(h2, w2, 64)
         self.p0 = self.new_act(h2 // 2, w2 // 2, 64)
         self.p0_idx = torch.empty(B, h2 // 2, w2 // 2, 64, dtype=torch.uint8, device=device)   # max-pool arg-max positions
@@ -275,7 +313,7 @@ class _UnetEngine:
         for l in self.all_layers:
             l.dw_off = tot
             l.dw_rows = l.cp
-            l.dw_cols = l.k * l.k * l.cin if l is not self.stem else ops.STEM_KPAD
+            l.dw_cols = l.k * l.k * l.cin if l is not self.stem else self.stem_kpad
             tot += l.dw_rows * l.dw_cols
         # ... followed by the BatchNorm backward sums of every layer, so that the same fill zeroes them too
         bn_layers = [l for l in self.all_layers if getattr(l, "sums", None) is not None]
@@ -294,11 +332,12 @@ class _UnetEngine:
         self.grad_bufs = {}
         self.side_stream, self.side_used = None, False
         self.pack_tab = self.unpack_tab = None
+        self._packed_key = None
         self._bn_keys = None
         self.graphs = {}
         self.sigmoid = None
         self.generation = 0
-        self.x_in = torch.empty(B, 3, H, W, device=device)
+        self.x_in = torch.empty(B, in_channels, H, W, dtype=in_dtype, device=device)
         self.dhal_in = torch.empty(B, module.classes, H, W, device=device)
         self.nbt = [m.num_batches_tracked for m in module.modules() if isinstance(m, nn.BatchNorm2d)]
 
@@ -316,7 +355,13 @@ class _UnetEngine:
         return t
 
     def _pack_sources(self):
-        return [self.head_w_pad if l is self.head else l.conv.weight.detach() for l in self.all_layers]
+        def src(l):
+            if l is self.head:
+                return self.head_w_pad
+            if l is self.stem and self.one_ch:
+                return self.stem_w1
+            return l.conv.weight.detach()
+        return [src(l) for l in self.all_layers]
 
     def _check_tables(self):
         """(Re)build the device descriptor tables of the one-launch weight packing / gradient unpacking.  They hold raw
@@ -332,18 +377,52 @@ class _UnetEngine:
         assert all(w.is_contiguous() for w in srcs)
         self.pack_tab = ops.pack_table([l.packed for l in self.all_layers], srcs, self.device)
         gv = self.grad_views
-        entries = [(l.dw, gv[l.name + ".weight"], l.cout, l.cin, l.k, l.cin, l.k * l.k * l.cin) for l in self.all_layers if l is not self.stem]
-        entries.append((self.stem.dw, gv["encoder.conv1.weight"], 64, 3, 7, 3, ops.STEM_KPAD))
-        self.unpack_tab = ops.unpack_table(entries, self.device)
+        def late(l):                                         # head, decoder, encoder.layer4: see _backward_late
+            return not l.name.startswith("encoder.") or l.name.startswith("encoder.layer4.")
+        convs = [l for l in self.all_layers if l is not self.stem]
+        ent = lambda l: (l.dw, gv[l.name + ".weight"], l.cout, l.cin, l.k, l.cin, l.k * l.k * l.cin)
+        early = [ent(l) for l in convs if not late(l)]
+        if self.one_ch:
+            early.append((self.stem.dw, self.stem_g1, 64, 1, 7, 1, self.stem_kpad))
+        else:
+            early.append((self.stem.dw, gv["encoder.conv1.weight"], 64, 3, 7, 3, self.stem_kpad))
+        self.unpack_tab_late = ops.unpack_table([ent(l) for l in convs if late(l)], self.device)
+        self.unpack_tab_early = ops.unpack_table(early, self.device)
+        self.unpack_tab = self.unpack_tab_early
+        self._packed_key = None
         self.graphs.clear()
+
+    def _version_key(self):
+        """Changes whenever a parameter (or, in eval mode, a BatchNorm buffer) may have changed: in-place torch updates bump
+        ``_version``; the fused optimizer (raw-pointer writes) bumps ``module._param_generation``; the BatchNorm kernels
+        (raw-pointer writes to the running statistics) are followed by the ``num_batches_tracked`` increment."""
+        key = [getattr(self.m, "_param_generation", 0)] + [p._version for _, p in self.named_params]
+        if not self.training:
+            key += [b._version for b in self.m.buffers()]
+        return key
+
+    def _pack_prologue(self):
+        """Small staging copies the pack launch reads: the head weight / bias padded to 16 channels, the channel-summed stem filter."""
+        if self.one_ch:
+            torch.sum(self.stem.conv.weight.detach(), dim=1, keepdim=True, out=self.stem_w1)
+        hd = self.head
+        self.head_w_pad[:hd.cout].copy_(hd.conv.weight.detach())
+        self.head_bias_pad[:hd.cout].copy_(hd.conv.bias.detach())
+
+    def mark_weights_packed(self):
+        """The bf16 operands of THIS engine match the fp32 masters (called by hallucidet_b200.optim.FusedAdam, whose kernel
+        re-packs while it updates): the next forward skips the pack launch.  Other engines of the module (eval mode) are told
+        that the parameters moved."""
+        self.m._param_generation = getattr(self.m, "_param_generation", 0) + 1
+        self._packed_key = self._version_key()
 
     def _pack_weights(self):
         if self.training:                                 # one launch for all layers (fp32 masters -> bf16 GEMM operands)
-            hd = self.head
-            self.head_w_pad[:hd.cout].copy_(hd.conv.weight.detach())
-            self.head_bias_pad[:hd.cout].copy_(hd.conv.bias.detach())
+            self._pack_prologue()
             ops.pack_conv_weights(self.pack_tab)
             return
+        if self.one_ch:
+            torch.sum(self.stem.conv.weight.detach(), dim=1, keepdim=True, out=self.stem_w1)
         for l in self.all_layers:
             if l is self.head:
                 self.head_w_pad[:l.cout].copy_(l.conv.weight.detach())
@@ -355,7 +434,8 @@ class _UnetEngine:
                 bn = l.bn
                 scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
                 l.bias.copy_(bn.bias.detach() - bn.running_mean * scale)
-                l.packed.pack(l.conv.weight.detach().contiguous(), scale.contiguous())
+                w = self.stem_w1 if (l is self.stem and self.one_ch) else l.conv.weight.detach().contiguous()
+                l.packed.pack(w, scale.contiguous())
 
     def _bn_fin(self, l, count):
         """The layer's hd_bn_fin descriptor (raw pointers to its BatchNorm parameters / buffers; rebuilt if they moved)."""
@@ -411,6 +491,10 @@ class _UnetEngine:
             self.graphs.clear()
         self.sigmoid = sigmoid
         self._check_tables()
+        key = self._version_key()
+        if key != self._packed_key:                          # (skipped when the fused optimizer has just re-packed, and in
+            self._pack_weights()                             #  eval mode while the weights are unchanged)
+            self._packed_key = key
         self.x_in.copy_(x)
         self._run("fwd", self._forward_impl)
         self.generation += 1
@@ -430,7 +514,16 @@ class _UnetEngine:
         # handed to autograd as a separate tensor, and AccumulateGrad adds them in place: p.grad (still a view of
         # flat_grad) ends up as old + new, as with any other module.
         saved = self.flat_grad.clone() if self._grads_alias_flat(params) else None
-        self._run("bwd", self._backward_impl)
+        hook = getattr(self.m, "grad_bucket_hook", None)
+        if hook is not None and saved is None:
+            # data parallelism: the two gradient buckets are handed to the hook (an asynchronous all-reduce) as soon as they are
+            # final -- the first one while the rest of the backward pass still runs (reverse-forward bucket order)
+            self._run("bwd_late", self._backward_late)
+            hook(self.flat_grad[self.bucket_split:])
+            self._run("bwd_early", self._backward_early)
+            hook(self.flat_grad[:self.bucket_split])
+        else:
+            self._run("bwd", self._backward_impl)
         alias_ok = saved is None and all(p.grad is None for p in params)
         src = self.flat_grad if alias_ok else self.flat_grad.clone()
         if saved is not None:
@@ -445,19 +538,22 @@ class _UnetEngine:
     def _forward_impl(self):
         sigmoid = self.sigmoid
         x = self.x_in
-        self._pack_weights()
         st = self.stem
-        ops.stem_im2col(x, self.patches)
+        if self.one_ch:
+            ops.stem_im2col_1ch(x, self.patches, scale=self.in_scale, k_pad=self.stem_kpad)
+        else:
+            ops.stem_im2col(x, self.patches)
+        stem_k = 49 if self.one_ch else 147
         zs = st.z.view(1, 1, -1, 64)
         a_stem_flat = self.a_stem.view(1, 1, -1, 64)
         if self.training:
             if st.stats is None:
                 st.stats = torch.zeros(ops.conv_fwd_tiles(self.patches, 1, 1), 2, 64, device=self.device)
-            ops.conv_fwd(ops.conv_args(self.patches, zs, st.packed.w_fwd, k=1, stats=st.stats, algo_cin=147,
+            ops.conv_fwd(ops.conv_args(self.patches, zs, st.packed.w_fwd, k=1, stats=st.stats, algo_cin=stem_k,
                                        bn_fin=self._bn_fin(st, zs.shape[2])))
             ops.bn_apply(zs, st.scale, st.shift, a_stem_flat, relu=True)
         else:
-            ops.conv_fwd(ops.conv_args(self.patches, a_stem_flat, st.packed.w_fwd, k=1, bias=st.bias, relu=True, algo_cin=147))
+            ops.conv_fwd(ops.conv_args(self.patches, a_stem_flat, st.packed.w_fwd, k=1, bias=st.bias, relu=True, algo_cin=stem_k))
         ops.maxpool_fwd(self.a_stem, self.p0, idx=self.p0_idx if self.training else None)
         x_in = self.p0
         feats = {1: self.a_stem}
@@ -525,7 +621,19 @@ class _UnetEngine:
     def _wgrad(self, l, x0, dz, x1=None):
         self._on_side(lambda: ops.conv_wgrad(ops.conv_args(x0, dz, k=l.k, stride=l.stride, x1=x1, dw=l.dw, algo_cout=l.cout)))
 
+    def _join_side(self):
+        if self.side_used:                                   # join: every weight-gradient accumulator issued so far is complete
+            torch.cuda.current_stream().wait_stream(self.side_stream)
+            self.side_used = False
+
     def _backward_impl(self):
+        self._backward_late()
+        self._backward_early()
+
+    def _backward_late(self):
+        """Head, decoder and encoder.layer4: the LAST parameters of the model = a contiguous suffix of the flat gradient
+        block (24.4 M parameters: 16.3 M here).  Under data parallelism this bucket is all-reduced while ``_backward_early``
+        (layer3 .. stem) still computes."""
         dhal = self.dhal_in
         self.dw_flat.zero_()
         hd = self.head
@@ -555,8 +663,21 @@ class _UnetEngine:
             ops.upsample2x_bwd(g_up, g)
         # skips: decoder block 0 <- f4 (layer3 out), 1 <- f3 (layer2 out), 2 <- f2 (layer1 out), 3 <- f1 (stem)
         skip_for_layer = {3: skip_grads[0], 2: skip_grads[1], 1: skip_grads[2]}
-        # ---- encoder
-        for blk in reversed(self.blocks):
+        # ---- encoder.layer4
+        self._bw_state = (g, skip_grads, skip_for_layer)
+        g = self._backward_blocks([b for b in self.blocks if b["li"] == 4], g, skip_for_layer)
+        self._bw_state = (g, skip_grads, skip_for_layer)
+        self._join_side()
+        ops.unpack_wgrads(self.unpack_tab_late)
+
+    def _backward_early(self):
+        """encoder.layer3 .. stem (the prefix of the flat gradient block)."""
+        g, skip_grads, skip_for_layer = self._bw_state
+        g = self._backward_blocks([b for b in self.blocks if b["li"] < 4], g, skip_for_layer)
+        self._backward_stem(g, skip_grads)
+
+    def _backward_blocks(self, blocks, g, skip_for_layer):
+        for blk in reversed(blocks):
             c1, c2, cd = blk["c1"], blk["c2"], blk["cd"]
             g_masked = self.gbuf(("gm", c2.name), blk["out"]) if cd is None else None
             dz2 = self._bn_bwd(c2, g, blk["out"], g_out=g_masked)
@@ -576,14 +697,17 @@ class _UnetEngine:
                 self._wgrad(cd, x_in, dzd)
                 ops.conv_dgrad(ops.conv_args(dzd, g_x, cd.packed.w_dgrad, k=1, stride=cd.stride, add=g_x))
             g = g_x
+        return g
+
+    def _backward_stem(self, g, skip_grads):
         # ---- stem: max-pool backward (+ decoder skip of f1), BN backward, weight gradient through the patch GEMM
         st = self.stem
         g_stem = self.gbuf(("g", "stem"), self.a_stem)
         ops.maxpool_bwd(self.a_stem, self.p0, g, g_stem, add=skip_grads[3], idx=self.p0_idx)
         zs = st.z.view(1, 1, -1, 64)
         dzs = self._bn_bwd(st, g_stem.view(1, 1, -1, 64), self.a_stem.view(1, 1, -1, 64), z=zs, direct_relu=True)
-        self._on_side(lambda: ops.conv_wgrad(ops.conv_args(self.patches, dzs, k=1, dw=st.dw, algo_cin=147)))
-        if self.side_used:                                   # join: every weight-gradient accumulator is complete
-            torch.cuda.current_stream().wait_stream(self.side_stream)
-            self.side_used = False
-        ops.unpack_wgrads(self.unpack_tab)                   # all layers: packed fp32 accumulators -> the flat OIHW gradient block
+        self._on_side(lambda: ops.conv_wgrad(ops.conv_args(self.patches, dzs, k=1, dw=st.dw, algo_cin=49 if self.one_ch else 147)))
+        self._join_side()
+        ops.unpack_wgrads(self.unpack_tab_early)             # packed fp32 accumulators -> the flat OIHW gradient block
+        if self.one_ch:                                      # x_c identical for all c  =>  dL/dW[:, c] identical: broadcast
+            self.grad_views["encoder.conv1.weight"].copy_(self.stem_g1.expand(-1, 3, -1, -1))

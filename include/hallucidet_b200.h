@@ -101,6 +101,7 @@ int hd_conv_fwd(const hd_conv_args* a, hd_stream stream);
 int hd_conv_fwd_tiles(const hd_conv_args* a);   /* statistics rows hd_conv_fwd needs for this problem (= CTAs of its grid; with y0.c unset: an upper bound); host-only, no launch */
 int hd_conv_dgrad(const hd_conv_args* a, hd_stream stream);
 int64_t hd_conv_workspace_bytes(void);           /* size of hd_conv_args.workspace */
+int hd_conv_has_streamk(void);                   /* 1 if built with the (experimental, default-off) stream-K code paths */
 /* Development aid (tools/conv_timeline.py): later hd_conv_fwd / hd_conv_dgrad launches write 8 %globaltimer stamps per CTA
  * into buf ([grid][8] int64, zeroed by the caller before each launch): kernel start, dependencies resolved, last TMA issued,
  * first operands landed, last MMA issued, last accumulator complete, epilogue done, CTA exit.  NULL = off (default). */
@@ -131,7 +132,29 @@ typedef struct hd_pack_desc {
     void* w_dgrad;        /* [cin_pad][kh*kw*cout] bf16 or NULL */
     void* w_t;            /* [k_pad][cout_pad] bf16 or NULL */
     int32_t cout, cin, kh, kw, cout_pad, k_pad, cin_pad, first_block;
+    /* hd_adam_pack_conv_weights only: gradient and Adam moments of `w` (same OIHW layout), all NULL = pack only.  Allowed
+     * only for layers of the tiled path (cout % 16 == 0, cin % 16 == 0, both bf16 layouts, no padding): there every master
+     * weight is read exactly once per launch, so the update happens on that read. */
+    const float* g;
+    float* m;
+    float* v;
 } hd_pack_desc;
+/* Adam hyper-parameters of one step (torch.optim.Adam, no weight decay / amsgrad; train_hallucidet.py:429-435,
+ * src/config/config.py:215-219) with the gradient post-processing of the reference's loop fused in: g <- clamp(g * grad_scale,
+ * -clip, clip) (grad_scale = 1/world after a summing all-reduce; clip_grad_value_(0.5), train_hallucidet.py:498-499; clip <= 0: off). */
+typedef struct hd_adam_args {
+    float lr, beta1, beta2, eps;
+    float bias_correction1, bias_correction2;     /* 1 - beta^t of this step */
+    float grad_scale, clip;
+    float one_minus_beta1, one_minus_beta2;       /* computed in double by the caller (1 - 0.999f is 4.7e-5 off in fp32) */
+} hd_adam_args;
+typedef struct hd_adam_desc {   /* one small parameter tensor of hd_adam_multi */
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    int32_t n, first_block;
+} hd_adam_desc;
 typedef struct hd_unpack_desc {
     const float* dw;      /* packed fp32 weight gradient (see hd_conv_wgrad) */
     float* g;             /* fp32 OIHW gradient */
@@ -143,11 +166,22 @@ int hd_multi_blocks(int64_t elements);
 int hd_pack_blocks(const hd_pack_desc* desc_host);   /* blocks one layer occupies in hd_pack_conv_weights (for first_block) */
 int hd_pack_conv_weights(const hd_pack_desc* descs_dev, int n_layers, int total_blocks, hd_stream stream);
 int hd_unpack_wgrads(const hd_unpack_desc* descs_dev, int n_layers, int total_blocks, hd_stream stream);
+/* The optimizer tail in one pass over the parameters: hd_pack_conv_weights whose tiled layers ALSO apply
+ * clip + Adam to the fp32 master weight as they read it (p, m, v written back, then both bf16 operand layouts from the new
+ * value) -- instead of clamp, multi-tensor Adam and re-pack as three passes.  Layers with g == NULL are packed only. */
+int hd_adam_pack_conv_weights(const hd_pack_desc* descs_dev, int n_layers, int total_blocks, const hd_adam_args* adam, hd_stream stream);
+/* Element-wise Adam (same arithmetic) for the tensors that are not on the tiled path: BatchNorm weights / biases, the head, the stem.
+ * first_block = running sum of hd_multi_blocks(n) over the preceding descriptors. */
+int hd_adam_multi(const hd_adam_desc* descs_dev, int n_tensors, int total_blocks, const hd_adam_args* adam, hd_stream stream);
 
 /* ---- stem 7x7 stride-2 pad-3 conv via explicit patches (cin = 3 is not TMA-addressable) --------------
  * Replaces encoder.conv1 (encoders/resnet.py:50) and body.conv1 (TV: models/resnet.py:197) im2col/col2im.
  * x fp32 NCHW [n][3][h][w] -> patches bf16 [n*ho*wo][k_pad], k = (r*7+s)*3 + c, ho = h/2, wo = w/2. */
 int hd_stem_im2col(const float* x_nchw, void* patches, int n, int h, int w, int k_pad, hd_stream stream);
+/* Single-channel stem input (the U-Net's IR plane, replicated x3 by src/utils/utils.py:52-53 -> conv with the channel-summed
+ * filter): x [n][1][h][w] as fp32 (x_dtype 0) or uint8 (x_dtype 1), multiplied by `scale` (1/255 for the camera bytes,
+ * src/dataloader/dataloader.py:13-73) -> patches bf16 [n*ho*wo][k_pad], k = r*7 + s (49 taps, zero padded to k_pad >= 56). */
+int hd_stem_im2col_1ch(const void* x, int x_dtype, float scale, void* patches, int n, int h, int w, int k_pad, hd_stream stream);
 /* dpatches bf16 [n*ho*wo][k_pad] -> dx fp32 NCHW [n][3][h][w] (overwrites). */
 int hd_stem_col2im(const void* dpatches, float* dx_nchw, int n, int h, int w, int k_pad, hd_stream stream);
 

@@ -20,6 +20,23 @@ def _worker(rank, world, port, results):
     dist.all_gather(gathered, mine)
     want = sum(gathered) / world
     ok = torch.allclose(flat, want, atol=1e-6)
+    # bucketed, overlapped path (grad_bucket_hook): two asynchronous bucket all-reduces in reverse-forward order, then the wait
+    from hallucidet_b200.train import HalluciDetTrainer
+    t = HalluciDetTrainer.__new__(HalluciDetTrainer)
+    torch.nn.Module.__init__(t)
+    t.world, t._bucket_works = world, []
+    flat2 = mine.clone()
+    t._flat_grad = lambda: flat2
+    t._allreduce_bucket(flat2[600:])          # "late" bucket first (head, decoder, layer4)
+    t._allreduce_bucket(flat2[:600])
+    t.allreduce_gradients(scale=True)
+    ok = ok and torch.allclose(flat2, want, atol=1e-6) and not t._bucket_works
+    flat3 = mine.clone()
+    t._flat_grad = lambda: flat3
+    t._allreduce_bucket(flat3[600:])
+    t._allreduce_bucket(flat3[:600])
+    t.allreduce_gradients(scale=False)        # fused optimizer: the sum is kept, 1/world is applied by the Adam kernel
+    ok = ok and torch.allclose(flat3, want * world, atol=1e-5)
     sl = shard_batch(16, rank, world)
     ok = ok and (sl.start, sl.stop) == (rank * 8, rank * 8 + 8)
     results[rank] = bool(ok)

@@ -728,6 +728,17 @@ def test_conv_streamk_epilogue_stats_add_mask_deterministic():
     """Stream-K launches (partial accumulators through the workspace, reduced in CTA order): fused epilogue operands and the
     BatchNorm statistics are unaffected, results are bit-identical run to run, and HD-level parity holds vs fp32 PyTorch."""
     o = ops()
+    from hallucidet_b200 import _lib
+    if not _lib.load().hd_conv_has_streamk():
+        pytest.skip("library built without the experimental stream-K paths (HD_BUILD_STREAMK=1)")
+    was, o.STREAMK = o.STREAMK, True                      # opt-in path (HD_STREAMK=1): conv_args attaches the workspace
+    try:
+        _streamk_case(o)
+    finally:
+        o.STREAMK = was
+
+
+def _streamk_case(o):
     n, h, w, cin, cout = 8, 32, 40, 256, 256
     x = rnd(n, h, w, cin, seed=1)
     wt = (torch.randn(cout, cin, 3, 3, generator=torch.Generator().manual_seed(3)) / (cin * 9) ** 0.5).to(torch.bfloat16).float().cuda()
@@ -757,3 +768,49 @@ def test_conv_streamk_epilogue_stats_add_mask_deterministic():
     assert_close_bf16(nchw(y2), ref2, "stream-K fused epilogue")
     ws = o.conv_workspace(x.device)
     assert int(ws[:4096].view(torch.int32).abs().sum()) == 0        # every partial flag was handed back
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 40, 40), (2, 5, 5), (2, 3, 3), (2, 75, 75)])
+def test_head_tower_kernel_shapes(n, h, w):
+    """The launches hallucidet_b200/heads.py issues: 1x1 256 -> 16 predictor with a channels-last fp32 output, its
+    input gradient (K = 16 per tap) with a ReLU mask, and the 3x3 input gradient written as channels-last fp32 only."""
+    o = ops()
+    c = 256
+    x = rnd(n, h, w, c, seed=1)
+    # predictor forward
+    wp = (torch.randn(16, c, 1, 1, generator=torch.Generator().manual_seed(3)) / c ** 0.5).to(torch.bfloat16).float().cuda()
+    bias = torch.randn(16, device="cuda")
+    pk = o.PackedConv(16, c, 1, "cuda").pack(wp)
+    dummy = torch.empty(n, h, w, 16, dtype=torch.bfloat16, device="cuda")
+    pred = torch.full((n, h, w, 16), float("nan"), device="cuda")
+    o.conv_fwd(o.conv_args(x, dummy, pk.w_fwd, k=1, bias=bias, out_f32=pred, out_f32_channels=16, out_f32_nhwc=True, store_bf16=False))
+    torch.cuda.synchronize()
+    ref = F.conv2d(nchw(x), wp, bias)
+    assert torch.allclose(pred.permute(0, 3, 1, 2), ref, rtol=1e-3, atol=1e-3 * ref.abs().max().item())
+    # predictor input gradient with the ReLU mask
+    dy = rnd(n, h, w, 16, seed=4)
+    mask = rnd(n, h, w, c, seed=5)
+    g = torch.full((n, h, w, c), float("nan"), dtype=torch.bfloat16, device="cuda")
+    o.conv_dgrad(o.conv_args(dy, g, pk.w_dgrad, k=1, mask=mask))
+    torch.cuda.synchronize()
+    ref_g = torch.nn.grad.conv2d_input((n, c, h, w), wp, nchw(dy)) * (nchw(mask) > 0)
+    assert_close_bf16(nchw(g), ref_g, "predictor dgrad (K=16, mask)")
+    # 3x3 input gradient, fp32 channels-last output only
+    w3 = (torch.randn(c, c, 3, 3, generator=torch.Generator().manual_seed(6)) / (c * 9) ** 0.5).to(torch.bfloat16).float().cuda()
+    pk3 = o.PackedConv(c, c, 3, "cuda").pack(w3)
+    dy3 = rnd(n, h, w, c, seed=7)
+    dx = torch.full((n, h, w, c), float("nan"), device="cuda")
+    dummy3 = torch.empty(n, h, w, c, dtype=torch.bfloat16, device="cuda")
+    o.conv_dgrad(o.conv_args(dy3, dummy3, pk3.w_dgrad, k=3, out_f32=dx, out_f32_channels=c, out_f32_nhwc=True, store_bf16=False))
+    torch.cuda.synchronize()
+    ref_dx = torch.nn.grad.conv2d_input((n, c, h, w), w3, nchw(dy3), padding=1)
+    assert torch.allclose(dx.permute(0, 3, 1, 2), ref_dx, rtol=1e-3, atol=2e-3 * ref_dx.abs().max().item())
+    # 3x3 forward with bias + ReLU (tower conv) and its masked input gradient
+    b3 = torch.randn(c, device="cuda")
+    hid = torch.empty(n, h, w, c, dtype=torch.bfloat16, device="cuda")
+    o.conv_fwd(o.conv_args(x, hid, pk3.w_fwd, k=3, bias=b3, relu=True))
+    g2 = torch.full((n, h, w, c), float("nan"), dtype=torch.bfloat16, device="cuda")
+    o.conv_dgrad(o.conv_args(dy3, g2, pk3.w_dgrad, k=3, mask=hid))
+    torch.cuda.synchronize()
+    assert_close_bf16(nchw(hid), F.relu(F.conv2d(nchw(x), w3, b3, padding=1)), "tower conv")
+    assert_close_bf16(nchw(g2), ref_dx * (nchw(hid) > 0), "tower dgrad (mask)")
