@@ -775,7 +775,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 P.stats[static_cast<long>(blockIdx.x) * 2 * C + i] = v;
                 for (int r = gridDim.x + blockIdx.x; r < P.stats_replicas; r += gridDim.x) P.stats[static_cast<long>(r) * 2 * C + i] = 0.f;
             }
-            if (P.fin.counter != nullptr) bn_finalize_tail(P.fin, P.stats, gridDim.x, C, et, kEpiThreads, 1, fin_flag);
+            if (P.fin.counter != nullptr) {
+                // the output staging region doubles as the reduction scratch: the last tile's TMA store must be done with it
+                if (et == 0) tma_store_wait_all();
+                named_bar_sync(1, kEpiThreads);
+                bn_finalize_tail(P.fin, P.stats, gridDim.x, C, et, kEpiThreads, 1, fin_flag,
+                                 reinterpret_cast<double*>(smem_raw + (staging0 - smem_u32(smem_raw))));
+            }
         }
         if (et == 0) tma_store_wait_all();
         if (et == 0) dbg_stamp(P, 6);                                // epilogue (incl. statistics / finalize) done

@@ -357,7 +357,8 @@ __global__ void __launch_bounds__(kNThreads, 2) narrow_conv_kernel(const NarrowP
         }
         if (P.fin.counter != nullptr) {
             __syncthreads();                                  // `red` has been consumed: its first word becomes the "last CTA" flag
-            bn_finalize_tail(P.fin, P.stats, gridDim.x, NC, threadIdx.x, kNThreads, 1, smem_u32(red));
+            // (all cp.async groups were waited for above: the halo stages at the start of the dynamic shared memory are free)
+            bn_finalize_tail(P.fin, P.stats, gridDim.x, NC, threadIdx.x, kNThreads, 1, smem_u32(red), reinterpret_cast<double*>(nsm));
         }
     }
 }
