@@ -412,11 +412,23 @@ __global__ void __launch_bounds__(kEwThreads) bn_apply_kernel(const __nv_bfloat1
     const int G = C / 8;
     const long total = n_pix * G;
     const int c0 = static_cast<int>(threadIdx.x % G) * 8;
+    // per-channel coefficients: loaded once per block into shared memory (32 scalar global loads per thread were most of the
+    // run time of the small layers, where a thread handles one or two 16-byte groups), then 16-byte shared loads
+    extern __shared__ __align__(16) float coef[];          // [4][C]: scale, shift, res scale, res shift
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        coef[c] = __ldg(scale + c); coef[C + c] = __ldg(shift + c);
+        coef[2 * C + c] = rscale ? __ldg(rscale + c) : 1.f; coef[3 * C + c] = rscale ? __ldg(rshift + c) : 0.f;
+    }
+    __syncthreads();
     float sc[8], sh[8], rs[8], rb[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        sc[j] = __ldg(scale + c0 + j); sh[j] = __ldg(shift + c0 + j);
-        rs[j] = rscale ? __ldg(rscale + c0 + j) : 1.f; rb[j] = rscale ? __ldg(rshift + c0 + j) : 0.f;
+    for (int h = 0; h < 2; ++h) {
+        const float4 a = *reinterpret_cast<const float4*>(coef + c0 + 4 * h), b = *reinterpret_cast<const float4*>(coef + C + c0 + 4 * h);
+        const float4 c = *reinterpret_cast<const float4*>(coef + 2 * C + c0 + 4 * h), d = *reinterpret_cast<const float4*>(coef + 3 * C + c0 + 4 * h);
+        sc[4 * h] = a.x; sc[4 * h + 1] = a.y; sc[4 * h + 2] = a.z; sc[4 * h + 3] = a.w;
+        sh[4 * h] = b.x; sh[4 * h + 1] = b.y; sh[4 * h + 2] = b.z; sh[4 * h + 3] = b.w;
+        rs[4 * h] = c.x; rs[4 * h + 1] = c.y; rs[4 * h + 2] = c.z; rs[4 * h + 3] = c.w;
+        rb[4 * h] = d.x; rb[4 * h + 1] = d.y; rb[4 * h + 2] = d.z; rb[4 * h + 3] = d.w;
     }
     const long stride = static_cast<long>(gridDim.x) * blockDim.x;
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += 2 * stride) {
@@ -465,17 +477,22 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const
                                      long pix_per_block) {
     pdl_trigger();
     pdl_wait();
-    extern __shared__ float sacc[];                    // [2][C]
+    extern __shared__ __align__(16) float sacc[];      // [2][C] sums, then [4][C] coefficients (mean, invstd, relu scale, relu shift)
+    float* coef = sacc + 2 * C;
     const int G = C / 8;
     const int L = blockDim.x / G;                      // pixel lanes
     const int g = threadIdx.x % G, l = threadIdx.x / G;
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        coef[c] = __ldg(mean + c); coef[C + c] = __ldg(invstd + c);
+        coef[2 * C + c] = rscale ? __ldg(rscale + c) : 0.f; coef[3 * C + c] = rscale ? __ldg(rshift + c) : 0.f;
+    }
     __syncthreads();
     float a[8], b[8], mu[8], is[8], rs[8], rb[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        a[j] = 0.f; b[j] = 0.f; mu[j] = mean[g * 8 + j]; is[j] = invstd[g * 8 + j];
-        rs[j] = rscale ? rscale[g * 8 + j] : 0.f; rb[j] = rscale ? rshift[g * 8 + j] : 0.f;
+        a[j] = 0.f; b[j] = 0.f; mu[j] = coef[g * 8 + j]; is[j] = coef[C + g * 8 + j];
+        rs[j] = coef[2 * C + g * 8 + j]; rb[j] = coef[3 * C + g * 8 + j];
     }
     const long p0 = blockIdx.x * pix_per_block;
     long p1 = p0 + pix_per_block;
@@ -549,18 +566,23 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_apply_kernel(const __nv_bfl
             if (dgamma) dgamma[c] = sums[C + c];
         }
     }
-    // loop-invariant channel group (see bn_apply_kernel): coefficients in registers
+    // loop-invariant channel group (see bn_apply_kernel): coefficients in registers, computed once per block via shared memory
     const int c0 = static_cast<int>(threadIdx.x % G) * 8;
     // dz = k1 * (g - m1 - xhat * m2), xhat = (z - mu) * is  ==  A * g + B * z + D  (three coefficients per channel)
-    float ca[8], cb[8], cd[8], rs[8], rb[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int c = c0 + j;
+    extern __shared__ __align__(16) float coef[];          // [5][C]: A, B, D, relu scale, relu shift
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const float is = __ldg(invstd + c), mu = __ldg(mean + c);
         const float k1 = __ldg(gamma + c) * is;
         const float m1 = __ldg(sums + c) * inv_count, m2 = __ldg(sums + C + c) * inv_count;
-        ca[j] = k1; cb[j] = -k1 * is * m2; cd[j] = k1 * (is * m2 * mu - m1);
-        rs[j] = rscale ? __ldg(rscale + c) : 0.f; rb[j] = rscale ? __ldg(rshift + c) : 0.f;
+        coef[c] = k1; coef[C + c] = -k1 * is * m2; coef[2 * C + c] = k1 * (is * m2 * mu - m1);
+        coef[3 * C + c] = rscale ? __ldg(rscale + c) : 0.f; coef[4 * C + c] = rscale ? __ldg(rshift + c) : 0.f;
+    }
+    __syncthreads();
+    float ca[8], cb[8], cd[8], rs[8], rb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        ca[j] = coef[c0 + j]; cb[j] = coef[C + c0 + j]; cd[j] = coef[2 * C + c0 + j];
+        rs[j] = coef[3 * C + c0 + j]; rb[j] = coef[4 * C + c0 + j];
     }
     for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -1451,7 +1473,7 @@ extern "C" int hd_bn_finalize(const float* stats, int reps, int C, double count,
 extern "C" int hd_bn_apply(const void* z, const float* scale, const float* shift, const void* res, const float* rscale,
                            const float* rshift, int relu, void* y, int64_t n_pix, int C, hd_stream st) {
     HD_CHECK_ARG(z && scale && shift && y && C % 8 == 0 && n_pix > 0 && kEwThreads % (C / 8) == 0);
-    HD_CUDA_OK(hd::launch(bn_apply_kernel, dim3(ew_blocks(n_pix * (C / 8))), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), static_cast<const __nv_bfloat16*>(z), scale, shift, static_cast<const __nv_bfloat16*>(res), rscale, rshift, relu,
+    HD_CUDA_OK(hd::launch(bn_apply_kernel, dim3(ew_blocks(n_pix * (C / 8))), dim3(kEwThreads), 4 * C * sizeof(float), static_cast<cudaStream_t>(st), static_cast<const __nv_bfloat16*>(z), scale, shift, static_cast<const __nv_bfloat16*>(res), rscale, rshift, relu,
         static_cast<__nv_bfloat16*>(y), n_pix, C));
     HD_LAUNCH_OK();
     return HD_OK;
@@ -1465,11 +1487,11 @@ extern "C" int hd_bn_bwd_reduce(const void* dy, const void* yrelu, const float* 
     if (L < 1) L = 1;
     const int threads = G * L;
     long blocks = 148L * 4;
-    if (blocks > n_pix / 128) blocks = n_pix / 128 > 0 ? n_pix / 128 : 1;   // small maps: fewer, fatter blocks (2C atomics each)
+    if (blocks > n_pix / 32) blocks = n_pix / 32 > 0 ? n_pix / 32 : 1;     // small maps: at least 32 pixels per block (2C atomics each)
     long ppb = (n_pix + blocks - 1) / blocks;
     if (ppb < L) ppb = L;
     blocks = (n_pix + ppb - 1) / ppb;
-    HD_CUDA_OK(hd::launch(bn_bwd_reduce_kernel, dim3(static_cast<int>(blocks)), dim3(threads), 2 * C * sizeof(float), static_cast<cudaStream_t>(st), static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(yrelu), rscale, rshift,
+    HD_CUDA_OK(hd::launch(bn_bwd_reduce_kernel, dim3(static_cast<int>(blocks)), dim3(threads), 6 * C * sizeof(float), static_cast<cudaStream_t>(st), static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(yrelu), rscale, rshift,
         static_cast<const __nv_bfloat16*>(z), mean, invstd, sums, n_pix, C, ppb));
     HD_LAUNCH_OK();
     return HD_OK;
@@ -1479,7 +1501,7 @@ extern "C" int hd_bn_bwd_apply(const void* dy, const void* yrelu, const float* r
                                const float* mean, const float* invstd, const float* gamma, const float* sums, double count,
                                void* dz, void* gout, float* dgamma, float* dbeta, int64_t n_pix, int C, hd_stream st) {
     HD_CHECK_ARG(dy && z && mean && invstd && gamma && sums && dz && C % 8 == 0 && n_pix > 0 && count > 0 && kEwThreads % (C / 8) == 0);
-    HD_CUDA_OK(hd::launch(bn_bwd_apply_kernel, dim3(ew_blocks(n_pix * (C / 8))), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(yrelu), rscale, rshift,
+    HD_CUDA_OK(hd::launch(bn_bwd_apply_kernel, dim3(ew_blocks(n_pix * (C / 8))), dim3(kEwThreads), 5 * C * sizeof(float), static_cast<cudaStream_t>(st), static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(yrelu), rscale, rshift,
         static_cast<const __nv_bfloat16*>(z), mean, invstd, gamma, sums, static_cast<float>(1.0 / count),
         static_cast<__nv_bfloat16*>(dz), static_cast<__nv_bfloat16*>(gout), dgamma, dbeta, n_pix, C));
     HD_LAUNCH_OK();
