@@ -86,6 +86,9 @@ PROTOTYPES = {
     "hd_unpack_wgrad": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p],
     "hd_stem_im2col": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "hd_stem_col2im": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "hd_stem_fwd": [c_void_p, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
+                    P_(HdBnFin), c_void_p],
+    "hd_stem_fwd_rows": [c_int, c_int, c_int],
     "hd_stem_im2col_1ch": [c_void_p, c_int, c_float, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "hd_bn_finalize": [c_void_p, c_int, c_int, c_double, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p,
                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],

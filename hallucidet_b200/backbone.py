@@ -22,6 +22,7 @@ from . import ops
 # epilogue writes them that way (no transpose), cuDNN's RPN / RetinaNet head convolutions and the RoIAlign kernels read
 # channels-last natively (no nchwToNhwc / nhwcToNchw passes), and the incoming gradients are a plain cast to bf16.
 CHANNELS_LAST_FEATURES = os.environ.get("HD_CL_FEATURES", "1") == "1"
+FUSED_STEM = os.environ.get("HD_FUSED_STEM", "1") != "0"       # halo-patch 7x7 stem (csrc/stem_conv.cu) instead of im2col + GEMM
 EVAL_CHUNK = int(os.environ.get("HD_EVAL_BACKBONE_CHUNK", "16"))      # images per engine pass when no gradient is needed
 
 
@@ -46,6 +47,7 @@ class _FConv:
         else:
             scale = None
             self.bias = conv.bias.detach().float().contiguous() if conv.bias is not None else None
+        self.scale = scale
         if stem:
             self.packed = ops.PackedConv(self.cout, 3, 7, dev, need_dgrad=False, need_t=True, k_pad=ops.STEM_KPAD).pack(w, scale)
         else:
@@ -277,8 +279,11 @@ class _BackboneEngine:
 
     def _forward_impl(self):
         st = self.stem
-        ops.stem_im2col(self.x_in, self.patches)
-        ops.conv_fwd(ops.conv_args(self.patches, st.y.view(1, 1, -1, 64), st.packed.w_fwd, k=1, bias=st.bias, relu=True, algo_cin=147))
+        if FUSED_STEM:        # halo-patch stem kernel straight from the fp32 master weight (frozen BatchNorm scale folded in the kernel)
+            ops.stem_fwd(self.x_in, st.conv.weight.detach(), st.y, w_scale=st.scale, bias=st.bias, relu=True)
+        else:
+            ops.stem_im2col(self.x_in, self.patches)
+            ops.conv_fwd(ops.conv_args(self.patches, st.y.view(1, 1, -1, 64), st.packed.w_fwd, k=1, bias=st.bias, relu=True, algo_cin=147))
         ops.maxpool_fwd(st.y, self.p0, idx=self.p0_idx, mask_nonpositive=True)
         x = self.p0
         for blk in self.blocks:

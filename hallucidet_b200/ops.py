@@ -354,6 +354,26 @@ def stem_im2col_1ch(x, patches, scale=1.0, k_pad=STEM1_KPAD):
                                              _stream()), "hd_stem_im2col_1ch")
 
 
+def stem_fwd_rows(x):
+    n, _, h, w = x.shape
+    return int(_lib.load().hd_stem_fwd_rows(n, h, w))
+
+
+def stem_fwd(x, w_oihw, y, x_scale=1.0, w_scale=None, bias=None, relu=False, stats=None, bn_fin=None):
+    """Fused 7x7/2 stem (hd_stem_fwd): x [n, 3, h, w] fp32, or the single plane [n, 1, h, w] (fp32 / uint8) of a replicated input;
+    w_oihw: the fp32 master weight [64, 3, 7, 7]; y: bf16 [n, h/2, w/2, 64]."""
+    n, cin, h, w = x.shape
+    assert cin in (1, 3) and x.is_contiguous() and x.dtype in (torch.float32, torch.uint8) and (cin == 1 or x.dtype == torch.float32)
+    assert w_oihw.dtype == torch.float32 and w_oihw.is_contiguous() and tuple(w_oihw.shape) == (64, 3, 7, 7)
+    assert y.dtype == torch.bfloat16 and y.is_contiguous() and tuple(y.shape) == (n, h // 2, w // 2, 64)
+    pix = n * (h // 2) * (w // 2)
+    with _Timed("stem_fwd", 2.0 * pix * 64 * 49 * cin, f"stem7x7 cin{cin} [{n},{h},{w}]") as t:
+        t.bytes = float(x.numel() * x.element_size() + y.numel() * 2)
+        check(_lib.load().hd_stem_fwd(_ptr(x), 0 if x.dtype == torch.float32 else 1, float(x_scale), cin, _ptr(w_oihw), _ptr(w_scale), _ptr(bias),
+                                      int(relu), _ptr(y), n, h, w, _ptr(stats), stats.shape[0] if stats is not None else 0,
+                                      ctypes.pointer(bn_fin) if bn_fin is not None else None, _stream()), "hd_stem_fwd")
+
+
 def stem_col2im(dpatches, dx_nchw, k_pad=STEM_KPAD):
     n, c, h, w = dx_nchw.shape
     assert c == 3 and dx_nchw.dtype == torch.float32 and dx_nchw.is_contiguous()

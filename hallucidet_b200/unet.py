@@ -204,6 +204,7 @@ class _UnetFunction(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------------
 # execution engine: static buffers + kernel program for one (B, H, W, mode)
 # ------------------------------------------------------------------------------------------------------
+FUSED_STEM = os.environ.get("HD_FUSED_STEM", "1") != "0"       # halo-patch stem kernels (no patch matrix on the forward path)
 ONE_CHANNEL_STEM = os.environ.get("HD_STEM_1CH", "1") != "0"   # replicated IR plane -> single-channel stem (K = 49 instead of 147)
 EVAL_CHUNK = int(os.environ.get("HD_EVAL_CHUNK", "8"))       # images per engine pass in eval / no-grad mode
 SIDE_STREAM_WGRAD = os.environ.get("HD_SIDE_WGRAD", "1") != "0"
@@ -436,6 +437,8 @@ class _UnetEngine:
                 l.bias.copy_(bn.bias.detach() - bn.running_mean * scale)
                 w = self.stem_w1 if (l is self.stem and self.one_ch) else l.conv.weight.detach().contiguous()
                 l.packed.pack(w, scale.contiguous())
+                if l is self.stem:
+                    self.stem_fold_scale = scale.contiguous()
 
     def _bn_fin(self, l, count):
         """The layer's hd_bn_fin descriptor (raw pointers to its BatchNorm parameters / buffers; rebuilt if they moved)."""
@@ -535,25 +538,42 @@ class _UnetEngine:
             off += n
         return out
 
+    def _stem_patches(self):
+        if self.one_ch:
+            ops.stem_im2col_1ch(self.x_in, self.patches, scale=self.in_scale, k_pad=self.stem_kpad)
+        else:
+            ops.stem_im2col(self.x_in, self.patches)
+
     def _forward_impl(self):
         sigmoid = self.sigmoid
         x = self.x_in
         st = self.stem
-        if self.one_ch:
-            ops.stem_im2col_1ch(x, self.patches, scale=self.in_scale, k_pad=self.stem_kpad)
-        else:
-            ops.stem_im2col(x, self.patches)
-        stem_k = 49 if self.one_ch else 147
+        w_stem = st.conv.weight.detach()
         zs = st.z.view(1, 1, -1, 64)
         a_stem_flat = self.a_stem.view(1, 1, -1, 64)
-        if self.training:
-            if st.stats is None:
-                st.stats = torch.zeros(ops.conv_fwd_tiles(self.patches, 1, 1), 2, 64, device=self.device)
-            ops.conv_fwd(ops.conv_args(self.patches, zs, st.packed.w_fwd, k=1, stats=st.stats, algo_cin=stem_k,
-                                       bn_fin=self._bn_fin(st, zs.shape[2])))
-            ops.bn_apply(zs, st.scale, st.shift, a_stem_flat, relu=True)
+        if FUSED_STEM:
+            # fused halo-patch stem (csrc/stem_conv.cu): no patch matrix on the forward path.  The patches are only needed by the
+            # stem's weight gradient at the very end of the backward pass: they are built on the side stream.
+            if self.training:
+                self._on_side(self._stem_patches)
+                if st.stats is None:
+                    st.stats = torch.zeros(ops.stem_fwd_rows(x), 2, 64, device=self.device)
+                ops.stem_fwd(x, w_stem, st.z, x_scale=self.in_scale, stats=st.stats,
+                             bn_fin=self._bn_fin(st, self.B * st.h * st.w))
+                ops.bn_apply(zs, st.scale, st.shift, a_stem_flat, relu=True)
+            else:
+                ops.stem_fwd(x, w_stem, self.a_stem, x_scale=self.in_scale, w_scale=self.stem_fold_scale, bias=st.bias, relu=True)
         else:
-            ops.conv_fwd(ops.conv_args(self.patches, a_stem_flat, st.packed.w_fwd, k=1, bias=st.bias, relu=True, algo_cin=stem_k))
+            self._stem_patches()
+            stem_k = 49 if self.one_ch else 147
+            if self.training:
+                if st.stats is None:
+                    st.stats = torch.zeros(ops.conv_fwd_tiles(self.patches, 1, 1), 2, 64, device=self.device)
+                ops.conv_fwd(ops.conv_args(self.patches, zs, st.packed.w_fwd, k=1, stats=st.stats, algo_cin=stem_k,
+                                           bn_fin=self._bn_fin(st, zs.shape[2])))
+                ops.bn_apply(zs, st.scale, st.shift, a_stem_flat, relu=True)
+            else:
+                ops.conv_fwd(ops.conv_args(self.patches, a_stem_flat, st.packed.w_fwd, k=1, bias=st.bias, relu=True, algo_cin=stem_k))
         ops.maxpool_fwd(self.a_stem, self.p0, idx=self.p0_idx if self.training else None)
         x_in = self.p0
         feats = {1: self.a_stem}
@@ -581,6 +601,7 @@ class _UnetEngine:
         ops.conv_fwd(ops.conv_args(xd, hd.z, hd.packed.w_fwd, k=3, bias=self.head_bias_pad, sigmoid=sigmoid, out_f32=self.hal,
                                    out_f32_channels=hd.cout, store_bf16=False, algo_cout=hd.cout))
         self.head_in = xd
+        self._join_side()
         if self.training:
             torch._foreach_add_(self.nbt, 1)
 

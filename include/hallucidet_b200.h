@@ -182,6 +182,14 @@ int hd_stem_im2col(const float* x_nchw, void* patches, int n, int h, int w, int 
  * filter): x [n][1][h][w] as fp32 (x_dtype 0) or uint8 (x_dtype 1), multiplied by `scale` (1/255 for the camera bytes,
  * src/dataloader/dataloader.py:13-73) -> patches bf16 [n*ho*wo][k_pad], k = r*7 + s (49 taps, zero padded to k_pad >= 56). */
 int hd_stem_im2col_1ch(const void* x, int x_dtype, float scale, void* patches, int n, int h, int w, int k_pad, hd_stream stream);
+/* Fused stem forward (csrc/stem_conv.cu): y = relu?(conv7x7/2(x * x_scale, w * w_scale[cout]) + bias) as bf16 NHWC [n][h/2][w/2][64],
+ * straight from the fp32 OIHW master weight [64][3][7][7] -- no patch matrix in HBM.  cin = 3: x fp32 NCHW [n][3][h][w];
+ * cin = 1: x is the single plane [n][1][h][w] (fp32, x_dtype 0, or uint8, x_dtype 1) of an input whose three channels are equal,
+ * convolved with the channel-summed filter.  Optional BatchNorm statistics of the output (stats: fp32 [stats_rows][2][64], one
+ * row per CTA, stats_rows >= hd_stem_fwd_rows) and fused finalize (bn_fin), as hd_conv_fwd. */
+int hd_stem_fwd(const void* x, int x_dtype, float x_scale, int cin, const float* w_oihw, const float* w_scale, const float* bias,
+                int relu, void* y, int n, int h, int w, float* stats, int stats_rows, const hd_bn_fin* bn_fin, hd_stream stream);
+int hd_stem_fwd_rows(int n, int h, int w);
 /* dpatches bf16 [n*ho*wo][k_pad] -> dx fp32 NCHW [n][3][h][w] (overwrites). */
 int hd_stem_col2im(const void* dpatches, float* dx_nchw, int n, int h, int w, int k_pad, hd_stream stream);
 

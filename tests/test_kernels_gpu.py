@@ -814,3 +814,57 @@ def test_head_tower_kernel_shapes(n, h, w):
     torch.cuda.synchronize()
     assert_close_bf16(nchw(hid), F.relu(F.conv2d(nchw(x), w3, b3, padding=1)), "tower conv")
     assert_close_bf16(nchw(g2), ref_dx * (nchw(hid) > 0), "tower dgrad (mask)")
+
+
+@pytest.mark.parametrize("cin,dtype", [(3, "f32"), (1, "f32"), (1, "u8")])
+@pytest.mark.parametrize("n,h,w", [(2, 64, 96), (1, 150, 300), (2, 128, 128)])
+def test_stem_fwd_fused(cin, dtype, n, h, w):
+    """hd_stem_fwd (halo-patch 7x7/2 stem, csrc/stem_conv.cu) against F.conv2d on the bf16-rounded input and weights:
+    three-channel input, and the single replicated plane (fp32 or uint8 * 1/255) with the channel-summed filter; the BatchNorm
+    statistics / fused finalize variant and the bias + ReLU variant."""
+    o = ops()
+    g = torch.Generator().manual_seed(7)
+    wt = (torch.randn(64, 3, 7, 7, generator=g) / 147 ** 0.5).cuda()
+    if dtype == "u8":
+        xu = torch.randint(0, 256, (n, 1, h, w), generator=g, dtype=torch.uint8).cuda()
+        x_in, scale = xu, 1.0 / 255.0
+        xf = (xu.float() * scale).to(torch.bfloat16).float()
+    else:
+        x_in = torch.rand(n, cin, h, w, generator=g).cuda()
+        scale = 1.0
+        xf = x_in.to(torch.bfloat16).float()
+    if cin == 1:
+        w_eff = wt.sum(1, keepdim=True).to(torch.bfloat16).float()
+        ref = F.conv2d(xf, w_eff, stride=2, padding=3)
+    else:
+        ref = F.conv2d(xf, wt.to(torch.bfloat16).float(), stride=2, padding=3)
+    ho, wo = h // 2, w // 2
+    # (a) raw output + statistics + fused finalize
+    y = torch.full((n, ho, wo, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    stats = torch.full((o.stem_fwd_rows(x_in), 2, 64), float("nan"), device="cuda")
+    gamma, beta = torch.rand(64, device="cuda") + 0.5, torch.randn(64, device="cuda")
+    rm, rv = torch.zeros(64, device="cuda"), torch.ones(64, device="cuda")
+    mean, invstd, sc, sh = (torch.full((64,), float("nan"), device="cuda") for _ in range(4))
+    counter = torch.zeros(1, dtype=torch.int32, device="cuda")
+    fin = o.bn_fin(n * ho * wo, gamma, beta, 1e-5, 0.1, rm, rv, mean, invstd, sc, sh, counter)
+    o.stem_fwd(x_in, wt, y, x_scale=scale, stats=stats, bn_fin=fin)
+    torch.cuda.synchronize()
+    assert_close_bf16(nchw(y), ref, "stem fwd")
+    yq = nchw(y).double()
+    ssum = stats.double().sum(0)
+    assert torch.allclose(ssum[0], yq.sum((0, 2, 3)), rtol=1e-3, atol=1e-2)
+    assert torch.allclose(ssum[1], (yq * yq).sum((0, 2, 3)), rtol=1e-3, atol=1e-2)
+    assert torch.allclose(mean.double(), yq.mean((0, 2, 3)), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(invstd.double(), (yq.var((0, 2, 3), unbiased=False) + 1e-5).rsqrt(), rtol=1e-4)
+    assert int(counter) == 0
+    # (b) folded scale + bias + ReLU (frozen backbone / eval-mode U-Net)
+    wsc, bias = torch.rand(64, device="cuda") + 0.5, torch.randn(64, device="cuda") * 0.1
+    y2 = torch.full((n, ho, wo, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    o.stem_fwd(x_in, wt, y2, x_scale=scale, w_scale=wsc, bias=bias, relu=True)
+    torch.cuda.synchronize()
+    if cin == 1:
+        w2 = (wt.sum(1, keepdim=True) * wsc.view(-1, 1, 1, 1)).to(torch.bfloat16).float()
+    else:
+        w2 = (wt * wsc.view(-1, 1, 1, 1)).to(torch.bfloat16).float()
+    ref2 = F.relu(F.conv2d(xf, w2, bias, stride=2, padding=3))
+    assert_close_bf16(nchw(y2), ref2, "stem fwd bias relu")
