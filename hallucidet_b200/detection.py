@@ -796,6 +796,42 @@ class DeferredDetections:
         return self._value
 
 
+class DeferredCall:
+    """A by-product of the step (here: RetinaNet's detections, which feed no loss) computed LATER: ``resolve()`` runs ``fn`` on a
+    side stream that only waits for what had been enqueued when the object was created.  The trainer resolves it after the
+    backward pass and the optimizer have been enqueued, so the per-image / per-level loops of the post-processing (with their
+    data-dependent host syncs) execute next to the backward pass instead of in front of it.  Same interface as
+    DeferredDetections."""
+
+    def __init__(self, fn, inputs):
+        self._fn, self._value = fn, None
+        self._stream = _side_streams(inputs[0].device, 2)[1]
+        self._event = torch.cuda.Event()
+        self._event.record()
+        for t in inputs:
+            t.record_stream(self._stream)
+
+    def then(self, fn):
+        inner = self._fn
+        self._fn = lambda: fn(inner())
+        return self
+
+    def resolve(self):
+        if self._value is None:
+            side = self._stream
+            side.wait_event(self._event)
+            with torch.cuda.stream(side), torch.no_grad():
+                value = self._fn()
+            main = torch.cuda.current_stream(side.device)
+            main.wait_stream(side)
+            for d in value:
+                for t in d.values():
+                    if torch.is_tensor(t) and t.is_cuda:
+                        t.record_stream(main)
+            self._value, self._fn = value, None
+        return self._value
+
+
 _ANCHOR_CACHE = {}
 
 
@@ -815,6 +851,7 @@ def _anchors(model, images, features):
 
 
 FUSED_RPN_PREDICTORS = _os.environ.get("HD_FUSED_RPN_PRED", "1") == "1"
+WHOLE_BATCH_RETINANET_LOSS = _os.environ.get("HD_RETINA_LOSS_BATCHED", "1") == "1"   # RetinaNet losses without per-image loop / host sync
 B200_HEADS = _os.environ.get("HD_B200_HEADS", "1") == "1"       # frozen RPN / RetinaNet heads on the B200 conv kernels (heads.py)
 
 
@@ -850,6 +887,7 @@ def rpn_eval(model, images, features, targets, targets_event=None):
         # the frozen RPN head on the tcgen05 conv kernels, reading the backbone's bf16 pyramid (forward + input gradient only)
         bf16 = model.backbone.bf16_features()
         if bf16 is not None and len(bf16) == len(features) and heads.rpn_head_tower(model.rpn.head) is not None:
+            heads.USE_CUDA_GRAPH = bool(model.backbone.use_cuda_graph)
             objectness, pred_bbox_deltas = heads.rpn_head_forward(model.rpn.head, features, bf16)
     if objectness is None:
         objectness, pred_bbox_deltas = _rpn_head(model.rpn.head, features)
@@ -1090,6 +1128,32 @@ def compute_retinanet_loss(targets, head_outputs, anchors, model, batched=True):
     the data-dependent counts (foreground / valid anchors per image) come back in one host read; the per-image index lists
     are then built with count-known ``nonzero`` -- same indices, same order, same reductions as the per-image loop."""
     cuda = batched and BATCHED_TAIL and anchors[0].is_cuda and all(a.shape == anchors[0].shape for a in anchors)
+    if cuda and WHOLE_BATCH_RETINANET_LOSS:
+        # Whole-batch form: no per-image loop and NO host sync.  Every anchor gets a (masked) loss term instead of indexing
+        # the valid / foreground subsets out first, so the fp32 sums run over the same non-zero terms in a different order
+        # (relative difference ~1e-6 against the per-image loop below; tests/test_heads_gpu.py).
+        logits, reg = head_outputs["cls_logits"], head_outputs["bbox_regression"]            # [B, A, K], [B, A, 4]
+        with torch.no_grad():
+            G = max(1, max(int(t["boxes"].shape[0]) for t in targets))
+            gt, present = _pad_rows([t["boxes"] for t in targets], G)
+            labels_pad, _ = _pad_rows([t["labels"] for t in targets], G)
+            anc = torch.stack(anchors)                                                       # [B, A, 4]
+            midx = _match_batched(model.proposal_matcher, gt, present, anc)                  # [B, A]
+            fg = midx >= 0
+            valid = midx != model.head.classification_head.BETWEEN_THRESHOLDS
+            n_fg = fg.sum(1).clamp(min=1).to(logits.dtype)
+            safe = midx.clamp(min=0)
+            gt_cls = torch.zeros_like(logits)
+            gt_cls.scatter_(2, torch.gather(labels_pad, 1, safe)[..., None], fg[..., None].to(logits.dtype))
+            matched_gt = torch.gather(gt, 1, safe[..., None].expand(-1, -1, 4))
+            # (background anchors are paired with gt 0 / a zero box: their targets are never used, only kept finite)
+            matched_gt = torch.where(fg[..., None], matched_gt, anc)
+            target_reg = _encode_single(model.box_coder, matched_gt.reshape(-1, 4), anc.reshape(-1, 4)).reshape(anc.shape)
+        cls_el = sigmoid_focal_loss(logits, gt_cls, reduction="none")
+        cls = torch.where(valid[..., None], cls_el, cls_el.new_zeros(())).sum((1, 2)) / n_fg
+        reg_el = F.smooth_l1_loss(reg, target_reg, reduction="none", beta=1.0)
+        box = torch.where(fg[..., None], reg_el, reg_el.new_zeros(())).sum((1, 2)) / n_fg
+        return {"classification": cls.sum() / len(targets), "bbox_regression": box.sum() / max(1, len(targets))}
     if cuda:
         with torch.no_grad():
             G = max(1, max(int(t["boxes"].shape[0]) for t in targets))
@@ -1176,6 +1240,38 @@ def retinanet_postprocess_detections(model, head_outputs, anchors, image_shapes)
     return detections
 
 
+def retinanet_postprocess_detections_batched_begin(model, head_outputs, anchors, image_shapes):
+    """``RetinaNet.postprocess_detections`` (TV models/detection/retinanet.py: per image and per level -- score threshold,
+    top-k candidates, box decoding, clipping -- then per-image ``batched_nms`` and top ``detections_per_img``) for the whole
+    batch: one ``topk`` per level over [B, anchors*classes] with the below-threshold scores masked out (the survivors come
+    out in the same descending order as torchvision's filter-then-topk), one batched decode per level, and the batched NMS
+    tail of _filter_nms_batched_begin.  ~12 launches per level and ONE host sync instead of ~14 launches and 2-3 syncs per
+    (image, level) pair.  head_outputs / anchors are split per level as in eval_forward_retinanet."""
+    class_logits, box_regression = head_outputs["cls_logits"], head_outputs["bbox_regression"]
+    B = len(image_shapes)
+    boxes_l, scores_l, labels_l, valid_l = [], [], [], []
+    for lvl, (logits, reg) in enumerate(zip(class_logits, box_regression)):
+        num_classes = logits.shape[-1]
+        scores = torch.sigmoid(logits).flatten(1)                                   # [B, n_l * K]
+        keep = scores > model.score_thresh
+        k = min(model.topk_candidates, scores.shape[1])
+        top_scores, top_idx = scores.masked_fill(~keep, -1.0).topk(k, dim=1)        # kept scores first, descending
+        valid = top_scores > model.score_thresh
+        anchor_idx = torch.div(top_idx, num_classes, rounding_mode="floor")
+        labels = top_idx % num_classes
+        anc = torch.stack([a[lvl] for a in anchors])                                # [B, n_l, 4]
+        gi = anchor_idx[..., None].expand(-1, -1, 4)
+        boxes = _decode(model.box_coder, torch.gather(reg, 1, gi).reshape(-1, 4), [torch.gather(anc, 1, gi).reshape(-1, 4)])
+        boxes = _clip_boxes_batched(boxes.reshape(B, k, 4), image_shapes)
+        boxes_l.append(boxes); scores_l.append(top_scores); labels_l.append(labels); valid_l.append(valid)
+    boxes, scores = torch.cat(boxes_l, 1), torch.cat(scores_l, 1)
+    labels, valid = torch.cat(labels_l, 1), torch.cat(valid_l, 1)
+    pend = _filter_nms_batched_begin(boxes, scores, labels, valid, model.nms_thresh, model.detections_per_img)
+    inner = pend.finish
+    pend.finish = lambda n_sel: (lambda r: (list(r[0]), list(r[1]), list(r[2])))(inner(n_sel))
+    return pend
+
+
 def eval_forward_retinanet(model, images, targets, train_det=False, model_name="retinanet"):
     if not train_det and model.training:
         model.eval()
@@ -1191,6 +1287,7 @@ def eval_forward_retinanet(model, images, targets, train_det=False, model_name="
     if B200_HEADS and features[0].is_cuda and isinstance(model.backbone, FrozenBackbone):
         bf16 = model.backbone.bf16_features()
         if bf16 is not None and len(bf16) == len(features) and heads.retinanet_head_towers(model.head) is not None:
+            heads.USE_CUDA_GRAPH = bool(model.backbone.use_cuda_graph)
             head_outputs = heads.retinanet_head_forward(model.head, features, bf16)
     if head_outputs is None:
         head_outputs = model.head(features)
@@ -1202,6 +1299,35 @@ def eval_forward_retinanet(model, images, targets, train_det=False, model_name="
     num_anchors_per_level = [n * a for n in num_anchors_per_level]
     split_head_outputs = {k: list(v.split(num_anchors_per_level, dim=1)) for k, v in head_outputs.items()}
     split_anchors = [list(x.split(num_anchors_per_level)) for x in anchors]
+    n_cand = sum(min(model.topk_candidates, n * head_outputs["cls_logits"].shape[-1]) for n in num_anchors_per_level)
+    if (BATCHED_TAIL and images.tensors.is_cuda and head_outputs["cls_logits"].dtype == torch.float32 and _batched_ok(n_cand)
+            and all(a.shape == anchors[0].shape for a in anchors)):
+        image_sizes = images.image_sizes
+        det_in = {k: [t.detach() for t in v] for k, v in split_head_outputs.items()}
+        with torch.no_grad():
+            if DEFER_DETECTIONS and POSTPROCESS_SIDE_STREAM:
+                # train step: the detections feed no loss -- they are post-processed on a side stream underneath the backward
+                # pass, their data-dependent sizes read back asynchronously, the lists assembled when the trainer asks
+                main = torch.cuda.current_stream(images.tensors.device)
+                side = _side_streams(images.tensors.device, 1)[0]
+                side.wait_stream(main)
+                for t in [t for v in det_in.values() for t in v] + [a for per_image in split_anchors for a in per_image]:
+                    t.record_stream(side)
+                with torch.cuda.stream(side):
+                    pend = retinanet_postprocess_detections_batched_begin(model, det_in, split_anchors, image_sizes)
+                    deferred = DeferredDetections(pend, side)
+                deferred.then(lambda d: model.transform.postprocess(d, image_sizes, original_image_sizes))
+                _run_deferred_checks()
+                return losses, deferred
+            pend = retinanet_postprocess_detections_batched_begin(model, det_in, split_anchors, image_sizes)
+            if DEFER_DETECTIONS:
+                _run_deferred_checks()
+                return losses, DeferredDetections(pend).then(lambda d: model.transform.postprocess(d, image_sizes, original_image_sizes))
+            boxes, scores, labels = _resolve(pend)[0]
+        detections = [{"boxes": boxes[i], "scores": scores[i], "labels": labels[i]} for i in range(len(boxes))]
+        detections = model.transform.postprocess(detections, images.image_sizes, original_image_sizes)
+        _run_deferred_checks()
+        return losses, detections
     if BATCHED_TAIL and images.tensors.is_cuda:
         with torch.no_grad():
             detections = retinanet_postprocess_detections(model, split_head_outputs, split_anchors, images.image_sizes)

@@ -46,6 +46,7 @@ class _Tower:
         self.pred_bias = torch.zeros(self.pred_cp, device=device)
         self.pred_bias[:self.pred_c] = pred_bias.detach().float()
         self.scratch = {}
+        self.programs = {}
 
     def _scratch(self, shape):
         """Scratch of one pyramid level (keyed by its [B, H, W, C] shape): nothing here has to survive until the backward."""
@@ -61,22 +62,24 @@ class _Tower:
             }
         return st
 
-    def forward(self, x):
-        """x: bf16 NHWC [B, H, W, C] -> (fp32 [B, H, W, pred_cp] channels-last predictor output, hidden activations)."""
+    def forward(self, x, hidden=None, pred=None):
+        """x: bf16 NHWC [B, H, W, C] -> (fp32 [B, H, W, pred_cp] channels-last predictor output, hidden activations).
+        ``hidden`` / ``pred``: optional pre-allocated outputs (CUDA-graph programs)."""
         st = self._scratch(tuple(x.shape))
         b, hh, ww, _ = x.shape
-        h, hidden = x, []
-        for pk, bias, co in self.convs:
-            out = torch.empty(b, hh, ww, co, dtype=torch.bfloat16, device=self.device)      # kept for the ReLU mask of the backward
+        h = x
+        if hidden is None:                                    # kept for the ReLU mask of the backward
+            hidden = [torch.empty(b, hh, ww, co, dtype=torch.bfloat16, device=self.device) for _, _, co in self.convs]
+        for (pk, bias, co), out in zip(self.convs, hidden):
             ops.conv_fwd(ops.conv_args(h, out, pk.w_fwd, k=3, bias=bias, relu=True))
-            hidden.append(out)
             h = out
-        pred = torch.empty(b, hh, ww, self.pred_cp, device=self.device)
+        if pred is None:
+            pred = torch.empty(b, hh, ww, self.pred_cp, device=self.device)
         ops.conv_fwd(ops.conv_args(h, st["pred_bf16"], self.pred.w_fwd, k=self.pred_k, bias=self.pred_bias,
                                    out_f32=pred, out_f32_channels=self.pred_cp, out_f32_nhwc=True, store_bf16=False))
         return pred, hidden
 
-    def backward(self, x_shape, hidden, dpred):
+    def backward(self, x_shape, hidden, dpred, dx=None):
         """dpred: fp32 [B, H, W, pred_cp] (any strides) -> fp32 [B, H, W, C] gradient of the level input."""
         st = self._scratch(tuple(x_shape))
         st["dpred"].copy_(dpred)                                            # fp32 -> bf16 NHWC
@@ -88,10 +91,61 @@ class _Tower:
             g = st["g"][i]
             pk, k = self.convs[i][0], 3
         b, hh, ww, c = x_shape
-        dx = torch.empty(b, hh, ww, c, device=self.device)
+        if dx is None:
+            dx = torch.empty(b, hh, ww, c, device=self.device)
         ops.conv_dgrad(ops.conv_args(g, st["dx_dummy"], pk.w_dgrad, k=k, out_f32=dx, out_f32_channels=c, out_f32_nhwc=True,
                                      store_bf16=False))
         return dx
+
+
+USE_CUDA_GRAPH = False          # set by the caller (detection.py: when the backbone runs its kernel programs as CUDA graphs)
+
+
+class _TowerProgram:
+    """The tower over all pyramid levels as two CUDA graphs (forward, input gradient) on static buffers: the levels' launches
+    (2-10 per level and direction, each with host-side tensor-map encoding) become one graph launch each -- the detection tail
+    is host-bound, so this is time on the critical path.  Keyed by the input pointers (the backbone's static bf16 pyramid)."""
+
+    def __init__(self, tower, feats_bf16):
+        self.tower, self.x = tower, list(feats_bf16)
+        dev = tower.device
+        self.hidden = [[torch.empty(x.shape[0], x.shape[1], x.shape[2], co, dtype=torch.bfloat16, device=dev) for _, _, co in tower.convs]
+                       for x in self.x]
+        self.pred = [torch.empty(x.shape[0], x.shape[1], x.shape[2], tower.pred_cp, device=dev) for x in self.x]
+        self.dpred = [torch.zeros_like(p) for p in self.pred]
+        self.dx = [torch.empty(tuple(x.shape), device=dev) for x in self.x]
+        self.graphs = {}
+        self.generation = 0
+
+    def _run(self, kind, fn):
+        state = self.graphs.get(kind)
+        if state is None:
+            fn()
+            self.graphs[kind] = "warm"
+        elif state == "warm":
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            self.graphs[kind] = g
+            g.replay()
+        else:
+            state.replay()
+
+    def forward(self):
+        self._run("fwd", lambda: [self.tower.forward(x, h, p) for x, h, p in zip(self.x, self.hidden, self.pred)])
+        self.generation += 1
+        return tuple(self.pred)
+
+    def backward(self, dpreds, need):
+        for buf, dp in zip(self.dpred, dpreds):
+            if dp is None:
+                buf.zero_()
+            else:
+                buf.copy_(dp)
+        self._run("bwd", lambda: [self.tower.backward(tuple(x.shape), h, dp, dx)
+                                  for x, h, dp, dx in zip(self.x, self.hidden, self.dpred, self.dx)])
+        return [dx.permute(0, 3, 1, 2) if n else None for dx, n in zip(self.dx, need)]
 
 
 class _TowerFunction(torch.autograd.Function):
@@ -103,12 +157,28 @@ class _TowerFunction(torch.autograd.Function):
         ctx.tower = tower
         ctx.shapes = [tuple(x.shape) for x in feats_bf16]
         ctx.need = [f.requires_grad for f in feats]
+        ctx.program = None
+        if USE_CUDA_GRAPH and any(ctx.need) and torch.is_grad_enabled():
+            key = tuple(x.data_ptr() for x in feats_bf16)
+            prog = tower.programs.get(key)
+            if prog is None:
+                if len(tower.programs) >= 4:
+                    tower.programs.clear()
+                prog = tower.programs[key] = _TowerProgram(tower, feats_bf16)
+            ctx.program = prog
+            outs = prog.forward()
+            ctx.generation = prog.generation
+            return outs
         outs = [tower.forward(x) for x in feats_bf16]
         ctx.hidden = [h for _, h in outs]
         return tuple(p for p, _ in outs)
 
     @staticmethod
     def backward(ctx, *dpreds):
+        if ctx.program is not None:
+            if ctx.generation != ctx.program.generation:
+                raise RuntimeError("hallucidet_b200.heads: the activations of this forward were overwritten by a later forward")
+            return (None, None) + tuple(ctx.program.backward(dpreds, ctx.need))
         grads = []
         for shape, need, hidden, dp in zip(ctx.shapes, ctx.need, ctx.hidden, dpreds):
             if not need or dp is None:

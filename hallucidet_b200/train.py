@@ -299,6 +299,6 @@ class HalluciDetTrainer(nn.Module):
             self.allreduce_gradients()
             self.clip_gradients()
         self.optimizer.step()
-        if isinstance(out["detections"], detection.DeferredDetections):
+        if isinstance(out["detections"], (detection.DeferredDetections, detection.DeferredCall)):
             out["detections"] = out["detections"].resolve()
         return out

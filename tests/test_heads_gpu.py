@@ -136,3 +136,129 @@ def test_train_step_with_b200_heads_vs_cudnn_heads(name):
     print(f"\n[{name}] loss with B200 heads {res[True][0]:.6f} vs cuDNN heads {res[False][0]:.6f} (rel {rel:.2e}); grad cosine {c:.4f}")
     assert rel <= 1e-2
     assert c >= 0.9            # (run-to-run noise of the free-running gradient alone is ~1e-2 relative, see test_modules_gpu)
+
+
+def test_rpn_head_cuda_graph_program_matches_eager():
+    """The head tower as two CUDA graphs on static buffers (heads._TowerProgram): warm-up, capture and replay all give the
+    eager launches' results, for changing inputs in the same (static) pyramid buffers."""
+    from hallucidet_b200 import heads
+    from oracle import detector as odet
+    det = odet.build_detector("fasterrcnn", seed=123).cuda()
+    head = det.rpn.head
+    _boost(head, 4.0)
+    sizes = [(40, 40), (20, 20), (10, 10), (5, 5), (3, 3)]
+    bf16, _, _ = _pyramid(sizes)
+    gen = torch.Generator().manual_seed(9)
+    try:
+        for it in range(4):
+            for x in bf16:                                          # new values, same buffers (as the backbone engine's pyramid)
+                x.copy_(torch.randn(x.shape, generator=gen).to(torch.bfloat16))
+            res = {}
+            for graph in (False, True):
+                heads.USE_CUDA_GRAPH = graph
+                f32 = [x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True) for x in bf16]
+                lo, bb = heads.rpn_head_forward(head, f32, bf16)
+                loss = sum((a * (i + 1)).sum() + (b * 0.5).sum() for i, (a, b) in enumerate(zip(lo, bb)))
+                loss.backward()
+                torch.cuda.synchronize()
+                res[graph] = ([t.detach().clone() for t in lo + bb], [f.grad.clone() for f in f32])
+            for a, b in zip(res[False][0] + res[False][1], res[True][0] + res[True][1]):
+                assert torch.equal(a, b), it
+    finally:
+        heads.USE_CUDA_GRAPH = False
+
+
+def test_retinanet_deferred_detections_equal_inline():
+    """Train-step mode post-processes RetinaNet's detections on a side stream after the backward pass has been enqueued
+    (detection.DeferredCall): same detections and losses as the in-line path."""
+    from hallucidet_b200 import detection
+    from hallucidet_b200.synthetic import synthetic_batch
+    from hallucidet_b200.train import HalluciDetTrainer
+    from oracle import detector as odet
+    dev = torch.device("cuda", 0)
+    ir, rgb, targets = synthetic_batch(2, 128, 160, seed=123, device=dev)
+    det_cpu = odet.build_detector("retinanet", seed=123)
+    odet.randomize_bn_stats(det_cpu, seed=7)
+    tr = HalluciDetTrainer(detector_name="retinanet", size=160, seed=123, device=dev, detector_state=det_cpu.state_dict())
+    tr.encoder_decoder.eval()
+    with torch.no_grad():
+        hal = tr.encoder_decoder(ir.expand(-1, 3, -1, -1))
+    res = {}
+    for defer in (False, True):
+        detection.DEFER_DETECTIONS = defer
+        try:
+            hal_in = hal.clone().requires_grad_(True)
+            losses, det = detection.Detector.calculate_loss(tr.detector, hal_in, targets, model_name="retinanet")
+            (losses["classification"] + losses["bbox_regression"]).backward()
+            if defer:
+                assert isinstance(det, detection.DeferredDetections)
+                det = det.resolve()
+            torch.cuda.synchronize()
+            res[defer] = (losses, det)
+        finally:
+            detection.DEFER_DETECTIONS = False
+    for k in ("classification", "bbox_regression"):
+        assert torch.equal(res[False][0][k], res[True][0][k])
+    assert len(res[False][1]) == len(res[True][1]) == 2
+    for a, b in zip(res[False][1], res[True][1]):
+        for k in ("boxes", "scores", "labels"):
+            assert torch.equal(a[k], b[k]), k
+
+
+def test_retinanet_batched_postprocess_equals_torchvision():
+    """retinanet_postprocess_detections_batched (whole batch per level, one host sync) against torchvision's own
+    ``RetinaNet.postprocess_detections`` on the same head outputs: identical boxes / scores / labels."""
+    from hallucidet_b200 import detection
+    from oracle import detector as odet
+    from torchvision.models.detection.image_list import ImageList
+    det = odet.build_detector("retinanet", seed=123).cuda()
+    det.score_thresh = 0.3
+    B, sizes = 3, [(20, 20), (10, 10), (5, 5), (3, 3), (2, 2)]
+    g = torch.Generator().manual_seed(3)
+    feats = [torch.randn(B, 256, h, w, generator=g).cuda() for h, w in sizes]
+    images = ImageList(torch.zeros(B, 3, 160, 160, device="cuda"), [(160, 160)] * B)
+    anchors = det.anchor_generator(images, feats)
+    A = det.anchor_generator.num_anchors_per_location()[0]
+    n_per = [h * w * A for h, w in sizes]
+    total = sum(n_per)
+    head = {"cls_logits": (torch.randn(B, total, 2, generator=g) * 2).cuda(), "bbox_regression": (torch.randn(B, total, 4, generator=g) * 0.3).cuda()}
+    split_head = {k: list(v.split(n_per, dim=1)) for k, v in head.items()}
+    split_anchors = [list(a.split(n_per)) for a in anchors]
+    ref = det.postprocess_detections(split_head, split_anchors, images.image_sizes)
+    boxes, scores, labels = detection._resolve(detection.retinanet_postprocess_detections_batched_begin(det, split_head, split_anchors, images.image_sizes))[0]
+    assert sum(len(r["boxes"]) for r in ref) > 50
+    for i, r in enumerate(ref):
+        assert torch.equal(boxes[i], r["boxes"]) and torch.equal(scores[i], r["scores"]) and torch.equal(labels[i], r["labels"]), i
+
+
+def test_retinanet_whole_batch_loss_matches_per_image_loop():
+    """compute_retinanet_loss: the sync-free whole-batch form against the per-image loop (the reference's
+    src/utils/eval_forward_retinanet.py:163-244 order of operations): same losses and gradients up to fp32 summation order."""
+    from hallucidet_b200 import detection
+    from oracle import detector as odet
+    from torchvision.models.detection.image_list import ImageList
+    det = odet.build_detector("retinanet", seed=123).cuda()
+    B, sizes = 3, [(20, 20), (10, 10), (5, 5), (3, 3), (2, 2)]
+    g = torch.Generator().manual_seed(4)
+    feats = [torch.randn(B, 256, h, w, generator=g).cuda() for h, w in sizes]
+    images = ImageList(torch.zeros(B, 3, 160, 160, device="cuda"), [(160, 160)] * B)
+    anchors = det.anchor_generator(images, feats)
+    total = anchors[0].shape[0]
+    targets = [{"boxes": torch.tensor([[10., 12., 60., 90.], [70., 40., 150., 120.]]).cuda(), "labels": torch.tensor([1, 1]).cuda()},
+               {"boxes": torch.tensor([[5., 5., 40., 40.]]).cuda(), "labels": torch.tensor([1]).cuda()},
+               {"boxes": torch.zeros(0, 4).cuda(), "labels": torch.zeros(0, dtype=torch.int64).cuda()}]
+    res = {}
+    for flag in (False, True):
+        detection.WHOLE_BATCH_RETINANET_LOSS = flag
+        try:
+            logits = (torch.randn(B, total, 2, generator=torch.Generator().manual_seed(5)) * 2).cuda().requires_grad_(True)
+            reg = (torch.randn(B, total, 4, generator=torch.Generator().manual_seed(6)) * 0.3).cuda().requires_grad_(True)
+            losses = detection.compute_retinanet_loss(targets, {"cls_logits": logits, "bbox_regression": reg}, anchors, det)
+            (losses["classification"] + 2.0 * losses["bbox_regression"]).backward()
+            res[flag] = (losses, logits.grad.clone(), reg.grad.clone())
+        finally:
+            detection.WHOLE_BATCH_RETINANET_LOSS = True
+    for k in ("classification", "bbox_regression"):
+        assert torch.allclose(res[True][0][k], res[False][0][k], rtol=1e-5, atol=1e-7), k
+    assert torch.allclose(res[True][1], res[False][1], rtol=1e-4, atol=1e-8)
+    assert torch.allclose(res[True][2], res[False][2], rtol=1e-4, atol=1e-8)
