@@ -832,6 +832,41 @@ class DeferredCall:
         return self._value
 
 
+GRAPH_PROPOSAL_FILTER = _os.environ.get("HD_GRAPH_PROPOSALS", "1") == "1"
+_STATIC_PROGRAMS = {}
+
+
+class _StaticProgram:
+    """A gradient-free, static-shape piece of the tail on static input buffers: run eagerly once (warm-up), captured into a
+    CUDA graph on the second call, replayed afterwards.  The captured function's return value (tensors in the graph's memory
+    pool, refreshed by every replay, and closures over them) is handed out each time."""
+
+    def __init__(self):
+        self.state, self.graph, self.out = None, None, None
+
+    def run(self, fn):
+        if self.state is None:
+            self.state = "warm"
+            return fn()
+        if self.state == "warm":
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.out = fn()
+            self.graph, self.state = g, "graph"
+        self.graph.replay()
+        return self.out
+
+
+def _static_program(key):
+    prog = _STATIC_PROGRAMS.get(key)
+    if prog is None:
+        if len(_STATIC_PROGRAMS) > 8:
+            _STATIC_PROGRAMS.clear()
+        prog = _STATIC_PROGRAMS[key] = _StaticProgram()
+    return prog
+
+
 _ANCHOR_CACHE = {}
 
 
@@ -882,35 +917,53 @@ def rpn_eval(model, images, features, targets, targets_event=None):
     (src/utils/eval_forward_fasterrcnn.py:62-99).  ``targets_event``: CUDA event recorded once ``targets`` are final on
     the current stream; lets the anchor-target work start before the backbone forward has finished."""
     features = list(features.values())
-    objectness = None
+    objectness, static_preds = None, False
     if B200_HEADS and features[0].is_cuda and isinstance(model.backbone, FrozenBackbone):
         # the frozen RPN head on the tcgen05 conv kernels, reading the backbone's bf16 pyramid (forward + input gradient only)
         bf16 = model.backbone.bf16_features()
         if bf16 is not None and len(bf16) == len(features) and heads.rpn_head_tower(model.rpn.head) is not None:
             heads.USE_CUDA_GRAPH = bool(model.backbone.use_cuda_graph)
-            objectness, pred_bbox_deltas = heads.rpn_head_forward(model.rpn.head, features, bf16)
+            objectness, pred_bbox_deltas, static_preds = heads.rpn_head_forward(model.rpn.head, features, bf16, return_static=True)
     if objectness is None:
         objectness, pred_bbox_deltas = _rpn_head(model.rpn.head, features)
     batched = BATCHED_TAIL and features[0].is_cuda
     anchors, anchors_fresh = _anchors(model, images, features) if batched else (model.rpn.anchor_generator(images, features), True)
     num_images = len(anchors)
     num_anchors_per_level = [o[0].shape[0] * o[0].shape[1] * o[0].shape[2] for o in objectness]
-    objectness, pred_bbox_deltas = concat_box_prediction_layers(objectness, pred_bbox_deltas)
-    proposals = _decode(model.rpn.box_coder, pred_bbox_deltas.detach(), anchors)
-    proposals = proposals.view(num_images, -1, 4)
     pre_nms = sum(min(model.rpn.pre_nms_top_n(), n) for n in num_anchors_per_level)
     if targets is None:
         raise ValueError("targets should not be None")
-    if (batched and proposals.dtype == torch.float32 and _batched_ok(pre_nms)
-            and all(a.shape == anchors[0].shape for a in anchors)):
+    use_batched = batched and objectness[0].dtype == torch.float32 and _batched_ok(pre_nms) and all(a.shape == anchors[0].shape for a in anchors)
+    pend_boxes = None
+    if use_batched and static_preds and GRAPH_PROPOSAL_FILTER and not anchors_fresh:
+        # The predictor outputs live in the static buffers of the head's CUDA-graph program and the anchors are cached: the whole
+        # gradient-free, static-shape chain concat -> decode -> per-level top-k -> clip / filter -> sort -> NMS (~45 launches) is
+        # captured once and replayed as ONE graph launch; only the final data-dependent gather stays eager (after the count read).
+        obj_lv, del_lv = [o.detach() for o in objectness], [d.detach() for d in pred_bbox_deltas]
+        image_sizes = images.image_sizes
+
+        def program():
+            o2, d2 = concat_box_prediction_layers(obj_lv, del_lv)
+            props = _decode(model.rpn.box_coder, d2, anchors).view(num_images, -1, 4)
+            return filter_proposals_batched_begin(model.rpn, props, o2, image_sizes, num_anchors_per_level)
+
+        key = (id(model.rpn), tuple(o.data_ptr() for o in obj_lv), anchors[0].data_ptr(), tuple(map(tuple, image_sizes)))
+        with torch.no_grad():
+            pend_boxes = _static_program(key).run(program)
+    objectness, pred_bbox_deltas = concat_box_prediction_layers(objectness, pred_bbox_deltas)
+    if pend_boxes is None:
+        proposals = _decode(model.rpn.box_coder, pred_bbox_deltas.detach(), anchors)
+        proposals = proposals.view(num_images, -1, 4)
+    if use_batched:
         # The proposal filter (up to its NMS) is enqueued on the main stream.  Target assignment, box encoding and the
         # anchor sampler depend only on the anchors and the targets, not on the network: they run on a side stream as soon
         # as the targets exist -- i.e. underneath the backbone forward -- including the sampler's host read and its
         # randperm calls, which therefore leave the critical path (same calls in the same order: same CUDA generator use).
-        pend_boxes = filter_proposals_batched_begin(model.rpn, proposals, objectness, images.image_sizes, num_anchors_per_level)
-        main = torch.cuda.current_stream(proposals.device)
+        if pend_boxes is None:
+            pend_boxes = filter_proposals_batched_begin(model.rpn, proposals, objectness, images.image_sizes, num_anchors_per_level)
+        main = torch.cuda.current_stream(objectness.device)
         if EARLY_RPN_TARGETS:
-            side = _side_streams(proposals.device, 1)[0]
+            side = _side_streams(objectness.device, 1)[0]
             if targets_event is None or anchors_fresh:
                 # (anchors computed just now are queued on the main stream behind the backbone: wait for them as well)
                 targets_event = torch.cuda.Event()

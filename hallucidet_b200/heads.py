@@ -222,17 +222,22 @@ def rpn_head_tower(head):
     return cached[1]
 
 
-def rpn_head_forward(head, features, features_bf16):
+def rpn_head_forward(head, features, features_bf16, return_static=False):
     """``RPNHead.forward`` (TV rpn.py:61-68) on the B200 kernels -> (objectness list, bbox-delta list), each [B, A | 4A, H, W]
-    fp32 views of one channels-last predictor output per level."""
+    fp32 views of one channels-last predictor output per level.  ``return_static``: also tell whether the outputs live in the
+    static buffers of a CUDA-graph program (same addresses every step: downstream static-shape work can be graphed too)."""
     tower = rpn_head_tower(head)
     a = head.cls_logits.out_channels
-    preds = _TowerFunction.apply(tower, list(features_bf16), *features)
+    feats_bf16 = list(features_bf16)
+    preds = _TowerFunction.apply(tower, feats_bf16, *features)
     logits, bbox = [], []
     for p in preds:
         nchw = p.permute(0, 3, 1, 2)
         logits.append(nchw[:, :a])
         bbox.append(nchw[:, a:a + 4 * a])
+    if return_static:
+        prog = tower.programs.get(tuple(x.data_ptr() for x in feats_bf16))
+        return logits, bbox, bool(prog is not None and preds[0].data_ptr() == prog.pred[0].data_ptr())
     return logits, bbox
 
 

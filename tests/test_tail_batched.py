@@ -134,8 +134,14 @@ def test_retinanet_tail_cuda():
         il = ImageList(x, [(128, 160)] * 3)
         anchors = det.anchor_generator(il, feats)
         a = D.compute_retinanet_loss(targets, ho, anchors, det, batched=False)
-        b = D.compute_retinanet_loss(targets, ho, anchors, det, batched=True)
+        D.WHOLE_BATCH_RETINANET_LOSS = False                      # count-known index lists: same terms in the same order
+        try:
+            b = D.compute_retinanet_loss(targets, ho, anchors, det, batched=True)
+        finally:
+            D.WHOLE_BATCH_RETINANET_LOSS = True
         assert torch.equal(a["classification"], b["classification"]) and torch.equal(a["bbox_regression"], b["bbox_regression"])
+        c = D.compute_retinanet_loss(targets, ho, anchors, det, batched=True)   # whole-batch, sync-free: other fp32 summation order
+        assert torch.allclose(a["classification"], c["classification"], rtol=1e-5) and torch.allclose(a["bbox_regression"], c["bbox_regression"], rtol=1e-5)
         assert float(a["bbox_regression"]) > 0
         napl = [f.size(2) * f.size(3) for f in feats]
         per = ho["cls_logits"].size(1) // sum(napl)
@@ -145,9 +151,11 @@ def test_retinanet_tail_cuda():
         det.score_thresh = 0.0095                       # random-init scores sit around the 0.01 prior
         d1 = det.postprocess_detections(sho, sa, il.image_sizes)
         d2 = D.retinanet_postprocess_detections(det, sho, sa, il.image_sizes)
+        b3, s3, l3 = D._resolve(D.retinanet_postprocess_detections_batched_begin(det, sho, sa, il.image_sizes))[0]
     assert sum(d["boxes"].shape[0] for d in d1) > 0
-    for p, q in zip(d1, d2):
+    for i, (p, q) in enumerate(zip(d1, d2)):
         assert all(torch.equal(p[k], q[k]) for k in ("boxes", "scores", "labels"))
+        assert torch.equal(p["boxes"], b3[i]) and torch.equal(p["scores"], s3[i]) and torch.equal(p["labels"], l3[i])
 
 
 def test_pad_rows_matches_pad_sequence_cpu():

@@ -4,7 +4,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hallucidet_b200.train import HalluciDetTrainer, expand_one_channel_to_output_channels  # noqa
 from hallucidet_b200 import detection as D  # noqa
-from oracle import step as ostep  # noqa
+from hallucidet_b200 import synthetic as ostep  # noqa
 from torchvision.models.detection.rpn import concat_box_prediction_layers
 from torchvision.models.detection.roi_heads import fastrcnn_loss
 
