@@ -466,6 +466,14 @@ def _gather_perms(nz, perms, starts, width):
     return sel[:, 0] * width + sel[:, 1]
 
 
+def _ascending(idx, total):
+    """``torch.sort(idx)[0]`` for UNIQUE flat indices < total (sampled anchor / proposal positions) as mask + count-known
+    ``nonzero``: 4 launches instead of the ~10 of a 64-bit radix sort (45 onesweep launches per step came from three such sorts)."""
+    mask = torch.zeros(total, dtype=torch.bool, device=idx.device)
+    mask[idx] = True
+    return torch.nonzero_static(mask, size=idx.numel())[:, 0]
+
+
 def _sample_batched_begin(sampler, labels):
     """``det_utils.BalancedPositiveNegativeSampler`` for labels [B, N] (>= 1 positive, 0 negative, -1 ignored / padding).
     Resolves to a ``_Samples``.  The two ``torch.randperm`` calls per image are issued with the same sizes and in the same
@@ -515,8 +523,8 @@ def rpn_compute_loss_batched(rpn, objectness, pred_bbox_deltas, labels, regressi
     B, A = labels.shape
     if samples is None:
         samples = _sample_batched(rpn.fg_bg_sampler, labels)
-    pos = torch.sort(samples.pos)[0]                                                     # == where(cat(pos masks))
-    neg = torch.sort(samples.neg)[0]
+    pos = _ascending(samples.pos, B * A)                                                 # == where(cat(pos masks))
+    neg = _ascending(samples.neg, B * A)
     sampled = torch.cat([pos, neg], dim=0)
     objectness = objectness.flatten()
     labels = labels.reshape(-1)
@@ -545,7 +553,7 @@ def select_training_samples_batched(roi_heads, proposals, targets, return_num_po
     labels = torch.where(p_present, labels, labels.new_full((), -1))        # padding is ignored by the sampler
     samples = _sample_batched(roi_heads.fg_bg_sampler, labels)
     per_image = [p + n for p, n in zip(samples.n_pos, samples.n_neg)]
-    flat = torch.sort(torch.cat((samples.pos, samples.neg)))[0]                 # == where(pos | neg) per image, back to back
+    flat = _ascending(torch.cat((samples.pos, samples.neg)), B * N)             # == where(pos | neg) per image, back to back
     out_props = P.view(-1, 4)[flat]
     out_labels = labels.view(-1)[flat]
     out_matched = clamped.view(-1)[flat]
