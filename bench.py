@@ -275,6 +275,8 @@ def main_inference(args):
     sampler.start()
     ms = timed(step_resident, args.steps)
     clocks = sampler.stop()
+    for _ in range(3):                            # first use of the pinned -> device slots is warm-up too
+        step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     line = {
         "metric": "inference images/s (1280x1024 IR -> hallucination + detection, bf16)", "value": world * B * args.steps / (ms / 1e3),
@@ -375,6 +377,7 @@ def main():
         tr.training_step(rgb_d, targets, ir_d, targets)
 
     host_loss = []
+    trace = [] if os.environ.get("HD_BENCH_TRACE") else None
 
     from hallucidet_b200.train import DevicePrefetcher
     prefetch = DevicePrefetcher(dev)
@@ -390,6 +393,8 @@ def main():
         # device -> host read of the step's result: the loss, copied to pinned memory where the step computes it (before
         # the backward pass) and waited for here, every step
         host_loss.append(float(out["total_host"]))
+        if trace is not None:
+            trace.append(time.perf_counter())
 
     ops.LAUNCHES = 0
     for _ in range(max(args.warmup, 3)):
@@ -421,9 +426,21 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    cuprof = bool(os.environ.get("HD_BENCH_CUPROF"))      # `ncu --profile-from-start off`: the launch list of the timed steps only
+    if cuprof:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     ms = timed(step_resident, args.steps)
+    if cuprof:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop() if rank == 0 else None
+    for _ in range(3):                            # first use of the pinned -> device slots and the copy stream is warm-up too
+        step_e2e()
+    if trace is not None:
+        del trace[:]
     ms_e2e = timed(step_e2e, args.steps)
+    if trace:
+        print("e2e step wall ms:", [round((b - a) * 1e3, 1) for a, b in zip(trace, trace[1:])], file=sys.stderr)
 
     if rank == 0:
         ms_step = ms / args.steps
