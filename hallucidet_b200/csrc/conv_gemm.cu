@@ -91,6 +91,11 @@ struct ConvGemmParams {
     long long* dbg;             // optional [gridDim.x][8] globaltimer stamps (hd_conv_debug_timestamps; nullptr in production)
     int stat_floats;            // 2 x (padded output channels): this CTA's running BatchNorm partial sums, in shared memory
     BnFin fin;                  // fused BatchNorm finalize (last CTA), fin.counter == nullptr: off
+    // halo mode (3x3 stride 1, 64-channel k-blocks, all weights of the layer <= 72 KB): see the note above the kernel
+    int halo;
+    int w_bytes;                // resident weight region ahead of the stage ring (9 * kpt sub-tiles of b_sub bytes)
+    int halo_tap[9];            // [dw + 1][dh + 1] -> filter tap (row of tap_bk) whose input offset is (dh, dw)
+    int aux_bufs;               // depth of the add / mask ring (2; 1 when shared memory is short)
 };
 
 __device__ __forceinline__ void decode_tile(const ConvGemmParams& P, int tile, int& z, int& n0, int& img, int& h0, int& w0, int* mt_out = nullptr) {
@@ -169,6 +174,15 @@ __device__ __forceinline__ bool walk_next(const ConvGemmParams& P, SegWalk& w, S
     return true;
 }
 
+// Halo mode.  In the general path every filter tap re-loads its own shifted 128-pixel A box: a 3x3 layer moves 9 x 128 rows of
+// 128 bytes per 64-channel k-block through the TMA unit, whose per-row cost (~2-3.5 cycles) is what bounds the shallow
+// 64-channel layers (profiles/r2_conv_timeline_v1.txt), plus 9 weight boxes per tile.  Here the output tile is 8 wide x 16
+// high and, per k-block, only THREE boxes are loaded -- one per horizontal tap offset dw, each 8 wide x 18 high (the rows
+// h0-1 .. h0+16).  A box is 18 groups of 8 rows (1 KB, swizzle-128B atoms), group g = input row h0-1+g; the A operand of
+// tap (dh, dw) is then simply groups (dh+1) .. (dh+16) of box dw: the SAME shared memory, descriptor start address moved
+// by whole 1 KB atoms, so the swizzle phase is untouched.  432 instead of 1152 A rows per k-block; the layer's weights are
+// loaded once per CTA and stay resident.  Accumulation order is (k-block, dw, dh) instead of (tap, k-block).
+//
 // Persistent CTA (one per SM): a static round-robin over output tiles; the TMA producer and the MMA issuer run
 // ahead across tile boundaries, the accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the
 // main loop of tile i+1.
@@ -182,7 +196,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
     const int stages = P.stages;
     const uint32_t stg_bytes = (128u * P.BN * 2u + 1023u) & ~1023u;
-    const uint32_t staging0 = smem_base + static_cast<uint32_t>(stages * P.stage_bytes);  // 2 x (128 x BN bf16), 1024-aligned
+    const uint32_t ring_base = smem_base + static_cast<uint32_t>(P.w_bytes);               // stage ring (after the resident weights)
+    const uint32_t staging0 = ring_base + static_cast<uint32_t>(stages * P.stage_bytes);   // 2 x (128 x BN bf16), 1024-aligned
     const uint32_t bias_s = staging0 + static_cast<uint32_t>(P.ring_bytes);               // bias of all output channels
     const uint32_t stat_s = bias_s + 4u * static_cast<uint32_t>(P.bias_floats);            // per-CTA BatchNorm partial sums
     const uint32_t bar_base = stat_s + 4u * static_cast<uint32_t>(P.stat_floats);
@@ -192,6 +207,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const uint32_t afull0 = tempty0 + 16u, aempty0 = afull0 + 16u;        // add / mask ring (aux_mode)
     const uint32_t tmem_slot = aempty0 + 16u;
     const uint32_t fin_flag = tmem_slot + 8u;
+    const uint32_t wfull = fin_flag + 8u;                                  // resident weights landed (halo mode)
     const int aux_ops = (P.add != nullptr ? 1 : 0) + (P.mask != nullptr ? 1 : 0);
     const uint32_t aux_buf_bytes = static_cast<uint32_t>(aux_ops) * stg_bytes;
 
@@ -206,6 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             mbar_init(tfull0 + 8u * a, 1);
             mbar_init(tempty0 + 8u * a, kEpiWarps);         // one arrival per epilogue warp
         }
+        mbar_init(wfull, 1);
         mbar_fence_init();
         tma_prefetch_desc(&P.tmA[0]);
         tma_prefetch_desc(&P.tmB);
@@ -234,6 +251,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             SegWalk wk;
             Seg sg;
             walk_init(P, wk);
+            if (P.halo) {
+                // the whole filter (9 taps x kpt k-blocks, BN rows each) once per CTA
+                mbar_expect_tx(wfull, static_cast<uint32_t>(9 * P.kpt * P.BN * 128));
+                for (int t = 0; t < 9; ++t)
+                    for (int kb = 0; kb < P.kpt; ++kb)
+                        tma_load_2d(smem_base + static_cast<uint32_t>((t * P.kpt + kb) * P.b_sub), &P.tmB, wfull, P.tap_bk[t] + kb * 64, 0);
+                while (walk_next(P, wk, sg)) {
+                    int z, n0, img, h0, w0;
+                    decode_tile(P, sg.tile, z, n0, img, h0, w0);
+                    for (int kb = 0; kb < P.kpt; ++kb) {
+                        const int src = kb < P.kb_split ? 0 : 1;
+                        const int c = (src ? kb - P.kb_split : kb) * 64;
+                        for (int dwi = 0; dwi < 3; ++dwi) {
+                            mbar_wait(empty0 + 8u * stage, phase ^ 1u);
+                            const uint32_t fb = full0 + 8u * stage;
+                            mbar_expect_tx(fb, 18u * 8u * 128u);
+                            tma_load_5d(ring_base + stage * P.stage_bytes, &P.tmA[src], fb, c, w0 + dwi - 1, 0, h0 - 1, img);
+                            if (++stage == stages) { stage = 0; phase ^= 1u; }
+                        }
+                    }
+                }
+            } else
             while (walk_next(P, wk, sg)) {
                 int z, n0, img, h0, w0;
                 decode_tile(P, sg.tile, z, n0, img, h0, w0);
@@ -245,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 }
                 for (int st = sg.sb; st < sg.se; ++st) {
                     mbar_wait(empty0 + 8u * stage, phase ^ 1u);
-                    const uint32_t sa = smem_base + stage * P.stage_bytes;
+                    const uint32_t sa = ring_base + stage * P.stage_bytes;
                     const uint32_t sb = sa + P.a_bytes;
                     const uint32_t fb = full0 + 8u * stage;
                     mbar_expect_tx(fb, tx_bytes);
@@ -274,7 +313,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const int ksub = P.BK / 16;
             const int tps = P.tps;
             const uint32_t stage_u = P.stage_bytes >> 4, a_sub_u = P.a_sub >> 4, b_sub_u = P.b_sub >> 4, a_bytes_u = P.a_bytes >> 4;
-            const uint32_t base_u = d_lo + (smem_base >> 4);
+            const uint32_t base_u = d_lo + (ring_base >> 4);
+            const uint32_t wbase_u = d_lo + (smem_base >> 4);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -282,6 +322,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             SegWalk wk;
             Seg sg;
             walk_init(P, wk);
+            if (P.halo) {
+                mbar_wait(wfull, 0);
+                while (walk_next(P, wk, sg)) {
+                    mbar_wait(tempty0 + 8u * acc, acc_phase ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * P.tmem_cols;
+                    uint32_t accum = 0;
+                    for (int kb = 0; kb < P.kpt; ++kb) {
+                        for (int dwi = 0; dwi < 3; ++dwi) {
+                            mbar_wait(full0 + 8u * stage, phase);
+                            if (HD_CONV_DBG && P.dbg != nullptr && P.dbg[static_cast<long>(blockIdx.x) * 8 + 3] == 0) dbg_stamp(P, 3);
+                            tc_fence_after();
+                            const uint32_t a_u = base_u + stage * stage_u;
+#pragma unroll
+                            for (int dhi = 0; dhi < 3; ++dhi) {
+                                const uint32_t a_t = a_u + dhi * 64u;                      // + dhi groups of 8 rows (1 KB)
+                                const uint32_t b_t = wbase_u + static_cast<uint32_t>(P.halo_tap[dwi * 3 + dhi] * P.kpt + kb) * b_sub_u;
+                                umma_bf16_lohi(d_tmem, a_t, d_hi, b_t, d_hi, idesc, accum);
+                                umma_bf16_lohi(d_tmem, a_t + 2, d_hi, b_t + 2, d_hi, idesc, 1);
+                                umma_bf16_lohi(d_tmem, a_t + 4, d_hi, b_t + 4, d_hi, idesc, 1);
+                                umma_bf16_lohi(d_tmem, a_t + 6, d_hi, b_t + 6, d_hi, idesc, 1);
+                                accum = 1;
+                            }
+                            umma_commit(empty0 + 8u * stage);
+                            if (++stage == stages) { stage = 0; phase ^= 1u; }
+                        }
+                    }
+                    umma_commit(tfull0 + 8u * acc);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                }
+            } else
             while (walk_next(P, wk, sg)) {
                 const int num_st = sg.se - sg.sb;
                 mbar_wait(tempty0 + 8u * acc, acc_phase ^ 1u);          // epilogue has drained this accumulator
@@ -356,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     }
                 }
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(afull0 + 8u * b) : "memory");
-                if (++b == 2) { b = 0; ph ^= 1u; }
+                if (++b == P.aux_bufs) { b = 0; ph ^= 1u; }
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
         } else
@@ -396,7 +467,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 const __nv_bfloat16* tile_base = P.a_ptr + ((static_cast<long>(img) * P.a_H + h0) * P.a_W + w0) * P.a_C;
                 for (int ks = 0; ks < num_k; ks += P.tps) {
                     mbar_wait(empty0 + 8u * stage, phase ^ 1u);
-                    const uint32_t sa = smem_base + stage * P.stage_bytes;
+                    const uint32_t sa = ring_base + stage * P.stage_bytes;
                     for (int j = 0; j < P.tps; ++j) {
                         const int dh = P.tap_dh[tap], dw = P.tap_dw[tap];
                         const long tap_off = (static_cast<long>(dh) * P.a_W + dw) * P.a_C + kb * P.BK;
@@ -688,7 +759,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
             if (P.aux_mode) {
                 if (lane == 0) mbar_arrive(aempty0 + 8u * ab);
-                if (++ab == 2) { ab = 0; aph ^= 1u; }
+                if (++ab == P.aux_bufs) { ab = 0; aph ^= 1u; }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             if (HD_CONV_SK && np > 0) {
@@ -855,6 +926,29 @@ static bool aux_mode_enabled() {
 
 static long long* g_conv_dbg = nullptr;
 
+// Halo mode (see the note above conv_gemm_kernel): 3x3 stride-1 layers with 64-channel k-blocks whose whole filter fits in
+// 72 KB of shared memory next to the stage ring, single N tile.  HD_HALO=0 turns it off (A/B measurements).
+static bool halo_ok(int k, int s, int bk, int kpt, int bn, int n_out, bool two_outputs) {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("HD_HALO");
+        on = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return on && k == 3 && s == 1 && bk == 64 && !two_outputs && bn <= 64 && n_out <= bn && kpt * bn <= 64;
+}
+
+static void halo_geometry(ConvGemmParams& P) {
+    P.halo = 1;
+    P.TW = 8;
+    P.TH = 16;
+    P.tiles_w = (P.Wg + P.TW - 1) / P.TW;
+    P.tiles_h = (P.Hg + P.TH - 1) / P.TH;
+    for (int dwi = 0; dwi < 3; ++dwi)
+        for (int dhi = 0; dhi < 3; ++dhi)
+            for (int t = 0; t < 9; ++t)
+                if (P.tap_dw[t] == dwi - 1 && P.tap_dh[t] == dhi - 1) P.halo_tap[dwi * 3 + dhi] = t;
+}
+
 static bool streamk_enabled() {
     static int on = -1;
     if (on < 0) {
@@ -887,6 +981,12 @@ static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStrea
     }
     P.a_bytes = P.a_sub * P.tps;
     P.stage_bytes = (P.a_sub + P.b_sub) * P.tps;
+    P.w_bytes = 0;
+    P.aux_bufs = 2;
+    if (P.halo) {
+        P.a_sub = P.a_bytes = P.stage_bytes = 18 * 8 * 128;        // one (dw, k-block) box: 18 input rows x 8 pixels x 64 channels
+        P.w_bytes = 9 * P.kpt * P.b_sub;
+    }
     P.stg_bufs = P.BN > 128 ? 1 : 2;
     const int staging = P.stg_bufs * round_up(128 * P.BN * 2, 1024);   // output staging (double-buffered up to BN = 128)
     P.n_tiles = (P.Cout_total + P.BN - 1) / P.BN;
@@ -895,7 +995,7 @@ static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStrea
     // stream-K when whole tiles quantise badly onto the SMs (one or two under-filled waves) and K is long enough to cut
     P.streamk = 0;
     P.m_tiles = P.tiles_w * P.tiles_h * n_img;
-    if (HD_CONV_SK && nphases == 1 && !P.cp_mode && P.tps == 1 && workspace != nullptr && streamk_enabled()) {
+    if (HD_CONV_SK && nphases == 1 && !P.cp_mode && !P.halo && P.tps == 1 && workspace != nullptr && streamk_enabled()) {
         const int sms = num_sms();
         const int nst = (P.tap_begin[1] - P.tap_begin[0]) * P.kpt;
         const long tiles = static_cast<long>(P.m_tiles) * P.n_tiles;
@@ -926,15 +1026,29 @@ static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStrea
         const int nk = (P.tap_begin[z + 1] - P.tap_begin[z]) * P.kpt / P.tps;
         if (nk > max_steps) max_steps = nk;
     }
-    const int stages_with_ring = (232448 - (1024 + 2 * n_ops * tile_bytes + 4 * P.bias_floats + 4 * P.stat_floats + 20 * 8 + 64)) / P.stage_bytes;
+    static int halo_min = 0;
+    if (halo_min == 0) {
+        const char* e = getenv("HD_HALO_MIN");
+        halo_min = (e != nullptr && e[0] >= '3' && e[0] <= '8') ? e[0] - '0' : 4;   // 4 parts + a two-deep add/mask ring beat 6 parts + a one-deep ring (25.9 vs 34.1 us)
+    }
+    const int min_stages = P.halo ? halo_min : (max_steps <= 2 ? 2 : 3);
+    int stages_with_ring = (232448 - P.w_bytes - (1024 + 2 * n_ops * tile_bytes + 4 * P.bias_floats + 4 * P.stat_floats + 20 * 8 + 64)) / P.stage_bytes;
+    if (P.halo && stages_with_ring < min_stages) {             // one-deep add / mask ring next to the resident weights
+        P.aux_bufs = 1;
+        stages_with_ring = (232448 - P.w_bytes - (1024 + n_ops * tile_bytes + 4 * P.bias_floats + 4 * P.stat_floats + 20 * 8 + 64)) / P.stage_bytes;
+    }
     P.aux_mode = (P.reg_store && n_ops > 0 && !P.cp_mode && !P.streamk && P.BN >= 16 && aux_mode_enabled() &&
-                  stages_with_ring >= (max_steps <= 2 ? 2 : 3)) ? 1 : 0;
+                  stages_with_ring >= min_stages) ? 1 : 0;
     // register-store epilogues need no output staging: the region becomes the two-deep add / mask ring (or nothing)
-    P.ring_bytes = P.reg_store ? (P.aux_mode ? 2 * n_ops * tile_bytes : 0) : staging;
+    P.ring_bytes = P.reg_store ? (P.aux_mode ? P.aux_bufs * n_ops * tile_bytes : 0) : staging;
     const int fixed = 1024 + P.ring_bytes + 4 * P.bias_floats + 4 * P.stat_floats + 20 * 8 + 64;   // alignment slack, ring, bias, stats, barriers
-    int stages = (232448 - fixed) / P.stage_bytes;              // 227 KB = the sm_100 per-block maximum
+    int stages = (232448 - fixed - P.w_bytes) / P.stage_bytes;  // 227 KB = the sm_100 per-block maximum
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
+    if (P.halo && stages < 4) {
+        set_last_error(__FILE__, __LINE__, "halo mode: shared memory budget");
+        return HD_ERR_BAD_ARG;
+    }
     P.stages = stages;
     int cols = 32;
     while (cols < P.BN) cols *= 2;
@@ -958,8 +1072,9 @@ static int launch_conv_gemm(ConvGemmParams& P, int n_img, int nphases, cudaStrea
     P.nphases = nphases;
     P.total_units = static_cast<int>(static_cast<long>(P.m_tiles) * P.n_tiles * nphases);
     for (int z = 0; z < nphases && z < 4; ++z) P.nst_phase[z] = (P.tap_begin[z + 1] - P.tap_begin[z]) * P.kpt / P.tps;
+    if (P.halo) P.nst_phase[0] = 3 * P.kpt;
     P.dbg = g_conv_dbg;
-    const size_t smem = static_cast<size_t>(fixed) + static_cast<size_t>(stages) * P.stage_bytes;
+    const size_t smem = static_cast<size_t>(fixed) + static_cast<size_t>(P.w_bytes) + static_cast<size_t>(stages) * P.stage_bytes;
     static SmemAttrOnce smem_attr;
     HD_CUDA_OK(ensure_dyn_smem(smem_attr, conv_gemm_kernel, 232448));
     const long total = static_cast<long>(P.m_tiles) * P.n_tiles * nphases;
@@ -1068,6 +1183,7 @@ extern "C" int hd_conv_fwd(const hd_conv_args* a, hd_stream stream_) {
             P.tap_bk[t] = t * cin;
         }
     P.tap_begin[0] = 0; P.tap_begin[1] = t;
+    if (halo_ok(k, s, P.BK, P.kpt, P.BN, cout, false)) halo_geometry(P);
     P.a_qstride[0] = a->x0.c; P.a_qstride[1] = two ? a->x1.c : 0;
     P.out_C0 = cout; P.Cout_total = cout;
     P.cp_mode = (P.BK < 64 && s == 1 && !two) ? 1 : 0;
@@ -1076,8 +1192,9 @@ extern "C" int hd_conv_fwd(const hd_conv_args* a, hd_stream stream_) {
     if (int e = fill_epilogue(P, a)) return e;
 
     const int swz = P.BK * 2;
-    if (act_map(&P.tmA[0], a->x0, s == 2, P.BK, P.TW, P.TH, swz)) return HD_ERR_CUDA;
-    if (two) { if (act_map(&P.tmA[1], a->x1, s == 2, P.BK, P.TW, P.TH, swz)) return HD_ERR_CUDA; }
+    const int a_th = P.halo ? P.TH + 2 : P.TH;               // halo mode: boxes of 18 input rows (see the kernel note)
+    if (act_map(&P.tmA[0], a->x0, s == 2, P.BK, P.TW, a_th, swz)) return HD_ERR_CUDA;
+    if (two) { if (act_map(&P.tmA[1], a->x1, s == 2, P.BK, P.TW, a_th, swz)) return HD_ERR_CUDA; }
     else P.tmA[1] = P.tmA[0];
     {
         uint64_t dims[2] = {static_cast<uint64_t>(k * k * cin), static_cast<uint64_t>(round_up(cout, 16))};
@@ -1101,9 +1218,16 @@ extern "C" int hd_conv_fwd_tiles(const hd_conv_args* a) {
     const int Ho = a->x0.h / a->stride, Wo = a->x0.w / a->stride;
     int TW, TH;
     pick_tile(Ho, Wo, &TW, &TH);
-    const long m_tiles = static_cast<long>((Wo + TW - 1) / TW) * ((Ho + TH - 1) / TH) * a->x0.n;
+    long m_tiles = static_cast<long>((Wo + TW - 1) / TW) * ((Ho + TH - 1) / TH) * a->x0.n;
     // one row per CTA of the persistent grid (<= SM count); without the output channel count the N-tile count is unknown
     if (a->y0.c <= 0) return num_sms();
+    {
+        const int c1 = a->x1.ptr != nullptr ? a->x1.c : a->x0.c;
+        const int bk = pick_bk(a->x0.c, c1);
+        const int cin = a->x0.c + (a->x1.ptr != nullptr ? a->x1.c : 0);
+        if (bk != 0 && halo_ok(a->kh, a->stride, bk, cin / bk, pick_bn(a->y0.c), a->y0.c, false))
+            m_tiles = static_cast<long>((Wo + 7) / 8) * ((Ho + 15) / 16) * a->x0.n;
+    }
     const int bn = maybe_bn256(pick_bn(a->y0.c), a->kh, a->y0.c, static_cast<int>(m_tiles));
     const long units = m_tiles * ((a->y0.c + bn - 1) / bn);
     if (HD_CONV_SK && streamk_enabled()) return num_sms();   // stream-K launches use every SM whatever the tile count
@@ -1153,6 +1277,7 @@ extern "C" int hd_conv_dgrad(const hd_conv_args* a, hd_stream stream_) {
             }
         P.tap_begin[0] = 0; P.tap_begin[1] = t;
         nph = 1;
+        if (halo_ok(k, s, P.BK, P.kpt, P.BN, cin, two)) halo_geometry(P);
     } else {
         for (int p = 0; p < 2; ++p)
             for (int q = 0; q < 2; ++q) {
@@ -1185,7 +1310,7 @@ extern "C" int hd_conv_dgrad(const hd_conv_args* a, hd_stream stream_) {
     if (int e = fill_epilogue(P, a)) return e;
 
     const int swz = P.BK * 2;
-    if (act_map(&P.tmA[0], a->x0, false, P.BK, P.TW, P.TH, swz)) return HD_ERR_CUDA;
+    if (act_map(&P.tmA[0], a->x0, false, P.BK, P.TW, P.halo ? P.TH + 2 : P.TH, swz)) return HD_ERR_CUDA;
     P.tmA[1] = P.tmA[0];
     {
         uint64_t dims[2] = {static_cast<uint64_t>(k * k * cout), static_cast<uint64_t>(round_up(cin, 16))};

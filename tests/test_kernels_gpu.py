@@ -70,6 +70,13 @@ CONV_CASES = [
     (8, 32, 40, 512, 256, 3, 1, 256),
     (3, 20, 20, 512, 512, 3, 1, 0),
     (5, 40, 40, 1024, 256, 1, 1, 0),
+    # halo mode (8x16 tiles, three 8x18 boxes per k-block, resident weights): ragged edges, many tiles per CTA, 2 k-blocks
+    (2, 23, 37, 64, 64, 3, 1, 0),
+    (8, 128, 160, 64, 64, 3, 1, 0),
+    (3, 50, 30, 64, 32, 3, 1, 0),
+    (2, 33, 20, 64, 16, 3, 1, 0),
+    (4, 64, 72, 64, 32, 3, 1, 64),
+    (1, 17, 9, 128, 32, 3, 1, 0),
 ]
 
 
@@ -180,7 +187,32 @@ DGRAD_CASES = [
     (8, 32, 40, 256, 256, 3, 1, 0),     # stream-K
     (8, 16, 20, 512, 512, 3, 1, 0),
     (8, 32, 40, 768, 256, 3, 1, 256),   # stream-K with a split gradient (512 | 256)
+    # halo mode
+    (2, 23, 37, 64, 64, 3, 1, 0),
+    (8, 128, 160, 64, 64, 3, 1, 0),
+    (3, 50, 30, 32, 64, 3, 1, 0),       # dX has 32 channels, dY 64
+    (1, 17, 9, 32, 128, 3, 1, 0),       # two k-blocks
 ]
+
+
+@pytest.mark.parametrize("n,h,w,c,use_add", [(2, 40, 48, 64, True), (2, 40, 48, 64, False), (8, 128, 160, 64, True), (3, 21, 19, 64, False)])
+def test_conv_dgrad_halo_add_mask(n, h, w, c, use_add):
+    """64 -> 64 3x3 input gradient with the fused ReLU mask (+ residual gradient): the halo-mode main loop under the
+    register-store epilogue with its add / mask ring (one-deep next to the resident weights when both operands are fused)."""
+    o = ops()
+    dy = rnd(n, h, w, c, seed=2)
+    wt = (torch.randn(c, c, 3, 3, generator=torch.Generator().manual_seed(4)) / (c * 9) ** 0.5).to(torch.bfloat16).float().cuda()
+    pk = o.PackedConv(c, c, 3, "cuda").pack(wt)
+    base = rnd(n, h, w, c, seed=7) if use_add else None
+    msk = rnd(n, h, w, c, seed=9)
+    out = torch.full((n, h, w, c), float("nan"), dtype=torch.bfloat16, device="cuda")
+    o.conv_dgrad(o.conv_args(dy, out, pk.w_dgrad, k=3, add=base, mask=msk))
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_input((n, c, h, w), wt, nchw(dy), padding=1)
+    if use_add:
+        ref = ref + nchw(base)
+    ref = ref * (nchw(msk) > 0)
+    assert_close_bf16(nchw(out), ref, "halo dgrad add/mask")
 
 
 @pytest.mark.parametrize("n,h,w,cin,cout,k,s,split", DGRAD_CASES)
@@ -628,6 +660,7 @@ def test_roi_align_fwd_matches_torchvision(h, w, scale, c):
 
 
 @pytest.mark.parametrize("n,h,w,cin,cout", [(2, 24, 40, 64, 128), (8, 32, 40, 256, 256), (2, 64, 64, 16, 16), (2, 40, 64, 32, 32),
+                                            (8, 128, 160, 64, 64), (2, 37, 41, 64, 64), (2, 48, 40, 128, 32),
                                             (4, 64, 80, 64, 64)])
 def test_conv_fwd_fused_bn_finalize(n, h, w, cin, cout):
     """hd_conv_args.bn_fin: the last CTA of the convolution finalizes train-mode BatchNorm (mean / invstd / scale / shift and

@@ -27,6 +27,10 @@ CASES = [
     ("fwd3x3_128_128_64x80_stats", "fwd", 64, 80, 128, 128, 3, 1, "stats"),
     ("fwd3x3_256_256_32x40_stats", "fwd", 32, 40, 256, 256, 3, 1, "stats"),
     ("fwd3x3_512_512_16x20_stats", "fwd", 16, 20, 512, 512, 3, 1, "stats"),
+    ("fwd3x3_64_64_128x160_statsfin", "fwd", 128, 160, 64, 64, 3, 1, "stats,fin"),
+    ("fwd3x3_128_128_64x80_statsfin", "fwd", 64, 80, 128, 128, 3, 1, "stats,fin"),
+    ("fwd3x3_256_256_32x40_statsfin", "fwd", 32, 40, 256, 256, 3, 1, "stats,fin"),
+    ("fwd3x3_512_512_16x20_statsfin", "fwd", 16, 20, 512, 512, 3, 1, "stats,fin"),
     ("fwd3x3_16_16_512x640_stats", "fwd", 512, 640, 16, 16, 3, 1, "stats"),
     ("fwd3x3_32_16_512x640_stats", "fwd", 512, 640, 32, 16, 3, 1, "stats"),
     ("fwd3x3_32_32_256x320_stats", "fwd", 256, 320, 32, 32, 3, 1, "stats"),
@@ -34,6 +38,10 @@ CASES = [
     ("fwd3x3_128_128_80_relu", "fwd", 80, 80, 128, 128, 3, 1, "bias,relu"),
     ("dgrad1x1_64to256_160_addmask", "dgrad", 160, 160, 256, 64, 1, 1, "add,mask"),
     ("dgrad3x3_64_64_160_mask", "dgrad", 160, 160, 64, 64, 3, 1, "mask"),
+    ("dgrad3x3_64_64_128x160_mask", "dgrad", 128, 160, 64, 64, 3, 1, "mask"),
+    ("dgrad3x3_64_64_128x160_addmask", "dgrad", 128, 160, 64, 64, 3, 1, "add,mask"),
+    ("fwd3x3_64_64_160_relu", "fwd", 160, 160, 64, 64, 3, 1, "bias,relu"),
+    ("fwd3x3_128_32_256x320_stats", "fwd", 256, 320, 128, 32, 3, 1, "stats"),
     ("dgrad3x3_256_256_40_mask", "dgrad", 40, 40, 256, 256, 3, 1, "mask"),
     ("dgrad3x3_16_16_512x640", "dgrad", 512, 640, 16, 16, 3, 1, ""),
     ("dgrad3x3_32_16_512x640", "dgrad", 512, 640, 32, 16, 3, 1, ""),
@@ -69,7 +77,12 @@ def main():
             return t
 
         if kind == "fwd":
-            args = ops.conv_args(x, y, pk.w_fwd, k=k, stride=s,
+            fin = None
+            if "fin" in flags:
+                t = [own(torch.ones(cout, device=dev)) for _ in range(8)]
+                fin = ops.bn_fin(B * ho * wo, t[0], t[1], 1e-5, 0.1, t[2], t[3], t[4], t[5], t[6], t[7],
+                                 own(torch.zeros(1, dtype=torch.int32, device=dev)))
+            args = ops.conv_args(x, y, pk.w_fwd, k=k, stride=s, bn_fin=fin,
                                  bias=own(torch.randn(cout, device=dev)) if "bias" in flags else None,
                                  add=own(bf(B, ho, wo, cout)) if "add" in flags else None, relu="relu" in flags,
                                  stats=own(torch.zeros(ops.conv_fwd_tiles(x, k, s), 2, cout, device=dev)) if "stats" in flags else None)

@@ -21,6 +21,8 @@ CASES = [
     ("fwd3x3_512_512_16x20 stats", 8, 16, 20, 512, 512, 3, "stats"),
     ("fwd3x3_128_128_64x80 stats", 8, 64, 80, 128, 128, 3, "stats"),
     ("fwd3x3_64_64_128x160 stats", 8, 128, 160, 64, 64, 3, "stats"),
+    ("fwd3x3_64_64_160 bias relu", 8, 160, 160, 64, 64, 3, "bias"),
+    ("fwd3x3_128_32_256x320 stats", 8, 256, 320, 128, 32, 3, "stats"),
     ("fwd1x1_64_256_160 bias relu", 8, 160, 160, 64, 256, 1, "bias"),
     ("fwd1x1_256_64_160 bias relu", 8, 160, 160, 256, 64, 1, "bias"),
     ("fwd3x3_256_256_160 bias", 8, 160, 160, 256, 256, 3, "bias"),
