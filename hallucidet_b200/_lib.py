@@ -126,8 +126,12 @@ PROTOTYPES = {
     "hd_nchw_to_nhwc_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "hd_nhwc_to_nchw_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "hd_nms": [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p],
+    "hd_sample_balanced_workspace_bytes": [c_int],
+    "hd_sample_balanced": [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_uint64, c_void_p, c_void_p, c_void_p, c_void_p,
+                           c_void_p, ctypes.c_int64, c_void_p],
 }
-_RESTYPES = {"hd_last_error": ctypes.c_char_p, "hd_conv_workspace_bytes": ctypes.c_int64}
+_RESTYPES = {"hd_last_error": ctypes.c_char_p, "hd_conv_workspace_bytes": ctypes.c_int64,
+             "hd_sample_balanced_workspace_bytes": ctypes.c_int64}
 
 _lib = None
 

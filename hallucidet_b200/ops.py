@@ -594,6 +594,92 @@ def nms_sorted_flat(sorted_boxes, offsets, iou_threshold, counts=None):
     return keep
 
 
+class DeviceRng:
+    """The default CUDA generator's Philox offset, continued in device memory by hd_sample_balanced so that data-dependent
+    draws need no host round trip.  ``begin()`` adopts the host generator's (seed, offset) whenever it differs from what this
+    object last saw there (the generator was reseeded or used by someone else); ``sync_host()`` -- called where the step
+    syncs with the device anyway -- writes the device-side offset back into the generator."""
+    _per_device = {}
+
+    @classmethod
+    def get(cls, device):
+        device = torch.device(device)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        r = cls._per_device.get(idx)
+        if r is None:
+            r = cls._per_device[idx] = cls(idx)
+        return r
+
+    def __init__(self, idx):
+        self.idx = idx
+        self.dev = torch.device("cuda", idx)
+        self.buf = torch.zeros(2, dtype=torch.int64, device=self.dev)      # ping-pong: kernels read one word, write the other
+        self.cur = 0
+        self.seed = None
+        self.host_seen = None
+        self.pending = False
+        self.ws = {}
+
+    def generator(self):
+        if len(torch.cuda.default_generators) <= self.idx:
+            torch.cuda.init()
+        return torch.cuda.default_generators[self.idx]
+
+    def begin(self):
+        g = self.generator()
+        state = (int(g.initial_seed()), int(g.get_offset()))
+        if state != self.host_seen:
+            self.seed = state[0]
+            self.buf[self.cur].fill_(state[1])
+            self.host_seen = state
+            self.pending = False
+        return self.seed
+
+    def sync_host(self):
+        """Mirror the device-side offset into torch's generator (one 8-byte device->host read; blocks until the stream that
+        ran the last draw reaches it)."""
+        if not self.pending:
+            return
+        off = int(self.buf[self.cur].item())
+        g = self.generator()
+        g.set_offset(off)
+        self.host_seen = (int(g.initial_seed()), off)
+        self.pending = False
+
+    def workspace(self, batch):
+        w = self.ws.get(batch)
+        if w is None:
+            n = int(_lib.load().hd_sample_balanced_workspace_bytes(batch))
+            if n <= 0:
+                raise RuntimeError("hd_sample_balanced_workspace_bytes failed")
+            w = self.ws[batch] = torch.empty(n, dtype=torch.uint8, device=self.dev)
+        return w
+
+
+def sample_balanced(labels, batch_size_per_image, positive_fraction):
+    """det_utils.BalancedPositiveNegativeSampler for labels [B, N] (float32 or int64; >= 1 positive, 0 negative, else ignored),
+    drawn on the device from the default CUDA generator's Philox stream: the same selection torchvision's per-image loop
+    makes, without reading the data-dependent randperm sizes on the host.  Returns (sampled [B, N] uint8: 1 = positive drawn,
+    2 = negative drawn, 0 = not drawn; counts [B, 4] int32 = positives, negatives, drawn positives, drawn negatives)."""
+    global LAUNCHES
+    assert labels.is_cuda and labels.dim() == 2 and labels.is_contiguous() and labels.dtype in (torch.float32, torch.int64)
+    B, N = labels.shape
+    rng = DeviceRng.get(labels.device)
+    seed = rng.begin()
+    sampled = torch.empty(B, N, dtype=torch.uint8, device=labels.device)
+    counts = torch.empty(B, 4, dtype=torch.int32, device=labels.device)
+    ws = rng.workspace(B)
+    src, dst = rng.buf[rng.cur:rng.cur + 1], rng.buf[1 - rng.cur:2 - rng.cur]
+    with _Timed("sample_balanced"):
+        check(_lib.load().hd_sample_balanced(_ptr(labels), 0 if labels.dtype == torch.float32 else 1, B, N, int(batch_size_per_image),
+                                             int(batch_size_per_image * positive_fraction), seed, _ptr(src), _ptr(dst), _ptr(sampled),
+                                             _ptr(counts), _ptr(ws), ws.numel(), _stream()), "hd_sample_balanced")
+    rng.cur = 1 - rng.cur
+    rng.pending = True
+    LAUNCHES += 3
+    return sampled, counts
+
+
 def roi_align_bwd(grad_out, rois, input_shape, spatial_scale, sampling_ratio):
     """Gradient of torchvision.ops.roi_align(aligned=False) w.r.t. its fp32 NCHW input of shape ``input_shape``, for grad_out
     [K, C, PH, PW]: channels-last vector reductions (hd_roi_align_bwd_nhwc) + one layout conversion.  Returns NCHW fp32."""

@@ -275,6 +275,21 @@ int hd_regulariser(int kind, const float* hal, const float* rgb, const float* ir
 int hd_nms(const float* boxes_sorted, const int* offsets, const int* counts_dev, int problems, float iou_threshold,
            void* mask_ws, unsigned char* keep, hd_stream stream);
 
+/* ---- Balanced positive / negative sampler (RPN loss, RoI heads) without a host round trip ----------------------
+ * torchvision det_utils.BalancedPositiveNegativeSampler as the reference's detector uses it (TV models/detection/rpn.py
+ * compute_loss, roi_heads.py subsample; reached from src/utils/eval_forward_fasterrcnn.py:62-99 and :112-128) for a batch
+ * of label rows, drawn on the device from the Philox stream that torch.randperm would consume, so the selection is
+ * bit-identical to torchvision's loop on the same generator state -- but the data-dependent randperm sizes never travel
+ * to the host.  labels: [batch][n] float32 (labels_dtype 0) or int64 (1); >= 1 positive, 0 negative, anything else is
+ * ignored.  seed / *offset_in: the CUDA generator's Philox seed and offset; *offset_out (a different device word) receives
+ * the offset after the 2 * batch randperm calls.  sampled: [batch][n] bytes out, 1 = drawn positive, 2 = drawn negative,
+ * 0 = not drawn.  counts: [batch][4] int32 out = (positives, negatives, drawn positives, drawn negatives).
+ * batch <= 64, batch_size_per_image <= 1024.  workspace: hd_sample_balanced_workspace_bytes(batch) bytes, 16-byte aligned. */
+int64_t hd_sample_balanced_workspace_bytes(int batch);
+int hd_sample_balanced(const void* labels, int labels_dtype, int batch, int n, int batch_size_per_image, int num_pos_max,
+                       uint64_t seed, const uint64_t* offset_in, uint64_t* offset_out, uint8_t* sampled, int32_t* counts,
+                       void* workspace, int64_t workspace_bytes, hd_stream stream);
+
 /* ---- RoIAlign backward (box head pooling over the FPN levels) ------------------------------------------------
  * grad_in_nhwc ([n][h][w][c] fp32 channels-last scratch, zeroed by the caller) += gradient of
  * torchvision.ops.roi_align(input, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio, aligned = False) -- the op

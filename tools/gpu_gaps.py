@@ -2,20 +2,20 @@
 import os, sys, time, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hallucidet_b200.train import HalluciDetTrainer
-from oracle import step as ostep
+from hallucidet_b200 import synthetic as ostep
 from torch.profiler import profile, ProfilerActivity
 dev = torch.device("cuda", 0)
 torch.backends.cudnn.benchmark = True
 torch.backends.cuda.matmul.allow_tf32 = True
 tr = HalluciDetTrainer(detector_name="fasterrcnn", size=640, seed=123, device=dev, use_cuda_graph=True)
-ir, rgb, targets = ostep.synthetic_batch(8, 512, 640, seed=123, device=dev)
+ir, rgb, targets = ostep.synthetic_batch(8, 512, 640, seed=123, device=dev, ir_uint8=True)
 for _ in range(5):
     tr.training_step(rgb, targets, ir, targets)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(3):
         out = tr.training_step(rgb, targets, ir, targets)
-        float(out["total"])
+        float(out["total_host"])
     torch.cuda.synchronize()
 ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 iv = sorted((e.time_range.start, e.time_range.end, e.name) for e in ev)
