@@ -342,6 +342,57 @@ def filter_proposals_batched_begin(rpn, proposals, objectness, image_shapes, num
     return pend
 
 
+class _StaticProposals:
+    """Proposals of the batch in a fixed-shape layout: ``boxes`` [B, T, 4] (T = post-NMS top-n; image b's proposals are
+    rows 0 .. counts[b]-1 in torchvision's order, the rest zeros) and ``counts`` [B] on the DEVICE -- the host never learns
+    how many proposals survived, so nothing waits for the proposal filter."""
+
+    def __init__(self, boxes, counts):
+        self.boxes, self.counts = boxes, counts
+
+
+def _filter_nms_static(boxes, scores, idxs, valid, nms_thresh, top_n):
+    """``_filter_nms_batched_begin`` with a fixed-shape result: the kept boxes of every image, in the same order, scattered to
+    the front of a [B, top_n, 4] tensor; returns it with the per-image counts (device)."""
+    B, M = scores.shape
+    neg_inf = float("-inf")
+    max_coord = boxes.masked_fill(~valid[..., None], neg_inf).amax(dim=(1, 2))
+    offsets = idxs.to(boxes) * (max_coord + 1)[:, None]
+    boxes_for_nms = boxes + offsets[..., None]
+    order = torch.sort(scores.masked_fill(~valid, neg_inf), dim=1, descending=True, stable=True)[1]
+    gidx = order[..., None].expand(-1, -1, 4)
+    sorted_for_nms = torch.gather(boxes_for_nms, 1, gidx).contiguous()
+    counts = valid.sum(1, dtype=torch.int32)
+    keep = ops.nms_sorted_flat(sorted_for_nms.view(-1, 4), [i * M for i in range(B + 1)], nms_thresh, counts=counts).view(B, M)
+    csum = keep.cumsum(1)
+    sel = keep & (csum <= top_n)
+    dest = torch.where(sel, csum - 1, csum.new_full((), top_n))              # unselected boxes go to a dump column
+    out = boxes.new_zeros(B, top_n + 1, 4)
+    out.scatter_(1, dest[..., None].expand(-1, -1, 4), torch.gather(boxes, 1, gidx))
+    return out[:, :top_n], sel.sum(1)
+
+
+def filter_proposals_static(rpn, proposals, objectness, image_shapes, num_anchors_per_level):
+    """``filter_proposals_batched`` without the host read of the survivor counts: returns a ``_StaticProposals``."""
+    num_images = proposals.shape[0]
+    device = proposals.device
+    objectness = objectness.detach().reshape(num_images, -1)
+    levels = torch.cat([torch.full((n,), idx, dtype=torch.int64, device=device) for idx, n in enumerate(num_anchors_per_level)], 0)
+    levels = levels.reshape(1, -1).expand_as(objectness)
+    top_n_idx = rpn._get_top_n_idx(objectness, num_anchors_per_level)
+    batch_idx = torch.arange(num_images, device=device)[:, None]
+    objectness = objectness[batch_idx, top_n_idx]
+    levels = levels[batch_idx, top_n_idx]
+    proposals = proposals[batch_idx, top_n_idx]
+    scores = torch.sigmoid(objectness)
+    with torch.no_grad():
+        boxes = _clip_boxes_batched(proposals, image_shapes)
+        ws, hs = boxes[..., 2] - boxes[..., 0], boxes[..., 3] - boxes[..., 1]
+        valid = (ws >= rpn.min_size) & (hs >= rpn.min_size) & (scores >= rpn.score_thresh)
+        out, n = _filter_nms_static(boxes, scores, levels, valid, rpn.nms_thresh, rpn.post_nms_top_n())
+    return _StaticProposals(out, n)
+
+
 def filter_proposals_batched(rpn, proposals, objectness, image_shapes, num_anchors_per_level):
     return _resolve(filter_proposals_batched_begin(rpn, proposals, objectness, image_shapes, num_anchors_per_level))[0]
 
@@ -567,6 +618,117 @@ def select_training_samples_batched(roi_heads, proposals, targets, return_num_po
     return out
 
 
+def _sampled_rows(sampled, counts, per_image):
+    """Flat positions (ascending = image-major, ascending column: torchvision's ``where(pos | neg)`` lists back to back) of the
+    drawn entries of ``sampled`` [B, N], as a FIXED-size list of B * per_image rows; rows past the drawn total (an image with
+    fewer candidates than ``per_image``) point at entry 0 and are flagged invalid.  No host read."""
+    B, N = sampled.shape
+    S = B * per_image
+    flat = torch.nonzero_static(sampled.view(-1), size=S, fill_value=0)[:, 0]
+    n_drawn = counts[:, 2:4].sum()
+    valid = torch.arange(S, device=sampled.device) < n_drawn
+    return flat, valid, n_drawn
+
+
+def rpn_compute_loss_static(rpn, objectness, pred_bbox_deltas, labels, regression_targets, sampled, counts):
+    """``RegionProposalNetwork.compute_loss`` (TV rpn.py) on the device-side draw (ops.sample_balanced): the sampled anchors as
+    a fixed-size row list + validity weights instead of index lists whose lengths the host would have to read.  Same samples,
+    same per-element losses, same divisors; only the order of the fp32 sums differs."""
+    B, A = labels.shape
+    flat, valid, n_drawn = _sampled_rows(sampled, counts, rpn.fg_bg_sampler.batch_size_per_image)
+    denom = n_drawn.to(torch.float32)
+    is_pos = (sampled.view(-1)[flat] == 1) & valid
+    box = F.smooth_l1_loss(pred_bbox_deltas[flat], regression_targets[flat], beta=1 / 9, reduction="none").sum(1)
+    box_loss = (box * is_pos).sum() / denom
+    obj = F.binary_cross_entropy_with_logits(objectness.flatten()[flat], labels.reshape(-1)[flat], reduction="none")
+    objectness_loss = (obj * valid).sum() / denom
+    return objectness_loss, box_loss
+
+
+class _StaticSamples:
+    """RoI-head training samples in a fixed-shape layout (B * batch_size_per_image rows, image-major; rows past ``n_drawn``
+    are padding: label -100, which cross_entropy ignores)."""
+
+    def __init__(self, proposals, image_of, labels, regression_targets, matched_idxs, valid, n_drawn, per_image):
+        self.proposals, self.image_of, self.labels, self.regression_targets = proposals, image_of, labels, regression_targets
+        self.matched_idxs, self.valid, self.n_drawn, self.per_image = matched_idxs, valid, n_drawn, per_image
+
+
+def select_training_samples_static(roi_heads, proposals, targets):
+    """``RoIHeads.select_training_samples`` for a ``_StaticProposals`` batch, without any host read: ground truth appended
+    behind the (padded) proposals of each image, padding rows ignored by the sampler, the draw made on the device
+    (ops.sample_balanced: the same selection as torchvision's loop on the same generator state)."""
+    roi_heads.check_targets(targets)
+    P0, n_props = proposals.boxes, proposals.counts
+    dtype, device = P0.dtype, P0.device
+    B, T = P0.shape[:2]
+    gt, present, gl = _padded_gt(targets, dtype)
+    G = gt.shape[1]
+    N = T + G
+    P = torch.cat([P0, gt], dim=1)                                                       # add_gt_proposals
+    p_present = torch.cat([torch.arange(T, device=device)[None, :] < n_props[:, None], present], dim=1)
+    matches = _match_batched(roi_heads.proposal_matcher, gt, present, P)
+    clamped = matches.clamp(min=0)
+    labels = torch.gather(gl, 1, clamped).to(torch.int64)
+    labels = torch.where(matches == roi_heads.proposal_matcher.BELOW_LOW_THRESHOLD, labels.new_zeros(()), labels)
+    labels = torch.where(matches == roi_heads.proposal_matcher.BETWEEN_THRESHOLDS, labels.new_full((), -1), labels)
+    labels = torch.where(p_present, labels, labels.new_full((), -1))
+    sampler = roi_heads.fg_bg_sampler
+    sampled, counts = ops.sample_balanced(labels.contiguous(), sampler.batch_size_per_image, sampler.positive_fraction)
+    flat, valid, n_drawn = _sampled_rows(sampled, counts, sampler.batch_size_per_image)
+    out_props = P.reshape(-1, 4)[flat]
+    out_labels = torch.where(valid, labels.view(-1)[flat], labels.new_full((), -100))
+    out_matched = clamped.view(-1)[flat]
+    img_of = torch.div(flat, N, rounding_mode="floor")
+    matched_gt = gt.reshape(-1, 4)[img_of * G + out_matched]
+    regression_targets = _encode_single(roi_heads.box_coder, matched_gt, out_props)
+    return _StaticSamples(out_props, img_of, out_labels, regression_targets, out_matched, valid, n_drawn, counts[:, 2] + counts[:, 3])
+
+
+def fastrcnn_loss_masked(class_logits, box_regression, samples):
+    """``torchvision.models.detection.roi_heads.fastrcnn_loss`` on a ``_StaticSamples`` batch: the foreground rows enter the
+    box loss through a 0 / 1 weight instead of ``torch.where(labels > 0)`` (a host read); padding rows carry the label
+    cross_entropy ignores.  Same per-row losses and divisors as torchvision."""
+    labels = samples.labels
+    classification_loss = F.cross_entropy(class_logits, labels)                           # ignore_index = -100: the padding rows
+    S = class_logits.shape[0]
+    pos = labels > 0
+    per_class = box_regression.reshape(S, box_regression.size(-1) // 4, 4)
+    picked = per_class[torch.arange(S, device=labels.device), labels.clamp(min=0)]
+    box = F.smooth_l1_loss(picked, samples.regression_targets, beta=1 / 9, reduction="none").sum(1)
+    box_loss = (box * pos).sum() / samples.n_drawn.to(box.dtype)
+    return classification_loss, box_loss
+
+
+def postprocess_detections_static_begin(roi_heads, class_logits, box_regression, samples, image_shapes, per_image_max):
+    """``postprocess_detections_batched_begin`` for a ``_StaticSamples`` batch: image b's rows start at the exclusive prefix
+    sum of the per-image counts (device), so they are gathered into a [B, per_image_max] layout with a presence mask."""
+    device = class_logits.device
+    num_classes = class_logits.shape[-1]
+    B = len(image_shapes)
+    S = class_logits.shape[0]
+    pred_boxes = _decode(roi_heads.box_coder, box_regression, [samples.proposals])
+    pred_scores = F.softmax(class_logits, -1)
+    n = samples.per_image.to(torch.int64)
+    start = n.cumsum(0) - n
+    j = torch.arange(per_image_max, device=device)[None, :]
+    src = (start[:, None] + j).clamp(max=S - 1)
+    present = j < n[:, None]
+    boxes = pred_boxes.reshape(S, num_classes, 4)[src]
+    scores = pred_scores[src]
+    boxes = _clip_boxes_batched(boxes, image_shapes)
+    labels = torch.arange(num_classes, device=device).view(1, 1, -1).expand_as(scores)
+    boxes, scores, labels = boxes[:, :, 1:], scores[:, :, 1:], labels[:, :, 1:]
+    boxes, scores, labels = boxes.reshape(B, -1, 4), scores.reshape(B, -1), labels.reshape(B, -1)
+    ws, hs = boxes[..., 2] - boxes[..., 0], boxes[..., 3] - boxes[..., 1]
+    valid = (scores > roi_heads.score_thresh) & (ws >= 1e-2) & (hs >= 1e-2)
+    valid = valid & present[:, :, None].expand(-1, -1, num_classes - 1).reshape(B, -1)
+    pend = _filter_nms_batched_begin(boxes, scores, labels, valid, roi_heads.nms_thresh, roi_heads.detections_per_img)
+    inner = pend.finish
+    pend.finish = lambda n_sel: (lambda r: (list(r[0]), list(r[1]), list(r[2])))(inner(n_sel))
+    return pend
+
+
 def fastrcnn_loss_static(class_logits, box_regression, labels, regression_targets, num_pos):
     """``torchvision.models.detection.roi_heads.fastrcnn_loss`` with the foreground count passed in (known on the host
     from the sampler), so ``torch.where(labels > 0)`` needs no device->host sync.  Same indices, same reductions."""
@@ -683,6 +845,46 @@ def multiscale_roi_align_one_sync(pooler, features, boxes, image_shapes):
     return result
 
 
+def multiscale_roi_align_static(pooler, features, boxes, image_of, image_shapes):
+    """``MultiScaleRoIAlign.forward`` for boxes [S, 4] whose image index is a device tensor (``_StaticSamples``): the RoI format
+    and the level mapper are the element-wise operations of TV ops/poolers.py on the concatenated boxes; all levels are pooled
+    by one launch each way (``_MultiLevelRoIAlign``).  Requires ``_ml_roi_align_ok``."""
+    from torchvision.ops import boxes as box_ops, poolers
+    x_filtered = poolers._filter_input(features, pooler.featmap_names)
+    if pooler.scales is None or pooler.map_levels is None:
+        pooler.scales, pooler.map_levels = poolers._setup_scales(x_filtered, image_shapes, pooler.canonical_scale, pooler.canonical_level)
+    rois = torch.cat([image_of.to(boxes.dtype)[:, None], boxes], dim=1)
+    if len(x_filtered) == 1:
+        levels = torch.zeros(boxes.shape[0], dtype=torch.int64, device=boxes.device)
+    else:
+        lm = pooler.map_levels
+        s = torch.sqrt(box_ops.box_area(boxes))
+        target_lvls = torch.floor(lm.lvl0 + torch.log2(s / lm.s0) + torch.tensor(lm.eps, dtype=s.dtype))
+        target_lvls = torch.clamp(target_lvls, min=lm.k_min, max=lm.k_max)
+        levels = (target_lvls.to(torch.int64) - lm.k_min).to(torch.int64)
+    return _MultiLevelRoIAlign.apply(rois, levels, tuple(float(sc) for sc in pooler.scales), tuple(pooler.output_size),
+                                     int(pooler.sampling_ratio), *x_filtered)
+
+
+def _static_tail_ok(model, features):
+    """The sync-free training tail (STATIC_TAIL) needs the whole-batch restatements, the multi-level RoIAlign kernels and
+    torchvision's stock sampler / pooler types."""
+    from torchvision.ops import MultiScaleRoIAlign, poolers
+    from torchvision.models.detection._utils import BalancedPositiveNegativeSampler
+    feats = list(features.values())
+    if not (STATIC_TAIL and BATCHED_TAIL and EARLY_RPN_TARGETS and feats[0].is_cuda and feats[0].dtype == torch.float32):
+        return False
+    rh = model.roi_heads
+    if type(rh.box_roi_pool) is not MultiScaleRoIAlign or type(rh.fg_bg_sampler) is not BalancedPositiveNegativeSampler:
+        return False
+    if type(model.rpn.fg_bg_sampler) is not BalancedPositiveNegativeSampler or rh.has_mask() or rh.has_keypoint():
+        return False
+    if max(rh.fg_bg_sampler.batch_size_per_image, model.rpn.fg_bg_sampler.batch_size_per_image) > 1024:
+        return False
+    x_filtered = poolers._filter_input(features, rh.box_roi_pool.featmap_names)
+    return _ml_roi_align_ok(x_filtered, rh.box_roi_pool.output_size, rh.box_roi_pool.sampling_ratio)
+
+
 def _batched_ok(n_boxes):
     return n_boxes <= ops.NMS_MAX_BOXES and n_boxes * 4 <= 100_000
 
@@ -787,6 +989,8 @@ class DeferredDetections:
     def resolve(self):
         if self._value is None:
             self._event.synchronize()
+            _run_deferred_checks()                    # input checks queued by a sync-free step are evaluated here
+            ops.DeviceRng.get(self._pending.counts_dev.device).sync_host()          # device-side sampler draws -> torch's generator
             side = self._stream
             with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()), torch.no_grad():
                 boxes, scores, labels = self._pending.finish(self._counts.tolist())
@@ -841,6 +1045,8 @@ class DeferredCall:
 
 
 GRAPH_PROPOSAL_FILTER = _os.environ.get("HD_GRAPH_PROPOSALS", "1") == "1"
+# Training tail without device->host reads: fixed-shape proposals, device-side sampler draws (ops.sample_balanced), masked losses
+STATIC_TAIL = _os.environ.get("HD_STATIC_TAIL", "1") == "1"
 _STATIC_PROGRAMS = {}
 
 
@@ -920,7 +1126,7 @@ def _rpn_head(head, features):
     return logits, bbox_reg
 
 
-def rpn_eval(model, images, features, targets, targets_event=None):
+def rpn_eval(model, images, features, targets, targets_event=None, static=False):
     """``RegionProposalNetwork.forward`` in training mode (TV rpn.py:337-388) as the reference's eval_forward uses it
     (src/utils/eval_forward_fasterrcnn.py:62-99).  ``targets_event``: CUDA event recorded once ``targets`` are final on
     the current stream; lets the anchor-target work start before the backbone forward has finished."""
@@ -953,9 +1159,11 @@ def rpn_eval(model, images, features, targets, targets_event=None):
         def program():
             o2, d2 = concat_box_prediction_layers(obj_lv, del_lv)
             props = _decode(model.rpn.box_coder, d2, anchors).view(num_images, -1, 4)
+            if static:
+                return filter_proposals_static(model.rpn, props, o2, image_sizes, num_anchors_per_level)
             return filter_proposals_batched_begin(model.rpn, props, o2, image_sizes, num_anchors_per_level)
 
-        key = (id(model.rpn), tuple(o.data_ptr() for o in obj_lv), anchors[0].data_ptr(), tuple(map(tuple, image_sizes)))
+        key = (id(model.rpn), tuple(o.data_ptr() for o in obj_lv), anchors[0].data_ptr(), tuple(map(tuple, image_sizes)), bool(static))
         with torch.no_grad():
             pend_boxes = _static_program(key).run(program)
     objectness, pred_bbox_deltas = concat_box_prediction_layers(objectness, pred_bbox_deltas)
@@ -967,9 +1175,34 @@ def rpn_eval(model, images, features, targets, targets_event=None):
         # anchor sampler depend only on the anchors and the targets, not on the network: they run on a side stream as soon
         # as the targets exist -- i.e. underneath the backbone forward -- including the sampler's host read and its
         # randperm calls, which therefore leave the critical path (same calls in the same order: same CUDA generator use).
+        static = static and EARLY_RPN_TARGETS
         if pend_boxes is None:
-            pend_boxes = filter_proposals_batched_begin(model.rpn, proposals, objectness, images.image_sizes, num_anchors_per_level)
+            if static:
+                pend_boxes = filter_proposals_static(model.rpn, proposals, objectness, images.image_sizes, num_anchors_per_level)
+            else:
+                pend_boxes = filter_proposals_batched_begin(model.rpn, proposals, objectness, images.image_sizes, num_anchors_per_level)
         main = torch.cuda.current_stream(objectness.device)
+        if static:
+            # sync-free variant: the anchor sampler's draw stays on the device (same selection, see ops.sample_balanced), the loss
+            # takes the sampled anchors as a fixed-size row list, and the proposals keep their fixed-shape layout
+            side = _side_streams(objectness.device, 1)[0]
+            if targets_event is None or anchors_fresh:
+                targets_event = torch.cuda.Event()
+                targets_event.record(main)
+            side.wait_event(targets_event)
+            sampler = model.rpn.fg_bg_sampler
+            with torch.cuda.stream(side), torch.no_grad():
+                labels, matched_gt_boxes = assign_targets_to_anchors_batched(model.rpn, anchors, targets)
+                regression_targets = _encode_single(model.rpn.box_coder, matched_gt_boxes.reshape(-1, 4), torch.cat(anchors, dim=0))
+                sampled, counts = ops.sample_balanced(labels.contiguous(), sampler.batch_size_per_image, sampler.positive_fraction)
+                done = torch.cuda.Event()
+                done.record(side)
+            main.wait_event(done)
+            for t in [labels, regression_targets, sampled, counts] + list(_padded_gt(targets, targets[0]["boxes"].dtype)):
+                t.record_stream(main)
+            loss_objectness, loss_rpn_box_reg = rpn_compute_loss_static(model.rpn, objectness, pred_bbox_deltas, labels,
+                                                                        regression_targets, sampled, counts)
+            return pend_boxes, {"loss_objectness": loss_objectness, "loss_rpn_box_reg": loss_rpn_box_reg}
         if EARLY_RPN_TARGETS:
             side = _side_streams(objectness.device, 1)[0]
             if targets_event is None or anchors_fresh:
@@ -1055,6 +1288,37 @@ def postprocess_detections_concurrent(roi_heads, class_logits, box_regression, p
     return [r[0] for r in results], [r[1] for r in results], [r[2] for r in results]
 
 
+def _roi_heads_eval_static(model, features, proposals, image_shapes, targets):
+    """``roi_heads_eval`` for ``_StaticProposals``: no device->host read between the backbone and the losses.  The detections
+    (a by-product in the train step) are post-processed on a side stream and assembled when the caller resolves them."""
+    rh = model.roi_heads
+    with torch.no_grad():
+        samples = select_training_samples_static(rh, proposals, targets)
+    box_features = multiscale_roi_align_static(rh.box_roi_pool, features, samples.proposals, samples.image_of, image_shapes)
+    box_features = rh.box_head(box_features)
+    class_logits, box_regression = rh.box_predictor(box_features)
+    loss_classifier, loss_box_reg = fastrcnn_loss_masked(class_logits, box_regression, samples)
+    losses = {"loss_classifier": loss_classifier, "loss_box_reg": loss_box_reg}
+    per_image_max = rh.fg_bg_sampler.batch_size_per_image
+    with torch.no_grad():
+        cl, br = class_logits.detach(), box_regression.detach()
+        if DEFER_DETECTIONS and POSTPROCESS_SIDE_STREAM:
+            main = torch.cuda.current_stream(cl.device)
+            side = _side_streams(cl.device, 1)[0]
+            side.wait_stream(main)
+            for t in (cl, br, samples.proposals, samples.per_image):
+                t.record_stream(side)
+            with torch.cuda.stream(side):
+                pend = postprocess_detections_static_begin(rh, cl, br, samples, image_shapes, per_image_max)
+                return DeferredDetections(pend, side), losses
+        pend = postprocess_detections_static_begin(rh, cl, br, samples, image_shapes, per_image_max)
+        if DEFER_DETECTIONS:
+            return DeferredDetections(pend), losses
+        boxes, scores, labels = _resolve(pend)[0]
+    ops.DeviceRng.get(cl.device).sync_host()
+    return [{"boxes": boxes[i], "labels": labels[i], "scores": scores[i]} for i in range(len(boxes))], losses
+
+
 def roi_heads_eval(model, features, proposals, image_shapes, targets=None, train_det=False):
     for t in targets:
         if t["boxes"].dtype not in (torch.float, torch.double, torch.half):
@@ -1062,6 +1326,8 @@ def roi_heads_eval(model, features, proposals, image_shapes, targets=None, train
         if t["labels"].dtype != torch.int64:
             raise TypeError(f"target labels must of int64 type, instead got {t['labels'].dtype}")
     from torchvision.ops import MultiScaleRoIAlign
+    if isinstance(proposals, _StaticProposals):
+        return _roi_heads_eval_static(model, features, proposals, image_shapes, targets)
     num_pos = None
     if BATCHED_TAIL and proposals[0].is_cuda:
         with torch.no_grad():
@@ -1155,14 +1421,17 @@ def eval_forward_fasterrcnn(model, images, targets, train_det=False, model_name=
     features = model.backbone(images.tensors)
     if isinstance(features, torch.Tensor):
         features = OrderedDict([("0", features)])
-    proposals, proposal_losses = rpn_eval(model, images, features, targets, targets_event)
+    static = _static_tail_ok(model, features)
+    proposals, proposal_losses = rpn_eval(model, images, features, targets, targets_event, static=static)
     detections, detector_losses = roi_heads_eval(model, features, proposals, images.image_sizes, targets)
     if isinstance(detections, DeferredDetections):
         image_sizes = images.image_sizes
         detections.then(lambda d: model.transform.postprocess(d, image_sizes, original_image_sizes))
+        if not static:
+            _run_deferred_checks()
     else:
         detections = model.transform.postprocess(detections, images.image_sizes, original_image_sizes)
-    _run_deferred_checks()                                # (already evaluated at the first host sync on the batched path)
+        _run_deferred_checks()                            # (already evaluated at the first host sync on the batched path)
     losses = {}
     losses.update(detector_losses)
     losses.update(proposal_losses)
