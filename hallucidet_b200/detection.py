@@ -638,10 +638,13 @@ def rpn_compute_loss_static(rpn, objectness, pred_bbox_deltas, labels, regressio
     flat, valid, n_drawn = _sampled_rows(sampled, counts, rpn.fg_bg_sampler.batch_size_per_image)
     denom = n_drawn.to(torch.float32)
     is_pos = (sampled.view(-1)[flat] == 1) & valid
-    box = F.smooth_l1_loss(pred_bbox_deltas[flat], regression_targets[flat], beta=1 / 9, reduction="none").sum(1)
-    box_loss = (box * is_pos).sum() / denom
-    obj = F.binary_cross_entropy_with_logits(objectness.flatten()[flat], labels.reshape(-1)[flat], reduction="none")
-    objectness_loss = (obj * valid).sum() / denom
+    # (the regression target of a background anchor is meaningless -- -inf / NaN when its image has no ground truth -- and
+    # torchvision never touches it: zero it before the element-wise loss instead of multiplying a NaN by 0)
+    tgt = torch.where(is_pos[:, None], regression_targets[flat], regression_targets.new_zeros(()))
+    box = F.smooth_l1_loss(pred_bbox_deltas[flat], tgt, beta=1 / 9, reduction="none").sum(1)
+    box_loss = torch.where(is_pos, box, box.new_zeros(())).sum() / denom
+    obj = F.binary_cross_entropy_with_logits(objectness.flatten()[flat], labels.reshape(-1)[flat].clamp(min=0), reduction="none")
+    objectness_loss = torch.where(valid, obj, obj.new_zeros(())).sum() / denom
     return objectness_loss, box_loss
 
 
@@ -695,8 +698,9 @@ def fastrcnn_loss_masked(class_logits, box_regression, samples):
     pos = labels > 0
     per_class = box_regression.reshape(S, box_regression.size(-1) // 4, 4)
     picked = per_class[torch.arange(S, device=labels.device), labels.clamp(min=0)]
-    box = F.smooth_l1_loss(picked, samples.regression_targets, beta=1 / 9, reduction="none").sum(1)
-    box_loss = (box * pos).sum() / samples.n_drawn.to(box.dtype)
+    tgt = torch.where(pos[:, None], samples.regression_targets, samples.regression_targets.new_zeros(()))   # (see rpn_compute_loss_static)
+    box = F.smooth_l1_loss(picked, tgt, beta=1 / 9, reduction="none").sum(1)
+    box_loss = torch.where(pos, box, box.new_zeros(())).sum() / samples.n_drawn.to(box.dtype)
     return classification_loss, box_loss
 
 

@@ -86,3 +86,132 @@ def test_sample_balanced_chains_across_calls():
     got_b, _ = ops.sample_balanced(b, 512, 0.25)
     ops.DeviceRng.get(a.device).sync_host()
     assert torch.equal(got_a, ref_a) and torch.equal(got_b, ref_b) and gen.get_offset() == ref_offset
+
+
+# ---- the sync-free training tail built on the device-side draw (hallucidet_b200.detection STATIC_TAIL) ----------------------
+
+def _detector_setup():
+    from oracle import detector as odet
+    from torchvision.models.detection.image_list import ImageList
+    det = odet.build_detector("fasterrcnn", seed=1).cuda()
+    g = torch.Generator().manual_seed(0)
+    B = 3
+    x = torch.rand(B, 3, 128, 160, generator=g).cuda()
+    with torch.no_grad():
+        feats = list(det.backbone(x).values())
+    anchors = det.rpn.anchor_generator(ImageList(x, [(128, 160)] * B), feats)
+
+    def mk(n):
+        xy, wh = torch.rand(n, 2, generator=g) * 80, torch.rand(n, 2, generator=g) * 60 + 8
+        return {"boxes": torch.cat([xy, xy + wh], 1).cuda(), "labels": torch.ones(n, dtype=torch.int64).cuda()}
+    targets = [mk(3), {"boxes": torch.zeros(0, 4).cuda(), "labels": torch.zeros(0, dtype=torch.int64).cuda()}, mk(5)]
+    return det, g, anchors, targets
+
+
+def test_static_rpn_loss_matches_torchvision():
+    """rpn_compute_loss_static (fixed-size row list + validity weights, device-side draw) against RegionProposalNetwork.compute_loss
+    on the same generator state: same anchors drawn, losses equal up to the order of the fp32 sums, generator left identical."""
+    from hallucidet_b200 import detection as D, ops
+    det, g, anchors, targets = _detector_setup()
+    B, A = len(anchors), anchors[0].shape[0]
+    la, ma = det.rpn.assign_targets_to_anchors(anchors, targets)
+    lb, mb = D.assign_targets_to_anchors_batched(det.rpn, anchors, targets)
+    obj = torch.randn(B * A, 1, generator=g).cuda().requires_grad_()
+    deltas = torch.randn(B * A, 4, generator=g).cuda().requires_grad_()
+    rt = det.rpn.box_coder.encode(ma, anchors)
+    torch.manual_seed(5)
+    l1 = det.rpn.compute_loss(obj, deltas, la, rt)
+    g1 = torch.autograd.grad(l1[0] + l1[1], (obj, deltas))
+    after1 = torch.rand(1, device="cuda")
+    rtb = det.rpn.box_coder.encode_single(mb.reshape(-1, 4), torch.cat(anchors, 0))
+    torch.manual_seed(5)
+    s = det.rpn.fg_bg_sampler
+    sampled, counts = ops.sample_balanced(lb.contiguous(), s.batch_size_per_image, s.positive_fraction)
+    l2 = D.rpn_compute_loss_static(det.rpn, obj, deltas, lb, rtb, sampled, counts)
+    g2 = torch.autograd.grad(l2[0] + l2[1], (obj, deltas))
+    ops.DeviceRng.get(obj.device).sync_host()
+    after2 = torch.rand(1, device="cuda")
+    assert torch.equal(after1, after2)
+    for a, b in zip(l1, l2):
+        assert torch.allclose(a, b, rtol=2e-6, atol=1e-7), (float(a), float(b))
+    for a, b in zip(g1, g2):
+        assert torch.equal(a != 0, b != 0) and torch.allclose(a, b, rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("sizes", [(50, 37, 64), (900, 1000, 700), (2000, 2000, 1500)])
+def test_static_roi_samples_and_loss_match_torchvision(sizes):
+    """select_training_samples_static + fastrcnn_loss_masked on padded fixed-shape proposals against torchvision's
+    select_training_samples + fastrcnn_loss on the ragged lists: identical sampled proposals / labels / regression targets
+    (also when an image has fewer candidates than the 512-row budget: padding rows), losses equal up to summation order."""
+    from torchvision.models.detection.roi_heads import fastrcnn_loss
+    from hallucidet_b200 import detection as D, ops
+    det, g, anchors, targets = _detector_setup()
+    rh = det.roi_heads
+    T = 2000
+    props = [torch.cat([torch.rand(n, 2, generator=g) * 100, torch.rand(n, 2, generator=g) * 60 + 100], 1).cuda() for n in sizes]
+    torch.manual_seed(9)
+    r_props, r_matched, r_labels, r_reg = rh.select_training_samples([p.clone() for p in props], targets)
+    after1 = torch.rand(1, device="cuda")
+    padded = torch.zeros(len(props), T, 4, device="cuda")
+    for b, p in enumerate(props):
+        padded[b, :p.shape[0]] = p
+    sp = D._StaticProposals(padded, torch.tensor(sizes, device="cuda"))
+    torch.manual_seed(9)
+    smp = D.select_training_samples_static(rh, sp, targets)
+    ops.DeviceRng.get(padded.device).sync_host()
+    after2 = torch.rand(1, device="cuda")
+    assert torch.equal(after1, after2)
+    n = sum(x.shape[0] for x in r_props)
+    assert int(smp.n_drawn) == n and smp.per_image.tolist() == [x.shape[0] for x in r_props]
+    assert bool(smp.valid[:n].all()) and not bool(smp.valid[n:].any())
+    assert torch.equal(smp.proposals[:n], torch.cat(r_props)) and torch.equal(smp.labels[:n], torch.cat(r_labels))
+    assert torch.equal(smp.regression_targets[:n], torch.cat(r_reg)) and torch.equal(smp.matched_idxs[:n], torch.cat(r_matched))
+    assert bool((smp.labels[n:] == -100).all())
+    img_ref = torch.cat([torch.full((x.shape[0],), b, device="cuda") for b, x in enumerate(r_props)])
+    assert torch.equal(smp.image_of[:n], img_ref)
+    S = smp.labels.shape[0]
+    logits = torch.randn(S, 2, generator=g).cuda().requires_grad_()
+    reg = torch.randn(S, 8, generator=g).cuda().requires_grad_()
+    l1 = fastrcnn_loss(logits[:n], reg[:n], r_labels, r_reg)
+    l2 = D.fastrcnn_loss_masked(logits, reg, smp)
+    for a, b in zip(l1, l2):
+        assert torch.allclose(a, b, rtol=2e-6, atol=1e-7), (float(a), float(b))
+    g1 = torch.autograd.grad(l1[0] + l1[1], (logits, reg))
+    g2 = torch.autograd.grad(l2[0] + l2[1], (logits, reg))
+    for a, b in zip(g1, g2):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-9) and bool((b[n:] == 0).all())
+
+
+def test_static_tail_matches_host_synchronised_tail():
+    """eval_forward_fasterrcnn with STATIC_TAIL on and off, same generator state: same detections, losses equal up to the
+    order of fp32 sums -- the sync-free tail draws the same anchors and proposals as the tail that reads the counts on the host."""
+    from hallucidet_b200 import detection as D
+    from hallucidet_b200.train import HalluciDetTrainer
+    from hallucidet_b200.synthetic import synthetic_batch
+    dev = torch.device("cuda", 0)
+    tr = HalluciDetTrainer(detector_name="fasterrcnn", size=320, seed=3, device=dev)
+    ir, rgb, targets = synthetic_batch(4, 256, 320, seed=5, device=dev)
+    tr.encoder_decoder.eval()
+    with torch.no_grad():
+        hal = tr.encoder_decoder(ir.repeat(1, 3, 1, 1)).float()
+    outs = {}
+    for mode in (False, True):
+        D.STATIC_TAIL = mode
+        try:
+            torch.manual_seed(21)
+            x = hal.clone().requires_grad_()
+            losses, dets = D.eval_forward_fasterrcnn(tr.detector.model if hasattr(tr.detector, "model") else tr.detector, list(x), targets)
+            total = sum(losses.values())
+            (gx,) = torch.autograd.grad(total, x)
+            outs[mode] = (losses, dets, gx, torch.rand(1, device=dev))
+        finally:
+            D.STATIC_TAIL = True
+    (l0, d0, g0, a0), (l1, d1, g1, a1) = outs[False], outs[True]
+    assert torch.equal(a0, a1)
+    for k in l0:
+        assert torch.allclose(l0[k], l1[k], rtol=1e-5, atol=1e-7), (k, float(l0[k]), float(l1[k]))
+    assert len(d0) == len(d1)
+    for a, b in zip(d0, d1):
+        assert torch.equal(a["boxes"], b["boxes"]) and torch.equal(a["labels"], b["labels"]) and torch.equal(a["scores"], b["scores"])
+    rel = float((g0 - g1).norm() / g0.norm())
+    assert rel < 2e-2, rel        # bf16 backbone backward: run-to-run gradient noise floor is ~1e-2 (see DESIGN.md)
