@@ -1038,6 +1038,8 @@ class DeferredCall:
             side.wait_event(self._event)
             with torch.cuda.stream(side), torch.no_grad():
                 value = self._fn()
+                _run_deferred_checks()
+                ops.DeviceRng.get(side.device).sync_host()        # device-side sampler draws -> torch's generator
             main = torch.cuda.current_stream(side.device)
             main.wait_stream(side)
             for d in value:
@@ -1307,14 +1309,12 @@ def _roi_heads_eval_static(model, features, proposals, image_shapes, targets):
     with torch.no_grad():
         cl, br = class_logits.detach(), box_regression.detach()
         if DEFER_DETECTIONS and POSTPROCESS_SIDE_STREAM:
-            main = torch.cuda.current_stream(cl.device)
-            side = _side_streams(cl.device, 1)[0]
-            side.wait_stream(main)
-            for t in (cl, br, samples.proposals, samples.per_image):
-                t.record_stream(side)
-            with torch.cuda.stream(side):
-                pend = postprocess_detections_static_begin(rh, cl, br, samples, image_shapes, per_image_max)
-                return DeferredDetections(pend, side), losses
+            # the detections feed no loss: even ISSUING their post-processing (~100 small launches of host time) waits until
+            # the caller has enqueued the backward pass; it then runs on a side stream next to it
+            def late():
+                boxes, scores, labels = _resolve(postprocess_detections_static_begin(rh, cl, br, samples, image_shapes, per_image_max))[0]
+                return [{"boxes": boxes[i], "labels": labels[i], "scores": scores[i]} for i in range(len(boxes))]
+            return DeferredCall(late, [cl, br, samples.proposals, samples.per_image]), losses
         pend = postprocess_detections_static_begin(rh, cl, br, samples, image_shapes, per_image_max)
         if DEFER_DETECTIONS:
             return DeferredDetections(pend), losses
@@ -1428,7 +1428,7 @@ def eval_forward_fasterrcnn(model, images, targets, train_det=False, model_name=
     static = _static_tail_ok(model, features)
     proposals, proposal_losses = rpn_eval(model, images, features, targets, targets_event, static=static)
     detections, detector_losses = roi_heads_eval(model, features, proposals, images.image_sizes, targets)
-    if isinstance(detections, DeferredDetections):
+    if isinstance(detections, (DeferredDetections, DeferredCall)):
         image_sizes = images.image_sizes
         detections.then(lambda d: model.transform.postprocess(d, image_sizes, original_image_sizes))
         if not static:

@@ -40,3 +40,11 @@ print("gaps < 10us total ms/step", sum(g for g, _, _ in gaps if g <= 10) / 3e3, 
 step = (t1 - t0) / 3
 for g, at, n in sorted(big, key=lambda x: x[1])[:40]:
     print(f"gap {g:8.1f} us at {at % step / 1e3:7.2f} ms into step, before {n[:80]}")
+
+# kernel sequence of the last profiled step (name, stream, start, duration) for offline inspection
+if os.environ.get("HD_GAPS_DUMP"):
+    ev3 = sorted(((e.time_range.start, e.time_range.end, e.name, getattr(e, "device_resource_id", -1)) for e in ev), key=lambda x: x[0])
+    last = [x for x in ev3 if x[0] >= t0 + 2 * step]
+    with open(os.environ["HD_GAPS_DUMP"], "w") as f:
+        for s, e, n, st in last:
+            f.write(f"{(s - last[0][0]):10.1f} {e - s:8.1f} s{st} {n[:140]}\n")
