@@ -126,6 +126,7 @@ PROTOTYPES = {
     "hd_nchw_to_nhwc_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "hd_nhwc_to_nchw_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "hd_nms": [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p],
+    "hd_nms_valid": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p],
     "hd_sample_balanced_workspace_bytes": [c_int],
     "hd_sample_balanced": [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_uint64, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_void_p, ctypes.c_int64, c_void_p],

@@ -22,13 +22,14 @@ namespace {
 
 constexpr int kNmsBox = 64;                 // boxes per mask word
 constexpr int kScanThreads = 256;
-constexpr int kMaxProblems = 16;            // per launch
+constexpr int kMaxProblems = 64;            // per launch
 constexpr int kMaxColBlocks = 128;          // shared-memory budget of the scan kernel: n <= 8192 boxes per problem
 
 struct NmsBatch {
     int count;
     int first;                              // index of the first problem of this launch (into counts)
     const int* counts;                      // optional device array: actual box count per problem (<= capacity)
+    const unsigned char* valid;             // optional device bytes, one per box slot: 0 = the box takes no part (never kept, suppresses nothing)
     int box_off[kMaxProblems];              // first box of the problem in the concatenated (sorted) box array
     int n[kMaxProblems];                    // capacity (boxes reserved for the problem)
     long mask_off[kMaxProblems];            // first mask word of the problem
@@ -97,7 +98,15 @@ __global__ void __launch_bounds__(kScanThreads, 1) nms_scan_kernel(const unsigne
     unsigned long long* removed = nsm;                                   // [col_blocks]
     unsigned long long* rows = nsm + kMaxColBlocks;                      // [2][64][col_blocks]: words c.. of the rows of chunk c
     const int tid = threadIdx.x;
-    for (int i = tid; i < col_blocks; i += kScanThreads) removed[i] = 0;
+    for (int i = tid; i < col_blocks; i += kScanThreads) {
+        unsigned long long r = 0;
+        if (B.valid != nullptr) {                                        // boxes filtered out by the caller start out "removed"
+            const unsigned char* v = B.valid + B.box_off[pb] + i * kNmsBox;
+            for (int b = 0; b < kNmsBox && i * kNmsBox + b < n; ++b)
+                if (!v[b]) r |= 1ULL << b;
+        }
+        removed[i] = r;
+    }
     for (int i = n + tid; i < B.n[pb]; i += kScanThreads) keep[i] = 0;   // reserved but unused slots
 
     // rows of chunk c, words [c, col_blocks) -> rows[buf][i][0 .. col_blocks - c)
@@ -157,8 +166,18 @@ using namespace hd;
 // offsets (host): problems + 1 box offsets (the capacity of each problem); counts_dev (optional, device): the number of
 // boxes actually present in each problem (the rest of its slots get keep = 0) -- lets the caller stay sync-free.  mask_ws: sum over problems of n * ceil(n / 64) 64-bit words (device scratch).
 // keep: [total] bytes, 1 = the box survives.  Replaces torchvision.ops.nms's kernels (see the header of this file).
+extern "C" int hd_nms_valid(const float* boxes_sorted, const int* offsets, const int* counts_dev, const unsigned char* valid_dev,
+                            int problems, float iou_threshold, void* mask_ws, unsigned char* keep, hd_stream stream_);
+
 extern "C" int hd_nms(const float* boxes_sorted, const int* offsets, const int* counts_dev, int problems, float iou_threshold,
                       void* mask_ws, unsigned char* keep, hd_stream stream_) {
+    return hd_nms_valid(boxes_sorted, offsets, counts_dev, nullptr, problems, iou_threshold, mask_ws, keep, stream_);
+}
+
+// hd_nms with an optional per-box-slot validity mask (device bytes): a box with valid = 0 is never kept and suppresses nothing,
+// wherever it sits in its problem -- the caller's score / size filters need no compaction (and no host sync) before the NMS.
+extern "C" int hd_nms_valid(const float* boxes_sorted, const int* offsets, const int* counts_dev, const unsigned char* valid_dev,
+                            int problems, float iou_threshold, void* mask_ws, unsigned char* keep, hd_stream stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     HD_CHECK_ARG(offsets != nullptr && problems >= 0);
     if (problems == 0) return HD_OK;
@@ -173,6 +192,7 @@ extern "C" int hd_nms(const float* boxes_sorted, const int* offsets, const int* 
         memset(&B, 0, sizeof(B));
         B.first = p0;
         B.counts = counts_dev;
+        B.valid = valid_dev;
         int max_cb = 0;
         for (int p = p0; p < problems && p < p0 + kMaxProblems; ++p) {
             const int n = offsets[p + 1] - offsets[p];

@@ -351,9 +351,15 @@ class _StaticProposals:
         self.boxes, self.counts = boxes, counts
 
 
-def _filter_nms_static(boxes, scores, idxs, valid, nms_thresh, top_n):
+def _filter_nms_static(boxes, scores, idxs, valid, nms_thresh, top_n, group_sizes=None):
     """``_filter_nms_batched_begin`` with a fixed-shape result: the kept boxes of every image, in the same order, scattered to
-    the front of a [B, top_n, 4] tensor; returns it with the per-image counts (device)."""
+    the front of a [B, top_n, 4] tensor; returns it with the per-image counts (device).
+
+    ``group_sizes`` (host ints summing to M): the columns are laid out category by category (``idxs`` constant within a group)
+    and every group is already in descending score order (the RPN's per-level top-k).  Boxes of different categories never
+    suppress each other, so each (image, category) pair is then its own NMS problem -- 40 short problems running side by side
+    instead of 8 long ones (the scan over a problem is sequential) -- on the SAME offset coordinates torchvision's
+    ``batched_nms`` feeds its kernel, with the filtered boxes masked instead of sorted to the end.  Same keep set."""
     B, M = scores.shape
     neg_inf = float("-inf")
     max_coord = boxes.masked_fill(~valid[..., None], neg_inf).amax(dim=(1, 2))
@@ -361,9 +367,17 @@ def _filter_nms_static(boxes, scores, idxs, valid, nms_thresh, top_n):
     boxes_for_nms = boxes + offsets[..., None]
     order = torch.sort(scores.masked_fill(~valid, neg_inf), dim=1, descending=True, stable=True)[1]
     gidx = order[..., None].expand(-1, -1, 4)
-    sorted_for_nms = torch.gather(boxes_for_nms, 1, gidx).contiguous()
-    counts = valid.sum(1, dtype=torch.int32)
-    keep = ops.nms_sorted_flat(sorted_for_nms.view(-1, 4), [i * M for i in range(B + 1)], nms_thresh, counts=counts).view(B, M)
+    if group_sizes is not None and sum(group_sizes) == M and len(group_sizes) * B <= 64:
+        bounds = [0]
+        for b in range(B):
+            for g in group_sizes:
+                bounds.append(bounds[-1] + g)
+        keep0 = ops.nms_sorted_flat(boxes_for_nms.reshape(-1, 4).contiguous(), bounds, nms_thresh, valid=valid.reshape(-1).contiguous())
+        keep = torch.gather(keep0.view(B, M), 1, order)
+    else:
+        sorted_for_nms = torch.gather(boxes_for_nms, 1, gidx).contiguous()
+        counts = valid.sum(1, dtype=torch.int32)
+        keep = ops.nms_sorted_flat(sorted_for_nms.view(-1, 4), [i * M for i in range(B + 1)], nms_thresh, counts=counts).view(B, M)
     csum = keep.cumsum(1)
     sel = keep & (csum <= top_n)
     dest = torch.where(sel, csum - 1, csum.new_full((), top_n))              # unselected boxes go to a dump column
@@ -389,7 +403,9 @@ def filter_proposals_static(rpn, proposals, objectness, image_shapes, num_anchor
         boxes = _clip_boxes_batched(proposals, image_shapes)
         ws, hs = boxes[..., 2] - boxes[..., 0], boxes[..., 3] - boxes[..., 1]
         valid = (ws >= rpn.min_size) & (hs >= rpn.min_size) & (scores >= rpn.score_thresh)
-        out, n = _filter_nms_static(boxes, scores, levels, valid, rpn.nms_thresh, rpn.post_nms_top_n())
+        per_level = [min(rpn.pre_nms_top_n(), n) for n in num_anchors_per_level]       # _get_top_n_idx: top-k per level, level-major
+        out, n = _filter_nms_static(boxes, scores, levels, valid, rpn.nms_thresh, rpn.post_nms_top_n(),
+                                    group_sizes=per_level if PER_LEVEL_NMS else None)
     return _StaticProposals(out, n)
 
 
@@ -1053,6 +1069,7 @@ class DeferredCall:
 GRAPH_PROPOSAL_FILTER = _os.environ.get("HD_GRAPH_PROPOSALS", "1") == "1"
 # Training tail without device->host reads: fixed-shape proposals, device-side sampler draws (ops.sample_balanced), masked losses
 STATIC_TAIL = _os.environ.get("HD_STATIC_TAIL", "1") == "1"
+PER_LEVEL_NMS = _os.environ.get("HD_PER_LEVEL_NMS", "1") == "1"     # proposal NMS as (image, level) problems (see _filter_nms_static)
 _STATIC_PROGRAMS = {}
 
 

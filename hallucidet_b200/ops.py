@@ -575,21 +575,24 @@ def nms_sorted_batch(sorted_boxes_list, iou_threshold):
     return list(nms_sorted_flat(allb, offs, iou_threshold).split(ns))
 
 
-def nms_sorted_flat(sorted_boxes, offsets, iou_threshold, counts=None):
+def nms_sorted_flat(sorted_boxes, offsets, iou_threshold, counts=None, valid=None):
     """hd_nms over problems laid back to back in ``sorted_boxes`` [total, 4]; ``offsets`` = host list of problems+1 slot
-    offsets; ``counts`` = optional int32 device tensor with the live box count of each problem (no host sync needed)."""
+    offsets; ``counts`` = optional int32 device tensor with the live box count of each problem (no host sync needed);
+    ``valid`` = optional bool / uint8 device tensor [total]: boxes with 0 take no part, wherever they sit in their problem."""
     global LAUNCHES
     ns = [offsets[i + 1] - offsets[i] for i in range(len(offsets) - 1)]
     assert sorted_boxes.is_cuda and sorted_boxes.dtype == torch.float32 and sorted_boxes.is_contiguous()
     assert all(0 <= n <= NMS_MAX_BOXES for n in ns) and offsets[-1] == sorted_boxes.shape[0]
     assert counts is None or (counts.dtype == torch.int32 and counts.is_cuda and counts.numel() == len(ns))
+    assert valid is None or (valid.dtype in (torch.bool, torch.uint8) and valid.is_cuda and valid.is_contiguous()
+                             and valid.numel() == sorted_boxes.shape[0])
     dev = sorted_boxes.device
     mask_ws = torch.empty(max(1, sum(n * ((n + 63) // 64) for n in ns)), dtype=torch.int64, device=dev)
     keep = torch.empty(offsets[-1], dtype=torch.bool, device=dev)
     c_off = (ctypes.c_int * len(offsets))(*offsets)
     with _Timed("nms"):
-        check(_lib.load().hd_nms(_ptr(sorted_boxes), c_off, _ptr(counts), len(ns), float(iou_threshold), _ptr(mask_ws), _ptr(keep),
-                                 _stream()), "hd_nms")
+        check(_lib.load().hd_nms_valid(_ptr(sorted_boxes), c_off, _ptr(counts), _ptr(valid), len(ns), float(iou_threshold), _ptr(mask_ws),
+                                       _ptr(keep), _stream()), "hd_nms")
     LAUNCHES += 1
     return keep
 

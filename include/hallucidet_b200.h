@@ -274,6 +274,10 @@ int hd_regulariser(int kind, const float* hal, const float* rgb, const float* ir
  * mask_ws: device scratch of sum_p n_p*ceil(n_p/64) 64-bit words.  keep: [total] bytes, 1 = kept. */
 int hd_nms(const float* boxes_sorted, const int* offsets, const int* counts_dev, int problems, float iou_threshold,
            void* mask_ws, unsigned char* keep, hd_stream stream);
+/* hd_nms with valid_dev: optional DEVICE bytes, one per box slot; a box with 0 is never kept and suppresses nothing, wherever it
+ * sits in its problem (the proposal filter's size / score tests of TV rpn.py:265-276 need no compaction before the NMS). */
+int hd_nms_valid(const float* boxes_sorted, const int* offsets, const int* counts_dev, const unsigned char* valid_dev, int problems,
+                 float iou_threshold, void* mask_ws, unsigned char* keep, hd_stream stream);
 
 /* ---- Balanced positive / negative sampler (RPN loss, RoI heads) without a host round trip ----------------------
  * torchvision det_utils.BalancedPositiveNegativeSampler as the reference's detector uses it (TV models/detection/rpn.py
