@@ -39,6 +39,16 @@ class HdUnpackDesc(ctypes.Structure):
                 ("row_stride", ctypes.c_int32), ("first_block", ctypes.c_int32), ("scale", ctypes.c_float), ("pad_", ctypes.c_int32)]
 
 
+class HdRoiGatherArgs(ctypes.Structure):
+    _fields_ = [("flat", c_void_p), ("counts", c_void_p), ("props", c_void_p), ("gt", c_void_p), ("labels", c_void_p),
+                ("matched", c_void_p), ("batch", ctypes.c_int32), ("slots", ctypes.c_int32), ("n_gt", ctypes.c_int32),
+                ("rows", ctypes.c_int32), ("weights", ctypes.c_float * 4), ("canonical_scale", ctypes.c_float),
+                ("canonical_level", ctypes.c_float), ("eps", ctypes.c_float), ("k_min", ctypes.c_float), ("k_max", ctypes.c_float),
+                ("out_props", c_void_p), ("out_labels", c_void_p), ("out_matched", c_void_p), ("out_image", c_void_p),
+                ("out_targets", c_void_p), ("out_rois", c_void_p), ("out_levels", c_void_p), ("out_n_drawn", c_void_p),
+                ("out_per_image", c_void_p)]
+
+
 class HdRoiLevel(ctypes.Structure):
     _fields_ = [("feat_nhwc", c_void_p), ("grad_nhwc", c_void_p), ("h", ctypes.c_int32), ("w", ctypes.c_int32),
                 ("scale", ctypes.c_float), ("pad_", ctypes.c_int32)]
@@ -127,6 +137,9 @@ PROTOTYPES = {
     "hd_nhwc_to_nchw_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "hd_nms": [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p],
     "hd_nms_valid": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p],
+    "hd_roi_match_labels": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p,
+                            c_void_p],
+    "hd_roi_gather_samples": [P(HdRoiGatherArgs), c_void_p],
     "hd_sample_balanced_workspace_bytes": [c_int],
     "hd_sample_balanced": [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_uint64, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_void_p, ctypes.c_int64, c_void_p],

@@ -1,0 +1,188 @@
+// roi_targets.cu -- target assignment and sample gathering of the RoI heads as two launches.
+//
+// The reference's detector is torchvision's Faster R-CNN; in training its RoI heads run, per image,
+//   add_gt_proposals -> box_iou -> Matcher -> labels -> BalancedPositiveNegativeSampler -> gathers -> BoxCoder.encode
+// (TV models/detection/roi_heads.py select_training_samples; reached from src/utils/eval_forward_fasterrcnn.py:112-128) and
+// MultiScaleRoIAlign then converts the sampled boxes to RoI format and maps them to pyramid levels (TV ops/poolers.py).
+// hallucidet_b200/detection.py restates that for the whole batch with ~80 element-wise PyTorch launches on small tensors: a
+// few microseconds each, back to back on the critical path between the proposal filter and RoIAlign.  The two kernels here
+// perform the same fp32 operations in the same order (no fused multiply-adds, IEEE division / sqrt / log), element for
+// element, so their results are bit-identical to the PyTorch operator chain:
+//   hd_roi_match_labels    box_iou(gt, [proposals | gt]) -> Matcher (no low-quality matches) -> class label per candidate
+//   hd_roi_gather_samples  the drawn candidates (ascending flat positions) -> proposals, labels, matched gt, regression
+//                          targets (encode_boxes), RoIs (image index, box) and FPN level (LevelMapper)
+#include <math.h>
+
+#include "hd_common.cuh"
+
+namespace hd {
+
+namespace {
+
+constexpr int kMaxGt = 64;
+
+__device__ __forceinline__ float box_area_rn(float x1, float y1, float x2, float y2) {
+    return __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
+}
+
+// candidates of image b: columns [0, T) = proposals (live below n_props[b]), [T, T + G) = the image's ground-truth boxes
+__global__ void __launch_bounds__(256) roi_match_labels_kernel(const float4* __restrict__ props, const long long* __restrict__ n_props,
+                                                             const float4* __restrict__ gt, const unsigned char* __restrict__ gt_present,
+                                                             const long long* __restrict__ gt_labels, int B, int T, int G,
+                                                             float low_thr, float high_thr, long long* __restrict__ labels,
+                                                             long long* __restrict__ matched) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float4 s_gt[kMaxGt];
+    __shared__ float s_area[kMaxGt];
+    __shared__ unsigned char s_pres[kMaxGt];
+    __shared__ long long s_lab[kMaxGt];
+    const int b = blockIdx.y, N = T + G;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        const float4 q = gt[b * G + g];
+        s_gt[g] = q;
+        s_area[g] = box_area_rn(q.x, q.y, q.z, q.w);
+        s_pres[g] = gt_present[b * G + g];
+        s_lab[g] = gt_labels[b * G + g];
+    }
+    __syncthreads();
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= N) return;
+    const float4 p = col < T ? props[static_cast<long>(b) * T + col] : s_gt[col - T];
+    const bool present = col < T ? static_cast<long long>(col) < n_props[b] : s_pres[col - T] != 0;
+    const float area2 = box_area_rn(p.x, p.y, p.z, p.w);
+    float best = 0.f;
+    int best_g = 0;
+    for (int g = 0; g < G; ++g) {
+        float v = -1.f;                                          // padded ground-truth rows never win
+        if (s_pres[g]) {
+            const float4 q = s_gt[g];
+            const float w = fmaxf(__fsub_rn(fminf(q.z, p.z), fmaxf(q.x, p.x)), 0.f);
+            const float h = fmaxf(__fsub_rn(fminf(q.w, p.w), fmaxf(q.y, p.y)), 0.f);
+            const float inter = __fmul_rn(w, h);
+            v = __fdiv_rn(inter, __fsub_rn(__fadd_rn(s_area[g], area2), inter));
+        }
+        if (g == 0 || v > best) { best = v; best_g = g; }        // torch.max: the first maximal value
+    }
+    long long m = best_g;
+    if (best < low_thr) m = -1;                                  // Matcher.BELOW_LOW_THRESHOLD
+    else if (best < high_thr) m = -2;                            // Matcher.BETWEEN_THRESHOLDS
+    const long long clamped = m < 0 ? 0 : m;
+    long long lab = s_lab[clamped];
+    if (m == -1) lab = 0;
+    if (m == -2) lab = -1;
+    if (!present) lab = -1;                                      // padding: ignored by the sampler
+    const long idx = static_cast<long>(b) * N + col;
+    labels[idx] = lab;
+    matched[idx] = clamped;
+}
+
+struct GatherParams {
+    const long long* flat;          // [S] ascending flat positions (image * N + column) of the drawn candidates, padded
+    const int* counts;              // [B][4] sampler counts (.., .., drawn positives, drawn negatives)
+    const float4* props;            // [B][T]
+    const float4* gt;               // [B][G]
+    const long long* labels;        // [B][N]
+    const long long* matched;       // [B][N]
+    int B, T, G, S;
+    float wx, wy, ww, wh;           // BoxCoder weights
+    float inv_s0, lvl0, eps, k_min, k_max;
+    float4* out_props;              // [S]
+    long long* out_labels;          // [S]   (-100 for padding rows)
+    long long* out_matched;         // [S]
+    long long* out_image;           // [S]
+    float4* out_targets;            // [S]
+    float* out_rois;                // [S][5]
+    long long* out_levels;          // [S]
+    long long* out_n_drawn;         // [1]
+    long long* out_per_image;       // [B]
+};
+
+__global__ void __launch_bounds__(256) roi_gather_samples_kernel(const GatherParams P) {
+    pdl_trigger();
+    pdl_wait();
+    const int N = P.T + P.G;
+    long long n_drawn = 0;
+    for (int b = 0; b < P.B; ++b) n_drawn += P.counts[b * 4 + 2] + P.counts[b * 4 + 3];
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == 0) *P.out_n_drawn = n_drawn;
+    if (s < P.B) P.out_per_image[s] = P.counts[s * 4 + 2] + P.counts[s * 4 + 3];
+    if (s >= P.S) return;
+    const long long f = P.flat[s];
+    const int img = static_cast<int>(f / N), col = static_cast<int>(f - static_cast<long long>(img) * N);
+    const float4 p = col < P.T ? P.props[static_cast<long>(img) * P.T + col] : P.gt[img * P.G + (col - P.T)];
+    const long long m = P.matched[f];
+    const float4 r = P.gt[img * P.G + static_cast<int>(m)];
+    P.out_props[s] = p;
+    P.out_labels[s] = s < n_drawn ? P.labels[f] : -100;
+    P.out_matched[s] = m;
+    P.out_image[s] = img;
+    // encode_boxes (TV models/detection/_utils.py:75-119)
+    const float ex_w = __fsub_rn(p.z, p.x), ex_h = __fsub_rn(p.w, p.y);
+    const float ex_cx = __fadd_rn(p.x, __fmul_rn(0.5f, ex_w)), ex_cy = __fadd_rn(p.y, __fmul_rn(0.5f, ex_h));
+    const float gt_w = __fsub_rn(r.z, r.x), gt_h = __fsub_rn(r.w, r.y);
+    const float gt_cx = __fadd_rn(r.x, __fmul_rn(0.5f, gt_w)), gt_cy = __fadd_rn(r.y, __fmul_rn(0.5f, gt_h));
+    float4 t;
+    t.x = __fdiv_rn(__fmul_rn(P.wx, __fsub_rn(gt_cx, ex_cx)), ex_w);
+    t.y = __fdiv_rn(__fmul_rn(P.wy, __fsub_rn(gt_cy, ex_cy)), ex_h);
+    t.z = __fmul_rn(P.ww, logf(__fdiv_rn(gt_w, ex_w)));
+    t.w = __fmul_rn(P.wh, logf(__fdiv_rn(gt_h, ex_h)));
+    P.out_targets[s] = t;
+    // _convert_to_roi_format + LevelMapper (TV ops/poolers.py:47-84)
+    float* roi = P.out_rois + static_cast<long>(s) * 5;
+    roi[0] = static_cast<float>(img); roi[1] = p.x; roi[2] = p.y; roi[3] = p.z; roi[4] = p.w;
+    const float sz = sqrtf(box_area_rn(p.x, p.y, p.z, p.w));
+    float lvl = floorf(__fadd_rn(__fadd_rn(P.lvl0, log2f(__fmul_rn(sz, P.inv_s0))), P.eps));
+    lvl = fminf(fmaxf(lvl, P.k_min), P.k_max);
+    P.out_levels[s] = static_cast<long long>(lvl) - static_cast<long long>(P.k_min);
+}
+
+}  // namespace
+
+}  // namespace hd
+
+using namespace hd;
+
+// See include/hallucidet_b200.h.
+extern "C" int hd_roi_match_labels(const float* props, const int64_t* n_props, const float* gt, const uint8_t* gt_present,
+                                   const int64_t* gt_labels, int batch, int slots, int n_gt, float low_threshold, float high_threshold,
+                                   int64_t* labels, int64_t* matched, hd_stream stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    HD_CHECK_ARG(props != nullptr && n_props != nullptr && gt != nullptr && gt_present != nullptr && gt_labels != nullptr);
+    HD_CHECK_ARG(labels != nullptr && matched != nullptr && batch > 0 && slots >= 0 && n_gt >= 1 && n_gt <= kMaxGt);
+    HD_CHECK_ARG((reinterpret_cast<uintptr_t>(props) & 15) == 0 && (reinterpret_cast<uintptr_t>(gt) & 15) == 0);
+    const int n = slots + n_gt;
+    HD_CUDA_OK(hd::launch(roi_match_labels_kernel, dim3((n + 255) / 256, batch), dim3(256), 0, stream, reinterpret_cast<const float4*>(props),
+                          reinterpret_cast<const long long*>(n_props), reinterpret_cast<const float4*>(gt), gt_present,
+                          reinterpret_cast<const long long*>(gt_labels), batch, slots, n_gt, low_threshold, high_threshold,
+                          reinterpret_cast<long long*>(labels), reinterpret_cast<long long*>(matched)));
+    HD_CUDA_OK(cudaPeekAtLastError());
+    return HD_OK;
+}
+
+extern "C" int hd_roi_gather_samples(const hd_roi_gather_args* a, hd_stream stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    HD_CHECK_ARG(a != nullptr && a->flat != nullptr && a->counts != nullptr && a->props != nullptr && a->gt != nullptr);
+    HD_CHECK_ARG(a->labels != nullptr && a->matched != nullptr && a->batch > 0 && a->slots >= 0 && a->n_gt >= 1 && a->rows > 0);
+    HD_CHECK_ARG(a->out_props != nullptr && a->out_labels != nullptr && a->out_matched != nullptr && a->out_image != nullptr);
+    HD_CHECK_ARG(a->out_targets != nullptr && a->out_rois != nullptr && a->out_levels != nullptr && a->out_n_drawn != nullptr);
+    HD_CHECK_ARG(a->out_per_image != nullptr && a->rows >= a->batch);
+    HD_CHECK_ARG((reinterpret_cast<uintptr_t>(a->props) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->gt) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(a->out_props) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->out_targets) & 15) == 0);
+    GatherParams P;
+    P.flat = reinterpret_cast<const long long*>(a->flat); P.counts = a->counts;
+    P.props = reinterpret_cast<const float4*>(a->props); P.gt = reinterpret_cast<const float4*>(a->gt);
+    P.labels = reinterpret_cast<const long long*>(a->labels); P.matched = reinterpret_cast<const long long*>(a->matched);
+    P.B = a->batch; P.T = a->slots; P.G = a->n_gt; P.S = a->rows;
+    P.wx = a->weights[0]; P.wy = a->weights[1]; P.ww = a->weights[2]; P.wh = a->weights[3];
+    P.inv_s0 = 1.0f / a->canonical_scale;                 // ATen divides by a host scalar as a multiplication by its reciprocal
+    P.lvl0 = a->canonical_level; P.eps = a->eps; P.k_min = a->k_min; P.k_max = a->k_max;
+    P.out_props = reinterpret_cast<float4*>(a->out_props); P.out_labels = reinterpret_cast<long long*>(a->out_labels);
+    P.out_matched = reinterpret_cast<long long*>(a->out_matched); P.out_image = reinterpret_cast<long long*>(a->out_image);
+    P.out_targets = reinterpret_cast<float4*>(a->out_targets); P.out_rois = a->out_rois;
+    P.out_levels = reinterpret_cast<long long*>(a->out_levels); P.out_n_drawn = reinterpret_cast<long long*>(a->out_n_drawn);
+    P.out_per_image = reinterpret_cast<long long*>(a->out_per_image);
+    HD_CUDA_OK(hd::launch(roi_gather_samples_kernel, dim3((a->rows + 255) / 256), dim3(256), 0, stream, P));
+    HD_CUDA_OK(cudaPeekAtLastError());
+    return HD_OK;
+}

@@ -383,7 +383,7 @@ def _filter_nms_static(boxes, scores, idxs, valid, nms_thresh, top_n, group_size
     dest = torch.where(sel, csum - 1, csum.new_full((), top_n))              # unselected boxes go to a dump column
     out = boxes.new_zeros(B, top_n + 1, 4)
     out.scatter_(1, dest[..., None].expand(-1, -1, 4), torch.gather(boxes, 1, gidx))
-    return out[:, :top_n], sel.sum(1)
+    return out[:, :top_n].contiguous(), sel.sum(1)
 
 
 def filter_proposals_static(rpn, proposals, objectness, image_shapes, num_anchors_per_level):
@@ -671,12 +671,16 @@ class _StaticSamples:
     def __init__(self, proposals, image_of, labels, regression_targets, matched_idxs, valid, n_drawn, per_image):
         self.proposals, self.image_of, self.labels, self.regression_targets = proposals, image_of, labels, regression_targets
         self.matched_idxs, self.valid, self.n_drawn, self.per_image = matched_idxs, valid, n_drawn, per_image
+        self.rois = self.levels = None            # RoI format + pyramid level of every row (fused path)
 
 
-def select_training_samples_static(roi_heads, proposals, targets):
+def select_training_samples_static(roi_heads, proposals, targets, level_mapper=None):
     """``RoIHeads.select_training_samples`` for a ``_StaticProposals`` batch, without any host read: ground truth appended
     behind the (padded) proposals of each image, padding rows ignored by the sampler, the draw made on the device
-    (ops.sample_balanced: the same selection as torchvision's loop on the same generator state)."""
+    (ops.sample_balanced: the same selection as torchvision's loop on the same generator state).
+
+    With FUSED_ROI_TARGETS the element-wise chains before and after the draw are the two launches of csrc/roi_targets.cu
+    (bit-identical results); ``level_mapper`` (the pooler's LevelMapper) then also yields the RoIs and their pyramid levels."""
     roi_heads.check_targets(targets)
     P0, n_props = proposals.boxes, proposals.counts
     dtype, device = P0.dtype, P0.device
@@ -684,15 +688,30 @@ def select_training_samples_static(roi_heads, proposals, targets):
     gt, present, gl = _padded_gt(targets, dtype)
     G = gt.shape[1]
     N = T + G
+    matcher, sampler = roi_heads.proposal_matcher, roi_heads.fg_bg_sampler
+    fused = (FUSED_ROI_TARGETS and dtype == torch.float32 and G <= 64 and not matcher.allow_low_quality_matches
+             and gl.dtype == torch.int64 and P0.is_contiguous())
+    if fused:
+        labels, clamped = ops.roi_match_labels(P0, n_props.to(torch.int64), gt.contiguous(), present.contiguous(), gl.contiguous(),
+                                               matcher.low_threshold, matcher.high_threshold)
+        sampled, counts = ops.sample_balanced(labels, sampler.batch_size_per_image, sampler.positive_fraction)
+        flat = torch.nonzero_static(sampled.view(-1), size=B * sampler.batch_size_per_image, fill_value=0)[:, 0]
+        lm = level_mapper if level_mapper is not None else _NO_LEVELS
+        o = ops.roi_gather_samples(flat, counts, P0, gt.contiguous(), labels, clamped, roi_heads.box_coder.weights, lm)
+        valid = torch.arange(flat.numel(), device=device) < o["n_drawn"]
+        smp = _StaticSamples(o["proposals"], o["image_of"], o["labels"], o["regression_targets"], o["matched"], valid, o["n_drawn"],
+                             o["per_image"])
+        if level_mapper is not None:
+            smp.rois, smp.levels = o["rois"], o["levels"]
+        return smp
     P = torch.cat([P0, gt], dim=1)                                                       # add_gt_proposals
     p_present = torch.cat([torch.arange(T, device=device)[None, :] < n_props[:, None], present], dim=1)
-    matches = _match_batched(roi_heads.proposal_matcher, gt, present, P)
+    matches = _match_batched(matcher, gt, present, P)
     clamped = matches.clamp(min=0)
     labels = torch.gather(gl, 1, clamped).to(torch.int64)
-    labels = torch.where(matches == roi_heads.proposal_matcher.BELOW_LOW_THRESHOLD, labels.new_zeros(()), labels)
-    labels = torch.where(matches == roi_heads.proposal_matcher.BETWEEN_THRESHOLDS, labels.new_full((), -1), labels)
+    labels = torch.where(matches == matcher.BELOW_LOW_THRESHOLD, labels.new_zeros(()), labels)
+    labels = torch.where(matches == matcher.BETWEEN_THRESHOLDS, labels.new_full((), -1), labels)
     labels = torch.where(p_present, labels, labels.new_full((), -1))
-    sampler = roi_heads.fg_bg_sampler
     sampled, counts = ops.sample_balanced(labels.contiguous(), sampler.batch_size_per_image, sampler.positive_fraction)
     flat, valid, n_drawn = _sampled_rows(sampled, counts, sampler.batch_size_per_image)
     out_props = P.reshape(-1, 4)[flat]
@@ -702,6 +721,13 @@ def select_training_samples_static(roi_heads, proposals, targets):
     matched_gt = gt.reshape(-1, 4)[img_of * G + out_matched]
     regression_targets = _encode_single(roi_heads.box_coder, matched_gt, out_props)
     return _StaticSamples(out_props, img_of, out_labels, regression_targets, out_matched, valid, n_drawn, counts[:, 2] + counts[:, 3])
+
+
+class _NoLevels:
+    s0, lvl0, eps, k_min, k_max = 224, 4, 1e-6, 0, 0
+
+
+_NO_LEVELS = _NoLevels()
 
 
 def fastrcnn_loss_masked(class_logits, box_regression, samples):
@@ -865,7 +891,15 @@ def multiscale_roi_align_one_sync(pooler, features, boxes, image_shapes):
     return result
 
 
-def multiscale_roi_align_static(pooler, features, boxes, image_of, image_shapes):
+def _pooler_setup(pooler, features, image_shapes):
+    from torchvision.ops import poolers
+    x_filtered = poolers._filter_input(features, pooler.featmap_names)
+    if pooler.scales is None or pooler.map_levels is None:
+        pooler.scales, pooler.map_levels = poolers._setup_scales(x_filtered, image_shapes, pooler.canonical_scale, pooler.canonical_level)
+    return x_filtered
+
+
+def multiscale_roi_align_static(pooler, features, boxes, image_of, image_shapes, rois=None, levels=None):
     """``MultiScaleRoIAlign.forward`` for boxes [S, 4] whose image index is a device tensor (``_StaticSamples``): the RoI format
     and the level mapper are the element-wise operations of TV ops/poolers.py on the concatenated boxes; all levels are pooled
     by one launch each way (``_MultiLevelRoIAlign``).  Requires ``_ml_roi_align_ok``."""
@@ -873,6 +907,9 @@ def multiscale_roi_align_static(pooler, features, boxes, image_of, image_shapes)
     x_filtered = poolers._filter_input(features, pooler.featmap_names)
     if pooler.scales is None or pooler.map_levels is None:
         pooler.scales, pooler.map_levels = poolers._setup_scales(x_filtered, image_shapes, pooler.canonical_scale, pooler.canonical_level)
+    if rois is not None and levels is not None:
+        return _MultiLevelRoIAlign.apply(rois, levels, tuple(float(sc) for sc in pooler.scales), tuple(pooler.output_size),
+                                         int(pooler.sampling_ratio), *x_filtered)
     rois = torch.cat([image_of.to(boxes.dtype)[:, None], boxes], dim=1)
     if len(x_filtered) == 1:
         levels = torch.zeros(boxes.shape[0], dtype=torch.int64, device=boxes.device)
@@ -1069,6 +1106,7 @@ class DeferredCall:
 GRAPH_PROPOSAL_FILTER = _os.environ.get("HD_GRAPH_PROPOSALS", "1") == "1"
 # Training tail without device->host reads: fixed-shape proposals, device-side sampler draws (ops.sample_balanced), masked losses
 STATIC_TAIL = _os.environ.get("HD_STATIC_TAIL", "1") == "1"
+FUSED_ROI_TARGETS = _os.environ.get("HD_FUSED_ROI_TARGETS", "1") == "1"   # csrc/roi_targets.cu instead of ~80 element-wise launches
 PER_LEVEL_NMS = _os.environ.get("HD_PER_LEVEL_NMS", "1") == "1"     # proposal NMS as (image, level) problems (see _filter_nms_static)
 _STATIC_PROGRAMS = {}
 
@@ -1315,9 +1353,12 @@ def _roi_heads_eval_static(model, features, proposals, image_shapes, targets):
     """``roi_heads_eval`` for ``_StaticProposals``: no device->host read between the backbone and the losses.  The detections
     (a by-product in the train step) are post-processed on a side stream and assembled when the caller resolves them."""
     rh = model.roi_heads
+    x_filtered = _pooler_setup(rh.box_roi_pool, features, image_shapes)
     with torch.no_grad():
-        samples = select_training_samples_static(rh, proposals, targets)
-    box_features = multiscale_roi_align_static(rh.box_roi_pool, features, samples.proposals, samples.image_of, image_shapes)
+        samples = select_training_samples_static(rh, proposals, targets,
+                                                 level_mapper=rh.box_roi_pool.map_levels if len(x_filtered) > 1 else None)
+    box_features = multiscale_roi_align_static(rh.box_roi_pool, features, samples.proposals, samples.image_of, image_shapes,
+                                               rois=samples.rois, levels=samples.levels)
     box_features = rh.box_head(box_features)
     class_logits, box_regression = rh.box_predictor(box_features)
     loss_classifier, loss_box_reg = fastrcnn_loss_masked(class_logits, box_regression, samples)

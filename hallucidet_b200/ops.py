@@ -10,7 +10,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import HdAct, HdBnFin, HdConvArgs, check
+from ._lib import HdRoiGatherArgs, HdAct, HdBnFin, HdConvArgs, check
 
 STATS_REPLICAS = 16      # legacy name: default row count for small test problems (see conv_fwd_tiles)
 STEM_KPAD = 160          # 7*7*3 = 147 -> 5 k-blocks of 32
@@ -638,13 +638,30 @@ class DeviceRng:
             self.pending = False
         return self.seed
 
+    _PENDING_MARK = 1 << 40
+
+    def mark_pending(self):
+        """After a device-side draw torch's generator is behind the device.  Its offset is moved to an out-of-the-way marker
+        until ``sync_host()``: re-seeding the generator -- even to exactly the state this object adopted last -- is then always
+        visible to ``begin()`` as a changed state."""
+        if not self.pending:
+            g = self.generator()
+            marked = int(g.get_offset()) + self._PENDING_MARK
+            g.set_offset(marked)
+            self.host_seen = (int(g.initial_seed()), marked)
+            self.pending = True
+
     def sync_host(self):
         """Mirror the device-side offset into torch's generator (one 8-byte device->host read; blocks until the stream that
         ran the last draw reaches it)."""
         if not self.pending:
             return
-        off = int(self.buf[self.cur].item())
         g = self.generator()
+        if (int(g.initial_seed()), int(g.get_offset())) != self.host_seen:      # re-seeded meanwhile: the device chain is obsolete
+            self.pending = False
+            self.host_seen = None
+            return
+        off = int(self.buf[self.cur].item())
         g.set_offset(off)
         self.host_seen = (int(g.initial_seed()), off)
         self.pending = False
@@ -678,9 +695,62 @@ def sample_balanced(labels, batch_size_per_image, positive_fraction):
                                              int(batch_size_per_image * positive_fraction), seed, _ptr(src), _ptr(dst), _ptr(sampled),
                                              _ptr(counts), _ptr(ws), ws.numel(), _stream()), "hd_sample_balanced")
     rng.cur = 1 - rng.cur
-    rng.pending = True
+    rng.mark_pending()
     LAUNCHES += 3
     return sampled, counts
+
+
+def roi_match_labels(props, n_props, gt, gt_present, gt_labels, low_threshold, high_threshold):
+    """hd_roi_match_labels: candidates [proposals (padded, live below n_props) | ground truth] of every image -> (labels [B, T + G]
+    int64: class / 0 background / -1 ignored or padding, matched [B, T + G] int64).  box_iou + Matcher (no low-quality matches)
+    + the label rules of RoIHeads.assign_targets_to_proposals, bit-identical to the PyTorch operator chain."""
+    global LAUNCHES
+    B, T = props.shape[:2]
+    G = gt.shape[1]
+    assert props.dtype == gt.dtype == torch.float32 and props.is_contiguous() and gt.is_contiguous() and props.is_cuda
+    assert n_props.dtype == torch.int64 and gt_labels.dtype == torch.int64 and gt_present.dtype == torch.bool
+    assert gt_present.is_contiguous() and gt_labels.is_contiguous() and 1 <= G <= 64
+    labels = torch.empty(B, T + G, dtype=torch.int64, device=props.device)
+    matched = torch.empty(B, T + G, dtype=torch.int64, device=props.device)
+    with _Timed("roi_match_labels"):
+        check(_lib.load().hd_roi_match_labels(_ptr(props), _ptr(n_props), _ptr(gt), _ptr(gt_present), _ptr(gt_labels), B, T, G,
+                                              float(low_threshold), float(high_threshold), _ptr(labels), _ptr(matched), _stream()),
+              "hd_roi_match_labels")
+    LAUNCHES += 1
+    return labels, matched
+
+
+def roi_gather_samples(flat, counts, props, gt, labels, matched, coder_weights, level_mapper):
+    """hd_roi_gather_samples: the drawn candidates -> dict(proposals [S, 4], labels [S], matched [S], image_of [S], regression_targets
+    [S, 4], rois [S, 5], levels [S], n_drawn (0-dim int64), per_image [B] int64) -- see include/hallucidet_b200.h."""
+    global LAUNCHES
+    B, T = props.shape[:2]
+    G = gt.shape[1]
+    S = flat.numel()
+    dev = props.device
+    a = HdRoiGatherArgs()
+    out = {"proposals": torch.empty(S, 4, device=dev), "labels": torch.empty(S, dtype=torch.int64, device=dev),
+           "matched": torch.empty(S, dtype=torch.int64, device=dev), "image_of": torch.empty(S, dtype=torch.int64, device=dev),
+           "regression_targets": torch.empty(S, 4, device=dev), "rois": torch.empty(S, 5, device=dev),
+           "levels": torch.empty(S, dtype=torch.int64, device=dev), "n_drawn": torch.empty((), dtype=torch.int64, device=dev),
+           "per_image": torch.empty(B, dtype=torch.int64, device=dev)}
+    assert flat.dtype == torch.int64 and counts.dtype == torch.int32 and flat.is_contiguous() and counts.is_contiguous()
+    a.flat, a.counts, a.props, a.gt, a.labels, a.matched = (flat.data_ptr(), counts.data_ptr(), props.data_ptr(), gt.data_ptr(),
+                                                            labels.data_ptr(), matched.data_ptr())
+    a.batch, a.slots, a.n_gt, a.rows = B, T, G, S
+    for i, w in enumerate(coder_weights):
+        a.weights[i] = float(w)
+    lm = level_mapper
+    a.canonical_scale, a.canonical_level, a.eps = float(lm.s0), float(lm.lvl0), float(lm.eps)
+    a.k_min, a.k_max = float(lm.k_min), float(lm.k_max)
+    a.out_props, a.out_labels, a.out_matched, a.out_image = (out["proposals"].data_ptr(), out["labels"].data_ptr(),
+                                                             out["matched"].data_ptr(), out["image_of"].data_ptr())
+    a.out_targets, a.out_rois, a.out_levels = out["regression_targets"].data_ptr(), out["rois"].data_ptr(), out["levels"].data_ptr()
+    a.out_n_drawn, a.out_per_image = out["n_drawn"].data_ptr(), out["per_image"].data_ptr()
+    with _Timed("roi_gather_samples"):
+        check(_lib.load().hd_roi_gather_samples(ctypes.byref(a), _stream()), "hd_roi_gather_samples")
+    LAUNCHES += 1
+    return out
 
 
 def roi_align_bwd(grad_out, rois, input_shape, spatial_scale, sampling_ratio):

@@ -294,6 +294,44 @@ int hd_sample_balanced(const void* labels, int labels_dtype, int batch, int n, i
                        uint64_t seed, const uint64_t* offset_in, uint64_t* offset_out, uint8_t* sampled, int32_t* counts,
                        void* workspace, int64_t workspace_bytes, hd_stream stream);
 
+/* ---- RoI-head target assignment and sample gathering (two launches instead of ~80 element-wise ones) --------------
+ * torchvision RoIHeads.select_training_samples (TV models/detection/roi_heads.py: add_gt_proposals, box_iou + Matcher,
+ * labels, the gathers after the sampler, BoxCoder.encode) followed by MultiScaleRoIAlign's RoI format + LevelMapper
+ * (TV ops/poolers.py:47-101), as the reference reaches them from src/utils/eval_forward_fasterrcnn.py:112-131 -- the same
+ * fp32 operations in the same order, so the results are bit-identical to the operator chain.
+ * hd_roi_match_labels: candidates of image b = props[b][0 .. slots) (live below n_props[b], a DEVICE count) followed by the
+ * image's n_gt (<= 64, padded; gt_present marks real rows) ground-truth boxes; labels[b][c] = class of the matched box,
+ * 0 = background (IoU below low_threshold), -1 = ignored (between the thresholds, or padding); matched[b][c] = matched
+ * ground-truth row (clamped at 0).  Matcher without low-quality matches (RoI heads).
+ * hd_roi_gather_samples: rows = batch * batch_size_per_image drawn candidates (flat = ascending positions b * (slots + n_gt)
+ * + c, padded; counts = hd_sample_balanced's) -> their boxes, labels (-100 on padding rows), matched rows, image index,
+ * regression targets (encode_boxes with `weights`), RoIs [rows][5] and pyramid level; out_n_drawn / out_per_image: the drawn
+ * totals (device int64). */
+typedef struct hd_roi_gather_args {
+    const int64_t* flat;
+    const int32_t* counts;
+    const float* props;
+    const float* gt;
+    const int64_t* labels;
+    const int64_t* matched;
+    int batch, slots, n_gt, rows;
+    float weights[4];
+    float canonical_scale, canonical_level, eps, k_min, k_max;
+    float* out_props;
+    int64_t* out_labels;
+    int64_t* out_matched;
+    int64_t* out_image;
+    float* out_targets;
+    float* out_rois;
+    int64_t* out_levels;
+    int64_t* out_n_drawn;
+    int64_t* out_per_image;
+} hd_roi_gather_args;
+int hd_roi_match_labels(const float* props, const int64_t* n_props, const float* gt, const uint8_t* gt_present,
+                        const int64_t* gt_labels, int batch, int slots, int n_gt, float low_threshold, float high_threshold,
+                        int64_t* labels, int64_t* matched, hd_stream stream);
+int hd_roi_gather_samples(const hd_roi_gather_args* args, hd_stream stream);
+
 /* ---- RoIAlign backward (box head pooling over the FPN levels) ------------------------------------------------
  * grad_in_nhwc ([n][h][w][c] fp32 channels-last scratch, zeroed by the caller) += gradient of
  * torchvision.ops.roi_align(input, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio, aligned = False) -- the op

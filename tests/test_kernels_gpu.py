@@ -574,6 +574,27 @@ def test_nms_batched_problems_and_coordinate_trick():
     assert torch.equal(D.batched_nms(b, s, idxs, 0.7), torchvision.ops.batched_nms(b, s, idxs, 0.7))
 
 
+def test_nms_valid_mask_and_many_problems():
+    """hd_nms_valid: boxes masked out in place (valid = 0) against torchvision.ops.nms on the compacted list, for 40 problems in
+    one call (the proposal filter's (image, level) layout) -- a masked box is never kept and suppresses nothing."""
+    import torchvision
+    o = ops()
+    sizes = [1000, 1000, 1000, 1000, 300] * 8
+    g = torch.Generator().manual_seed(3)
+    boxes_all, valid_all, refs, offs = [], [], [], [0]
+    for i, n in enumerate(sizes):
+        b, s = _nms_boxes(n, seed=500 + i)
+        order = torch.sort(s, dim=0, descending=True, stable=True)[1]
+        b, s = b[order], s[order]
+        v = (torch.rand(n, generator=g) < (0.8 if i % 3 else 0.2)).cuda()
+        live = torch.nonzero(v)[:, 0]
+        ref = torch.zeros(n, dtype=torch.bool, device="cuda")
+        ref[live[torchvision.ops.nms(b[live], s[live], 0.7)]] = True
+        boxes_all.append(b); valid_all.append(v); refs.append(ref); offs.append(offs[-1] + n)
+    keep = o.nms_sorted_flat(torch.cat(boxes_all).contiguous(), offs, 0.7, valid=torch.cat(valid_all).contiguous())
+    assert torch.equal(keep, torch.cat(refs))
+
+
 def test_multi_layer_pack_and_unpack_match_single_layer_calls():
     """hd_pack_conv_weights / hd_unpack_wgrads (one launch for every layer) against the per-layer entry points."""
     o = ops()

@@ -215,3 +215,55 @@ def test_static_tail_matches_host_synchronised_tail():
         assert torch.equal(a["boxes"], b["boxes"]) and torch.equal(a["labels"], b["labels"]) and torch.equal(a["scores"], b["scores"])
     rel = float((g0 - g1).norm() / g0.norm())
     assert rel < 2e-2, rel        # bf16 backbone backward: run-to-run gradient noise floor is ~1e-2
+
+
+@pytest.mark.parametrize("sizes", [(50, 37, 64), (2000, 1800, 1500)])
+def test_fused_roi_targets_match_operator_chain(sizes):
+    """csrc/roi_targets.cu (hd_roi_match_labels, hd_roi_gather_samples) against the PyTorch operator chain it replaces, bit for
+    bit: labels / matched rows of every candidate, then proposals, labels, regression targets, image index, RoIs and pyramid
+    levels (torchvision LevelMapper) of the drawn rows."""
+    from torchvision.ops import poolers
+    from hallucidet_b200 import detection as D, ops
+    det, g, anchors, targets = _detector_setup()
+    rh = det.roi_heads
+    T = 2000
+    padded = torch.zeros(len(sizes), T, 4, device="cuda")
+    for b, n in enumerate(sizes):
+        xy = torch.rand(n, 2, generator=g) * 100
+        wh = torch.rand(n, 2, generator=g) ** 3 * 400 + 1                       # sizes from a pixel to several hundred: all pyramid levels
+        padded[b, :n] = torch.cat([xy, xy + wh], 1).cuda()
+    sp = D._StaticProposals(padded, torch.tensor(sizes, device="cuda"))
+    lm = poolers.LevelMapper(2, 5)
+    out = {}
+    for fused in (False, True):
+        D.FUSED_ROI_TARGETS = fused
+        try:
+            torch.manual_seed(9)
+            out[fused] = D.select_training_samples_static(rh, sp, targets, level_mapper=lm)
+        finally:
+            D.FUSED_ROI_TARGETS = True
+    a, b = out[False], out[True]
+    assert int(a.n_drawn) == int(b.n_drawn) and torch.equal(a.per_image, b.per_image) and torch.equal(a.valid, b.valid)
+    for f in ("proposals", "image_of", "labels", "regression_targets", "matched_idxs"):
+        x, y = getattr(a, f), getattr(b, f)
+        assert x.dtype == y.dtype and torch.equal(x, y), f
+    n = int(a.n_drawn)
+    assert b.rois is not None and torch.equal(b.rois[:, 0], a.image_of.float()) and torch.equal(b.rois[:, 1:], a.proposals)
+    assert torch.equal(b.levels, lm([a.proposals]))
+    assert len(torch.unique(b.levels[:n])) >= 3
+
+
+def test_sample_balanced_sees_a_reseed_without_host_sync():
+    """Re-seeding torch's generator to the very state the device chain started from (no sync_host() in between) restarts the
+    draw: the pending marker offset makes the re-seed visible."""
+    ops = _ops()
+    lab = _labels(4, 3000, 0.02, 0.05, 31, torch.float32)
+    torch.manual_seed(5)
+    a1, _ = ops.sample_balanced(lab, 256, 0.5)
+    torch.manual_seed(5)
+    a2, _ = ops.sample_balanced(lab, 256, 0.5)
+    a3, _ = ops.sample_balanced(lab, 256, 0.5)                    # no re-seed: the chain continues
+    ops.DeviceRng.get(lab.device).sync_host()
+    torch.manual_seed(5)
+    ref1, ref2 = _reference(lab, 256, 0.5), _reference(lab, 256, 0.5)
+    assert torch.equal(a1, a2) and torch.equal(a1, ref1) and torch.equal(a3, ref2) and not torch.equal(a1, a3)
