@@ -140,6 +140,9 @@ PROTOTYPES = {
     "hd_roi_match_labels": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p,
                             c_void_p],
     "hd_roi_gather_samples": [P(HdRoiGatherArgs), c_void_p],
+    "hd_fastrcnn_loss": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p],
+    "hd_rpn_loss": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p,
+                    c_void_p, c_void_p],
     "hd_sample_balanced_workspace_bytes": [c_int],
     "hd_sample_balanced": [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_uint64, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_void_p, ctypes.c_int64, c_void_p],

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhallucidet_b200.so")
 SOURCES = ["hd_common.cu", "conv_gemm.cu", "wgrad_gemm.cu", "narrow_conv.cu", "elementwise.cu", "nms.cu", "roi_align.cu",
-           "stem_conv.cu", "sampler.cu", "roi_targets.cu"]
+           "stem_conv.cu", "sampler.cu", "roi_targets.cu", "det_losses.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 if os.environ.get("HD_BUILD_STREAMK") == "1":          # experimental stream-K paths of conv_gemm.cu (measured: no gain, see the file)

@@ -651,6 +651,11 @@ def rpn_compute_loss_static(rpn, objectness, pred_bbox_deltas, labels, regressio
     a fixed-size row list + validity weights instead of index lists whose lengths the host would have to read.  Same samples,
     same per-element losses, same divisors; only the order of the fp32 sums differs."""
     B, A = labels.shape
+    if (FUSED_DET_LOSSES and objectness.is_cuda and objectness.dtype == torch.float32 and labels.dtype == torch.float32
+            and regression_targets.dtype == torch.float32 and pred_bbox_deltas.dtype == torch.float32):
+        flat = torch.nonzero_static(sampled.view(-1), size=B * rpn.fg_bg_sampler.batch_size_per_image, fill_value=0)[:, 0]
+        return _RPNLoss.apply(objectness.reshape(-1), pred_bbox_deltas.reshape(-1, 4), labels.reshape(-1).contiguous(),
+                              regression_targets.reshape(-1, 4).contiguous(), flat, sampled, counts)
     flat, valid, n_drawn = _sampled_rows(sampled, counts, rpn.fg_bg_sampler.batch_size_per_image)
     denom = n_drawn.to(torch.float32)
     is_pos = (sampled.view(-1)[flat] == 1) & valid
@@ -730,11 +735,46 @@ class _NoLevels:
 _NO_LEVELS = _NoLevels()
 
 
+class _FastRCNNLoss(torch.autograd.Function):
+    """fastrcnn_loss with value and gradient from one launch (ops.fastrcnn_loss); backward only scales the stored gradients."""
+
+    @staticmethod
+    def forward(ctx, class_logits, box_regression, labels, regression_targets):
+        losses, g_logits, g_box = ops.fastrcnn_loss(class_logits.detach().contiguous(), box_regression.detach().contiguous(), labels,
+                                                    regression_targets)
+        ctx.save_for_backward(g_logits, g_box)
+        return losses[0], losses[1]
+
+    @staticmethod
+    def backward(ctx, g_cls, g_reg):
+        g_logits, g_box = ctx.saved_tensors
+        return g_logits * g_cls, g_box * g_reg, None, None
+
+
+class _RPNLoss(torch.autograd.Function):
+    """RegionProposalNetwork.compute_loss on the device-side draw, value and gradient from one launch (ops.rpn_loss)."""
+
+    @staticmethod
+    def forward(ctx, objectness, pred_bbox_deltas, labels, regression_targets, flat, sampled, counts):
+        losses, g_obj, g_deltas = ops.rpn_loss(objectness.detach().contiguous(), pred_bbox_deltas.detach().contiguous(), labels,
+                                               regression_targets, flat, sampled, counts)
+        ctx.save_for_backward(g_obj, g_deltas)
+        return losses[0], losses[1]
+
+    @staticmethod
+    def backward(ctx, g0, g1):
+        g_obj, g_deltas = ctx.saved_tensors
+        return g_obj * g0, g_deltas * g1, None, None, None, None, None
+
+
 def fastrcnn_loss_masked(class_logits, box_regression, samples):
     """``torchvision.models.detection.roi_heads.fastrcnn_loss`` on a ``_StaticSamples`` batch: the foreground rows enter the
     box loss through a 0 / 1 weight instead of ``torch.where(labels > 0)`` (a host read); padding rows carry the label
     cross_entropy ignores.  Same per-row losses and divisors as torchvision."""
     labels = samples.labels
+    if (FUSED_DET_LOSSES and class_logits.is_cuda and class_logits.dtype == torch.float32 and box_regression.dtype == torch.float32
+            and samples.regression_targets.dtype == torch.float32):
+        return _FastRCNNLoss.apply(class_logits, box_regression, labels.contiguous(), samples.regression_targets.contiguous())
     classification_loss = F.cross_entropy(class_logits, labels)                           # ignore_index = -100: the padding rows
     S = class_logits.shape[0]
     pos = labels > 0
@@ -1107,6 +1147,7 @@ GRAPH_PROPOSAL_FILTER = _os.environ.get("HD_GRAPH_PROPOSALS", "1") == "1"
 # Training tail without device->host reads: fixed-shape proposals, device-side sampler draws (ops.sample_balanced), masked losses
 STATIC_TAIL = _os.environ.get("HD_STATIC_TAIL", "1") == "1"
 FUSED_ROI_TARGETS = _os.environ.get("HD_FUSED_ROI_TARGETS", "1") == "1"   # csrc/roi_targets.cu instead of ~80 element-wise launches
+FUSED_DET_LOSSES = _os.environ.get("HD_FUSED_DET_LOSSES", "1") == "1"     # csrc/det_losses.cu: loss value + gradient in one launch
 PER_LEVEL_NMS = _os.environ.get("HD_PER_LEVEL_NMS", "1") == "1"     # proposal NMS as (image, level) problems (see _filter_nms_static)
 _STATIC_PROGRAMS = {}
 

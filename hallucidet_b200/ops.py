@@ -753,6 +753,41 @@ def roi_gather_samples(flat, counts, props, gt, labels, matched, coder_weights, 
     return out
 
 
+def fastrcnn_loss(class_logits, box_regression, labels, regression_targets, beta=1 / 9):
+    """hd_fastrcnn_loss: (losses [2] = classification, box regression; d/d class_logits; d/d box_regression) in one launch."""
+    global LAUNCHES
+    S, C = class_logits.shape
+    assert class_logits.dtype == box_regression.dtype == regression_targets.dtype == torch.float32 and labels.dtype == torch.int64
+    assert class_logits.is_contiguous() and box_regression.is_contiguous() and regression_targets.is_contiguous() and labels.is_contiguous()
+    assert tuple(box_regression.shape) == (S, 4 * C) and tuple(regression_targets.shape) == (S, 4) and labels.numel() == S
+    losses = torch.empty(2, device=class_logits.device)
+    g_logits, g_box = torch.empty_like(class_logits), torch.empty_like(box_regression)
+    with _Timed("fastrcnn_loss"):
+        check(_lib.load().hd_fastrcnn_loss(_ptr(class_logits), _ptr(box_regression), _ptr(labels), _ptr(regression_targets), S, C, float(beta),
+                                           _ptr(losses), _ptr(g_logits), _ptr(g_box), _stream()), "hd_fastrcnn_loss")
+    LAUNCHES += 1
+    return losses, g_logits, g_box
+
+
+def rpn_loss(objectness, pred_bbox_deltas, labels, regression_targets, flat, sampled, counts, beta=1 / 9):
+    """hd_rpn_loss: (losses [2] = objectness, box regression; dense d/d objectness; dense d/d pred_bbox_deltas) in one launch
+    (+ the two zero fills)."""
+    global LAUNCHES
+    n = objectness.numel()
+    assert objectness.dtype == pred_bbox_deltas.dtype == labels.dtype == regression_targets.dtype == torch.float32
+    assert objectness.is_contiguous() and pred_bbox_deltas.is_contiguous() and labels.is_contiguous() and regression_targets.is_contiguous()
+    assert pred_bbox_deltas.numel() == 4 * n and labels.numel() == n and regression_targets.numel() == 4 * n
+    assert flat.dtype == torch.int64 and sampled.dtype == torch.uint8 and sampled.numel() == n and counts.dtype == torch.int32
+    losses = torch.empty(2, device=objectness.device)
+    g_obj, g_deltas = torch.zeros_like(objectness), torch.zeros_like(pred_bbox_deltas)
+    with _Timed("rpn_loss"):
+        check(_lib.load().hd_rpn_loss(_ptr(objectness), _ptr(pred_bbox_deltas), _ptr(labels), _ptr(regression_targets), _ptr(flat),
+                                      _ptr(sampled), _ptr(counts), counts.shape[0], flat.numel(), float(beta), _ptr(losses), _ptr(g_obj),
+                                      _ptr(g_deltas), _stream()), "hd_rpn_loss")
+    LAUNCHES += 1
+    return losses, g_obj, g_deltas
+
+
 def roi_align_bwd(grad_out, rois, input_shape, spatial_scale, sampling_ratio):
     """Gradient of torchvision.ops.roi_align(aligned=False) w.r.t. its fp32 NCHW input of shape ``input_shape``, for grad_out
     [K, C, PH, PW]: channels-last vector reductions (hd_roi_align_bwd_nhwc) + one layout conversion.  Returns NCHW fp32."""

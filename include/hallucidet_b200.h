@@ -332,6 +332,22 @@ int hd_roi_match_labels(const float* props, const int64_t* n_props, const float*
                         int64_t* labels, int64_t* matched, hd_stream stream);
 int hd_roi_gather_samples(const hd_roi_gather_args* args, hd_stream stream);
 
+/* ---- Detection losses, value and gradient in one launch -------------------------------------------------------------
+ * hd_fastrcnn_loss: torchvision roi_heads.fastrcnn_loss (cross-entropy over the sampled proposals, mean; smooth-L1 with
+ * `beta` of the matched class's box deltas over the foreground rows, summed, / number of sampled rows) as the reference's
+ * roi_heads_eval calls it (src/utils/eval_forward_fasterrcnn.py:133-136).  labels [rows] int64: class, 0 = background,
+ * -100 = padding row (ignored, as F.cross_entropy's ignore_index).  losses [2] = (classification, box regression);
+ * grad_logits [rows][classes] / grad_box [rows][4*classes] = d(loss) / d(input), fully written.
+ * hd_rpn_loss: RegionProposalNetwork.compute_loss (TV rpn.py; reference :96-99) on the sampled anchors given as a row list:
+ * flat [rows] int64 = positions of the drawn anchors in the flattened [batch * anchors] arrays (rows past the drawn total
+ * are padding), sampled = hd_sample_balanced's byte map (1 = positive), counts = its counts.  losses [2] = (objectness,
+ * box regression); grad_objectness [batch * anchors] / grad_deltas [batch * anchors][4] must be zeroed by the caller. */
+int hd_fastrcnn_loss(const float* class_logits, const float* box_regression, const int64_t* labels, const float* regression_targets,
+                     int rows, int num_classes, float beta, float* losses, float* grad_logits, float* grad_box, hd_stream stream);
+int hd_rpn_loss(const float* objectness, const float* pred_bbox_deltas, const float* labels, const float* regression_targets,
+                const int64_t* flat, const uint8_t* sampled, const int32_t* counts, int batch, int rows, float beta, float* losses,
+                float* grad_objectness, float* grad_deltas, hd_stream stream);
+
 /* ---- RoIAlign backward (box head pooling over the FPN levels) ------------------------------------------------
  * grad_in_nhwc ([n][h][w][c] fp32 channels-last scratch, zeroed by the caller) += gradient of
  * torchvision.ops.roi_align(input, rois, spatial_scale, pooled_h, pooled_w, sampling_ratio, aligned = False) -- the op
