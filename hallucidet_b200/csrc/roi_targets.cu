@@ -12,6 +12,7 @@
 //   hd_roi_gather_samples  the drawn candidates (ascending flat positions) -> proposals, labels, matched gt, regression
 //                          targets (encode_boxes), RoIs (image index, box) and FPN level (LevelMapper)
 #include <math.h>
+#include <string.h>
 
 #include "hd_common.cuh"
 
@@ -137,11 +138,68 @@ __global__ void __launch_bounds__(256) roi_gather_samples_kernel(const GatherPar
     P.out_levels[s] = static_cast<long long>(lvl) - static_cast<long long>(P.k_min);
 }
 
+constexpr int kMaxPredLevels = 8;
+
+struct PredLevels {
+    float* pred[kMaxPredLevels];        // [B][hw][cp] channels-last predictor output (or its gradient) of the level
+    int hw[kMaxPredLevels];             // pixels per image
+    int cp[kMaxPredLevels];             // channel pitch (>= 5 * a)
+    int first_pixel[kMaxPredLevels];    // pixels of the earlier levels (per image)
+    int levels, a, pixels;              // anchors per pixel, pixels per image over all levels
+};
+
+// objectness [B][pixels * a] / deltas [B][pixels * a][4] <-> per-level channels-last predictor maps (channels: a objectness
+// logits, then 4 * a box deltas): torchvision's concat_box_prediction_layers (TV rpn.py:81-110) and its adjoint.
+template <bool kBackward>
+__global__ void __launch_bounds__(256) rpn_concat_kernel(const PredLevels L, int B, float* __restrict__ obj, float* __restrict__ deltas) {
+    pdl_trigger();
+    pdl_wait();
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= B * L.pixels) return;
+    const int b = q / L.pixels, px = q - b * L.pixels;
+    int l = 0;
+    while (l + 1 < L.levels && px >= L.first_pixel[l + 1]) ++l;
+    const int hw = px - L.first_pixel[l];
+    float* p = L.pred[l] + (static_cast<long>(b) * L.hw[l] + hw) * L.cp[l];
+    const long o = (static_cast<long>(b) * L.pixels + px) * L.a;
+    if (!kBackward) {
+        for (int j = 0; j < L.a; ++j) obj[o + j] = p[j];
+        for (int j = 0; j < 4 * L.a; ++j) deltas[o * 4 + j] = p[L.a + j];
+    } else {
+        for (int j = 0; j < L.a; ++j) p[j] = obj[o + j];
+        for (int j = 0; j < 4 * L.a; ++j) p[L.a + j] = deltas[o * 4 + j];
+        for (int j = 5 * L.a; j < L.cp[l]; ++j) p[j] = 0.f;
+    }
+}
+
 }  // namespace
 
 }  // namespace hd
 
 using namespace hd;
+
+// direction 0: preds -> (objectness, deltas); 1: (objectness, deltas) -> preds (every channel written, padding = 0)
+extern "C" int hd_rpn_concat_preds(void* const* preds, const int* hw, const int* channel_pitch, int levels, int batch, int anchors_per_pixel,
+                                   float* objectness, float* deltas, int direction, hd_stream stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    HD_CHECK_ARG(preds != nullptr && hw != nullptr && channel_pitch != nullptr && levels >= 1 && levels <= kMaxPredLevels);
+    HD_CHECK_ARG(batch > 0 && anchors_per_pixel >= 1 && objectness != nullptr && deltas != nullptr && (direction == 0 || direction == 1));
+    PredLevels L;
+    memset(&L, 0, sizeof(L));
+    int px = 0;
+    for (int l = 0; l < levels; ++l) {
+        HD_CHECK_ARG(preds[l] != nullptr && hw[l] > 0 && channel_pitch[l] >= 5 * anchors_per_pixel);
+        L.pred[l] = static_cast<float*>(preds[l]); L.hw[l] = hw[l]; L.cp[l] = channel_pitch[l]; L.first_pixel[l] = px;
+        px += hw[l];
+    }
+    L.levels = levels; L.a = anchors_per_pixel; L.pixels = px;
+    const long total = static_cast<long>(batch) * px;
+    const dim3 grid(static_cast<unsigned>((total + 255) / 256));
+    if (direction == 0) HD_CUDA_OK(hd::launch(rpn_concat_kernel<false>, grid, dim3(256), 0, stream, L, batch, objectness, deltas));
+    else HD_CUDA_OK(hd::launch(rpn_concat_kernel<true>, grid, dim3(256), 0, stream, L, batch, objectness, deltas));
+    HD_CUDA_OK(cudaPeekAtLastError());
+    return HD_OK;
+}
 
 // See include/hallucidet_b200.h.
 extern "C" int hd_roi_match_labels(const float* props, const int64_t* n_props, const float* gt, const uint8_t* gt_present,

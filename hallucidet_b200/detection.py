@@ -1148,6 +1148,7 @@ GRAPH_PROPOSAL_FILTER = _os.environ.get("HD_GRAPH_PROPOSALS", "1") == "1"
 STATIC_TAIL = _os.environ.get("HD_STATIC_TAIL", "1") == "1"
 FUSED_ROI_TARGETS = _os.environ.get("HD_FUSED_ROI_TARGETS", "1") == "1"   # csrc/roi_targets.cu instead of ~80 element-wise launches
 FUSED_DET_LOSSES = _os.environ.get("HD_FUSED_DET_LOSSES", "1") == "1"     # csrc/det_losses.cu: loss value + gradient in one launch
+FLAT_RPN_PREDS = _os.environ.get("HD_FLAT_RPN_PREDS", "1") == "1"         # RPN head outputs flattened by one launch each way (heads.py)
 PER_LEVEL_NMS = _os.environ.get("HD_PER_LEVEL_NMS", "1") == "1"     # proposal NMS as (image, level) problems (see _filter_nms_static)
 _STATIC_PROGRAMS = {}
 
@@ -1233,33 +1234,45 @@ def rpn_eval(model, images, features, targets, targets_event=None, static=False)
     (src/utils/eval_forward_fasterrcnn.py:62-99).  ``targets_event``: CUDA event recorded once ``targets`` are final on
     the current stream; lets the anchor-target work start before the backbone forward has finished."""
     features = list(features.values())
-    objectness, static_preds = None, False
+    objectness, static_preds, flat_obj = None, False, None
     if B200_HEADS and features[0].is_cuda and isinstance(model.backbone, FrozenBackbone):
         # the frozen RPN head on the tcgen05 conv kernels, reading the backbone's bf16 pyramid (forward + input gradient only)
         bf16 = model.backbone.bf16_features()
         if bf16 is not None and len(bf16) == len(features) and heads.rpn_head_tower(model.rpn.head) is not None:
             heads.USE_CUDA_GRAPH = bool(model.backbone.use_cuda_graph)
-            objectness, pred_bbox_deltas, static_preds = heads.rpn_head_forward(model.rpn.head, features, bf16, return_static=True)
+            if FLAT_RPN_PREDS and features[0].dtype == torch.float32:
+                # the head's outputs directly in torchvision's flattened per-anchor order (one launch each way)
+                flat_obj, flat_deltas, flat_napl, static_preds = heads.rpn_head_forward_flat(model.rpn.head, features, bf16)
+                objectness = flat_obj
+            else:
+                objectness, pred_bbox_deltas, static_preds = heads.rpn_head_forward(model.rpn.head, features, bf16, return_static=True)
     if objectness is None:
         objectness, pred_bbox_deltas = _rpn_head(model.rpn.head, features)
     batched = BATCHED_TAIL and features[0].is_cuda
     anchors, anchors_fresh = _anchors(model, images, features) if batched else (model.rpn.anchor_generator(images, features), True)
     num_images = len(anchors)
-    num_anchors_per_level = [o[0].shape[0] * o[0].shape[1] * o[0].shape[2] for o in objectness]
+    if flat_obj is not None:
+        num_anchors_per_level = flat_napl
+    else:
+        num_anchors_per_level = [o[0].shape[0] * o[0].shape[1] * o[0].shape[2] for o in objectness]
     pre_nms = sum(min(model.rpn.pre_nms_top_n(), n) for n in num_anchors_per_level)
     if targets is None:
         raise ValueError("targets should not be None")
-    use_batched = batched and objectness[0].dtype == torch.float32 and _batched_ok(pre_nms) and all(a.shape == anchors[0].shape for a in anchors)
+    use_batched = (batched and (flat_obj if flat_obj is not None else objectness[0]).dtype == torch.float32 and _batched_ok(pre_nms)
+                   and all(a.shape == anchors[0].shape for a in anchors))
     pend_boxes = None
     if use_batched and static_preds and GRAPH_PROPOSAL_FILTER and not anchors_fresh:
         # The predictor outputs live in the static buffers of the head's CUDA-graph program and the anchors are cached: the whole
         # gradient-free, static-shape chain concat -> decode -> per-level top-k -> clip / filter -> sort -> NMS (~45 launches) is
         # captured once and replayed as ONE graph launch; only the final data-dependent gather stays eager (after the count read).
-        obj_lv, del_lv = [o.detach() for o in objectness], [d.detach() for d in pred_bbox_deltas]
+        if flat_obj is not None:
+            obj_lv, del_lv = [flat_obj.detach()], [flat_deltas.detach()]
+        else:
+            obj_lv, del_lv = [o.detach() for o in objectness], [d.detach() for d in pred_bbox_deltas]
         image_sizes = images.image_sizes
 
         def program():
-            o2, d2 = concat_box_prediction_layers(obj_lv, del_lv)
+            o2, d2 = (obj_lv[0], del_lv[0]) if flat_obj is not None else concat_box_prediction_layers(obj_lv, del_lv)
             props = _decode(model.rpn.box_coder, d2, anchors).view(num_images, -1, 4)
             if static:
                 return filter_proposals_static(model.rpn, props, o2, image_sizes, num_anchors_per_level)
@@ -1268,7 +1281,10 @@ def rpn_eval(model, images, features, targets, targets_event=None, static=False)
         key = (id(model.rpn), tuple(o.data_ptr() for o in obj_lv), anchors[0].data_ptr(), tuple(map(tuple, image_sizes)), bool(static))
         with torch.no_grad():
             pend_boxes = _static_program(key).run(program)
-    objectness, pred_bbox_deltas = concat_box_prediction_layers(objectness, pred_bbox_deltas)
+    if flat_obj is not None:
+        objectness, pred_bbox_deltas = flat_obj, flat_deltas
+    else:
+        objectness, pred_bbox_deltas = concat_box_prediction_layers(objectness, pred_bbox_deltas)
     if pend_boxes is None:
         proposals = _decode(model.rpn.box_coder, pred_bbox_deltas.detach(), anchors)
         proposals = proposals.view(num_images, -1, 4)

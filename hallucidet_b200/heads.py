@@ -141,7 +141,7 @@ class _TowerProgram:
         for buf, dp in zip(self.dpred, dpreds):
             if dp is None:
                 buf.zero_()
-            else:
+            elif dp.data_ptr() != buf.data_ptr():
                 buf.copy_(dp)
         self._run("bwd", lambda: [self.tower.backward(tuple(x.shape), h, dp, dx)
                                   for x, h, dp, dx in zip(self.x, self.hidden, self.dpred, self.dx)])
@@ -239,6 +239,48 @@ def rpn_head_forward(head, features, features_bf16, return_static=False):
         prog = tower.programs.get(tuple(x.data_ptr() for x in feats_bf16))
         return logits, bbox, bool(prog is not None and preds[0].data_ptr() == prog.pred[0].data_ptr())
     return logits, bbox
+
+
+class _ConcatRPNPreds(torch.autograd.Function):
+    """torchvision ``concat_box_prediction_layers`` on the tower's channels-last predictor maps, one launch each way
+    (ops.rpn_concat_preds) instead of ~12 copies forward and autograd's ~30 slice / cat / permute kernels backward."""
+
+    @staticmethod
+    def forward(ctx, a, out, prog, *preds):
+        B = preds[0].shape[0]
+        total = B * sum(p.shape[1] * p.shape[2] for p in preds) * a
+        if out is None:
+            out = (torch.empty(total, 1, device=preds[0].device), torch.empty(total, 4, device=preds[0].device))
+        ops.rpn_concat_preds([p.detach() for p in preds], a, out[0], out[1])
+        ctx.a, ctx.shapes, ctx.prog = a, [tuple(p.shape) for p in preds], prog
+        return out[0], out[1]
+
+    @staticmethod
+    def backward(ctx, g_obj, g_deltas):
+        # straight into the tower program's static gradient buffers when there is one (its backward then skips its copies)
+        grads = ctx.prog.dpred if ctx.prog is not None else [torch.empty(s, device=g_obj.device, dtype=torch.float32) for s in ctx.shapes]
+        ops.rpn_concat_preds(grads, ctx.a, g_obj.contiguous(), g_deltas.contiguous(), backward=True)
+        return (None, None, None) + tuple(grads)
+
+
+def rpn_head_forward_flat(head, features, features_bf16):
+    """``RPNHead.forward`` + ``concat_box_prediction_layers``: (objectness [B * A, 1], deltas [B * A, 4], anchors per level,
+    static) -- ``static``: both tensors live at fixed addresses (the tower runs as a CUDA-graph program), so downstream
+    fixed-shape work can be captured too."""
+    tower = rpn_head_tower(head)
+    a = head.cls_logits.out_channels
+    feats_bf16 = list(features_bf16)
+    preds = _TowerFunction.apply(tower, feats_bf16, *features)
+    prog = tower.programs.get(tuple(x.data_ptr() for x in feats_bf16))
+    static = bool(prog is not None and preds[0].data_ptr() == prog.pred[0].data_ptr())
+    out = None
+    if static:
+        out = getattr(prog, "flat_out", None)
+        if out is None:
+            total = preds[0].shape[0] * sum(p.shape[1] * p.shape[2] for p in preds) * a
+            out = prog.flat_out = (torch.empty(total, 1, device=preds[0].device), torch.empty(total, 4, device=preds[0].device))
+    objectness, deltas = _ConcatRPNPreds.apply(a, out, prog if static else None, *preds)
+    return objectness, deltas, [p.shape[1] * p.shape[2] * a for p in preds], static
 
 
 def retinanet_head_towers(head):

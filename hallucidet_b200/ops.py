@@ -753,6 +753,25 @@ def roi_gather_samples(flat, counts, props, gt, labels, matched, coder_weights, 
     return out
 
 
+def rpn_concat_preds(preds, a, objectness, deltas, backward=False):
+    """hd_rpn_concat_preds: channels-last predictor maps [B, H, W, Cp] (a objectness + 4a delta channels) -> objectness [B * sum HWa, 1]
+    and deltas [B * sum HWa, 4] in torchvision's order (``backward``: the adjoint, filling ``preds`` from the two flat tensors)."""
+    global LAUNCHES
+    n = len(preds)
+    B = preds[0].shape[0]
+    assert all(p.dtype == torch.float32 and p.is_contiguous() and p.dim() == 4 and p.shape[0] == B for p in preds)
+    assert objectness.dtype == deltas.dtype == torch.float32 and objectness.is_contiguous() and deltas.is_contiguous()
+    total = B * sum(p.shape[1] * p.shape[2] for p in preds) * a
+    assert objectness.numel() == total and deltas.numel() == 4 * total
+    ptrs = (ctypes.c_void_p * n)(*[p.data_ptr() for p in preds])
+    hw = (ctypes.c_int * n)(*[p.shape[1] * p.shape[2] for p in preds])
+    cp = (ctypes.c_int * n)(*[p.shape[3] for p in preds])
+    with _Timed("rpn_concat_preds"):
+        check(_lib.load().hd_rpn_concat_preds(ptrs, hw, cp, n, B, int(a), _ptr(objectness), _ptr(deltas), 1 if backward else 0, _stream()),
+              "hd_rpn_concat_preds")
+    LAUNCHES += 1
+
+
 def fastrcnn_loss(class_logits, box_regression, labels, regression_targets, beta=1 / 9):
     """hd_fastrcnn_loss: (losses [2] = classification, box regression; d/d class_logits; d/d box_regression) in one launch."""
     global LAUNCHES

@@ -332,6 +332,16 @@ int hd_roi_match_labels(const float* props, const int64_t* n_props, const float*
                         int64_t* labels, int64_t* matched, hd_stream stream);
 int hd_roi_gather_samples(const hd_roi_gather_args* args, hd_stream stream);
 
+/* ---- RPN predictor maps <-> flattened per-anchor tensors --------------------------------------------------------------
+ * torchvision concat_box_prediction_layers (TV rpn.py:81-110, called from RegionProposalNetwork.forward; reference
+ * src/utils/eval_forward_fasterrcnn.py:76-78) for channels-last predictor maps preds[l] = [batch][hw[l]][channel_pitch[l]]
+ * fp32 whose channels are `anchors_per_pixel` objectness logits followed by 4 * anchors_per_pixel box deltas:
+ * direction 0 writes objectness [batch][sum_l hw[l] * a] and deltas [batch][sum_l hw[l] * a][4] (level-major, then pixel,
+ * then anchor -- torchvision's order); direction 1 is the adjoint (gradients back into the maps, padding channels = 0).
+ * One launch for all levels instead of ~12 forward / ~30 backward (autograd's slice / cat backward). */
+int hd_rpn_concat_preds(void* const* preds, const int* hw, const int* channel_pitch, int levels, int batch, int anchors_per_pixel,
+                        float* objectness, float* deltas, int direction, hd_stream stream);
+
 /* ---- Detection losses, value and gradient in one launch -------------------------------------------------------------
  * hd_fastrcnn_loss: torchvision roi_heads.fastrcnn_loss (cross-entropy over the sampled proposals, mean; smooth-L1 with
  * `beta` of the matched class's box deltas over the foreground rows, summed, / number of sampled rows) as the reference's

@@ -267,3 +267,23 @@ def test_sample_balanced_sees_a_reseed_without_host_sync():
     torch.manual_seed(5)
     ref1, ref2 = _reference(lab, 256, 0.5), _reference(lab, 256, 0.5)
     assert torch.equal(a1, a2) and torch.equal(a1, ref1) and torch.equal(a3, ref2) and not torch.equal(a1, a3)
+
+
+def test_rpn_concat_preds_matches_torchvision_and_autograd():
+    """hd_rpn_concat_preds (both directions) against torchvision's concat_box_prediction_layers on NCHW views of the same
+    channels-last predictor maps, forward values and the gradients autograd sends back."""
+    from torchvision.models.detection.rpn import concat_box_prediction_layers
+    from hallucidet_b200 import heads
+    g = torch.Generator().manual_seed(4)
+    a, B = 3, 2
+    preds = [torch.randn(B, h, w, 16, generator=g).cuda().requires_grad_() for h, w in ((20, 24), (10, 12), (5, 6), (3, 3), (2, 2))]
+    obj, deltas = heads._ConcatRPNPreds.apply(a, None, None, *preds)
+    ref_preds = [p.detach().clone().requires_grad_() for p in preds]
+    nchw = [p.permute(0, 3, 1, 2) for p in ref_preds]
+    ro, rd = concat_box_prediction_layers([x[:, :a] for x in nchw], [x[:, a:5 * a] for x in nchw])
+    assert torch.equal(obj, ro) and torch.equal(deltas, rd)
+    wo, wd = torch.randn(obj.shape, generator=g).cuda(), torch.randn(deltas.shape, generator=g).cuda()
+    ((obj * wo).sum() + (deltas * wd).sum()).backward()
+    ((ro * wo).sum() + (rd * wd).sum()).backward()
+    for p, q in zip(preds, ref_preds):
+        assert torch.equal(p.grad, q.grad)
