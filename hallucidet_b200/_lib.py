@@ -132,6 +132,7 @@ PROTOTYPES = {
     "hd_roi_align_bwd_nhwc": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
     "hd_roi_align_fwd_nhwc": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p],
     "hd_roi_align_ml_fwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
+    "hd_roi_align_ml_fwd_bf16": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "hd_roi_align_ml_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "hd_nchw_to_nhwc_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "hd_nhwc_to_nchw_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],

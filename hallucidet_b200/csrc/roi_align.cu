@@ -25,7 +25,7 @@ constexpr int kMaxLevels = 8;
 
 // feature-pyramid levels a RoI can be pooled from (level_of_roi selects one; a single-level call passes level_of_roi = NULL)
 struct RoiLevels {
-    const float* feat[kMaxLevels];      // forward: channels-last feature maps [N][H][W][C]
+    const void* feat[kMaxLevels];       // forward: channels-last feature maps [N][H][W][C], fp32 or bf16
     float* grad[kMaxLevels];            // backward: channels-last gradient scratch (zeroed by the caller)
     int h[kMaxLevels], w[kMaxLevels];
     float scale[kMaxLevels];
@@ -110,6 +110,18 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_bwd_nhwc_kernel(const f
 // channels of one pixel (torchvision gathers 16 scattered 4-byte values per output element from NCHW).  Same expression
 // per output element as torchvision's roi_align_forward_kernel_impl: val += w1*v1 + w2*v2 + w3*v3 + w4*v4 over the samples
 // in (iy, ix) order, then val /= count.  The [C][PH*PW] result of a RoI is staged in shared memory and written coalesced.
+template <typename T>
+__device__ __forceinline__ float4 load4(const T* p);
+template <>
+__device__ __forceinline__ float4 load4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <>
+__device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+    const uint2 w = *reinterpret_cast<const uint2*>(p);                     // 4 channels: exact widening to fp32
+    return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u), __uint_as_float(w.y << 16),
+                       __uint_as_float(w.y & 0xffff0000u));
+}
+
+template <typename T>
 __global__ void __launch_bounds__(kRoiThreads) roi_align_fwd_nhwc_kernel(const float* __restrict__ rois, const long long* __restrict__ level_of_roi,
                                                                          const RoiLevels L, float* __restrict__ out, int C, int PH, int PW,
                                                                          int sampling_ratio) {
@@ -124,7 +136,7 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_fwd_nhwc_kernel(const f
     const int lvl = level_of_roi != nullptr ? static_cast<int>(level_of_roi[k]) : 0;
     const int H = L.h[lvl], W = L.w[lvl];
     const float spatial_scale = L.scale[lvl];
-    const float* __restrict__ feat = L.feat[lvl];
+    const T* __restrict__ feat = static_cast<const T*>(L.feat[lvl]);
     const float roi_start_w = roi[1] * spatial_scale, roi_start_h = roi[2] * spatial_scale;
     const float roi_end_w = roi[3] * spatial_scale, roi_end_h = roi[4] * spatial_scale;
     const float roi_width = fmaxf(roi_end_w - roi_start_w, 1.f), roi_height = fmaxf(roi_end_h - roi_start_h, 1.f);
@@ -155,7 +167,7 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_fwd_nhwc_kernel(const f
     __syncthreads();
     const int lanes = C / 4, groups = kRoiThreads / lanes;
     const int grp = threadIdx.x / lanes, c0 = (threadIdx.x - grp * lanes) * 4;
-    const float* fin = feat + static_cast<long>(n) * H * W * C + c0;
+    const T* fin = feat + static_cast<long>(n) * H * W * C + c0;
     if (grp < groups) {
         for (int bin = grp; bin < nbins; bin += groups) {
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -163,10 +175,10 @@ __global__ void __launch_bounds__(kRoiThreads) roi_align_fwd_nhwc_kernel(const f
                 const int s4 = (bin * per_bin + r) * 4;
                 if (s_off[s4] < 0) continue;                   // sample outside the map contributes 0
                 const float w1 = s_w[s4], w2 = s_w[s4 + 1], w3 = s_w[s4 + 2], w4 = s_w[s4 + 3];
-                const float4 v1 = *reinterpret_cast<const float4*>(fin + static_cast<long>(s_off[s4]) * C);
-                const float4 v2 = *reinterpret_cast<const float4*>(fin + static_cast<long>(s_off[s4 + 1]) * C);
-                const float4 v3 = *reinterpret_cast<const float4*>(fin + static_cast<long>(s_off[s4 + 2]) * C);
-                const float4 v4 = *reinterpret_cast<const float4*>(fin + static_cast<long>(s_off[s4 + 3]) * C);
+                const float4 v1 = load4<T>(fin + static_cast<long>(s_off[s4]) * C);
+                const float4 v2 = load4<T>(fin + static_cast<long>(s_off[s4 + 1]) * C);
+                const float4 v3 = load4<T>(fin + static_cast<long>(s_off[s4 + 2]) * C);
+                const float4 v4 = load4<T>(fin + static_cast<long>(s_off[s4 + 3]) * C);
                 acc.x += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
                 acc.y += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
                 acc.z += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
@@ -251,11 +263,18 @@ static int roi_bwd_launch(const float* grad_out, const float* rois, const long l
 }
 
 static int roi_fwd_launch(const float* rois, const long long* level_of_roi, const RoiLevels& L, float* out, int num_rois, int channels,
-                          int pooled_h, int pooled_w, int sampling_ratio, cudaStream_t stream) {
+                          int pooled_h, int pooled_w, int sampling_ratio, cudaStream_t stream, bool bf16 = false) {
     const size_t smem = static_cast<size_t>(channels) * pooled_h * pooled_w * sizeof(float);
-    static SmemAttrOnce smem_attr;
-    HD_CUDA_OK(ensure_dyn_smem(smem_attr, roi_align_fwd_nhwc_kernel, static_cast<int>(kMaxC * kMaxBins * sizeof(float))));
-    HD_CUDA_OK(hd::launch(roi_align_fwd_nhwc_kernel, dim3(num_rois), dim3(kRoiThreads), smem, stream, rois, level_of_roi, L, out, channels, pooled_h, pooled_w, sampling_ratio));
+    static SmemAttrOnce smem_attr, smem_attr16;
+    if (bf16) {
+        HD_CUDA_OK(ensure_dyn_smem(smem_attr16, roi_align_fwd_nhwc_kernel<__nv_bfloat16>, static_cast<int>(kMaxC * kMaxBins * sizeof(float))));
+        HD_CUDA_OK(hd::launch(roi_align_fwd_nhwc_kernel<__nv_bfloat16>, dim3(num_rois), dim3(kRoiThreads), smem, stream, rois, level_of_roi, L, out,
+                              channels, pooled_h, pooled_w, sampling_ratio));
+        HD_CUDA_OK(cudaPeekAtLastError());
+        return HD_OK;
+    }
+    HD_CUDA_OK(ensure_dyn_smem(smem_attr, roi_align_fwd_nhwc_kernel<float>, static_cast<int>(kMaxC * kMaxBins * sizeof(float))));
+    HD_CUDA_OK(hd::launch(roi_align_fwd_nhwc_kernel<float>, dim3(num_rois), dim3(kRoiThreads), smem, stream, rois, level_of_roi, L, out, channels, pooled_h, pooled_w, sampling_ratio));
     HD_CUDA_OK(cudaPeekAtLastError());
     return HD_OK;
 }
@@ -292,6 +311,24 @@ extern "C" int hd_roi_align_ml_fwd(const hd_roi_level* levels, int n_levels, con
     }
     return roi_fwd_launch(rois, reinterpret_cast<const long long*>(level_of_roi), L, out, num_rois, channels, pooled_h, pooled_w,
                           sampling_ratio, static_cast<cudaStream_t>(stream_));
+}
+
+// the same with bf16 channels-last feature maps (levels[i].feat_nhwc points at __nv_bfloat16): half the L2 traffic, identical
+// results when the fp32 maps are widened copies of these
+extern "C" int hd_roi_align_ml_fwd_bf16(const hd_roi_level* levels, int n_levels, const float* rois, const int64_t* level_of_roi, float* out,
+                                   int num_rois, int channels, int pooled_h, int pooled_w, int sampling_ratio, hd_stream stream_) {
+    if (int e = roi_check(num_rois, channels, pooled_h, pooled_w, sampling_ratio)) return e;
+    HD_CHECK_ARG(levels != nullptr && n_levels >= 1 && n_levels <= kMaxLevels);
+    if (num_rois == 0) return HD_OK;
+    HD_CHECK_ARG(rois != nullptr && level_of_roi != nullptr && out != nullptr);
+    RoiLevels L;
+    memset(&L, 0, sizeof(L));
+    for (int i = 0; i < n_levels; ++i) {
+        HD_CHECK_ARG(levels[i].feat_nhwc != nullptr && (reinterpret_cast<uintptr_t>(levels[i].feat_nhwc) & 7) == 0 && levels[i].h > 0 && levels[i].w > 0);
+        L.feat[i] = levels[i].feat_nhwc; L.h[i] = levels[i].h; L.w[i] = levels[i].w; L.scale[i] = levels[i].scale;
+    }
+    return roi_fwd_launch(rois, reinterpret_cast<const long long*>(level_of_roi), L, out, num_rois, channels, pooled_h, pooled_w,
+                          sampling_ratio, static_cast<cudaStream_t>(stream_), true);
 }
 
 extern "C" int hd_roi_align_ml_bwd(const hd_roi_level* levels, int n_levels, const float* grad_out, const float* rois,

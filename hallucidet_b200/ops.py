@@ -850,7 +850,7 @@ def roi_align_fwd(feat_nhwc, rois, output_size, spatial_scale, sampling_ratio):
 def _roi_level_table(tensors_nhwc, scales, grads=False):
     table = (_lib.HdRoiLevel * len(tensors_nhwc))()
     for i, (t, sc) in enumerate(zip(tensors_nhwc, scales)):
-        assert t.dtype == torch.float32 and t.is_contiguous()
+        assert t.dtype == tensors_nhwc[0].dtype and t.dtype in (torch.float32, torch.bfloat16) and t.is_contiguous()
         if grads:
             table[i].grad_nhwc = _ptr(t)
         else:
@@ -866,9 +866,10 @@ def roi_align_ml_fwd(feats_nhwc, scales, rois, levels, output_size, sampling_rat
     assert rois.dtype == torch.float32 and rois.is_contiguous() and levels.dtype == torch.int64 and levels.is_contiguous()
     out = torch.empty(k, c, int(output_size[0]), int(output_size[1]), dtype=torch.float32, device=rois.device)
     table = _roi_level_table(feats_nhwc, scales)
+    fn = _lib.load().hd_roi_align_ml_fwd_bf16 if feats_nhwc[0].dtype == torch.bfloat16 else _lib.load().hd_roi_align_ml_fwd
     with _Timed("roi_align_fwd"):
-        check(_lib.load().hd_roi_align_ml_fwd(table, len(feats_nhwc), _ptr(rois), _ptr(levels), _ptr(out), k, c, int(output_size[0]),
-                                              int(output_size[1]), int(sampling_ratio), _stream()), "hd_roi_align_ml_fwd")
+        check(fn(table, len(feats_nhwc), _ptr(rois), _ptr(levels), _ptr(out), k, c, int(output_size[0]),
+                 int(output_size[1]), int(sampling_ratio), _stream()), "hd_roi_align_ml_fwd")
     return out
 
 

@@ -380,7 +380,7 @@ int hd_nchw_to_nhwc_f32(const float* x_nchw, float* y_nhwc, int n, int channels,
  * per-level index lists -- one host sync per level in torchvision -- disappear.  levels: HOST array of n_levels (<= 8)
  * entries; forward reads feat_nhwc, backward accumulates into grad_nhwc (zeroed by the caller). */
 typedef struct hd_roi_level {
-    const float* feat_nhwc;   /* [n][h][w][c] fp32 */
+    const void* feat_nhwc;    /* [n][h][w][c] fp32 (hd_roi_align_ml_fwd) or bf16 (hd_roi_align_ml_fwd_bf16) */
     float* grad_nhwc;         /* [n][h][w][c] fp32 */
     int32_t h, w;
     float scale;              /* spatial_scale of the level */
@@ -388,6 +388,9 @@ typedef struct hd_roi_level {
 } hd_roi_level;
 int hd_roi_align_ml_fwd(const hd_roi_level* levels, int n_levels, const float* rois, const int64_t* level_of_roi, float* out,
                         int num_rois, int channels, int pooled_h, int pooled_w, int sampling_ratio, hd_stream stream);
+/* the same with bf16 feature maps: half the L2 traffic; identical results when the fp32 maps are widened copies of the bf16 ones */
+int hd_roi_align_ml_fwd_bf16(const hd_roi_level* levels, int n_levels, const float* rois, const int64_t* level_of_roi, float* out,
+                             int num_rois, int channels, int pooled_h, int pooled_w, int sampling_ratio, hd_stream stream);
 int hd_roi_align_ml_bwd(const hd_roi_level* levels, int n_levels, const float* grad_out, const float* rois,
                         const int64_t* level_of_roi, int num_rois, int channels, int pooled_h, int pooled_w, int sampling_ratio,
                         hd_stream stream);

@@ -287,3 +287,23 @@ def test_rpn_concat_preds_matches_torchvision_and_autograd():
     ((ro * wo).sum() + (rd * wd).sum()).backward()
     for p, q in zip(preds, ref_preds):
         assert torch.equal(p.grad, q.grad)
+
+
+def test_roi_align_ml_fwd_bf16_equals_fp32_on_widened_maps():
+    """hd_roi_align_ml_fwd_bf16 reads the bf16 pyramid; on fp32 maps that are widened copies of it the fp32 entry point gives the
+    same bits (same arithmetic, half the traffic)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(8)
+    B, C = 2, 256
+    sizes = ((40, 48), (20, 24), (10, 12), (5, 6))
+    scales = (0.25, 0.125, 0.0625, 0.03125)
+    maps16 = [torch.randn(B, h, w, C, generator=g).to(torch.bfloat16).cuda() for h, w in sizes]
+    maps32 = [m.float() for m in maps16]
+    K = 300
+    xy = torch.rand(K, 2, generator=g) * 120
+    wh = torch.rand(K, 2, generator=g) ** 2 * 150 + 2
+    rois = torch.cat([torch.randint(0, B, (K, 1), generator=g).float(), xy, xy + wh], 1).cuda()
+    levels = torch.randint(0, 4, (K,), generator=g).cuda()
+    a = ops.roi_align_ml_fwd(maps32, scales, rois, levels, (7, 7), 2)
+    b = ops.roi_align_ml_fwd(maps16, scales, rois, levels, (7, 7), 2)
+    assert torch.equal(a, b)
