@@ -142,7 +142,7 @@ class _BackboneFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, eng):
         ctx.eng = eng
-        outs = eng.forward(x)
+        outs = eng.forward(x, clone=not getattr(eng.m, "static_outputs", False))
         ctx.generation = eng.generation
         return tuple(outs)
 
@@ -271,10 +271,12 @@ class _BackboneEngine:
                                    out_f32=out_f32, out_f32_channels=c.cout if out_f32 is not None else 0, store_bf16=store_bf16,
                                    out_f32_nhwc=out_f32 is not None and self.cl))
 
-    def forward(self, x):
+    def forward(self, x, clone=True):
         self.x_in.copy_(x)
         self._run("fwd", self._forward_impl)
         self.generation += 1
+        if not clone:      # the engine's own buffers (valid until its next forward): FrozenBackbone.static_outputs
+            return [lv["out"] for lv in self.levels] + [e["out"] for e in self.extra]
         return [lv["out"].clone() for lv in self.levels] + [e["out"].clone() for e in self.extra]
 
     def _forward_impl(self):

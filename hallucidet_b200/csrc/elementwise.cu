@@ -806,12 +806,12 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
     pdl_trigger();
     pdl_wait();
     const int ho = h / 2, wo = w / 2, G = C / 8;
-    const long total = static_cast<long>(n) * ho * wo * G;
-    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long>(gridDim.x) * blockDim.x) {
+    // 32-bit index arithmetic (the host checks n*h*w*C/8 < 2^31)
+    const unsigned total = static_cast<unsigned>(n) * ho * wo * G;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int g = static_cast<int>(i % G);
-        const long pix = i / G;
-        const int ow = static_cast<int>(pix % wo), oh = static_cast<int>((pix / wo) % ho), b = static_cast<int>(pix / (static_cast<long>(wo) * ho));
+        const unsigned pix = i / G;
+        const int ow = static_cast<int>(pix % wo), oh = static_cast<int>((pix / wo) % ho), b = static_cast<int>(pix / (static_cast<unsigned>(wo) * ho));
         float m[8];
         unsigned am[8];                                    // window position (r*3+s) of the FIRST maximum, as ATen
 #pragma unroll
@@ -833,7 +833,7 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
         }
         bf8 o;
         o.pack(m);
-        o.store(y + pix * C + g * 8);
+        o.store(y + static_cast<size_t>(pix) * C + g * 8);
         if (idx != nullptr) {
             unsigned lo = 0, hi = 0;
 #pragma unroll
@@ -841,7 +841,7 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
                 lo |= ((mask_nonpositive && !(m[j] > 0.f)) ? 15u : am[j]) << (8 * j);
                 hi |= ((mask_nonpositive && !(m[j + 4] > 0.f)) ? 15u : am[j + 4]) << (8 * j);
             }
-            *reinterpret_cast<uint2*>(idx + pix * C + g * 8) = make_uint2(lo, hi);
+            *reinterpret_cast<uint2*>(idx + static_cast<size_t>(pix) * C + g * 8) = make_uint2(lo, hi);
         }
     }
 }
@@ -873,13 +873,24 @@ __global__ void maxpool_bwd_idx_kernel(const unsigned char* __restrict__ idx, co
         uint2 am[4];
         unsigned hit[4];
         size_t off[4];
+        bool on_q[4];
+        bf8 dvq[4];
+        // all loads of the candidate windows (arg-max bytes AND their dy vectors) are issued before anything is decoded: one
+        // L2 round trip per element instead of two dependent ones (a vector of 8 channels is hit ~90 % of the time anyway)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const unsigned oh = oh0 + (q >> 1), ow = ow0 + (q & 1);
-            const bool on = ((q >> 1) == 0 || (ih & 1u)) && ((q & 1) == 0 || (iw & 1u)) && oh < static_cast<unsigned>(ho) &&
-                            ow < static_cast<unsigned>(wo);
+            on_q[q] = ((q >> 1) == 0 || (ih & 1u)) && ((q & 1) == 0 || (iw & 1u)) && oh < static_cast<unsigned>(ho) &&
+                      ow < static_cast<unsigned>(wo);
             off[q] = (static_cast<size_t>(b * ho + oh) * wo + ow) * C + g * 8;
-            am[q] = on ? *reinterpret_cast<const uint2*>(idx + off[q]) : make_uint2(0xffffffffu, 0xffffffffu);
+            am[q] = on_q[q] ? *reinterpret_cast<const uint2*>(idx + off[q]) : make_uint2(0xffffffffu, 0xffffffffu);
+            if (on_q[q]) dvq[q].load(dy + off[q]);
+            else dvq[q].u = make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const unsigned oh = oh0 + (q >> 1), ow = ow0 + (q & 1);
+            const bool on = on_q[q];
             const unsigned pos = (ih + 1 - 2 * oh) * 3 + (iw + 1 - 2 * ow);
             const unsigned pat = pos * 0x01010101u;                    // pos in every byte
             const unsigned x0 = am[q].x ^ pat, x1 = am[q].y ^ pat;     // a zero byte = arg-max here
@@ -894,10 +905,8 @@ __global__ void maxpool_bwd_idx_kernel(const unsigned char* __restrict__ idx, co
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             if (!hit[q]) continue;
-            bf8 dv;
-            dv.load(dy + off[q]);
             float df[8];
-            dv.unpack(df);
+            dvq[q].unpack(df);
 #pragma unroll
             for (int j = 0; j < 8; ++j) if (hit[q] & (1u << j)) acc[j] += df[j];
         }
@@ -987,16 +996,20 @@ __global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_
                                       int C) {
     pdl_trigger();
     pdl_wait();            // h,w = OUTPUT size
-    const int G = C / 8;
-    const long total = static_cast<long>(n) * h * w * G;
-    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long>(gridDim.x) * blockDim.x) {
-        const int g = static_cast<int>(i % G);
-        const long pix = i / G;
-        const int ow = static_cast<int>(pix % w), oh = static_cast<int>((pix / w) % h), b = static_cast<int>(pix / (static_cast<long>(w) * h));
+    // one thread per INPUT vector (8 channels): loaded once, stored to its 2 x 2 output pixels; 32-bit index arithmetic
+    // (the host checks the element count) -- the per-output-vector form spent its time in 64-bit divisions (3.0 TB/s)
+    const unsigned G = C / 8, hi = h / 2, wi = w / 2;
+    const unsigned total = static_cast<unsigned>(n) * hi * wi * G;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned g = i % G, pix = i / G;
+        const unsigned iw = pix % wi, t = pix / wi, ih = t % hi, b = t / hi;
         bf8 v;
-        v.load(x + ((static_cast<long>(b) * (h / 2) + oh / 2) * (w / 2) + ow / 2) * C + g * 8);
-        v.store(y + pix * C + g * 8);
+        v.load(x + static_cast<size_t>(pix) * C + g * 8);
+        __nv_bfloat16* o = y + ((static_cast<size_t>(b) * h + 2 * ih) * w + 2 * iw) * C + g * 8;
+        v.store(o);
+        v.store(o + C);
+        v.store(o + static_cast<size_t>(w) * C);
+        v.store(o + static_cast<size_t>(w) * C + C);
     }
 }
 
@@ -1266,51 +1279,48 @@ __global__ void sigmoid_bwd_pack_kernel(const float* __restrict__ dhal, const fl
 // -------------------------------------------------------------------------------------------------
 // detector input transform (fp32 NCHW)
 // -------------------------------------------------------------------------------------------------
-__global__ void resize_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int c, int hi, int wi, int ho,
-                                  int wo, float sh, float sw, const float* mean, const float* stdv) {
+// grid (ceil(wo / 256), ho, n * c): the row / plane of a block are uniform, no per-element divisions (the flat grid-stride form
+// spent its time in 64-bit index arithmetic: 59 us for 39 MB)
+__global__ void __launch_bounds__(kEwThreads) resize_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int c, int hi, int wi,
+                                                                int ho, int wo, float sh, float sw, const float* mean, const float* stdv) {
     pdl_trigger();
     pdl_wait();
-    const long total = static_cast<long>(n) * c * ho * wo;
-    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long>(gridDim.x) * blockDim.x) {
-        const int ow = static_cast<int>(i % wo), oh = static_cast<int>((i / wo) % ho);
-        const long bc = i / (static_cast<long>(wo) * ho);
-        const int ch = static_cast<int>(bc % c);
-        const int ih = nearest_src(oh, sh, hi), iw = nearest_src(ow, sw, wi);
-        float v = __ldg(x + (bc * hi + ih) * wi + iw);
-        if (mean) v = (v - mean[ch]) / stdv[ch];
-        y[i] = v;
-    }
+    const int ow = blockIdx.x * blockDim.x + threadIdx.x, oh = blockIdx.y, bc = blockIdx.z;
+    if (ow >= wo) return;
+    const int ch = bc % c;
+    const int ih = nearest_src(oh, sh, hi), iw = nearest_src(ow, sw, wi);
+    float v = __ldg(x + (static_cast<size_t>(bc) * hi + ih) * wi + iw);
+    if (mean) v = (v - mean[ch]) / stdv[ch];
+    y[(static_cast<size_t>(bc) * ho + oh) * wo + ow] = v;
 }
 
-__global__ void resize_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int n, int c, int hi, int wi, int ho,
-                                  int wo, float sh, float sw, const float* stdv, int accumulate) {
+// grid (ceil(wi / 256), hi, n * c): gather-sum of the output pixels whose nearest source is (ih, iw)
+__global__ void __launch_bounds__(kEwThreads) resize_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int n, int c, int hi, int wi,
+                                                                int ho, int wo, float sh, float sw, const float* stdv, int accumulate) {
     pdl_trigger();
     pdl_wait();
-    const long total = static_cast<long>(n) * c * hi * wi;
-    for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long>(gridDim.x) * blockDim.x) {
-        const int iw = static_cast<int>(i % wi), ih = static_cast<int>((i / wi) % hi);
-        const long bc = i / (static_cast<long>(wi) * hi);
-        const int ch = static_cast<int>(bc % c);
-        int h_lo = static_cast<int>(ih / sh) - 2, w_lo = static_cast<int>(iw / sw) - 2;
-        if (h_lo < 0) h_lo = 0;
-        if (w_lo < 0) w_lo = 0;
-        float acc = 0.f;
-        for (int oh = h_lo; oh < ho; ++oh) {
-            const int s = nearest_src(oh, sh, hi);
-            if (s < ih) continue;
-            if (s > ih) break;
-            for (int ow = w_lo; ow < wo; ++ow) {
-                const int t = nearest_src(ow, sw, wi);
-                if (t < iw) continue;
-                if (t > iw) break;
-                acc += __ldg(dy + (bc * ho + oh) * wo + ow);
-            }
-        }
-        if (stdv) acc /= stdv[ch];
-        dx[i] = accumulate ? dx[i] + acc : acc;
+    const int iw = blockIdx.x * blockDim.x + threadIdx.x, ih = blockIdx.y, bc = blockIdx.z;
+    if (iw >= wi) return;
+    const int ch = bc % c;
+    int h_lo = static_cast<int>(ih / sh) - 2, w_lo = static_cast<int>(iw / sw) - 2;
+    if (h_lo < 0) h_lo = 0;
+    if (w_lo < 0) w_lo = 0;
+    // output columns that map to iw: a short contiguous run starting at or after w_lo
+    int w0 = w_lo;
+    while (w0 < wo && nearest_src(w0, sw, wi) < iw) ++w0;
+    int w1 = w0;
+    while (w1 < wo && nearest_src(w1, sw, wi) == iw) ++w1;
+    float acc = 0.f;
+    const float* plane = dy + static_cast<size_t>(bc) * ho * wo;
+    for (int oh = h_lo; oh < ho; ++oh) {
+        const int s = nearest_src(oh, sh, hi);
+        if (s < ih) continue;
+        if (s > ih) break;
+        for (int ow = w0; ow < w1; ++ow) acc += __ldg(plane + static_cast<size_t>(oh) * wo + ow);
     }
+    if (stdv) acc /= stdv[ch];
+    const size_t o = (static_cast<size_t>(bc) * hi + ih) * wi + iw;
+    dx[o] = accumulate ? dx[o] + acc : acc;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1546,6 +1556,7 @@ extern "C" int hd_maxpool_fwd(const hd_act* x, const hd_act* y, void* idx, int m
     HD_CHECK_ARG(x && y && x->ptr && y->ptr && x->c % 8 == 0 && x->c == y->c && x->h % 2 == 0 && x->w % 2 == 0);
     HD_CHECK_ARG(y->h == x->h / 2 && y->w == x->w / 2 && y->n == x->n);
     HD_CHECK_ARG(idx == nullptr || (reinterpret_cast<uintptr_t>(idx) & 7) == 0);
+    HD_CHECK_ARG(static_cast<long>(x->n) * x->h * x->w * (x->c / 8) < (1L << 31));         // 32-bit index arithmetic in the kernel
     HD_CUDA_OK(hd::launch(maxpool_fwd_kernel, dim3(ew_blocks(static_cast<long>(y->n) * y->h * y->w * (y->c / 8))), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), static_cast<const __nv_bfloat16*>(x->ptr),
                                                           static_cast<__nv_bfloat16*>(y->ptr), static_cast<unsigned char*>(idx),
                                                           mask_nonpositive, x->n, x->h, x->w, x->c));
@@ -1576,7 +1587,8 @@ extern "C" int hd_maxpool_bwd(const hd_act* x, const hd_act* y, const void* dy, 
 
 extern "C" int hd_upsample2x_fwd(const hd_act* x, const hd_act* y, hd_stream st) {
     HD_CHECK_ARG(x && y && x->ptr && y->ptr && x->c == y->c && x->c % 8 == 0 && y->h == 2 * x->h && y->w == 2 * x->w && x->n == y->n);
-    HD_CUDA_OK(hd::launch(upsample2x_fwd_kernel, dim3(ew_blocks(static_cast<long>(y->n) * y->h * y->w * (y->c / 8))), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), static_cast<const __nv_bfloat16*>(x->ptr),
+    HD_CHECK_ARG(static_cast<long>(y->n) * y->h * y->w * (y->c / 8) < (1L << 31));        // 32-bit index arithmetic in the kernel
+    HD_CUDA_OK(hd::launch(upsample2x_fwd_kernel, dim3(ew_blocks(static_cast<long>(x->n) * x->h * x->w * (x->c / 8))), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), static_cast<const __nv_bfloat16*>(x->ptr),
                                                              static_cast<__nv_bfloat16*>(y->ptr), y->n, y->h, y->w, y->c));
     HD_LAUNCH_OK();
     return HD_OK;
@@ -1650,7 +1662,8 @@ extern "C" int hd_resize_nearest_fwd(const float* x, float* y, int n, int c, int
                                      const float* stdv, hd_stream st) {
     HD_CHECK_ARG(x && y && n > 0 && c > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0 && ((mean == nullptr) == (stdv == nullptr)));
     const float sh = static_cast<float>(hi) / static_cast<float>(ho), sw = static_cast<float>(wi) / static_cast<float>(wo);
-    HD_CUDA_OK(hd::launch(resize_fwd_kernel, dim3(ew_blocks(static_cast<long>(n) * c * ho * wo)), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), x, y, n, c, hi, wi, ho, wo, sh, sw, mean, stdv));
+    HD_CHECK_ARG(ho <= 65535 && n * c <= 65535);
+    HD_CUDA_OK(hd::launch(resize_fwd_kernel, dim3((wo + kEwThreads - 1) / kEwThreads, ho, n * c), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), x, y, n, c, hi, wi, ho, wo, sh, sw, mean, stdv));
     HD_LAUNCH_OK();
     return HD_OK;
 }
@@ -1659,7 +1672,8 @@ extern "C" int hd_resize_nearest_bwd(const float* dy, float* dx, int n, int c, i
                                      int accumulate, hd_stream st) {
     HD_CHECK_ARG(dy && dx && n > 0 && c > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0);
     const float sh = static_cast<float>(hi) / static_cast<float>(ho), sw = static_cast<float>(wi) / static_cast<float>(wo);
-    HD_CUDA_OK(hd::launch(resize_bwd_kernel, dim3(ew_blocks(static_cast<long>(n) * c * hi * wi)), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), dy, dx, n, c, hi, wi, ho, wo, sh, sw, stdv, accumulate));
+    HD_CHECK_ARG(hi <= 65535 && n * c <= 65535);
+    HD_CUDA_OK(hd::launch(resize_bwd_kernel, dim3((wi + kEwThreads - 1) / kEwThreads, hi, n * c), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), dy, dx, n, c, hi, wi, ho, wo, sh, sw, stdv, accumulate));
     HD_LAUNCH_OK();
     return HD_OK;
 }

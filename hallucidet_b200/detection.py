@@ -1159,6 +1159,7 @@ FLAT_RPN_PREDS = _os.environ.get("HD_FLAT_RPN_PREDS", "1") == "1"         # RPN 
 # are its un-rounded fp32 accumulators, not widened copies of the bf16 pyramid, so this would round the box head's input once
 # more (loss_classifier moves by 5e-5 relative) for a 0.4 % gain.
 ROI_ALIGN_BF16 = _os.environ.get("HD_ROI_ALIGN_BF16", "0") == "1"
+STATIC_FEATURES = _os.environ.get("HD_STATIC_FEATURES", "1") == "1"       # feature maps = the backbone engine's own buffers (no clones)
 PER_LEVEL_NMS = _os.environ.get("HD_PER_LEVEL_NMS", "1") == "1"     # proposal NMS as (image, level) problems (see _filter_nms_static)
 _STATIC_PROGRAMS = {}
 
@@ -1542,6 +1543,18 @@ def _assert_no_degenerate_boxes(targets):
     _DEFERRED_CHECKS.append((event, flag, fail))
 
 
+def _backbone_features(model, x):
+    bb = model.backbone
+    if STATIC_FEATURES and isinstance(bb, FrozenBackbone):
+        prev = getattr(bb, "static_outputs", False)
+        bb.static_outputs = True
+        try:
+            return bb(x)
+        finally:
+            bb.static_outputs = prev
+    return bb(x)
+
+
 def eval_forward_fasterrcnn(model, images, targets, train_det=False, model_name="fasterrcnn"):
     if not train_det and model.training:                 # (Module.eval() walks every sub-module: only when the mode changes)
         model.eval()
@@ -1553,7 +1566,8 @@ def eval_forward_fasterrcnn(model, images, targets, train_det=False, model_name=
     if images.tensors.is_cuda:
         targets_event = torch.cuda.Event()
         targets_event.record()
-    features = model.backbone(images.tensors)
+    # the feature maps do not leave this function: the backbone may hand out its own static buffers (no 280 MB of clones)
+    features = _backbone_features(model, images.tensors)
     if isinstance(features, torch.Tensor):
         features = OrderedDict([("0", features)])
     static = _static_tail_ok(model, features)
@@ -1744,7 +1758,7 @@ def eval_forward_retinanet(model, images, targets, train_det=False, model_name="
     original_image_sizes = [tuple(img.shape[-2:]) for img in images]
     images, targets = model.transform(images, targets)
     _assert_no_degenerate_boxes(targets)                  # src/utils/eval_forward_retinanet.py "Check for degenerate boxes"
-    features = model.backbone(images.tensors)
+    features = _backbone_features(model, images.tensors)
     if isinstance(features, torch.Tensor):
         features = OrderedDict([("0", features)])
     features = list(features.values())
