@@ -1279,48 +1279,80 @@ __global__ void sigmoid_bwd_pack_kernel(const float* __restrict__ dhal, const fl
 // -------------------------------------------------------------------------------------------------
 // detector input transform (fp32 NCHW)
 // -------------------------------------------------------------------------------------------------
-// grid (ceil(wo / 256), ho, n * c): the row / plane of a block are uniform, no per-element divisions (the flat grid-stride form
-// spent its time in 64-bit index arithmetic: 59 us for 39 MB)
+// grid (ceil(wo / 1024), ceil(ho / 4), n * c): four output pixels per thread (one 16-byte store when the row allows), four
+// rows per block; row / plane are uniform per block, no per-element divisions (the flat grid-stride form spent its time in
+// 64-bit index arithmetic: 59 us for 39 MB)
 __global__ void __launch_bounds__(kEwThreads) resize_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int c, int hi, int wi,
                                                                 int ho, int wo, float sh, float sw, const float* mean, const float* stdv) {
     pdl_trigger();
     pdl_wait();
-    const int ow = blockIdx.x * blockDim.x + threadIdx.x, oh = blockIdx.y, bc = blockIdx.z;
-    if (ow >= wo) return;
+    const int ow0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, bc = blockIdx.z;
+    if (ow0 >= wo) return;
     const int ch = bc % c;
-    const int ih = nearest_src(oh, sh, hi), iw = nearest_src(ow, sw, wi);
-    float v = __ldg(x + (static_cast<size_t>(bc) * hi + ih) * wi + iw);
-    if (mean) v = (v - mean[ch]) / stdv[ch];
-    y[(static_cast<size_t>(bc) * ho + oh) * wo + ow] = v;
+    const float m = mean ? mean[ch] : 0.f, sd = mean ? stdv[ch] : 1.f;
+    int iw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) iw[j] = nearest_src(min(ow0 + j, wo - 1), sw, wi);
+    for (int r = 0; r < 4; ++r) {
+        const int oh = blockIdx.y * 4 + r;
+        if (oh >= ho) break;
+        const float* src = x + (static_cast<size_t>(bc) * hi + nearest_src(oh, sh, hi)) * wi;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[j] = __ldg(src + iw[j]);
+            if (mean) v[j] = (v[j] - m) / sd;
+        }
+        float* dst = y + (static_cast<size_t>(bc) * ho + oh) * wo + ow0;
+        if (ow0 + 3 < wo && (wo & 3) == 0) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+        else
+            for (int j = 0; j < 4 && ow0 + j < wo; ++j) dst[j] = v[j];
+    }
 }
 
-// grid (ceil(wi / 256), hi, n * c): gather-sum of the output pixels whose nearest source is (ih, iw)
+// grid (ceil(wi / 1024), ceil(hi / 4), n * c): gather-sum of the output pixels whose nearest source is (ih, iw); four input
+// pixels per thread, four rows per block (same summation order as the scalar form: output rows, then columns)
 __global__ void __launch_bounds__(kEwThreads) resize_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int n, int c, int hi, int wi,
                                                                 int ho, int wo, float sh, float sw, const float* stdv, int accumulate) {
     pdl_trigger();
     pdl_wait();
-    const int iw = blockIdx.x * blockDim.x + threadIdx.x, ih = blockIdx.y, bc = blockIdx.z;
-    if (iw >= wi) return;
+    const int iw0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, bc = blockIdx.z;
+    if (iw0 >= wi) return;
     const int ch = bc % c;
-    int h_lo = static_cast<int>(ih / sh) - 2, w_lo = static_cast<int>(iw / sw) - 2;
-    if (h_lo < 0) h_lo = 0;
-    if (w_lo < 0) w_lo = 0;
-    // output columns that map to iw: a short contiguous run starting at or after w_lo
-    int w0 = w_lo;
-    while (w0 < wo && nearest_src(w0, sw, wi) < iw) ++w0;
-    int w1 = w0;
-    while (w1 < wo && nearest_src(w1, sw, wi) == iw) ++w1;
-    float acc = 0.f;
-    const float* plane = dy + static_cast<size_t>(bc) * ho * wo;
-    for (int oh = h_lo; oh < ho; ++oh) {
-        const int s = nearest_src(oh, sh, hi);
-        if (s < ih) continue;
-        if (s > ih) break;
-        for (int ow = w0; ow < w1; ++ow) acc += __ldg(plane + static_cast<size_t>(oh) * wo + ow);
+    int w0[4], w1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int iw = iw0 + j;
+        int a = static_cast<int>(iw / sw) - 2;
+        if (a < 0) a = 0;
+        while (a < wo && nearest_src(a, sw, wi) < iw) ++a;
+        int b = a;
+        while (b < wo && nearest_src(b, sw, wi) == iw) ++b;
+        w0[j] = a; w1[j] = iw < wi ? b : a;
     }
-    if (stdv) acc /= stdv[ch];
-    const size_t o = (static_cast<size_t>(bc) * hi + ih) * wi + iw;
-    dx[o] = accumulate ? dx[o] + acc : acc;
+    const float* plane = dy + static_cast<size_t>(bc) * ho * wo;
+    for (int r = 0; r < 4; ++r) {
+        const int ih = blockIdx.y * 4 + r;
+        if (ih >= hi) break;
+        int h0 = static_cast<int>(ih / sh) - 2;
+        if (h0 < 0) h0 = 0;
+        while (h0 < ho && nearest_src(h0, sh, hi) < ih) ++h0;
+        int h1 = h0;
+        while (h1 < ho && nearest_src(h1, sh, hi) == ih) ++h1;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int oh = h0; oh < h1; ++oh) {
+            const float* row = plane + static_cast<size_t>(oh) * wo;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                for (int ow = w0[j]; ow < w1[j]; ++ow) acc[j] += __ldg(row + ow);
+        }
+        float* o = dx + (static_cast<size_t>(bc) * hi + ih) * wi + iw0;
+        for (int j = 0; j < 4 && iw0 + j < wi; ++j) {
+            float a = acc[j];
+            if (stdv) a /= stdv[ch];
+            o[j] = accumulate ? o[j] + a : a;
+        }
+    }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1663,7 +1695,8 @@ extern "C" int hd_resize_nearest_fwd(const float* x, float* y, int n, int c, int
     HD_CHECK_ARG(x && y && n > 0 && c > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0 && ((mean == nullptr) == (stdv == nullptr)));
     const float sh = static_cast<float>(hi) / static_cast<float>(ho), sw = static_cast<float>(wi) / static_cast<float>(wo);
     HD_CHECK_ARG(ho <= 65535 && n * c <= 65535);
-    HD_CUDA_OK(hd::launch(resize_fwd_kernel, dim3((wo + kEwThreads - 1) / kEwThreads, ho, n * c), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), x, y, n, c, hi, wi, ho, wo, sh, sw, mean, stdv));
+    HD_CHECK_ARG((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+    HD_CUDA_OK(hd::launch(resize_fwd_kernel, dim3((wo + 4 * kEwThreads - 1) / (4 * kEwThreads), (ho + 3) / 4, n * c), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), x, y, n, c, hi, wi, ho, wo, sh, sw, mean, stdv));
     HD_LAUNCH_OK();
     return HD_OK;
 }
@@ -1673,7 +1706,7 @@ extern "C" int hd_resize_nearest_bwd(const float* dy, float* dx, int n, int c, i
     HD_CHECK_ARG(dy && dx && n > 0 && c > 0 && hi > 0 && wi > 0 && ho > 0 && wo > 0);
     const float sh = static_cast<float>(hi) / static_cast<float>(ho), sw = static_cast<float>(wi) / static_cast<float>(wo);
     HD_CHECK_ARG(hi <= 65535 && n * c <= 65535);
-    HD_CUDA_OK(hd::launch(resize_bwd_kernel, dim3((wi + kEwThreads - 1) / kEwThreads, hi, n * c), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), dy, dx, n, c, hi, wi, ho, wo, sh, sw, stdv, accumulate));
+    HD_CUDA_OK(hd::launch(resize_bwd_kernel, dim3((wi + 4 * kEwThreads - 1) / (4 * kEwThreads), (hi + 3) / 4, n * c), dim3(kEwThreads), 0, static_cast<cudaStream_t>(st), dy, dx, n, c, hi, wi, ho, wo, sh, sw, stdv, accumulate));
     HD_LAUNCH_OK();
     return HD_OK;
 }
