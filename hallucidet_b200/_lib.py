@@ -145,6 +145,7 @@ PROTOTYPES = {
     "hd_rpn_loss": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p,
                     c_void_p, c_void_p],
     "hd_rpn_concat_preds": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p],
+    "hd_unpack_blocks": [c_int, c_int, c_int],
     "hd_sample_balanced_workspace_bytes": [c_int],
     "hd_sample_balanced": [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_uint64, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_void_p, ctypes.c_int64, c_void_p],

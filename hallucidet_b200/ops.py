@@ -323,7 +323,7 @@ def unpack_table(entries, device):
     descs, first = [], 0
     for dw, g, cout, cin, k, tap_stride, row_stride in entries:
         d = _lib.HdUnpackDesc(dw.data_ptr(), g.data_ptr(), cout, cin, k * k, tap_stride, row_stride, first, 1.0, 0)
-        d._blocks = multi_blocks(cout * cin * k * k)
+        d._blocks = int(_lib.load().hd_unpack_blocks(cout, cin, k * k))     # one block = whole output-channel rows
         d._key = g.data_ptr()
         first += d._blocks
         descs.append(d)

@@ -124,7 +124,7 @@ int hd_unpack_wgrad(const float* dw_packed, float* grad_oihw, int cout, int cin,
 
 /* Whole-network variants of the two calls above: one launch for every layer.  The descriptor tables live in DEVICE
  * memory; first_block is the running sum, over the preceding layers, of hd_pack_blocks(desc) for packing and of
- * hd_multi_blocks(cout*cin*taps) for unpacking; total_blocks is the grand total. */
+ * hd_unpack_blocks(cout, cin, taps) for unpacking; total_blocks is the grand total. */
 typedef struct hd_pack_desc {
     const float* w;       /* fp32 OIHW master weight */
     const float* scale;   /* optional per-cout scale (folded BN) */
@@ -165,6 +165,7 @@ typedef struct hd_unpack_desc {
 int hd_multi_blocks(int64_t elements);
 int hd_pack_blocks(const hd_pack_desc* desc_host);   /* blocks one layer occupies in hd_pack_conv_weights (for first_block) */
 int hd_pack_conv_weights(const hd_pack_desc* descs_dev, int n_layers, int total_blocks, hd_stream stream);
+int hd_unpack_blocks(int cout, int cin, int taps);     /* blocks one layer occupies in hd_unpack_wgrads (for first_block) */
 int hd_unpack_wgrads(const hd_unpack_desc* descs_dev, int n_layers, int total_blocks, hd_stream stream);
 /* The optimizer tail in one pass over the parameters: hd_pack_conv_weights whose tiled layers ALSO apply
  * clip + Adam to the fp32 master weight as they read it (p, m, v written back, then both bf16 operand layouts from the new
