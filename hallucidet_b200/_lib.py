@@ -146,6 +146,10 @@ PROTOTYPES = {
                     c_void_p, c_void_p],
     "hd_rpn_concat_preds": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p],
     "hd_unpack_blocks": [c_int, c_int, c_int],
+    "hd_rpn_assign_targets": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p],
+    "hd_rpn_decode_selected": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_float, c_float, c_float,
+                               c_float, c_void_p, c_void_p, c_void_p, c_void_p],
     "hd_sample_balanced_workspace_bytes": [c_int],
     "hd_sample_balanced": [c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.c_uint64, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_void_p, ctypes.c_int64, c_void_p],

@@ -172,11 +172,168 @@ __global__ void __launch_bounds__(256) rpn_concat_kernel(const PredLevels L, int
     }
 }
 
+// RegionProposalNetwork.assign_targets_to_anchors + BoxCoder.encode (TV rpn.py:190-229, _utils.py:139-160) for the whole
+// batch: box_iou(gt, anchors), Matcher WITH low-quality matches (every anchor that attains a ground-truth box's best IoU gets
+// its plain arg-max back), labels 1 / 0 / -1 and the regression target of every anchor -- two launches instead of ~85
+// element-wise ones over [B, G, A] tensors (they run on a side stream next to the backbone's persistent kernels, where every
+// small launch has to wait for a gap: the chain used to finish AFTER the proposal filter it is supposed to hide under).
+// Pass 1: per ground-truth box the best IoU over all anchors (bit pattern maximum: IoUs are >= 0); pass 2: the assignment.
+__device__ __forceinline__ float iou_rn(const float4 q, float area_q, const float4 p, float area_p) {
+    const float w = fmaxf(__fsub_rn(fminf(q.z, p.z), fmaxf(q.x, p.x)), 0.f);
+    const float h = fmaxf(__fsub_rn(fminf(q.w, p.w), fmaxf(q.y, p.y)), 0.f);
+    const float inter = __fmul_rn(w, h);
+    return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_q, area_p), inter));
+}
+
+template <int kPass>
+__global__ void __launch_bounds__(256) rpn_assign_kernel(const float4* __restrict__ anchors, const float4* __restrict__ gt,
+                                                         const unsigned char* __restrict__ gt_present, int B, int A, int G, float low_thr,
+                                                         float high_thr, int allow_low_quality, float wx, float wy, float ww, float wh,
+                                                         unsigned int* __restrict__ highest, float* __restrict__ labels,
+                                                         float4* __restrict__ targets) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float4 s_gt[kMaxGt];
+    __shared__ float s_area[kMaxGt];
+    __shared__ unsigned char s_pres[kMaxGt];
+    __shared__ unsigned int s_hi[kMaxGt];
+    const int b = blockIdx.y;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        const float4 q = gt[b * G + g];
+        s_gt[g] = q;
+        s_area[g] = box_area_rn(q.x, q.y, q.z, q.w);
+        s_pres[g] = gt_present[b * G + g];
+        s_hi[g] = kPass == 1 ? 0u : highest[b * G + g];
+    }
+    __syncthreads();
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = a < A;
+    const float4 p = live ? anchors[a] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float area_p = box_area_rn(p.x, p.y, p.z, p.w);
+    if (kPass == 1) {
+        for (int g = 0; g < G; ++g) {
+            if (!s_pres[g]) continue;                                    // (uniform per block)
+            unsigned int v = live ? __float_as_uint(iou_rn(s_gt[g], s_area[g], p, area_p)) : 0u;
+            for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+            if ((threadIdx.x & 31) == 0) atomicMax(&s_hi[g], v);
+        }
+        __syncthreads();
+        for (int g = threadIdx.x; g < G; g += blockDim.x)
+            if (s_pres[g]) atomicMax(&highest[b * G + g], s_hi[g]);
+        return;
+    }
+    if (!live) return;
+    float best = 0.f;
+    int best_g = 0;
+    bool restore = false;
+    for (int g = 0; g < G; ++g) {
+        float v = -1.f;
+        if (s_pres[g]) {
+            v = iou_rn(s_gt[g], s_area[g], p, area_p);
+            restore = restore || __float_as_uint(v) == s_hi[g];        // attains this box's best IoU (exact equality, as torch)
+        }
+        if (g == 0 || v > best) { best = v; best_g = g; }
+    }
+    int m = best_g;
+    if (best < low_thr) m = -1;
+    else if (best < high_thr) m = -2;
+    if (allow_low_quality && restore) m = best_g;
+    const long idx = static_cast<long>(b) * A + a;
+    labels[idx] = m >= 0 ? 1.f : (m == -2 ? -1.f : 0.f);
+    // regression target against the matched box (clamped index 0 for unmatched anchors, as torchvision gathers it)
+    const float4 r = s_gt[m < 0 ? 0 : m];
+    const float ex_w = __fsub_rn(p.z, p.x), ex_h = __fsub_rn(p.w, p.y);
+    const float ex_cx = __fadd_rn(p.x, __fmul_rn(0.5f, ex_w)), ex_cy = __fadd_rn(p.y, __fmul_rn(0.5f, ex_h));
+    const float gt_w = __fsub_rn(r.z, r.x), gt_h = __fsub_rn(r.w, r.y);
+    const float gt_cx = __fadd_rn(r.x, __fmul_rn(0.5f, gt_w)), gt_cy = __fadd_rn(r.y, __fmul_rn(0.5f, gt_h));
+    float4 t;
+    t.x = __fdiv_rn(__fmul_rn(wx, __fsub_rn(gt_cx, ex_cx)), ex_w);
+    t.y = __fdiv_rn(__fmul_rn(wy, __fsub_rn(gt_cy, ex_cy)), ex_h);
+    t.z = __fmul_rn(ww, logf(__fdiv_rn(gt_w, ex_w)));
+    t.w = __fmul_rn(wh, logf(__fdiv_rn(gt_h, ex_h)));
+    targets[idx] = t;
+}
+
+// The RPN proposal filter's element-wise front end for the SELECTED candidates only: torchvision decodes all anchors
+// (BoxCoder.decode_single, TV models/detection/_utils.py:188-226), then gathers the per-level top-k, applies sigmoid, clips to
+// the image and tests size / score (TV rpn.py:263-276) -- ~45 launches, 25 of them over every anchor.  The operations are
+// element-wise, so decoding only the gathered rows gives the same bits (same fp32 operations in the same order, no FMA).
+__global__ void __launch_bounds__(256) rpn_decode_selected_kernel(const float* __restrict__ objectness, const float4* __restrict__ deltas,
+                                                                  const float4* __restrict__ anchors, const long long* __restrict__ idx,
+                                                                  int B, int A, int M, float inv_wx, float inv_wy, float inv_ww, float inv_wh,
+                                                                  float xform_clip, float img_w, float img_h, float min_size, float score_thresh,
+                                                                  float4* __restrict__ boxes, float* __restrict__ scores,
+                                                                  unsigned char* __restrict__ valid) {
+    pdl_trigger();
+    pdl_wait();
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= B * M) return;
+    const int b = q / M;
+    const long long a = idx[q];
+    const float4 an = anchors[a], d = deltas[static_cast<long>(b) * A + a];
+    const float w = __fsub_rn(an.z, an.x), h = __fsub_rn(an.w, an.y);
+    const float cx = __fadd_rn(an.x, __fmul_rn(0.5f, w)), cy = __fadd_rn(an.y, __fmul_rn(0.5f, h));
+    const float dx = __fmul_rn(d.x, inv_wx), dy = __fmul_rn(d.y, inv_wy);
+    const float dw = fminf(__fmul_rn(d.z, inv_ww), xform_clip), dh = fminf(__fmul_rn(d.w, inv_wh), xform_clip);
+    const float pcx = __fadd_rn(__fmul_rn(dx, w), cx), pcy = __fadd_rn(__fmul_rn(dy, h), cy);
+    const float pw = __fmul_rn(expf(dw), w), ph = __fmul_rn(expf(dh), h);
+    const float hw = __fmul_rn(0.5f, pw), hh = __fmul_rn(0.5f, ph);
+    float x1 = __fsub_rn(pcx, hw), y1 = __fsub_rn(pcy, hh), x2 = __fadd_rn(pcx, hw), y2 = __fadd_rn(pcy, hh);
+    x1 = fminf(fmaxf(x1, 0.f), img_w); x2 = fminf(fmaxf(x2, 0.f), img_w);          // clip_boxes_to_image
+    y1 = fminf(fmaxf(y1, 0.f), img_h); y2 = fminf(fmaxf(y2, 0.f), img_h);
+    const float sc = __fdiv_rn(1.f, __fadd_rn(1.f, expf(-objectness[static_cast<long>(b) * A + a])));
+    boxes[q] = make_float4(x1, y1, x2, y2);
+    scores[q] = sc;
+    valid[q] = (__fsub_rn(x2, x1) >= min_size && __fsub_rn(y2, y1) >= min_size && sc >= score_thresh) ? 1 : 0;
+}
+
 }  // namespace
 
 }  // namespace hd
 
 using namespace hd;
+
+extern "C" int hd_rpn_assign_targets(const float* anchors, const float* gt, const uint8_t* gt_present, int batch, int n_anchors, int n_gt,
+                                     float low_threshold, float high_threshold, int allow_low_quality, const float* coder_weights,
+                                     void* highest_ws, float* labels, float* regression_targets, hd_stream stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    HD_CHECK_ARG(anchors != nullptr && gt != nullptr && gt_present != nullptr && coder_weights != nullptr && highest_ws != nullptr);
+    HD_CHECK_ARG(labels != nullptr && regression_targets != nullptr && batch > 0 && n_anchors > 0 && n_gt >= 1 && n_gt <= kMaxGt);
+    HD_CHECK_ARG((reinterpret_cast<uintptr_t>(anchors) & 15) == 0 && (reinterpret_cast<uintptr_t>(gt) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(regression_targets) & 15) == 0);
+    HD_CUDA_OK(cudaMemsetAsync(highest_ws, 0, static_cast<size_t>(batch) * n_gt * sizeof(unsigned int), stream));
+    const dim3 grid((n_anchors + 255) / 256, batch);
+    HD_CUDA_OK(hd::launch(rpn_assign_kernel<1>, grid, dim3(256), 0, stream, reinterpret_cast<const float4*>(anchors),
+                          reinterpret_cast<const float4*>(gt), gt_present, batch, n_anchors, n_gt, low_threshold, high_threshold,
+                          allow_low_quality, coder_weights[0], coder_weights[1], coder_weights[2], coder_weights[3],
+                          static_cast<unsigned int*>(highest_ws), labels, reinterpret_cast<float4*>(regression_targets)));
+    HD_CUDA_OK(hd::launch(rpn_assign_kernel<2>, grid, dim3(256), 0, stream, reinterpret_cast<const float4*>(anchors),
+                          reinterpret_cast<const float4*>(gt), gt_present, batch, n_anchors, n_gt, low_threshold, high_threshold,
+                          allow_low_quality, coder_weights[0], coder_weights[1], coder_weights[2], coder_weights[3],
+                          static_cast<unsigned int*>(highest_ws), labels, reinterpret_cast<float4*>(regression_targets)));
+    HD_CUDA_OK(cudaPeekAtLastError());
+    return HD_OK;
+}
+
+extern "C" int hd_rpn_decode_selected(const float* objectness, const float* deltas, const float* anchors, const int64_t* idx, int batch,
+                                      int anchors_per_image, int selected, const float* coder_weights, float xform_clip, float img_w,
+                                      float img_h, float min_size, float score_thresh, float* boxes, float* scores, uint8_t* valid,
+                                      hd_stream stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    HD_CHECK_ARG(objectness != nullptr && deltas != nullptr && anchors != nullptr && idx != nullptr && coder_weights != nullptr);
+    HD_CHECK_ARG(boxes != nullptr && scores != nullptr && valid != nullptr && batch > 0 && anchors_per_image > 0 && selected > 0);
+    HD_CHECK_ARG((reinterpret_cast<uintptr_t>(deltas) & 15) == 0 && (reinterpret_cast<uintptr_t>(anchors) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(boxes) & 15) == 0);
+    const long total = static_cast<long>(batch) * selected;
+    // ATen divides a tensor by a host scalar as a multiplication by its fp32 reciprocal
+    HD_CUDA_OK(hd::launch(rpn_decode_selected_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, objectness,
+                          reinterpret_cast<const float4*>(deltas), reinterpret_cast<const float4*>(anchors),
+                          reinterpret_cast<const long long*>(idx), batch, anchors_per_image, selected, 1.0f / coder_weights[0],
+                          1.0f / coder_weights[1], 1.0f / coder_weights[2], 1.0f / coder_weights[3], xform_clip, img_w, img_h, min_size,
+                          score_thresh, reinterpret_cast<float4*>(boxes), scores, valid));
+    HD_CUDA_OK(cudaPeekAtLastError());
+    return HD_OK;
+}
 
 // direction 0: preds -> (objectness, deltas); 1: (objectness, deltas) -> preds (every channel written, padding = 0)
 extern "C" int hd_rpn_concat_preds(void* const* preds, const int* hw, const int* channel_pitch, int levels, int batch, int anchors_per_pixel,

@@ -409,6 +409,36 @@ def filter_proposals_static(rpn, proposals, objectness, image_shapes, num_anchor
     return _StaticProposals(out, n)
 
 
+_LEVEL_IDS = {}
+
+
+def filter_proposals_static_fused(rpn, deltas, anchors, objectness, image_shapes, num_anchors_per_level):
+    """``filter_proposals_static`` from the raw box deltas: the per-level top-k is taken on the objectness logits first, and only
+    those candidates are decoded / clipped / tested, by one launch (ops.rpn_decode_selected) -- torchvision decodes all anchors
+    and then gathers; the operations are element-wise, so the selected rows are bit-identical.  Needs one anchor set shared by
+    the images of the batch and one image size (what the detector transform produces)."""
+    num_images = len(anchors)
+    device = deltas.device
+    objectness = objectness.detach().reshape(num_images, -1)
+    top_n_idx = rpn._get_top_n_idx(objectness, num_anchors_per_level).contiguous()
+    per_level = [min(rpn.pre_nms_top_n(), n) for n in num_anchors_per_level]
+    key = (tuple(per_level), num_images, str(device))
+    levels = _LEVEL_IDS.get(key)
+    if levels is None:
+        if len(_LEVEL_IDS) > 8:
+            _LEVEL_IDS.clear()
+        one = torch.cat([torch.full((n,), i, dtype=torch.int64, device=device) for i, n in enumerate(per_level)], 0)
+        levels = _LEVEL_IDS[key] = one.reshape(1, -1).expand(num_images, -1).contiguous()
+    coder = rpn.box_coder
+    with torch.no_grad():
+        boxes, scores, valid = ops.rpn_decode_selected(objectness.contiguous(), deltas.detach().contiguous(), anchors[0].contiguous(),
+                                                       top_n_idx, coder.weights, coder.bbox_xform_clip, image_shapes[0], rpn.min_size,
+                                                       rpn.score_thresh)
+        out, n = _filter_nms_static(boxes, scores, levels, valid, rpn.nms_thresh, rpn.post_nms_top_n(),
+                                    group_sizes=per_level if PER_LEVEL_NMS else None)
+    return _StaticProposals(out, n)
+
+
 def filter_proposals_batched(rpn, proposals, objectness, image_shapes, num_anchors_per_level):
     return _resolve(filter_proposals_batched_begin(rpn, proposals, objectness, image_shapes, num_anchors_per_level))[0]
 
@@ -644,6 +674,19 @@ def _sampled_rows(sampled, counts, per_image):
     n_drawn = counts[:, 2:4].sum()
     valid = torch.arange(S, device=sampled.device) < n_drawn
     return flat, valid, n_drawn
+
+
+def rpn_targets_static(rpn, anchors, targets):
+    """Anchor labels [B, A] and regression targets [B * A, 4] of the batch: two launches (ops.rpn_assign_targets, bit-identical)
+    when the images share one anchor set, else ``assign_targets_to_anchors_batched`` + ``encode_boxes``."""
+    gt, present, _ = _padded_gt(targets, targets[0]["boxes"].dtype)
+    m = rpn.proposal_matcher
+    if (FUSED_RPN_TARGETS and gt.dtype == torch.float32 and anchors[0].dtype == torch.float32 and gt.shape[1] <= 64
+            and all(a.data_ptr() == anchors[0].data_ptr() or a.shape == anchors[0].shape for a in anchors)):
+        return ops.rpn_assign_targets(anchors[0].contiguous(), gt.contiguous(), present.contiguous(), m.low_threshold, m.high_threshold,
+                                      m.allow_low_quality_matches, rpn.box_coder.weights)
+    labels, matched_gt_boxes = assign_targets_to_anchors_batched(rpn, anchors, targets)
+    return labels, _encode_single(rpn.box_coder, matched_gt_boxes.reshape(-1, 4), torch.cat(anchors, dim=0))
 
 
 def rpn_compute_loss_static(rpn, objectness, pred_bbox_deltas, labels, regression_targets, sampled, counts):
@@ -1160,6 +1203,8 @@ FLAT_RPN_PREDS = _os.environ.get("HD_FLAT_RPN_PREDS", "1") == "1"         # RPN 
 # more (loss_classifier moves by 5e-5 relative) for a 0.4 % gain.
 ROI_ALIGN_BF16 = _os.environ.get("HD_ROI_ALIGN_BF16", "0") == "1"
 STATIC_FEATURES = _os.environ.get("HD_STATIC_FEATURES", "1") == "1"       # feature maps = the backbone engine's own buffers (no clones)
+FUSED_PROPOSAL_DECODE = _os.environ.get("HD_FUSED_PROPOSAL_DECODE", "1") == "1"   # decode only the per-level top-k (one launch)
+FUSED_RPN_TARGETS = _os.environ.get("HD_FUSED_RPN_TARGETS", "1") == "1"     # anchor target assignment + encode as two launches
 PER_LEVEL_NMS = _os.environ.get("HD_PER_LEVEL_NMS", "1") == "1"     # proposal NMS as (image, level) problems (see _filter_nms_static)
 _STATIC_PROGRAMS = {}
 
@@ -1272,6 +1317,9 @@ def rpn_eval(model, images, features, targets, targets_event=None, static=False)
     use_batched = (batched and (flat_obj if flat_obj is not None else objectness[0]).dtype == torch.float32 and _batched_ok(pre_nms)
                    and all(a.shape == anchors[0].shape for a in anchors))
     pend_boxes = None
+    fused_decode = bool(static and use_batched and FUSED_PROPOSAL_DECODE and features[0].dtype == torch.float32
+                        and anchors[0].dtype == torch.float32
+                        and all(tuple(sz) == tuple(images.image_sizes[0]) for sz in images.image_sizes))
     if use_batched and static_preds and GRAPH_PROPOSAL_FILTER and not anchors_fresh:
         # The predictor outputs live in the static buffers of the head's CUDA-graph program and the anchors are cached: the whole
         # gradient-free, static-shape chain concat -> decode -> per-level top-k -> clip / filter -> sort -> NMS (~45 launches) is
@@ -1284,6 +1332,8 @@ def rpn_eval(model, images, features, targets, targets_event=None, static=False)
 
         def program():
             o2, d2 = (obj_lv[0], del_lv[0]) if flat_obj is not None else concat_box_prediction_layers(obj_lv, del_lv)
+            if static and fused_decode:
+                return filter_proposals_static_fused(model.rpn, d2, anchors, o2, image_sizes, num_anchors_per_level)
             props = _decode(model.rpn.box_coder, d2, anchors).view(num_images, -1, 4)
             if static:
                 return filter_proposals_static(model.rpn, props, o2, image_sizes, num_anchors_per_level)
@@ -1296,6 +1346,10 @@ def rpn_eval(model, images, features, targets, targets_event=None, static=False)
         objectness, pred_bbox_deltas = flat_obj, flat_deltas
     else:
         objectness, pred_bbox_deltas = concat_box_prediction_layers(objectness, pred_bbox_deltas)
+    if pend_boxes is None and fused_decode:
+        with torch.no_grad():
+            pend_boxes = filter_proposals_static_fused(model.rpn, pred_bbox_deltas.detach(), anchors, objectness, images.image_sizes,
+                                                       num_anchors_per_level)
     if pend_boxes is None:
         proposals = _decode(model.rpn.box_coder, pred_bbox_deltas.detach(), anchors)
         proposals = proposals.view(num_images, -1, 4)
@@ -1321,8 +1375,7 @@ def rpn_eval(model, images, features, targets, targets_event=None, static=False)
             side.wait_event(targets_event)
             sampler = model.rpn.fg_bg_sampler
             with torch.cuda.stream(side), torch.no_grad():
-                labels, matched_gt_boxes = assign_targets_to_anchors_batched(model.rpn, anchors, targets)
-                regression_targets = _encode_single(model.rpn.box_coder, matched_gt_boxes.reshape(-1, 4), torch.cat(anchors, dim=0))
+                labels, regression_targets = rpn_targets_static(model.rpn, anchors, targets)
                 sampled, counts = ops.sample_balanced(labels.contiguous(), sampler.batch_size_per_image, sampler.positive_fraction)
                 done = torch.cuda.Event()
                 done.record(side)

@@ -98,6 +98,7 @@ class _Tower:
         return dx
 
 
+_GRAD_ENABLED_AT_CALL = [False]  # torch.is_grad_enabled() where _TowerFunction.apply was called (see _tower_apply)
 USE_CUDA_GRAPH = False          # set by the caller (detection.py: when the backbone runs its kernel programs as CUDA graphs)
 
 
@@ -158,7 +159,8 @@ class _TowerFunction(torch.autograd.Function):
         ctx.shapes = [tuple(x.shape) for x in feats_bf16]
         ctx.need = [f.requires_grad for f in feats]
         ctx.program = None
-        if USE_CUDA_GRAPH and any(ctx.need) and torch.is_grad_enabled():
+        # (grad mode is always off INSIDE Function.forward: the caller's grad mode travels in _GRAD_ENABLED_AT_CALL)
+        if USE_CUDA_GRAPH and any(ctx.need) and _GRAD_ENABLED_AT_CALL[0]:
             key = tuple(x.data_ptr() for x in feats_bf16)
             prog = tower.programs.get(key)
             if prog is None:
@@ -186,6 +188,11 @@ class _TowerFunction(torch.autograd.Function):
                 continue
             grads.append(ctx.tower.backward(shape, hidden, dp).permute(0, 3, 1, 2))      # logical NCHW, channels-last strides
         return (None, None) + tuple(grads)
+
+
+def _tower_apply(tower, feats_bf16, *feats):
+    _GRAD_ENABLED_AT_CALL[0] = torch.is_grad_enabled()
+    return _TowerFunction.apply(tower, feats_bf16, *feats)
 
 
 def _frozen(*params):
@@ -229,7 +236,7 @@ def rpn_head_forward(head, features, features_bf16, return_static=False):
     tower = rpn_head_tower(head)
     a = head.cls_logits.out_channels
     feats_bf16 = list(features_bf16)
-    preds = _TowerFunction.apply(tower, feats_bf16, *features)
+    preds = _tower_apply(tower, feats_bf16, *features)
     logits, bbox = [], []
     for p in preds:
         nchw = p.permute(0, 3, 1, 2)
@@ -270,7 +277,7 @@ def rpn_head_forward_flat(head, features, features_bf16):
     tower = rpn_head_tower(head)
     a = head.cls_logits.out_channels
     feats_bf16 = list(features_bf16)
-    preds = _TowerFunction.apply(tower, feats_bf16, *features)
+    preds = _tower_apply(tower, feats_bf16, *features)
     prog = tower.programs.get(tuple(x.data_ptr() for x in feats_bf16))
     static = bool(prog is not None and preds[0].data_ptr() == prog.pred[0].data_ptr())
     out = None
@@ -308,7 +315,7 @@ def retinanet_head_forward(head, features, features_bf16):
     k = head.classification_head.num_classes
     outs = {}
     for name, tower, last in (("cls_logits", towers[0], k), ("bbox_regression", towers[1], 4)):
-        preds = _TowerFunction.apply(tower, list(features_bf16), *features)
+        preds = _tower_apply(tower, list(features_bf16), *features)
         per_level = [p[..., :tower.pred_c].reshape(p.shape[0], -1, last) for p in preds]
         outs[name] = torch.cat(per_level, dim=1)
     return outs

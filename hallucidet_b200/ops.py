@@ -772,6 +772,46 @@ def rpn_concat_preds(preds, a, objectness, deltas, backward=False):
     LAUNCHES += 1
 
 
+def rpn_assign_targets(anchors, gt, gt_present, low_threshold, high_threshold, allow_low_quality, coder_weights):
+    """hd_rpn_assign_targets: anchors [A, 4] (shared by the batch), gt [B, G, 4] padded + presence mask -> (labels [B, A] float32:
+    1 / 0 / -1, regression_targets [B * A, 4]); box_iou + Matcher + encode_boxes, bit-identical to the operator chain."""
+    global LAUNCHES
+    A, (B, G) = anchors.shape[0], gt.shape[:2]
+    assert anchors.dtype == gt.dtype == torch.float32 and anchors.is_contiguous() and gt.is_contiguous()
+    assert gt_present.dtype == torch.bool and gt_present.is_contiguous() and 1 <= G <= 64
+    labels = torch.empty(B, A, device=anchors.device)
+    targets = torch.empty(B * A, 4, device=anchors.device)
+    ws = torch.empty(B * G, dtype=torch.int32, device=anchors.device)
+    w = (ctypes.c_float * 4)(*[float(x) for x in coder_weights])
+    with _Timed("rpn_assign_targets"):
+        check(_lib.load().hd_rpn_assign_targets(_ptr(anchors), _ptr(gt), _ptr(gt_present), B, A, G, float(low_threshold),
+                                                float(high_threshold), int(bool(allow_low_quality)), w, _ptr(ws), _ptr(labels),
+                                                _ptr(targets), _stream()), "hd_rpn_assign_targets")
+    LAUNCHES += 2
+    return labels, targets
+
+
+def rpn_decode_selected(objectness, deltas, anchors, idx, coder_weights, xform_clip, image_size, min_size, score_thresh):
+    """hd_rpn_decode_selected: decode + sigmoid + clip + size / score tests for the candidates ``idx`` [B, M] only.
+    objectness [B, A] logits, deltas [B * A, 4], anchors [A, 4] -> (boxes [B, M, 4], scores [B, M], valid [B, M] bool)."""
+    global LAUNCHES
+    B, M = idx.shape
+    A = anchors.shape[0]
+    assert objectness.dtype == deltas.dtype == anchors.dtype == torch.float32 and idx.dtype == torch.int64
+    assert objectness.is_contiguous() and deltas.is_contiguous() and anchors.is_contiguous() and idx.is_contiguous()
+    assert objectness.numel() == B * A and deltas.numel() == 4 * B * A
+    boxes = torch.empty(B, M, 4, device=idx.device)
+    scores = torch.empty(B, M, device=idx.device)
+    valid = torch.empty(B, M, dtype=torch.bool, device=idx.device)
+    w = (ctypes.c_float * 4)(*[float(x) for x in coder_weights])
+    with _Timed("rpn_decode_selected"):
+        check(_lib.load().hd_rpn_decode_selected(_ptr(objectness), _ptr(deltas), _ptr(anchors), _ptr(idx), B, A, M, w, float(xform_clip),
+                                                 float(image_size[1]), float(image_size[0]), float(min_size), float(score_thresh),
+                                                 _ptr(boxes), _ptr(scores), _ptr(valid), _stream()), "hd_rpn_decode_selected")
+    LAUNCHES += 1
+    return boxes, scores, valid
+
+
 def fastrcnn_loss(class_logits, box_regression, labels, regression_targets, beta=1 / 9):
     """hd_fastrcnn_loss: (losses [2] = classification, box regression; d/d class_logits; d/d box_regression) in one launch."""
     global LAUNCHES

@@ -343,6 +343,27 @@ int hd_roi_gather_samples(const hd_roi_gather_args* args, hd_stream stream);
 int hd_rpn_concat_preds(void* const* preds, const int* hw, const int* channel_pitch, int levels, int batch, int anchors_per_pixel,
                         float* objectness, float* deltas, int direction, hd_stream stream);
 
+/* ---- RPN anchor targets ----------------------------------------------------------------------------------------------
+ * RegionProposalNetwork.assign_targets_to_anchors + BoxCoder.encode (TV rpn.py:190-229, _utils.py:139-160; reference
+ * src/utils/eval_forward_fasterrcnn.py:93-95) for a batch that shares one anchor set: box_iou(gt, anchors), Matcher with
+ * (allow_low_quality != 0) or without low-quality matches, labels[b][a] = 1 foreground / 0 background / -1 ignored and the
+ * regression target of every anchor against its matched box -- bit-identical to the operator chain.  gt [batch][n_gt][4] padded
+ * (n_gt <= 64), gt_present marks real rows; coder_weights: HOST array of 4; highest_ws: batch * n_gt * 4 bytes of device scratch. */
+int hd_rpn_assign_targets(const float* anchors, const float* gt, const uint8_t* gt_present, int batch, int n_anchors, int n_gt,
+                          float low_threshold, float high_threshold, int allow_low_quality, const float* coder_weights,
+                          void* highest_ws, float* labels, float* regression_targets, hd_stream stream);
+
+/* ---- RPN proposal filter, element-wise front end for the selected candidates ------------------------------------------
+ * BoxCoder.decode (TV models/detection/_utils.py:162-226) + sigmoid + clip_boxes_to_image + the size / score tests of
+ * RegionProposalNetwork.filter_proposals (TV rpn.py:263-276; reference src/utils/eval_forward_fasterrcnn.py:80-84) for the
+ * candidates idx[b][j] (anchor index of image b; the per-level top-k) only -- bit-identical to decoding every anchor first.
+ * objectness [batch][anchors] logits, deltas [batch][anchors][4], anchors [anchors][4] (the same for every image),
+ * coder_weights: HOST array of 4.  boxes [batch][selected][4], scores [batch][selected], valid [batch][selected] bytes. */
+int hd_rpn_decode_selected(const float* objectness, const float* deltas, const float* anchors, const int64_t* idx, int batch,
+                           int anchors_per_image, int selected, const float* coder_weights, float xform_clip, float img_w,
+                           float img_h, float min_size, float score_thresh, float* boxes, float* scores, uint8_t* valid,
+                           hd_stream stream);
+
 /* ---- Detection losses, value and gradient in one launch -------------------------------------------------------------
  * hd_fastrcnn_loss: torchvision roi_heads.fastrcnn_loss (cross-entropy over the sampled proposals, mean; smooth-L1 with
  * `beta` of the matched class's box deltas over the foreground rows, summed, / number of sampled rows) as the reference's

@@ -307,3 +307,44 @@ def test_roi_align_ml_fwd_bf16_equals_fp32_on_widened_maps():
     a = ops.roi_align_ml_fwd(maps32, scales, rois, levels, (7, 7), 2)
     b = ops.roi_align_ml_fwd(maps16, scales, rois, levels, (7, 7), 2)
     assert torch.equal(a, b)
+
+
+def test_fused_proposal_decode_matches_decode_all_then_gather():
+    """filter_proposals_static_fused (top-k first, then ONE launch decoding / clipping / testing only the selected candidates)
+    against filter_proposals_static on BoxCoder.decode of every anchor: identical proposals and counts, bit for bit."""
+    from torchvision.models.detection.image_list import ImageList
+    from hallucidet_b200 import detection as D
+    det, g, anchors, targets = _detector_setup()
+    B = len(anchors)
+    x = torch.rand(B, 3, 128, 160, generator=g).cuda()
+    with torch.no_grad():
+        feats = list(det.backbone(x).values())
+        obj, deltas = det.rpn.head(feats)
+    napl = [o[0].shape[0] * o[0].shape[1] * o[0].shape[2] for o in obj]
+    from torchvision.models.detection.rpn import concat_box_prediction_layers
+    o2, d2 = concat_box_prediction_layers(obj, deltas)
+    d2 = d2 * 3.0                                                   # wider spread of box sizes: clipping / min-size tests bite
+    sizes = [(128, 160)] * B
+    props = D._decode(det.rpn.box_coder, d2, anchors).view(B, -1, 4)
+    a = D.filter_proposals_static(det.rpn, props, o2, sizes, napl)
+    b = D.filter_proposals_static_fused(det.rpn, d2, anchors, o2, sizes, napl)
+    assert torch.equal(a.counts, b.counts) and torch.equal(a.boxes, b.boxes)
+    assert int(a.counts.min()) > 50
+
+
+def test_fused_rpn_targets_match_operator_chain():
+    """hd_rpn_assign_targets against assign_targets_to_anchors (torchvision, per image) + BoxCoder.encode: labels of every anchor
+    and the regression targets of every anchor that has a matched box, bit for bit (one image without ground truth)."""
+    from hallucidet_b200 import detection as D
+    det, g, anchors, targets = _detector_setup()
+    la, ma = det.rpn.assign_targets_to_anchors(anchors, targets)
+    rt = det.rpn.box_coder.encode(ma, anchors)
+    labels, reg = D.rpn_targets_static(det.rpn, anchors, targets)
+    A = anchors[0].shape[0]
+    assert torch.equal(labels, torch.stack(la))
+    assert sum(int((x == 1).sum()) for x in la) > 0 and sum(int((x == -1).sum()) for x in la) > 0
+    reg = reg.view(len(anchors), A, 4)
+    for b in range(len(anchors)):
+        if targets[b]["boxes"].numel() == 0:
+            continue
+        assert torch.equal(reg[b], rt[b])
