@@ -162,6 +162,26 @@ __global__ void __launch_bounds__(256) rpn_concat_kernel(const PredLevels L, int
     const int hw = px - L.first_pixel[l];
     float* p = L.pred[l] + (static_cast<long>(b) * L.hw[l] + hw) * L.cp[l];
     const long o = (static_cast<long>(b) * L.pixels + px) * L.a;
+    if (L.a == 3 && L.cp[l] == 16) {
+        // the stock RPN head (3 anchors per pixel, 15 channels padded to 16): one pixel = four 16-byte words of the map, its
+        // twelve box deltas = three aligned 16-byte words of the flat tensor (48 bytes per pixel)
+        float4* p4 = reinterpret_cast<float4*>(p);
+        float4* d4 = reinterpret_cast<float4*>(deltas + o * 4);
+        if (!kBackward) {
+            const float4 v0 = p4[0], v1 = p4[1], v2 = p4[2], v3 = p4[3];
+            obj[o] = v0.x; obj[o + 1] = v0.y; obj[o + 2] = v0.z;
+            d4[0] = make_float4(v0.w, v1.x, v1.y, v1.z);
+            d4[1] = make_float4(v1.w, v2.x, v2.y, v2.z);
+            d4[2] = make_float4(v2.w, v3.x, v3.y, v3.z);
+        } else {
+            const float4 e0 = d4[0], e1 = d4[1], e2 = d4[2];
+            p4[0] = make_float4(obj[o], obj[o + 1], obj[o + 2], e0.x);
+            p4[1] = make_float4(e0.y, e0.z, e0.w, e1.x);
+            p4[2] = make_float4(e1.y, e1.z, e1.w, e2.x);
+            p4[3] = make_float4(e2.y, e2.z, e2.w, 0.f);
+        }
+        return;
+    }
     if (!kBackward) {
         for (int j = 0; j < L.a; ++j) obj[o + j] = p[j];
         for (int j = 0; j < 4 * L.a; ++j) deltas[o * 4 + j] = p[L.a + j];
