@@ -164,6 +164,12 @@ def test_rpn_head_cuda_graph_program_matches_eager():
                 res[graph] = ([t.detach().clone() for t in lo + bb], [f.grad.clone() for f in f32])
             for a, b in zip(res[False][0] + res[False][1], res[True][0] + res[True][1]):
                 assert torch.equal(a, b), it
+        # the program must really have been selected and captured (its selection once tested the grad mode inside
+        # Function.forward, where it is always off, and silently ran the eager launches instead)
+        tower = heads.rpn_head_tower(head)
+        prog = tower.programs.get(tuple(x.data_ptr() for x in bf16))
+        assert prog is not None and isinstance(prog.graphs.get("fwd"), torch.cuda.CUDAGraph)
+        assert isinstance(prog.graphs.get("bwd"), torch.cuda.CUDAGraph)
     finally:
         heads.USE_CUDA_GRAPH = False
 
