@@ -101,10 +101,10 @@ __device__ void call_info(const SampParams& P, const int* s_cnt, int q, CallInfo
     ci.bits = bits;
     ci.mask = bits >= 64 ? ~0ull : ((1ull << bits) - 1ull);
     ci.range = bits <= 32 ? 0xFFFFFFFFull : ~0ull;
-    if (n_self <= kCap) {
-        ci.thr = ci.mask;
+    const double want = static_cast<double>(ci.k) + 4.0 * sqrt(static_cast<double>(ci.k)) + 32.0;
+    if (n_self <= kCap && static_cast<double>(n_self) <= 1.5 * want) {
+        ci.thr = ci.mask;                        // short row, or most of it is needed anyway: every key is a candidate
     } else {
-        const double want = static_cast<double>(ci.k) + 4.0 * sqrt(static_cast<double>(ci.k)) + 32.0;
         const double t = ldexp(want / nd, bits);
         ci.thr = t >= 18446744073709551615.0 ? ci.mask : static_cast<unsigned long long>(t);
         if (ci.thr > ci.mask) ci.thr = ci.mask;
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(kSelThreads) samp_select_kernel(const SampPara
     // the threshold missed (fewer than k candidates, or more than the list holds): move it and re-scan the whole row here
     int m = s_m;
     while (ci.thr < ci.mask && (m < ci.k || m > kCap)) {
-        if (m < ci.k) ci.thr = ci.thr > (ci.mask >> 1) ? ci.mask - 1ull : ci.thr * 2ull + 1ull;
+        if (m < ci.k) ci.thr = ci.thr > (ci.mask >> 1) ? (ci.n <= kCap ? ci.mask : ci.mask - 1ull) : ci.thr * 2ull + 1ull;
         else ci.thr = ci.thr / 2ull;
         __syncthreads();                       // everyone has read s_m
         if (threadIdx.x == 0) s_m = 0;
@@ -259,12 +259,14 @@ __global__ void __launch_bounds__(kSelThreads) samp_select_kernel(const SampPara
         __syncthreads();
         m = s_m;
     }
-    for (int i = threadIdx.x; i < kCap; i += blockDim.x) s_c[i] = i < m ? gc[i] : Cand{~0ull, ~0u, 0u};
+    int sort_n = 64;                               // power of two >= m: the padding entries sort to the end
+    while (sort_n < m) sort_n <<= 1;
+    for (int i = threadIdx.x; i < sort_n; i += blockDim.x) s_c[i] = i < m ? gc[i] : Cand{~0ull, ~0u, 0u};
     __syncthreads();
     // bitonic sort, ascending by (key, rank): the stable radix sort of the keys restricted to the candidates
-    for (int size = 2; size <= kCap; size <<= 1) {
+    for (int size = 2; size <= sort_n; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int t = threadIdx.x; t < kCap / 2; t += blockDim.x) {
+            for (int t = threadIdx.x; t < sort_n / 2; t += blockDim.x) {
                 const int lo = 2 * t - (t & (stride - 1));
                 const int hi = lo + stride;
                 const bool up = (lo & size) == 0;
