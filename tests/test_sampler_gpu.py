@@ -348,3 +348,22 @@ def test_fused_rpn_targets_match_operator_chain():
         if targets[b]["boxes"].numel() == 0:
             continue
         assert torch.equal(reg[b], rt[b])
+
+
+@pytest.mark.parametrize("B,N,p_pos,p_ign,bs,frac,dtype", [(3, 700, 0.05, 0.1, 64, 0.5, torch.float32), (2, 45000, 0.001, 0.0, 256, 0.5, torch.float32),
+                                                           (4, 50, 0.4, 0.2, 16, 0.25, torch.int64)])
+def test_sample_balanced_matches_the_oracle(B, N, p_pos, p_ign, bs, frac, dtype):
+    """hd_sample_balanced against oracle/randperm_cuda.py (the numpy restatement of torch.randperm's CUDA algorithm, pinned by
+    golden vectors of torch itself): same draws and same generator offset for an explicit (seed, offset) state."""
+    from oracle import randperm_cuda as R
+    ops = _ops()
+    gen = ops.DeviceRng.get(torch.device("cuda", torch.cuda.current_device())).generator()
+    labels = _labels(B, N, p_pos, p_ign, 77, dtype)
+    seed, offset = 20240607, 1024
+    gen.manual_seed(seed)
+    gen.set_offset(offset)
+    got, _ = ops.sample_balanced(labels, bs, frac)
+    ops.DeviceRng.get(labels.device).sync_host()
+    want, after = R.balanced_sample(labels.cpu().numpy(), bs, frac, seed, offset)
+    assert gen.get_offset() == after
+    assert torch.equal(got.cpu(), torch.from_numpy(want))
