@@ -19,6 +19,7 @@ from .unet import Unet
 
 import os as _os
 
+FUSED_LOSS_WEIGHTS = _os.environ.get("HD_FUSED_LOSS_WEIGHTS", "1") == "1"      # weighted loss terms as one stack / multiply / sum
 OVERLAP_ALLREDUCE = _os.environ.get("HD_OVERLAP_ALLREDUCE", "1") != "0"   # bucketed all-reduce underneath the backward pass
 FUSED_OPTIMIZER = _os.environ.get("HD_FUSED_ADAM", "1") != "0"     # clip + Adam + bf16 re-pack as one pass (optim.FusedAdam)
 
@@ -197,13 +198,27 @@ class HalluciDetTrainer(nn.Module):
         if frcnn:
             losses_det["classification"] = losses_det["loss_classifier"]
             losses_det["bbox_regression"] = losses_det["loss_box_reg"]
-        losses_det["bbox_regression"] = losses_det["bbox_regression"] * w["det_regression"]
-        losses_det["classification"] = losses_det["classification"] * w["det_classification"]
-        losses_det["loss_objectness"] = losses_det["loss_objectness"] * w["det_objectness"] if frcnn else 0.0
-        losses_det["loss_rpn_box_reg"] = losses_det["loss_rpn_box_reg"] * w["det_rpn_box_reg"] if frcnn else 0.0
-        loss_det_total = losses_det["bbox_regression"] + losses_det["classification"] + losses_det["loss_objectness"] + \
-            losses_det["loss_rpn_box_reg"]
-        total = loss_det_total + loss_pixel_rgb + loss_pixel_ir
+        names = ("bbox_regression", "classification", "loss_objectness", "loss_rpn_box_reg")
+        if frcnn and FUSED_LOSS_WEIGHTS and all(torch.is_tensor(losses_det[n]) and losses_det[n].is_cuda and losses_det[n].dim() == 0
+                                                 for n in names):
+            # the four weighted terms and their sum as stack -> multiply -> sum (3 launches forward, 1 backward) instead of four
+            # scalar multiplies and three adds each way (train_hallucidet.py:198-207: same terms, same weights)
+            wt = getattr(self, "_loss_weight_tensor", None)
+            key = (w["det_regression"], w["det_classification"], w["det_objectness"], w["det_rpn_box_reg"], str(hal.device))
+            if wt is None or wt[0] != key:
+                wt = self._loss_weight_tensor = (key, torch.tensor(key[:4], dtype=torch.float32, device=hal.device))
+            weighted = torch.stack([losses_det[n] for n in names]) * wt[1]
+            loss_det_total = weighted.sum()
+            for i, n in enumerate(names):
+                losses_det[n] = weighted[i]
+        else:
+            losses_det["bbox_regression"] = losses_det["bbox_regression"] * w["det_regression"]
+            losses_det["classification"] = losses_det["classification"] * w["det_classification"]
+            losses_det["loss_objectness"] = losses_det["loss_objectness"] * w["det_objectness"] if frcnn else 0.0
+            losses_det["loss_rpn_box_reg"] = losses_det["loss_rpn_box_reg"] * w["det_rpn_box_reg"] if frcnn else 0.0
+            loss_det_total = losses_det["bbox_regression"] + losses_det["classification"] + losses_det["loss_objectness"] + \
+                losses_det["loss_rpn_box_reg"]
+        total = loss_det_total if self.pixel is None else loss_det_total + loss_pixel_rgb + loss_pixel_ir
         return {"total": total, "det_total": loss_det_total, "pixel_rgb": loss_pixel_rgb, "pixel_ir": loss_pixel_ir,
                 "losses_det": losses_det, "hal": hal, "detections": detections}
 
