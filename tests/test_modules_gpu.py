@@ -487,8 +487,12 @@ def test_side_stream_tail_equals_in_order_path():
             runs.append(torch.stack(losses).cpu())
         finally:
             D.EARLY_RPN_TARGETS = D.POSTPROCESS_SIDE_STREAM = True
-    # the first step is identical by construction; later steps also see the (atomics-ordered) gradients of the first
-    assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][0], runs[2][0])
+    # the first step is identical by construction for the two side-stream runs; the in-order run (EARLY_RPN_TARGETS off) takes the
+    # host-synchronised tail, whose PyTorch loss operators add the same per-row terms in another order than the sync-free tail's
+    # single-launch loss kernels (same samples, same detections -- checked below): equal up to fp32 summation order.  Later steps
+    # also see the (atomics-ordered) gradients of the first.
+    assert torch.equal(runs[0][0], runs[2][0])
+    assert torch.allclose(runs[0][0], runs[1][0], rtol=2e-6, atol=1e-8)
     assert torch.allclose(runs[0], runs[1], rtol=2e-2) and torch.allclose(runs[0], runs[2], rtol=2e-2)
     for other in dets[1:]:
         assert len(other) == len(dets[0]) == 4
